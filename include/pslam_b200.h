@@ -1,0 +1,239 @@
+/*
+ * pslam_b200.h -- C ABI of libpslam_b200.so: PUTSLAM's data-parallel front-end hot path
+ * (depth back-projection -> Hamming matching -> RANSAC/Umeyama/Kabsch) on one B200 (sm_100a).
+ *
+ * The reference (LRMPUT/PUTSLAM) has no FFI layer; its seams are C++ virtuals and free functions.
+ * Each entry point below names the reference interface it replaces (file:line relative to the
+ * reference root); adapter/ holds the C++ classes that put these calls behind the reference's own
+ * signatures, INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (PSLAM_OK) or a negative pslam_status; pslam_last_error(ctx) has text.
+ *   - all pointers are HOST pointers owned by the caller unless the name says `_resident`;
+ *     device memory, the CUDA stream and pinned staging live inside pslam_ctx.
+ *   - one pslam_ctx per reference Matcher instance (tracking thread / loop-closure thread); calls on
+ *     one ctx are not re-entrant, separate ctxs are independent.  No global mutable state.
+ *   - there is NO CPU fallback: without a usable sm_100 device pslam_ctx_create fails.
+ *   - descriptors are 32 bytes (ORB / LDB-256, reference src/LDB/ldb.cpp:61,657), rows contiguous.
+ *   - 4x4 transforms are column-major float[16] (Eigen::Matrix4f layout); 3x4 Kabsch results are
+ *     column-major double[12] (Eigen::Transform<double,3,Affine>::matrix().topRows(3) layout).
+ */
+#ifndef PSLAM_B200_H_
+#define PSLAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PSLAM_API __attribute__((visibility("default")))
+#else
+#define PSLAM_API
+#endif
+
+typedef struct pslam_ctx pslam_ctx;
+
+typedef enum {
+    PSLAM_OK = 0,
+    PSLAM_ERR_ARG = -1,          /* null pointer, negative size, unsupported descriptor width ... */
+    PSLAM_ERR_CUDA = -2,         /* a CUDA runtime call failed; see pslam_last_error */
+    PSLAM_ERR_CAPACITY = -3,     /* output truncated: more results than the caller's capacity */
+    PSLAM_ERR_UNSUPPORTED = -4,  /* size beyond a documented kernel limit, or dead reference mode */
+    PSLAM_ERR_NCCL = -5,
+    PSLAM_ERR_NO_DEVICE = -6
+} pslam_status;
+
+#define PSLAM_DESC_BYTES 32
+#define PSLAM_MAX_BF_ROWS 65535      /* pslam_match_bf_mutual / knn2: nq, nt <= 65535 (16-bit packed index) */
+#define PSLAM_LC_MAX_KF_DESC 4096    /* descriptors per keyframe in the loop-closure database */
+#define PSLAM_LC_MAX_QUERY 1024      /* query descriptors per loop-closure sweep */
+#define PSLAM_LC_MAX_TOPK 64
+
+/* ---- context ------------------------------------------------------------------------------ */
+PSLAM_API int pslam_ctx_create(int device, pslam_ctx** out);
+PSLAM_API void pslam_ctx_destroy(pslam_ctx* ctx);
+PSLAM_API const char* pslam_last_error(const pslam_ctx* ctx);
+PSLAM_API int pslam_version(void);
+/* cudaStream_t every kernel of this ctx is launched on (for CUDA-event timing by the caller) */
+PSLAM_API void* pslam_ctx_stream(pslam_ctx* ctx);
+PSLAM_API int pslam_ctx_sync(pslam_ctx* ctx);
+/* number of kernels of this library launched on the ctx since creation */
+PSLAM_API uint64_t pslam_kernel_launches(const pslam_ctx* ctx);
+PSLAM_API int pslam_sm_count(const pslam_ctx* ctx);
+
+/* ---- stage 1: back-projection --------------------------------------------------------------
+ * Replaces RGBD::removeImageDistortion + RGBD::keypoints2Dto3D (include/putslam/RGBD/RGBD.h:38-73,
+ * src/RGBD/RGBD.cpp:30-65,254-314), the detDist loop (src/Matcher/matcher.cpp:51-58) and, when
+ * cov_out != NULL, DepthSensorModel::computeCov (src/Grabber/depthSensorModel.cpp:28-36). */
+typedef struct {
+    float fx, fy, cx, cy;     /* cameraMatrixMat (CV_32F) */
+    float dist[5];            /* distortionCoeffsMat k1 k2 p1 p2 k3 (CV_32F) */
+} pslam_camera;
+
+typedef struct {
+    double fx, fy, cx, cy;       /* DepthSensorModel::Config focalLength / focalAxis */
+    double var_u, var_v;         /* Ruvd(0,0), Ruvd(1,1) */
+    double dist_var_coefs[4];    /* c3 c2 c1 c0 of the depth variance polynomial */
+} pslam_cov_params;
+
+/* uv: n x 2 float keypoints (distorted pixels if undistort != 0). depth: H rows of row_stride uint16.
+ * Outputs (nullable except xyz_out): uv_undist_out n x 2, xyz_out n x 3 float, det_dist_out n double,
+ * cov_out n x 9 double row-major (needs cov != NULL). */
+PSLAM_API int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* depth, int W, int H,
+                                int row_stride, const pslam_camera* cam, int undistort, double depth_scale,
+                                float* uv_undist_out, float* xyz_out, double* det_dist_out, double* cov_out,
+                                const pslam_cov_params* cov);
+
+/* ---- stage 2: Hamming matching --------------------------------------------------------------
+ * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
+ * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==
+ * cv::BFMatcher(NORM_HAMMING, crossCheck=true).match(query=prev, train=cur)): mutual nearest neighbours,
+ * first-argmin ties, ascending queryIdx, imgIdx 0.  Outputs sized min(nq, nt). */
+PSLAM_API int pslam_match_bf_mutual(pslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                    int desc_bytes, int* out_query_idx, int* out_train_idx, float* out_distance,
+                                    int* n_out);
+
+/* knnMatch(k = 2) extension (north_star "ratio test"): out_idx / out_dist are nq x 2, ascending
+ * distance, lowest train index first on ties; -1 where nt < 2.  The caller applies d1 < r*d2. */
+PSLAM_API int pslam_match_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                               int desc_bytes, int* out_idx, float* out_dist);
+
+/* Guided frame-to-map matching: the loop nest of Matcher::matchXYZ (src/Matcher/matcher.cpp:662-748).
+ * map_xyz: M x 3 float (MapFeature.position cast to float, :665), map_level / cur_level: predicted
+ * pyramid levels computed by the caller in double exactly as :639-651 / :682-692.  radius and
+ * accept_ratio are the values after the retry adjustment (:617-622).  distance_mode 0 = the reference's
+ * saturating-subtract popcount (:719-721), 1 = XOR Hamming.  Matches come out in (map j, cur i) order.
+ * n_out receives the full count; if it exceeds cap the first cap are written and PSLAM_ERR_CAPACITY is
+ * returned.  perfect_out (nullable) = features whose best value is 0 (:729-731). */
+PSLAM_API int pslam_match_guided_xyz(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc,
+                                     const int* map_level, int M, const float* cur_xyz, const uint8_t* cur_desc,
+                                     const int* cur_level, int N, int desc_bytes, double radius, double accept_ratio,
+                                     int distance_mode, int* out_query_idx, int* out_train_idx, float* out_distance,
+                                     int cap, int* n_out, int* perfect_out);
+
+/* ---- stage 3: RANSAC + Umeyama, Kabsch ------------------------------------------------------
+ * Mirrors RANSAC::parameters (include/putslam/TransformEst/RANSAC.h:23-31) plus the intrinsics the
+ * reprojection metrics read from cameraMatrix. */
+typedef struct {
+    int error_version;                  /* RANSAC::ERROR_VERSION: 0 EUCLIDEAN, 1 REPROJECTION, 2 EUCLIDEAN_AND_
+                                           REPROJECTION, 4 ADAPTIVE; 3 (MAHALANOBIS) is dead code in the reference
+                                           (RANSAC.cpp:301-303) -> PSLAM_ERR_UNSUPPORTED */
+    double inlier_threshold_euclidean;
+    double inlier_threshold_reprojection;
+    double minimal_inlier_ratio_threshold;
+    int minimal_number_of_matches;
+    int used_pairs;                     /* must be 3 */
+    float fx, fy, cx, cy;
+} pslam_ransac_params;
+
+/* Replaces RANSAC::estimateTransformation (RANSAC.h:44-48, src/TransformEst/RANSAC.cpp:50-174).
+ * prev: n_prev x 3, cur: n_cur x 3 float; match k pairs prev[match_query[k]] with cur[match_train[k]].
+ * Hypothesis i samples 3 matches with Philox4x32-10(key = seed, counter = {block, i, 0, 0}) % m with
+ * rejection (pslam_ransac_sample reproduces the draw on the host).  num_hyp = 0: the reference's
+ * adaptive loop (bound 487, shrinking as better models appear); num_hyp > 0: exactly that many.
+ * T_out: column-major 4x4, prev ~= R*cur + t.  inlier_idx_out (capacity m): indices into the match list,
+ * ascending.  Failure conventions are the reference's: too few matches or best ratio below the
+ * threshold -> identity and zero inliers, return value still PSLAM_OK. */
+PSLAM_API int pslam_ransac_estimate(pslam_ctx* ctx, const float* prev, int n_prev, const float* cur, int n_cur,
+                                    const int* match_query, const int* match_train, int m,
+                                    const pslam_ransac_params* params, uint64_t seed, int num_hyp, float* T_out,
+                                    int* inlier_idx_out, int* n_inliers_out, double* best_ratio_out,
+                                    int* hyp_used_out);
+
+/* Per-hypothesis inlier counts of the last pslam_ransac_estimate / frame call on this ctx
+ * (-1 = degenerate model); for diagnostics and parity tests.  Copies min(cap, hypotheses) ints. */
+PSLAM_API int pslam_ransac_last_counts(pslam_ctx* ctx, int* counts_out, int cap, int* n_out);
+
+/* Host mirror of the device sampler: the 3 match indices hypothesis `hyp` draws out of m matches. */
+PSLAM_API void pslam_ransac_sample(uint64_t seed, uint32_t hyp, int m, int out3[3]);
+
+/* RANSAC::pointInlierRatio (RANSAC.h:56-66): unique trainIdx of inliers / unique trainIdx of all matches. */
+PSLAM_API double pslam_point_inlier_ratio(const int* inlier_train, int n_inliers, const int* all_train, int n_all);
+
+/* Replaces KabschEst::computeTransformation (include/putslam/TransformEst/kabschEst.h:34,
+ * src/TransformEst/kabschEst.cpp:24-68) for a batch of independent point-set pairs.
+ * A, B: concatenated n_i x 3 ROW-major double points; offsets[batch + 1].  T_out: batch x 12, column-major
+ * 3x4 with B ~= R*A + t.  An empty pair yields identity. */
+PSLAM_API int pslam_kabsch_batch(pslam_ctx* ctx, const double* A, const double* B, const int* offsets, int batch,
+                                 double* T_out);
+
+/* ---- fused per-frame pipelines (one submission, no host round trips between stages) ---------
+ * Frame-to-frame VO: Matcher::match (src/Matcher/matcher.cpp:452-516) minus detection/description:
+ * performMatching(prev_desc, cur_desc) -> removeImageDistortion + keypoints2Dto3D on the current frame
+ * -> RANSAC(prev_xyz, cur_xyz, matches). */
+typedef struct {
+    int n_matches;
+    int n_inliers;
+    int hyp_used;
+    int n_filtered;
+    double best_ratio;        /* bestInlierRatio */
+    double inlier_ratio;      /* RANSAC::pointInlierRatio(inliers, matches) -- the value match()/matchXYZ return */
+    float T[16];              /* column-major */
+} pslam_frame_result;
+
+PSLAM_API int pslam_frame_to_frame(pslam_ctx* ctx, const uint8_t* prev_desc, const float* prev_xyz, int n_prev,
+                                   const uint8_t* cur_desc, const float* cur_uv, int n_cur, const uint16_t* depth,
+                                   int W, int H, int row_stride, const pslam_camera* cam, int undistort,
+                                   double depth_scale, const pslam_ransac_params* params, uint64_t seed, int num_hyp,
+                                   float* cur_xyz_out, float* cur_uv_undist_out, double* cur_det_dist_out,
+                                   int* match_query_out, int* match_train_out, float* match_dist_out,
+                                   int* inlier_idx_out, pslam_frame_result* result);
+
+/* Frame-to-map: Matcher::matchXYZ private overload (src/Matcher/matcher.cpp:606-798) minus the
+ * MapFeature marshalling: guided matching -> RANSAC(map_xyz, cur_xyz, matches).  match_cap bounds the
+ * guided matches kept (PSLAM_ERR_CAPACITY if exceeded).  result->inlier_ratio = -1 when no matches (:755). */
+PSLAM_API int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level,
+                                 int M, const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N,
+                                 double radius, double accept_ratio, int distance_mode,
+                                 const pslam_ransac_params* params, uint64_t seed, int num_hyp, int match_cap,
+                                 int* match_query_out, int* match_train_out, float* match_dist_out,
+                                 int* inlier_idx_out, pslam_frame_result* result);
+
+/* Re-run the kernels of the last pslam_frame_to_map call on the inputs already resident in HBM:
+ * no host<->device copies, no synchronisation (device-time measurements; matchXYZ retries). */
+PSLAM_API int pslam_frame_to_map_resident(pslam_ctx* ctx);
+PSLAM_API int pslam_frame_to_frame_resident(pslam_ctx* ctx);
+
+/* ---- loop-closure sweep: query frame vs every keyframe of the map --------------------------
+ * Generalises Matcher::matchFeatureLoopClosure's performMatching step (src/Matcher/matcher.cpp:802-861,
+ * :835) from one FABMAP-proposed pair to all keyframes: score(k) = number of mutual-NN matches between
+ * the query and keyframe k with distance <= tau; result = top-k keyframes, score descending, keyframe id
+ * ascending on ties.  The keyframe descriptors stay resident in HBM. */
+PSLAM_API int pslam_lc_db_reserve(pslam_ctx* ctx, int64_t max_descriptors, int max_keyframes);
+/* append keyframes: desc = sum(counts) x 32 bytes, kf_off[n_kf + 1] descriptor offsets relative to desc */
+PSLAM_API int pslam_lc_db_append(pslam_ctx* ctx, const uint8_t* desc, const int64_t* kf_off, int n_kf);
+PSLAM_API int pslam_lc_db_clear(pslam_ctx* ctx);
+PSLAM_API int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* n_descriptors);
+/* global id of local keyframe 0 (rank r of a sharded map owns ids [base, base + n_keyframes)) */
+PSLAM_API int pslam_lc_set_id_base(pslam_ctx* ctx, int kf_id_base);
+
+/* Single-GPU query.  out_* sized k (<= PSLAM_LC_MAX_TOPK); unused slots -1.  scores_out (nullable):
+ * n_keyframes per-keyframe scores. */
+PSLAM_API int pslam_lc_query(pslam_ctx* ctx, const uint8_t* query, int nq, int tau, int k, int* out_kf_ids,
+                             int* out_scores, int* scores_out);
+/* kernels only, on the query already resident from the last pslam_lc_query / _sharded call */
+PSLAM_API int pslam_lc_query_resident(pslam_ctx* ctx, int tau, int k);
+
+/* Multi-GPU (one process per GPU, keyframes sharded by rank).  The library brings up its own NCCL
+ * communicator from a caller-distributed ncclUniqueId (128 bytes): rank 0 calls pslam_comm_unique_id,
+ * ships the bytes to the other ranks over whatever the host application already has, every rank calls
+ * pslam_comm_init.  pslam_lc_query_sharded: ncclBroadcast of the query descriptors from `root`
+ * (root < 0: every rank already passes the same query), local sweep + local top-k, ncclAllGather of
+ * k {score, id} pairs per rank, merge -> the same global top-k on every rank. */
+PSLAM_API int pslam_comm_unique_id(uint8_t id_out[128]);
+PSLAM_API int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world);
+PSLAM_API int pslam_comm_destroy(pslam_ctx* ctx);
+PSLAM_API int pslam_lc_query_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int tau, int k,
+                                     int* out_kf_ids, int* out_scores);
+PSLAM_API int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k);
+
+/* Per-query-descriptor 2-NN against the whole resident database (SURVEY 8e variant V2):
+ * out_idx: nq x 2 GLOBAL descriptor indices (int64), out_dist: nq x 2 float. */
+PSLAM_API int pslam_lc_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, int64_t* out_idx, float* out_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLAM_B200_H_ */

@@ -1,0 +1,356 @@
+"""ctypes binding of libpslam_b200.so (include/pslam_b200.h) with numpy-facing wrappers.
+
+This is host-side plumbing for the tests and bench.py; the product is the C ABI + adapter/ C++ classes.
+There is no CPU path here: if the shared library is missing or no sm_100 GPU is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpslam_b200.so")
+
+PSLAM_OK = 0
+ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
+
+# every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
+ABI_SYMBOLS = [
+    "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_match_bf_mutual",
+    "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_last_counts",
+    "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
+    "pslam_frame_to_map", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
+    "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
+    "pslam_lc_query_resident", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
+    "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2",
+]
+
+
+class PslamError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pslam error {code}: {msg}")
+        self.code = code
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("dist", C.c_float * 5)]
+
+
+class CovParams(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("var_u", C.c_double), ("var_v", C.c_double), ("dist_var_coefs", C.c_double * 4)]
+
+
+class RansacParams(C.Structure):
+    _fields_ = [("error_version", C.c_int), ("inlier_threshold_euclidean", C.c_double),
+                ("inlier_threshold_reprojection", C.c_double), ("minimal_inlier_ratio_threshold", C.c_double),
+                ("minimal_number_of_matches", C.c_int), ("used_pairs", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class FrameResult(C.Structure):
+    _fields_ = [("n_matches", C.c_int), ("n_inliers", C.c_int), ("hyp_used", C.c_int), ("n_filtered", C.c_int),
+                ("best_ratio", C.c_double), ("inlier_ratio", C.c_double), ("T", C.c_float * 16)]
+
+
+def default_ransac_params(error_version=0):
+    """resources/putslammatcherOpenCVParameters.xml:29-37 defaults + freiburg1 intrinsics."""
+    return RansacParams(error_version, 0.04, 2.0, 0.2, 15, 3, 517.3, 516.5, 318.6, 255.3)
+
+
+def make_camera(fx=517.3, fy=516.5, cx=318.6, cy=255.3, dist=(-0.0410, 0.3286, 0.0087, 0.0051, -0.5643)):
+    return Camera(fx, fy, cx, cy, (C.c_float * 5)(*dist))
+
+
+_lib = None
+
+
+def load_library():
+    """Load libpslam_b200.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PslamError(ERR_NO_DEVICE, f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    lib.pslam_last_error.restype = C.c_char_p
+    lib.pslam_ctx_stream.restype = C.c_void_p
+    lib.pslam_kernel_launches.restype = C.c_uint64
+    lib.pslam_point_inlier_ratio.restype = C.c_double
+    lib.pslam_ctx_destroy.restype = None
+    lib.pslam_ransac_sample.restype = None
+    for name in ("pslam_ctx_destroy", "pslam_last_error", "pslam_ctx_stream", "pslam_ctx_sync",
+                 "pslam_kernel_launches", "pslam_sm_count"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def _arr(a, dt, shape_last=None):
+    if a is None:
+        return np.zeros((0,), dt)
+    a = np.ascontiguousarray(a, dtype=dt)
+    if shape_last is not None and a.size:
+        a = a.reshape(-1, shape_last)
+    return a
+
+
+class Context:
+    """One pslam_ctx (one CUDA stream, one staging arena) -- one per reference Matcher instance."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        r = self.lib.pslam_ctx_create(int(device), C.byref(h))
+        if r != PSLAM_OK:
+            raise PslamError(r, "pslam_ctx_create failed (no usable sm_100 GPU; there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pslam_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, r, allow=()):
+        if r != PSLAM_OK and r not in allow:
+            raise PslamError(r, (self.lib.pslam_last_error(self.h) or b"").decode())
+        return r
+
+    @property
+    def stream(self):
+        return self.lib.pslam_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.pslam_kernel_launches(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.lib.pslam_sm_count(self.h))
+
+    def sync(self):
+        self._ck(self.lib.pslam_ctx_sync(self.h))
+
+    # ---- stage 1 ----
+    def backproject(self, uv, depth, cam=None, undistort=False, depth_scale=5000.0, cov=None):
+        uv = _arr(uv, np.float32, 2)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        n = uv.shape[0] if uv.size else 0
+        cam = cam or make_camera()
+        und = np.empty((n, 2), np.float32); xyz = np.empty((n, 3), np.float32); dd = np.empty(n, np.float64)
+        covo = np.empty((n, 3, 3), np.float64) if cov is not None else None
+        self._ck(self.lib.pslam_backproject(self.h, _p(uv, C.c_float), n, _p(depth, C.c_uint16), W, H, W, C.byref(cam),
+                                            int(bool(undistort)), C.c_double(depth_scale), _p(und, C.c_float),
+                                            _p(xyz, C.c_float), _p(dd, C.c_double), _p(covo, C.c_double),
+                                            C.byref(cov) if cov is not None else None))
+        return dict(xyz=xyz, uv_undist=und, det_dist=dd, cov=covo)
+
+    # ---- stage 2 ----
+    def match_bf_mutual(self, query, train):
+        q = _arr(query, np.uint8); t = _arr(train, np.uint8)
+        nq = q.shape[0] if q.ndim == 2 else 0
+        nt = t.shape[0] if t.ndim == 2 else 0
+        nb = q.shape[1] if q.ndim == 2 else (t.shape[1] if t.ndim == 2 else 32)
+        cap = max(1, min(nq, nt))
+        oq = np.empty(cap, np.int32); ot = np.empty(cap, np.int32); od = np.empty(cap, np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.pslam_match_bf_mutual(self.h, _p(q, C.c_uint8), nq, _p(t, C.c_uint8), nt, nb, _p(oq, C.c_int),
+                                                _p(ot, C.c_int), _p(od, C.c_float), C.byref(n)))
+        return oq[:n.value].copy(), ot[:n.value].copy(), od[:n.value].copy()
+
+    def match_knn2(self, query, train):
+        q = _arr(query, np.uint8); t = _arr(train, np.uint8)
+        nq = q.shape[0]
+        nt = t.shape[0] if t.ndim == 2 else 0
+        idx = np.empty((nq, 2), np.int32); dist = np.empty((nq, 2), np.float32)
+        self._ck(self.lib.pslam_match_knn2(self.h, _p(q, C.c_uint8), nq, _p(t, C.c_uint8), nt, q.shape[1],
+                                           _p(idx, C.c_int), _p(dist, C.c_float)))
+        return idx, dist
+
+    def match_guided_xyz(self, map_xyz, map_desc, map_level, cur_xyz, cur_desc, cur_level, radius, ratio, mode=0,
+                         cap=65536):
+        mx = _arr(map_xyz, np.float32, 3); cx = _arr(cur_xyz, np.float32, 3)
+        md = _arr(map_desc, np.uint8); cd = _arr(cur_desc, np.uint8)
+        ml = _arr(map_level, np.int32); cl = _arr(cur_level, np.int32)
+        M, N = ml.size, cl.size
+        oq = np.empty(cap, np.int32); ot = np.empty(cap, np.int32); od = np.empty(cap, np.float32)
+        n = C.c_int(0); perfect = C.c_int(0)
+        r = self.lib.pslam_match_guided_xyz(self.h, _p(mx, C.c_float), _p(md, C.c_uint8), _p(ml, C.c_int), M,
+                                            _p(cx, C.c_float), _p(cd, C.c_uint8), _p(cl, C.c_int), N, 32,
+                                            C.c_double(radius), C.c_double(ratio), mode, _p(oq, C.c_int),
+                                            _p(ot, C.c_int), _p(od, C.c_float), cap, C.byref(n), C.byref(perfect))
+        self._ck(r, allow=(ERR_CAPACITY,))
+        k = min(n.value, cap)
+        return dict(q=oq[:k].copy(), t=ot[:k].copy(), d=od[:k].copy(), total=n.value, perfect=perfect.value,
+                    truncated=(r == ERR_CAPACITY))
+
+    # ---- stage 3 ----
+    def ransac_estimate(self, prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False):
+        prev = _arr(prev, np.float32, 3); cur = _arr(cur, np.float32, 3)
+        mq = _arr(mq, np.int32); mt = _arr(mt, np.int32)
+        m = mq.size
+        params = params or default_ransac_params()
+        T = np.empty(16, np.float32); inl = np.empty(max(1, m), np.int32)
+        n_inl = C.c_int(0); best = C.c_double(0); used = C.c_int(0)
+        self._ck(self.lib.pslam_ransac_estimate(self.h, _p(prev, C.c_float), prev.shape[0] if prev.size else 0,
+                                                _p(cur, C.c_float), cur.shape[0] if cur.size else 0, _p(mq, C.c_int),
+                                                _p(mt, C.c_int), m, C.byref(params), C.c_uint64(seed), num_hyp,
+                                                _p(T, C.c_float), _p(inl, C.c_int), C.byref(n_inl), C.byref(best),
+                                                C.byref(used)))
+        counts = None
+        if want_counts:
+            cap = max(num_hyp, 487)
+            counts = np.empty(cap, np.int32); n = C.c_int(0)
+            self._ck(self.lib.pslam_ransac_last_counts(self.h, _p(counts, C.c_int), cap, C.byref(n)))
+            counts = counts[:n.value]
+        return dict(T=T.reshape(4, 4).T.copy(), inliers=inl[:n_inl.value].copy(), best_ratio=best.value,
+                    hyp_used=used.value, counts=counts)
+
+    def kabsch_batch(self, A_list, B_list):
+        off = np.zeros(len(A_list) + 1, np.int32)
+        for i, a in enumerate(A_list):
+            off[i + 1] = off[i] + len(a)
+        A = np.concatenate([np.asarray(a, np.float64).reshape(-1, 3) for a in A_list]) if off[-1] else np.zeros((0, 3))
+        B = np.concatenate([np.asarray(b, np.float64).reshape(-1, 3) for b in B_list]) if off[-1] else np.zeros((0, 3))
+        A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+        T = np.empty((len(A_list), 12), np.float64)
+        self._ck(self.lib.pslam_kabsch_batch(self.h, _p(A, C.c_double), _p(B, C.c_double), _p(off, C.c_int),
+                                             len(A_list), _p(T, C.c_double)))
+        return [t.reshape(4, 3).T.copy() for t in T]   # column-major 3x4 -> numpy [3,4]
+
+    # ---- fused pipelines ----
+    def frame_to_frame(self, prev_desc, prev_xyz, cur_desc, cur_uv, depth, cam=None, undistort=False,
+                       depth_scale=5000.0, params=None, seed=0, num_hyp=0):
+        pd = _arr(prev_desc, np.uint8); px = _arr(prev_xyz, np.float32, 3)
+        cd = _arr(cur_desc, np.uint8); uv = _arr(cur_uv, np.float32, 2)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        H, W = depth.shape
+        n_prev = pd.shape[0] if pd.ndim == 2 else 0
+        n_cur = cd.shape[0]
+        cam = cam or make_camera(); params = params or default_ransac_params()
+        cap = max(1, min(n_prev, n_cur))
+        xyz = np.empty((n_cur, 3), np.float32); und = np.empty((n_cur, 2), np.float32); dd = np.empty(n_cur, np.float64)
+        mq = np.empty(cap, np.int32); mt = np.empty(cap, np.int32); md = np.empty(cap, np.float32)
+        inl = np.empty(cap, np.int32)
+        res = FrameResult()
+        self._ck(self.lib.pslam_frame_to_frame(self.h, _p(pd, C.c_uint8), _p(px, C.c_float), n_prev, _p(cd, C.c_uint8),
+                                               _p(uv, C.c_float), n_cur, _p(depth, C.c_uint16), W, H, W, C.byref(cam),
+                                               int(bool(undistort)), C.c_double(depth_scale), C.byref(params),
+                                               C.c_uint64(seed), num_hyp, _p(xyz, C.c_float), _p(und, C.c_float),
+                                               _p(dd, C.c_double), _p(mq, C.c_int), _p(mt, C.c_int), _p(md, C.c_float),
+                                               _p(inl, C.c_int), C.byref(res)))
+        n = res.n_matches
+        return dict(xyz=xyz, uv_undist=und, det_dist=dd, mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(),
+                    inliers=inl[:res.n_inliers].copy(), T=np.array(res.T, np.float32).reshape(4, 4).T.copy(),
+                    best_ratio=res.best_ratio, inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used,
+                    n_filtered=res.n_filtered)
+
+    def frame_to_map(self, map_xyz, map_desc, map_level, cur_xyz, cur_desc, cur_level, radius=0.12, ratio=0.55,
+                     mode=0, params=None, seed=0, num_hyp=0, match_cap=16384):
+        mx = _arr(map_xyz, np.float32, 3); cx = _arr(cur_xyz, np.float32, 3)
+        md_ = _arr(map_desc, np.uint8); cd = _arr(cur_desc, np.uint8)
+        ml = _arr(map_level, np.int32); cl = _arr(cur_level, np.int32)
+        params = params or default_ransac_params()
+        mq = np.empty(match_cap, np.int32); mt = np.empty(match_cap, np.int32); md = np.empty(match_cap, np.float32)
+        inl = np.empty(match_cap, np.int32)
+        res = FrameResult()
+        self._ck(self.lib.pslam_frame_to_map(self.h, _p(mx, C.c_float), _p(md_, C.c_uint8), _p(ml, C.c_int), ml.size,
+                                             _p(cx, C.c_float), _p(cd, C.c_uint8), _p(cl, C.c_int), cl.size,
+                                             C.c_double(radius), C.c_double(ratio), mode, C.byref(params),
+                                             C.c_uint64(seed), num_hyp, match_cap, _p(mq, C.c_int), _p(mt, C.c_int),
+                                             _p(md, C.c_float), _p(inl, C.c_int), C.byref(res)))
+        n = min(res.n_matches, match_cap)
+        return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
+                    T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
+                    inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used, n_filtered=res.n_filtered)
+
+    def frame_to_map_resident(self):
+        self._ck(self.lib.pslam_frame_to_map_resident(self.h))
+
+    def frame_to_frame_resident(self):
+        self._ck(self.lib.pslam_frame_to_frame_resident(self.h))
+
+    # ---- loop-closure database ----
+    def lc_reserve(self, max_desc, max_kf):
+        self._ck(self.lib.pslam_lc_db_reserve(self.h, C.c_int64(max_desc), int(max_kf)))
+
+    def lc_append(self, desc, kf_off):
+        d = _arr(desc, np.uint8); off = _arr(kf_off, np.int64)
+        self._ck(self.lib.pslam_lc_db_append(self.h, _p(d, C.c_uint8), _p(off, C.c_int64), off.size - 1))
+
+    def lc_clear(self):
+        self._ck(self.lib.pslam_lc_db_clear(self.h))
+
+    def lc_size(self):
+        nk = C.c_int(0); nd = C.c_int64(0)
+        self._ck(self.lib.pslam_lc_db_size(self.h, C.byref(nk), C.byref(nd)))
+        return nk.value, nd.value
+
+    def lc_set_id_base(self, base):
+        self._ck(self.lib.pslam_lc_set_id_base(self.h, int(base)))
+
+    def lc_query(self, query, tau=64, k=16, want_scores=False):
+        q = _arr(query, np.uint8)
+        ids = np.empty(k, np.int32); sc = np.empty(k, np.int32)
+        scores = np.empty(max(1, self.lc_size()[0]), np.int32) if want_scores else None
+        self._ck(self.lib.pslam_lc_query(self.h, _p(q, C.c_uint8), q.shape[0], tau, k, _p(ids, C.c_int), _p(sc, C.c_int),
+                                         _p(scores, C.c_int)))
+        if want_scores:
+            return ids, sc, scores[:self.lc_size()[0]]
+        return ids, sc
+
+    def lc_query_resident(self, tau=64, k=16):
+        self._ck(self.lib.pslam_lc_query_resident(self.h, tau, k))
+
+    def comm_init(self, uid_bytes, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid_bytes))
+        self._ck(self.lib.pslam_comm_init(self.h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._ck(self.lib.pslam_comm_destroy(self.h))
+
+    def lc_query_sharded(self, query, root=-1, tau=64, k=16, nq=None):
+        q = _arr(query, np.uint8) if query is not None else None
+        nq = q.shape[0] if q is not None else int(nq)
+        ids = np.empty(k, np.int32); sc = np.empty(k, np.int32)
+        self._ck(self.lib.pslam_lc_query_sharded(self.h, _p(q, C.c_uint8), nq, root, tau, k, _p(ids, C.c_int),
+                                                 _p(sc, C.c_int)))
+        return ids, sc
+
+    def lc_query_sharded_resident(self, tau=64, k=16):
+        self._ck(self.lib.pslam_lc_query_sharded_resident(self.h, tau, k))
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    r = lib.pslam_comm_unique_id(buf)
+    if r != PSLAM_OK:
+        raise PslamError(r, "pslam_comm_unique_id failed (libnccl.so.2 not loadable)")
+    return bytes(buf)
+
+
+def ransac_sample(seed, hyp, m):
+    lib = load_library()
+    out = (C.c_int * 3)()
+    lib.pslam_ransac_sample(C.c_uint64(seed), C.c_uint32(hyp), int(m), out)
+    return np.array(list(out), np.int32)
+
+
+def point_inlier_ratio(inl_t, all_t):
+    lib = load_library()
+    a = _arr(inl_t, np.int32); b = _arr(all_t, np.int32)
+    return lib.pslam_point_inlier_ratio(_p(a, C.c_int), a.size, _p(b, C.c_int), b.size)

@@ -1,0 +1,115 @@
+// backproject.cu -- K1: keypoint undistortion, depth back-projection, detection distance and the
+// per-point sensor covariance.
+//   cv::undistortPoints + re-projection : reference src/RGBD/RGBD.cpp:254-314 (OpenCV model: doubles,
+//                                         5 fixed-point iterations, result cast to float)
+//   RGBD::point2Dto3D / keypoints2Dto3D : reference src/RGBD/RGBD.cpp:30-65 (roundSize :10-16)
+//   detDist                             : reference src/Matcher/matcher.cpp:51-58
+//   DepthSensorModel::computeCov        : reference src/Grabber/depthSensorModel.cpp:28-36
+// One thread per keypoint; the only memory traffic is one 2-byte depth gather per keypoint.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+__device__ __forceinline__ int round_size(double x, int size) {
+    // reference returns `size` (one past the edge) for x > size-1; clamped to size-1 here, see DESIGN.md
+    if (x < 0) x = 0;
+    else if (x > size - 1) x = size - 1;
+    return (int)round(x);
+}
+
+// d^3 with a single rounding of the exact product (what a correctly rounded pow(d, 3.0) returns).
+__device__ __forceinline__ double cube_rn(double d) {
+    const double p = d * d;
+    const double pe = fma(d, d, -p);        // exact error of d*d
+    const double h = p * d;
+    const double he = fma(p, d, -h);        // exact error of p*d
+    return h + (he + pe * d);
+}
+
+__global__ void backproject_kernel(const float* __restrict__ uv, int n, const uint16_t* __restrict__ depth, int W, int H,
+                                   int stride, pslam_camera cam, int undistort, double depth_scale,
+                                   float* __restrict__ uv_und, float* __restrict__ xyz, double* __restrict__ det_dist,
+                                   double* __restrict__ cov, pslam_cov_params cp, int want_cov) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float u2 = uv[2 * i], v2 = uv[2 * i + 1];
+    if (undistort) {
+        const double k1 = cam.dist[0], k2 = cam.dist[1], p1 = cam.dist[2], p2 = cam.dist[3], k3 = cam.dist[4];
+        const double ifx = 1. / (double)cam.fx, ify = 1. / (double)cam.fy;
+        double x = ((double)u2 - (double)cam.cx) * ifx;
+        double y = ((double)v2 - (double)cam.cy) * ify;
+        const double x0 = x, y0 = y;
+#pragma unroll 1
+        for (int it = 0; it < 5; ++it) {
+            const double r2 = x * x + y * y;
+            const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+            const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const float xf = (float)x, yf = (float)y;
+        u2 = xf * cam.fx + cam.cx;
+        v2 = yf * cam.fy + cam.cy;
+    }
+    if (uv_und) { uv_und[2 * i] = u2; uv_und[2 * i + 1] = v2; }
+    const int uR = round_size((double)u2, W), vR = round_size((double)v2, H);
+    const uint16_t dz = depth[(size_t)vR * stride + uR];
+    const float Z = (float)(((double)dz) / depth_scale);
+    const float u = __fdiv_rn(u2 - cam.cx, cam.fx);
+    const float v = __fdiv_rn(v2 - cam.cy, cam.fy);
+    const float X = u * Z, Y = v * Z;
+    xyz[3 * i] = X; xyz[3 * i + 1] = Y; xyz[3 * i + 2] = Z;
+    if (det_dist) {
+        const float s = X * X + Y * Y + Z * Z;     // float products and adds, left to right
+        det_dist[i] = (double)__fsqrt_rn(s);       // std::sqrt(float) overload, then widened
+    }
+    if (want_cov) {
+        // FeaturesMap::addFeatures feeds (u, v, depth) of the undistorted keypoint, u/v truncated to integers
+        const unsigned ui = (unsigned)u2, vi = (unsigned)v2;
+        const double d = (double)Z;
+        const double J00 = d / cp.fx, J02 = ((double)ui / cp.fx) - (cp.cx / cp.fx);
+        const double J11 = d / cp.fy, J12 = ((double)vi / cp.fy) - (cp.cy / cp.fy);
+        const double r0 = cp.var_u, r1 = cp.var_v;
+        const double r2 = cp.dist_var_coefs[0] * cube_rn(d) + cp.dist_var_coefs[1] * (d * d) + cp.dist_var_coefs[2] * d +
+                          cp.dist_var_coefs[3];
+        const double J[9] = {J00, 0.0, J02, 0.0, J11, J12, 0.0, 0.0, 1.0};
+        const double R[3] = {r0, r1, r2};
+        double JR[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double s = J[3 * a + 0] * (b == 0 ? R[0] : 0.0);
+                s = s + J[3 * a + 1] * (b == 1 ? R[1] : 0.0);
+                s = s + J[3 * a + 2] * (b == 2 ? R[2] : 0.0);
+                JR[3 * a + b] = s;
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                double s = JR[3 * a + 0] * J[3 * b + 0];
+                s = s + JR[3 * a + 1] * J[3 * b + 1];
+                s = s + JR[3 * a + 2] * J[3 * b + 2];
+                cov[9 * (size_t)i + 3 * a + b] = s;
+            }
+    }
+}
+
+cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth, int W, int H, int stride,
+                               const pslam_camera& cam, int undistort, double depth_scale, float* d_uv_und,
+                               float* d_xyz, double* d_det_dist, double* d_cov, const pslam_cov_params* cov,
+                               cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    pslam_cov_params cp = {};
+    if (cov) cp = *cov;
+    backproject_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_uv, n, d_depth, W, H, stride, cam, undistort, depth_scale,
+                                                        d_uv_und, d_xyz, d_det_dist, d_cov, cp,
+                                                        (cov && d_cov) ? 1 : 0);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pslam

@@ -1,0 +1,100 @@
+// common.cuh -- shared device helpers for the sm_100a kernels of putslam_b200.
+// Compiled with -fmad=false -prec-div=true -prec-sqrt=true: every float/double operation is a
+// single IEEE-754 rounding, which is what the CPU reference build does (no FMA on baseline x86-64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PSLAM_SM_COUNT_HINT 148
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP).  Descriptor tiles are contiguous runs of
+// 32-byte rows, so the 1-D bulk form is the natural TMA shape: no tensor map needed.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// 256-bit Hamming distance.
+//   Algorithmic definition (cv::norm NORM_HAMMING): sum over 8 words of popc(q ^ t) = 8 XOR + 8 POPC.
+//   POPC issues at a quarter of the LOP3 rate, so the 8 XORed words are first compressed with four
+//   3:2 carry-save adders (2 LOP3 each): weight-1 {s2, x7}, weight-2 {s3}, weight-4 {c3}
+//   => 16 LOP3 + 4 POPC, result identical bit for bit.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// returns the distance already scaled by 65536 and added to `low` (an index < 65536): the packed
+// key (dist << 16 | idx) that a single unsigned min turns into a lowest-index-first argmin.
+__device__ __forceinline__ uint32_t ham256_packed(const uint32_t (&q)[8], const uint4& ta, const uint4& tb,
+                                                  uint32_t low) {
+    uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
+    uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
+    uint32_t s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
+    uint32_t s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
+    uint32_t s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
+    uint32_t s3 = lop3_xor3(c0, c1, c2), c3 = lop3_maj(c0, c1, c2);
+    // weights folded into the 16-bit shift; mad.lo keeps the adds off the LOP3 pipe
+    uint32_t r = low;
+    r = __popc(s2) * 65536u + r;
+    r = __popc(x7) * 65536u + r;
+    r = __popc(s3) * 131072u + r;
+    r = __popc(c3) * 262144u + r;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ham256(const uint32_t (&q)[8], const uint4& ta, const uint4& tb) {
+    return ham256_packed(q, ta, tb, 0u) >> 16;
+}
+
+// saturating-subtract "Hamming" of Matcher::matchXYZ (reference src/Matcher/matcher.cpp:719-721):
+// popcount of per-byte max(a - b, 0).
+__device__ __forceinline__ uint32_t satsub_popc32(uint32_t a, uint32_t b) {
+    return __popc(__vsubus4(a, b));
+}
+
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t warp_add_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }

@@ -1,0 +1,1002 @@
+// ctx.cu -- the C ABI of libpslam_b200.so (include/pslam_b200.h): context, staging, stage entry
+// points, fused per-frame pipelines, the resident loop-closure database and the NCCL glue.
+//
+// Data movement pattern of every host-pointer entry point: caller buffers -> one pinned arena ->
+// ONE cudaMemcpyAsync H2D -> kernels on the ctx stream -> ONE cudaMemcpyAsync D2H of the output arena
+// -> one stream synchronise -> caller buffers.  No CPU implementation of any stage exists in this
+// library: if the device or a launch fails the call returns an error.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "geometry.cuh"
+#include "kernels.h"
+
+using namespace pslam;
+
+namespace {
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off = (off + bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+// NCCL is resolved at run time (dlopen) so that the library has no link-time dependency on it and
+// shares whatever libnccl.so.2 the host process already loaded.
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid*);
+typedef int (*fn_ncclCommInitRank)(void**, int, nccl_uid, int);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef int (*fn_ncclBroadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi {
+    void* handle = nullptr;
+    fn_ncclGetUniqueId GetUniqueId = nullptr;
+    fn_ncclCommInitRank CommInitRank = nullptr;
+    fn_ncclCommDestroy CommDestroy = nullptr;
+    fn_ncclAllGather AllGather = nullptr;
+    fn_ncclBroadcast Broadcast = nullptr;
+    fn_ncclGetErrorString GetErrorString = nullptr;
+    bool ok = false;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    for (const char* n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return &api;
+    api.GetUniqueId = (fn_ncclGetUniqueId)dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (fn_ncclCommInitRank)dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (fn_ncclCommDestroy)dlsym(api.handle, "ncclCommDestroy");
+    api.AllGather = (fn_ncclAllGather)dlsym(api.handle, "ncclAllGather");
+    api.Broadcast = (fn_ncclBroadcast)dlsym(api.handle, "ncclBroadcast");
+    api.GetErrorString = (fn_ncclGetErrorString)dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast;
+    return &api;
+}
+constexpr int kNcclUint8 = 1, kNcclInt32 = 2;
+
+// what a *_resident re-run needs to replay a pipeline on the buffers already in HBM
+struct F2MState {
+    bool valid = false;
+    const float* map_xyz; const uint8_t* map_desc; const int* map_level; int M;
+    const float* cur_xyz; const uint8_t* cur_desc; const int* cur_level; int N;
+    float radius_f; double ratio; int mode; int cap;
+    int* count; int* best; int* gout;
+    RansacDeviceParams rp; RansacWorkspace ws;
+};
+struct F2FState {
+    bool valid = false;
+    const uint8_t* prev_desc; const float* prev_xyz; int n_prev;
+    const uint8_t* cur_desc; const float* cur_uv; int n_cur;
+    const uint16_t* depth; int W, H, stride; pslam_camera cam; int undistort; double scale;
+    float* cur_xyz; float* cur_uv_und; double* det_dist;
+    uint32_t* rowmin; uint32_t* colmin; int* mout; int cap;
+    RansacDeviceParams rp; RansacWorkspace ws;
+};
+
+}  // namespace
+
+struct pslam_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    uint64_t launches = 0;
+    HostBuf h_in, h_out;
+    DevBuf d_in, d_out, d_work;
+    // loop-closure database
+    uint8_t* d_db = nullptr;
+    int64_t db_cap = 0, db_n = 0;
+    int64_t* d_kf_off = nullptr;
+    std::vector<int64_t> h_kf_off;  // host mirror (n_kf + 1)
+    int kf_cap = 0, n_kf = 0, kf_id_base = 0;
+    int* d_scores = nullptr;
+    uint8_t* d_lc_query = nullptr;
+    int lc_nq = 0;
+    int* d_lc_pairs = nullptr;  // local k pairs | gathered world*k pairs | merged k pairs
+    bool lc_configured = false;
+    // NCCL
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    // last RANSAC (for pslam_ransac_last_counts)
+    int* d_last_counts = nullptr;
+    int last_H = 0;
+    F2MState f2m;
+    F2FState f2f;
+};
+
+namespace {
+
+int fail(pslam_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(ctx, PSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_dev(pslam_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return PSLAM_OK;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    CK(cudaMalloc((void**)&b.p, want));
+    b.cap = want;
+    // buffers moved: resident replays no longer point at valid inputs
+    ctx->f2m.valid = false;
+    ctx->f2f.valid = false;
+    return PSLAM_OK;
+}
+int ensure_host(pslam_ctx* ctx, HostBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return PSLAM_OK;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFreeHost(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    CK(cudaMallocHost((void**)&b.p, want));
+    b.cap = want;
+    return PSLAM_OK;
+}
+#define TRY(x)                     \
+    do {                           \
+        int r__ = (x);             \
+        if (r__ != PSLAM_OK) return r__; \
+    } while (0)
+
+float float_at_least(double v) {  // smallest float >= v, so that (double)f < v  <=>  f < result
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t seed, int num_hyp, RansacDeviceParams& o) {
+    if (!p) return fail(ctx, PSLAM_ERR_ARG, "ransac params is NULL");
+    if (p->used_pairs != 3) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "used_pairs must be 3 (got %d)", p->used_pairs);
+    if (p->error_version == 3)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "MAHALANOBIS_ERROR is dead code in the reference (RANSAC.cpp:301-303)");
+    if (p->error_version < 0 || p->error_version > 4) return fail(ctx, PSLAM_ERR_ARG, "bad error_version %d", p->error_version);
+    if (num_hyp < 0 || num_hyp > (1 << 20)) return fail(ctx, PSLAM_ERR_ARG, "num_hyp out of range");
+    o.error_version = p->error_version;
+    o.thr_euclid = p->inlier_threshold_euclidean;
+    o.thr_euclid_f = float_at_least(p->inlier_threshold_euclidean);
+    o.thr_reproj = p->inlier_threshold_reprojection;
+    o.min_inlier_ratio = p->minimal_inlier_ratio_threshold;
+    o.min_matches = p->minimal_number_of_matches;
+    o.fx = p->fx; o.fy = p->fy; o.cx = p->cx; o.cy = p->cy;
+    o.seed_lo = (uint32_t)seed; o.seed_hi = (uint32_t)(seed >> 32);
+    o.num_hyp = num_hyp;
+    return PSLAM_OK;
+}
+
+// carve a RANSAC workspace out of the work arena
+struct RansacLayout {
+    size_t pts, keep, nfil, counts, result;
+    int m_cap, h_cap;
+};
+RansacLayout plan_ransac(Arena& A, int m_cap, int num_hyp) {
+    RansacLayout L;
+    L.m_cap = m_cap > 0 ? m_cap : 1;
+    L.h_cap = num_hyp > 0 ? num_hyp : 487;
+    L.pts = A.take(sizeof(float) * 6 * (size_t)L.m_cap);
+    L.keep = A.take(sizeof(int) * 2 * (size_t)L.m_cap);
+    L.nfil = A.take(sizeof(int) * 4);
+    L.counts = A.take(sizeof(int) * (size_t)L.h_cap);
+    return L;
+}
+RansacWorkspace bind_ransac(const RansacLayout& L, uint8_t* work, int* result) {
+    RansacWorkspace ws;
+    ws.pts = reinterpret_cast<float*>(work + L.pts);
+    ws.keep = reinterpret_cast<int*>(work + L.keep);
+    ws.n_filtered = reinterpret_cast<int*>(work + L.nfil);
+    ws.counts = reinterpret_cast<int*>(work + L.counts);
+    ws.result = result;
+    ws.m_cap = L.m_cap;
+    ws.h_cap = L.h_cap;
+    return ws;
+}
+
+double point_inlier_ratio(const int* inl_t, int n_inl, const int* all_t, int n_all) {
+    int mx = -1;
+    for (int i = 0; i < n_all; ++i) if (all_t[i] > mx) mx = all_t[i];
+    for (int i = 0; i < n_inl; ++i) if (inl_t[i] > mx) mx = inl_t[i];
+    std::vector<uint8_t> seen((size_t)(mx + 1), 0);
+    int a = 0, b = 0;
+    for (int i = 0; i < n_all; ++i) if (!seen[all_t[i]]) { seen[all_t[i]] = 1; ++b; }
+    std::fill(seen.begin(), seen.end(), 0);
+    for (int i = 0; i < n_inl; ++i) if (!seen[inl_t[i]]) { seen[inl_t[i]] = 1; ++a; }
+    return (double)a / (double)b;  // 0/0 -> NaN exactly like the reference's double(0)/double(0)
+}
+
+void unpack_ransac_result(const int* res, float* T_out, int* inl_out, int* n_inl, double* best, int* used, int* nfil) {
+    const int n = res[0];
+    if (n_inl) *n_inl = n;
+    if (used) *used = res[1];
+    if (nfil) *nfil = res[2];
+    if (T_out) memcpy(T_out, res + 4, sizeof(float) * 16);
+    if (best) memcpy(best, res + 20, sizeof(double));
+    if (inl_out && n > 0) memcpy(inl_out, res + 24, sizeof(int) * (size_t)n);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int pslam_version(void) { return 100; }
+
+int pslam_ctx_create(int device, pslam_ctx** out) {
+    if (!out) return PSLAM_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return PSLAM_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return PSLAM_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PSLAM_ERR_CUDA;
+    if (prop.major != 10) return PSLAM_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return PSLAM_ERR_CUDA;
+    pslam_ctx* ctx = new pslam_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return PSLAM_ERR_CUDA;
+    }
+    *out = ctx;
+    return PSLAM_OK;
+}
+
+void pslam_ctx_destroy(pslam_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
+    cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p);
+    cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
+    cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
+    cudaFree(ctx->d_lc_pairs);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pslam_last_error(const pslam_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+void* pslam_ctx_stream(pslam_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t pslam_kernel_launches(const pslam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int pslam_sm_count(const pslam_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int pslam_ctx_sync(pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PSLAM_OK;
+}
+
+void pslam_ransac_sample(uint64_t seed, uint32_t hyp, int m, int out3[3]) {
+    int s[3];
+    sample3((uint32_t)seed, (uint32_t)(seed >> 32), hyp, (uint32_t)m, s);
+    out3[0] = s[0]; out3[1] = s[1]; out3[2] = s[2];
+}
+
+double pslam_point_inlier_ratio(const int* inlier_train, int n_inliers, const int* all_train, int n_all) {
+    return point_inlier_ratio(inlier_train, n_inliers, all_train, n_all);
+}
+
+// ---- stage 1 ----------------------------------------------------------------------------------
+int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* depth, int W, int H, int row_stride,
+                      const pslam_camera* cam, int undistort, double depth_scale, float* uv_undist_out, float* xyz_out,
+                      double* det_dist_out, double* cov_out, const pslam_cov_params* cov) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n < 0 || (n > 0 && (!uv || !xyz_out)) || !depth || !cam || W <= 0 || H <= 0 || row_stride < W)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_backproject: bad argument");
+    if (cov_out && !cov) return fail(ctx, PSLAM_ERR_ARG, "cov_out needs cov params");
+    if (n == 0) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_uv = in.take(sizeof(float) * 2 * (size_t)n);
+    const size_t o_depth = in.take(sizeof(uint16_t) * (size_t)H * row_stride);
+    const size_t o_xyz = out.take(sizeof(float) * 3 * (size_t)n);
+    const size_t o_und = out.take(sizeof(float) * 2 * (size_t)n);
+    const size_t o_dd = out.take(sizeof(double) * (size_t)n);
+    const size_t o_cov = out.take(cov_out ? sizeof(double) * 9 * (size_t)n : 8);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    memcpy(ctx->h_in.p + o_uv, uv, sizeof(float) * 2 * (size_t)n);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_backproject((const float*)(ctx->d_in.p + o_uv), n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H,
+                          row_stride, *cam, undistort, depth_scale, (float*)(ctx->d_out.p + o_und),
+                          (float*)(ctx->d_out.p + o_xyz), (double*)(ctx->d_out.p + o_dd),
+                          cov_out ? (double*)(ctx->d_out.p + o_cov) : nullptr, cov, ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(xyz_out, ctx->h_out.p + o_xyz, sizeof(float) * 3 * (size_t)n);
+    if (uv_undist_out) memcpy(uv_undist_out, ctx->h_out.p + o_und, sizeof(float) * 2 * (size_t)n);
+    if (det_dist_out) memcpy(det_dist_out, ctx->h_out.p + o_dd, sizeof(double) * (size_t)n);
+    if (cov_out) memcpy(cov_out, ctx->h_out.p + o_cov, sizeof(double) * 9 * (size_t)n);
+    return PSLAM_OK;
+}
+
+// ---- stage 2 ----------------------------------------------------------------------------------
+int pslam_match_bf_mutual(pslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int desc_bytes,
+                          int* out_query_idx, int* out_train_idx, float* out_distance, int* n_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || nq < 0 || nt < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_match_bf_mutual: bad argument");
+    *n_out = 0;
+    if (desc_bytes != PSLAM_DESC_BYTES) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "descriptor width %d (only 32)", desc_bytes);
+    if (nq > PSLAM_MAX_BF_ROWS || nt > PSLAM_MAX_BF_ROWS)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "nq/nt above %d: use the loop-closure database API", PSLAM_MAX_BF_ROWS);
+    if (nq == 0 || nt == 0) return PSLAM_OK;  // BFMatcher on an empty set yields no matches
+    if (!query || !train || !out_query_idx || !out_train_idx || !out_distance)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_match_bf_mutual: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = nq < nt ? nq : nt;
+    Arena in, out, work;
+    const size_t o_q = in.take((size_t)nq * 32), o_t = in.take((size_t)nt * 32);
+    const size_t o_out = out.take(sizeof(int) * (1 + 3 * (size_t)cap));
+    const size_t o_row = work.take(sizeof(uint32_t) * (size_t)nq), o_col = work.take(sizeof(uint32_t) * (size_t)nt);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    memcpy(ctx->h_in.p + o_q, query, (size_t)nq * 32);
+    memcpy(ctx->h_in.p + o_t, train, (size_t)nt * 32);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_bf_mutual(ctx->d_in.p + o_q, nq, ctx->d_in.p + o_t, nt, (uint32_t*)(ctx->d_work.p + o_row),
+                        (uint32_t*)(ctx->d_work.p + o_col), (int*)(ctx->d_out.p + o_out), cap, ctx->sm_count,
+                        ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int* r = (const int*)(ctx->h_out.p + o_out);
+    const int n = r[0];
+    memcpy(out_query_idx, r + 1, sizeof(int) * (size_t)n);
+    memcpy(out_train_idx, r + 1 + cap, sizeof(int) * (size_t)n);
+    memcpy(out_distance, r + 1 + 2 * cap, sizeof(float) * (size_t)n);
+    *n_out = n;
+    return PSLAM_OK;
+}
+
+int pslam_match_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int desc_bytes,
+                     int* out_idx, float* out_dist) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (nq < 0 || nt < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_match_knn2: bad argument");
+    if (desc_bytes != PSLAM_DESC_BYTES) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "descriptor width %d (only 32)", desc_bytes);
+    if (nq > PSLAM_MAX_BF_ROWS || nt > PSLAM_MAX_BF_ROWS)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "nq/nt above %d: use pslam_lc_knn2", PSLAM_MAX_BF_ROWS);
+    if (nq == 0) return PSLAM_OK;
+    if (!query || (nt > 0 && !train) || !out_idx || !out_dist) return fail(ctx, PSLAM_ERR_ARG, "pslam_match_knn2: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int parts = nt > 0 ? knn2_parts(nq, nt, ctx->sm_count) : 1;
+    Arena in, out, work;
+    const size_t o_q = in.take((size_t)nq * 32), o_t = in.take((size_t)(nt > 0 ? nt : 1) * 32);
+    const size_t o_idx = out.take(sizeof(int) * 2 * (size_t)nq), o_dist = out.take(sizeof(float) * 2 * (size_t)nq);
+    const size_t o_part = work.take(sizeof(uint2) * (size_t)parts * nq);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    memcpy(ctx->h_in.p + o_q, query, (size_t)nq * 32);
+    if (nt > 0) memcpy(ctx->h_in.p + o_t, train, (size_t)nt * 32);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_knn2(ctx->d_in.p + o_q, nq, ctx->d_in.p + o_t, nt, (uint2*)(ctx->d_work.p + o_part),
+                   (int*)(ctx->d_out.p + o_idx), (float*)(ctx->d_out.p + o_dist), ctx->sm_count, ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_idx, ctx->h_out.p + o_idx, sizeof(int) * 2 * (size_t)nq);
+    memcpy(out_dist, ctx->h_out.p + o_dist, sizeof(float) * 2 * (size_t)nq);
+    return PSLAM_OK;
+}
+
+int pslam_match_guided_xyz(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level, int M,
+                           const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N, int desc_bytes,
+                           double radius, double accept_ratio, int distance_mode, int* out_query_idx,
+                           int* out_train_idx, float* out_distance, int cap, int* n_out, int* perfect_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || M < 0 || N < 0 || cap < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_match_guided_xyz: bad argument");
+    *n_out = 0;
+    if (perfect_out) *perfect_out = 0;
+    if (desc_bytes != PSLAM_DESC_BYTES) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "descriptor width %d (only 32)", desc_bytes);
+    if (distance_mode != 0 && distance_mode != 1) return fail(ctx, PSLAM_ERR_ARG, "distance_mode must be 0 or 1");
+    if (N > 12000) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "N above 12000 current keypoints");
+    if (M == 0 || N == 0) return PSLAM_OK;
+    if (!map_xyz || !map_desc || !map_level || !cur_xyz || !cur_desc || !cur_level || (cap > 0 && (!out_query_idx || !out_train_idx || !out_distance)))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_match_guided_xyz: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int dcap = cap > 0 ? cap : 1;
+    Arena in, out, work;
+    const size_t o_mx = in.take(12 * (size_t)M), o_md = in.take(32 * (size_t)M), o_ml = in.take(4 * (size_t)M);
+    const size_t o_cx = in.take(12 * (size_t)N), o_cd = in.take(32 * (size_t)N), o_cl = in.take(4 * (size_t)N);
+    const size_t o_out = out.take(sizeof(int) * (2 + 3 * (size_t)dcap));
+    const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* h = ctx->h_in.p;
+    memcpy(h + o_mx, map_xyz, 12 * (size_t)M); memcpy(h + o_md, map_desc, 32 * (size_t)M); memcpy(h + o_ml, map_level, 4 * (size_t)M);
+    memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N); memcpy(h + o_cl, cur_level, 4 * (size_t)N);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p;
+    int l = 0;
+    CK(launch_guided_match((const float*)(d + o_mx), d + o_md, (const int*)(d + o_ml), M, (const float*)(d + o_cx),
+                           d + o_cd, (const int*)(d + o_cl), N, float_at_least(radius), accept_ratio, distance_mode,
+                           (int*)(ctx->d_work.p + o_cnt), (int*)(ctx->d_work.p + o_best), (int*)(ctx->d_out.p + o_out),
+                           dcap, ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int* r = (const int*)(ctx->h_out.p + o_out);
+    const int total = r[0];
+    const int n = total < cap ? total : cap;
+    if (n > 0) {
+        memcpy(out_query_idx, r + 2, sizeof(int) * (size_t)n);
+        memcpy(out_train_idx, r + 2 + dcap, sizeof(int) * (size_t)n);
+        memcpy(out_distance, r + 2 + 2 * dcap, sizeof(float) * (size_t)n);
+    }
+    *n_out = total;
+    if (perfect_out) *perfect_out = r[1];
+    if (total > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "guided matching produced %d matches, capacity %d", total, cap);
+    return PSLAM_OK;
+}
+
+// ---- stage 3 ----------------------------------------------------------------------------------
+int pslam_ransac_estimate(pslam_ctx* ctx, const float* prev, int n_prev, const float* cur, int n_cur,
+                          const int* match_query, const int* match_train, int m, const pslam_ransac_params* params,
+                          uint64_t seed, int num_hyp, float* T_out, int* inlier_idx_out, int* n_inliers_out,
+                          double* best_ratio_out, int* hyp_used_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!T_out || !n_inliers_out || n_prev < 0 || n_cur < 0 || m < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_ransac_estimate: bad argument");
+    RansacDeviceParams rp;
+    TRY(make_ransac_params(ctx, params, seed, num_hyp, rp));
+    for (int i = 0; i < 16; ++i) T_out[i] = (i % 5 == 0) ? 1.f : 0.f;
+    *n_inliers_out = 0;
+    if (best_ratio_out) *best_ratio_out = 0.0;
+    if (hyp_used_out) *hyp_used_out = 0;
+    if (m == 0 || m < params->minimal_number_of_matches) return PSLAM_OK;  // RANSAC.cpp:77-80 before any device work
+    if (!prev || !cur || !match_query || !match_train || !inlier_idx_out) return fail(ctx, PSLAM_ERR_ARG, "pslam_ransac_estimate: null buffer");
+    for (int k = 0; k < m; ++k)
+        if (match_query[k] < 0 || match_query[k] >= n_prev || match_train[k] < 0 || match_train[k] >= n_cur)
+            return fail(ctx, PSLAM_ERR_ARG, "match %d indexes outside the point sets", k);
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out, work;
+    const size_t o_p = in.take(12 * (size_t)n_prev), o_c = in.take(12 * (size_t)n_cur);
+    const size_t o_mq = in.take(4 * (size_t)m), o_mt = in.take(4 * (size_t)m);
+    const size_t o_res = out.take(sizeof(int) * ransac_result_ints(m));
+    RansacLayout L = plan_ransac(work, m, num_hyp);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* h = ctx->h_in.p;
+    memcpy(h + o_p, prev, 12 * (size_t)n_prev); memcpy(h + o_c, cur, 12 * (size_t)n_cur);
+    memcpy(h + o_mq, match_query, 4 * (size_t)m); memcpy(h + o_mt, match_train, 4 * (size_t)m);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p;
+    RansacWorkspace ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+    int l = 0;
+    CK(cudaMemsetAsync(ws.counts, 0xff, sizeof(int) * (size_t)ws.h_cap, ctx->stream));
+    CK(launch_ransac((const float*)(d + o_p), (const float*)(d + o_c), (const int*)(d + o_mq), (const int*)(d + o_mt),
+                     nullptr, m, rp, ws, ctx->sm_count, ctx->stream, &l));
+    ctx->launches += l;
+    ctx->d_last_counts = ws.counts;
+    ctx->last_H = ws.h_cap;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unpack_ransac_result((const int*)(ctx->h_out.p + o_res), T_out, inlier_idx_out, n_inliers_out, best_ratio_out,
+                         hyp_used_out, nullptr);
+    return PSLAM_OK;
+}
+
+int pslam_ransac_last_counts(pslam_ctx* ctx, int* counts_out, int cap, int* n_out) {
+    if (!ctx || !counts_out || !n_out) return PSLAM_ERR_ARG;
+    *n_out = 0;
+    if (!ctx->d_last_counts) return fail(ctx, PSLAM_ERR_ARG, "no RANSAC run on this ctx yet");
+    CK(cudaSetDevice(ctx->device));
+    const int n = cap < ctx->last_H ? cap : ctx->last_H;
+    CK(cudaMemcpyAsync(counts_out, ctx->d_last_counts, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return PSLAM_OK;
+}
+
+int pslam_kabsch_batch(pslam_ctx* ctx, const double* A, const double* B, const int* offsets, int batch, double* T_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (batch < 0 || (batch > 0 && (!offsets || !T_out))) return fail(ctx, PSLAM_ERR_ARG, "pslam_kabsch_batch: bad argument");
+    if (batch == 0) return PSLAM_OK;
+    const int total = offsets[batch];
+    if (total < 0 || (total > 0 && (!A || !B))) return fail(ctx, PSLAM_ERR_ARG, "pslam_kabsch_batch: bad point buffers");
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_a = in.take(24 * (size_t)(total > 0 ? total : 1)), o_b = in.take(24 * (size_t)(total > 0 ? total : 1));
+    const size_t o_off = in.take(4 * (size_t)(batch + 1));
+    const size_t o_t = out.take(sizeof(double) * 12 * (size_t)batch);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    uint8_t* h = ctx->h_in.p;
+    if (total > 0) { memcpy(h + o_a, A, 24 * (size_t)total); memcpy(h + o_b, B, 24 * (size_t)total); }
+    memcpy(h + o_off, offsets, 4 * (size_t)(batch + 1));
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_kabsch_batch((const double*)(ctx->d_in.p + o_a), (const double*)(ctx->d_in.p + o_b),
+                           (const int*)(ctx->d_in.p + o_off), batch, (double*)(ctx->d_out.p + o_t), ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // device result is row-major 3x4; the ABI is column-major (Eigen layout)
+    const double* r = (const double*)(ctx->h_out.p + o_t);
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 4; ++j) T_out[12 * (size_t)b + 3 * j + i] = r[12 * (size_t)b + 4 * i + j];
+    return PSLAM_OK;
+}
+
+// ---- fused pipelines ----------------------------------------------------------------------------
+static int enqueue_f2m(pslam_ctx* ctx) {
+    F2MState& s = ctx->f2m;
+    int l = 0;
+    CK(launch_guided_match(s.map_xyz, s.map_desc, s.map_level, s.M, s.cur_xyz, s.cur_desc, s.cur_level, s.N, s.radius_f,
+                           s.ratio, s.mode, s.count, s.best, s.gout, s.cap, ctx->stream, &l));
+    CK(launch_ransac(s.map_xyz, s.cur_xyz, s.gout + 2, s.gout + 2 + s.cap, s.gout, 0, s.rp, s.ws, ctx->sm_count,
+                     ctx->stream, &l));
+    ctx->launches += l;
+    return PSLAM_OK;
+}
+
+int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level, int M,
+                       const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N, double radius,
+                       double accept_ratio, int distance_mode, const pslam_ransac_params* params, uint64_t seed,
+                       int num_hyp, int match_cap, int* match_query_out, int* match_train_out, float* match_dist_out,
+                       int* inlier_idx_out, pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!result || M < 0 || N < 0 || match_cap <= 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map: bad argument");
+    memset(result, 0, sizeof(*result));
+    for (int i = 0; i < 16; ++i) result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    result->inlier_ratio = -1.0;
+    RansacDeviceParams rp;
+    TRY(make_ransac_params(ctx, params, seed, num_hyp, rp));
+    if (distance_mode != 0 && distance_mode != 1) return fail(ctx, PSLAM_ERR_ARG, "distance_mode must be 0 or 1");
+    if (N > 12000) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "N above 12000 current keypoints");
+    if (M == 0 || N == 0) return PSLAM_OK;  // no matches -> -1.0 (matcher.cpp:755)
+    if (!map_xyz || !map_desc || !map_level || !cur_xyz || !cur_desc || !cur_level || !match_query_out ||
+        !match_train_out || !match_dist_out || !inlier_idx_out)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = match_cap;
+    Arena in, out, work;
+    const size_t o_mx = in.take(12 * (size_t)M), o_md = in.take(32 * (size_t)M), o_ml = in.take(4 * (size_t)M);
+    const size_t o_cx = in.take(12 * (size_t)N), o_cd = in.take(32 * (size_t)N), o_cl = in.take(4 * (size_t)N);
+    const size_t o_g = out.take(sizeof(int) * (2 + 3 * (size_t)cap));
+    const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
+    const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
+    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* h = ctx->h_in.p;
+    memcpy(h + o_mx, map_xyz, 12 * (size_t)M); memcpy(h + o_md, map_desc, 32 * (size_t)M); memcpy(h + o_ml, map_level, 4 * (size_t)M);
+    memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N); memcpy(h + o_cl, cur_level, 4 * (size_t)N);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p;
+    F2MState& s = ctx->f2m;
+    s.map_xyz = (const float*)(d + o_mx); s.map_desc = d + o_md; s.map_level = (const int*)(d + o_ml); s.M = M;
+    s.cur_xyz = (const float*)(d + o_cx); s.cur_desc = d + o_cd; s.cur_level = (const int*)(d + o_cl); s.N = N;
+    s.radius_f = float_at_least(radius); s.ratio = accept_ratio; s.mode = distance_mode; s.cap = cap;
+    s.count = (int*)(ctx->d_work.p + o_cnt); s.best = (int*)(ctx->d_work.p + o_best); s.gout = (int*)(ctx->d_out.p + o_g);
+    s.rp = rp; s.ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+    s.valid = true;
+    TRY(enqueue_f2m(ctx));
+    ctx->d_last_counts = s.ws.counts; ctx->last_H = s.ws.h_cap;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int* g = (const int*)(ctx->h_out.p + o_g);
+    const int total = g[0];
+    const int n = total < cap ? total : cap;
+    result->n_matches = total;
+    if (n > 0) {
+        memcpy(match_query_out, g + 2, 4 * (size_t)n);
+        memcpy(match_train_out, g + 2 + cap, 4 * (size_t)n);
+        memcpy(match_dist_out, g + 2 + 2 * cap, 4 * (size_t)n);
+    }
+    if (total > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "guided matching produced %d matches, capacity %d", total, cap);
+    if (total == 0) return PSLAM_OK;
+    unpack_ransac_result((const int*)(ctx->h_out.p + o_res), result->T, inlier_idx_out, &result->n_inliers,
+                         &result->best_ratio, &result->hyp_used, &result->n_filtered);
+    std::vector<int> inl_t((size_t)result->n_inliers);
+    for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
+    result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
+    return PSLAM_OK;
+}
+
+int pslam_frame_to_map_resident(pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!ctx->f2m.valid) return fail(ctx, PSLAM_ERR_ARG, "no resident frame-to-map inputs");
+    CK(cudaSetDevice(ctx->device));
+    return enqueue_f2m(ctx);
+}
+
+static int enqueue_f2f(pslam_ctx* ctx) {
+    F2FState& s = ctx->f2f;
+    int l = 0;
+    CK(launch_bf_mutual(s.prev_desc, s.n_prev, s.cur_desc, s.n_cur, s.rowmin, s.colmin, s.mout, s.cap, ctx->sm_count,
+                        ctx->stream, &l));
+    CK(launch_backproject(s.cur_uv, s.n_cur, s.depth, s.W, s.H, s.stride, s.cam, s.undistort, s.scale, s.cur_uv_und,
+                          s.cur_xyz, s.det_dist, nullptr, nullptr, ctx->stream, &l));
+    CK(launch_ransac(s.prev_xyz, s.cur_xyz, s.mout + 1, s.mout + 1 + s.cap, s.mout, 0, s.rp, s.ws, ctx->sm_count,
+                     ctx->stream, &l));
+    ctx->launches += l;
+    return PSLAM_OK;
+}
+
+int pslam_frame_to_frame(pslam_ctx* ctx, const uint8_t* prev_desc, const float* prev_xyz, int n_prev,
+                         const uint8_t* cur_desc, const float* cur_uv, int n_cur, const uint16_t* depth, int W, int H,
+                         int row_stride, const pslam_camera* cam, int undistort, double depth_scale,
+                         const pslam_ransac_params* params, uint64_t seed, int num_hyp, float* cur_xyz_out,
+                         float* cur_uv_undist_out, double* cur_det_dist_out, int* match_query_out, int* match_train_out,
+                         float* match_dist_out, int* inlier_idx_out, pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!result || n_prev < 0 || n_cur < 0 || !cam || !depth || W <= 0 || H <= 0 || row_stride < W)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_frame: bad argument");
+    memset(result, 0, sizeof(*result));
+    for (int i = 0; i < 16; ++i) result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    RansacDeviceParams rp;
+    TRY(make_ransac_params(ctx, params, seed, num_hyp, rp));
+    if (n_prev > PSLAM_MAX_BF_ROWS || n_cur > PSLAM_MAX_BF_ROWS) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "more than %d keypoints", PSLAM_MAX_BF_ROWS);
+    if (n_cur == 0) return PSLAM_OK;
+    if (!cur_desc || !cur_uv || !cur_xyz_out || (n_prev > 0 && (!prev_desc || !prev_xyz)) || !match_query_out ||
+        !match_train_out || !match_dist_out || !inlier_idx_out)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_frame: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int np = n_prev > 0 ? n_prev : 1;
+    const int cap = (n_prev < n_cur ? n_prev : n_cur) > 0 ? (n_prev < n_cur ? n_prev : n_cur) : 1;
+    Arena in, out, work;
+    const size_t o_pd = in.take(32 * (size_t)np), o_px = in.take(12 * (size_t)np);
+    const size_t o_cd = in.take(32 * (size_t)n_cur), o_uv = in.take(8 * (size_t)n_cur);
+    const size_t o_depth = in.take(sizeof(uint16_t) * (size_t)H * row_stride);
+    const size_t o_xyz = out.take(12 * (size_t)n_cur), o_und = out.take(8 * (size_t)n_cur), o_dd = out.take(8 * (size_t)n_cur);
+    const size_t o_m = out.take(sizeof(int) * (1 + 3 * (size_t)cap));
+    const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
+    const size_t o_row = work.take(4 * (size_t)np), o_col = work.take(4 * (size_t)n_cur);
+    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* h = ctx->h_in.p;
+    if (n_prev > 0) { memcpy(h + o_pd, prev_desc, 32 * (size_t)n_prev); memcpy(h + o_px, prev_xyz, 12 * (size_t)n_prev); }
+    memcpy(h + o_cd, cur_desc, 32 * (size_t)n_cur); memcpy(h + o_uv, cur_uv, 8 * (size_t)n_cur);
+    memcpy(h + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p;
+    F2FState& s = ctx->f2f;
+    s.prev_desc = d + o_pd; s.prev_xyz = (const float*)(d + o_px); s.n_prev = n_prev;
+    s.cur_desc = d + o_cd; s.cur_uv = (const float*)(d + o_uv); s.n_cur = n_cur;
+    s.depth = (const uint16_t*)(d + o_depth); s.W = W; s.H = H; s.stride = row_stride; s.cam = *cam;
+    s.undistort = undistort; s.scale = depth_scale;
+    s.cur_xyz = (float*)(ctx->d_out.p + o_xyz); s.cur_uv_und = (float*)(ctx->d_out.p + o_und);
+    s.det_dist = (double*)(ctx->d_out.p + o_dd);
+    s.rowmin = (uint32_t*)(ctx->d_work.p + o_row); s.colmin = (uint32_t*)(ctx->d_work.p + o_col);
+    s.mout = (int*)(ctx->d_out.p + o_m); s.cap = cap;
+    s.rp = rp; s.ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+    s.valid = n_prev > 0;
+    if (n_prev > 0) {
+        TRY(enqueue_f2f(ctx));
+        ctx->d_last_counts = s.ws.counts; ctx->last_H = s.ws.h_cap;
+    } else {  // first frame: back-projection only (Matcher::detectInitFeatures, matcher.cpp:37-58)
+        int l = 0;
+        CK(cudaMemsetAsync(s.mout, 0, sizeof(int), ctx->stream));
+        CK(launch_backproject(s.cur_uv, n_cur, s.depth, W, H, row_stride, *cam, undistort, depth_scale, s.cur_uv_und,
+                              s.cur_xyz, s.det_dist, nullptr, nullptr, ctx->stream, &l));
+        ctx->launches += l;
+    }
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(cur_xyz_out, ctx->h_out.p + o_xyz, 12 * (size_t)n_cur);
+    if (cur_uv_undist_out) memcpy(cur_uv_undist_out, ctx->h_out.p + o_und, 8 * (size_t)n_cur);
+    if (cur_det_dist_out) memcpy(cur_det_dist_out, ctx->h_out.p + o_dd, 8 * (size_t)n_cur);
+    const int* mo = (const int*)(ctx->h_out.p + o_m);
+    const int n = mo[0];
+    result->n_matches = n;
+    if (n > 0) {
+        memcpy(match_query_out, mo + 1, 4 * (size_t)n);
+        memcpy(match_train_out, mo + 1 + cap, 4 * (size_t)n);
+        memcpy(match_dist_out, mo + 1 + 2 * cap, 4 * (size_t)n);
+    }
+    if (n_prev == 0) return PSLAM_OK;
+    unpack_ransac_result((const int*)(ctx->h_out.p + o_res), result->T, inlier_idx_out, &result->n_inliers,
+                         &result->best_ratio, &result->hyp_used, &result->n_filtered);
+    std::vector<int> inl_t((size_t)result->n_inliers);
+    for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
+    result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
+    return PSLAM_OK;
+}
+
+int pslam_frame_to_frame_resident(pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!ctx->f2f.valid) return fail(ctx, PSLAM_ERR_ARG, "no resident frame-to-frame inputs");
+    CK(cudaSetDevice(ctx->device));
+    return enqueue_f2f(ctx);
+}
+
+// ---- loop-closure database ----------------------------------------------------------------------
+int pslam_lc_db_reserve(pslam_ctx* ctx, int64_t max_descriptors, int max_keyframes) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (max_descriptors < 0 || max_keyframes < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_db_reserve: negative size");
+    CK(cudaSetDevice(ctx->device));
+    if (max_descriptors > ctx->db_cap) {
+        uint8_t* nd = nullptr;
+        CK(cudaMalloc((void**)&nd, (size_t)max_descriptors * 32));
+        if (ctx->d_db) {
+            CK(cudaMemcpyAsync(nd, ctx->d_db, (size_t)ctx->db_n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->d_db));
+        }
+        ctx->d_db = nd;
+        ctx->db_cap = max_descriptors;
+    }
+    if (max_keyframes > ctx->kf_cap) {
+        int64_t* no = nullptr;
+        int* ns = nullptr;
+        CK(cudaMalloc((void**)&no, sizeof(int64_t) * ((size_t)max_keyframes + 1)));
+        CK(cudaMalloc((void**)&ns, sizeof(int) * ((size_t)max_keyframes + 1)));
+        if (ctx->d_kf_off) {
+            CK(cudaMemcpyAsync(no, ctx->d_kf_off, sizeof(int64_t) * ((size_t)ctx->n_kf + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->d_kf_off));
+            CK(cudaFree(ctx->d_scores));
+        }
+        ctx->d_kf_off = no;
+        ctx->d_scores = ns;
+        ctx->kf_cap = max_keyframes;
+    }
+    if (ctx->h_kf_off.empty()) ctx->h_kf_off.push_back(0);
+    return PSLAM_OK;
+}
+
+int pslam_lc_db_append(pslam_ctx* ctx, const uint8_t* desc, const int64_t* kf_off, int n_kf) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n_kf < 0 || (n_kf > 0 && !kf_off)) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_db_append: bad argument");
+    if (n_kf == 0) return PSLAM_OK;
+    const int64_t nd = kf_off[n_kf] - kf_off[0];
+    if (nd < 0 || (nd > 0 && !desc)) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_db_append: bad offsets");
+    for (int k = 0; k < n_kf; ++k) {
+        const int64_t c = kf_off[k + 1] - kf_off[k];
+        if (c < 0) return fail(ctx, PSLAM_ERR_ARG, "keyframe offsets must be non-decreasing");
+        if (c > PSLAM_LC_MAX_KF_DESC) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "keyframe with %lld descriptors (max %d)", (long long)c, PSLAM_LC_MAX_KF_DESC);
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->h_kf_off.empty()) ctx->h_kf_off.push_back(0);
+    if (ctx->db_n + nd > ctx->db_cap || ctx->n_kf + n_kf > ctx->kf_cap) {
+        int64_t want_d = ctx->db_n + nd, want_k = (int64_t)ctx->n_kf + n_kf;
+        if (want_d < 2 * ctx->db_cap) want_d = 2 * ctx->db_cap;
+        if (want_k < 2 * (int64_t)ctx->kf_cap) want_k = 2 * (int64_t)ctx->kf_cap;
+        TRY(pslam_lc_db_reserve(ctx, want_d, (int)want_k));
+    }
+    // descriptors go straight from the caller's buffer (chunked through the pinned arena)
+    const size_t chunk = (size_t)8 << 20;
+    TRY(ensure_host(ctx, ctx->h_in, nd > 0 ? (chunk < (size_t)nd * 32 ? chunk : (size_t)nd * 32) : 64));
+    const uint8_t* src = desc + (size_t)kf_off[0] * 32;
+    for (size_t done = 0; done < (size_t)nd * 32; done += chunk) {
+        const size_t b = ((size_t)nd * 32 - done) < chunk ? ((size_t)nd * 32 - done) : chunk;
+        memcpy(ctx->h_in.p, src + done, b);
+        CK(cudaMemcpyAsync(ctx->d_db + (size_t)ctx->db_n * 32 + done, ctx->h_in.p, b, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int64_t base = ctx->db_n - kf_off[0];
+    for (int k = 1; k <= n_kf; ++k) ctx->h_kf_off.push_back(kf_off[k] + base);
+    CK(cudaMemcpyAsync(ctx->d_kf_off + ctx->n_kf, ctx->h_kf_off.data() + ctx->n_kf, sizeof(int64_t) * ((size_t)n_kf + 1),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->db_n += nd;
+    ctx->n_kf += n_kf;
+    return PSLAM_OK;
+}
+
+int pslam_lc_db_clear(pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    ctx->db_n = 0;
+    ctx->n_kf = 0;
+    ctx->h_kf_off.assign(1, 0);
+    return PSLAM_OK;
+}
+
+int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* n_descriptors) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n_keyframes) *n_keyframes = ctx->n_kf;
+    if (n_descriptors) *n_descriptors = ctx->db_n;
+    return PSLAM_OK;
+}
+
+int pslam_lc_set_id_base(pslam_ctx* ctx, int kf_id_base) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    ctx->kf_id_base = kf_id_base;
+    return PSLAM_OK;
+}
+
+static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
+    if (nq <= 0 || nq > PSLAM_LC_MAX_QUERY) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "query size %d outside 1..%d", nq, PSLAM_LC_MAX_QUERY);
+    if (k <= 0 || k > PSLAM_LC_MAX_TOPK) return fail(ctx, PSLAM_ERR_ARG, "k outside 1..%d", PSLAM_LC_MAX_TOPK);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->lc_configured) {
+        CK(lc_sweep_configure());
+        CK(cudaMalloc((void**)&ctx->d_lc_query, (size_t)PSLAM_LC_MAX_QUERY * 32));
+        CK(cudaMalloc((void**)&ctx->d_lc_pairs, sizeof(int) * 2 * PSLAM_LC_MAX_TOPK * (2 + 64)));
+        ctx->lc_configured = true;
+    }
+    if (!ctx->d_scores) TRY(pslam_lc_db_reserve(ctx, 1, 1));
+    if (query) {
+        TRY(ensure_host(ctx, ctx->h_in, (size_t)nq * 32));
+        memcpy(ctx->h_in.p, query, (size_t)nq * 32);
+        CK(cudaMemcpyAsync(ctx->d_lc_query, ctx->h_in.p, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->lc_nq = nq;
+    return PSLAM_OK;
+}
+
+static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
+    int l = 0;
+    CK(launch_lc_sweep(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, ctx->n_kf, tau, ctx->d_scores,
+                       ctx->sm_count, ctx->stream, &l));
+    CK(launch_lc_topk(ctx->d_scores, ctx->n_kf, ctx->kf_id_base, k, ctx->d_lc_pairs, ctx->stream, &l));
+    ctx->launches += l;
+    return PSLAM_OK;
+}
+
+static void unpack_pairs(const int* pairs, int k, int* ids, int* scores) {
+    for (int i = 0; i < k; ++i) {
+        scores[i] = pairs[2 * i];
+        ids[i] = pairs[2 * i + 1];
+    }
+}
+
+int pslam_lc_query(pslam_ctx* ctx, const uint8_t* query, int nq, int tau, int k, int* out_kf_ids, int* out_scores,
+                   int* scores_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!query || !out_kf_ids || !out_scores) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_query: null buffer");
+    TRY(lc_prepare(ctx, query, nq, k));
+    TRY(lc_enqueue_local(ctx, tau, k));
+    const size_t need = sizeof(int) * (2 * (size_t)k + (scores_out ? (size_t)ctx->n_kf : 0));
+    TRY(ensure_host(ctx, ctx->h_out, need));
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_lc_pairs, sizeof(int) * 2 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores_out && ctx->n_kf > 0)
+        CK(cudaMemcpyAsync(ctx->h_out.p + sizeof(int) * 2 * (size_t)k, ctx->d_scores, sizeof(int) * (size_t)ctx->n_kf,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unpack_pairs((const int*)ctx->h_out.p, k, out_kf_ids, out_scores);
+    if (scores_out && ctx->n_kf > 0) memcpy(scores_out, ctx->h_out.p + sizeof(int) * 2 * (size_t)k, sizeof(int) * (size_t)ctx->n_kf);
+    return PSLAM_OK;
+}
+
+int pslam_lc_query_resident(pslam_ctx* ctx, int tau, int k) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->lc_nq <= 0 || !ctx->lc_configured) return fail(ctx, PSLAM_ERR_ARG, "no resident query");
+    if (k <= 0 || k > PSLAM_LC_MAX_TOPK) return fail(ctx, PSLAM_ERR_ARG, "k outside 1..%d", PSLAM_LC_MAX_TOPK);
+    CK(cudaSetDevice(ctx->device));
+    return lc_enqueue_local(ctx, tau, k);
+}
+
+// ---- NCCL ----------------------------------------------------------------------------------------
+int pslam_comm_unique_id(uint8_t id_out[128]) {
+    NcclApi* api = nccl_api();
+    if (!api->ok || !id_out) return PSLAM_ERR_NCCL;
+    nccl_uid uid;
+    if (api->GetUniqueId(&uid) != 0) return PSLAM_ERR_NCCL;
+    memcpy(id_out, uid.internal, 128);
+    return PSLAM_OK;
+}
+
+int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!id || world < 1 || rank < 0 || rank >= world || world > 64) return fail(ctx, PSLAM_ERR_ARG, "pslam_comm_init: bad argument");
+    NcclApi* api = nccl_api();
+    if (!api->ok) return fail(ctx, PSLAM_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) { api->CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    nccl_uid uid;
+    memcpy(uid.internal, id, 128);
+    const int r = api->CommInitRank(&ctx->comm, world, uid, rank);
+    if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
+    ctx->rank = rank;
+    ctx->world = world;
+    return PSLAM_OK;
+}
+
+int pslam_comm_destroy(pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->comm && nccl_api()->ok) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api()->CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return PSLAM_OK;
+}
+
+static int lc_enqueue_sharded(pslam_ctx* ctx, int root, int tau, int k) {
+    NcclApi* api = nccl_api();
+    if (ctx->world > 1 && root >= 0) {
+        const int r = api->Broadcast(ctx->d_lc_query, ctx->d_lc_query, (size_t)ctx->lc_nq * 32, kNcclUint8, root, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
+    }
+    TRY(lc_enqueue_local(ctx, tau, k));
+    if (ctx->world > 1) {
+        int* local = ctx->d_lc_pairs;
+        int* gathered = ctx->d_lc_pairs + 2 * PSLAM_LC_MAX_TOPK;
+        int* merged = gathered + 2 * PSLAM_LC_MAX_TOPK * 64;
+        const int r = api->AllGather(local, gathered, 2 * (size_t)k, kNcclInt32, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclAllGather: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
+        int l = 0;
+        CK(launch_lc_merge_topk(gathered, ctx->world * k, k, merged, ctx->stream, &l));
+        ctx->launches += l;
+    }
+    return PSLAM_OK;
+}
+
+int pslam_lc_query_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int tau, int k, int* out_kf_ids,
+                           int* out_scores) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!out_kf_ids || !out_scores) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_query_sharded: null buffer");
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, PSLAM_ERR_NCCL, "communicator not initialised");
+    if (ctx->world * k > 1024) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "world*k above 1024");
+    const bool have_query = (root < 0) || (root == ctx->rank) || ctx->world == 1;
+    if (have_query && !query) return fail(ctx, PSLAM_ERR_ARG, "query is NULL on a rank that must supply it");
+    TRY(lc_prepare(ctx, have_query ? query : nullptr, nq, k));
+    TRY(lc_enqueue_sharded(ctx, root, tau, k));
+    const int* src = ctx->world > 1 ? ctx->d_lc_pairs + 2 * PSLAM_LC_MAX_TOPK + 2 * PSLAM_LC_MAX_TOPK * 64 : ctx->d_lc_pairs;
+    TRY(ensure_host(ctx, ctx->h_out, sizeof(int) * 2 * (size_t)k));
+    CK(cudaMemcpyAsync(ctx->h_out.p, src, sizeof(int) * 2 * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unpack_pairs((const int*)ctx->h_out.p, k, out_kf_ids, out_scores);
+    return PSLAM_OK;
+}
+
+int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->lc_nq <= 0 || !ctx->lc_configured) return fail(ctx, PSLAM_ERR_ARG, "no resident query");
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, PSLAM_ERR_NCCL, "communicator not initialised");
+    CK(cudaSetDevice(ctx->device));
+    return lc_enqueue_sharded(ctx, -1, tau, k);
+}
+
+int pslam_lc_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, int64_t* out_idx, float* out_dist) {
+    (void)query; (void)nq; (void)out_idx; (void)out_dist;
+    return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_lc_knn2 is not built yet");
+}
+
+}  // extern "C"

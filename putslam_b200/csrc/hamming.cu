@@ -1,0 +1,525 @@
+// hamming.cu -- brute-force Hamming matching kernels (sm_100a).
+//
+//   K2  bf_tile_kernel + bf_finalize_kernel : cv::BFMatcher(NORM_HAMMING, crossCheck=true).match
+//        (reference src/Matcher/matcherOpenCV.cpp:97-106,198-206; semantics SURVEY A.2)
+//   K2' knn2_tile_kernel + knn2_merge_kernel : knnMatch(k=2) extension (north_star ratio test)
+//   K7  lc_sweep_kernel + lc_topk_kernel     : query frame vs every keyframe of the resident map DB,
+//        per-keyframe mutual-NN count with distance <= tau, local top-k
+//        (generalises Matcher::matchFeatureLoopClosure, reference src/Matcher/matcher.cpp:802-861)
+//
+// Common shape: a thread owns RQ query descriptors in registers (8 words each); train descriptors
+// are staged global->shared with TMA bulk copies and read back as warp-broadcast LDS.128; distance =
+// CSA-compressed popcount (common.cuh); argmin = unsigned min over (dist << 16 | index), which
+// resolves ties to the lowest index exactly like OpenCV's first-argmin.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTT = 128;  // train descriptors per column-reduce sub-tile
+
+// Per-thread query registers.  Query q = qtile_base + j*kThreads + tid; rows beyond nq get an offset
+// that can never win a column minimum.
+template <int RQ>
+struct QueryRegs {
+    uint32_t v[RQ][8];
+    uint32_t off[RQ];  // (q index) for valid queries, 0x40000000|q for padding
+    __device__ __forceinline__ void load(const uint4* __restrict__ query, int nq, int qbase, int tid) {
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) {
+            int q = qbase + j * kThreads + tid;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (q < nq) {
+                a = __ldg(query + 2 * (size_t)q);
+                b = __ldg(query + 2 * (size_t)q + 1);
+            }
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+            v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+            off[j] = (q < nq) ? (uint32_t)(q - qbase) : (0x40000000u | (uint32_t)(q - qbase));
+        }
+    }
+};
+
+// One sub-tile: cnt (<= kTT) train descriptors in shared memory vs this thread's RQ queries.
+// rowmin[j]  : running (dist<<16 | train index) for query j
+// partial_w  : this warp's per-train (dist<<16 | query offset) minima, one word per train
+template <int RQ>
+__device__ __forceinline__ void tile_compute(const QueryRegs<RQ>& Q, uint32_t (&rowmin)[RQ],
+                                             const uint4* __restrict__ tile, int cnt, uint32_t tbase,
+                                             uint32_t* __restrict__ partial_w, int lane) {
+#pragma unroll 2
+    for (int tt = 0; tt < cnt; ++tt) {
+        const uint4 a = tile[2 * tt], b = tile[2 * tt + 1];
+        const uint32_t tcur = tbase + (uint32_t)tt;
+        uint32_t cmin = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) {
+            uint32_t rp = ham256_packed(Q.v[j], a, b, tcur);
+            rowmin[j] = min(rowmin[j], rp);
+            cmin = min(cmin, rp + (Q.off[j] - tcur));
+        }
+        cmin = warp_min_u32(cmin);
+        if (lane == 0) partial_w[tt] = cmin;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: one query set vs one train set, spread over the grid by train range (x) and query tile (y).
+// ------------------------------------------------------------------------------------------------
+template <int RQ>
+__global__ void __launch_bounds__(kThreads, 2)
+bf_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt, int t_per_cta,
+               uint32_t* __restrict__ rowmin_g, uint32_t* __restrict__ colmin_g) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4* tile = reinterpret_cast<uint4*>(smem_raw);                                   // t_per_cta * 32 B
+    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + (size_t)t_per_cta * 32);  // kWarps * kTT
+    uint64_t* bar = reinterpret_cast<uint64_t*>(partial + kWarps * kTT);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = blockIdx.x * t_per_cta;
+    const int tcnt = min(t_per_cta, nt - t0);
+    const int qbase = blockIdx.y * (kThreads * RQ);
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (uint32_t)tcnt * 32u);
+        tma_load_1d(tile, train + 2 * (size_t)t0, (uint32_t)tcnt * 32u, bar);
+    }
+    QueryRegs<RQ> Q;
+    Q.load(query, nq, qbase, tid);
+    uint32_t rowmin[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
+    __syncthreads();  // barrier init visible
+    mbar_wait(bar, 0);
+
+    for (int s = 0; s < tcnt; s += kTT) {
+        const int cnt = min(kTT, tcnt - s);
+        tile_compute<RQ>(Q, rowmin, tile + 2 * s, cnt, (uint32_t)(t0 + s), partial + warp * kTT, lane);
+        __syncthreads();
+        if (tid < cnt) {
+            uint32_t m = partial[tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) m = min(m, partial[w * kTT + tid]);
+            if (m < 0x40000000u) {  // a real query won this column
+                m += (uint32_t)qbase;  // query offset -> global query index (low 16 bits)
+                if (gridDim.y == 1) colmin_g[t0 + s + tid] = m;
+                else atomicMin(colmin_g + t0 + s + tid, m);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) {
+        int q = qbase + j * kThreads + tid;
+        if (q < nq) atomicMin(rowmin_g + q, rowmin[j]);
+    }
+}
+
+// Cross-check + ordered compaction (single CTA).  out layout: [0] = n, then q[cap], t[cap], dist[cap].
+__global__ void __launch_bounds__(1024, 1)
+bf_finalize_kernel(const uint32_t* __restrict__ rowmin_g, const uint32_t* __restrict__ colmin_g, int nq, int cap,
+                   int* __restrict__ out) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    int* oq = out + 1;
+    int* ot = out + 1 + cap;
+    float* od = reinterpret_cast<float*>(out + 1 + 2 * cap);
+    for (int base = 0; base < nq; base += 1024) {
+        const int q = base + tid;
+        bool keep = false;
+        uint32_t rp = 0;
+        if (q < nq) {
+            rp = rowmin_g[q];
+            const uint32_t t = rp & 0xffffu;
+            keep = (rp != 0xffffffffu) && ((colmin_g[t] & 0xffffu) == (uint32_t)q);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        const int wpre = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c = warp_tot[w];
+            if (w < warp) woff += c;
+            tot += c;
+        }
+        const int pos = carry + woff + wpre;
+        if (keep && pos < cap) {
+            oq[pos] = q;
+            ot[pos] = (int)(rp & 0xffffu);
+            od[pos] = (float)(rp >> 16);
+        }
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) out[0] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2': two nearest neighbours per query (ascending distance, lowest train index first on ties).
+// Each CTA handles one train range; per-range top-2 go to a partial buffer and are merged per query.
+// ------------------------------------------------------------------------------------------------
+template <int RQ>
+__global__ void __launch_bounds__(kThreads, 2)
+knn2_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt, int t_per_cta,
+                 uint2* __restrict__ partial_g /* [gridDim.x][nq] */) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4* tile = reinterpret_cast<uint4*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)t_per_cta * 32);
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * t_per_cta;
+    const int tcnt = min(t_per_cta, nt - t0);
+    const int qbase = blockIdx.y * (kThreads * RQ);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (uint32_t)tcnt * 32u);
+        tma_load_1d(tile, train + 2 * (size_t)t0, (uint32_t)tcnt * 32u, bar);
+    }
+    QueryRegs<RQ> Q;
+    Q.load(query, nq, qbase, tid);
+    uint32_t m1[RQ], m2[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) m1[j] = m2[j] = 0xffffffffu;
+    __syncthreads();
+    mbar_wait(bar, 0);
+#pragma unroll 2
+    for (int tt = 0; tt < tcnt; ++tt) {
+        const uint4 a = tile[2 * tt], b = tile[2 * tt + 1];
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) {
+            const uint32_t rp = ham256_packed(Q.v[j], a, b, (uint32_t)(t0 + tt));
+            m2[j] = min(m2[j], max(m1[j], rp));
+            m1[j] = min(m1[j], rp);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) {
+        int q = qbase + j * kThreads + tid;
+        if (q < nq) partial_g[(size_t)blockIdx.x * nq + q] = make_uint2(m1[j], m2[j]);
+    }
+}
+
+// out_idx/out_dist: nq x 2 (int / float); -1 where fewer than two train descriptors exist.
+__global__ void knn2_merge_kernel(const uint2* __restrict__ partial_g, int nparts, int nq, int* __restrict__ out_idx,
+                                  float* __restrict__ out_dist) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+    for (int p = 0; p < nparts; ++p) {
+        const uint2 v = partial_g[(size_t)p * nq + q];
+        // merge two sorted pairs
+        m2 = min(m2, max(m1, v.x));
+        m1 = min(m1, v.x);
+        m2 = min(m2, max(m1, v.y));  // v.y >= v.x, so it can only land in slot 2
+    }
+    out_idx[2 * q] = (m1 == 0xffffffffu) ? -1 : (int)(m1 & 0xffffu);
+    out_dist[2 * q] = (m1 == 0xffffffffu) ? -1.f : (float)(m1 >> 16);
+    out_idx[2 * q + 1] = (m2 == 0xffffffffu) ? -1 : (int)(m2 & 0xffffu);
+    out_dist[2 * q + 1] = (m2 == 0xffffffffu) ? -1.f : (float)(m2 >> 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: loop-closure sweep.  Persistent CTAs walk keyframes (round-robin); the keyframe's descriptors
+// stream through a kStages-deep TMA/mbarrier ring of kTT-row tiles.  Per keyframe: row minima in
+// registers, column minima reduced per sub-tile into shared memory, then the cross-check count.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStages = 4;
+constexpr int kMaxKfDesc = 4096;  // descriptors per keyframe supported by the shared-memory column array
+
+struct SweepCursor {  // walks (keyframe, tile) items of this CTA in order
+    int kf, tile, ntiles;
+    int64_t off;  // descriptor offset of the keyframe
+    int cnt;      // descriptors in the keyframe
+};
+
+__device__ __forceinline__ void cursor_load(SweepCursor& c, const int64_t* __restrict__ kf_off, int n_kf) {
+    while (c.kf < n_kf) {  // skip empty keyframes (they score 0, written by the consumer path)
+        c.off = kf_off[c.kf];
+        c.cnt = (int)(kf_off[c.kf + 1] - c.off);
+        c.ntiles = (c.cnt + kTT - 1) / kTT;
+        if (c.ntiles > 0) break;
+        c.kf += gridDim.x;
+    }
+    c.tile = 0;
+}
+__device__ __forceinline__ void cursor_next(SweepCursor& c, const int64_t* __restrict__ kf_off, int n_kf) {
+    if (++c.tile >= c.ntiles) {
+        c.kf += gridDim.x;
+        cursor_load(c, kf_off, n_kf);
+    }
+}
+
+template <int RQ>
+__global__ void __launch_bounds__(kThreads, 2)
+lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db,
+                const int64_t* __restrict__ kf_off, int n_kf, int tau, int* __restrict__ scores) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4* stages = reinterpret_cast<uint4*>(smem_raw);                                        // kStages*kTT*32
+    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + kStages * kTT * 32);            // 2*kWarps*kTT
+    uint32_t* colmin = partial + 2 * kWarps * kTT;                                             // kMaxKfDesc
+    uint64_t* bars = reinterpret_cast<uint64_t*>(colmin + kMaxKfDesc);                         // kStages
+    int* score_s = reinterpret_cast<int*>(bars + kStages);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+        *score_s = 0;
+    }
+    QueryRegs<RQ> Q;
+    Q.load(query, nq, 0, tid);
+    uint32_t rowmin[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
+    __syncthreads();
+
+    // keyframes with no descriptors never enter the tile stream: score them here
+    for (int kf = blockIdx.x * kThreads + tid; kf < n_kf; kf += gridDim.x * kThreads)
+        if (kf_off[kf + 1] == kf_off[kf]) scores[kf] = 0;
+
+    SweepCursor prod, cons;
+    prod.kf = cons.kf = blockIdx.x;
+    cursor_load(cons, kf_off, n_kf);
+    prod = cons;
+    int issued = 0;
+    if (tid == 0) {
+        for (; issued < kStages - 1 && prod.kf < n_kf; ++issued) {
+            const int cnt = min(kTT, prod.cnt - prod.tile * kTT);
+            uint64_t* bar = bars + (issued % kStages);
+            mbar_expect_tx(bar, (uint32_t)cnt * 32u);
+            tma_load_1d(stages + (size_t)(issued % kStages) * kTT * 2, db + 2 * (prod.off + (int64_t)prod.tile * kTT),
+                        (uint32_t)cnt * 32u, bar);
+            cursor_next(prod, kf_off, n_kf);
+        }
+    }
+
+    for (int it = 0; cons.kf < n_kf; ++it) {
+        const int stage = it % kStages;
+        const uint32_t phase = (uint32_t)(it / kStages) & 1u;
+        if (tid == 0 && prod.kf < n_kf) {  // refill the stage freed by the previous iteration
+            const int cnt = min(kTT, prod.cnt - prod.tile * kTT);
+            const int st = issued % kStages;
+            mbar_expect_tx(bars + st, (uint32_t)cnt * 32u);
+            tma_load_1d(stages + (size_t)st * kTT * 2, db + 2 * (prod.off + (int64_t)prod.tile * kTT),
+                        (uint32_t)cnt * 32u, bars + st);
+            ++issued;
+            cursor_next(prod, kf_off, n_kf);
+        }
+        const int tbase = cons.tile * kTT;
+        const int cnt = min(kTT, cons.cnt - tbase);
+        uint32_t* pbuf = partial + (it & 1) * (kWarps * kTT);
+        mbar_wait(bars + stage, phase);
+        tile_compute<RQ>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        __syncthreads();
+        if (tid < cnt) {
+            uint32_t m = pbuf[tid];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) m = min(m, pbuf[w * kTT + tid]);
+            colmin[tbase + tid] = m;
+        }
+        const bool last = (cons.tile + 1 == cons.ntiles);
+        if (last) {
+            __syncthreads();
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < RQ; ++j) {
+                const uint32_t rp = rowmin[j];
+                const uint32_t t = rp & 0xffffu;
+                const bool valid = Q.off[j] < 0x40000000u;
+                if (valid && (colmin[t] & 0xffffu) == Q.off[j] && (int)(rp >> 16) <= tau) ++c;
+                rowmin[j] = 0xffffffffu;
+            }
+            c = (int)warp_add_u32((uint32_t)c);
+            if (lane == 0 && c) atomicAdd(score_s, c);
+            __syncthreads();
+            if (tid == 0) {
+                scores[cons.kf] = *score_s;
+                *score_s = 0;
+            }
+        }
+        cursor_next(cons, kf_off, n_kf);
+    }
+}
+
+// Local top-k over per-keyframe scores: score descending, keyframe id ascending on ties.
+// Key = score << 32 | (0xffffffff - id); slot r is the largest key below slot r-1, found by one
+// block-wide pass + shared atomicMax per slot (k <= 64; the score array is a few tens of KB).
+// out_pairs: k x {score, global keyframe id}; unused slots {-1, -1}.
+__global__ void __launch_bounds__(1024, 1)
+lc_topk_kernel(const int* __restrict__ scores, int n_kf, int kf_id_base, int k, int* __restrict__ out_pairs) {
+    __shared__ unsigned long long best[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) best[tid] = 0ull;
+    __syncthreads();
+    for (int r = 0; r < k; ++r) {
+        const unsigned long long prev = r ? best[r - 1] : ~0ull;
+        unsigned long long loc = 0ull;
+        if (r == 0 || prev != 0ull) {
+            for (int i = tid; i < n_kf; i += blockDim.x) {
+                const unsigned long long key =
+                    ((unsigned long long)(uint32_t)scores[i] << 32) | (0xffffffffu - (uint32_t)i);
+                if (key < prev && key > loc) loc = key;
+            }
+        }
+        if (loc) atomicMax(best + r, loc);
+        __syncthreads();
+    }
+    if (tid < k) {
+        const unsigned long long key = best[tid];
+        if (key) {
+            out_pairs[2 * tid] = (int)(key >> 32);
+            out_pairs[2 * tid + 1] = kf_id_base + (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+        } else {
+            out_pairs[2 * tid] = -1;
+            out_pairs[2 * tid + 1] = -1;
+        }
+    }
+}
+
+// Merge world*k gathered {score, id} pairs into the global top-k (same order).  Single warp-sized job.
+__global__ void lc_merge_topk_kernel(const int* __restrict__ gathered, int n_pairs, int k, int* __restrict__ out_pairs) {
+    __shared__ unsigned long long keys[1024];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < n_pairs && gathered[2 * i + 1] >= 0)
+            key = ((unsigned long long)(uint32_t)gathered[2 * i] << 32) | (0xffffffffu - (uint32_t)gathered[2 * i + 1]);
+        keys[i] = key;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long prev = ~0ull;
+        for (int r = 0; r < k; ++r) {
+            unsigned long long loc = 0ull;
+            for (int i = 0; i < n_pairs && i < 1024; ++i)
+                if (keys[i] < prev && keys[i] > loc) loc = keys[i];
+            if (loc) {
+                out_pairs[2 * r] = (int)(loc >> 32);
+                out_pairs[2 * r + 1] = (int)(0xffffffffu - (uint32_t)(loc & 0xffffffffu));
+                prev = loc;
+            } else {
+                out_pairs[2 * r] = -1;
+                out_pairs[2 * r + 1] = -1;
+                prev = 0ull;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+static int pick_rq(int nq) { return nq <= kThreads ? 1 : (nq <= 2 * kThreads ? 2 : 4); }
+
+static int pick_t_per_cta(int nt, int qtiles, int sm_count) {
+    // aim for about two CTAs per SM, at least 16 and at most 256 train descriptors per CTA
+    int want = (2 * sm_count + qtiles - 1) / qtiles;
+    int tpc = (nt + want - 1) / want;
+    tpc = (tpc + 15) / 16 * 16;
+    if (tpc < 16) tpc = 16;
+    if (tpc > 256) tpc = 256;
+    return tpc;
+}
+
+cudaError_t launch_bf_mutual(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, uint32_t* d_rowmin,
+                             uint32_t* d_colmin, int* d_out, int cap, int sm_count, cudaStream_t st, int* launches) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(d_rowmin, 0xff, sizeof(uint32_t) * (size_t)nq, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_colmin, 0xff, sizeof(uint32_t) * (size_t)nt, st)) != cudaSuccess) return e;
+    const int rq = pick_rq(nq);
+    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
+    dim3 grid((nt + tpc - 1) / tpc, qtiles);
+    const size_t smem = (size_t)tpc * 32 + sizeof(uint32_t) * kWarps * kTT + 16;
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
+    const uint4* t4 = reinterpret_cast<const uint4*>(d_train);
+    if (rq == 1) bf_tile_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else if (rq == 2) bf_tile_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else bf_tile_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    bf_finalize_kernel<<<1, 1024, 0, st>>>(d_rowmin, d_colmin, nq, cap, d_out);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+int knn2_parts(int nq, int nt, int sm_count) {
+    const int rq = pick_rq(nq);
+    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
+    return (nt + tpc - 1) / tpc;
+}
+
+cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, uint2* d_partial, int* d_idx,
+                        float* d_dist, int sm_count, cudaStream_t st, int* launches) {
+    const int rq = pick_rq(nq);
+    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
+    dim3 grid((nt + tpc - 1) / tpc, qtiles);
+    const size_t smem = (size_t)tpc * 32 + 16;
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
+    const uint4* t4 = reinterpret_cast<const uint4*>(d_train);
+    if (nt > 0) {
+        if (rq == 1) knn2_tile_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        else if (rq == 2) knn2_tile_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        else knn2_tile_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        if (launches) *launches += 1;
+    }
+    knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_partial, nt > 0 ? (int)grid.x : 0, nq, d_idx, d_dist);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+size_t lc_sweep_smem() {
+    return (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * kWarps * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
+}
+int lc_max_kf_desc() { return kMaxKfDesc; }
+int lc_max_query() { return kThreads * 4; }
+
+cudaError_t lc_sweep_configure() {
+    cudaError_t e;
+    const int smem = (int)lc_sweep_smem();
+    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off, int n_kf,
+                            int tau, int* d_scores, int sm_count, cudaStream_t st, int* launches) {
+    if (n_kf <= 0) return cudaSuccess;
+    const int rq = pick_rq(nq);
+    int grid = 2 * sm_count;
+    if (grid > n_kf) grid = n_kf;
+    const size_t smem = lc_sweep_smem();
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
+    const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
+    if (rq == 1) lc_sweep_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    else if (rq == 2) lc_sweep_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    else lc_sweep_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
+                           int* launches) {
+    lc_topk_kernel<<<1, 1024, 0, st>>>(d_scores, n_kf, kf_id_base, k, d_out_pairs);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
+                                 int* launches) {
+    lc_merge_topk_kernel<<<1, 256, 0, st>>>(d_gathered, n_pairs, k, d_out_pairs);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace pslam

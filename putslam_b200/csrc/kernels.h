@@ -1,0 +1,70 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to libpslam_b200.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pslam_b200.h"
+
+namespace pslam {
+
+// ---- hamming.cu ------------------------------------------------------------------------------
+// d_out: int[1 + 3*cap] = {n, queryIdx[cap], trainIdx[cap], distance(float)[cap]}
+cudaError_t launch_bf_mutual(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, uint32_t* d_rowmin,
+                             uint32_t* d_colmin, int* d_out, int cap, int sm_count, cudaStream_t st, int* launches);
+int knn2_parts(int nq, int nt, int sm_count);
+cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, uint2* d_partial, int* d_idx,
+                        float* d_dist, int sm_count, cudaStream_t st, int* launches);
+cudaError_t lc_sweep_configure();
+int lc_max_kf_desc();
+int lc_max_query();
+cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off, int n_kf,
+                            int tau, int* d_scores, int sm_count, cudaStream_t st, int* launches);
+cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
+                           int* launches);
+cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
+                                 int* launches);
+
+// ---- guided.cu -------------------------------------------------------------------------------
+// d_out: int[2 + 3*cap] = {n_total, perfect, queryIdx[cap], trainIdx[cap], distance(float)[cap]}
+cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
+                                const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
+                                float radius_f, double accept_ratio, int mode, int* d_count, int* d_best, int* d_out,
+                                int cap, cudaStream_t st, int* launches);
+
+// ---- ransac.cu -------------------------------------------------------------------------------
+struct RansacDeviceParams {
+    int error_version;
+    float thr_euclid_f;       // smallest float >= inlierThresholdEuclidean (float<double compare, exact)
+    double thr_euclid;
+    double thr_reproj;
+    double min_inlier_ratio;
+    int min_matches;
+    float fx, fy, cx, cy;
+    uint32_t seed_lo, seed_hi;
+    int num_hyp;              // 0 = adaptive (reference bound 487, shrinking), >0 fixed
+};
+struct RansacWorkspace {
+    // all device pointers; sized for m_cap matches and h_cap hypotheses
+    float* pts;        // 6 * m_cap : filtered prev xyz | cur xyz as SoA px,py,pz,cx,cy,cz
+    int* keep;         // m_cap     : original match index of filtered match k
+    int* n_filtered;   // 1
+    int* counts;       // h_cap
+    int* result;       // header (see ransac.cu) + inlier list (m_cap)
+    int m_cap, h_cap;
+};
+size_t ransac_result_ints(int m_cap);
+cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_mq, const int* d_mt,
+                          const int* d_m /* device count, may be NULL */, int m_host, const RansacDeviceParams& P,
+                          const RansacWorkspace& ws, int sm_count, cudaStream_t st, int* launches);
+
+// ---- backproject.cu --------------------------------------------------------------------------
+cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth, int W, int H, int stride,
+                               const pslam_camera& cam, int undistort, double depth_scale, float* d_uv_und,
+                               float* d_xyz, double* d_det_dist, double* d_cov, const pslam_cov_params* cov,
+                               cudaStream_t st, int* launches);
+
+// ---- kabsch.cu -------------------------------------------------------------------------------
+cudaError_t launch_kabsch_batch(const double* d_A, const double* d_B, const int* d_off, int batch, double* d_T,
+                                cudaStream_t st, int* launches);
+
+}  // namespace pslam

@@ -1,0 +1,416 @@
+// ransac.cu -- RANSAC hypothesis scoring and model selection/refit (sm_100a).
+//
+//   ransac_filter_kernel  : drop matches with NaN / z outside [0.1, 6] and gather the surviving pairs
+//                           into SoA form (reference src/TransformEst/RANSAC.cpp:65-80)
+//   K4 ransac_score_kernel: one warp per hypothesis -- counter-based sample of 3 matches, 3-point
+//                           Umeyama, score every match, inlier count by warp reduction
+//                           (reference RANSAC.cpp:87-150 loop body, :180-281, :325-436)
+//   K5 ransac_select_kernel: replay of saveBetterModel / iterationCount (RANSAC.cpp:438-461) over the
+//                           per-hypothesis counts, inlier list of the winner, Umeyama refit over all its
+//                           inliers, Euclidean recount restricted to them, ratio gate (RANSAC.cpp:152-164)
+//
+// All float arithmetic is single-rounding (-fmad=false); summation orders are sequential exactly as
+// written in DESIGN.md, so inlier sets are reproducible bit for bit.
+#include <math.h>
+
+#include "common.cuh"
+#include "geometry.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+constexpr int kHdrInts = 24;  // result header: see layout below
+// result layout (ints): [0] n_inliers  [1] hyp_used  [2] n_filtered  [3] best_count  [4..19] T (col-major float)
+//                       [20..21] best_ratio (double)  [22] winner hypothesis  [23] flags   [24..] inlier match idx
+
+size_t ransac_result_ints(int m_cap) { return (size_t)kHdrInts + (size_t)(m_cap > 0 ? m_cap : 1); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+ransac_filter_kernel(const float* __restrict__ prev, const float* __restrict__ cur, const int* __restrict__ mq,
+                     const int* __restrict__ mt, const int* __restrict__ d_m, int m_host, int m_cap,
+                     float* __restrict__ pts, int* __restrict__ keep, int* __restrict__ n_filtered) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int m = d_m ? *d_m : m_host;
+    if (m > m_cap) m = m_cap;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int k = base + tid;
+        bool ok = false;
+        float p[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+        if (k < m) {
+            const int qi = mq[k], ti = mt[k];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { p[a] = prev[3 * qi + a]; c[a] = cur[3 * ti + a]; }
+            const bool bad = isnan(p[0]) || isnan(p[1]) || isnan(p[2]) || isnan(c[0]) || isnan(c[1]) || isnan(c[2]) ||
+                             (double)p[2] < 0.1 || p[2] > 6.f || (double)c[2] < 0.1 || c[2] > 6.f;
+            ok = !bad;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        const int wpre = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int cw = warp_tot[w];
+            if (w < warp) woff += cw;
+            tot += cw;
+        }
+        if (ok) {
+            const int pos = carry + woff + wpre;
+            keep[pos] = k;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                pts[(size_t)a * m_cap + pos] = p[a];
+                pts[(size_t)(3 + a) * m_cap + pos] = c[a];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    if (tid == 0) *n_filtered = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Scorer {
+    int ev;
+    float thr_f;
+    double thr, thr_reproj;
+    float fx, fy, cx, cy;
+};
+
+__device__ __forceinline__ void project(const Scorer& S, float x, float y, float z, float& u, float& v) {
+    u = __fdiv_rn(x * S.fx, z) + S.cx;  // RGBD::point3Dto2D, reference src/RGBD/RGBD.cpp:92-98
+    v = __fdiv_rn(y * S.fy, z) + S.cy;
+}
+
+// One inlier test; force_euclid reproduces the refit recount (always the Euclidean routine, which still
+// applies the ADAPTIVE depth scaling).  Tinv is R|t of the general inverse, only read for ev 1 and 2.
+__device__ __forceinline__ bool inlier_test(const Scorer& S, const float (&R)[9], const float (&t)[3],
+                                            const float (&Ri)[9], const float (&ti)[3], float px, float py, float pz,
+                                            float cx, float cy, float cz, bool force_euclid) {
+    float ex, ey, ez;
+    rigid_apply(R, t, cx, cy, cz, ex, ey, ez);
+    if (force_euclid || S.ev == 0 || S.ev == 4) {
+        const float nrm = norm3(ex - px, ey - py, ez - pz);
+        if (S.ev == 4) return (double)nrm < S.thr * (double)pz;
+        return nrm < S.thr_f;  // == (double)nrm < thr, thr_f = smallest float >= thr
+    }
+    float nx, ny, nz;
+    rigid_apply(Ri, ti, px, py, pz, nx, ny, nz);
+    float pnu, pnv, rnu, rnv, pou, pov, rou, rov;
+    project(S, nx, ny, nz, pnu, pnv);
+    project(S, cx, cy, cz, rnu, rnv);
+    project(S, ex, ey, ez, pou, pov);
+    project(S, px, py, pz, rou, rov);
+    const float ax = pnu - rnu, ay = pnv - rnv, bx = pou - rou, by = pov - rov;
+    const double e0 = __dsqrt_rn((double)ax * (double)ax + (double)ay * (double)ay);
+    const double e1 = __dsqrt_rn((double)bx * (double)bx + (double)by * (double)by);
+    const bool ok2d = e0 < S.thr_reproj && e1 < S.thr_reproj;
+    if (S.ev == 1) return ok2d;
+    const double e3 = (double)norm3(ex - px, ey - py, ez - pz);
+    return e3 < S.thr && ok2d;
+}
+
+__device__ __forceinline__ void model_inverse(const Rigid3f& M, float (&Ri)[9], float (&ti)[3]) {
+    float T[16], Tin[16];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = M.R[3 * i + j];
+        T[4 * i + 3] = M.t[i];
+    }
+    T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+    inverse4(T, Tin);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ri[3 * i + j] = Tin[4 * i + j];
+        ti[i] = Tin[4 * i + 3];
+    }
+}
+
+__device__ __forceinline__ Rigid3f hypothesis_model(const float* __restrict__ pts, int m_cap, int mf, uint32_t seed_lo,
+                                                    uint32_t seed_hi, uint32_t h) {
+    int s[3];
+    sample3(seed_lo, seed_hi, h, (uint32_t)mf, s);
+    float src[3][3], dst[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            dst[k][a] = pts[(size_t)a * m_cap + s[k]];
+            src[k][a] = pts[(size_t)(3 + a) * m_cap + s[k]];
+        }
+    return umeyama3(src, dst);
+}
+
+constexpr int kScoreThreads = 256;
+
+__global__ void __launch_bounds__(kScoreThreads)
+ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ n_filtered, int min_matches,
+                    Scorer S, uint32_t seed_lo, uint32_t seed_hi, int H, int* __restrict__ counts) {
+    const int mf = *n_filtered;
+    if (mf < min_matches || mf < 3) return;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (kScoreThreads / 32);
+    const float* px = pts;
+    const float* py = pts + (size_t)m_cap;
+    const float* pz = pts + 2 * (size_t)m_cap;
+    const float* cx = pts + 3 * (size_t)m_cap;
+    const float* cy = pts + 4 * (size_t)m_cap;
+    const float* cz = pts + 5 * (size_t)m_cap;
+    for (int h = blockIdx.x * (kScoreThreads / 32) + (threadIdx.x >> 5); h < H; h += warps_total) {
+        const Rigid3f M = hypothesis_model(pts, m_cap, mf, seed_lo, seed_hi, (uint32_t)h);
+        if (!M.ok) {
+            if (lane == 0) counts[h] = -1;
+            continue;
+        }
+        float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
+        if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
+        int c = 0;
+        for (int k = lane; k < mf; k += 32)
+            c += inlier_test(S, M.R, M.t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], false) ? 1 : 0;
+        c = (int)warp_add_u32((uint32_t)c);
+        if (lane == 0) counts[h] = c;
+    }
+}
+
+// computeRANSACIteration (reference RANSAC.cpp:457-461): int(log(1-0.98) / log(1 - w^3)); the
+// out-of-range double->int conversion is pinned to INT_MIN (x86-64 cvttsd2si behaviour).
+__device__ __forceinline__ int ransac_iterations(double w) {
+    const double v = log(1 - 0.98) / log(1 - pow(w, 3.0));
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+    return (int)v;
+}
+
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads, 1)
+ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
+                     const int* __restrict__ n_filtered, const int* __restrict__ counts, int H, int adaptive,
+                     int min_matches, double min_ratio, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
+                     int* __restrict__ inl_tmp /* m_cap scratch */, int* __restrict__ result) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    __shared__ unsigned long long best_key;
+    __shared__ int s_win, s_used, s_cnt;
+    __shared__ float s_mean[6];
+    __shared__ float s_sig[9];
+    __shared__ float s_R[9], s_t[3];
+    __shared__ int s_ok;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mf = *n_filtered;
+    float* Tout = reinterpret_cast<float*>(result + 4);
+    int* inl_out = result + kHdrInts;
+
+    auto write_identity = [&](int used) {
+        if (tid < 16) Tout[tid] = (tid % 5 == 0) ? 1.f : 0.f;
+        if (tid == 0) {
+            result[0] = 0; result[1] = used; result[2] = mf; result[3] = 0; result[22] = -1; result[23] = 0;
+            *reinterpret_cast<double*>(result + 20) = 0.0;
+        }
+    };
+    if (mf < min_matches || mf < 3) {  // RANSAC.cpp:77-80 (3 is the sample size; guards the sampler)
+        write_identity(0);
+        return;
+    }
+
+    // ---- winner: replay of the sequential loop over the scored hypotheses ----
+    if (tid == 0) { best_key = 0ull; s_win = -1; s_used = H; s_cnt = 0; carry = 0; }
+    __syncthreads();
+    if (adaptive) {
+        if (tid == 0) {
+            int bound = H, win = -1, bc = 0;
+            double best = 0.0;
+            int i = 0;
+            for (; i < bound; ++i) {
+                const int c = counts[i];
+                if (c < 0) continue;
+                const float ratio = __fdiv_rn((float)c, (float)mf);
+                if ((double)ratio > best) {
+                    best = (double)ratio; win = i; bc = c;
+                    const int a = ransac_iterations(min_ratio), b = ransac_iterations(best);
+                    bound = a < b ? a : b;
+                }
+            }
+            s_win = win; s_used = i; s_cnt = bc;
+        }
+    } else {
+        // fixed bound: first maximum of float(c)/float(mf) == first maximum of c (monotone, c <= mf < 2^24)
+        unsigned long long loc = 0ull;
+        for (int i = tid; i < H; i += kSelThreads) {
+            const int c = counts[i];
+            if (c > 0) {
+                const unsigned long long key = ((unsigned long long)(uint32_t)c << 32) | (0xffffffffu - (uint32_t)i);
+                if (key > loc) loc = key;
+            }
+        }
+        if (loc) atomicMax(&best_key, loc);
+        __syncthreads();
+        if (tid == 0 && best_key) {
+            s_cnt = (int)(best_key >> 32);
+            s_win = (int)(0xffffffffu - (uint32_t)(best_key & 0xffffffffu));
+        }
+    }
+    __syncthreads();
+    const int win = s_win, used = s_used, best_cnt = s_cnt;
+    if (win < 0) {  // no hypothesis scored above zero: refit on the empty set fails -> identity (RANSAC.cpp:152-164)
+        write_identity(used);
+        return;
+    }
+    const float best_ratio_f = __fdiv_rn((float)best_cnt, (float)mf);
+    const double best_ratio = (double)best_ratio_f;
+
+    const float* px = pts;
+    const float* py = pts + (size_t)m_cap;
+    const float* pz = pts + 2 * (size_t)m_cap;
+    const float* cx = pts + 3 * (size_t)m_cap;
+    const float* cy = pts + 4 * (size_t)m_cap;
+    const float* cz = pts + 5 * (size_t)m_cap;
+
+    // ---- inlier list of the winner (ordered) ----
+    const Rigid3f M = hypothesis_model(pts, m_cap, mf, seed_lo, seed_hi, (uint32_t)win);
+    float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
+    if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
+    for (int base = 0; base < mf; base += kSelThreads) {
+        const int k = base + tid;
+        const bool in = (k < mf) && inlier_test(S, M.R, M.t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], false);
+        const uint32_t bal = __ballot_sync(0xffffffffu, in);
+        const int wpre = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int cw = warp_tot[w];
+            if (w < warp) woff += cw;
+            tot += cw;
+        }
+        if (in) inl_tmp[carry + woff + wpre] = k;
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    const int n_in = carry;
+    __syncthreads();
+
+    // ---- refit: Umeyama over all inliers; every sum is a sequential float chain, one thread per chain ----
+    const float one_over_n = __fdiv_rn(1.f, (float)n_in);
+    if (tid < 6) {
+        const float* col = pts + (size_t)tid * m_cap;  // 0..2 prev (dst), 3..5 cur (src)
+        float s = 0.f;
+        for (int k = 0; k < n_in; ++k) s = s + col[inl_tmp[k]];
+        s_mean[tid] = s * one_over_n;
+    }
+    __syncthreads();
+    if (tid < 9) {
+        const int i = tid / 3, j = tid % 3;
+        const float* dcol = pts + (size_t)i * m_cap;
+        const float* scol = pts + (size_t)(3 + j) * m_cap;
+        const float dmean = s_mean[i], smean = s_mean[3 + j];
+        float s = 0.f;
+        for (int k = 0; k < n_in; ++k) {
+            const int id = inl_tmp[k];
+            s = s + (dcol[id] - dmean) * (scol[id] - smean);
+        }
+        s_sig[tid] = one_over_n * s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float sig[9], sm[3], dm[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sig[i] = s_sig[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { dm[i] = s_mean[i]; sm[i] = s_mean[3 + i]; }
+        const Rigid3f F = umeyama_from_sigma(sig, sm, dm);
+        s_ok = F.ok ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_R[i] = F.ok ? F.R[i] : ((i % 4 == 0) ? 1.f : 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_t[i] = F.ok ? F.t[i] : 0.f;
+        carry = 0;
+    }
+    __syncthreads();
+    float R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = s_R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = s_t[i];
+
+    // ---- Euclidean recount restricted to the winner's inliers (RANSAC.cpp:155-157), ordered ----
+    const bool gate = !(best_ratio < min_ratio);  // RANSAC.cpp:161
+    for (int base = 0; base < n_in; base += kSelThreads) {
+        const int a = base + tid;
+        int k = 0;
+        bool in = false;
+        if (a < n_in) {
+            k = inl_tmp[a];
+            in = inlier_test(S, R, t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], true);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, in);
+        const int wpre = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int cw = warp_tot[w];
+            if (w < warp) woff += cw;
+            tot += cw;
+        }
+        if (in && gate) inl_out[carry + woff + wpre] = keep[k];
+        __syncthreads();
+        if (tid == 0) carry += tot;
+        __syncthreads();
+    }
+    if (tid < 16) {  // column-major 4x4 (Eigen::Matrix4f layout)
+        const int r = tid % 4, c = tid / 4;
+        float v = (r == c) ? 1.f : 0.f;
+        if (gate) {
+            if (r < 3 && c < 3) v = R[3 * r + c];
+            else if (r < 3 && c == 3) v = t[r];
+        }
+        Tout[tid] = v;
+    }
+    if (tid == 0) {
+        result[0] = gate ? carry : 0;
+        result[1] = used;
+        result[2] = mf;
+        result[3] = best_cnt;
+        *reinterpret_cast<double*>(result + 20) = best_ratio;
+        result[22] = win;
+        result[23] = s_ok;
+    }
+}
+
+cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_mq, const int* d_mt, const int* d_m,
+                          int m_host, const RansacDeviceParams& P, const RansacWorkspace& ws, int sm_count,
+                          cudaStream_t st, int* launches) {
+    Scorer S;
+    S.ev = P.error_version;
+    S.thr_f = P.thr_euclid_f;
+    S.thr = P.thr_euclid;
+    S.thr_reproj = P.thr_reproj;
+    S.fx = P.fx; S.fy = P.fy; S.cx = P.cx; S.cy = P.cy;
+    const int adaptive = P.num_hyp <= 0;
+    const int H = adaptive ? 487 : P.num_hyp;  // int(log(0.02)/log(1-0.2^3)), reference RANSAC.cpp:30
+    ransac_filter_kernel<<<1, 1024, 0, st>>>(d_prev, d_cur, d_mq, d_mt, d_m, m_host, ws.m_cap, ws.pts, ws.keep,
+                                             ws.n_filtered);
+    const int warps_per_cta = kScoreThreads / 32;
+    int grid = (H + warps_per_cta - 1) / warps_per_cta;
+    const int max_grid = sm_count * 8;
+    if (grid > max_grid) grid = max_grid;
+    ransac_score_kernel<<<grid, kScoreThreads, 0, st>>>(ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, P.seed_lo,
+                                                        P.seed_hi, H, ws.counts);
+    ransac_select_kernel<<<1, kSelThreads, 0, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, H, adaptive,
+                                                    P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
+                                                    ws.keep + ws.m_cap /* scratch: second half of keep */, ws.result);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
+
+}  // namespace pslam

@@ -1,0 +1,75 @@
+"""Generates tests/golden/*.npz from the REAL OpenCV (cv2) -- the third-party code that carries the
+arithmetic of the reference's matching and undistortion calls:
+
+  cv::BFMatcher(NORM_HAMMING, crossCheck=true).match   src/Matcher/matcherOpenCV.cpp:105,203
+  cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)            (north_star ratio-test extension)
+  cv::Mat a - b (saturating) + cv::norm(NORM_HAMMING)  src/Matcher/matcher.cpp:719-721
+  cv::undistortPoints                                  src/RGBD/RGBD.cpp:268,298
+
+Run in the build container (cv2 4.13.0):  python tests/golden/make_golden.py
+The vectors are small on purpose; the oracle (oracle/oracle.c) and the CUDA path are both checked
+against them, bit for bit.
+"""
+import os
+import sys
+
+import cv2
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def bf_cases():
+    rng = np.random.default_rng(20261017)
+    cases = {}
+    shapes = [("sq500", 500, 500, 32, 256), ("q_lt_t", 200, 700, 32, 256), ("q_gt_t", 700, 200, 32, 256),
+              ("ties4", 300, 300, 32, 4), ("dups", 128, 128, 32, 256), ("one", 1, 1, 32, 256),
+              ("onerow", 1, 50, 32, 256)]
+    for name, nq, nt, nb, alphabet in shapes:
+        if alphabet == 256:
+            q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+            t = rng.integers(0, 256, (nt, nb), dtype=np.uint8)
+        else:  # heavy ties: descriptors drawn from a tiny alphabet in a few bytes, zeros elsewhere
+            q = np.zeros((nq, nb), np.uint8); t = np.zeros((nt, nb), np.uint8)
+            q[:, :2] = rng.integers(0, alphabet, (nq, 2)); t[:, :2] = rng.integers(0, alphabet, (nt, 2))
+        if name == "dups":
+            t[::2] = t[0]; q[::3] = t[0]; q[5] = t[7]
+        ms = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(q, t)
+        cases[name + "_q"] = q; cases[name + "_t"] = t
+        cases[name + "_mq"] = np.array([m.queryIdx for m in ms], np.int32)
+        cases[name + "_mt"] = np.array([m.trainIdx for m in ms], np.int32)
+        cases[name + "_md"] = np.array([m.distance for m in ms], np.float32)
+        if nt >= 2:
+            kn = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)
+            cases[name + "_k_idx"] = np.array([[m[0].trainIdx, m[1].trainIdx] for m in kn], np.int32)
+            cases[name + "_k_dist"] = np.array([[m[0].distance, m[1].distance] for m in kn], np.float32)
+    cases["names"] = np.array([s[0] for s in shapes])
+    return cases
+
+
+def satsub_cases():
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    a[0] = b[0]; a[1] = 255; b[1] = 0; a[2] = 0; b[2] = 255
+    quirk = np.array([cv2.norm(cv2.subtract(x.reshape(1, -1), y.reshape(1, -1)), cv2.NORM_HAMMING) for x, y in zip(a, b)], np.float32)
+    xor = np.array([cv2.norm(x, y, cv2.NORM_HAMMING) for x, y in zip(a, b)], np.float32)
+    return dict(a=a, b=b, quirk=quirk, xor=xor)
+
+
+def undistort_cases():
+    rng = np.random.default_rng(11)
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    d = np.array([-0.0410, 0.3286, 0.0087, 0.0051, -0.5643], np.float32)
+    uv = np.stack([rng.uniform(0, 639, 400), rng.uniform(0, 479, 400)], 1).astype(np.float32)
+    und = cv2.undistortPoints(uv.reshape(-1, 1, 2), K, d).reshape(-1, 2)
+    # RGBD::removeImageDistortion re-projection, float32 (src/RGBD/RGBD.cpp:274-279)
+    out = np.stack([und[:, 0] * K[0, 0] + K[0, 2], und[:, 1] * K[1, 1] + K[1, 2]], 1).astype(np.float32)
+    return dict(K=K, dist=d, uv=uv, normalized=und.astype(np.float32), uv_undist=out)
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "bf_cv2.npz"), **bf_cases())
+    np.savez_compressed(os.path.join(HERE, "satsub_cv2.npz"), **satsub_cases())
+    np.savez_compressed(os.path.join(HERE, "undistort_cv2.npz"), **undistort_cases())
+    print("cv2", cv2.__version__, "golden vectors written to", HERE)

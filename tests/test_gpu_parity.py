@@ -1,0 +1,276 @@
+"""GPU parity tests (-m gpu): every kernel, called through the C ABI, against the oracle and the cv2
+golden vectors.  Integer / index / inlier-set results are bit-exact; poses within 1e-5 m and 1e-5 rad
+(north_star tolerance), float32 back-projection bit-exact, float64 covariance within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-5      # north_star: 1e-5 m translation
+POSE_TOL_RAD = 1e-5    # north_star: 1e-5 rad rotation
+
+
+def rot_angle(Ra, Rb):
+    R = Ra.astype(np.float64).T @ Rb.astype(np.float64)
+    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+
+
+def assert_pose_close(Ta, Tb):
+    assert np.abs(Ta[:3, 3].astype(np.float64) - Tb[:3, 3]).max() <= POSE_TOL_M
+    # arccos near 1 has sqrt(eps) resolution; compare matrices, which bounds the angle
+    assert np.abs(Ta[:3, :3].astype(np.float64) - Tb[:3, :3]).max() <= POSE_TOL_RAD
+
+
+# ---------------------------------------------------------------- stage 2: brute force + cross-check
+def test_bf_mutual_golden_cv2(ctx, golden):
+    g = golden["bf_cv2"]
+    for name in g["names"]:
+        oq, ot, od = ctx.match_bf_mutual(g[f"{name}_q"], g[f"{name}_t"])
+        assert np.array_equal(oq, g[f"{name}_mq"]), name
+        assert np.array_equal(ot, g[f"{name}_mt"]), name
+        assert np.array_equal(od, g[f"{name}_md"]), name
+
+
+@pytest.mark.parametrize("nq,nt", [(500, 500), (1000, 1000), (1000, 5000), (5000, 1000), (1, 1), (33, 2047),
+                                    (257, 255), (1025, 300), (2500, 2500)])
+def test_bf_mutual_vs_oracle(ctx, O, nq, nt):
+    rng = np.random.default_rng(nq * 7919 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    n = min(nq, nt) // 2
+    if n:  # plant near-duplicates so that many mutual matches exist
+        from putslam_b200 import synth
+        t[rng.choice(nt, n, replace=False)] = synth.flip_bits(rng, q[rng.choice(nq, n, replace=False)], 0.05)
+    a = ctx.match_bf_mutual(q, t)
+    b = O.bf_mutual(q, t, threads=4)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_bf_mutual_heavy_ties_and_empty(ctx, O):
+    rng = np.random.default_rng(1)
+    q = np.zeros((700, 32), np.uint8); t = np.zeros((900, 32), np.uint8)
+    q[:, 0] = rng.integers(0, 4, 700); t[:, 0] = rng.integers(0, 4, 900)
+    for x, y in zip(ctx.match_bf_mutual(q, t), O.bf_mutual(q, t)):
+        assert np.array_equal(x, y)
+    same = np.tile(rng.integers(0, 256, (1, 32), dtype=np.uint8), (300, 1))
+    oq, ot, od = ctx.match_bf_mutual(same, same)   # all distances 0: only (0, 0) is mutual
+    assert oq.tolist() == [0] and ot.tolist() == [0] and od.tolist() == [0.0]
+    e = np.zeros((0, 32), np.uint8)
+    assert ctx.match_bf_mutual(e, t)[0].size == 0 and ctx.match_bf_mutual(q, e)[0].size == 0
+
+
+def test_bf_rejects_unsupported(ctx):
+    from putslam_b200 import api
+    with pytest.raises(api.PslamError) as ei:
+        ctx.match_bf_mutual(np.zeros((4, 64), np.uint8), np.zeros((4, 64), np.uint8))
+    assert ei.value.code == api.ERR_UNSUPPORTED
+
+
+def test_knn2_golden_and_oracle(ctx, O, golden):
+    g = golden["bf_cv2"]
+    for name in g["names"]:
+        if f"{name}_k_idx" not in g:
+            continue
+        idx, dist = ctx.match_knn2(g[f"{name}_q"], g[f"{name}_t"])
+        assert np.array_equal(idx, g[f"{name}_k_idx"]), name
+        assert np.array_equal(dist, g[f"{name}_k_dist"]), name
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 256, (1000, 32), dtype=np.uint8); t = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    idx, dist = ctx.match_knn2(q, t)
+    oi, od = O.knn2(q, t)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od.astype(np.float32))
+    idx, dist = ctx.match_knn2(q[:5], t[:1])
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all() and (dist[:, 1] == -1).all()
+
+
+# ---------------------------------------------------------------- stage 1: back-projection
+@pytest.mark.parametrize("distorted", [False, True])
+def test_backproject_bit_exact(ctx, O, distorted):
+    from putslam_b200 import api, synth
+    fp = synth.frame_pair(n=1000, seed=5, distorted=distorted)
+    cam = api.make_camera()
+    out = ctx.backproject(fp["uv1"], fp["depth1"], cam=cam, undistort=distorted)
+    uv = fp["uv1"]
+    if distorted:
+        uv = O.undistort(uv, synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+        assert np.array_equal(bits(out["uv_undist"]), bits(uv))
+    xyz, dd = O.backproject(uv, fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DEPTH_SCALE)
+    assert np.array_equal(bits(out["xyz"]), bits(xyz))
+    assert np.array_equal(bits(out["det_dist"]), bits(dd))
+
+
+def test_undistort_golden_cv2(ctx, golden):
+    from putslam_b200 import api
+    g = golden["undistort_cv2"]
+    K = g["K"]
+    cam = api.make_camera(K[0, 0], K[1, 1], K[0, 2], K[1, 2], tuple(float(x) for x in g["dist"]))
+    out = ctx.backproject(g["uv"], np.full((480, 640), 5000, np.uint16), cam=cam, undistort=True)
+    assert np.array_equal(bits(out["uv_undist"]), bits(g["uv_undist"]))
+
+
+def test_backproject_cov_and_edges(ctx, O):
+    from putslam_b200 import api, synth
+    fp = synth.frame_pair(n=300, seed=6)
+    cp = api.CovParams(synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U, synth.VAR_V,
+                       (api.C.c_double * 4)(*synth.DIST_VAR_COEFS))
+    uv = fp["uv1"].copy()
+    uv[0] = [-3.5, 10.2]; uv[1] = [639.4, 479.4]; uv[2] = [0.49, 0.51]   # border clamps (no OOB read)
+    out = ctx.backproject(uv, fp["depth1"], cov=cp)
+    xyz, _ = O.backproject(uv, fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DEPTH_SCALE)
+    assert np.array_equal(bits(out["xyz"]), bits(xyz))
+    for i in range(0, 300, 7):
+        if uv[i, 0] < 0:
+            continue
+        ref = O.compute_cov(int(uv[i, 0]), int(uv[i, 1]), float(xyz[i, 2]), synth.FX, synth.FY, synth.CX, synth.CY,
+                            synth.VAR_U, synth.VAR_V, synth.DIST_VAR_COEFS)
+        assert np.allclose(out["cov"][i], ref, rtol=1e-12, atol=0), i   # float64 tolerance 1e-12 relative
+    assert ctx.backproject(np.zeros((0, 2), np.float32), fp["depth1"])["xyz"].shape == (0, 3)
+
+
+# ---------------------------------------------------------------- stage 2: guided map matching
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("M,N,seed", [(5000, 1000, 0), (5000, 1000, 1), (800, 333, 2), (40, 7, 3)])
+def test_guided_match_vs_oracle(ctx, O, M, N, seed, mode):
+    from putslam_b200 import host, synth
+    mf = synth.map_frame(M=M, N=N, n_reobs=int(0.7 * N), seed=seed)
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    for cn in (1, 4):   # retry ladder widens the gates (matcher.cpp:617-622)
+        radius, ratio = host.retry_gates(0.12, 0.55, cn)
+        out = ctx.match_guided_xyz(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, radius, ratio, mode)
+        q, t, d, perfect = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, radius, ratio, mode)
+        assert out["total"] == q.size and out["perfect"] == perfect
+        assert np.array_equal(out["q"], q) and np.array_equal(out["t"], t) and np.array_equal(out["d"], d)
+
+
+def test_guided_match_capacity_and_empty(ctx, O):
+    from putslam_b200 import host, synth
+    mf = synth.map_frame(M=600, N=300, n_reobs=200, seed=9)
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    full = ctx.match_guided_xyz(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0)
+    cut = ctx.match_guided_xyz(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0, cap=10)
+    assert cut["truncated"] and cut["total"] == full["total"] and np.array_equal(cut["q"], full["q"][:10])
+    none = ctx.match_guided_xyz(mf["map_xyz"] + 100.0, mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0)
+    assert none["total"] == 0
+
+
+# ---------------------------------------------------------------- stage 3: RANSAC / Umeyama / Kabsch
+@pytest.mark.parametrize("ev", [0, 4, 1, 2])
+@pytest.mark.parametrize("num_hyp", [0, 256, 4096])
+def test_ransac_vs_oracle(ctx, O, ev, num_hyp):
+    from putslam_b200 import api, synth
+    for seed in range(3):
+        mc = synth.matched_clouds(m=1000, inlier_frac=0.55, seed=seed)
+        r = ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=api.default_ransac_params(ev),
+                                seed=100 + seed, num_hyp=num_hyp, want_counts=True)
+        o = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=O.default_ransac_params(ev), seed=100 + seed,
+                     num_hyp=num_hyp, want_counts=True)
+        n = o["hyp_used"]
+        if num_hyp:  # every hypothesis is evaluated in fixed-H mode: all counts must agree
+            assert np.array_equal(r["counts"][:num_hyp], o["counts"][:num_hyp])
+        else:
+            assert np.array_equal(r["counts"][:n], o["counts"][:n])
+        assert r["hyp_used"] == o["hyp_used"]
+        assert r["best_ratio"] == o["best_ratio"]
+        assert np.array_equal(r["inliers"], o["inliers"])
+        assert_pose_close(r["T"], o["T"].astype(np.float64))
+        assert np.abs(r["T"] - mc["T_gt"]).max() < 0.02
+
+
+def test_ransac_models_bit_exact(ctx, O):
+    """Hypothesis models are reproducible bit for bit: identical counts over 65536 hypotheses."""
+    from putslam_b200 import synth
+    mc = synth.matched_clouds(m=500, inlier_frac=0.4, seed=11)
+    r = ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=5, num_hyp=65536, want_counts=True)
+    o = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=5, num_hyp=65536, want_counts=True)
+    assert np.array_equal(r["counts"], o["counts"])
+    assert np.array_equal(r["inliers"], o["inliers"]) and np.array_equal(bits(r["T"]), bits(o["T"]))
+
+
+def test_ransac_failure_conventions(ctx, O):
+    from putslam_b200 import api, synth
+    mc = synth.matched_clouds(m=600, inlier_frac=0.6, seed=2)
+    r = ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"][:10], mc["mt"][:10], seed=1)
+    assert np.array_equal(r["T"], np.eye(4)) and r["inliers"].size == 0
+    rng = np.random.default_rng(0)
+    prev = rng.uniform(0.5, 4, (300, 3)).astype(np.float32); cur = rng.uniform(0.5, 4, (300, 3)).astype(np.float32)
+    r = ctx.ransac_estimate(prev, cur, np.arange(300), np.arange(300), seed=1)
+    o = O.ransac(prev, cur, np.arange(300), np.arange(300), seed=1)
+    assert np.array_equal(r["T"], np.eye(4)) and r["inliers"].size == 0 and r["best_ratio"] == o["best_ratio"]
+    prev2 = mc["prev"].copy(); prev2[::7, 2] = np.nan; prev2[1::7, 2] = 7.0; prev2[2::7, 2] = 0.05
+    r = ctx.ransac_estimate(prev2, mc["cur"], mc["mq"], mc["mt"], seed=3)
+    o = O.ransac(prev2, mc["cur"], mc["mq"], mc["mt"], seed=3)
+    assert np.array_equal(r["inliers"], o["inliers"]) and r["hyp_used"] == o["hyp_used"]
+    # filtered count falls below minimalNumberOfMatches on the device
+    prev3 = mc["prev"].copy(); prev3[:, 2] = 9.0
+    r = ctx.ransac_estimate(prev3, mc["cur"], mc["mq"], mc["mt"], seed=3)
+    assert np.array_equal(r["T"], np.eye(4)) and r["inliers"].size == 0
+    with pytest.raises(api.PslamError):
+        ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=api.default_ransac_params(3))
+
+
+def test_kabsch_batch_vs_oracle(ctx, O):
+    from putslam_b200 import synth
+    rng = np.random.default_rng(4)
+    As, Bs = [], []
+    for n in (100, 4, 1000, 0, 57):
+        A = rng.uniform(-1.5, 1.5, (n, 3))
+        R = synth.rot_from_rotvec(rng.standard_normal(3) * 0.4)
+        B = A @ R.T + np.array([0.1, 0.2, -0.3]) + rng.normal(0, [0.01, 0.02, 0.03], (n, 3))
+        As.append(A); Bs.append(B)
+    Ts = ctx.kabsch_batch(As, Bs)
+    for A, B, T in zip(As, Bs, Ts):
+        ref = O.kabsch(A, B)
+        assert np.array_equal(bits(T), bits(ref))     # same operation order -> same bits
+
+
+# ---------------------------------------------------------------- fused pipelines
+def test_frame_to_frame_pipeline(ctx, O):
+    from putslam_b200 import api, synth
+    for seed, n, distorted in [(0, 500, False), (1, 500, True), (2, 1000, False)]:
+        fp = synth.frame_pair(n=n, seed=seed, distorted=distorted)
+        cam = api.make_camera()
+        f1 = ctx.frame_to_frame(None, None, fp["desc1"], fp["uv1"], fp["depth1"], cam=cam, undistort=distorted)
+        out = ctx.frame_to_frame(fp["desc1"], f1["xyz"], fp["desc2"], fp["uv2"], fp["depth2"], cam=cam,
+                                 undistort=distorted, seed=seed + 50)
+        uv1, uv2 = fp["uv1"], fp["uv2"]
+        if distorted:
+            uv1 = O.undistort(uv1, synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+            uv2 = O.undistort(uv2, synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+        x1, _ = O.backproject(uv1, fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DEPTH_SCALE)
+        x2, dd2 = O.backproject(uv2, fp["depth2"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DEPTH_SCALE)
+        oq, ot, od = O.bf_mutual(fp["desc1"], fp["desc2"])
+        ref = O.ransac(x1, x2, oq, ot, seed=seed + 50)
+        assert np.array_equal(bits(f1["xyz"]), bits(x1)) and np.array_equal(bits(out["xyz"]), bits(x2))
+        assert np.array_equal(bits(out["det_dist"]), bits(dd2))
+        assert np.array_equal(out["mq"], oq) and np.array_equal(out["mt"], ot) and np.array_equal(out["md"], od)
+        assert np.array_equal(out["inliers"], ref["inliers"]) and out["hyp_used"] == ref["hyp_used"]
+        assert_pose_close(out["T"], ref["T"].astype(np.float64))
+        assert out["inlier_ratio"] == O.point_inlier_ratio(ot[ref["inliers"]], ot, n)
+        # the planted motion is recovered
+        assert np.abs(out["T"] - fp["T_gt"]).max() < 0.01
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_frame_to_map_pipeline(ctx, O, mode):
+    from putslam_b200 import host, synth
+    for seed in range(2):
+        mf = synth.map_frame(M=5000, N=1000, seed=seed)
+        ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+        cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+        for num_hyp in (0, 4096):
+            out = ctx.frame_to_map(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55,
+                                   mode, seed=7, num_hyp=num_hyp)
+            q, t, d, _ = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, mode)
+            ref = O.ransac(mf["map_xyz"].astype(np.float32), mf["cur_xyz"], q, t, seed=7, num_hyp=num_hyp)
+            assert np.array_equal(out["mq"], q) and np.array_equal(out["mt"], t) and np.array_equal(out["md"], d)
+            assert np.array_equal(out["inliers"], ref["inliers"]) and out["hyp_used"] == ref["hyp_used"]
+            assert_pose_close(out["T"], ref["T"].astype(np.float64))
+            assert out["inlier_ratio"] == O.point_inlier_ratio(t[ref["inliers"]], t, 1000)
+            assert len(ref["inliers"]) > 300 and np.abs(out["T"] - mf["T_gt"]).max() < 0.01
+        # resident replay leaves the answer unchanged
+        ctx.frame_to_map_resident(); ctx.sync()

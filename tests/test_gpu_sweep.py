@@ -1,0 +1,68 @@
+"""GPU tests (-m gpu) of the loop-closure sweep: per-keyframe scores and top-k against the oracle,
+ragged / empty keyframes, incremental appends, and a size-independent check at the full C4 size."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fresh(ctx):
+    ctx.lc_clear()
+    ctx.lc_set_id_base(0)
+
+
+@pytest.mark.parametrize("n_kf,per_kf,nq,ragged", [(64, 1000, 1000, False), (200, 300, 500, True), (50, 1000, 200, True),
+                                                   (300, 128, 1000, False), (7, 4096, 1000, False)])
+def test_lc_scores_vs_oracle(ctx, O, n_kf, per_kf, nq, ragged):
+    from putslam_b200 import synth
+    db = synth.keyframe_db(n_kf=n_kf, per_kf=per_kf, n_query=nq, n_planted=min(5, n_kf), shared=min(nq, per_kf) // 3,
+                           seed=n_kf, ragged=ragged)
+    _fresh(ctx)
+    ctx.lc_append(db["db"], db["kf_off"])
+    ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=16, want_scores=True)
+    ref = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=8)
+    assert np.array_equal(scores, ref)
+    eid, esc = O.topk(ref, 16)
+    assert np.array_equal(ids, eid) and np.array_equal(sc, esc)
+    for tau in (0, 30, 256):
+        _, _, s2 = ctx.lc_query(db["query"], tau=tau, k=4, want_scores=True)
+        assert np.array_equal(s2, O.lc_scores(db["query"], db["db"], db["kf_off"], tau=tau, threads=8))
+
+
+def test_lc_empty_keyframes_and_incremental_append(ctx, O):
+    from putslam_b200 import synth
+    db = synth.keyframe_db(n_kf=30, per_kf=200, n_query=300, n_planted=3, shared=100, seed=1)
+    off = db["kf_off"].copy()
+    # make keyframes 4 and 17 empty by collapsing their ranges
+    counts = np.diff(off); counts[4] = 0; counts[17] = 0
+    keep = np.concatenate([np.arange(off[k], off[k] + counts[k]) for k in range(30)])
+    d2 = db["db"][keep]; off2 = np.concatenate([[0], np.cumsum(counts)])
+    _fresh(ctx)
+    for lo in range(0, 30, 7):   # append in pieces
+        hi = min(30, lo + 7)
+        ctx.lc_append(d2, off2[lo:hi + 1])
+    assert ctx.lc_size() == (30, int(off2[-1]))
+    ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=8, want_scores=True)
+    ref = O.lc_scores(db["query"], d2, off2, tau=64)
+    assert np.array_equal(scores, ref) and scores[4] == 0 and scores[17] == 0
+    assert np.array_equal(ids, O.topk(ref, 8)[0])
+    _fresh(ctx)
+    ids, sc = ctx.lc_query(db["query"], k=4)   # empty database
+    assert (ids == -1).all()
+
+
+def test_lc_full_size_planted_recall(ctx):
+    """C4 size (10k keyframes x 1000): the 20 planted keyframes must be the top-20, random ones score ~0."""
+    from putslam_b200 import synth
+    db = synth.keyframe_db(n_kf=10000, per_kf=1000, n_query=1000, n_planted=20, shared=400, seed=7)
+    _fresh(ctx)
+    ctx.lc_reserve(db["db"].shape[0], 10000)
+    ctx.lc_append(db["db"], db["kf_off"])
+    ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=20, want_scores=True)
+    assert sorted(ids.tolist()) == db["planted"].tolist()
+    assert sc.min() > 300 and np.delete(scores, db["planted"]).max() < 5
+    # idempotence: the resident replay gives the same answer
+    ctx.lc_query_resident(tau=64, k=20); ctx.sync()
+    ids2, sc2 = ctx.lc_query(db["query"], tau=64, k=20)
+    assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+    _fresh(ctx)

@@ -1,0 +1,245 @@
+"""CPU tests (-m "not gpu"): the oracle against the cv2 golden vectors, live cv2, numpy float64."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+
+def test_bf_mutual_and_knn2_match_cv2_golden(O, golden):
+    g = golden["bf_cv2"]
+    for name in g["names"]:
+        q, t = g[f"{name}_q"], g[f"{name}_t"]
+        oq, ot, od = O.bf_mutual(q, t)
+        assert np.array_equal(oq, g[f"{name}_mq"]), name
+        assert np.array_equal(ot, g[f"{name}_mt"]), name
+        assert np.array_equal(od, g[f"{name}_md"]), name
+        oq2, ot2, od2 = O.bf_mutual(q, t, threads=3)
+        assert np.array_equal(oq, oq2) and np.array_equal(ot, ot2) and np.array_equal(od, od2)
+        if f"{name}_k_idx" in g:
+            idx, dist = O.knn2(q, t)
+            assert np.array_equal(idx, g[f"{name}_k_idx"]), name
+            assert np.array_equal(dist.astype(np.float32), g[f"{name}_k_dist"]), name
+
+
+def test_bf_mutual_live_cv2(O):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for nq, nt in [(257, 511), (640, 129)]:
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        ms = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(q, t)
+        oq, ot, od = O.bf_mutual(q, t)
+        assert [m.queryIdx for m in ms] == oq.tolist()
+        assert [m.trainIdx for m in ms] == ot.tolist()
+        assert [m.distance for m in ms] == od.tolist()
+
+
+def test_empty_inputs(O):
+    e = np.zeros((0, 32), np.uint8)
+    q = np.zeros((5, 32), np.uint8)
+    assert O.bf_mutual(e, q)[0].size == 0 and O.bf_mutual(q, e)[0].size == 0
+    idx, dist = O.knn2(q, np.zeros((1, 32), np.uint8))
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all()
+
+
+def test_satsub_quirk_matches_cv2_golden(O, golden):
+    g = golden["satsub_cv2"]
+    for a, b, quirk, xor in zip(g["a"], g["b"], g["quirk"], g["xor"]):
+        assert O.hamming_satsub(a, b) == int(quirk)
+        assert O.hamming_xor(a, b) == int(xor)
+    # the quirk is not symmetric and not the Hamming distance (SURVEY finding 4)
+    assert any(O.hamming_satsub(a, b) != O.hamming_satsub(b, a) for a, b in zip(g["a"], g["b"]))
+
+
+def test_undistort_matches_cv2_golden(O, golden):
+    g = golden["undistort_cv2"]
+    K = g["K"]
+    out = O.undistort(g["uv"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], g["dist"])
+    assert np.array_equal(bits(out), bits(g["uv_undist"]))
+
+
+def test_backproject_definition(O):
+    from putslam_b200 import synth
+    fp = synth.frame_pair(n=200, seed=1)
+    xyz, dd = O.backproject(fp["uv1"], fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DEPTH_SCALE)
+    uv = fp["uv1"]
+    uR = np.clip(np.rint(uv[:, 0]), 0, 639).astype(int); vR = np.clip(np.rint(uv[:, 1]), 0, 479).astype(int)
+    Z = (fp["depth1"][vR, uR].astype(np.float64) / 5000.0).astype(np.float32)
+    X = ((uv[:, 0] - np.float32(synth.CX)) / np.float32(synth.FX)) * Z
+    assert np.array_equal(bits(xyz[:, 2]), bits(Z)) and np.array_equal(bits(xyz[:, 0]), bits(X.astype(np.float32)))
+    assert np.allclose(dd, np.linalg.norm(xyz.astype(np.float64), axis=1), rtol=1e-6)
+    # zero depth -> origin (later dropped by RANSAC's z < 0.1 filter)
+    z = np.zeros((480, 640), np.uint16)
+    xyz0, _ = O.backproject(uv[:3], z, synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+    assert (xyz0 == 0).all()
+
+
+def test_cov_is_J_R_Jt(O):
+    from putslam_b200 import synth
+    c = synth.DIST_VAR_COEFS
+    cov = O.compute_cov(321, 200, 2.5, synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U, synth.VAR_V, c)
+    d = 2.5
+    J = np.array([[d / synth.FX, 0, 321 / synth.FX - synth.CX / synth.FX], [0, d / synth.FY, 200 / synth.FY - synth.CY / synth.FY], [0, 0, 1]])
+    R = np.diag([synth.VAR_U, synth.VAR_V, c[0] * d ** 3 + c[1] * d ** 2 + c[2] * d + c[3]])
+    assert np.allclose(cov, J @ R @ J.T, rtol=1e-13, atol=0)
+
+
+def test_philox_known_answers(O):
+    # Random123 kat_vectors, philox4x32-10
+    assert O.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert O.philox([0xffffffff] * 4, [0xffffffff] * 2).tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert O.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]).tolist() == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_sample3_distinct_and_in_range(O):
+    for m in (3, 4, 15, 1000):
+        for h in range(50):
+            s = O.sample3(12345, h, m)
+            assert len(set(s.tolist())) == 3 and s.min() >= 0 and s.max() < m
+
+
+def test_svd_against_numpy(O):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        A = rng.standard_normal((3, 3)).astype(np.float32)
+        U, S, V = O.svd3f(A)
+        assert np.abs(U @ np.diag(S) @ V.T - A).max() < 5e-6
+        assert np.allclose(S, np.linalg.svd(A.astype(np.float64))[1], atol=5e-6)
+        assert S[0] >= S[1] >= S[2] >= 0
+        assert np.abs(U.T @ U - np.eye(3)).max() < 5e-6 and np.abs(V.T @ V - np.eye(3)).max() < 5e-6
+    Ud, Sd, Vd = O.svd3d(np.diag([3.0, 0.0, 1.0]))
+    assert np.allclose(Sd, [3, 1, 0])
+    # rank-2 (three centred points are coplanar) and rank-1 inputs stay finite
+    B = np.outer([1, 2, 3], [4, 5, 6]).astype(np.float32)
+    U, S, V = O.svd3f(B)
+    assert np.isfinite(U).all() and np.isfinite(V).all() and S[1] < 1e-4 * S[0]
+
+
+def _umeyama64(src, dst):
+    sm, dm = src.mean(0), dst.mean(0)
+    sig = (dst - dm).T @ (src - sm) / len(src)
+    U, S, Vt = np.linalg.svd(sig)
+    D = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        D[2, 2] = -1
+    R = U @ D @ Vt
+    return R, dm - R @ sm
+
+
+def test_umeyama_and_kabsch_against_float64(O):
+    from putslam_b200 import synth
+    rng = np.random.default_rng(1)
+    for n in (3, 4, 10, 100, 1000):
+        src = rng.uniform(-1.5, 1.5, (n, 3))
+        R = synth.rot_from_rotvec(rng.standard_normal(3) * 0.3)
+        t = np.array([0.1, 0.2, -0.3])
+        dst = src @ R.T + t + rng.normal(0, 0.01, (n, 3))
+        ok, T = O.umeyama(src.astype(np.float32), dst.astype(np.float32))
+        R64, t64 = _umeyama64(src.astype(np.float32).astype(np.float64), dst.astype(np.float32).astype(np.float64))
+        assert ok == 1
+        assert np.abs(T[:3, :3] - R64).max() < 1e-5 and np.abs(T[:3, 3] - t64).max() < 1e-5
+        if n >= 4:
+            Tk = O.kabsch(src, dst)
+            Rk, tk = _umeyama64(src, dst)
+            assert np.abs(Tk[:, :3] - Rk).max() < 1e-10 and np.abs(Tk[:, 3] - tk).max() < 1e-10
+    # reflection case: planar mirrored configuration must still give det(R) = +1
+    src = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    dst = np.array([[0, 0, 0], [1, 0, 0], [0, -1, 0]], np.float32)
+    ok, T = O.umeyama(src, dst)
+    assert ok == 1 and abs(np.linalg.det(T[:3, :3].astype(np.float64)) - 1) < 1e-5
+    assert np.array_equal(O.kabsch(np.zeros((0, 3)), np.zeros((0, 3))), np.eye(3, 4))
+
+
+def test_inverse4_against_numpy(O):
+    from putslam_b200 import synth
+    T = np.eye(4, dtype=np.float32)
+    T[:3, :3] = synth.rot_from_rotvec([0.2, -0.1, 0.3]); T[:3, 3] = [0.3, -0.2, 0.1]
+    assert np.abs(O.inverse4(T) - np.linalg.inv(T.astype(np.float64))).max() < 1e-6
+
+
+def test_ransac_iterations(O):
+    assert O.ransac_iterations(0.2) == 487            # reference RANSAC.cpp:30
+    assert O.ransac_iterations(1.0) == 0              # log(0) = -inf
+    assert O.ransac_iterations(0.0005) == -2**31      # out-of-range double -> int (x86-64)
+    assert O.ransac_iterations(0.5) == int(np.log(0.02) / np.log(1 - 0.125))
+
+
+def test_ransac_recovers_planted_transform(O):
+    from putslam_b200 import synth
+    mc = synth.matched_clouds(m=600, inlier_frac=0.6, seed=2)
+    for ev in (0, 4, 1, 2):
+        p = O.default_ransac_params(ev)
+        r = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=p, seed=9, num_hyp=0, want_counts=True)
+        assert len(r["inliers"]) > 250, ev
+        assert np.abs(r["T"] - mc["T_gt"]).max() < 0.02, ev
+        assert 0 < r["hyp_used"] <= 487
+        assert np.all(np.diff(r["inliers"]) > 0)
+    r1 = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=9, num_hyp=256)
+    r2 = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=9, num_hyp=256)
+    assert np.array_equal(r1["inliers"], r2["inliers"]) and r1["hyp_used"] == 256
+
+
+def test_ransac_failure_conventions(O):
+    from putslam_b200 import synth
+    mc = synth.matched_clouds(m=600, inlier_frac=0.6, seed=2)
+    # fewer than minimalNumberOfMatches -> identity, no inliers (RANSAC.cpp:77-80)
+    r = O.ransac(mc["prev"], mc["cur"], mc["mq"][:10], mc["mt"][:10], seed=1)
+    assert np.array_equal(r["T"], np.eye(4)) and r["inliers"].size == 0
+    # pure outliers -> ratio below 0.2 -> identity (RANSAC.cpp:161-164)
+    rng = np.random.default_rng(0)
+    prev = rng.uniform(0.5, 4, (300, 3)).astype(np.float32); cur = rng.uniform(0.5, 4, (300, 3)).astype(np.float32)
+    r = O.ransac(prev, cur, np.arange(300), np.arange(300), seed=1)
+    assert np.array_equal(r["T"], np.eye(4)) and r["inliers"].size == 0
+    # NaN / out-of-range depth are filtered before sampling (RANSAC.cpp:65-74)
+    prev2 = mc["prev"].copy(); prev2[::7, 2] = np.nan; prev2[1::7, 2] = 7.0; prev2[2::7, 2] = 0.05
+    r = O.ransac(prev2, mc["cur"], mc["mq"], mc["mt"], seed=3)
+    bad = np.isnan(prev2[mc["mq"], 2]) | (prev2[mc["mq"], 2] > 6) | (prev2[mc["mq"], 2] < 0.1)
+    assert not bad[r["inliers"]].any()
+
+
+def test_guided_match_against_python_restatement(O):
+    from putslam_b200 import host, synth
+    mf = synth.map_frame(M=300, N=120, n_reobs=80, seed=4)
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    for mode in (0, 1):
+        q, t, d, perfect = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, mode)
+        exp = []
+        mx = mf["map_xyz"].astype(np.float32)
+        for j in range(300):
+            diff = mx[j] - mf["cur_xyz"]
+            nrm = np.sqrt((diff[:, 0] ** 2 + (diff[:, 1] ** 2 + diff[:, 2] ** 2)).astype(np.float32))
+            cand = [i for i in range(120) if nrm[i] < 0.12 and abs(int(cl[i]) - int(ml[j])) <= 1]
+            if mode == 0:
+                vals = [int(np.unpackbits(np.clip(mf["map_desc"][j].astype(int) - mf["cur_desc"][i].astype(int), 0, 255).astype(np.uint8)).sum()) for i in cand]
+            else:
+                vals = [int(np.unpackbits(mf["map_desc"][j] ^ mf["cur_desc"][i]).sum()) for i in cand]
+            if cand:
+                best = min(vals)
+                exp += [(j, i, v) for i, v in zip(cand, vals) if 0.55 * v <= best]
+        assert list(zip(q.tolist(), t.tolist(), d.astype(int).tolist())) == exp
+        assert len(exp) > 40
+
+
+def test_levels_host_equals_oracle(O):
+    from putslam_b200 import host
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        o = int(rng.integers(0, 8)); dd = float(rng.uniform(0.5, 6)); cd = float(dd * rng.uniform(0.6, 1.6))
+        assert host.predicted_level(o, dd, cd) == O.pred_level(o, dd, cd)
+
+
+def test_lc_scores_and_topk(O):
+    from putslam_b200 import synth
+    db = synth.keyframe_db(n_kf=40, per_kf=120, n_query=100, n_planted=4, shared=50, seed=3, ragged=True)
+    s = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=2)
+    top, sc = O.topk(s, 4)
+    assert sorted(top.tolist()) == db["planted"].tolist()
+    assert (sc >= 30).all() and (np.delete(s, db["planted"]) < 10).all()
+    order = sorted(range(40), key=lambda i: (-s[i], i))[:8]
+    assert O.topk(s, 8)[0].tolist() == order
+
+
+def test_point_inlier_ratio(O):
+    assert O.point_inlier_ratio([1, 1, 2], [1, 2, 3, 3, 4], 10) == 2 / 4
