@@ -215,6 +215,8 @@ PSLAM_API int pslam_lc_query(pslam_ctx* ctx, const uint8_t* query, int nq, int t
                              int* out_scores, int* scores_out);
 /* kernels only, on the query already resident from the last pslam_lc_query / _sharded call */
 PSLAM_API int pslam_lc_query_resident(pslam_ctx* ctx, int tau, int k);
+/* device time (CUDA events on the ctx stream) of the sweep kernel of the most recent query on this ctx */
+PSLAM_API int pslam_lc_last_sweep_ms(pslam_ctx* ctx, float* ms_out);
 
 /* Multi-GPU (one process per GPU, keyframes sharded by rank).  The library brings up its own NCCL
  * communicator from a caller-distributed ncclUniqueId (128 bytes): rank 0 calls pslam_comm_unique_id,

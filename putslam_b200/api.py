@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
-    "pslam_lc_query_resident", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
+    "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2",
 ]
 
@@ -314,6 +314,11 @@ class Context:
 
     def lc_query_resident(self, tau=64, k=16):
         self._ck(self.lib.pslam_lc_query_resident(self.h, tau, k))
+
+    def lc_last_sweep_ms(self):
+        ms = C.c_float(0)
+        self._ck(self.lib.pslam_lc_last_sweep_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def comm_init(self, uid_bytes, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid_bytes))

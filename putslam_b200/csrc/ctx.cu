@@ -119,6 +119,7 @@ struct pslam_ctx {
     int lc_nq = 0;
     int* d_lc_pairs = nullptr;  // local k pairs | gathered world*k pairs | merged k pairs
     bool lc_configured = false;
+    cudaEvent_t ev_sweep0 = nullptr, ev_sweep1 = nullptr;  // bracket the sweep kernel of the last query
     // NCCL
     void* comm = nullptr;
     int rank = 0, world = 1;
@@ -291,6 +292,8 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
+    if (ctx->ev_sweep0) cudaEventDestroy(ctx->ev_sweep0);
+    if (ctx->ev_sweep1) cudaEventDestroy(ctx->ev_sweep1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -855,6 +858,8 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
         CK(lc_sweep_configure());
         CK(cudaMalloc((void**)&ctx->d_lc_query, (size_t)PSLAM_LC_MAX_QUERY * 32));
         CK(cudaMalloc((void**)&ctx->d_lc_pairs, sizeof(int) * 2 * PSLAM_LC_MAX_TOPK * (2 + 64)));
+        CK(cudaEventCreate(&ctx->ev_sweep0));
+        CK(cudaEventCreate(&ctx->ev_sweep1));
         ctx->lc_configured = true;
     }
     if (!ctx->d_scores) TRY(pslam_lc_db_reserve(ctx, 1, 1));
@@ -869,8 +874,10 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
 
 static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
     int l = 0;
+    CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
     CK(launch_lc_sweep(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, ctx->n_kf, tau, ctx->d_scores,
                        ctx->sm_count, ctx->stream, &l));
+    CK(cudaEventRecord(ctx->ev_sweep1, ctx->stream));
     CK(launch_lc_topk(ctx->d_scores, ctx->n_kf, ctx->kf_id_base, k, ctx->d_lc_pairs, ctx->stream, &l));
     ctx->launches += l;
     return PSLAM_OK;
@@ -898,6 +905,15 @@ int pslam_lc_query(pslam_ctx* ctx, const uint8_t* query, int nq, int tau, int k,
     CK(cudaStreamSynchronize(ctx->stream));
     unpack_pairs((const int*)ctx->h_out.p, k, out_kf_ids, out_scores);
     if (scores_out && ctx->n_kf > 0) memcpy(scores_out, ctx->h_out.p + sizeof(int) * 2 * (size_t)k, sizeof(int) * (size_t)ctx->n_kf);
+    return PSLAM_OK;
+}
+
+int pslam_lc_last_sweep_ms(pslam_ctx* ctx, float* ms_out) {
+    if (!ctx || !ms_out) return PSLAM_ERR_ARG;
+    if (!ctx->lc_configured) return fail(ctx, PSLAM_ERR_ARG, "no sweep has run on this ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_sweep1));
+    CK(cudaEventElapsedTime(ms_out, ctx->ev_sweep0, ctx->ev_sweep1));
     return PSLAM_OK;
 }
 

@@ -180,11 +180,14 @@ ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restr
     }
 }
 
-// computeRANSACIteration (reference RANSAC.cpp:457-461): int(log(1-0.98) / log(1 - w^3)); the
-// out-of-range double->int conversion is pinned to INT_MIN (x86-64 cvttsd2si behaviour).
+// computeRANSACIteration (reference RANSAC.cpp:457-461): int(log(1-0.98) / log(1 - w^3)).  The
+// reference's conversion is undefined behaviour once the quotient leaves the int range (tiny ratios);
+// it is defined here as the saturating conversion (deliberate divergences).
 __device__ __forceinline__ int ransac_iterations(double w) {
     const double v = log(1 - 0.98) / log(1 - pow(w, 3.0));
-    if (!(v > -2147483649.0 && v < 2147483648.0)) return (int)0x80000000;
+    if (v != v) return (int)0x80000000;
+    if (v >= 2147483648.0) return 0x7fffffff;
+    if (v <= -2147483649.0) return (int)0x80000000;
     return (int)v;
 }
 

@@ -178,7 +178,7 @@ def test_ransac_vs_oracle(ctx, O, ev, num_hyp):
         assert r["best_ratio"] == o["best_ratio"]
         assert np.array_equal(r["inliers"], o["inliers"])
         assert_pose_close(r["T"], o["T"].astype(np.float64))
-        assert np.abs(r["T"] - mc["T_gt"]).max() < 0.02
+        assert len(o["inliers"]) > 300 and np.abs(r["T"] - mc["T_gt"]).max() < 0.02
 
 
 def test_ransac_models_bit_exact(ctx, O):
