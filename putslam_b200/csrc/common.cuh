@@ -67,27 +67,37 @@ __device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 
-// returns the distance already scaled by 65536 and added to `low` (an index < 65536): the packed
-// key (dist << 16 | idx) that a single unsigned min turns into a lowest-index-first argmin.
-__device__ __forceinline__ uint32_t ham256_packed(const uint32_t (&q)[8], const uint4& ta, const uint4& tb,
-                                                  uint32_t low) {
+// Packed reduction key:  dist << 22 | train index (12 bits) << 10 | query offset (10 bits).
+// Within one query row the query field is constant, within one train column the train field is
+// constant, so ONE unsigned min over this key is simultaneously the first-argmin over train indices
+// (row reduction) and the first-argmin over query indices (column reduction) -- lowest index wins ties,
+// exactly like OpenCV.  `low` carries the two index fields; the popcount weights are folded into the
+// shifts of an IMAD chain so the adds stay off the LOP3 pipe.
+constexpr int kKeyQBits = 10;
+constexpr int kKeyTBits = 12;
+constexpr int kKeyDShift = kKeyQBits + kKeyTBits;  // 22
+constexpr uint32_t kKeyInvalid = 0x80000000u;      // set in the query field of padding rows: never wins
+
+__device__ __forceinline__ uint32_t ham256_key(const uint32_t (&q)[8], const uint4& ta, const uint4& tb, uint32_t low) {
     uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, x2 = q[2] ^ ta.z, x3 = q[3] ^ ta.w;
     uint32_t x4 = q[4] ^ tb.x, x5 = q[5] ^ tb.y, x6 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
     uint32_t s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
     uint32_t s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
     uint32_t s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
     uint32_t s3 = lop3_xor3(c0, c1, c2), c3 = lop3_maj(c0, c1, c2);
-    // weights folded into the 16-bit shift; mad.lo keeps the adds off the LOP3 pipe
     uint32_t r = low;
-    r = __popc(s2) * 65536u + r;
-    r = __popc(x7) * 65536u + r;
-    r = __popc(s3) * 131072u + r;
-    r = __popc(c3) * 262144u + r;
+    r = __popc(s2) * (1u << kKeyDShift) + r;
+    r = __popc(x7) * (1u << kKeyDShift) + r;
+    r = __popc(s3) * (2u << kKeyDShift) + r;
+    r = __popc(c3) * (4u << kKeyDShift) + r;
     return r;
 }
+__device__ __forceinline__ uint32_t key_dist(uint32_t k) { return k >> kKeyDShift; }
+__device__ __forceinline__ uint32_t key_tidx(uint32_t k) { return (k >> kKeyQBits) & ((1u << kKeyTBits) - 1u); }
+__device__ __forceinline__ uint32_t key_qoff(uint32_t k) { return k & ((1u << kKeyQBits) - 1u); }
 
 __device__ __forceinline__ uint32_t ham256(const uint32_t (&q)[8], const uint4& ta, const uint4& tb) {
-    return ham256_packed(q, ta, tb, 0u) >> 16;
+    return ham256_key(q, ta, tb, 0u) >> kKeyDShift;
 }
 
 // saturating-subtract "Hamming" of Matcher::matchXYZ (reference src/Matcher/matcher.cpp:719-721):

@@ -11,25 +11,25 @@
 // are staged global->shared with TMA bulk copies and read back as warp-broadcast LDS.128; distance =
 // CSA-compressed popcount (common.cuh); argmin = unsigned min over (dist << 16 | index), which
 // resolves ties to the lowest index exactly like OpenCV's first-argmin.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace pslam {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kTT = 128;  // train descriptors per column-reduce sub-tile
 
-// Per-thread query registers.  Query q = qtile_base + j*kThreads + tid; rows beyond nq get an offset
-// that can never win a column minimum.
-template <int RQ>
+// Per-thread query registers.  Query q = qtile_base + j*NT + tid; `off` is the query field of the packed
+// key (offset inside the q-tile, < 1024); rows beyond nq carry kKeyInvalid and can never win a column.
+template <int RQ, int NT>
 struct QueryRegs {
     uint32_t v[RQ][8];
-    uint32_t off[RQ];  // (q index) for valid queries, 0x40000000|q for padding
+    uint32_t off[RQ];
     __device__ __forceinline__ void load(const uint4* __restrict__ query, int nq, int qbase, int tid) {
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
-            int q = qbase + j * kThreads + tid;
+            const int q = qbase + j * NT + tid;
             uint4 a = make_uint4(0, 0, 0, 0), b = a;
             if (q < nq) {
                 a = __ldg(query + 2 * (size_t)q);
@@ -37,50 +37,69 @@ struct QueryRegs {
             }
             v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
             v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
-            off[j] = (q < nq) ? (uint32_t)(q - qbase) : (0x40000000u | (uint32_t)(q - qbase));
+            off[j] = (uint32_t)(j * NT + tid) | ((q < nq) ? 0u : kKeyInvalid);
         }
     }
 };
 
-// One sub-tile: cnt (<= kTT) train descriptors in shared memory vs this thread's RQ queries.
-// rowmin[j]  : running (dist<<16 | train index) for query j
-// partial_w  : this warp's per-train (dist<<16 | query offset) minima, one word per train
-template <int RQ>
-__device__ __forceinline__ void tile_compute(const QueryRegs<RQ>& Q, uint32_t (&rowmin)[RQ],
+// One sub-tile: cnt (<= kTT) train descriptors in shared memory vs this thread's RQ queries, two train
+// descriptors per iteration so that the row update is a single 3-input min.
+//   rowmin[j] : running key for query j (min over train)   partial_w[tt] : this warp's min over its queries
+template <int RQ, int NT>
+__device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_t (&rowmin)[RQ],
                                              const uint4* __restrict__ tile, int cnt, uint32_t tbase,
                                              uint32_t* __restrict__ partial_w, int lane) {
-#pragma unroll 2
-    for (int tt = 0; tt < cnt; ++tt) {
-        const uint4 a = tile[2 * tt], b = tile[2 * tt + 1];
-        const uint32_t tcur = tbase + (uint32_t)tt;
-        uint32_t cmin = 0xffffffffu;
+    int tt = 0;
+#pragma unroll 1
+    for (; tt + 2 <= cnt; tt += 2) {
+        const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1], a1 = tile[2 * tt + 2], b1 = tile[2 * tt + 3];
+        const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits, t1 = t0 + (1u << kKeyQBits);
+        uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
-            uint32_t rp = ham256_packed(Q.v[j], a, b, tcur);
-            rowmin[j] = min(rowmin[j], rp);
-            cmin = min(cmin, rp + (Q.off[j] - tcur));
+            const uint32_t k0 = ham256_key(Q.v[j], a0, b0, Q.off[j] + t0);
+            const uint32_t k1 = ham256_key(Q.v[j], a1, b1, Q.off[j] + t1);
+            rowmin[j] = __vimin3_u32(rowmin[j], k0, k1);
+            c0 = min(c0, k0);
+            c1 = min(c1, k1);
         }
-        cmin = warp_min_u32(cmin);
-        if (lane == 0) partial_w[tt] = cmin;
+        c0 = warp_min_u32(c0);
+        c1 = warp_min_u32(c1);
+        if (lane == 0) *reinterpret_cast<uint2*>(partial_w + tt) = make_uint2(c0, c1);
+    }
+    if (tt < cnt) {
+        const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1];
+        const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits;
+        uint32_t c0 = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) {
+            const uint32_t k0 = ham256_key(Q.v[j], a0, b0, Q.off[j] + t0);
+            rowmin[j] = min(rowmin[j], k0);
+            c0 = min(c0, k0);
+        }
+        c0 = warp_min_u32(c0);
+        if (lane == 0) partial_w[tt] = c0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: one query set vs one train set, spread over the grid by train range (x) and query tile (y).
+// Keys use CTA-local train indices; results go to global memory as (dist << 16 | global index).
 // ------------------------------------------------------------------------------------------------
-template <int RQ>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int RQ, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 bf_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt, int t_per_cta,
                uint32_t* __restrict__ rowmin_g, uint32_t* __restrict__ colmin_g) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4* tile = reinterpret_cast<uint4*>(smem_raw);                                   // t_per_cta * 32 B
-    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + (size_t)t_per_cta * 32);  // kWarps * kTT
-    uint64_t* bar = reinterpret_cast<uint64_t*>(partial + kWarps * kTT);
+    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + (size_t)t_per_cta * 32);  // NW * kTT
+    uint64_t* bar = reinterpret_cast<uint64_t*>(partial + NW * kTT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * t_per_cta;
     const int tcnt = min(t_per_cta, nt - t0);
-    const int qbase = blockIdx.y * (kThreads * RQ);
+    const int qbase = blockIdx.y * (NT * RQ);
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -88,7 +107,7 @@ bf_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
         mbar_expect_tx(bar, (uint32_t)tcnt * 32u);
         tma_load_1d(tile, train + 2 * (size_t)t0, (uint32_t)tcnt * 32u, bar);
     }
-    QueryRegs<RQ> Q;
+    QueryRegs<RQ, NT> Q;
     Q.load(query, nq, qbase, tid);
     uint32_t rowmin[RQ];
 #pragma unroll
@@ -98,24 +117,24 @@ bf_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
 
     for (int s = 0; s < tcnt; s += kTT) {
         const int cnt = min(kTT, tcnt - s);
-        tile_compute<RQ>(Q, rowmin, tile + 2 * s, cnt, (uint32_t)(t0 + s), partial + warp * kTT, lane);
+        tile_compute<RQ, NT>(Q, rowmin, tile + 2 * s, cnt, (uint32_t)s, partial + warp * kTT, lane);
         __syncthreads();
         if (tid < cnt) {
             uint32_t m = partial[tid];
 #pragma unroll
-            for (int w = 1; w < kWarps; ++w) m = min(m, partial[w * kTT + tid]);
-            if (m < 0x40000000u) {  // a real query won this column
-                m += (uint32_t)qbase;  // query offset -> global query index (low 16 bits)
-                if (gridDim.y == 1) colmin_g[t0 + s + tid] = m;
-                else atomicMin(colmin_g + t0 + s + tid, m);
+            for (int w = 1; w < NW; ++w) m = min(m, partial[w * kTT + tid]);
+            if (m < kKeyInvalid) {  // a real query won this column
+                const uint32_t g = (key_dist(m) << 16) | (uint32_t)(qbase + (int)key_qoff(m));
+                if (gridDim.y == 1) colmin_g[t0 + s + tid] = g;
+                else atomicMin(colmin_g + t0 + s + tid, g);
             }
         }
         __syncthreads();
     }
 #pragma unroll
     for (int j = 0; j < RQ; ++j) {
-        int q = qbase + j * kThreads + tid;
-        if (q < nq) atomicMin(rowmin_g + q, rowmin[j]);
+        const int q = qbase + j * NT + tid;
+        if (q < nq) atomicMin(rowmin_g + q, (key_dist(rowmin[j]) << 16) | (uint32_t)(t0 + (int)key_tidx(rowmin[j])));
     }
 }
 
@@ -167,8 +186,8 @@ bf_finalize_kernel(const uint32_t* __restrict__ rowmin_g, const uint32_t* __rest
 // K2': two nearest neighbours per query (ascending distance, lowest train index first on ties).
 // Each CTA handles one train range; per-range top-2 go to a partial buffer and are merged per query.
 // ------------------------------------------------------------------------------------------------
-template <int RQ>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int RQ, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 knn2_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ train, int nt, int t_per_cta,
                  uint2* __restrict__ partial_g /* [gridDim.x][nq] */) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -177,14 +196,14 @@ knn2_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restric
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * t_per_cta;
     const int tcnt = min(t_per_cta, nt - t0);
-    const int qbase = blockIdx.y * (kThreads * RQ);
+    const int qbase = blockIdx.y * (NT * RQ);
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
         mbar_expect_tx(bar, (uint32_t)tcnt * 32u);
         tma_load_1d(tile, train + 2 * (size_t)t0, (uint32_t)tcnt * 32u, bar);
     }
-    QueryRegs<RQ> Q;
+    QueryRegs<RQ, NT> Q;
     Q.load(query, nq, qbase, tid);
     uint32_t m1[RQ], m2[RQ];
 #pragma unroll
@@ -196,15 +215,20 @@ knn2_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restric
         const uint4 a = tile[2 * tt], b = tile[2 * tt + 1];
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
-            const uint32_t rp = ham256_packed(Q.v[j], a, b, (uint32_t)(t0 + tt));
-            m2[j] = min(m2[j], max(m1[j], rp));
-            m1[j] = min(m1[j], rp);
+            const uint32_t k = ham256_key(Q.v[j], a, b, (uint32_t)tt << kKeyQBits);
+            m2[j] = min(m2[j], max(m1[j], k));
+            m1[j] = min(m1[j], k);
         }
     }
 #pragma unroll
     for (int j = 0; j < RQ; ++j) {
-        int q = qbase + j * kThreads + tid;
-        if (q < nq) partial_g[(size_t)blockIdx.x * nq + q] = make_uint2(m1[j], m2[j]);
+        const int q = qbase + j * NT + tid;
+        if (q < nq) {
+            const uint32_t g1 = (key_dist(m1[j]) << 16) | (uint32_t)(t0 + (int)key_tidx(m1[j]));
+            const uint32_t g2 = (m2[j] == 0xffffffffu) ? 0xffffffffu
+                                                       : ((key_dist(m2[j]) << 16) | (uint32_t)(t0 + (int)key_tidx(m2[j])));
+            partial_g[(size_t)blockIdx.x * nq + q] = make_uint2(g1, g2);
+        }
     }
 }
 
@@ -233,7 +257,7 @@ __global__ void knn2_merge_kernel(const uint2* __restrict__ partial_g, int npart
 // registers, column minima reduced per sub-tile into shared memory, then the cross-check count.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStages = 4;
-constexpr int kMaxKfDesc = 4096;  // descriptors per keyframe supported by the shared-memory column array
+constexpr int kMaxKfDesc = 1 << kKeyTBits;  // 4096 descriptors per keyframe (train field of the key)
 
 struct SweepCursor {  // walks (keyframe, tile) items of this CTA in order
     int kf, tile, ntiles;
@@ -242,7 +266,7 @@ struct SweepCursor {  // walks (keyframe, tile) items of this CTA in order
 };
 
 __device__ __forceinline__ void cursor_load(SweepCursor& c, const int64_t* __restrict__ kf_off, int n_kf) {
-    while (c.kf < n_kf) {  // skip empty keyframes (they score 0, written by the consumer path)
+    while (c.kf < n_kf) {  // skip empty keyframes (they score 0, written up front)
         c.off = kf_off[c.kf];
         c.cnt = (int)(kf_off[c.kf + 1] - c.off);
         c.ntiles = (c.cnt + kTT - 1) / kTT;
@@ -258,14 +282,15 @@ __device__ __forceinline__ void cursor_next(SweepCursor& c, const int64_t* __res
     }
 }
 
-template <int RQ>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int RQ, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db,
                 const int64_t* __restrict__ kf_off, int n_kf, int tau, int* __restrict__ scores) {
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4* stages = reinterpret_cast<uint4*>(smem_raw);                                        // kStages*kTT*32
-    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + kStages * kTT * 32);            // 2*kWarps*kTT
-    uint32_t* colmin = partial + 2 * kWarps * kTT;                                             // kMaxKfDesc
+    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + kStages * kTT * 32);            // 2*NW*kTT
+    uint32_t* colmin = partial + 2 * NW * kTT;                                                 // kMaxKfDesc
     uint64_t* bars = reinterpret_cast<uint64_t*>(colmin + kMaxKfDesc);                         // kStages
     int* score_s = reinterpret_cast<int*>(bars + kStages);
 
@@ -275,7 +300,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
         fence_mbar_init();
         *score_s = 0;
     }
-    QueryRegs<RQ> Q;
+    QueryRegs<RQ, NT> Q;
     Q.load(query, nq, 0, tid);
     uint32_t rowmin[RQ];
 #pragma unroll
@@ -283,7 +308,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
     __syncthreads();
 
     // keyframes with no descriptors never enter the tile stream: score them here
-    for (int kf = blockIdx.x * kThreads + tid; kf < n_kf; kf += gridDim.x * kThreads)
+    for (int kf = blockIdx.x * NT + tid; kf < n_kf; kf += gridDim.x * NT)
         if (kf_off[kf + 1] == kf_off[kf]) scores[kf] = 0;
 
     SweepCursor prod, cons;
@@ -316,14 +341,14 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
         }
         const int tbase = cons.tile * kTT;
         const int cnt = min(kTT, cons.cnt - tbase);
-        uint32_t* pbuf = partial + (it & 1) * (kWarps * kTT);
+        uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
         mbar_wait(bars + stage, phase);
-        tile_compute<RQ>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        tile_compute<RQ, NT>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
         __syncthreads();
         if (tid < cnt) {
             uint32_t m = pbuf[tid];
 #pragma unroll
-            for (int w = 1; w < kWarps; ++w) m = min(m, pbuf[w * kTT + tid]);
+            for (int w = 1; w < NW; ++w) m = min(m, pbuf[w * kTT + tid]);
             colmin[tbase + tid] = m;
         }
         const bool last = (cons.tile + 1 == cons.ntiles);
@@ -332,10 +357,9 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
             int c = 0;
 #pragma unroll
             for (int j = 0; j < RQ; ++j) {
-                const uint32_t rp = rowmin[j];
-                const uint32_t t = rp & 0xffffu;
-                const bool valid = Q.off[j] < 0x40000000u;
-                if (valid && (colmin[t] & 0xffffu) == Q.off[j] && (int)(rp >> 16) <= tau) ++c;
+                const uint32_t rk = rowmin[j];
+                // the winner of the column this row points at must be this very (dist, t, q) key
+                if (Q.off[j] < kKeyInvalid && colmin[key_tidx(rk)] == rk && (int)key_dist(rk) <= tau) ++c;
                 rowmin[j] = 0xffffffffu;
             }
             c = (int)warp_add_u32((uint32_t)c);
@@ -418,7 +442,8 @@ __global__ void lc_merge_topk_kernel(const int* __restrict__ gathered, int n_pai
 // ------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
-static int pick_rq(int nq) { return nq <= kThreads ? 1 : (nq <= 2 * kThreads ? 2 : 4); }
+constexpr int kNT = 256;   // threads per CTA of the matching kernels
+static int pick_rq(int nq) { return nq <= kNT ? 1 : (nq <= 2 * kNT ? 2 : 4); }
 
 static int pick_t_per_cta(int nt, int qtiles, int sm_count) {
     // aim for about two CTAs per SM, at least 16 and at most 256 train descriptors per CTA
@@ -436,15 +461,15 @@ cudaError_t launch_bf_mutual(const uint8_t* d_query, int nq, const uint8_t* d_tr
     if ((e = cudaMemsetAsync(d_rowmin, 0xff, sizeof(uint32_t) * (size_t)nq, st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d_colmin, 0xff, sizeof(uint32_t) * (size_t)nt, st)) != cudaSuccess) return e;
     const int rq = pick_rq(nq);
-    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int qtiles = (nq + kNT * rq - 1) / (kNT * rq);
     const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
     dim3 grid((nt + tpc - 1) / tpc, qtiles);
-    const size_t smem = (size_t)tpc * 32 + sizeof(uint32_t) * kWarps * kTT + 16;
+    const size_t smem = (size_t)tpc * 32 + sizeof(uint32_t) * (kNT / 32) * kTT + 16;
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* t4 = reinterpret_cast<const uint4*>(d_train);
-    if (rq == 1) bf_tile_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
-    else if (rq == 2) bf_tile_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
-    else bf_tile_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    if (rq == 1) bf_tile_kernel<1, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else if (rq == 2) bf_tile_kernel<2, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else bf_tile_kernel<4, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
     bf_finalize_kernel<<<1, 1024, 0, st>>>(d_rowmin, d_colmin, nq, cap, d_out);
     if (launches) *launches += 2;
     return cudaGetLastError();
@@ -452,7 +477,7 @@ cudaError_t launch_bf_mutual(const uint8_t* d_query, int nq, const uint8_t* d_tr
 
 int knn2_parts(int nq, int nt, int sm_count) {
     const int rq = pick_rq(nq);
-    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int qtiles = (nq + kNT * rq - 1) / (kNT * rq);
     const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
     return (nt + tpc - 1) / tpc;
 }
@@ -460,16 +485,16 @@ int knn2_parts(int nq, int nt, int sm_count) {
 cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, uint2* d_partial, int* d_idx,
                         float* d_dist, int sm_count, cudaStream_t st, int* launches) {
     const int rq = pick_rq(nq);
-    const int qtiles = (nq + kThreads * rq - 1) / (kThreads * rq);
+    const int qtiles = (nq + kNT * rq - 1) / (kNT * rq);
     const int tpc = pick_t_per_cta(nt, qtiles, sm_count);
     dim3 grid((nt + tpc - 1) / tpc, qtiles);
     const size_t smem = (size_t)tpc * 32 + 16;
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* t4 = reinterpret_cast<const uint4*>(d_train);
     if (nt > 0) {
-        if (rq == 1) knn2_tile_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
-        else if (rq == 2) knn2_tile_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
-        else knn2_tile_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        if (rq == 1) knn2_tile_kernel<1, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        else if (rq == 2) knn2_tile_kernel<2, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
+        else knn2_tile_kernel<4, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_partial);
         if (launches) *launches += 1;
     }
     knn2_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_partial, nt > 0 ? (int)grid.x : 0, nq, d_idx, d_dist);
@@ -477,18 +502,29 @@ cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, 
     return cudaGetLastError();
 }
 
-size_t lc_sweep_smem() {
-    return (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * kWarps * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
+// sweep variants: (queries per thread, threads per CTA).  PSLAM_SWEEP_VARIANT=1 selects 8 x 128.
+static int sweep_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PSLAM_SWEEP_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+template <int NT>
+static size_t lc_sweep_smem_nt() {
+    return (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * (NT / 32) * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
 }
 int lc_max_kf_desc() { return kMaxKfDesc; }
-int lc_max_query() { return kThreads * 4; }
+int lc_max_query() { return 1024; }
 
 cudaError_t lc_sweep_configure() {
     cudaError_t e;
-    const int smem = (int)lc_sweep_smem();
-    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+#define CFG(RQ, NT)                                                                                              \
+    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<RQ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                  (int)lc_sweep_smem_nt<NT>())) != cudaSuccess) return e;
+    CFG(1, 256) CFG(2, 256) CFG(4, 256) CFG(8, 128)
+#undef CFG
     return cudaSuccess;
 }
 
@@ -496,14 +532,20 @@ cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db,
                             int tau, int* d_scores, int sm_count, cudaStream_t st, int* launches) {
     if (n_kf <= 0) return cudaSuccess;
     const int rq = pick_rq(nq);
-    int grid = 2 * sm_count;
-    if (grid > n_kf) grid = n_kf;
-    const size_t smem = lc_sweep_smem();
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
-    if (rq == 1) lc_sweep_kernel<1><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-    else if (rq == 2) lc_sweep_kernel<2><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-    else lc_sweep_kernel<4><<<grid, kThreads, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    if (rq == 4 && sweep_variant() == 1) {
+        int grid = 4 * sm_count;
+        if (grid > n_kf) grid = n_kf;
+        lc_sweep_kernel<8, 128><<<grid, 128, lc_sweep_smem_nt<128>(), st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    } else {
+        int grid = 2 * sm_count;
+        if (grid > n_kf) grid = n_kf;
+        const size_t smem = lc_sweep_smem_nt<256>();
+        if (rq == 1) lc_sweep_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+        else if (rq == 2) lc_sweep_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+        else lc_sweep_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    }
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
