@@ -1,0 +1,288 @@
+// pslam_adapter.cpp -- see pslam_adapter.h.  Pure host C++; every numeric stage goes through the C ABI.
+#include "pslam_adapter.h"
+
+#include <algorithm>
+#include <cmath>
+#include <ctime>
+#include <iostream>
+#include <memory>
+#include <set>
+
+namespace putslam_b200 {
+
+static void logError(pslam_ctx* c, const char* where, int code) {
+    std::cerr << "[putslam_b200] " << where << " failed (" << code << "): " << (c ? pslam_last_error(c) : "no context")
+              << std::endl;
+}
+
+Device::Device(int device) : device_(device) {}
+Device::~Device() {
+    if (ctx_) pslam_ctx_destroy(ctx_);
+}
+pslam_ctx* Device::ctx() {
+    if (!ctx_) {
+        const int r = pslam_ctx_create(device_, &ctx_);
+        if (r != PSLAM_OK) {
+            std::cerr << "[putslam_b200] pslam_ctx_create(" << device_ << ") failed (" << r
+                      << "): no usable sm_100 GPU and no CPU fallback" << std::endl;
+            ctx_ = nullptr;
+        }
+    }
+    return ctx_;
+}
+Device& defaultDevice() {
+    static Device d(0);
+    return d;
+}
+
+static pslam_camera cameraFrom(const cv::Mat& K, const cv::Mat* dist) {
+    pslam_camera cam;
+    cam.fx = K.at<float>(0, 0); cam.fy = K.at<float>(1, 1); cam.cx = K.at<float>(0, 2); cam.cy = K.at<float>(1, 2);
+    for (int i = 0; i < 5; ++i) cam.dist[i] = 0.f;
+    if (dist && !dist->empty()) {
+        const int n = std::min(5, dist->rows * dist->cols);
+        for (int i = 0; i < n; ++i) cam.dist[i] = dist->ptr<float>(0)[i];
+    }
+    return cam;
+}
+
+// A cv::Mat with non-contiguous rows is packed first ("check isContinuous(), else copy").
+static const uint8_t* contiguousBytes(const cv::Mat& m, size_t rowBytes, std::vector<uint8_t>& tmp) {
+    if (m.empty()) return nullptr;
+    if (m.isContinuous()) return m.data;
+    tmp.resize(rowBytes * (size_t)m.rows);
+    for (int r = 0; r < m.rows; ++r) std::memcpy(tmp.data() + rowBytes * r, m.ptr<uint8_t>(r), rowBytes);
+    return tmp.data();
+}
+
+// ---- RGBD -----------------------------------------------------------------------------------------
+namespace RGBD {
+static std::vector<cv::Point2f> undistortImpl(const std::vector<cv::Point2f>& pts, const cv::Mat& K, const cv::Mat& dist) {
+    if (pts.empty()) return std::vector<cv::Point2f>();   // RGBD.cpp:259-260
+    pslam_ctx* c = defaultDevice().ctx();
+    std::vector<cv::Point2f> out(pts.size());
+    pslam_camera cam = cameraFrom(K, &dist);
+    // undistortion needs no depth: a 1x1 dummy image keeps the entry point single
+    uint16_t dummy = 0;
+    std::vector<float> xyz(3 * pts.size());
+    const int r = c ? pslam_backproject(c, &pts[0].x, (int)pts.size(), &dummy, 1, 1, 1, &cam, 1, 1.0, &out[0].x, xyz.data(),
+                                        nullptr, nullptr, nullptr)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "removeImageDistortion", r); return std::vector<cv::Point2f>(); }
+    return out;
+}
+std::vector<cv::Point2f> removeImageDistortion(std::vector<cv::Point2f>& features, cv::Mat cameraMatrix, cv::Mat distCoeffs) {
+    return undistortImpl(features, cameraMatrix, distCoeffs);
+}
+std::vector<cv::Point2f> removeImageDistortion(std::vector<cv::KeyPoint>& features, cv::Mat cameraMatrix, cv::Mat distCoeffs) {
+    std::vector<cv::Point2f> pts(features.size());   // cv::KeyPoint::convert
+    for (size_t i = 0; i < features.size(); ++i) pts[i] = features[i].pt;
+    return undistortImpl(pts, cameraMatrix, distCoeffs);
+}
+std::vector<Eigen::Vector3f> keypoints2Dto3D(std::vector<cv::Point2f> undistortedFeatures2D, cv::Mat depthImage,
+                                             cv::Mat cameraMatrix, double depthImageScale, int startingID) {
+    const int n = (int)undistortedFeatures2D.size() - startingID;
+    std::vector<Eigen::Vector3f> features3D((size_t)std::max(0, n));
+    if (n <= 0) return features3D;
+    pslam_ctx* c = defaultDevice().ctx();
+    pslam_camera cam = cameraFrom(cameraMatrix, nullptr);
+    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
+    const int r = c ? pslam_backproject(c, &undistortedFeatures2D[(size_t)startingID].x, n, depthImage.ptr<uint16_t>(0),
+                                        depthImage.cols, depthImage.rows, stride, &cam, 0, depthImageScale, nullptr,
+                                        features3D[0].data(), nullptr, nullptr, nullptr)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) logError(c, "keypoints2Dto3D", r);
+    return features3D;
+}
+}  // namespace RGBD
+
+// ---- RANSAC ---------------------------------------------------------------------------------------
+RANSAC::RANSAC(parameters p, cv::Mat cameraMatrix) : RANSACParams(p) {
+    seed_ = (uint64_t)time((time_t*)0);   // the reference seeds from the clock (RANSAC.cpp:13); use setSeed for reproducibility
+    RANSACParams.iterationCount = 487;    // computeRANSACIteration(0.20), RANSAC.cpp:30
+    if (!cameraMatrix.empty()) {
+        fx_ = cameraMatrix.at<float>(0, 0); fy_ = cameraMatrix.at<float>(1, 1);
+        cx_ = cameraMatrix.at<float>(0, 2); cy_ = cameraMatrix.at<float>(1, 2);
+    }
+}
+
+static pslam_ransac_params toAbi(const RANSAC::parameters& p, float fx, float fy, float cx, float cy) {
+    pslam_ransac_params a;
+    a.error_version = p.errorVersion;
+    a.inlier_threshold_euclidean = p.inlierThresholdEuclidean;
+    a.inlier_threshold_reprojection = p.inlierThresholdReprojection;
+    a.minimal_inlier_ratio_threshold = p.minimalInlierRatioThreshold;
+    a.minimal_number_of_matches = p.minimalNumberOfMatches;
+    a.used_pairs = p.usedPairs;
+    a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy;
+    return a;
+}
+
+Eigen::Matrix4f RANSAC::estimateTransformation(std::vector<Eigen::Vector3f> prevFeatures, std::vector<Eigen::Vector3f> features,
+                                               std::vector<cv::DMatch> matches, std::vector<cv::DMatch>& bestInlierMatches) {
+    Eigen::Matrix4f T = Eigen::Matrix4f::Identity();
+    const int m = (int)matches.size();
+    std::vector<int> mq((size_t)m), mt((size_t)m), inl((size_t)std::max(1, m));
+    for (int k = 0; k < m; ++k) { mq[k] = matches[k].queryIdx; mt[k] = matches[k].trainIdx; }
+    int nInl = 0;
+    pslam_ransac_params a = toAbi(RANSACParams, fx_, fy_, cx_, cy_);
+    pslam_ctx* c = defaultDevice().ctx();
+    const int r = c ? pslam_ransac_estimate(c, prevFeatures.empty() ? nullptr : prevFeatures[0].data(), (int)prevFeatures.size(),
+                                            features.empty() ? nullptr : features[0].data(), (int)features.size(), mq.data(),
+                                            mt.data(), m, &a, seed_, numHyp_, T.data(), inl.data(), &nInl, &bestRatio_, &hypUsed_)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) {   // reference failure value: identity + no inliers (RANSAC.cpp:78-79,162-163)
+        logError(c, "RANSAC::estimateTransformation", r);
+        bestInlierMatches.clear();
+        return Eigen::Matrix4f::Identity();
+    }
+    bestInlierMatches.clear();
+    for (int i = 0; i < nInl; ++i) bestInlierMatches.push_back(matches[(size_t)inl[i]]);
+    return T;
+}
+
+double RANSAC::pointInlierRatio(std::vector<cv::DMatch>& inlierMatches, std::vector<cv::DMatch>& allMatches) {
+    std::set<int> inlier, all;   // RANSAC.h:56-66 verbatim semantics
+    for (auto& m : allMatches) all.insert(m.trainIdx);
+    for (auto& in : inlierMatches) inlier.insert(in.trainIdx);
+    return double(inlier.size()) / double(all.size());
+}
+
+// ---- Matcher ---------------------------------------------------------------------------------------
+std::vector<cv::DMatch> MatcherB200::performMatching(cv::Mat prevDescriptors, cv::Mat descriptors) {
+    std::vector<cv::DMatch> out;
+    const int nq = prevDescriptors.rows, nt = descriptors.rows;
+    if (nq == 0 || nt == 0) return out;
+    std::vector<uint8_t> tq, tt;
+    const uint8_t* q = contiguousBytes(prevDescriptors, (size_t)prevDescriptors.cols, tq);
+    const uint8_t* t = contiguousBytes(descriptors, (size_t)descriptors.cols, tt);
+    const int cap = std::min(nq, nt);
+    std::vector<int> oq((size_t)cap), ot((size_t)cap);
+    std::vector<float> od((size_t)cap);
+    int n = 0;
+    pslam_ctx* c = dev_.ctx();
+    const int r = c ? pslam_match_bf_mutual(c, q, nq, t, nt, prevDescriptors.cols, oq.data(), ot.data(), od.data(), &n)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "performMatching", r); return out; }
+    out.reserve((size_t)n);
+    for (int i = 0; i < n; ++i) out.push_back(cv::DMatch(oq[i], ot[i], 0, od[i]));   // imgIdx = 0 like BFMatcher
+    return out;
+}
+
+std::vector<cv::DMatch> MatcherB200::performMatchingRatio(cv::Mat prevDescriptors, cv::Mat descriptors, float ratio) {
+    std::vector<cv::DMatch> out;
+    const int nq = prevDescriptors.rows, nt = descriptors.rows;
+    if (nq == 0 || nt < 2) return out;
+    std::vector<uint8_t> tq, tt;
+    const uint8_t* q = contiguousBytes(prevDescriptors, (size_t)prevDescriptors.cols, tq);
+    const uint8_t* t = contiguousBytes(descriptors, (size_t)descriptors.cols, tt);
+    std::vector<int> idx(2 * (size_t)nq);
+    std::vector<float> dist(2 * (size_t)nq);
+    pslam_ctx* c = dev_.ctx();
+    const int r = c ? pslam_match_knn2(c, q, nq, t, nt, prevDescriptors.cols, idx.data(), dist.data()) : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "performMatchingRatio", r); return out; }
+    for (int i = 0; i < nq; ++i)
+        if (dist[2 * i] < ratio * dist[2 * i + 1]) out.push_back(cv::DMatch(i, idx[2 * i], 0, dist[2 * i]));
+    return out;
+}
+
+// predicted pyramid level, all double, host libm -- matcher.cpp:641-651 / 682-692, matcher.h:26-28
+static int predictedLevel(int detLevel, double detDist, double curDist) {
+    static const double scaleFactor = 1.2;
+    static const double logScaleFactor = std::log(scaleFactor);
+    const int nLevels = 8;
+    double detLevelScaleFactor = pow(scaleFactor, detLevel);
+    double curLevelScaleFactor = detLevelScaleFactor * detDist / curDist;
+    int curLevel = (int)std::ceil(std::log(curLevelScaleFactor) / logScaleFactor);
+    curLevel = std::max(0, curLevel);
+    curLevel = std::min(nLevels - 1, curLevel);
+    return curLevel;
+}
+
+double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescriptors,
+                                 std::vector<Eigen::Vector3f>& currentPoseFeatures3D,
+                                 std::vector<cv::KeyPoint>& currentPoseKeyPoints, std::vector<double>& currentPoseDetDists,
+                                 double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch, int computationNumber,
+                                 const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,
+                                 Eigen::Matrix4f& estimatedTransformation, std::vector<cv::DMatch>& matches,
+                                 std::vector<cv::DMatch>& inlierMatches, bool xorDistance) {
+    matches.clear();
+    inlierMatches.clear();
+    if (computationNumber > 1) {   // matcher.cpp:619-622
+        matchingXYZSphereRadius += 0.02 * (computationNumber - 1);
+        matchingXYZacceptRatioOfBestMatch = std::max(0.1, matchingXYZacceptRatioOfBestMatch - 0.05 * (computationNumber - 1));
+    }
+    const int N = (int)currentPoseKeyPoints.size(), M = (int)map.octave.size();
+    std::vector<int> curLevels((size_t)N), mapLevels((size_t)M);
+    for (int i = 0; i < N; ++i) {   // matcher.cpp:639-651: curDist = Vector3f::norm() (float) widened
+        const float x = currentPoseFeatures3D[i][0], y = currentPoseFeatures3D[i][1], z = currentPoseFeatures3D[i][2];
+        const float yy = y * y, zz = z * z;
+        const double curDist = std::sqrt(x * x + (yy + zz));   // float expression -> sqrtf -> double
+        curLevels[i] = predictedLevel(currentPoseKeyPoints[i].octave, currentPoseDetDists[i], curDist);
+    }
+    std::vector<float> mapXyz(3 * (size_t)M);
+    for (int j = 0; j < M; ++j) {   // matcher.cpp:682-692 (double norm of the double position), :665 (cast to float)
+        const double px = map.xyz[3 * j], py = map.xyz[3 * j + 1], pz = map.xyz[3 * j + 2];
+        const double curDist = std::sqrt(px * px + py * py + pz * pz);
+        mapLevels[j] = predictedLevel(map.octave[j], map.detDist[j], curDist);
+        mapXyz[3 * j] = (float)px; mapXyz[3 * j + 1] = (float)py; mapXyz[3 * j + 2] = (float)pz;
+    }
+    std::vector<uint8_t> tm, tc;
+    const uint8_t* md = contiguousBytes(map.descriptors, 32, tm);
+    const uint8_t* cd = contiguousBytes(currentPoseDescriptors, 32, tc);
+    RANSAC::parameters rp = ransacParams;
+    rp.errorVersion = rp.errorVersionMap;   // matcher.cpp:760-761
+    float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+    if (!cameraMatrix.empty()) {
+        fx = cameraMatrix.at<float>(0, 0); fy = cameraMatrix.at<float>(1, 1);
+        cx = cameraMatrix.at<float>(0, 2); cy = cameraMatrix.at<float>(1, 2);
+    }
+    pslam_ransac_params a = toAbi(rp, fx, fy, cx, cy);
+    int cap = std::max(4096, 4 * std::max(M, N));
+    std::vector<int> mq, mt, inl;
+    std::vector<float> mdist;
+    pslam_frame_result res;
+    pslam_ctx* c = dev_.ctx();
+    int r = PSLAM_ERR_NO_DEVICE;
+    for (int attempt = 0; c && attempt < 6; ++attempt) {   // the reference's match vector is unbounded: grow on truncation
+        mq.resize((size_t)cap); mt.resize((size_t)cap); mdist.resize((size_t)cap); inl.resize((size_t)cap);
+        r = pslam_frame_to_map(c, mapXyz.data(), md, mapLevels.data(), M, &currentPoseFeatures3D[0][0], cd, curLevels.data(), N,
+                               matchingXYZSphereRadius, matchingXYZacceptRatioOfBestMatch, xorDistance ? 1 : 0, &a, seed_, numHyp_,
+                               cap, mq.data(), mt.data(), mdist.data(), inl.data(), &res);
+        if (r != PSLAM_ERR_CAPACITY) break;
+        cap = res.n_matches + 16;
+    }
+    estimatedTransformation = Eigen::Matrix4f::Identity();
+    if (r != PSLAM_OK) { logError(c, "matchXYZ", r); return -1.0; }
+    if (res.n_matches <= 0) return -1.0;   // matcher.cpp:755-756
+    for (int k = 0; k < res.n_matches; ++k) matches.push_back(cv::DMatch(mq[k], mt[k], -1, mdist[k]));
+    for (int k = 0; k < res.n_inliers; ++k) inlierMatches.push_back(matches[(size_t)inl[k]]);
+    std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
+    return RANSAC::pointInlierRatio(inlierMatches, matches);   // matcher.cpp:797
+}
+
+// ---- Kabsch ----------------------------------------------------------------------------------------
+Mat34& KabschEst::computeTransformation(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB) {
+    transformation.setIdentity();
+    const int n = (int)setA.rows();
+    if (n == 0) return transformation;   // kabschEst.cpp:28
+    std::vector<double> A(3 * (size_t)n), B(3 * (size_t)n);   // Eigen is column-major: (r, c) -> row-major points
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < 3; ++c) { A[3 * r + c] = setA(r, c); B[3 * r + c] = setB(r, c); }
+    int off[2] = {0, n};
+    double T[12];
+    pslam_ctx* c = defaultDevice().ctx();
+    const int r = c ? pslam_kabsch_batch(c, A.data(), B.data(), off, 1, T) : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "KabschEst::computeTransformation", r); return transformation; }
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 3; ++row) transformation.m[4 * col + row] = T[3 * col + row];
+    return transformation;
+}
+
+static std::unique_ptr<KabschEst> kabsch;
+TransformEst* createKabschEstimator(void) {
+    kabsch.reset(new KabschEst());
+    return kabsch.get();
+}
+
+}  // namespace putslam_b200

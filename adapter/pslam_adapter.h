@@ -1,0 +1,136 @@
+// pslam_adapter.h -- C++ host side of the drop-in: PUTSLAM's own hot-path interfaces, re-implemented
+// on top of the C ABI (include/pslam_b200.h).  Same class / function names, argument meaning, ownership
+// and failure conventions as the reference, inside namespace putslam_b200 so that both can be linked
+// into one binary during a migration (INTEGRATION.md shows the three-line change per call site).
+//
+//   putslam_b200::RANSAC                  <->  class RANSAC               include/putslam/TransformEst/RANSAC.h:20-198
+//   putslam_b200::MatcherB200::performMatching  <->  MatcherOpenCV::performMatching  src/Matcher/matcherOpenCV.cpp:198-206
+//   putslam_b200::MatcherB200::matchXYZCore     <->  loop nest of Matcher::matchXYZ  src/Matcher/matcher.cpp:606-767
+//   putslam_b200::RGBD::*                 <->  namespace RGBD             include/putslam/RGBD/RGBD.h:38-73
+//   putslam_b200::KabschEst               <->  putslam::KabschEst         include/putslam/TransformEst/kabschEst.h:21-41
+//
+// Error convention: the reference has no error codes on this path; failure is "identity
+// transform + no inliers" / "no matches".  Any C-ABI error is logged to std::cerr and mapped to exactly
+// those values.  There is no CPU fallback.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../include/pslam_b200.h"
+#include "shim/pslam_shim_types.h"
+
+namespace putslam_b200 {
+
+// One device context per Matcher instance (tracking thread / loop-closure thread), created lazily.
+class Device {
+public:
+    explicit Device(int device = 0);
+    ~Device();
+    pslam_ctx* ctx();
+    Device(const Device&) = delete;
+    Device& operator=(const Device&) = delete;
+private:
+    int device_;
+    pslam_ctx* ctx_ = nullptr;
+};
+Device& defaultDevice();   // process-wide context used by the free functions and by RANSAC objects
+
+namespace RGBD {
+// include/putslam/RGBD/RGBD.h:38-73 -- identical signatures (arguments by value like the reference)
+std::vector<cv::Point2f> removeImageDistortion(std::vector<cv::Point2f>& features, cv::Mat cameraMatrix, cv::Mat distCoeffs);
+std::vector<cv::Point2f> removeImageDistortion(std::vector<cv::KeyPoint>& features, cv::Mat cameraMatrix, cv::Mat distCoeffs);
+std::vector<Eigen::Vector3f> keypoints2Dto3D(std::vector<cv::Point2f> undistortedFeatures2D, cv::Mat depthImage,
+                                             cv::Mat cameraMatrix, double depthImageScale, int startingID = 0);
+}  // namespace RGBD
+
+class RANSAC {
+public:
+    enum ERROR_VERSION { EUCLIDEAN_ERROR, REPROJECTION_ERROR, EUCLIDEAN_AND_REPROJECTION_ERROR, MAHALANOBIS_ERROR, ADAPTIVE_ERROR };
+    struct parameters {   // field for field RANSAC::parameters (RANSAC.h:23-31)
+        int verbose;
+        int errorVersion, errorVersionVO, errorVersionMap;
+        double inlierThresholdEuclidean, inlierThresholdReprojection, inlierThresholdMahalanobis;
+        double minimalInlierRatioThreshold;
+        int minimalNumberOfMatches;
+        int usedPairs;
+        int iterationCount;
+    };
+    RANSAC(parameters RANSACParameters, cv::Mat cameraMatrix = cv::Mat());
+
+    Eigen::Matrix4f estimateTransformation(std::vector<Eigen::Vector3f> prevFeatures, std::vector<Eigen::Vector3f> features,
+                                           std::vector<cv::DMatch> matches, std::vector<cv::DMatch>& inlierMatches);
+    static double pointInlierRatio(std::vector<cv::DMatch>& inlierMatches, std::vector<cv::DMatch>& allMatches);
+
+    // Additions (defaults keep the reference's behaviour): the reference seeds rand() with time(0) per
+    // object (RANSAC.cpp:13); here the seed is explicit and the sample stream is counter-based.
+    void setSeed(uint64_t seed) { seed_ = seed; }
+    void setFixedHypotheses(int n) { numHyp_ = n; }   // 0 = the reference's adaptive bound (487, shrinking)
+    int hypothesesUsed() const { return hypUsed_; }
+    double bestInlierRatio() const { return bestRatio_; }
+private:
+    parameters RANSACParams;
+    float fx_ = 517.3f, fy_ = 516.5f, cx_ = 318.6f, cy_ = 255.3f;
+    uint64_t seed_;
+    int numHyp_ = 0, hypUsed_ = 0;
+    double bestRatio_ = 0.0;
+};
+
+// Matching half of the Matcher facade.  In a PUTSLAM build this is used as
+//   class MatcherB200 : public MatcherOpenCV { std::vector<cv::DMatch> performMatching(cv::Mat a, cv::Mat b) override
+//       { return core.performMatching(a, b); } putslam_b200::MatcherB200 core; };
+class MatcherB200 {
+public:
+    explicit MatcherB200(int device = 0) : dev_(device) {}
+    // MatcherOpenCV::performMatching (src/Matcher/matcherOpenCV.cpp:198-206), NORM_HAMMING + crossCheck
+    std::vector<cv::DMatch> performMatching(cv::Mat prevDescriptors, cv::Mat descriptors);
+    // knnMatch(k=2) + Lowe ratio (north_star extension): matches with d1 < ratio * d2
+    std::vector<cv::DMatch> performMatchingRatio(cv::Mat prevDescriptors, cv::Mat descriptors, float ratio);
+
+    struct MapSide {   // SoA view of std::vector<MapFeature> (one ExtendedDescriptor per feature, SURVEY B#13)
+        std::vector<double> xyz;        // M x 3, MapFeature.position (double)
+        cv::Mat descriptors;            // M x 32 CV_8U
+        std::vector<int> octave;        // ExtendedDescriptor.octave
+        std::vector<double> detDist;    // ExtendedDescriptor.detDist
+    };
+    // The loop nest + RANSAC of Matcher::matchXYZ (src/Matcher/matcher.cpp:617-767).  Returns what matchXYZ returns
+    // (pointInlierRatio, or -1.0 when there are no matches); fills matches / inlierMatches / estimatedTransformation.
+    double matchXYZCore(const MapSide& map, cv::Mat currentPoseDescriptors, std::vector<Eigen::Vector3f>& currentPoseFeatures3D,
+                        std::vector<cv::KeyPoint>& currentPoseKeyPoints, std::vector<double>& currentPoseDetDists,
+                        double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch, int computationNumber,
+                        const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix, Eigen::Matrix4f& estimatedTransformation,
+                        std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches, bool xorDistance = false);
+    void setSeed(uint64_t s) { seed_ = s; }
+    void setFixedHypotheses(int n) { numHyp_ = n; }
+private:
+    Device dev_;
+    uint64_t seed_ = 0x5eed5eedULL;
+    int numHyp_ = 0;
+};
+
+// putslam::TransformEst / KabschEst (transformEst.h:16-26, kabschEst.h:21-41).  Mat34 is
+// Eigen::Transform<double,3,Affine>; its 4x4 column-major matrix is exposed here as double[16].
+struct Mat34 {
+    double m[16];
+    Mat34() { setIdentity(); }
+    void setIdentity() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+    double operator()(int r, int c) const { return m[4 * c + r]; }
+};
+class TransformEst {
+public:
+    virtual const std::string& getName() const = 0;
+    virtual Mat34& computeTransformation(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB) = 0;
+    virtual ~TransformEst() {}
+protected:
+    Mat34 transformation;
+};
+class KabschEst : public TransformEst {
+public:
+    KabschEst() : name("Kabsch Estimator") {}
+    const std::string& getName() const override { return name; }
+    Mat34& computeTransformation(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB) override;
+private:
+    const std::string name;
+};
+TransformEst* createKabschEstimator(void);   // kabschEst.cpp:70-73: singleton, a second call replaces the first
+
+}  // namespace putslam_b200

@@ -1,0 +1,115 @@
+// selftest.cpp -- drives the C++ adapter exactly the way PUTSLAM's call sites do (Matcher::match,
+// Matcher::matchXYZ, demoKabsch) on inputs written by tests/test_gpu_adapter.py, and writes the results
+// back as raw arrays for comparison with the oracle.  usage: adapter_selftest <dir>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "pslam_adapter.h"
+
+using namespace putslam_b200;
+
+static std::string g_dir;
+template <typename T>
+static std::vector<T> rd(const std::string& name) {
+    std::ifstream f(g_dir + "/" + name, std::ios::binary | std::ios::ate);
+    if (!f) { std::cerr << "missing " << name << std::endl; exit(2); }
+    const size_t n = (size_t)f.tellg();
+    std::vector<T> v(n / sizeof(T));
+    f.seekg(0);
+    f.read((char*)v.data(), (std::streamsize)n);
+    return v;
+}
+template <typename T>
+static void wr(const std::string& name, const std::vector<T>& v) {
+    std::ofstream f(g_dir + "/" + name, std::ios::binary);
+    f.write((const char*)v.data(), (std::streamsize)(v.size() * sizeof(T)));
+}
+static cv::Mat descMat(std::vector<uint8_t>& raw) { return cv::Mat((int)(raw.size() / 32), 32, CV_8U, raw.data()); }
+static void wrMatches(const std::string& name, const std::vector<cv::DMatch>& m) {
+    std::vector<int> q, t, img; std::vector<float> d;
+    for (auto& x : m) { q.push_back(x.queryIdx); t.push_back(x.trainIdx); img.push_back(x.imgIdx); d.push_back(x.distance); }
+    wr(name + "_q.bin", q); wr(name + "_t.bin", t); wr(name + "_img.bin", img); wr(name + "_d.bin", d);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::cerr << "usage: adapter_selftest <dir>" << std::endl; return 2; }
+    g_dir = argv[1];
+    float Kf[9] = {517.3f, 0, 318.6f, 0, 516.5f, 255.3f, 0, 0, 1};
+    float Df[5] = {-0.0410f, 0.3286f, 0.0087f, 0.0051f, -0.5643f};
+    cv::Mat K(3, 3, CV_32FC1, Kf), D(1, 5, CV_32FC1, Df);
+
+    // ---- Matcher::match path (matcher.cpp:470-496): performMatching -> undistort -> back-project -> RANSAC ----
+    auto d1 = rd<uint8_t>("desc1.bin"), d2 = rd<uint8_t>("desc2.bin");
+    auto uv1 = rd<float>("uv1.bin"), uv2 = rd<float>("uv2.bin");
+    auto z1 = rd<uint16_t>("depth1.bin"), z2 = rd<uint16_t>("depth2.bin");
+    MatcherB200 matcher(0);
+    std::vector<cv::DMatch> matches = matcher.performMatching(descMat(d1), descMat(d2));
+    wrMatches("vo_matches", matches);
+    std::vector<cv::KeyPoint> kp1(uv1.size() / 2), kp2(uv2.size() / 2);
+    for (size_t i = 0; i < kp1.size(); ++i) kp1[i].pt = cv::Point2f(uv1[2 * i], uv1[2 * i + 1]);
+    for (size_t i = 0; i < kp2.size(); ++i) kp2[i].pt = cv::Point2f(uv2[2 * i], uv2[2 * i + 1]);
+    std::vector<cv::Point2f> und1 = RGBD::removeImageDistortion(kp1, K, D), und2 = RGBD::removeImageDistortion(kp2, K, D);
+    cv::Mat depth1(480, 640, CV_16U, z1.data()), depth2(480, 640, CV_16U, z2.data());
+    std::vector<Eigen::Vector3f> p1 = RGBD::keypoints2Dto3D(und1, depth1, K, 5000.0), p2 = RGBD::keypoints2Dto3D(und2, depth2, K, 5000.0);
+    std::vector<float> und2f, p2f;
+    for (auto& p : und2) { und2f.push_back(p.x); und2f.push_back(p.y); }
+    for (auto& p : p2) { p2f.push_back(p[0]); p2f.push_back(p[1]); p2f.push_back(p[2]); }
+    wr("vo_und2.bin", und2f); wr("vo_xyz2.bin", p2f);
+    RANSAC::parameters rp;
+    rp.verbose = 0; rp.errorVersion = rp.errorVersionVO = rp.errorVersionMap = 0;
+    rp.inlierThresholdEuclidean = 0.04; rp.inlierThresholdReprojection = 2.0; rp.inlierThresholdMahalanobis = 9.0;
+    rp.minimalInlierRatioThreshold = 0.2; rp.minimalNumberOfMatches = 15; rp.usedPairs = 3; rp.iterationCount = 0;
+    rp.errorVersion = rp.errorVersionVO;   // matcher.cpp:491-492
+    RANSAC ransac(rp, K);
+    ransac.setSeed(4242);
+    std::vector<cv::DMatch> inliers;
+    Eigen::Matrix4f T = ransac.estimateTransformation(p1, p2, matches, inliers);
+    wrMatches("vo_inliers", inliers);
+    wr("vo_T.bin", std::vector<float>(T.data(), T.data() + 16));
+    std::vector<double> ratio{RANSAC::pointInlierRatio(inliers, matches), (double)ransac.hypothesesUsed(), ransac.bestInlierRatio()};
+    wr("vo_ratio.bin", ratio);
+
+    // ---- Matcher::matchXYZ path (matcher.cpp:606-797) ----
+    MatcherB200::MapSide map;
+    map.xyz = rd<double>("map_xyz.bin");
+    auto mdesc = rd<uint8_t>("map_desc.bin");
+    map.descriptors = descMat(mdesc);
+    map.octave = rd<int>("map_octave.bin");
+    map.detDist = rd<double>("map_detdist.bin");
+    auto cxyz = rd<float>("cur_xyz.bin");
+    auto cdesc = rd<uint8_t>("cur_desc.bin");
+    auto coct = rd<int>("cur_octave.bin");
+    std::vector<double> cdet = rd<double>("cur_detdist.bin");
+    std::vector<Eigen::Vector3f> cur3D(cxyz.size() / 3);
+    std::vector<cv::KeyPoint> curKp(cur3D.size());
+    for (size_t i = 0; i < cur3D.size(); ++i) { cur3D[i] = Eigen::Vector3f(cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2]); curKp[i].octave = coct[i]; }
+    for (int cn = 1; cn <= 2; ++cn) {
+        Eigen::Matrix4f Tm;
+        std::vector<cv::DMatch> mm, mi;
+        matcher.setSeed(77);
+        const double r = matcher.matchXYZCore(map, descMat(cdesc), cur3D, curKp, cdet, 0.12, 0.55, cn, rp, K, Tm, mm, mi);
+        const std::string tag = "map" + std::to_string(cn);
+        wrMatches(tag + "_matches", mm); wrMatches(tag + "_inliers", mi);
+        wr(tag + "_T.bin", std::vector<float>(Tm.data(), Tm.data() + 16));
+        wr(tag + "_ratio.bin", std::vector<double>{r});
+    }
+
+    // ---- demoKabsch path (demoKabsch.cpp:1020): createKabschEstimator()->computeTransformation(A, B) ----
+    auto A = rd<double>("kabsch_A.bin"), B = rd<double>("kabsch_B.bin");   // row-major n x 3
+    const long n = (long)(A.size() / 3);
+    Eigen::MatrixXd setA(n, 3), setB(n, 3);
+    for (long r = 0; r < n; ++r) for (int c = 0; c < 3; ++c) { setA(r, c) = A[3 * r + c]; setB(r, c) = B[3 * r + c]; }
+    TransformEst* est = createKabschEstimator();
+    Mat34& Tk = est->computeTransformation(setA, setB);
+    wr("kabsch_T.bin", std::vector<double>(Tk.m, Tk.m + 16));
+    Mat34& Te = est->computeTransformation(Eigen::MatrixXd(0, 3), Eigen::MatrixXd(0, 3));
+    wr("kabsch_T_empty.bin", std::vector<double>(Te.m, Te.m + 16));
+    std::cout << "adapter_selftest ok: " << matches.size() << " VO matches, " << inliers.size() << " inliers, est " << est->getName() << std::endl;
+    return 0;
+}

@@ -1,0 +1,81 @@
+"""GPU test (-m gpu) of the C++ adapter: PUTSLAM-shaped classes (MatcherB200::performMatching, RGBD::*,
+RANSAC::estimateTransformation, matchXYZ core, KabschEst) driven by adapter/adapter_selftest the way the
+reference's call sites drive them, compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "adapter", "adapter_selftest")
+
+
+def _rd(d, name, dt):
+    return np.fromfile(os.path.join(d, name), dtype=dt)
+
+
+def test_adapter_end_to_end(tmp_path, O):
+    from putslam_b200 import host, synth
+    assert os.path.exists(EXE), "adapter_selftest not built (run __graft_entry__.build())"
+    d = str(tmp_path)
+    fp = synth.frame_pair(n=500, seed=21, distorted=True)
+    mf = synth.map_frame(M=2000, N=600, n_reobs=400, seed=22)
+    rng = np.random.default_rng(23)
+    A = rng.uniform(-1.5, 1.5, (100, 3))
+    B = A @ synth.rot_from_rotvec([0.2, 0.1, -0.3]).T + [0.1, 0.2, -0.3] + rng.normal(0, [0.01, 0.02, 0.03], (100, 3))
+    for name, arr, dt in [("desc1", fp["desc1"], np.uint8), ("desc2", fp["desc2"], np.uint8), ("uv1", fp["uv1"], np.float32),
+                          ("uv2", fp["uv2"], np.float32), ("depth1", fp["depth1"], np.uint16), ("depth2", fp["depth2"], np.uint16),
+                          ("map_xyz", mf["map_xyz"], np.float64), ("map_desc", mf["map_desc"], np.uint8),
+                          ("map_octave", mf["map_octave"], np.int32), ("map_detdist", mf["map_detdist"], np.float64),
+                          ("cur_xyz", mf["cur_xyz"], np.float32), ("cur_desc", mf["cur_desc"], np.uint8),
+                          ("cur_octave", mf["cur_octave"], np.int32), ("cur_detdist", mf["cur_detdist"], np.float64),
+                          ("kabsch_A", A, np.float64), ("kabsch_B", B, np.float64)]:
+        np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
+    out = subprocess.run([EXE, d], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+    # ---- VO path ----
+    oq, ot, od = O.bf_mutual(fp["desc1"], fp["desc2"])
+    assert np.array_equal(_rd(d, "vo_matches_q.bin", np.int32), oq)
+    assert np.array_equal(_rd(d, "vo_matches_t.bin", np.int32), ot)
+    assert np.array_equal(_rd(d, "vo_matches_d.bin", np.float32), od)
+    assert (_rd(d, "vo_matches_img.bin", np.int32) == 0).all()          # BFMatcher sets imgIdx = 0
+    u1 = O.undistort(fp["uv1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+    u2 = O.undistort(fp["uv2"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+    x1, _ = O.backproject(u1, fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+    x2, _ = O.backproject(u2, fp["depth2"], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+    assert np.array_equal(bits(_rd(d, "vo_und2.bin", np.float32)), bits(u2.ravel()))
+    assert np.array_equal(bits(_rd(d, "vo_xyz2.bin", np.float32)), bits(x2.ravel()))
+    ref = O.ransac(x1, x2, oq, ot, seed=4242)
+    assert np.array_equal(_rd(d, "vo_inliers_q.bin", np.int32), oq[ref["inliers"]])
+    assert np.array_equal(_rd(d, "vo_inliers_t.bin", np.int32), ot[ref["inliers"]])
+    T = _rd(d, "vo_T.bin", np.float32).reshape(4, 4).T                  # column-major Eigen layout
+    assert np.abs(T - ref["T"]).max() <= 1e-5                           # 1e-5 m / 1e-5 rad (north_star)
+    ratio, used, best = _rd(d, "vo_ratio.bin", np.float64)
+    assert ratio == O.point_inlier_ratio(ot[ref["inliers"]], ot, 500) and int(used) == ref["hyp_used"] and best == ref["best_ratio"]
+
+    # ---- matchXYZ path, first call and first retry (wider gates) ----
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    for cn in (1, 2):
+        radius, ratio_g = host.retry_gates(0.12, 0.55, cn)
+        q, t, dd, _ = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, radius, ratio_g, 0)
+        tag = f"map{cn}"
+        assert np.array_equal(_rd(d, tag + "_matches_q.bin", np.int32), q)
+        assert np.array_equal(_rd(d, tag + "_matches_t.bin", np.int32), t)
+        assert np.array_equal(_rd(d, tag + "_matches_d.bin", np.float32), dd)
+        r = O.ransac(mf["map_xyz"].astype(np.float32), mf["cur_xyz"], q, t, seed=77)
+        assert np.array_equal(_rd(d, tag + "_inliers_q.bin", np.int32), q[r["inliers"]])
+        Tm = _rd(d, tag + "_T.bin", np.float32).reshape(4, 4).T
+        assert np.abs(Tm - r["T"]).max() <= 1e-5
+        assert _rd(d, tag + "_ratio.bin", np.float64)[0] == O.point_inlier_ratio(t[r["inliers"]], t, 600)
+
+    # ---- Kabsch ----
+    Tk = _rd(d, "kabsch_T.bin", np.float64).reshape(4, 4).T
+    assert np.array_equal(bits(Tk[:3]), bits(O.kabsch(A, B)))
+    assert np.array_equal(Tk[3], [0, 0, 0, 1])
+    assert np.array_equal(_rd(d, "kabsch_T_empty.bin", np.float64).reshape(4, 4).T, np.eye(4))
