@@ -333,6 +333,9 @@ def run_ours(args):
     dev_ms, sweep_ms = 0.0, []
     for i in range(args.steps):
         flush_l2()
+        if world > 1:
+            dist.barrier()          # untimed: align the ranks so that the collective does not wait for stragglers
+            torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(st)
         ctx.lc_query_sharded_resident(TAU, TOPK)

@@ -374,67 +374,115 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
     }
 }
 
-// Local top-k over per-keyframe scores: score descending, keyframe id ascending on ties.
-// Key = score << 32 | (0xffffffff - id); slot r is the largest key below slot r-1, found by one
-// block-wide pass + shared atomicMax per slot (k <= 64; the score array is a few tens of KB).
+// Local top-k over per-keyframe scores: score descending, keyframe id ascending on ties.  Single CTA.
+// Scores are bounded by the query count (<= 1024), so a shared-memory histogram finds the cut score s*
+// exactly: everything above s* is taken, ties at s* are taken in id order (ordered compaction), and the
+// <= 64 selected keys are placed by rank counting.  A handful of block barriers instead of k passes.
 // out_pairs: k x {score, global keyframe id}; unused slots {-1, -1}.
+constexpr int kTopkMaxScore = 1024;
 __global__ void __launch_bounds__(1024, 1)
 lc_topk_kernel(const int* __restrict__ scores, int n_kf, int kf_id_base, int k, int* __restrict__ out_pairs) {
-    __shared__ unsigned long long best[64];
-    const int tid = threadIdx.x;
-    if (tid < 64) best[tid] = 0ull;
+    __shared__ int hist[kTopkMaxScore + 2];
+    __shared__ unsigned long long sel[64];
+    __shared__ int warp_tot[32];
+    __shared__ int s_cut, s_above, s_nsel, s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kTopkMaxScore + 2; i += 1024) hist[i] = 0;
+    if (tid < 64) sel[tid] = 0ull;
+    if (tid == 0) { s_nsel = 0; s_carry = 0; }
     __syncthreads();
-    for (int r = 0; r < k; ++r) {
-        const unsigned long long prev = r ? best[r - 1] : ~0ull;
-        unsigned long long loc = 0ull;
-        if (r == 0 || prev != 0ull) {
-            for (int i = tid; i < n_kf; i += blockDim.x) {
-                const unsigned long long key =
-                    ((unsigned long long)(uint32_t)scores[i] << 32) | (0xffffffffu - (uint32_t)i);
-                if (key < prev && key > loc) loc = key;
+    for (int i = tid; i < n_kf; i += 1024) atomicAdd(hist + min(max(scores[i], 0), kTopkMaxScore + 1), 1);
+    __syncthreads();
+    if (warp == 0) {  // cut = largest s with count(score >= s) >= k (or 0); above = count(score > cut)
+        int acc = 0, cut = 0, above = 0;
+        bool found = false;
+        for (int hi = kTopkMaxScore + 1; hi >= 0 && !found; hi -= 32) {
+            const int sidx = hi - lane;
+            const int c = sidx >= 0 ? hist[sidx] : 0;
+            int incl = c;  // inclusive prefix over lanes (descending scores)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const uint32_t hit = __ballot_sync(0xffffffffu, sidx >= 0 && acc + incl >= k);
+            if (hit) {
+                const int l = __ffs(hit) - 1;
+                cut = hi - l;
+                above = acc + __shfl_sync(0xffffffffu, incl - c, l);
+                found = true;
+            } else {
+                acc += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
-        if (loc) atomicMax(best + r, loc);
-        __syncthreads();
+        if (!found) { cut = 0; above = acc - hist[0]; }
+        if (lane == 0) { s_cut = cut; s_above = above; }
     }
-    if (tid < k) {
-        const unsigned long long key = best[tid];
+    __syncthreads();
+    const int cut = s_cut, above = s_above;
+    const int need_eq = max(0, min(k, n_kf) - above);  // ties at the cut to take, lowest ids first
+    for (int base = 0; base < n_kf; base += 1024) {
+        const int i = base + tid;
+        const int sc = i < n_kf ? min(max(scores[i], 0), kTopkMaxScore + 1) : -1;
+        if (sc > cut) {
+            const int slot = atomicAdd(&s_nsel, 1);
+            if (slot < 64) sel[slot] = ((unsigned long long)(uint32_t)sc << 32) | (0xffffffffu - (uint32_t)i);
+        }
+        if (s_carry < need_eq) {  // uniform: s_carry only changes between the barriers below
+            const bool eq = (sc == cut);
+            const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+            const int wpre = __popc(bal & ((1u << lane) - 1u));
+            if (lane == 0) warp_tot[warp] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+            for (int w = 0; w < 32; ++w) {
+                const int cw = warp_tot[w];
+                if (w < warp) woff += cw;
+                tot += cw;
+            }
+            const int pos = s_carry + woff + wpre;
+            if (eq && pos < need_eq) {
+                const int slot = atomicAdd(&s_nsel, 1);
+                if (slot < 64) sel[slot] = ((unsigned long long)(uint32_t)sc << 32) | (0xffffffffu - (uint32_t)i);
+            }
+            __syncthreads();
+            if (tid == 0) s_carry += tot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * k) out_pairs[tid] = -1;
+    __syncthreads();
+    if (tid < 64) {
+        const unsigned long long key = sel[tid];
         if (key) {
-            out_pairs[2 * tid] = (int)(key >> 32);
-            out_pairs[2 * tid + 1] = kf_id_base + (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
-        } else {
-            out_pairs[2 * tid] = -1;
-            out_pairs[2 * tid + 1] = -1;
+            int rank = 0;
+            for (int j = 0; j < 64; ++j) rank += (sel[j] > key) ? 1 : 0;
+            if (rank < k) {
+                out_pairs[2 * rank] = (int)(key >> 32);
+                out_pairs[2 * rank + 1] = kf_id_base + (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+            }
         }
     }
 }
 
-// Merge world*k gathered {score, id} pairs into the global top-k (same order).  Single warp-sized job.
-__global__ void lc_merge_topk_kernel(const int* __restrict__ gathered, int n_pairs, int k, int* __restrict__ out_pairs) {
+// Merge world*k gathered {score, id} pairs (<= 1024) into the global top-k by rank counting.
+__global__ void __launch_bounds__(1024, 1)
+lc_merge_topk_kernel(const int* __restrict__ gathered, int n_pairs, int k, int* __restrict__ out_pairs) {
     __shared__ unsigned long long keys[1024];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 1024; i += blockDim.x) {
-        unsigned long long key = 0ull;
-        if (i < n_pairs && gathered[2 * i + 1] >= 0)
-            key = ((unsigned long long)(uint32_t)gathered[2 * i] << 32) | (0xffffffffu - (uint32_t)gathered[2 * i + 1]);
-        keys[i] = key;
-    }
+    unsigned long long key = 0ull;
+    if (tid < n_pairs && gathered[2 * tid + 1] >= 0)
+        key = ((unsigned long long)(uint32_t)gathered[2 * tid] << 32) | (0xffffffffu - (uint32_t)gathered[2 * tid + 1]);
+    keys[tid] = key;
+    if (tid < 2 * k) out_pairs[tid] = -1;
     __syncthreads();
-    if (tid == 0) {
-        unsigned long long prev = ~0ull;
-        for (int r = 0; r < k; ++r) {
-            unsigned long long loc = 0ull;
-            for (int i = 0; i < n_pairs && i < 1024; ++i)
-                if (keys[i] < prev && keys[i] > loc) loc = keys[i];
-            if (loc) {
-                out_pairs[2 * r] = (int)(loc >> 32);
-                out_pairs[2 * r + 1] = (int)(0xffffffffu - (uint32_t)(loc & 0xffffffffu));
-                prev = loc;
-            } else {
-                out_pairs[2 * r] = -1;
-                out_pairs[2 * r + 1] = -1;
-                prev = 0ull;
-            }
+    if (key) {
+        int rank = 0;
+        for (int j = 0; j < n_pairs; ++j) rank += (keys[j] > key) ? 1 : 0;
+        if (rank < k) {
+            out_pairs[2 * rank] = (int)(key >> 32);
+            out_pairs[2 * rank + 1] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
         }
     }
 }
@@ -559,7 +607,7 @@ cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k,
 
 cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
                                  int* launches) {
-    lc_merge_topk_kernel<<<1, 256, 0, st>>>(d_gathered, n_pairs, k, d_out_pairs);
+    lc_merge_topk_kernel<<<1, 1024, 0, st>>>(d_gathered, n_pairs, k, d_out_pairs);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
