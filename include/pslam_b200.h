@@ -231,9 +231,15 @@ PSLAM_API int pslam_lc_query_sharded(pslam_ctx* ctx, const uint8_t* query, int n
                                      int* out_kf_ids, int* out_scores);
 PSLAM_API int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k);
 
-/* Per-query-descriptor 2-NN against the whole resident database (SURVEY 8e variant V2):
- * out_idx: nq x 2 GLOBAL descriptor indices (int64), out_dist: nq x 2 float. */
+/* Per-query-descriptor 2-NN against the whole resident database (SURVEY 8e variant V2; the oracle is
+ * cv::BFMatcher::knnMatch(query, whole_db, 2)): out_idx nq x 2 GLOBAL descriptor indices (int64, -1 = none;
+ * global = desc_id_base + position in this ctx's database), out_dist nq x 2 float, ascending distance, lowest
+ * index first on ties.  _sharded: ncclBroadcast(query) / local sweep / ncclAllGather of nq x 2 keys / merge. */
+PSLAM_API int pslam_lc_set_desc_base(pslam_ctx* ctx, int64_t desc_id_base);
 PSLAM_API int pslam_lc_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, int64_t* out_idx, float* out_dist);
+PSLAM_API int pslam_lc_knn2_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int64_t* out_idx,
+                                    float* out_dist);
+PSLAM_API int pslam_lc_knn2_resident(pslam_ctx* ctx, int sharded);
 
 #ifdef __cplusplus
 }

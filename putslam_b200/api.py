@@ -23,7 +23,8 @@ ABI_SYMBOLS = [
     "pslam_frame_to_map", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
-    "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2",
+    "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
+    "pslam_lc_knn2_sharded", "pslam_lc_knn2_resident",
 ]
 
 
@@ -334,6 +335,22 @@ class Context:
         self._ck(self.lib.pslam_lc_query_sharded(self.h, _p(q, C.c_uint8), nq, root, tau, k, _p(ids, C.c_int),
                                                  _p(sc, C.c_int)))
         return ids, sc
+
+    def lc_set_desc_base(self, base):
+        self._ck(self.lib.pslam_lc_set_desc_base(self.h, C.c_int64(int(base))))
+
+    def lc_knn2(self, query, sharded=False, root=-1, nq=None):
+        q = _arr(query, np.uint8) if query is not None else None
+        nq = q.shape[0] if q is not None else int(nq)
+        idx = np.empty((nq, 2), np.int64); dist = np.empty((nq, 2), np.float32)
+        if sharded:
+            self._ck(self.lib.pslam_lc_knn2_sharded(self.h, _p(q, C.c_uint8), nq, root, _p(idx, C.c_int64), _p(dist, C.c_float)))
+        else:
+            self._ck(self.lib.pslam_lc_knn2(self.h, _p(q, C.c_uint8), nq, _p(idx, C.c_int64), _p(dist, C.c_float)))
+        return idx, dist
+
+    def lc_knn2_resident(self, sharded=False):
+        self._ck(self.lib.pslam_lc_knn2_resident(self.h, int(bool(sharded))))
 
     def lc_query_sharded_resident(self, tau=64, k=16):
         self._ck(self.lib.pslam_lc_query_sharded_resident(self.h, tau, k))

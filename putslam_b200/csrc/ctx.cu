@@ -114,6 +114,8 @@ struct pslam_ctx {
     int64_t* d_kf_off = nullptr;
     std::vector<int64_t> h_kf_off;  // host mirror (n_kf + 1)
     int kf_cap = 0, n_kf = 0, kf_id_base = 0;
+    long long desc_id_base = 0;
+    DevBuf d_knn;  // V2 sweep scratch: per-CTA partials | merged keys | gathered keys | idx | dist
     int* d_scores = nullptr;
     uint8_t* d_lc_query = nullptr;
     int lc_nq = 0;
@@ -288,7 +290,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
-    cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p);
+    cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p); cudaFree(ctx->d_knn.p);
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
@@ -1010,9 +1012,71 @@ int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k) {
     return lc_enqueue_sharded(ctx, -1, tau, k);
 }
 
+int pslam_lc_set_desc_base(pslam_ctx* ctx, int64_t desc_id_base) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    ctx->desc_id_base = desc_id_base;
+    return PSLAM_OK;
+}
+
+// layout of d_knn: [partials grid*nq*16][keys nq*16][gathered world*nq*16][idx nq*16][dist nq*8]
+static int lc_knn2_run(pslam_ctx* ctx, const uint8_t* query, int nq, int root, bool sharded, int64_t* out_idx,
+                       float* out_dist, bool copy_out) {
+    if (nq <= 0 || nq > PSLAM_LC_MAX_QUERY) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "query size %d outside 1..%d", nq, PSLAM_LC_MAX_QUERY);
+    TRY(lc_prepare(ctx, query, nq, 1));
+    const int world = sharded ? ctx->world : 1;
+    const int grid = lc_knn2_grid(ctx->db_n, ctx->sm_count);
+    Arena A;
+    const size_t o_part = A.take(16 * (size_t)grid * nq), o_keys = A.take(16 * (size_t)nq);
+    const size_t o_gath = A.take(16 * (size_t)world * nq), o_idx = A.take(16 * (size_t)nq), o_dist = A.take(8 * (size_t)nq);
+    TRY(ensure_dev(ctx, ctx->d_knn, A.off));
+    uint8_t* d = ctx->d_knn.p;
+    NcclApi* api = nccl_api();
+    int l = 0;
+    if (world > 1 && root >= 0) {
+        const int r = api->Broadcast(ctx->d_lc_query, ctx->d_lc_query, (size_t)nq * 32, kNcclUint8, root, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast failed");
+    }
+    if (ctx->db_n > 0) {
+        CK(launch_lc_knn2(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, grid, ctx->stream, &l));
+    }
+    CK(launch_lc_knn2_merge(d + o_part, ctx->db_n > 0 ? grid : 0, nq, (unsigned long long*)(d + o_keys),
+                            world > 1 ? nullptr : (long long*)(d + o_idx), (float*)(d + o_dist), ctx->stream, &l));
+    if (world > 1) {
+        const int r = api->AllGather(d + o_keys, d + o_gath, 16 * (size_t)nq, kNcclUint8, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclAllGather failed");
+        CK(launch_lc_knn2_merge(d + o_gath, world, nq, nullptr, (long long*)(d + o_idx), (float*)(d + o_dist), ctx->stream, &l));
+    }
+    ctx->launches += l;
+    if (!copy_out) return PSLAM_OK;
+    TRY(ensure_host(ctx, ctx->h_out, 24 * (size_t)nq));
+    CK(cudaMemcpyAsync(ctx->h_out.p, d + o_idx, 16 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out.p + 16 * (size_t)nq, d + o_dist, 8 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_idx, ctx->h_out.p, 16 * (size_t)nq);
+    memcpy(out_dist, ctx->h_out.p + 16 * (size_t)nq, 8 * (size_t)nq);
+    return PSLAM_OK;
+}
+
 int pslam_lc_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, int64_t* out_idx, float* out_dist) {
-    (void)query; (void)nq; (void)out_idx; (void)out_dist;
-    return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_lc_knn2 is not built yet");
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!query || !out_idx || !out_dist) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_knn2: null buffer");
+    return lc_knn2_run(ctx, query, nq, -1, false, out_idx, out_dist, true);
+}
+
+int pslam_lc_knn2_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int64_t* out_idx, float* out_dist) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!out_idx || !out_dist) return fail(ctx, PSLAM_ERR_ARG, "pslam_lc_knn2_sharded: null buffer");
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, PSLAM_ERR_NCCL, "communicator not initialised");
+    const bool have_query = (root < 0) || (root == ctx->rank) || ctx->world == 1;
+    if (have_query && !query) return fail(ctx, PSLAM_ERR_ARG, "query is NULL on a rank that must supply it");
+    return lc_knn2_run(ctx, have_query ? query : nullptr, nq, root, true, out_idx, out_dist, true);
+}
+
+int pslam_lc_knn2_resident(pslam_ctx* ctx, int sharded) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->lc_nq <= 0 || !ctx->lc_configured) return fail(ctx, PSLAM_ERR_ARG, "no resident query");
+    if (sharded && ctx->world > 1 && !ctx->comm) return fail(ctx, PSLAM_ERR_NCCL, "communicator not initialised");
+    return lc_knn2_run(ctx, nullptr, ctx->lc_nq, -1, sharded != 0, nullptr, nullptr, false);
 }
 
 }  // extern "C"

@@ -374,6 +374,148 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// V2 sweep: two nearest database descriptors per query descriptor over the WHOLE resident database
+// (keyframe boundaries ignored).  Persistent CTAs walk 2048-row chunks (round-robin) through the same
+// TMA ring; inside a chunk the running top-2 are 32-bit keys with chunk-local indices, at chunk end they
+// are folded into 64-bit (dist << 40 | global index) keys.  Per-CTA results are merged per query.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunk = 2048;
+__device__ __forceinline__ unsigned long long key64(uint32_t k, long long base) {
+    return ((unsigned long long)key_dist(k) << 40) | (unsigned long long)(base + (long long)key_tidx(k));
+}
+__device__ __forceinline__ void top2_insert64(unsigned long long& g1, unsigned long long& g2, unsigned long long v) {
+    const unsigned long long hi = v > g1 ? v : g1;
+    g1 = v < g1 ? v : g1;
+    g2 = hi < g2 ? hi : g2;
+}
+
+template <int RQ, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
+lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db, long long n_desc,
+               long long desc_id_base, ulonglong2* __restrict__ partial /* [gridDim.x][nq] */) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4* stages = reinterpret_cast<uint4*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTT * 32);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+    }
+    QueryRegs<RQ, NT> Q;
+    Q.load(query, nq, 0, tid);
+    unsigned long long g1[RQ], g2[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) g1[j] = g2[j] = ~0ull;
+    __syncthreads();
+
+    const long long n_tiles_total = (n_desc + kTT - 1) / kTT;
+    constexpr int kTilesPerChunk = kChunk / kTT;
+    const long long n_chunks = (n_desc + kChunk - 1) / kChunk;
+    // flat list of this CTA's tiles: chunk c = blockIdx.x + i*gridDim.x, tiles c*16 .. c*16+15
+    auto tile_of = [&](long long item) -> long long {
+        const long long c = (long long)blockIdx.x + (item / kTilesPerChunk) * gridDim.x;
+        return c * kTilesPerChunk + (item % kTilesPerChunk);
+    };
+    long long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // number of items: full chunks have 16 tiles, the globally last chunk may have fewer
+    long long n_items = 0;
+    for (long long i = 0; i < my_chunks; ++i) {
+        const long long c = (long long)blockIdx.x + i * gridDim.x;
+        const long long first = c * kTilesPerChunk;
+        const long long cnt = n_tiles_total - first;
+        n_items += cnt < kTilesPerChunk ? cnt : kTilesPerChunk;
+    }
+    auto issue = [&](long long item) {
+        const long long t = tile_of(item);
+        const long long row0 = t * kTT;
+        const int cnt = (int)((n_desc - row0) < kTT ? (n_desc - row0) : kTT);
+        const int st = (int)(item % kStages);
+        mbar_expect_tx(bars + st, (uint32_t)cnt * 32u);
+        tma_load_1d(stages + (size_t)st * kTT * 2, db + 2 * row0, (uint32_t)cnt * 32u, bars + st);
+    };
+    if (tid == 0)
+        for (long long i = 0; i < kStages - 1 && i < n_items; ++i) issue(i);
+
+    uint32_t m1[RQ], m2[RQ];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) m1[j] = m2[j] = 0xffffffffu;
+    for (long long it = 0; it < n_items; ++it) {
+        const int stage = (int)(it % kStages);
+        const uint32_t phase = (uint32_t)(it / kStages) & 1u;
+        if (tid == 0 && it + kStages - 1 < n_items) issue(it + kStages - 1);
+        const long long t = tile_of(it);
+        const long long row0 = t * kTT;
+        const int cnt = (int)((n_desc - row0) < kTT ? (n_desc - row0) : kTT);
+        const uint32_t tbase = (uint32_t)((t % kTilesPerChunk) * kTT);  // chunk-local row of the tile
+        mbar_wait(bars + stage, phase);
+        const uint4* tile = stages + (size_t)stage * kTT * 2;
+        int tt = 0;
+#pragma unroll 1
+        for (; tt + 2 <= cnt; tt += 2) {
+            const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1], a1 = tile[2 * tt + 2], b1 = tile[2 * tt + 3];
+            const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits, t1 = t0 + (1u << kKeyQBits);
+#pragma unroll
+            for (int j = 0; j < RQ; ++j) {
+                const uint32_t k0 = ham256_key(Q.v[j], a0, b0, t0);
+                const uint32_t k1 = ham256_key(Q.v[j], a1, b1, t1);
+                const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+                const uint32_t mid = max(m1[j], lo);
+                m1[j] = min(m1[j], lo);
+                m2[j] = __vimin3_u32(m2[j], mid, hi);
+            }
+        }
+        if (tt < cnt) {
+            const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1];
+            const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits;
+#pragma unroll
+            for (int j = 0; j < RQ; ++j) {
+                const uint32_t k0 = ham256_key(Q.v[j], a0, b0, t0);
+                m2[j] = min(m2[j], max(m1[j], k0));
+                m1[j] = min(m1[j], k0);
+            }
+        }
+        const bool chunk_end = ((t % kTilesPerChunk) == kTilesPerChunk - 1) || (t == n_tiles_total - 1);
+        if (chunk_end) {
+            const long long base = desc_id_base + (t / kTilesPerChunk) * (long long)kChunk;
+#pragma unroll
+            for (int j = 0; j < RQ; ++j) {
+                if (m1[j] != 0xffffffffu) top2_insert64(g1[j], g2[j], key64(m1[j], base));
+                if (m2[j] != 0xffffffffu) top2_insert64(g1[j], g2[j], key64(m2[j], base));
+                m1[j] = m2[j] = 0xffffffffu;
+            }
+        }
+        __syncthreads();  // every warp is done with this stage before it is refilled
+    }
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) {
+        const int q = j * NT + tid;
+        if (q < nq) partial[(size_t)blockIdx.x * nq + q] = make_ulonglong2(g1[j], g2[j]);
+    }
+}
+
+// Merge nparts sorted pairs per query.  out_keys (nullable): nq x 2 merged 64-bit keys (for the all-gather);
+// out_idx / out_dist (nullable): nq x 2 global descriptor index (int64, -1 = none) and distance (float).
+__global__ void lc_knn2_merge_kernel(const ulonglong2* __restrict__ partial, int nparts, int nq,
+                                     unsigned long long* __restrict__ out_keys, long long* __restrict__ out_idx,
+                                     float* __restrict__ out_dist) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long g1 = ~0ull, g2 = ~0ull;
+    for (int p = 0; p < nparts; ++p) {
+        const ulonglong2 v = partial[(size_t)p * nq + q];
+        top2_insert64(g1, g2, v.x);
+        top2_insert64(g1, g2, v.y);
+    }
+    if (out_keys) { out_keys[2 * q] = g1; out_keys[2 * q + 1] = g2; }
+    if (out_idx) {
+        out_idx[2 * q] = g1 == ~0ull ? -1 : (long long)(g1 & ((1ull << 40) - 1));
+        out_idx[2 * q + 1] = g2 == ~0ull ? -1 : (long long)(g2 & ((1ull << 40) - 1));
+        out_dist[2 * q] = g1 == ~0ull ? -1.f : (float)(g1 >> 40);
+        out_dist[2 * q + 1] = g2 == ~0ull ? -1.f : (float)(g2 >> 40);
+    }
+}
+
 // Local top-k over per-keyframe scores: score descending, keyframe id ascending on ties.  Single CTA.
 // Scores are bounded by the query count (<= 1024), so a shared-memory histogram finds the cut score s*
 // exactly: everything above s* is taken, ties at s* are taken in id order (ordered compaction), and the
@@ -608,6 +750,36 @@ cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k,
 cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
                                  int* launches) {
     lc_merge_topk_kernel<<<1, 1024, 0, st>>>(d_gathered, n_pairs, k, d_out_pairs);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+int lc_knn2_grid(long long n_desc, int sm_count) {
+    long long chunks = (n_desc + kChunk - 1) / kChunk;
+    long long g = 2LL * sm_count;
+    if (g > chunks) g = chunks;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
+                           void* d_partial, int grid, cudaStream_t st, int* launches) {
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
+    const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
+    const size_t smem = (size_t)kStages * kTT * 32 + sizeof(uint64_t) * kStages + 16;
+    ulonglong2* part = reinterpret_cast<ulonglong2*>(d_partial);
+    const int rq = pick_rq(nq);
+    if (rq == 1) lc_knn2_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
+    else if (rq == 2) lc_knn2_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
+    else lc_knn2_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsigned long long* d_keys, long long* d_idx,
+                                 float* d_dist, cudaStream_t st, int* launches) {
+    lc_knn2_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const ulonglong2*>(d_partial), nparts, nq,
+                                                         d_keys, d_idx, d_dist);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -24,6 +24,13 @@ cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k,
 cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
                                  int* launches);
 
+int lc_knn2_grid(long long n_desc, int sm_count);
+// d_partial: grid x nq ulonglong2.  Keys are dist << 40 | global descriptor index.
+cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
+                           void* d_partial, int grid, cudaStream_t st, int* launches);
+cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsigned long long* d_keys, long long* d_idx,
+                                 float* d_dist, cudaStream_t st, int* launches);
+
 // ---- guided.cu -------------------------------------------------------------------------------
 // d_out: int[2 + 3*cap] = {n_total, perfect, queryIdx[cap], trainIdx[cap], distance(float)[cap]}
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,

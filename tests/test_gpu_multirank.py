@@ -43,6 +43,9 @@ def _worker(rank, world, tmp):
         res.append((ids.tolist(), sc.tolist()))
     ids, sc = ctx.lc_query_sharded(db["query"], root=-1, tau=40, k=16)      # every rank supplies the query
     res.append((ids.tolist(), sc.tolist()))
+    ctx.lc_set_desc_base(int(off[0]))                                       # V2: global descriptor indices
+    idx, dist = ctx.lc_knn2(db["query"] if rank == 0 else None, sharded=True, root=0, nq=700)
+    np.save(os.path.join(tmp, f"knn{rank}.npy"), np.concatenate([idx, dist.astype(np.int64)], 1))
     np.save(os.path.join(tmp, f"res{rank}.npy"), np.array(res, dtype=object), allow_pickle=True)
     ctx.comm_destroy()
     ctx.close()
@@ -62,3 +65,6 @@ def test_sharded_sweep_nccl(tmp_path, O):
         res = np.load(tmp_path / f"res{r}.npy", allow_pickle=True)
         for (ids, sc), (eid, esc) in zip(res, exp):
             assert list(ids) == eid.tolist() and list(sc) == esc.tolist(), f"rank {r}"
+        knn = np.load(tmp_path / f"knn{r}.npy")
+        oi, od = O.knn2(db["query"], db["db"])
+        assert np.array_equal(knn[:, :2], oi.astype(np.int64)) and np.array_equal(knn[:, 2:], od.astype(np.int64))

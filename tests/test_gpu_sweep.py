@@ -66,3 +66,26 @@ def test_lc_full_size_planted_recall(ctx):
     ids2, sc2 = ctx.lc_query(db["query"], tau=64, k=20)
     assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
     _fresh(ctx)
+
+
+@pytest.mark.parametrize("n_desc,nq", [(50000, 300), (4097, 1000), (2048, 77), (130, 1000), (1, 5)])
+def test_lc_knn2_whole_db_vs_oracle(ctx, O, n_desc, nq):
+    """V2: two nearest database descriptors per query descriptor (oracle = cv2-pinned knnMatch restatement)."""
+    rng = np.random.default_rng(n_desc + nq)
+    db = rng.integers(0, 256, (n_desc, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    if n_desc > 1000:   # exact duplicates and near-duplicates: ties must resolve to the lowest index
+        db[rng.choice(n_desc, 200, replace=False)] = q[rng.integers(0, nq, 200)]
+        db[7] = db[4100 % n_desc] = q[0]
+    _fresh(ctx)
+    ctx.lc_set_desc_base(0)
+    ctx.lc_append(db, np.array([0, n_desc], np.int64) if n_desc <= 4096 else
+                  np.arange(0, n_desc + 1, 1000).tolist() + ([n_desc] if n_desc % 1000 else []))
+    idx, dist = ctx.lc_knn2(q)
+    oi, od = O.knn2(q, db)
+    assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32))
+    ctx.lc_set_desc_base(10 ** 10)   # global ids beyond 32 bits
+    idx2, _ = ctx.lc_knn2(q)
+    assert np.array_equal(idx2[oi >= 0], oi[oi >= 0].astype(np.int64) + 10 ** 10) and (idx2[oi < 0] == -1).all()
+    ctx.lc_set_desc_base(0)
+    _fresh(ctx)
