@@ -1037,7 +1037,7 @@ static int lc_knn2_run(pslam_ctx* ctx, const uint8_t* query, int nq, int root, b
         if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast failed");
     }
     if (ctx->db_n > 0) {
-        CK(launch_lc_knn2(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, grid, ctx->stream, &l));
+        CK(launch_lc_knn2(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, grid, ctx->sm_count, ctx->stream, &l));
     }
     CK(launch_lc_knn2_merge(d + o_part, ctx->db_n > 0 ? grid : 0, nq, (unsigned long long*)(d + o_keys),
                             world > 1 ? nullptr : (long long*)(d + o_idx), (float*)(d + o_dist), ctx->stream, &l));

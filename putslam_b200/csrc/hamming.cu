@@ -380,7 +380,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
 // TMA ring; inside a chunk the running top-2 are 32-bit keys with chunk-local indices, at chunk end they
 // are folded into 64-bit (dist << 40 | global index) keys.  Per-CTA results are merged per query.
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunk = 2048;
+constexpr int kChunkMax = 2048;  // chunk-local row index must fit the 12-bit train field of the key
 __device__ __forceinline__ unsigned long long key64(uint32_t k, long long base) {
     return ((unsigned long long)key_dist(k) << 40) | (unsigned long long)(base + (long long)key_tidx(k));
 }
@@ -393,7 +393,7 @@ __device__ __forceinline__ void top2_insert64(unsigned long long& g1, unsigned l
 template <int RQ, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
 lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db, long long n_desc,
-               long long desc_id_base, ulonglong2* __restrict__ partial /* [gridDim.x][nq] */) {
+               long long desc_id_base, int chunk_rows, ulonglong2* __restrict__ partial /* [gridDim.x][nq] */) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4* stages = reinterpret_cast<uint4*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTT * 32);
@@ -410,8 +410,8 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
     __syncthreads();
 
     const long long n_tiles_total = (n_desc + kTT - 1) / kTT;
-    constexpr int kTilesPerChunk = kChunk / kTT;
-    const long long n_chunks = (n_desc + kChunk - 1) / kChunk;
+    const int kTilesPerChunk = chunk_rows / kTT;
+    const long long n_chunks = (n_desc + chunk_rows - 1) / chunk_rows;
     // flat list of this CTA's tiles: chunk c = blockIdx.x + i*gridDim.x, tiles c*16 .. c*16+15
     auto tile_of = [&](long long item) -> long long {
         const long long c = (long long)blockIdx.x + (item / kTilesPerChunk) * gridDim.x;
@@ -477,7 +477,7 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
         }
         const bool chunk_end = ((t % kTilesPerChunk) == kTilesPerChunk - 1) || (t == n_tiles_total - 1);
         if (chunk_end) {
-            const long long base = desc_id_base + (t / kTilesPerChunk) * (long long)kChunk;
+            const long long base = desc_id_base + (t / kTilesPerChunk) * (long long)chunk_rows;
 #pragma unroll
             for (int j = 0; j < RQ; ++j) {
                 if (m1[j] != 0xffffffffu) top2_insert64(g1[j], g2[j], key64(m1[j], base));
@@ -754,8 +754,16 @@ cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int*
     return cudaGetLastError();
 }
 
+// rows per chunk: large enough to amortise the 64-bit fold, small enough to give every CTA work
+static int lc_knn2_chunk(long long n_desc, int sm_count) {
+    long long c = (n_desc / (2LL * sm_count) + kTT - 1) / kTT * kTT;
+    if (c < kTT) c = kTT;
+    if (c > kChunkMax) c = kChunkMax;
+    return (int)c;
+}
 int lc_knn2_grid(long long n_desc, int sm_count) {
-    long long chunks = (n_desc + kChunk - 1) / kChunk;
+    const int chunk = lc_knn2_chunk(n_desc, sm_count);
+    long long chunks = (n_desc + chunk - 1) / chunk;
     long long g = 2LL * sm_count;
     if (g > chunks) g = chunks;
     if (g < 1) g = 1;
@@ -763,15 +771,16 @@ int lc_knn2_grid(long long n_desc, int sm_count) {
 }
 
 cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
-                           void* d_partial, int grid, cudaStream_t st, int* launches) {
+                           void* d_partial, int grid, int sm_count, cudaStream_t st, int* launches) {
+    const int chunk = lc_knn2_chunk(n_desc, sm_count);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
     const size_t smem = (size_t)kStages * kTT * 32 + sizeof(uint64_t) * kStages + 16;
     ulonglong2* part = reinterpret_cast<ulonglong2*>(d_partial);
     const int rq = pick_rq(nq);
-    if (rq == 1) lc_knn2_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
-    else if (rq == 2) lc_knn2_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
-    else lc_knn2_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, part);
+    if (rq == 1) lc_knn2_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);
+    else if (rq == 2) lc_knn2_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);
+    else lc_knn2_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

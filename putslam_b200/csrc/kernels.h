@@ -27,7 +27,7 @@ cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int*
 int lc_knn2_grid(long long n_desc, int sm_count);
 // d_partial: grid x nq ulonglong2.  Keys are dist << 40 | global descriptor index.
 cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
-                           void* d_partial, int grid, cudaStream_t st, int* launches);
+                           void* d_partial, int grid, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsigned long long* d_keys, long long* d_idx,
                                  float* d_dist, cudaStream_t st, int* launches);
 
