@@ -692,15 +692,8 @@ cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, 
     return cudaGetLastError();
 }
 
-// sweep variants: (queries per thread, threads per CTA).  PSLAM_SWEEP_VARIANT=1 selects 8 x 128.
-static int sweep_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PSLAM_SWEEP_VARIANT");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
+// Shapes tried for the sweep on B200 (C4, 1 GPU): 4 queries/thread x 256 threads x 2 CTAs/SM = 775 Gcmp/s (kept);
+// 8 x 128 x 4 CTAs/SM = 753; 2 x 512 x 2 CTAs/SM (32 warps/SM) = 778.  The LOP3 pipe, not latency, is the limit.
 template <int NT>
 static size_t lc_sweep_smem_nt() {
     return (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * (NT / 32) * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
@@ -713,7 +706,7 @@ cudaError_t lc_sweep_configure() {
 #define CFG(RQ, NT)                                                                                              \
     if ((e = cudaFuncSetAttribute(lc_sweep_kernel<RQ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                   (int)lc_sweep_smem_nt<NT>())) != cudaSuccess) return e;
-    CFG(1, 256) CFG(2, 256) CFG(4, 256) CFG(8, 128)
+    CFG(1, 256) CFG(2, 256) CFG(4, 256)
 #undef CFG
     return cudaSuccess;
 }
@@ -724,18 +717,12 @@ cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db,
     const int rq = pick_rq(nq);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
-    if (rq == 4 && sweep_variant() == 1) {
-        int grid = 4 * sm_count;
-        if (grid > n_kf) grid = n_kf;
-        lc_sweep_kernel<8, 128><<<grid, 128, lc_sweep_smem_nt<128>(), st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-    } else {
-        int grid = 2 * sm_count;
-        if (grid > n_kf) grid = n_kf;
-        const size_t smem = lc_sweep_smem_nt<256>();
-        if (rq == 1) lc_sweep_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-        else if (rq == 2) lc_sweep_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-        else lc_sweep_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
-    }
+    int grid = 2 * sm_count;
+    if (grid > n_kf) grid = n_kf;
+    const size_t smem = lc_sweep_smem_nt<256>();
+    if (rq == 1) lc_sweep_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    else if (rq == 2) lc_sweep_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+    else lc_sweep_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
