@@ -238,7 +238,7 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
         cx = cameraMatrix.at<float>(0, 2); cy = cameraMatrix.at<float>(1, 2);
     }
     pslam_ransac_params a = toAbi(rp, fx, fy, cx, cy);
-    int cap = std::max(4096, 4 * std::max(M, N));
+    int cap = std::max(2048, 2 * N);   // typical yield is ~1 match per current keypoint; grown on truncation
     std::vector<int> mq, mt, inl;
     std::vector<float> mdist;
     pslam_frame_result res;

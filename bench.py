@@ -227,10 +227,10 @@ def frontend_numbers(ctx, steps, warmup):
         frames.append((mf["map_xyz"].astype(np.float32), mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl))
     for mode, name in ((0, "c3_satsub_quirk"), (1, "c3_xor")):
         for i in range(warmup):
-            r = ctx.frame_to_map(*frames[i % 4], 0.12, 0.55, mode, seed=i, num_hyp=4096)
+            r = ctx.frame_to_map(*frames[i % 4], 0.12, 0.55, mode, seed=i, num_hyp=4096, match_cap=4096)
         t0 = time.perf_counter()
         for i in range(steps):
-            r = ctx.frame_to_map(*frames[i % 4], 0.12, 0.55, mode, seed=i, num_hyp=4096)
+            r = ctx.frame_to_map(*frames[i % 4], 0.12, 0.55, mode, seed=i, num_hyp=4096, match_cap=4096)
         e2e_ms = (time.perf_counter() - t0) / steps * 1e3
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ctx.frame_to_map_resident(); ctx.sync()

@@ -84,8 +84,8 @@ struct F2MState {
     bool valid = false;
     const float* map_xyz; const uint8_t* map_desc; const int* map_level; int M;
     const float* cur_xyz; const uint8_t* cur_desc; const int* cur_level; int N;
-    float radius_f; double ratio; int mode; int cap;
-    int* count; int* best; int* gout;
+    float sq_radius_f; double ratio; int mode; int cap;
+    int* count; int* best; void* cache; int* gout;
     RansacDeviceParams rp; RansacWorkspace ws;
 };
 struct F2FState {
@@ -189,6 +189,16 @@ float float_at_least(double v) {  // smallest float >= v, so that (double)f < v 
     return f;
 }
 
+float sq_threshold(float thr_f) {  // smallest float T such that sqrtf(T) >= thr_f (sqrtf is correctly rounded, monotone)
+    if (!(thr_f > 0.f)) return 0.f;          // sqrtf(s) < thr_f <= 0 never holds; s < 0 never holds for a sum of squares
+    if (isinf(thr_f)) return INFINITY;
+    float t = thr_f * thr_f;
+    if (isinf(t)) t = 3.402823466e+38f;
+    while (t > 0.f && sqrtf(t) >= thr_f) t = nextafterf(t, 0.f);
+    while (sqrtf(t) < thr_f) t = nextafterf(t, INFINITY);
+    return t;
+}
+
 int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t seed, int num_hyp, RansacDeviceParams& o) {
     if (!p) return fail(ctx, PSLAM_ERR_ARG, "ransac params is NULL");
     if (p->used_pairs != 3) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "used_pairs must be 3 (got %d)", p->used_pairs);
@@ -199,6 +209,7 @@ int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t se
     o.error_version = p->error_version;
     o.thr_euclid = p->inlier_threshold_euclidean;
     o.thr_euclid_f = float_at_least(p->inlier_threshold_euclidean);
+    o.sq_thr_euclid_f = sq_threshold(o.thr_euclid_f);
     o.thr_reproj = p->inlier_threshold_reprojection;
     o.min_inlier_ratio = p->minimal_inlier_ratio_threshold;
     o.min_matches = p->minimal_number_of_matches;
@@ -210,7 +221,7 @@ int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t se
 
 // carve a RANSAC workspace out of the work arena
 struct RansacLayout {
-    size_t pts, keep, nfil, counts, result;
+    size_t pts, keep, nfil, counts, models, result;
     int m_cap, h_cap;
 };
 RansacLayout plan_ransac(Arena& A, int m_cap, int num_hyp) {
@@ -221,6 +232,7 @@ RansacLayout plan_ransac(Arena& A, int m_cap, int num_hyp) {
     L.keep = A.take(sizeof(int) * 2 * (size_t)L.m_cap);
     L.nfil = A.take(sizeof(int) * 4);
     L.counts = A.take(sizeof(int) * (size_t)L.h_cap);
+    L.models = A.take(sizeof(float) * 12 * (size_t)L.h_cap);
     return L;
 }
 RansacWorkspace bind_ransac(const RansacLayout& L, uint8_t* work, int* result) {
@@ -229,6 +241,7 @@ RansacWorkspace bind_ransac(const RansacLayout& L, uint8_t* work, int* result) {
     ws.keep = reinterpret_cast<int*>(work + L.keep);
     ws.n_filtered = reinterpret_cast<int*>(work + L.nfil);
     ws.counts = reinterpret_cast<int*>(work + L.counts);
+    ws.models = reinterpret_cast<float*>(work + L.models);
     ws.result = result;
     ws.m_cap = L.m_cap;
     ws.h_cap = L.h_cap;
@@ -451,6 +464,7 @@ int pslam_match_guided_xyz(pslam_ctx* ctx, const float* map_xyz, const uint8_t* 
     const size_t o_cx = in.take(12 * (size_t)N), o_cd = in.take(32 * (size_t)N), o_cl = in.take(4 * (size_t)N);
     const size_t o_out = out.take(sizeof(int) * (2 + 3 * (size_t)dcap));
     const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
+    const size_t o_cache = work.take(guided_cache_bytes(M));
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -461,9 +475,9 @@ int pslam_match_guided_xyz(pslam_ctx* ctx, const float* map_xyz, const uint8_t* 
     uint8_t* d = ctx->d_in.p;
     int l = 0;
     CK(launch_guided_match((const float*)(d + o_mx), d + o_md, (const int*)(d + o_ml), M, (const float*)(d + o_cx),
-                           d + o_cd, (const int*)(d + o_cl), N, float_at_least(radius), accept_ratio, distance_mode,
-                           (int*)(ctx->d_work.p + o_cnt), (int*)(ctx->d_work.p + o_best), (int*)(ctx->d_out.p + o_out),
-                           dcap, ctx->stream, &l));
+                           d + o_cd, (const int*)(d + o_cl), N, sq_threshold(float_at_least(radius)), accept_ratio,
+                           distance_mode, (int*)(ctx->d_work.p + o_cnt), (int*)(ctx->d_work.p + o_best),
+                           ctx->d_work.p + o_cache, (int*)(ctx->d_out.p + o_out), dcap, ctx->stream, &l));
     ctx->launches += l;
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -575,8 +589,8 @@ int pslam_kabsch_batch(pslam_ctx* ctx, const double* A, const double* B, const i
 static int enqueue_f2m(pslam_ctx* ctx) {
     F2MState& s = ctx->f2m;
     int l = 0;
-    CK(launch_guided_match(s.map_xyz, s.map_desc, s.map_level, s.M, s.cur_xyz, s.cur_desc, s.cur_level, s.N, s.radius_f,
-                           s.ratio, s.mode, s.count, s.best, s.gout, s.cap, ctx->stream, &l));
+    CK(launch_guided_match(s.map_xyz, s.map_desc, s.map_level, s.M, s.cur_xyz, s.cur_desc, s.cur_level, s.N, s.sq_radius_f,
+                           s.ratio, s.mode, s.count, s.best, s.cache, s.gout, s.cap, ctx->stream, &l));
     CK(launch_ransac(s.map_xyz, s.cur_xyz, s.gout + 2, s.gout + 2 + s.cap, s.gout, 0, s.rp, s.ws, ctx->sm_count,
                      ctx->stream, &l));
     ctx->launches += l;
@@ -609,6 +623,7 @@ int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_
     const size_t o_g = out.take(sizeof(int) * (2 + 3 * (size_t)cap));
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
     const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
+    const size_t o_cache = work.take(guided_cache_bytes(M));
     RansacLayout L = plan_ransac(work, cap, num_hyp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
@@ -621,8 +636,9 @@ int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_
     F2MState& s = ctx->f2m;
     s.map_xyz = (const float*)(d + o_mx); s.map_desc = d + o_md; s.map_level = (const int*)(d + o_ml); s.M = M;
     s.cur_xyz = (const float*)(d + o_cx); s.cur_desc = d + o_cd; s.cur_level = (const int*)(d + o_cl); s.N = N;
-    s.radius_f = float_at_least(radius); s.ratio = accept_ratio; s.mode = distance_mode; s.cap = cap;
-    s.count = (int*)(ctx->d_work.p + o_cnt); s.best = (int*)(ctx->d_work.p + o_best); s.gout = (int*)(ctx->d_out.p + o_g);
+    s.sq_radius_f = sq_threshold(float_at_least(radius)); s.ratio = accept_ratio; s.mode = distance_mode; s.cap = cap;
+    s.count = (int*)(ctx->d_work.p + o_cnt); s.best = (int*)(ctx->d_work.p + o_best); s.cache = ctx->d_work.p + o_cache;
+    s.gout = (int*)(ctx->d_out.p + o_g);
     s.rp = rp; s.ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
     s.valid = true;
     TRY(enqueue_f2m(ctx));

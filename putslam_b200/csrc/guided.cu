@@ -5,8 +5,8 @@
 // the sphere radius AND predicted pyramid levels within one of each other (:699-711); distance =
 // popcount of the per-byte saturating difference (the reference's cv::Mat subtraction quirk, :719-721)
 // or XOR Hamming; best = first minimum (:714-726); every candidate with ratio*value <= best is emitted
-// (:734-747) in (j, i) order.  Three launches: count -> scan -> emit (gates are recomputed, they are a
-// handful of float ops; only gated candidates touch descriptors).
+// (:734-747) in (j, i) order.  Two launches: collect (gate, distances, best, ratio filter into a per-feature
+// candidate cache) -> scan + emit (one CTA).  Only gated candidates touch descriptors.
 #include "common.cuh"
 #include "geometry.cuh"
 #include "kernels.h"
@@ -36,25 +36,28 @@ struct GuidedArgs {
     const uint4* cur_desc;
     const int* cur_level;
     int N;
-    float radius_f;       // smallest float >= radius: (double)norm < radius  <=>  norm < radius_f
+    float sq_radius_f;    // squared-norm form of the gate: (double)sqrtf(s) < radius  <=>  s < sq_radius_f (exact)
     double accept_ratio;
     int mode;
 };
 
+constexpr int kCacheCap = 16;   // gated candidates cached per map feature; more than that -> recompute path
+
 __device__ __forceinline__ bool gate(const GuidedArgs& A, float px, float py, float pz, int lvl, const float* sxyz,
                                      const int* slvl, int i) {
     const float dx = px - sxyz[3 * i], dy = py - sxyz[3 * i + 1], dz = pz - sxyz[3 * i + 2];
-    const float nrm = norm3(dx, dy, dz);
+    const float yy = dy * dy, zz = dz * dz;
+    const float sq = dx * dx + (yy + zz);           // Eigen squaredNorm association
     const int li = slvl[i];
-    return (nrm < A.radius_f) && (li - 1 <= lvl) && (lvl <= li + 1);
+    return (sq < A.sq_radius_f) && (li - 1 <= lvl) && (lvl <= li + 1);
 }
 
-// EMIT = false: writes best[j] (value<<16 | i, 0xffffffff if no candidate) and count[j].
-// EMIT = true : writes the matches of feature j at offsets[j].
-template <bool EMIT>
+// Pass 1 (grid): one warp per map feature.  Gate all current keypoints, evaluate the descriptor distance of
+// the gated ones, keep (i, value) of the first kCacheCap in a per-feature cache, find the best (first
+// minimum), then filter the cached candidates by the accept ratio in place.  count[j] = matches of feature j;
+// bit 31 set = more than kCacheCap candidates, the emit pass recomputes that feature.
 __global__ void __launch_bounds__(kGThreads)
-guided_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict__ count, const int* __restrict__ offsets,
-              int cap, int* __restrict__ out_q, int* __restrict__ out_t, float* __restrict__ out_d) {
+guided_collect_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict__ count, uint2* __restrict__ cache) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     float* sxyz = reinterpret_cast<float*>(smem_raw);
     int* slvl = reinterpret_cast<int*>(sxyz + 3 * (size_t)A.N);
@@ -62,61 +65,81 @@ guided_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict__ count
     for (int i = threadIdx.x; i < A.N; i += kGThreads) slvl[i] = A.cur_level[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
     const int gw = blockIdx.x * kGWarps + (threadIdx.x >> 5);
     for (int j = gw; j < A.M; j += gridDim.x * kGWarps) {
         const float px = A.map_xyz[3 * j], py = A.map_xyz[3 * j + 1], pz = A.map_xyz[3 * j + 2];
         const int lvl = A.map_level[j];
         const uint4* dj = A.map_desc + 2 * (size_t)j;
-        uint32_t bestp;
-        if (!EMIT) {
-            bestp = 0xffffffffu;
-            for (int i = lane; i < A.N; i += 32)
-                if (gate(A, px, py, pz, lvl, sxyz, slvl, i))
-                    bestp = min(bestp, (desc_distance(dj, A.cur_desc + 2 * (size_t)i, A.mode) << 16) | (uint32_t)i);
-            bestp = warp_min_u32(bestp);
-            if (lane == 0) best[j] = bestp;
-        } else {
-            bestp = best[j];
+        uint2* slot = cache + (size_t)j * kCacheCap;
+        uint32_t bestp = 0xffffffffu;
+        int nc = 0;
+        for (int base = 0; base < A.N; base += 32) {
+            const int i = base + lane;
+            const bool g = i < A.N && gate(A, px, py, pz, lvl, sxyz, slvl, i);
+            const uint32_t bal = __ballot_sync(0xffffffffu, g);
+            if (bal == 0u) continue;
+            if (g) {
+                const uint32_t v = desc_distance(dj, A.cur_desc + 2 * (size_t)i, A.mode);
+                const int pos = nc + __popc(bal & lt);
+                if (pos < kCacheCap) slot[pos] = make_uint2((uint32_t)i, v);
+                bestp = min(bestp, (v << 16) | (uint32_t)i);
+            }
+            nc += __popc(bal);
         }
-        if (bestp == 0xffffffffu) {
-            if (!EMIT && lane == 0) count[j] = 0;
+        bestp = warp_min_u32(bestp);
+        if (lane == 0) best[j] = bestp;
+        if (nc == 0) {
+            if (lane == 0) count[j] = 0;
             continue;
         }
         const double bestVal = (double)(float)(bestp >> 16);
-        int run = EMIT ? offsets[j] : 0;
-        for (int base = 0; base < A.N; base += 32) {
-            const int i = base + lane;
-            bool emit = false;
-            uint32_t v = 0;
-            if (i < A.N && gate(A, px, py, pz, lvl, sxyz, slvl, i)) {
-                v = desc_distance(dj, A.cur_desc + 2 * (size_t)i, A.mode);
-                emit = __dmul_rn(A.accept_ratio, (double)(float)v) <= bestVal;
-            }
+        int cnt = 0;
+        if (nc <= kCacheCap) {
+            __syncwarp();
+            uint2 e = make_uint2(0, 0);
+            if (lane < nc) e = slot[lane];
+            const bool emit = lane < nc && __dmul_rn(A.accept_ratio, (double)(float)e.y) <= bestVal;
             const uint32_t bal = __ballot_sync(0xffffffffu, emit);
-            if (EMIT && emit) {
-                const int pos = run + __popc(bal & ((1u << lane) - 1u));
-                if (pos < cap) { out_q[pos] = j; out_t[pos] = i; out_d[pos] = (float)v; }
+            __syncwarp();
+            if (emit) slot[__popc(bal & lt)] = e;
+            cnt = __popc(bal);
+            if (lane == 0) count[j] = cnt;
+        } else {  // rare: recount by recomputation, flag for the emit pass
+            for (int base = 0; base < A.N; base += 32) {
+                const int i = base + lane;
+                bool emit = false;
+                if (i < A.N && gate(A, px, py, pz, lvl, sxyz, slvl, i)) {
+                    const uint32_t v = desc_distance(dj, A.cur_desc + 2 * (size_t)i, A.mode);
+                    emit = __dmul_rn(A.accept_ratio, (double)(float)v) <= bestVal;
+                }
+                cnt += __popc(__ballot_sync(0xffffffffu, emit));
             }
-            run += __popc(bal);
+            if (lane == 0) count[j] = cnt | (int)0x80000000;
         }
-        if (!EMIT && lane == 0) count[j] = run;
     }
 }
 
-// Exclusive scan of count[0..M) into offsets[0..M]; header[0] = total, header[1] = perfect matches
-// (best value < 0.1, i.e. 0; reference matcher.cpp:729-731).  Single CTA.
+// Pass 2 (one CTA): exclusive scan of the counts, then every warp copies its features' cached matches to
+// their place in the (j, i)-ordered output; flagged features are recomputed.  header[0] = total,
+// header[1] = perfect matches (best value 0; reference matcher.cpp:729-731).
 __global__ void __launch_bounds__(1024, 1)
-guided_scan_kernel(const int* __restrict__ count, const uint32_t* __restrict__ best, int M, int* __restrict__ offsets,
-                   int* __restrict__ header) {
+guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* __restrict__ count,
+                   const uint2* __restrict__ cache, int* __restrict__ offsets, int cap, int* __restrict__ header,
+                   int* __restrict__ out_q, int* __restrict__ out_t, float* __restrict__ out_d) {
     __shared__ int warp_tot[32];
-    __shared__ int carry, perfect;
+    __shared__ int carry, perfect, n_ovf;
+    __shared__ int ovf_list[1024];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; perfect = 0; }
+    const int M = A.M;
+    if (tid == 0) { carry = 0; perfect = 0; n_ovf = 0; }
     __syncthreads();
     int my_perfect = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     for (int base = 0; base < M; base += 1024) {
         const int j = base + tid;
-        const int c = (j < M) ? count[j] : 0;
+        const int cj = (j < M) ? count[j] : 0;
+        const int c = cj & 0x7fffffff;
         if (j < M && (best[j] >> 16) == 0u) ++my_perfect;
         int incl = c;
 #pragma unroll
@@ -132,9 +155,51 @@ guided_scan_kernel(const int* __restrict__ count, const uint32_t* __restrict__ b
             if (w < warp) woff += cw;
             tot += cw;
         }
-        if (j < M) offsets[j] = carry + woff + incl - c;
+        const int off = carry + woff + incl - c;
+        if (j < M) {
+            offsets[j] = off;
+            if (cj >= 0) {  // the thread that scanned feature j also copies its (few) cached matches
+                for (int e = 0; e < c; ++e) {
+                    const uint2 m = cache[(size_t)j * kCacheCap + e];
+                    const int pos = off + e;
+                    if (pos < cap) { out_q[pos] = j; out_t[pos] = (int)m.x; out_d[pos] = (float)m.y; }
+                }
+            } else if (c > 0) {
+                const int slot = atomicAdd(&n_ovf, 1);
+                if (slot < 1024) ovf_list[slot] = j;
+            }
+        }
         __syncthreads();
         if (tid == 0) carry += tot;
+        __syncthreads();
+        // features with more candidates than the cache holds: recomputed by whole warps, in any order
+        // (their output positions are fixed by `offsets`)
+        const int novf = n_ovf < 1024 ? n_ovf : 1024;
+        for (int a = warp; a < novf; a += 32) {
+            const int jj = ovf_list[a];
+            const float px = A.map_xyz[3 * jj], py = A.map_xyz[3 * jj + 1], pz = A.map_xyz[3 * jj + 2];
+            const int lvl = A.map_level[jj];
+            const uint4* dj = A.map_desc + 2 * (size_t)jj;
+            const double bestVal = (double)(float)(best[jj] >> 16);
+            int run = offsets[jj];
+            for (int b0 = 0; b0 < A.N; b0 += 32) {
+                const int i = b0 + lane;
+                bool emit = false;
+                uint32_t v = 0;
+                if (i < A.N && gate(A, px, py, pz, lvl, A.cur_xyz, A.cur_level, i)) {
+                    v = desc_distance(dj, A.cur_desc + 2 * (size_t)i, A.mode);
+                    emit = __dmul_rn(A.accept_ratio, (double)(float)v) <= bestVal;
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, emit);
+                if (emit) {
+                    const int pos = run + __popc(bal & lt);
+                    if (pos < cap) { out_q[pos] = jj; out_t[pos] = i; out_d[pos] = (float)v; }
+                }
+                run += __popc(bal);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) n_ovf = 0;
         __syncthreads();
     }
     my_perfect = (int)warp_add_u32((uint32_t)my_perfect);
@@ -143,14 +208,16 @@ guided_scan_kernel(const int* __restrict__ count, const uint32_t* __restrict__ b
     if (tid == 0) { offsets[M] = carry; header[0] = carry; header[1] = perfect; }
 }
 
+size_t guided_cache_bytes(int M) { return sizeof(uint2) * (size_t)kCacheCap * (size_t)(M > 0 ? M : 1); }
+
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
-                                float radius_f, double accept_ratio, int mode, int* d_count, int* d_best, int* d_out,
-                                int cap, cudaStream_t st, int* launches) {
+                                float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
+                                int* d_out, int cap, cudaStream_t st, int* launches) {
     GuidedArgs A;
     A.map_xyz = d_map_xyz; A.map_desc = reinterpret_cast<const uint4*>(d_map_desc); A.map_level = d_map_level; A.M = M;
     A.cur_xyz = d_cur_xyz; A.cur_desc = reinterpret_cast<const uint4*>(d_cur_desc); A.cur_level = d_cur_level; A.N = N;
-    A.radius_f = radius_f; A.accept_ratio = accept_ratio; A.mode = mode;
+    A.sq_radius_f = sq_radius_f; A.accept_ratio = accept_ratio; A.mode = mode;
     // d_count: M counts followed by M+1 offsets
     int* d_offsets = d_count + M;
     int* out_q = d_out + 2;
@@ -162,15 +229,13 @@ cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_des
     if (grid < 1) grid = 1;
     cudaError_t e;
     if (smem > 48 * 1024) {
-        if ((e = cudaFuncSetAttribute(guided_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(guided_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(guided_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     }
-    guided_kernel<false><<<grid, kGThreads, smem, st>>>(A, reinterpret_cast<uint32_t*>(d_best), d_count, nullptr, cap,
-                                                        nullptr, nullptr, nullptr);
-    guided_scan_kernel<<<1, 1024, 0, st>>>(d_count, reinterpret_cast<const uint32_t*>(d_best), M, d_offsets, d_out);
-    guided_kernel<true><<<grid, kGThreads, smem, st>>>(A, reinterpret_cast<uint32_t*>(d_best), d_count, d_offsets, cap,
-                                                       out_q, out_t, out_d);
-    if (launches) *launches += 3;
+    guided_collect_kernel<<<grid, kGThreads, smem, st>>>(A, reinterpret_cast<uint32_t*>(d_best), d_count,
+                                                         reinterpret_cast<uint2*>(d_cache));
+    guided_emit_kernel<<<1, 1024, 0, st>>>(A, reinterpret_cast<const uint32_t*>(d_best), d_count,
+                                           reinterpret_cast<const uint2*>(d_cache), d_offsets, cap, d_out, out_q, out_t, out_d);
+    if (launches) *launches += 2;
     return cudaGetLastError();
 }
 

@@ -33,15 +33,17 @@ cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsi
 
 // ---- guided.cu -------------------------------------------------------------------------------
 // d_out: int[2 + 3*cap] = {n_total, perfect, queryIdx[cap], trainIdx[cap], distance(float)[cap]}
+size_t guided_cache_bytes(int M);
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
-                                float radius_f, double accept_ratio, int mode, int* d_count, int* d_best, int* d_out,
-                                int cap, cudaStream_t st, int* launches);
+                                float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
+                                int* d_out, int cap, cudaStream_t st, int* launches);
 
 // ---- ransac.cu -------------------------------------------------------------------------------
 struct RansacDeviceParams {
     int error_version;
     float thr_euclid_f;       // smallest float >= inlierThresholdEuclidean (float<double compare, exact)
+    float sq_thr_euclid_f;    // smallest float T with sqrtf(T) >= thr_euclid_f (squared-norm form of the same test)
     double thr_euclid;
     double thr_reproj;
     double min_inlier_ratio;
@@ -56,6 +58,7 @@ struct RansacWorkspace {
     int* keep;         // m_cap     : original match index of filtered match k
     int* n_filtered;   // 1
     int* counts;       // h_cap
+    float* models;     // 12 * h_cap : per-hypothesis R (row-major) and t
     int* result;       // header (see ransac.cu) + inlier list (m_cap)
     int m_cap, h_cap;
 };

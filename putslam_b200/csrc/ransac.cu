@@ -2,8 +2,8 @@
 //
 //   ransac_filter_kernel  : drop matches with NaN / z outside [0.1, 6] and gather the surviving pairs
 //                           into SoA form (reference src/TransformEst/RANSAC.cpp:65-80)
-//   K4 ransac_score_kernel: one warp per hypothesis -- counter-based sample of 3 matches, 3-point
-//                           Umeyama, score every match, inlier count by warp reduction
+//   K4a ransac_model_kernel: one thread per hypothesis -- counter-based sample of 3 matches, 3-point Umeyama
+//   K4b ransac_score_kernel: one warp per hypothesis -- score every match, inlier count by warp reduction
 //                           (reference RANSAC.cpp:87-150 loop body, :180-281, :325-436)
 //   K5 ransac_select_kernel: replay of saveBetterModel / iterationCount (RANSAC.cpp:438-461) over the
 //                           per-hypothesis counts, inlier list of the winner, Umeyama refit over all its
@@ -79,6 +79,7 @@ ransac_filter_kernel(const float* __restrict__ prev, const float* __restrict__ c
 struct Scorer {
     int ev;
     float thr_f;
+    float sq_thr_f;   // smallest float T with sqrtf(T) >= thr_f:  sqrtf(s) < thr_f  <=>  s < T  (sqrt is monotone)
     double thr, thr_reproj;
     float fx, fy, cx, cy;
 };
@@ -96,9 +97,11 @@ __device__ __forceinline__ bool inlier_test(const Scorer& S, const float (&R)[9]
     float ex, ey, ez;
     rigid_apply(R, t, cx, cy, cz, ex, ey, ez);
     if (force_euclid || S.ev == 0 || S.ev == 4) {
-        const float nrm = norm3(ex - px, ey - py, ez - pz);
-        if (S.ev == 4) return (double)nrm < S.thr * (double)pz;
-        return nrm < S.thr_f;  // == (double)nrm < thr, thr_f = smallest float >= thr
+        const float dx = ex - px, dy = ey - py, dz = ez - pz;
+        if (S.ev == 4) return (double)norm3(dx, dy, dz) < S.thr * (double)pz;
+        // (double)sqrtf(s) < thr  <=>  sqrtf(s) < thr_f  <=>  s < sq_thr_f : same predicate, no square root
+        const float yy = dy * dy, zz = dz * dz;
+        return dx * dx + (yy + zz) < S.sq_thr_f;
     }
     float nx, ny, nz;
     rigid_apply(Ri, ti, px, py, pz, nx, ny, nz);
@@ -150,10 +153,31 @@ __device__ __forceinline__ Rigid3f hypothesis_model(const float* __restrict__ pt
 }
 
 constexpr int kScoreThreads = 256;
+constexpr int kModelThreads = 64;
 
+// K4a: one THREAD per hypothesis -- counter-based sample of 3 matches and the 3-point Umeyama model
+// (Jacobi SVD is ~2000 dependent instructions: running it once per thread instead of redundantly on the
+// 32 lanes of a scoring warp removes most of the stage's instruction count).  counts[h] = -1 marks a
+// degenerate model (NaN, reference RANSAC.cpp:238-242), 0 otherwise.
+__global__ void __launch_bounds__(kModelThreads)
+ransac_model_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ n_filtered, int min_matches,
+                    uint32_t seed_lo, uint32_t seed_hi, int H, int* __restrict__ counts, float* __restrict__ models) {
+    const int mf = *n_filtered;
+    if (mf < min_matches || mf < 3) return;
+    const int h = blockIdx.x * kModelThreads + threadIdx.x;
+    if (h >= H) return;
+    const Rigid3f M = hypothesis_model(pts, m_cap, mf, seed_lo, seed_hi, (uint32_t)h);
+    counts[h] = M.ok ? 0 : -1;
+    float4* mp = reinterpret_cast<float4*>(models + 12 * (size_t)h);
+    mp[0] = make_float4(M.R[0], M.R[1], M.R[2], M.R[3]);
+    mp[1] = make_float4(M.R[4], M.R[5], M.R[6], M.R[7]);
+    mp[2] = make_float4(M.R[8], M.t[0], M.t[1], M.t[2]);
+}
+
+// K4b: one WARP per hypothesis -- lanes stride over the matches, inlier count by warp reduction.
 __global__ void __launch_bounds__(kScoreThreads)
 ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ n_filtered, int min_matches,
-                    Scorer S, uint32_t seed_lo, uint32_t seed_hi, int H, int* __restrict__ counts) {
+                    Scorer S, int H, int* __restrict__ counts, const float* __restrict__ models) {
     const int mf = *n_filtered;
     if (mf < min_matches || mf < 3) return;
     const int lane = threadIdx.x & 31;
@@ -165,11 +189,12 @@ ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restr
     const float* cy = pts + 4 * (size_t)m_cap;
     const float* cz = pts + 5 * (size_t)m_cap;
     for (int h = blockIdx.x * (kScoreThreads / 32) + (threadIdx.x >> 5); h < H; h += warps_total) {
-        const Rigid3f M = hypothesis_model(pts, m_cap, mf, seed_lo, seed_hi, (uint32_t)h);
-        if (!M.ok) {
-            if (lane == 0) counts[h] = -1;
-            continue;
-        }
+        if (counts[h] < 0) continue;   // degenerate model
+        Rigid3f M;
+        const float4* mp = reinterpret_cast<const float4*>(models + 12 * (size_t)h);
+        const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+        M.R[0] = m0.x; M.R[1] = m0.y; M.R[2] = m0.z; M.R[3] = m0.w; M.R[4] = m1.x; M.R[5] = m1.y; M.R[6] = m1.z;
+        M.R[7] = m1.w; M.R[8] = m2.x; M.t[0] = m2.y; M.t[1] = m2.z; M.t[2] = m2.w; M.ok = true;
         float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
         if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
         int c = 0;
@@ -195,9 +220,10 @@ constexpr int kSelThreads = 1024;
 
 __global__ void __launch_bounds__(kSelThreads, 1)
 ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
-                     const int* __restrict__ n_filtered, const int* __restrict__ counts, int H, int adaptive,
+                     const int* __restrict__ n_filtered, const int* __restrict__ counts,
+                     const float* __restrict__ models, int H, int adaptive,
                      int min_matches, double min_ratio, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
-                     int* __restrict__ inl_tmp /* m_cap scratch */, int* __restrict__ result) {
+                     int* __restrict__ inl_tmp /* m_cap scratch */, int stage_cap, int* __restrict__ result) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     __shared__ unsigned long long best_key;
@@ -277,8 +303,13 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     const float* cy = pts + 4 * (size_t)m_cap;
     const float* cz = pts + 5 * (size_t)m_cap;
 
-    // ---- inlier list of the winner (ordered) ----
-    const Rigid3f M = hypothesis_model(pts, m_cap, mf, seed_lo, seed_hi, (uint32_t)win);
+    // ---- inlier list of the winner (ordered); its model was stored by the scoring kernel ----
+    Rigid3f M;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M.R[i] = models[12 * (size_t)win + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) M.t[i] = models[12 * (size_t)win + 9 + i];
+    M.ok = true;
     float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
     if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
     for (int base = 0; base < mf; base += kSelThreads) {
@@ -303,23 +334,46 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     __syncthreads();
 
     // ---- refit: Umeyama over all inliers; every sum is a sequential float chain, one thread per chain ----
+    // The inlier coordinates are first gathered into shared memory (all threads, coalesced index reads) so
+    // that the 15 chain threads stream them with pipelined LDS instead of dependent global loads.
+    extern __shared__ float s_pts[];                      // 6 x n_stage (dst xyz | src xyz), SoA
+    const int n_stage = n_in <= stage_cap ? n_in : 0;     // too many inliers for shared memory: read global
+    for (int k = tid; k < n_stage; k += kSelThreads) {
+        const int id = inl_tmp[k];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) s_pts[a * n_stage + k] = pts[(size_t)a * m_cap + id];
+    }
+    __syncthreads();
     const float one_over_n = __fdiv_rn(1.f, (float)n_in);
     if (tid < 6) {
-        const float* col = pts + (size_t)tid * m_cap;  // 0..2 prev (dst), 3..5 cur (src)
         float s = 0.f;
-        for (int k = 0; k < n_in; ++k) s = s + col[inl_tmp[k]];
+        if (n_stage) {
+            const float* col = s_pts + tid * n_stage;
+#pragma unroll 8
+            for (int k = 0; k < n_in; ++k) s = s + col[k];
+        } else {
+            const float* col = pts + (size_t)tid * m_cap;  // 0..2 prev (dst), 3..5 cur (src)
+            for (int k = 0; k < n_in; ++k) s = s + col[inl_tmp[k]];
+        }
         s_mean[tid] = s * one_over_n;
     }
     __syncthreads();
     if (tid < 9) {
         const int i = tid / 3, j = tid % 3;
-        const float* dcol = pts + (size_t)i * m_cap;
-        const float* scol = pts + (size_t)(3 + j) * m_cap;
         const float dmean = s_mean[i], smean = s_mean[3 + j];
         float s = 0.f;
-        for (int k = 0; k < n_in; ++k) {
-            const int id = inl_tmp[k];
-            s = s + (dcol[id] - dmean) * (scol[id] - smean);
+        if (n_stage) {
+            const float* dcol = s_pts + i * n_stage;
+            const float* scol = s_pts + (3 + j) * n_stage;
+#pragma unroll 8
+            for (int k = 0; k < n_in; ++k) s = s + (dcol[k] - dmean) * (scol[k] - smean);
+        } else {
+            const float* dcol = pts + (size_t)i * m_cap;
+            const float* scol = pts + (size_t)(3 + j) * m_cap;
+            for (int k = 0; k < n_in; ++k) {
+                const int id = inl_tmp[k];
+                s = s + (dcol[id] - dmean) * (scol[id] - smean);
+            }
         }
         s_sig[tid] = one_over_n * s;
     }
@@ -396,6 +450,7 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     Scorer S;
     S.ev = P.error_version;
     S.thr_f = P.thr_euclid_f;
+    S.sq_thr_f = P.sq_thr_euclid_f;
     S.thr = P.thr_euclid;
     S.thr_reproj = P.thr_reproj;
     S.fx = P.fx; S.fy = P.fy; S.cx = P.cx; S.cy = P.cy;
@@ -407,12 +462,24 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     int grid = (H + warps_per_cta - 1) / warps_per_cta;
     const int max_grid = sm_count * 8;
     if (grid > max_grid) grid = max_grid;
-    ransac_score_kernel<<<grid, kScoreThreads, 0, st>>>(ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, P.seed_lo,
-                                                        P.seed_hi, H, ws.counts);
-    ransac_select_kernel<<<1, kSelThreads, 0, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, H, adaptive,
-                                                    P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
-                                                    ws.keep + ws.m_cap /* scratch: second half of keep */, ws.result);
-    if (launches) *launches += 3;
+    ransac_model_kernel<<<(H + kModelThreads - 1) / kModelThreads, kModelThreads, 0, st>>>(
+        ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, P.seed_lo, P.seed_hi, H, ws.counts, ws.models);
+    ransac_score_kernel<<<grid, kScoreThreads, 0, st>>>(ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, H, ws.counts,
+                                                        ws.models);
+    // shared-memory staging of the winner's inliers for the refit: up to 8192 inliers (192 KB)
+    int stage_cap = ws.m_cap < 8192 ? ws.m_cap : 8192;
+    const size_t sel_smem = sizeof(float) * 6 * (size_t)stage_cap;
+    static bool sel_cfg = false;
+    if (!sel_cfg) {
+        cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4);
+        if (e != cudaSuccess) return e;
+        sel_cfg = true;
+    }
+    ransac_select_kernel<<<1, kSelThreads, sel_smem, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, ws.models, H, adaptive,
+                                                           P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
+                                                           ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap,
+                                                           ws.result);
+    if (launches) *launches += 4;
     return cudaGetLastError();
 }
 

@@ -146,6 +146,22 @@ def test_guided_match_vs_oracle(ctx, O, M, N, seed, mode):
         assert np.array_equal(out["q"], q) and np.array_equal(out["t"], t) and np.array_equal(out["d"], d)
 
 
+def test_guided_match_many_candidates(ctx, O):
+    """More gated candidates per map feature than the kernel's per-feature cache: the recompute path."""
+    from putslam_b200 import host, synth
+    mf = synth.map_frame(M=700, N=400, n_reobs=300, seed=12)
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    for mode in (0, 1):
+        for radius, ratio in ((10.0, 0.1), (1.0, 0.9), (10.0, 1.0)):
+            out = ctx.match_guided_xyz(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, radius, ratio,
+                                       mode, cap=400000)
+            q, t, d, perfect = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, radius, ratio, mode)
+            assert out["total"] == q.size and out["perfect"] == perfect
+            assert np.array_equal(out["q"], q) and np.array_equal(out["t"], t) and np.array_equal(out["d"], d)
+    assert q.size > 700
+
+
 def test_guided_match_capacity_and_empty(ctx, O):
     from putslam_b200 import host, synth
     mf = synth.map_frame(M=600, N=300, n_reobs=200, seed=9)
