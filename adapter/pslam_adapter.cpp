@@ -261,6 +261,44 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return RANSAC::pointInlierRatio(inlierMatches, matches);   // matcher.cpp:797
 }
 
+double MatcherB200::matchFeatureLoopClosureCore(cv::Mat descriptors0, const std::vector<Eigen::Vector3f>& points3D0,
+                                                cv::Mat descriptors1, const std::vector<Eigen::Vector3f>& points3D1,
+                                                const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,
+                                                std::vector<std::pair<int, int>>& pairedFeatures,
+                                                Eigen::Matrix4f& estimatedTransformation) {
+    const int n0 = descriptors0.rows, n1 = descriptors1.rows;
+    if (n0 < 10 || n1 < 10) {   // matcher.cpp:830-834
+        std::cout << "Too few features :(" << std::endl;
+        return 0;
+    }
+    std::vector<uint8_t> t0, t1;
+    const uint8_t* d0 = contiguousBytes(descriptors0, 32, t0);
+    const uint8_t* d1 = contiguousBytes(descriptors1, 32, t1);
+    RANSAC::parameters rp = ransacParams;
+    rp.errorVersion = rp.errorVersionMap;   // matcher.cpp:843-844
+    float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+    if (!cameraMatrix.empty()) {
+        fx = cameraMatrix.at<float>(0, 0); fy = cameraMatrix.at<float>(1, 1);
+        cx = cameraMatrix.at<float>(0, 2); cy = cameraMatrix.at<float>(1, 2);
+    }
+    pslam_ransac_params a = toAbi(rp, fx, fy, cx, cy);
+    const int cap = std::min(n0, n1);
+    std::vector<int> mq((size_t)cap), mt((size_t)cap), inl((size_t)cap);
+    std::vector<float> md((size_t)cap);
+    pslam_frame_result res;
+    pslam_ctx* c = dev_.ctx();
+    const int r = c ? pslam_loop_closure_pair(c, d0, points3D0[0].data(), n0, d1, points3D1[0].data(), n1, &a, seed_, numHyp_,
+                                              mq.data(), mt.data(), md.data(), inl.data(), &res)
+                    : PSLAM_ERR_NO_DEVICE;
+    estimatedTransformation = Eigen::Matrix4f::Identity();
+    pairedFeatures.clear();
+    if (r != PSLAM_OK) { logError(c, "matchFeatureLoopClosure", r); return -1.0; }
+    if (res.n_matches <= 0) return -1.0;   // matcher.cpp:838-839
+    std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
+    for (int k = 0; k < res.n_inliers; ++k) pairedFeatures.push_back(std::make_pair(mq[(size_t)inl[k]], mt[(size_t)inl[k]]));
+    return res.inlier_ratio;
+}
+
 // ---- Kabsch ----------------------------------------------------------------------------------------
 Mat34& KabschEst::computeTransformation(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB) {
     transformation.setIdentity();

@@ -14,6 +14,7 @@
 // those values.  There is no CPU fallback.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../include/pslam_b200.h"
@@ -99,6 +100,13 @@ public:
                         double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch, int computationNumber,
                         const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix, Eigen::Matrix4f& estimatedTransformation,
                         std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches, bool xorDistance = false);
+    // Matcher::matchFeatureLoopClosure (src/Matcher/matcher.cpp:802-861) after its MapFeature gathering loop (:809-827):
+    // descriptors / 3-D points of the two frames -> paired feature indices, transform, and the value it returns
+    // (0 for fewer than 10 features, -1.0 for no matches, else pointInlierRatio).
+    double matchFeatureLoopClosureCore(cv::Mat descriptors0, const std::vector<Eigen::Vector3f>& points3D0, cv::Mat descriptors1,
+                                       const std::vector<Eigen::Vector3f>& points3D1, const RANSAC::parameters& ransacParams,
+                                       cv::Mat cameraMatrix, std::vector<std::pair<int, int>>& pairedFeatures,
+                                       Eigen::Matrix4f& estimatedTransformation);
     void setSeed(uint64_t s) { seed_ = s; }
     void setFixedHypotheses(int n) { numHyp_ = n; }
 private:

@@ -86,6 +86,13 @@ PSLAM_API int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const ui
                                 float* uv_undist_out, float* xyz_out, double* det_dist_out, double* cov_out,
                                 const pslam_cov_params* cov);
 
+/* Batched DepthSensorModel::informationMatrixFromImageCoordinates (src/Grabber/depthSensorModel.cpp:55-59), the
+ * measurement information FeaturesMap::addFeatures / addMeasurements attach to every map measurement
+ * (src/Map/featuresMap.cpp:110-114, 263-267): uvz = n x {u, v, depth} doubles (u, v truncated to unsigned like the
+ * reference), info_out n x 9 row-major = inverse of the sensor covariance, cov_out (nullable) the covariance. */
+PSLAM_API int pslam_information_matrices(pslam_ctx* ctx, const double* uvz, int n, const pslam_cov_params* cov,
+                                         double* info_out, double* cov_out);
+
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
  * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==
@@ -190,6 +197,15 @@ PSLAM_API int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uin
                                  const pslam_ransac_params* params, uint64_t seed, int num_hyp, int match_cap,
                                  int* match_query_out, int* match_train_out, float* match_dist_out,
                                  int* inlier_idx_out, pslam_frame_result* result);
+
+/* Loop-closure pair verification: Matcher::matchFeatureLoopClosure (src/Matcher/matcher.cpp:802-861) minus the
+ * MapFeature marshalling: performMatching(desc0, desc1) -> RANSAC(xyz0, xyz1, matches) in one submission.
+ * result->inlier_ratio follows the reference: 0 when either set has fewer than 10 features (:830-834), -1 when
+ * there are no matches (:838-839), else pointInlierRatio.  Match / inlier buffers sized min(n0, n1). */
+PSLAM_API int pslam_loop_closure_pair(pslam_ctx* ctx, const uint8_t* desc0, const float* xyz0, int n0,
+                                      const uint8_t* desc1, const float* xyz1, int n1, const pslam_ransac_params* params,
+                                      uint64_t seed, int num_hyp, int* match_query_out, int* match_train_out,
+                                      float* match_dist_out, int* inlier_idx_out, pslam_frame_result* result);
 
 /* Re-run the kernels of the last pslam_frame_to_map call on the inputs already resident in HBM:
  * no host<->device copies, no synchronisation (device-time measurements; matchXYZ retries). */

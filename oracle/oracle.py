@@ -173,6 +173,16 @@ def compute_cov(u, v, depth, fx, fy, cx, cy, varU, varV, coefs):
     return cov.reshape(3, 3)
 
 
+def information_matrix(u, v, z, fx, fy, cx, cy, varU, varV, coefs):
+    """-> (cov[3,3], info[3,3]) of DepthSensorModel::informationMatrixFromImageCoordinates"""
+    c = np.ascontiguousarray(coefs, np.float64)
+    cov = np.empty(9, np.float64); info = np.empty(9, np.float64)
+    lib().orc_information_matrix(C.c_double(u), C.c_double(v), C.c_double(z), C.c_double(fx), C.c_double(fy),
+                                 C.c_double(cx), C.c_double(cy), C.c_double(varU), C.c_double(varV),
+                                 _p(c, C.c_double), _p(cov, C.c_double), _p(info, C.c_double))
+    return cov.reshape(3, 3), info.reshape(3, 3)
+
+
 def svd3f(A):
     A = np.ascontiguousarray(A, np.float32)
     U = np.empty((3, 3), np.float32); S = np.empty(3, np.float32); V = np.empty((3, 3), np.float32)

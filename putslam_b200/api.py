@@ -17,10 +17,10 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
-    "pslam_frame_to_map", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
+    "pslam_frame_to_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
@@ -159,6 +159,14 @@ class Context:
                                             C.byref(cov) if cov is not None else None))
         return dict(xyz=xyz, uv_undist=und, det_dist=dd, cov=covo)
 
+    def information_matrices(self, uvz, cov):
+        uvz = _arr(uvz, np.float64, 3)
+        n = uvz.shape[0] if uvz.size else 0
+        info = np.empty((n, 3, 3), np.float64); covo = np.empty((n, 3, 3), np.float64)
+        self._ck(self.lib.pslam_information_matrices(self.h, _p(uvz, C.c_double), n, C.byref(cov), _p(info, C.c_double),
+                                                     _p(covo, C.c_double)))
+        return info, covo
+
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):
         q = _arr(query, np.uint8); t = _arr(train, np.uint8)
@@ -277,6 +285,23 @@ class Context:
         return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
                     T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
                     inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used, n_filtered=res.n_filtered)
+
+    def loop_closure_pair(self, desc0, xyz0, desc1, xyz1, params=None, seed=0, num_hyp=0):
+        d0 = _arr(desc0, np.uint8); x0 = _arr(xyz0, np.float32, 3); d1 = _arr(desc1, np.uint8); x1 = _arr(xyz1, np.float32, 3)
+        n0 = d0.shape[0] if d0.ndim == 2 else 0
+        n1 = d1.shape[0] if d1.ndim == 2 else 0
+        params = params or default_ransac_params()
+        cap = max(1, min(n0, n1))
+        mq = np.empty(cap, np.int32); mt = np.empty(cap, np.int32); md = np.empty(cap, np.float32); inl = np.empty(cap, np.int32)
+        res = FrameResult()
+        self._ck(self.lib.pslam_loop_closure_pair(self.h, _p(d0, C.c_uint8), _p(x0, C.c_float), n0, _p(d1, C.c_uint8),
+                                                  _p(x1, C.c_float), n1, C.byref(params), C.c_uint64(seed), num_hyp,
+                                                  _p(mq, C.c_int), _p(mt, C.c_int), _p(md, C.c_float), _p(inl, C.c_int),
+                                                  C.byref(res)))
+        n = res.n_matches
+        return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
+                    T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
+                    inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used)
 
     def frame_to_map_resident(self):
         self._ck(self.lib.pslam_frame_to_map_resident(self.h))

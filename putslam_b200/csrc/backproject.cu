@@ -98,6 +98,67 @@ __global__ void backproject_kernel(const float* __restrict__ uv, int n, const ui
     }
 }
 
+// 3x3 double inverse by cofactors (the closed form Eigen uses for Matrix3d::inverse()).
+__device__ __forceinline__ void inverse3d(const double (&m)[9], double (&r)[9]) {
+#define CF(i, j) (m[3 * (((i) + 1) % 3) + (((j) + 1) % 3)] * m[3 * (((i) + 2) % 3) + (((j) + 2) % 3)] - \
+                  m[3 * (((i) + 1) % 3) + (((j) + 2) % 3)] * m[3 * (((i) + 2) % 3) + (((j) + 1) % 3)])
+    const double c00 = CF(0, 0), c10 = CF(1, 0), c20 = CF(2, 0);
+    const double det = c00 * m[0] + (c10 * m[3] + c20 * m[6]);
+    const double invdet = __ddiv_rn(1.0, det);
+    r[0] = c00 * invdet; r[1] = c10 * invdet; r[2] = c20 * invdet;
+    r[3] = CF(0, 1) * invdet; r[4] = CF(1, 1) * invdet; r[5] = CF(2, 1) * invdet;
+    r[6] = CF(0, 2) * invdet; r[7] = CF(1, 2) * invdet; r[8] = CF(2, 2) * invdet;
+#undef CF
+}
+
+// DepthSensorModel::informationMatrixFromImageCoordinates (reference src/Grabber/depthSensorModel.cpp:55-59),
+// batched: uvz = n x {u, v, depth} doubles; u, v truncated to unsigned like the reference's cast.
+__global__ void information_kernel(const double* __restrict__ uvz, int n, pslam_cov_params cp, double* __restrict__ cov_out,
+                                   double* __restrict__ info_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned ui = (unsigned)(unsigned long long)uvz[3 * i], vi = (unsigned)(unsigned long long)uvz[3 * i + 1];
+    const double d = uvz[3 * i + 2];
+    const double J[9] = {d / cp.fx, 0.0, ((double)ui / cp.fx) - (cp.cx / cp.fx), 0.0, d / cp.fy,
+                         ((double)vi / cp.fy) - (cp.cy / cp.fy), 0.0, 0.0, 1.0};
+    const double R[3] = {cp.var_u, cp.var_v,
+                         cp.dist_var_coefs[0] * cube_rn(d) + cp.dist_var_coefs[1] * (d * d) + cp.dist_var_coefs[2] * d +
+                             cp.dist_var_coefs[3]};
+    double JR[9], cov[9], info[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            double s = J[3 * a + 0] * (b == 0 ? R[0] : 0.0);
+            s = s + J[3 * a + 1] * (b == 1 ? R[1] : 0.0);
+            s = s + J[3 * a + 2] * (b == 2 ? R[2] : 0.0);
+            JR[3 * a + b] = s;
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            double s = JR[3 * a + 0] * J[3 * b + 0];
+            s = s + JR[3 * a + 1] * J[3 * b + 1];
+            s = s + JR[3 * a + 2] * J[3 * b + 2];
+            cov[3 * a + b] = s;
+        }
+    inverse3d(cov, info);
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+        if (cov_out) cov_out[9 * (size_t)i + a] = cov[a];
+        info_out[9 * (size_t)i + a] = info[a];
+    }
+}
+
+cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_params& cp, double* d_cov, double* d_info,
+                               cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    information_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_uvz, n, cp, d_cov, d_info);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth, int W, int H, int stride,
                                const pslam_camera& cam, int undistort, double depth_scale, float* d_uv_und,
                                float* d_xyz, double* d_det_dist, double* d_cov, const pslam_cov_params* cov,

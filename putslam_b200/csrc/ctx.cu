@@ -371,6 +371,30 @@ int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* de
     return PSLAM_OK;
 }
 
+int pslam_information_matrices(pslam_ctx* ctx, const double* uvz, int n, const pslam_cov_params* cov, double* info_out,
+                               double* cov_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n < 0 || !cov || (n > 0 && (!uvz || !info_out))) return fail(ctx, PSLAM_ERR_ARG, "pslam_information_matrices: bad argument");
+    if (n == 0) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_in = in.take(24 * (size_t)n);
+    const size_t o_info = out.take(72 * (size_t)n), o_cov = out.take(72 * (size_t)n);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    memcpy(ctx->h_in.p + o_in, uvz, 24 * (size_t)n);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_information((const double*)(ctx->d_in.p + o_in), n, *cov, cov_out ? (double*)(ctx->d_out.p + o_cov) : nullptr,
+                          (double*)(ctx->d_out.p + o_info), ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(info_out, ctx->h_out.p + o_info, 72 * (size_t)n);
+    if (cov_out) memcpy(cov_out, ctx->h_out.p + o_cov, 72 * (size_t)n);
+    return PSLAM_OK;
+}
+
 // ---- stage 2 ----------------------------------------------------------------------------------
 int pslam_match_bf_mutual(pslam_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int desc_bytes,
                           int* out_query_idx, int* out_train_idx, float* out_distance, int* n_out) {
@@ -758,6 +782,64 @@ int pslam_frame_to_frame(pslam_ctx* ctx, const uint8_t* prev_desc, const float* 
         memcpy(match_dist_out, mo + 1 + 2 * cap, 4 * (size_t)n);
     }
     if (n_prev == 0) return PSLAM_OK;
+    unpack_ransac_result((const int*)(ctx->h_out.p + o_res), result->T, inlier_idx_out, &result->n_inliers,
+                         &result->best_ratio, &result->hyp_used, &result->n_filtered);
+    std::vector<int> inl_t((size_t)result->n_inliers);
+    for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
+    result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
+    return PSLAM_OK;
+}
+
+int pslam_loop_closure_pair(pslam_ctx* ctx, const uint8_t* desc0, const float* xyz0, int n0, const uint8_t* desc1,
+                            const float* xyz1, int n1, const pslam_ransac_params* params, uint64_t seed, int num_hyp,
+                            int* match_query_out, int* match_train_out, float* match_dist_out, int* inlier_idx_out,
+                            pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!result || n0 < 0 || n1 < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_loop_closure_pair: bad argument");
+    memset(result, 0, sizeof(*result));
+    for (int i = 0; i < 16; ++i) result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    RansacDeviceParams rp;
+    TRY(make_ransac_params(ctx, params, seed, num_hyp, rp));
+    if (n0 > PSLAM_MAX_BF_ROWS || n1 > PSLAM_MAX_BF_ROWS) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "more than %d features", PSLAM_MAX_BF_ROWS);
+    if (n0 < 10 || n1 < 10) return PSLAM_OK;   // "Too few features" -> 0 (matcher.cpp:830-834)
+    if (!desc0 || !xyz0 || !desc1 || !xyz1 || !match_query_out || !match_train_out || !match_dist_out || !inlier_idx_out)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_loop_closure_pair: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = n0 < n1 ? n0 : n1;
+    Arena in, out, work;
+    const size_t o_d0 = in.take(32 * (size_t)n0), o_x0 = in.take(12 * (size_t)n0);
+    const size_t o_d1 = in.take(32 * (size_t)n1), o_x1 = in.take(12 * (size_t)n1);
+    const size_t o_m = out.take(sizeof(int) * (1 + 3 * (size_t)cap));
+    const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
+    const size_t o_row = work.take(4 * (size_t)n0), o_col = work.take(4 * (size_t)n1);
+    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    ctx->f2m.valid = false; ctx->f2f.valid = false;   // the arenas are reused
+    uint8_t* h = ctx->h_in.p;
+    memcpy(h + o_d0, desc0, 32 * (size_t)n0); memcpy(h + o_x0, xyz0, 12 * (size_t)n0);
+    memcpy(h + o_d1, desc1, 32 * (size_t)n1); memcpy(h + o_x1, xyz1, 12 * (size_t)n1);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p;
+    int* mout = (int*)(ctx->d_out.p + o_m);
+    RansacWorkspace ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+    int l = 0;
+    CK(launch_bf_mutual(d + o_d0, n0, d + o_d1, n1, (uint32_t*)(ctx->d_work.p + o_row), (uint32_t*)(ctx->d_work.p + o_col),
+                        mout, cap, ctx->sm_count, ctx->stream, &l));
+    CK(launch_ransac((const float*)(d + o_x0), (const float*)(d + o_x1), mout + 1, mout + 1 + cap, mout, 0, rp, ws,
+                     ctx->sm_count, ctx->stream, &l));
+    ctx->launches += l;
+    ctx->d_last_counts = ws.counts; ctx->last_H = ws.h_cap;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int* mo = (const int*)(ctx->h_out.p + o_m);
+    const int n = mo[0];
+    result->n_matches = n;
+    if (n <= 0) { result->inlier_ratio = -1.0; return PSLAM_OK; }   // matcher.cpp:838-839
+    memcpy(match_query_out, mo + 1, 4 * (size_t)n);
+    memcpy(match_train_out, mo + 1 + cap, 4 * (size_t)n);
+    memcpy(match_dist_out, mo + 1 + 2 * cap, 4 * (size_t)n);
     unpack_ransac_result((const int*)(ctx->h_out.p + o_res), result->T, inlier_idx_out, &result->n_inliers,
                          &result->best_ratio, &result->hyp_used, &result->n_filtered);
     std::vector<int> inl_t((size_t)result->n_inliers);

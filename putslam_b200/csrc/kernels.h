@@ -73,6 +73,9 @@ cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth
                                float* d_xyz, double* d_det_dist, double* d_cov, const pslam_cov_params* cov,
                                cudaStream_t st, int* launches);
 
+cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_params& cp, double* d_cov, double* d_info,
+                               cudaStream_t st, int* launches);
+
 // ---- kabsch.cu -------------------------------------------------------------------------------
 cudaError_t launch_kabsch_batch(const double* d_A, const double* d_B, const int* d_off, int batch, double* d_T,
                                 cudaStream_t st, int* launches);

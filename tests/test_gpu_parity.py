@@ -290,3 +290,38 @@ def test_frame_to_map_pipeline(ctx, O, mode):
             assert len(ref["inliers"]) > 300 and np.abs(out["T"] - mf["T_gt"]).max() < 0.01
         # resident replay leaves the answer unchanged
         ctx.frame_to_map_resident(); ctx.sync()
+
+
+def test_information_matrices(ctx, O):
+    """DepthSensorModel::informationMatrixFromImageCoordinates batch (float64, tolerance 1e-12 relative vs the oracle,
+    1e-9 vs numpy's LU inverse)."""
+    from putslam_b200 import api, synth
+    rng = np.random.default_rng(8)
+    uvz = np.stack([rng.uniform(0, 639, 500), rng.uniform(0, 479, 500), rng.uniform(0.8, 6.0, 500)], 1)
+    cp = api.CovParams(synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U, synth.VAR_V,
+                       (api.C.c_double * 4)(*synth.DIST_VAR_COEFS))
+    info, cov = ctx.information_matrices(uvz, cp)
+    for i in range(0, 500, 11):
+        c, f = O.information_matrix(uvz[i, 0], uvz[i, 1], uvz[i, 2], synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U,
+                                    synth.VAR_V, synth.DIST_VAR_COEFS)
+        assert np.allclose(cov[i], c, rtol=1e-12, atol=0) and np.allclose(info[i], f, rtol=1e-11, atol=0)
+        assert np.allclose(info[i] @ cov[i], np.eye(3), atol=1e-9)
+    assert ctx.information_matrices(np.zeros((0, 3)), cp)[0].shape == (0, 3, 3)
+
+
+def test_loop_closure_pair(ctx, O):
+    """Matcher::matchFeatureLoopClosure core: performMatching + RANSAC (map error version) in one submission."""
+    from putslam_b200 import synth
+    for seed, n in ((3, 400), (4, 35)):
+        fp = synth.frame_pair(n=n, seed=seed)
+        x1, _ = O.backproject(fp["uv1"], fp["depth1"], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+        x2, _ = O.backproject(fp["uv2"], fp["depth2"], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+        out = ctx.loop_closure_pair(fp["desc1"], x1, fp["desc2"], x2, seed=9)
+        oq, ot, od = O.bf_mutual(fp["desc1"], fp["desc2"])
+        ref = O.ransac(x1, x2, oq, ot, seed=9)
+        assert np.array_equal(out["mq"], oq) and np.array_equal(out["mt"], ot) and np.array_equal(out["md"], od)
+        assert np.array_equal(out["inliers"], ref["inliers"]) and np.abs(out["T"] - ref["T"]).max() <= 1e-5
+        exp = O.point_inlier_ratio(ot[ref["inliers"]], ot, n)
+        assert out["inlier_ratio"] == exp or (np.isnan(out["inlier_ratio"]) and np.isnan(exp))
+    small = ctx.loop_closure_pair(fp["desc1"][:9], x1[:9], fp["desc2"], x2)      # fewer than 10 features -> 0
+    assert small["inlier_ratio"] == 0 and small["mq"].size == 0

@@ -84,6 +84,15 @@ def test_cov_is_J_R_Jt(O):
     assert np.allclose(cov, J @ R @ J.T, rtol=1e-13, atol=0)
 
 
+def test_information_matrix_is_inverse(O):
+    from putslam_b200 import synth
+    cov, info = O.information_matrix(321.7, 200.2, 2.5, synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U, synth.VAR_V,
+                                     synth.DIST_VAR_COEFS)
+    ref = O.compute_cov(321, 200, 2.5, synth.FX, synth.FY, synth.CX, synth.CY, synth.VAR_U, synth.VAR_V, synth.DIST_VAR_COEFS)
+    assert np.array_equal(cov, ref)
+    assert np.allclose(info, np.linalg.inv(cov), rtol=1e-10)
+
+
 def test_philox_known_answers(O):
     # Random123 kat_vectors, philox4x32-10
     assert O.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
