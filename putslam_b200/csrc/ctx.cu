@@ -78,6 +78,8 @@ NcclApi* nccl_api() {
     return &api;
 }
 constexpr int kNcclUint8 = 1, kNcclInt32 = 2;
+// below this many keyframes per GPU the sweep uses 128-row tiles as work units (see hamming.cu, split form)
+constexpr int kSplitMaxKeyframes = 2048;
 
 // what a *_resident re-run needs to replay a pipeline on the buffers already in HBM
 struct F2MState {
@@ -113,6 +115,10 @@ struct pslam_ctx {
     int64_t db_cap = 0, db_n = 0;
     int64_t* d_kf_off = nullptr;
     std::vector<int64_t> h_kf_off;  // host mirror (n_kf + 1)
+    // split (tile-granular) sweep for small maps: prefix tile counts + scratch
+    DevBuf d_tile_start, d_split;
+    int n_tiles = 0;
+    bool tiles_dirty = true;
     int kf_cap = 0, n_kf = 0, kf_id_base = 0;
     long long desc_id_base = 0;
     DevBuf d_knn;  // V2 sweep scratch: per-CTA partials | merged keys | gathered keys | idx | dist
@@ -304,6 +310,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
     cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p); cudaFree(ctx->d_knn.p);
+    cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p);
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
@@ -926,6 +933,7 @@ int pslam_lc_db_append(pslam_ctx* ctx, const uint8_t* desc, const int64_t* kf_of
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->db_n += nd;
     ctx->n_kf += n_kf;
+    ctx->tiles_dirty = true;
     return PSLAM_OK;
 }
 
@@ -934,6 +942,7 @@ int pslam_lc_db_clear(pslam_ctx* ctx) {
     ctx->db_n = 0;
     ctx->n_kf = 0;
     ctx->h_kf_off.assign(1, 0);
+    ctx->tiles_dirty = true;
     return PSLAM_OK;
 }
 
@@ -974,9 +983,32 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
 
 static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
     int l = 0;
+    // work-unit choice: whole keyframes when every CTA gets many of them, 128-row tiles otherwise
+    const bool split = ctx->n_kf > 0 && ctx->n_kf < kSplitMaxKeyframes;
+    if (split && ctx->tiles_dirty) {
+        std::vector<int> ts((size_t)ctx->n_kf + 1, 0);
+        for (int k = 0; k < ctx->n_kf; ++k)
+            ts[(size_t)k + 1] = ts[(size_t)k] + (int)((ctx->h_kf_off[(size_t)k + 1] - ctx->h_kf_off[(size_t)k] + 127) / 128);
+        ctx->n_tiles = ts[(size_t)ctx->n_kf];
+        const bool keep_f2m = ctx->f2m.valid, keep_f2f = ctx->f2f.valid;   // these buffers are not the frame arenas
+        TRY(ensure_dev(ctx, ctx->d_tile_start, sizeof(int) * ts.size()));
+        const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
+        TRY(ensure_dev(ctx, ctx->d_split, o_col + lc_split_colmin_bytes(ctx->n_kf)));
+        ctx->f2m.valid = keep_f2m; ctx->f2f.valid = keep_f2f;
+        CK(cudaMemcpyAsync(ctx->d_tile_start.p, ts.data(), sizeof(int) * ts.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // ts is a stack-lifetime host buffer
+        ctx->tiles_dirty = false;
+    }
     CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
-    CK(launch_lc_sweep(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, ctx->n_kf, tau, ctx->d_scores,
-                       ctx->sm_count, ctx->stream, &l));
+    if (split) {
+        const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
+        CK(launch_lc_sweep_split(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, (const int*)ctx->d_tile_start.p,
+                                 ctx->n_kf, ctx->n_tiles, tau, (uint32_t*)ctx->d_split.p, (uint32_t*)(ctx->d_split.p + o_col),
+                                 ctx->d_scores, ctx->sm_count, ctx->stream, &l));
+    } else {
+        CK(launch_lc_sweep(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, ctx->n_kf, tau, ctx->d_scores,
+                           ctx->sm_count, ctx->stream, &l));
+    }
     CK(cudaEventRecord(ctx->ev_sweep1, ctx->stream));
     CK(launch_lc_topk(ctx->d_scores, ctx->n_kf, ctx->kf_id_base, k, ctx->d_lc_pairs, ctx->stream, &l));
     ctx->launches += l;

@@ -375,12 +375,113 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7 (split form) for small maps / small shards: with fewer than a few keyframes per CTA the keyframe is too
+// coarse a work unit (100 keyframes keep 100 of 296 CTAs busy).  Here the unit is one 128-row TILE:
+// persistent CTAs walk all tiles of all keyframes; per tile they write the per-query row keys of that tile
+// (4 KB, coalesced) and the finished column keys of its rows; lc_sweep_finalize_kernel then merges the row
+// partials of each keyframe and does the cross-check count.  Extra traffic: 4 KB per tile -- only used when
+// the map is small enough for that to be noise (launcher decides).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_item(int item, const int* __restrict__ tile_start, const int64_t* __restrict__ kf_off,
+                                           int n_kf, int& kf, int& tile, int64_t& row0, int& cnt) {
+    int lo = 0, hi = n_kf;  // largest kf with tile_start[kf] <= item
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tile_start[mid] <= item) lo = mid; else hi = mid;
+    }
+    kf = lo;
+    tile = item - tile_start[kf];
+    const int64_t o = kf_off[kf];
+    const int kcnt = (int)(kf_off[kf + 1] - o);
+    row0 = o + (int64_t)tile * kTT;
+    cnt = min(kTT, kcnt - tile * kTT);
+}
+
+template <int RQ, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
+lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db,
+                      const int64_t* __restrict__ kf_off, const int* __restrict__ tile_start, int n_kf, int n_tiles,
+                      uint32_t* __restrict__ rowpart /* [n_tiles][RQ*NT] */, uint32_t* __restrict__ colmin_g /* [n_kf][4096] */) {
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint4* stages = reinterpret_cast<uint4*>(smem_raw);
+    uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + kStages * kTT * 32);  // 2*NW*kTT
+    uint64_t* bars = reinterpret_cast<uint64_t*>(partial + 2 * NW * kTT);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+    }
+    QueryRegs<RQ, NT> Q;
+    Q.load(query, nq, 0, tid);
+    __syncthreads();
+    const int my_items = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto issue = [&](int a) {
+        int kf, tile, cnt; int64_t row0;
+        split_item((int)blockIdx.x + a * (int)gridDim.x, tile_start, kf_off, n_kf, kf, tile, row0, cnt);
+        const int st = a % kStages;
+        mbar_expect_tx(bars + st, (uint32_t)cnt * 32u);
+        tma_load_1d(stages + (size_t)st * kTT * 2, db + 2 * row0, (uint32_t)cnt * 32u, bars + st);
+    };
+    if (tid == 0)
+        for (int a = 0; a < kStages - 1 && a < my_items; ++a) issue(a);
+    for (int it = 0; it < my_items; ++it) {
+        const int stage = it % kStages;
+        const uint32_t phase = (uint32_t)(it / kStages) & 1u;
+        if (tid == 0 && it + kStages - 1 < my_items) issue(it + kStages - 1);
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        int kf, tile, cnt; int64_t row0;
+        split_item(item, tile_start, kf_off, n_kf, kf, tile, row0, cnt);
+        const int tbase = tile * kTT;
+        uint32_t rowmin[RQ];
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
+        uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
+        mbar_wait(bars + stage, phase);
+        tile_compute<RQ, NT>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+#pragma unroll
+        for (int j = 0; j < RQ; ++j) rowpart[(size_t)item * (RQ * NT) + j * NT + tid] = rowmin[j];
+        __syncthreads();
+        if (tid < cnt) {
+            uint32_t m = pbuf[tid];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) m = min(m, pbuf[w * kTT + tid]);
+            colmin_g[(size_t)kf * kMaxKfDesc + tbase + tid] = m;
+        }
+    }
+}
+
+// One CTA per keyframe: merge the row partials of its tiles, cross-check against the column keys, count.
+__global__ void __launch_bounds__(256)
+lc_sweep_finalize_kernel(const int* __restrict__ tile_start, const int64_t* __restrict__ kf_off, int nq, int row_stride,
+                         const uint32_t* __restrict__ rowpart, const uint32_t* __restrict__ colmin_g, int tau,
+                         int* __restrict__ scores) {
+    __shared__ int s_cnt;
+    const int kf = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const int t0 = tile_start[kf], t1 = tile_start[kf + 1];
+    int c = 0;
+    if (t1 > t0) {
+        for (int q = tid; q < nq; q += 256) {
+            uint32_t rk = 0xffffffffu;
+            for (int t = t0; t < t1; ++t) rk = min(rk, rowpart[(size_t)t * row_stride + q]);
+            if (rk != 0xffffffffu && colmin_g[(size_t)kf * kMaxKfDesc + key_tidx(rk)] == rk && (int)key_dist(rk) <= tau) ++c;
+        }
+    }
+    c = (int)warp_add_u32((uint32_t)c);
+    if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (tid == 0) scores[kf] = s_cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
 // V2 sweep: two nearest database descriptors per query descriptor over the WHOLE resident database
 // (keyframe boundaries ignored).  Persistent CTAs walk 2048-row chunks (round-robin) through the same
 // TMA ring; inside a chunk the running top-2 are 32-bit keys with chunk-local indices, at chunk end they
 // are folded into 64-bit (dist << 40 | global index) keys.  Per-CTA results are merged per query.
 // ------------------------------------------------------------------------------------------------
-constexpr int kChunkMax = 2048;  // chunk-local row index must fit the 12-bit train field of the key
+// chunk = 128 << shift rows, at most 2048: the chunk-local row index must fit the 12-bit train field of the key
 __device__ __forceinline__ unsigned long long key64(uint32_t k, long long base) {
     return ((unsigned long long)key_dist(k) << 40) | (unsigned long long)(base + (long long)key_tidx(k));
 }
@@ -393,7 +494,8 @@ __device__ __forceinline__ void top2_insert64(unsigned long long& g1, unsigned l
 template <int RQ, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT)
 lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db, long long n_desc,
-               long long desc_id_base, int chunk_rows, ulonglong2* __restrict__ partial /* [gridDim.x][nq] */) {
+               long long desc_id_base, int tpc_shift /* log2(tiles per chunk) */,
+               ulonglong2* __restrict__ partial /* [gridDim.x][nq] */) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint4* stages = reinterpret_cast<uint4*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTT * 32);
@@ -410,12 +512,13 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
     __syncthreads();
 
     const long long n_tiles_total = (n_desc + kTT - 1) / kTT;
-    const int kTilesPerChunk = chunk_rows / kTT;
+    const int kTilesPerChunk = 1 << tpc_shift;
+    const int chunk_rows = kTilesPerChunk * kTT;
     const long long n_chunks = (n_desc + chunk_rows - 1) / chunk_rows;
     // flat list of this CTA's tiles: chunk c = blockIdx.x + i*gridDim.x, tiles c*16 .. c*16+15
     auto tile_of = [&](long long item) -> long long {
-        const long long c = (long long)blockIdx.x + (item / kTilesPerChunk) * gridDim.x;
-        return c * kTilesPerChunk + (item % kTilesPerChunk);
+        const long long c = (long long)blockIdx.x + (item >> tpc_shift) * gridDim.x;
+        return (c << tpc_shift) + (item & (kTilesPerChunk - 1));
     };
     long long my_chunks = n_chunks > blockIdx.x ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     // number of items: full chunks have 16 tiles, the globally last chunk may have fewer
@@ -447,7 +550,7 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
         const long long t = tile_of(it);
         const long long row0 = t * kTT;
         const int cnt = (int)((n_desc - row0) < kTT ? (n_desc - row0) : kTT);
-        const uint32_t tbase = (uint32_t)((t % kTilesPerChunk) * kTT);  // chunk-local row of the tile
+        const uint32_t tbase = (uint32_t)((t & (kTilesPerChunk - 1)) * kTT);  // chunk-local row of the tile
         mbar_wait(bars + stage, phase);
         const uint4* tile = stages + (size_t)stage * kTT * 2;
         int tt = 0;
@@ -475,9 +578,9 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
                 m1[j] = min(m1[j], k0);
             }
         }
-        const bool chunk_end = ((t % kTilesPerChunk) == kTilesPerChunk - 1) || (t == n_tiles_total - 1);
+        const bool chunk_end = ((t & (kTilesPerChunk - 1)) == kTilesPerChunk - 1) || (t == n_tiles_total - 1);
         if (chunk_end) {
-            const long long base = desc_id_base + (t / kTilesPerChunk) * (long long)chunk_rows;
+            const long long base = desc_id_base + (t >> tpc_shift) * (long long)chunk_rows;
 #pragma unroll
             for (int j = 0; j < RQ; ++j) {
                 if (m1[j] != 0xffffffffu) top2_insert64(g1[j], g2[j], key64(m1[j], base));
@@ -727,6 +830,30 @@ cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db,
     return cudaGetLastError();
 }
 
+size_t lc_split_rowpart_bytes(int n_tiles) { return sizeof(uint32_t) * 1024 * (size_t)(n_tiles > 0 ? n_tiles : 1); }
+size_t lc_split_colmin_bytes(int n_kf) { return sizeof(uint32_t) * (size_t)kMaxKfDesc * (size_t)(n_kf > 0 ? n_kf : 1); }
+
+cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off,
+                                  const int* d_tile_start, int n_kf, int n_tiles, int tau, uint32_t* d_rowpart,
+                                  uint32_t* d_colmin, int* d_scores, int sm_count, cudaStream_t st, int* launches) {
+    if (n_kf <= 0) return cudaSuccess;
+    const int rq = pick_rq(nq);
+    const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
+    const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
+    int grid = 2 * sm_count;
+    if (grid > n_tiles) grid = n_tiles;
+    if (n_tiles > 0) {
+        const size_t smem = (size_t)kStages * kTT * 32 + sizeof(uint32_t) * 2 * (256 / 32) * kTT + sizeof(uint64_t) * kStages + 16;
+        if (rq == 1) lc_sweep_split_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, d_tile_start, n_kf, n_tiles, d_rowpart, d_colmin);
+        else if (rq == 2) lc_sweep_split_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, d_tile_start, n_kf, n_tiles, d_rowpart, d_colmin);
+        else lc_sweep_split_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, d_tile_start, n_kf, n_tiles, d_rowpart, d_colmin);
+        if (launches) *launches += 1;
+    }
+    lc_sweep_finalize_kernel<<<n_kf, 256, 0, st>>>(d_tile_start, d_kf_off, nq, rq * 256, d_rowpart, d_colmin, tau, d_scores);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
                            int* launches) {
     lc_topk_kernel<<<1, 1024, 0, st>>>(d_scores, n_kf, kf_id_base, k, d_out_pairs);
@@ -742,12 +869,13 @@ cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int*
 }
 
 // rows per chunk: large enough to amortise the 64-bit fold, small enough to give every CTA work
-static int lc_knn2_chunk(long long n_desc, int sm_count) {
-    long long c = (n_desc / (2LL * sm_count) + kTT - 1) / kTT * kTT;
-    if (c < kTT) c = kTT;
-    if (c > kChunkMax) c = kChunkMax;
-    return (int)c;
+static int lc_knn2_shift(long long n_desc, int sm_count) {   // log2(tiles per chunk), chunk = 128 << shift rows
+    const long long want = n_desc / (2LL * sm_count);
+    int sh = 0;
+    while (sh < 4 && ((long long)kTT << (sh + 1)) <= want) ++sh;   // at most 2048 rows (12-bit local index)
+    return sh;
 }
+static int lc_knn2_chunk(long long n_desc, int sm_count) { return kTT << lc_knn2_shift(n_desc, sm_count); }
 int lc_knn2_grid(long long n_desc, int sm_count) {
     const int chunk = lc_knn2_chunk(n_desc, sm_count);
     long long chunks = (n_desc + chunk - 1) / chunk;
@@ -759,7 +887,7 @@ int lc_knn2_grid(long long n_desc, int sm_count) {
 
 cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
                            void* d_partial, int grid, int sm_count, cudaStream_t st, int* launches) {
-    const int chunk = lc_knn2_chunk(n_desc, sm_count);
+    const int chunk = lc_knn2_shift(n_desc, sm_count);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
     const size_t smem = (size_t)kStages * kTT * 32 + sizeof(uint64_t) * kStages + 16;

@@ -19,6 +19,12 @@ int lc_max_kf_desc();
 int lc_max_query();
 cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off, int n_kf,
                             int tau, int* d_scores, int sm_count, cudaStream_t st, int* launches);
+// split form (tile-granular work units) for small maps; tile_start[n_kf + 1] = prefix count of 128-row tiles
+size_t lc_split_rowpart_bytes(int n_tiles);
+size_t lc_split_colmin_bytes(int n_kf);
+cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off,
+                                  const int* d_tile_start, int n_kf, int n_tiles, int tau, uint32_t* d_rowpart,
+                                  uint32_t* d_colmin, int* d_scores, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
                            int* launches);
 cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
