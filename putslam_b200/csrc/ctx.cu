@@ -79,7 +79,7 @@ NcclApi* nccl_api() {
 }
 constexpr int kNcclUint8 = 1, kNcclInt32 = 2;
 // below this many keyframes per GPU the sweep uses 128-row tiles as work units (see hamming.cu, split form)
-constexpr int kSplitMaxKeyframes = 2048;
+constexpr int kSplitMaxKeyframes = 4096;
 
 // what a *_resident re-run needs to replay a pipeline on the buffers already in HBM
 struct F2MState {
