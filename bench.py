@@ -91,6 +91,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(n_kf, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep kernel from the committed
+    `ncu --set full` capture (profiles/ncu_sweep_r1.json); only valid for the configuration it was taken on."""
+    p = os.path.join(ROOT, "profiles", "ncu_sweep_r1.json")
+    if n_kf != N_KF or world != 1 or not os.path.exists(p):
+        return None
+    try:
+        return float(json.load(open(p))["dram_traffic_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peaks():
     """Pipe rates measured live by bench/peaks (register-only loops) + the driver's MEASURED_PEAKS.json."""
     out = {}
@@ -392,7 +404,7 @@ def run_ours(args):
             "avg_launch_ms": sweep_avg_ms,
             "hbm": {"achieved_gbs": (32.0 * shard_desc + 40.0 * NQ) / (sweep_avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": peaks.get("hbm_peak_source")},
-            "traffic": None,
+            "traffic": ncu_traffic(n_kf, world),
             "measured_pipe_rates": {k: peaks.get(k) for k in ("popc_per_clk_per_sm", "lop3_per_clk_per_sm",
                                                                "imad_per_clk_per_sm", "min_u32_per_clk_per_sm",
                                                                "ham_plain8_gcmps", "ham_csa4_gcmps", "hbm_copy_gbs")},
