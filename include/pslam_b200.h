@@ -93,6 +93,15 @@ PSLAM_API int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const ui
 PSLAM_API int pslam_information_matrices(pslam_ctx* ctx, const double* uvz, int n, const pslam_cov_params* cov,
                                          double* info_out, double* cov_out);
 
+/* Uncertainty model 1: RGBD::computeNormals (include/putslam/RGBD/RGBD.h:91-95, src/RGBD/RGBD.cpp:101-144) followed
+ * by DepthSensorModel::uncertinatyFromNormal (src/Grabber/depthSensorModel.cpp:62-76).  px = n x {u, v} integer
+ * pixels; normals_out (nullable) n x 3, cov_out (nullable) n x 9 row-major, both double.  A pixel with fewer than
+ * two neighbours that have depth yields NaN, as in the reference.  (Model 2, RGB gradients, is not provided: the
+ * reference reads the 8-bit BGR patch as uint16, src/RGBD/RGBD.cpp:156-159.) */
+PSLAM_API int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_t* depth, int W, int H,
+                                       int row_stride, const pslam_camera* cam, double depth_scale,
+                                       double scale_uncertainty_normal, double* normals_out, double* cov_out);
+
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
  * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==

@@ -183,6 +183,22 @@ def information_matrix(u, v, z, fx, fy, cx, cy, varU, varV, coefs):
     return cov.reshape(3, 3), info.reshape(3, 3)
 
 
+def compute_normal(depth, u, v, fx, fy, cx, cy, depth_scale):
+    depth = np.ascontiguousarray(depth, np.uint16)
+    H, W = depth.shape
+    n = np.empty(3, np.float64)
+    lib().orc_compute_normal(_p(depth, C.c_uint16), W, H, W, int(u), int(v), C.c_float(fx), C.c_float(fy), C.c_float(cx),
+                             C.c_float(cy), C.c_double(depth_scale), _p(n, C.c_double))
+    return n
+
+
+def uncertainty_from_normal(normal, scale):
+    nrm = np.ascontiguousarray(normal, np.float64)
+    cov = np.empty(9, np.float64)
+    lib().orc_uncertainty_from_normal(_p(nrm, C.c_double), C.c_double(scale), _p(cov, C.c_double))
+    return cov.reshape(3, 3)
+
+
 def svd3f(A):
     A = np.ascontiguousarray(A, np.float32)
     U = np.empty((3, 3), np.float32); S = np.empty(3, np.float32); V = np.empty((3, 3), np.float32)

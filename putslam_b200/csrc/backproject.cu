@@ -151,6 +151,98 @@ __global__ void information_kernel(const double* __restrict__ uvz, int n, pslam_
     }
 }
 
+__device__ __forceinline__ void px_to_3d(float fu, float fv, const uint16_t* __restrict__ depth, int W, int H, int stride,
+                                         const pslam_camera& cam, double depth_scale, float (&o)[3]) {
+    const int uR = round_size((double)fu, W), vR = round_size((double)fv, H);
+    const float Z = (float)(((double)depth[(size_t)vR * stride + uR]) / depth_scale);
+    const float u = __fdiv_rn(fu - cam.cx, cam.fx), v = __fdiv_rn(fv - cam.cy, cam.fy);
+    o[0] = u * Z; o[1] = v * Z; o[2] = Z;
+}
+__device__ __forceinline__ void normalize3(double (&v)[3]) {
+    const double yy = v[1] * v[1], zz = v[2] * v[2];
+    const double n = __dsqrt_rn(v[0] * v[0] + (yy + zz));
+    v[0] = __ddiv_rn(v[0], n); v[1] = __ddiv_rn(v[1], n); v[2] = __ddiv_rn(v[2], n);
+}
+__device__ __forceinline__ void matmul3(const double (&A)[9], const double (&B)[9], double (&C)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double s = A[3 * i] * B[j];
+            s = s + A[3 * i + 1] * B[3 + j];
+            s = s + A[3 * i + 2] * B[6 + j];
+            C[3 * i + j] = s;
+        }
+}
+
+// Uncertainty model 1: RGBD::computeNormal (reference src/RGBD/RGBD.cpp:101-144) + DepthSensorModel::
+// uncertinatyFromNormal (src/Grabber/depthSensorModel.cpp:62-76).  px = n x {u, v} integer pixels
+// ((int)it->u, (int)it->v in RGBD::computeNormals, include/putslam/RGBD/RGBD.h:91-95).
+__global__ void normal_cov_kernel(const int* __restrict__ px, int n, const uint16_t* __restrict__ depth, int W, int H,
+                                  int stride, pslam_camera cam, double depth_scale, double scale_unc,
+                                  double* __restrict__ normals, double* __restrict__ cov_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int u = px[2 * i], v = px[2 * i + 1];
+    float c[3];
+    px_to_3d((float)u, (float)v, depth, W, H, stride, cam, depth_scale, c);
+    double first[3] = {0, 0, 0}, prev[3] = {0, 0, 0};
+    double sx = 0, sy = 0, sz = 0;
+    int nv = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int du = (k < 3) ? -1 : ((k == 3 || k == 7) ? 0 : 1);
+        const int dv = (k == 0 || k == 6 || k == 7) ? -1 : ((k == 1 || k == 5) ? 0 : 1);
+        float e[3];
+        px_to_3d((float)(u + du), (float)(v + dv), depth, W, H, stride, cam, depth_scale, e);
+        if (e[2] > 0.f) {
+            const double cur[3] = {(double)(e[0] - c[0]), (double)(e[1] - c[1]), (double)(e[2] - c[2])};
+            if (nv == 0) { first[0] = cur[0]; first[1] = cur[1]; first[2] = cur[2]; }
+            else {   // cross(prev, cur), accumulated in order
+                sx += prev[1] * cur[2] - prev[2] * cur[1];
+                sy += prev[2] * cur[0] - prev[0] * cur[2];
+                sz += prev[0] * cur[1] - prev[1] * cur[0];
+            }
+            prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
+            ++nv;
+        }
+    }
+    if (nv > 0) {   // closing cross(last, first)
+        sx += prev[1] * first[2] - prev[2] * first[1];
+        sy += prev[2] * first[0] - prev[0] * first[2];
+        sz += prev[0] * first[1] - prev[1] * first[0];
+    }
+    double nr[3] = {__ddiv_rn(sx, (double)nv), __ddiv_rn(sy, (double)nv), __ddiv_rn(sz, (double)nv)};
+    normalize3(nr);
+    if (normals) { normals[3 * (size_t)i] = nr[0]; normals[3 * (size_t)i + 1] = nr[1]; normals[3 * (size_t)i + 2] = nr[2]; }
+    if (cov_out) {
+        double nn[3] = {nr[0], nr[1], nr[2]};
+        double y[3] = {nn[1] * 0.0 - nn[2] * 0.0, nn[2] * 1.0 - nn[0] * 0.0, nn[0] * 0.0 - nn[1] * 1.0};
+        normalize3(nn);
+        double x[3] = {y[1] * nn[2] - y[2] * nn[1], y[2] * nn[0] - y[0] * nn[2], y[0] * nn[1] - y[1] * nn[0]};
+        normalize3(x);
+        const double R[9] = {x[0], y[0], nn[0], x[1], y[1], nn[1], x[2], y[2], nn[2]};
+        const double S[9] = {1, 0, 0, 0, 1, 0, 0, 0, scale_unc};
+        double RS[9], RSS[9], Rinv[9], cov[9];
+        matmul3(R, S, RS);
+        matmul3(RS, S, RSS);
+        inverse3d(R, Rinv);
+        matmul3(RSS, Rinv, cov);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) cov_out[9 * (size_t)i + a] = cov[a];
+    }
+}
+
+cudaError_t launch_normal_cov(const int* d_px, int n, const uint16_t* d_depth, int W, int H, int stride,
+                              const pslam_camera& cam, double depth_scale, double scale_unc, double* d_normals,
+                              double* d_cov, cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    normal_cov_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_px, n, d_depth, W, H, stride, cam, depth_scale, scale_unc,
+                                                       d_normals, d_cov);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_params& cp, double* d_cov, double* d_info,
                                cudaStream_t st, int* launches) {
     if (n <= 0) return cudaSuccess;

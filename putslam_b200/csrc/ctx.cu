@@ -378,6 +378,34 @@ int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* de
     return PSLAM_OK;
 }
 
+int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_t* depth, int W, int H, int row_stride,
+                             const pslam_camera* cam, double depth_scale, double scale_uncertainty_normal,
+                             double* normals_out, double* cov_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n < 0 || (n > 0 && !px) || !depth || !cam || W <= 0 || H <= 0 || row_stride < W)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_normal_uncertainty: bad argument");
+    if (n == 0) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_px = in.take(8 * (size_t)n), o_depth = in.take(sizeof(uint16_t) * (size_t)H * row_stride);
+    const size_t o_n = out.take(24 * (size_t)n), o_cov = out.take(72 * (size_t)n);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    memcpy(ctx->h_in.p + o_px, px, 8 * (size_t)n);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_normal_cov((const int*)(ctx->d_in.p + o_px), n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H, row_stride, *cam,
+                         depth_scale, scale_uncertainty_normal, (double*)(ctx->d_out.p + o_n), (double*)(ctx->d_out.p + o_cov),
+                         ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (normals_out) memcpy(normals_out, ctx->h_out.p + o_n, 24 * (size_t)n);
+    if (cov_out) memcpy(cov_out, ctx->h_out.p + o_cov, 72 * (size_t)n);
+    return PSLAM_OK;
+}
+
 int pslam_information_matrices(pslam_ctx* ctx, const double* uvz, int n, const pslam_cov_params* cov, double* info_out,
                                double* cov_out) {
     if (!ctx) return PSLAM_ERR_ARG;

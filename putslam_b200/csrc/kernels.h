@@ -79,6 +79,9 @@ cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth
                                float* d_xyz, double* d_det_dist, double* d_cov, const pslam_cov_params* cov,
                                cudaStream_t st, int* launches);
 
+cudaError_t launch_normal_cov(const int* d_px, int n, const uint16_t* d_depth, int W, int H, int stride,
+                              const pslam_camera& cam, double depth_scale, double scale_unc, double* d_normals,
+                              double* d_cov, cudaStream_t st, int* launches);
 cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_params& cp, double* d_cov, double* d_info,
                                cudaStream_t st, int* launches);
 

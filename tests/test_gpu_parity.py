@@ -325,3 +325,33 @@ def test_loop_closure_pair(ctx, O):
         assert out["inlier_ratio"] == exp or (np.isnan(out["inlier_ratio"]) and np.isnan(exp))
     small = ctx.loop_closure_pair(fp["desc1"][:9], x1[:9], fp["desc2"], x2)      # fewer than 10 features -> 0
     assert small["inlier_ratio"] == 0 and small["mq"].size == 0
+
+
+def test_normal_uncertainty(ctx, O):
+    """Uncertainty model 1: surface normal from the 8 depth neighbours + covariance aligned with it (float64;
+    1e-12 relative vs the oracle; NaN where the reference yields NaN)."""
+    from putslam_b200 import synth
+    rng = np.random.default_rng(10)
+    # a tilted plane z = 1.5 + 0.001*u + 0.0005*v (metres), with holes and a depth edge
+    uu, vv = np.meshgrid(np.arange(640), np.arange(480))
+    z = 1.5 + 0.001 * uu + 0.0005 * vv
+    z[:, 400:] += 0.7
+    depth = np.rint(z * 5000).astype(np.uint16)
+    depth[rng.random(depth.shape) < 0.05] = 0
+    depth[100:110, 100:110] = 0
+    px = np.stack([rng.integers(0, 640, 400), rng.integers(0, 480, 400)], 1).astype(np.int32)
+    px[:4] = [[0, 0], [639, 479], [105, 105], [399, 200]]
+    nrm, cov = ctx.normal_uncertainty(px, depth, scale=0.8)
+    n_nan = 0
+    for i in range(400):
+        rn = O.compute_normal(depth, px[i, 0], px[i, 1], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+        rc = O.uncertainty_from_normal(rn, 0.8)
+        if np.isnan(rn).any():
+            assert np.isnan(nrm[i]).any(); n_nan += 1
+            continue
+        assert np.allclose(nrm[i], rn, rtol=1e-12, atol=1e-15), i
+        assert np.allclose(cov[i], rc, rtol=1e-10, atol=1e-14), i
+    assert n_nan >= 1 and n_nan < 100
+    # on the clean plane the normal is the plane normal (up to sign) and cov shrinks along it by 0.8^2
+    good = np.nonzero((px[:, 0] > 5) & (px[:, 0] < 390) & ~np.isnan(nrm).any(1))[0]
+    assert abs(np.abs(nrm[good[0]] @ nrm[good[1]]) - 1) < 1e-2

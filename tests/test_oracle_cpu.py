@@ -93,6 +93,21 @@ def test_information_matrix_is_inverse(O):
     assert np.allclose(info, np.linalg.inv(cov), rtol=1e-10)
 
 
+def test_normal_and_uncertainty_from_normal(O):
+    from putslam_b200 import synth
+    uu, vv = np.meshgrid(np.arange(640), np.arange(480))
+    z = 2.0 + 0.002 * uu                       # plane tilted about the image y axis
+    depth = np.rint(z * 5000).astype(np.uint16)
+    n = O.compute_normal(depth, 300, 200, synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+    assert abs(np.linalg.norm(n) - 1) < 1e-12 and abs(n[1]) < 0.05 and abs(n[2]) > 0.5
+    cov = O.uncertainty_from_normal(n, 0.8)
+    w = np.linalg.eigvals(cov).real
+    assert np.allclose(sorted(w), [0.64, 1.0, 1.0], atol=1e-9)       # S^2 in the frame of the normal
+    assert np.allclose(cov @ n, 0.64 * n, atol=1e-9)
+    depth[:] = 0
+    assert np.isnan(O.compute_normal(depth, 300, 200, synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)).all()
+
+
 def test_philox_known_answers(O):
     # Random123 kat_vectors, philox4x32-10
     assert O.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
