@@ -158,6 +158,12 @@ PSLAM_API int pslam_ransac_estimate(pslam_ctx* ctx, const float* prev, int n_pre
                                     int* inlier_idx_out, int* n_inliers_out, double* best_ratio_out,
                                     int* hyp_used_out);
 
+/* Termination rule of the hypothesis loop for this ctx.  rule 0 (default): RANSAC::computeRANSACIteration /
+ * saveBetterModel (src/TransformEst/RANSAC.cpp:438-461).  rule 1: the standard stopping criterion of the reference's
+ * (not compiled) USAC framework, USAC<T>::updateStandardStopping (include/putslam/USAC/USAC.h:944-971), confidence
+ * 0.99 in src/USAC/USAC_wrapper.cpp:66; the bound is capped by the hypothesis budget (num_hyp, or 487 when 0). */
+PSLAM_API int pslam_ransac_set_stopping(pslam_ctx* ctx, int rule, double confidence);
+
 /* Per-hypothesis inlier counts of the last pslam_ransac_estimate / frame call on this ctx
  * (-1 = degenerate model); for diagnostics and parity tests.  Copies min(cap, hypotheses) ints. */
 PSLAM_API int pslam_ransac_last_counts(pslam_ctx* ctx, int* counts_out, int cap, int* n_out);

@@ -279,5 +279,9 @@ def point_inlier_ratio(inl_t, all_t, n_train):
     return lib().orc_point_inlier_ratio(_p(inl_t, C.c_int), inl_t.size, _p(all_t, C.c_int), all_t.size, n_train)
 
 
+def set_stopping(rule, conf=0.99):
+    lib().orc_set_stopping(int(rule), C.c_double(conf))
+
+
 def num_threads():
     return lib().orc_num_threads()

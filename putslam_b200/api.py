@@ -18,7 +18,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
     "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_match_bf_mutual",
-    "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_last_counts",
+    "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
@@ -239,6 +239,9 @@ class Context:
             counts = counts[:n.value]
         return dict(T=T.reshape(4, 4).T.copy(), inliers=inl[:n_inl.value].copy(), best_ratio=best.value,
                     hyp_used=used.value, counts=counts)
+
+    def ransac_set_stopping(self, rule, confidence=0.99):
+        self._ck(self.lib.pslam_ransac_set_stopping(self.h, int(rule), C.c_double(confidence)))
 
     def kabsch_batch(self, A_list, B_list):
         off = np.zeros(len(A_list) + 1, np.int32)

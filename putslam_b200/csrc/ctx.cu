@@ -131,6 +131,8 @@ struct pslam_ctx {
     // NCCL
     void* comm = nullptr;
     int rank = 0, world = 1;
+    int stop_rule = 0;          // 0 reference RANSAC rule, 1 USAC standard stopping
+    double usac_conf = 0.99;
     // last RANSAC (for pslam_ransac_last_counts)
     int* d_last_counts = nullptr;
     int last_H = 0;
@@ -222,6 +224,8 @@ int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t se
     o.fx = p->fx; o.fy = p->fy; o.cx = p->cx; o.cy = p->cy;
     o.seed_lo = (uint32_t)seed; o.seed_hi = (uint32_t)(seed >> 32);
     o.num_hyp = num_hyp;
+    o.stop_rule = ctx->stop_rule;
+    o.usac_conf = ctx->usac_conf;
     return PSLAM_OK;
 }
 
@@ -598,6 +602,14 @@ int pslam_ransac_estimate(pslam_ctx* ctx, const float* prev, int n_prev, const f
     CK(cudaStreamSynchronize(ctx->stream));
     unpack_ransac_result((const int*)(ctx->h_out.p + o_res), T_out, inlier_idx_out, n_inliers_out, best_ratio_out,
                          hyp_used_out, nullptr);
+    return PSLAM_OK;
+}
+
+int pslam_ransac_set_stopping(pslam_ctx* ctx, int rule, double confidence) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if ((rule != 0 && rule != 1) || !(confidence > 0.0 && confidence < 1.0)) return fail(ctx, PSLAM_ERR_ARG, "bad stopping rule");
+    ctx->stop_rule = rule;
+    ctx->usac_conf = confidence;
     return PSLAM_OK;
 }
 

@@ -57,6 +57,8 @@ struct RansacDeviceParams {
     float fx, fy, cx, cy;
     uint32_t seed_lo, seed_hi;
     int num_hyp;              // 0 = adaptive (reference bound 487, shrinking), >0 fixed
+    int stop_rule;            // 0 = reference RANSAC rule, 1 = USAC standard stopping (capped by the budget)
+    double usac_conf;
 };
 struct RansacWorkspace {
     // all device pointers; sized for m_cap matches and h_cap hypotheses

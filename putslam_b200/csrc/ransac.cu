@@ -216,12 +216,26 @@ __device__ __forceinline__ int ransac_iterations(double w) {
     return (int)v;
 }
 
+// USAC<T>::updateStandardStopping (reference include/putslam/USAC/USAC.h:944-971), sample size 3.
+__device__ __forceinline__ unsigned usac_standard_stopping(unsigned inl, unsigned tot, double conf, unsigned max_hyp) {
+    double n_inl = 1.0, n_pts = 1.0;
+#pragma unroll
+    for (unsigned i = 0; i < 3; ++i) {
+        n_inl = n_inl * (double)(inl - i);   // unsigned wrap-around like the reference
+        n_pts = n_pts * (double)(tot - i);
+    }
+    const double prob = n_inl / n_pts;
+    if (prob < 2.220446049250313e-16) return max_hyp;
+    if (1 - prob < 2.220446049250313e-16) return 1u;
+    return (unsigned)ceil(log(1 - conf) / log(1 - prob));
+}
+
 constexpr int kSelThreads = 1024;
 
 __global__ void __launch_bounds__(kSelThreads, 1)
 ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
                      const int* __restrict__ n_filtered, const int* __restrict__ counts,
-                     const float* __restrict__ models, int H, int adaptive,
+                     const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
                      int min_matches, double min_ratio, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
                      int* __restrict__ inl_tmp /* m_cap scratch */, int stage_cap, int* __restrict__ result) {
     __shared__ int warp_tot[32];
@@ -264,8 +278,13 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
                 const float ratio = __fdiv_rn((float)c, (float)mf);
                 if ((double)ratio > best) {
                     best = (double)ratio; win = i; bc = c;
-                    const int a = ransac_iterations(min_ratio), b = ransac_iterations(best);
-                    bound = a < b ? a : b;
+                    if (stop_rule == 1) {
+                        const unsigned b = usac_standard_stopping((unsigned)c, (unsigned)mf, usac_conf, (unsigned)H);
+                        bound = (int)(b < (unsigned)H ? b : (unsigned)H);
+                    } else if (adaptive == 1) {
+                        const int a = ransac_iterations(min_ratio), b = ransac_iterations(best);
+                        bound = a < b ? a : b;
+                    }
                 }
             }
             s_win = win; s_used = i; s_cnt = bc;
@@ -454,7 +473,9 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     S.thr = P.thr_euclid;
     S.thr_reproj = P.thr_reproj;
     S.fx = P.fx; S.fy = P.fy; S.cx = P.cx; S.cy = P.cy;
-    const int adaptive = P.num_hyp <= 0;
+    // sequential replay is needed for the reference's adaptive bound and for USAC stopping (2 = replay with a fixed
+    // budget); plain fixed-H is a parallel first-max
+    const int adaptive = P.num_hyp <= 0 ? 1 : (P.stop_rule == 1 ? 2 : 0);
     const int H = adaptive ? 487 : P.num_hyp;  // int(log(0.02)/log(1-0.2^3)), reference RANSAC.cpp:30
     ransac_filter_kernel<<<1, 1024, 0, st>>>(d_prev, d_cur, d_mq, d_mt, d_m, m_host, ws.m_cap, ws.pts, ws.keep,
                                              ws.n_filtered);
@@ -475,7 +496,7 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
         if (e != cudaSuccess) return e;
         sel_cfg = true;
     }
-    ransac_select_kernel<<<1, kSelThreads, sel_smem, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, ws.models, H, adaptive,
+    ransac_select_kernel<<<1, kSelThreads, sel_smem, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf,
                                                            P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
                                                            ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap,
                                                            ws.result);

@@ -355,3 +355,19 @@ def test_normal_uncertainty(ctx, O):
     # on the clean plane the normal is the plane normal (up to sign) and cov shrinks along it by 0.8^2
     good = np.nonzero((px[:, 0] > 5) & (px[:, 0] < 390) & ~np.isnan(nrm).any(1))[0]
     assert abs(np.abs(nrm[good[0]] @ nrm[good[1]]) - 1) < 1e-2
+
+
+def test_ransac_usac_standard_stopping(ctx, O):
+    """Alternative termination rule: USAC<T>::updateStandardStopping replayed over the scored hypotheses."""
+    from putslam_b200 import synth
+    try:
+        ctx.ransac_set_stopping(1, 0.99); O.set_stopping(1, 0.99)
+        for seed in range(3):
+            mc = synth.matched_clouds(m=800, inlier_frac=0.5, seed=20 + seed)
+            for num_hyp in (0, 2048):
+                r = ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=seed, num_hyp=num_hyp)
+                o = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], seed=seed, num_hyp=num_hyp)
+                assert r["hyp_used"] == o["hyp_used"] and r["hyp_used"] < 200    # stops long before the budget
+                assert np.array_equal(r["inliers"], o["inliers"]) and np.abs(r["T"] - o["T"]).max() <= 1e-5
+    finally:
+        ctx.ransac_set_stopping(0, 0.99); O.set_stopping(0, 0.99)

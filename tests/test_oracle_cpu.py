@@ -189,6 +189,14 @@ def test_ransac_iterations(O):
     assert O.ransac_iterations(0.5) == int(np.log(0.02) / np.log(1 - 0.125))
 
 
+def test_usac_standard_stopping(O):
+    import math
+    assert O.lib().orc_usac_stopping(0, 100, 850000) == 850000 and O.lib().orc_usac_stopping(2, 100, 850000) == 850000
+    assert O.lib().orc_usac_stopping(100, 100, 850000) == 1
+    p = (50 * 49 * 48) / (100 * 99 * 98)
+    assert O.lib().orc_usac_stopping(50, 100, 850000) == math.ceil(math.log(0.01) / math.log(1 - p))
+
+
 def test_ransac_recovers_planted_transform(O):
     from putslam_b200 import synth
     mc = synth.matched_clouds(m=600, inlier_frac=0.6, seed=2)
