@@ -227,6 +227,25 @@ PSLAM_API int pslam_loop_closure_pair(pslam_ctx* ctx, const uint8_t* desc0, cons
 PSLAM_API int pslam_frame_to_map_resident(pslam_ctx* ctx);
 PSLAM_API int pslam_frame_to_frame_resident(pslam_ctx* ctx);
 
+/* ---- map-side preparation (the step in front of matchXYZ) ------------------------
+ * Body of PUTSLAM::getAndFilterFeaturesFromMap (src/PUTSLAM/PUTSLAM.cpp:624-674) after getCovisibleFeatures:
+ * FeaturesMap::findNearestFrame's view-angle test (src/Map/featuresMap.cpp:528-563), removal of features without a
+ * good observation angle (PUTSLAM.cpp:932-950), moveMapFeaturesToLocalCordinateSystem (PUTSLAM.cpp:28-51) with
+ * DepthSensorModel::inverseModel (src/Grabber/depthSensorModel.cpp:18-25), RGBD::removeFarMapFeatures (RGBD.cpp:232-252).
+ * map_xyz: M x 3 double global positions; view_axis: M x 3 float, third column of the rotation of the view that
+ * holds each feature's descriptor; camera_pose: column-major 4x4 double (camera -> global, Mat34::matrix()).
+ * Outputs, compacted in input order (capacity M): kept_idx, xyz_local M x 3 double, uv M x 2 double ((-1,-1) when the
+ * projection leaves the image or the depth box), angles.  */
+typedef struct {
+    double fx, fy, cx, cy;      /* DepthSensorModel focalLength / focalAxis */
+    double image_w, image_h;    /* DepthSensorModel imageSize */
+    double max_angle;           /* matcherParameters.maxAngleBetweenFrames */
+    double max_z;               /* 5.0 in PUTSLAM.cpp:662 */
+} pslam_map_prepare_params;
+PSLAM_API int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_axis, int M,
+                                const double camera_pose[16], const pslam_map_prepare_params* params, int* kept_idx,
+                                double* xyz_local, double* uv, double* angles, int* n_out);
+
 /* ---- loop-closure sweep: query frame vs every keyframe of the map --------------------------
  * Generalises Matcher::matchFeatureLoopClosure's performMatching step (src/Matcher/matcher.cpp:802-861,
  * :835) from one FABMAP-proposed pair to all keyframes: score(k) = number of mutual-NN matches between

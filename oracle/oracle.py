@@ -199,6 +199,20 @@ def uncertainty_from_normal(normal, scale):
     return cov.reshape(3, 3)
 
 
+def map_prepare(xyz, view_axis, pose, fx, fy, cx, cy, img_w=640, img_h=480, max_angle=0.6, max_z=5.0):
+    """-> (kept int32[n], xyz_local f64[n,3], uv f64[n,2], angles f64[n]); pose = 4x4 camera->global (numpy row-major)"""
+    xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+    va = np.ascontiguousarray(view_axis, np.float32).reshape(-1, 3)
+    pcm = np.ascontiguousarray(np.asarray(pose, np.float64).T)      # column-major
+    M = xyz.shape[0]
+    kept = np.empty(max(1, M), np.int32); xl = np.empty((max(1, M), 3), np.float64)
+    uv = np.empty((max(1, M), 2), np.float64); ang = np.empty(max(1, M), np.float64)
+    n = lib().orc_map_prepare(_p(xyz, C.c_double), _p(va, C.c_float), M, _p(pcm, C.c_double), C.c_double(fx), C.c_double(fy),
+                              C.c_double(cx), C.c_double(cy), C.c_double(img_w), C.c_double(img_h), C.c_double(max_angle),
+                              C.c_double(max_z), _p(kept, C.c_int), _p(xl, C.c_double), _p(uv, C.c_double), _p(ang, C.c_double))
+    return kept[:n].copy(), xl[:n].copy(), uv[:n].copy(), ang[:n].copy()
+
+
 def svd3f(A):
     A = np.ascontiguousarray(A, np.float32)
     U = np.empty((3, 3), np.float32); S = np.empty(3, np.float32); V = np.empty((3, 3), np.float32)

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
-    "pslam_frame_to_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
+    "pslam_frame_to_map", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
@@ -48,6 +48,11 @@ class RansacParams(C.Structure):
                 ("inlier_threshold_reprojection", C.c_double), ("minimal_inlier_ratio_threshold", C.c_double),
                 ("minimal_number_of_matches", C.c_int), ("used_pairs", C.c_int),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class MapPrepareParams(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("image_w", C.c_double), ("image_h", C.c_double), ("max_angle", C.c_double), ("max_z", C.c_double)]
 
 
 class FrameResult(C.Structure):
@@ -317,6 +322,20 @@ class Context:
         return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
                     T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
                     inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used)
+
+    def map_prepare(self, map_xyz, view_axis, pose, params):
+        """pose: numpy 4x4 (camera -> global)."""
+        x = _arr(map_xyz, np.float64, 3); a = _arr(view_axis, np.float32, 3)
+        M = x.shape[0] if x.size else 0
+        pcm = np.ascontiguousarray(np.asarray(pose, np.float64).T)
+        kept = np.empty(max(1, M), np.int32); xl = np.empty((max(1, M), 3), np.float64)
+        uv = np.empty((max(1, M), 2), np.float64); ang = np.empty(max(1, M), np.float64)
+        n = C.c_int(0)
+        self._ck(self.lib.pslam_map_prepare(self.h, _p(x, C.c_double), _p(a, C.c_float), M, _p(pcm, C.c_double), C.byref(params),
+                                            _p(kept, C.c_int), _p(xl, C.c_double), _p(uv, C.c_double), _p(ang, C.c_double),
+                                            C.byref(n)))
+        k = n.value
+        return kept[:k].copy(), xl[:k].copy(), uv[:k].copy(), ang[:k].copy()
 
     def frame_to_map_resident(self):
         self._ck(self.lib.pslam_frame_to_map_resident(self.h))

@@ -902,6 +902,43 @@ int pslam_frame_to_frame_resident(pslam_ctx* ctx) {
     return enqueue_f2f(ctx);
 }
 
+// ---- map-side preparation -------------------------------------------------------------------------
+int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_axis, int M, const double camera_pose[16],
+                      const pslam_map_prepare_params* params, int* kept_idx, double* xyz_local, double* uv, double* angles,
+                      int* n_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || M < 0 || !camera_pose || !params) return fail(ctx, PSLAM_ERR_ARG, "pslam_map_prepare: bad argument");
+    *n_out = 0;
+    if (M == 0) return PSLAM_OK;
+    if (!map_xyz || !view_axis || !kept_idx || !xyz_local || !uv || !angles) return fail(ctx, PSLAM_ERR_ARG, "pslam_map_prepare: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_x = in.take(24 * (size_t)M), o_a = in.take(12 * (size_t)M);
+    const size_t o_n = out.take(16), o_k = out.take(4 * (size_t)M), o_xl = out.take(24 * (size_t)M);
+    const size_t o_uv = out.take(16 * (size_t)M), o_ang = out.take(8 * (size_t)M);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    memcpy(ctx->h_in.p + o_x, map_xyz, 24 * (size_t)M);
+    memcpy(ctx->h_in.p + o_a, view_axis, 12 * (size_t)M);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_map_prepare((const double*)(ctx->d_in.p + o_x), (const float*)(ctx->d_in.p + o_a), M, camera_pose, params->fx,
+                          params->fy, params->cx, params->cy, params->image_w, params->image_h, params->max_angle,
+                          params->max_z, (int*)(ctx->d_out.p + o_k), (double*)(ctx->d_out.p + o_xl),
+                          (double*)(ctx->d_out.p + o_uv), (double*)(ctx->d_out.p + o_ang), (int*)(ctx->d_out.p + o_n),
+                          ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int n = *(const int*)(ctx->h_out.p + o_n);
+    memcpy(kept_idx, ctx->h_out.p + o_k, 4 * (size_t)n);
+    memcpy(xyz_local, ctx->h_out.p + o_xl, 24 * (size_t)n);
+    memcpy(uv, ctx->h_out.p + o_uv, 16 * (size_t)n);
+    memcpy(angles, ctx->h_out.p + o_ang, 8 * (size_t)n);
+    *n_out = n;
+    return PSLAM_OK;
+}
+
 // ---- loop-closure database ----------------------------------------------------------------------
 int pslam_lc_db_reserve(pslam_ctx* ctx, int64_t max_descriptors, int max_keyframes) {
     if (!ctx) return PSLAM_ERR_ARG;

@@ -91,4 +91,10 @@ cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_param
 cudaError_t launch_kabsch_batch(const double* d_A, const double* d_B, const int* d_off, int batch, double* d_T,
                                 cudaStream_t st, int* launches);
 
+// ---- mapprep.cu ------------------------------------------------------------------------------
+cudaError_t launch_map_prepare(const double* d_xyz, const float* d_view_axis, int M, const double* pose_colmajor,
+                               double fx, double fy, double cx, double cy, double img_w, double img_h, double max_angle,
+                               double max_z, int* d_kept, double* d_xyz_local, double* d_uv, double* d_angles, int* d_n,
+                               cudaStream_t st, int* launches);
+
 }  // namespace pslam

@@ -371,3 +371,27 @@ def test_ransac_usac_standard_stopping(ctx, O):
                 assert np.array_equal(r["inliers"], o["inliers"]) and np.abs(r["T"] - o["T"]).max() <= 1e-5
     finally:
         ctx.ransac_set_stopping(0, 0.99); O.set_stopping(0, 0.99)
+
+
+def test_map_prepare(ctx, O):
+    """Map-side preparation: view-angle filter, global->local, projection, far-feature removal.
+    Kept indices identical; float64 positions within 1e-12 relative, angles within 1e-6 rad (acos of a float ratio)."""
+    from putslam_b200 import api, synth
+    rng = np.random.default_rng(17)
+    M = 5000
+    pose = np.eye(4); pose[:3, :3] = synth.rot_from_rotvec([0.1, 0.7, -0.2]); pose[:3, 3] = [1.0, -0.5, 2.0]
+    local = np.stack([rng.uniform(-3, 3, M), rng.uniform(-2, 2, M), rng.uniform(0.3, 7.0, M)], 1)
+    glob = local @ pose[:3, :3].T + pose[:3, 3]
+    axes = np.stack([synth.rot_from_rotvec(rng.normal(0, 0.5, 3))[:, 2] for _ in range(M)]) @ pose[:3, :3].T
+    axes = (axes * rng.uniform(0.9, 1.1, (M, 1))).astype(np.float32)
+    axes[5] = np.nan
+    prm = api.MapPrepareParams(synth.FX, synth.FY, synth.CX, synth.CY, 640, 480, 0.6, 5.0)
+    kept, xl, uv, ang = ctx.map_prepare(glob, axes, pose, prm)
+    ek, exl, euv, eang = O.map_prepare(glob, axes, pose, synth.FX, synth.FY, synth.CX, synth.CY, 640, 480, 0.6, 5.0)
+    assert np.array_equal(kept, ek) and 500 < kept.size < M and 5 not in kept
+    assert np.allclose(xl, exl, rtol=1e-12, atol=1e-13) and np.allclose(uv, euv, rtol=1e-12, atol=1e-10)
+    assert np.abs(ang - eang).max() < 1e-6
+    assert np.abs(xl - local[kept]).max() < 1e-9 and (xl[:, 2] <= 5.0).all() and (ang <= 0.6).all()
+    inside = uv[:, 0] >= 0
+    assert inside.any() and (~inside).any() and (xl[inside, 2] >= 0.8).all()
+    assert ctx.map_prepare(np.zeros((0, 3)), np.zeros((0, 3), np.float32), pose, prm)[0].size == 0

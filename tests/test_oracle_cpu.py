@@ -108,6 +108,26 @@ def test_normal_and_uncertainty_from_normal(O):
     assert np.isnan(O.compute_normal(depth, 300, 200, synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)).all()
 
 
+def test_map_prepare_against_numpy(O):
+    from putslam_b200 import synth
+    rng = np.random.default_rng(3)
+    pose = np.eye(4); pose[:3, :3] = synth.rot_from_rotvec([0.3, -0.2, 0.1]); pose[:3, 3] = [0.5, 0.2, -1.0]
+    M = 300
+    local = np.stack([rng.uniform(-2, 2, M), rng.uniform(-1, 1, M), rng.uniform(0.5, 6.5, M)], 1)
+    glob = local @ pose[:3, :3].T + pose[:3, 3]
+    axes = np.stack([synth.rot_from_rotvec(rng.normal(0, 0.5, 3))[:, 2] for _ in range(M)]).astype(np.float32)
+    kept, xl, uv, ang = O.map_prepare(glob, axes, pose, synth.FX, synth.FY, synth.CX, synth.CY, 640, 480, 0.6, 5.0)
+    zc = pose[:3, 2]
+    a = np.arccos(np.clip((axes.astype(np.float64) @ zc) / np.linalg.norm(axes.astype(np.float64), axis=1), -1, 1))
+    exp = np.nonzero((a <= 0.6) & (local[:, 2] <= 5.0))[0]
+    border = np.abs(a - 0.6) < 1e-6
+    assert set(kept.tolist()) ^ set(exp.tolist()) <= set(np.nonzero(border)[0].tolist())
+    assert np.abs(xl - local[kept]).max() < 1e-12 and np.abs(ang - a[kept]).max() < 1e-6
+    u = synth.FX * local[kept, 0] / local[kept, 2] + synth.CX
+    ok = uv[:, 0] >= 0
+    assert np.abs(uv[ok, 0] - u[ok]).max() < 1e-9
+
+
 def test_philox_known_answers(O):
     # Random123 kat_vectors, philox4x32-10
     assert O.philox([0, 0, 0, 0], [0, 0]).tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
