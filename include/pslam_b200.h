@@ -259,6 +259,10 @@ PSLAM_API int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* 
 /* global id of local keyframe 0 (rank r of a sharded map owns ids [base, base + n_keyframes)) */
 PSLAM_API int pslam_lc_set_id_base(pslam_ctx* ctx, int kf_id_base);
 
+/* Work unit of the V1 sweep: 0 = automatic (whole keyframes when the GPU holds >= 4096 of them, 128-row tiles with a
+ * finalize pass below that), 1 = keyframes, 2 = tiles.  Results are identical; this is a performance knob. */
+PSLAM_API int pslam_lc_set_work_unit(pslam_ctx* ctx, int mode);
+
 /* Single-GPU query.  out_* sized k (<= PSLAM_LC_MAX_TOPK); unused slots -1.  scores_out (nullable):
  * n_keyframes per-keyframe scores. */
 PSLAM_API int pslam_lc_query(pslam_ctx* ctx, const uint8_t* query, int nq, int tau, int k, int* out_kf_ids,

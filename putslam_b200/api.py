@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
-    "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_query",
+    "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_set_work_unit", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
     "pslam_lc_knn2_sharded", "pslam_lc_knn2_resident",
@@ -358,6 +358,9 @@ class Context:
         nk = C.c_int(0); nd = C.c_int64(0)
         self._ck(self.lib.pslam_lc_db_size(self.h, C.byref(nk), C.byref(nd)))
         return nk.value, nd.value
+
+    def lc_set_work_unit(self, mode):
+        self._ck(self.lib.pslam_lc_set_work_unit(self.h, int(mode)))
 
     def lc_set_id_base(self, base):
         self._ck(self.lib.pslam_lc_set_id_base(self.h, int(base)))

@@ -119,6 +119,7 @@ struct pslam_ctx {
     DevBuf d_tile_start, d_split;
     int n_tiles = 0;
     bool tiles_dirty = true;
+    int lc_work_unit = 0;       // 0 auto, 1 keyframes, 2 tiles
     int kf_cap = 0, n_kf = 0, kf_id_base = 0;
     long long desc_id_base = 0;
     DevBuf d_knn;  // V2 sweep scratch: per-CTA partials | merged keys | gathered keys | idx | dist
@@ -1030,6 +1031,13 @@ int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* n_descript
     return PSLAM_OK;
 }
 
+int pslam_lc_set_work_unit(pslam_ctx* ctx, int mode) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (mode < 0 || mode > 2) return fail(ctx, PSLAM_ERR_ARG, "work unit mode must be 0, 1 or 2");
+    ctx->lc_work_unit = mode;
+    return PSLAM_OK;
+}
+
 int pslam_lc_set_id_base(pslam_ctx* ctx, int kf_id_base) {
     if (!ctx) return PSLAM_ERR_ARG;
     ctx->kf_id_base = kf_id_base;
@@ -1061,7 +1069,7 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
 static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
     int l = 0;
     // work-unit choice: whole keyframes when every CTA gets many of them, 128-row tiles otherwise
-    const bool split = ctx->n_kf > 0 && ctx->n_kf < kSplitMaxKeyframes;
+    const bool split = ctx->n_kf > 0 && (ctx->lc_work_unit == 2 || (ctx->lc_work_unit == 0 && ctx->n_kf < kSplitMaxKeyframes));
     if (split && ctx->tiles_dirty) {
         std::vector<int> ts((size_t)ctx->n_kf + 1, 0);
         for (int k = 0; k < ctx->n_kf; ++k)

@@ -19,11 +19,13 @@ def test_lc_scores_vs_oracle(ctx, O, n_kf, per_kf, nq, ragged):
                            seed=n_kf, ragged=ragged)
     _fresh(ctx)
     ctx.lc_append(db["db"], db["kf_off"])
-    ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=16, want_scores=True)
     ref = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=8)
-    assert np.array_equal(scores, ref)
     eid, esc = O.topk(ref, 16)
-    assert np.array_equal(ids, eid) and np.array_equal(sc, esc)
+    for unit in (1, 2, 0):     # keyframe work units, tile work units, automatic
+        ctx.lc_set_work_unit(unit)
+        ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=16, want_scores=True)
+        assert np.array_equal(scores, ref), unit
+        assert np.array_equal(ids, eid) and np.array_equal(sc, esc), unit
     for tau in (0, 30, 256):
         _, _, s2 = ctx.lc_query(db["query"], tau=tau, k=4, want_scores=True)
         assert np.array_equal(s2, O.lc_scores(db["query"], db["db"], db["kf_off"], tau=tau, threads=8))
