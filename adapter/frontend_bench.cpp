@@ -1,0 +1,96 @@
+// frontend_bench.cpp -- end-to-end timing of the front end through the C++ adapter (the call a PUTSLAM build
+// makes): MatcherB200::matchXYZCore (frame-to-map, host buffers in, matches + pose out) and the VO path
+// performMatching -> keypoints2Dto3D -> RANSAC.  Inputs are raw arrays written by bench.py.
+// usage: frontend_bench <dir> <frames> <warmup> <num_hyp>      prints one JSON object
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "pslam_adapter.h"
+
+using namespace putslam_b200;
+static std::string g_dir;
+template <typename T>
+static std::vector<T> rd(const std::string& name) {
+    std::ifstream f(g_dir + "/" + name, std::ios::binary | std::ios::ate);
+    if (!f) { std::cerr << "missing " << name << std::endl; exit(2); }
+    const size_t n = (size_t)f.tellg();
+    std::vector<T> v(n / sizeof(T));
+    f.seekg(0);
+    f.read((char*)v.data(), (std::streamsize)n);
+    return v;
+}
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char** argv) {
+    if (argc < 5) { std::cerr << "usage: frontend_bench <dir> <frames> <warmup> <num_hyp>" << std::endl; return 2; }
+    g_dir = argv[1];
+    const int frames = atoi(argv[2]), warmup = atoi(argv[3]), num_hyp = atoi(argv[4]);
+    float Kf[9] = {517.3f, 0, 318.6f, 0, 516.5f, 255.3f, 0, 0, 1};
+    cv::Mat K(3, 3, CV_32FC1, Kf);
+    MatcherB200 matcher(0);
+    matcher.setFixedHypotheses(num_hyp);
+    RANSAC::parameters rp;
+    rp.verbose = 0; rp.errorVersion = rp.errorVersionVO = rp.errorVersionMap = 0;
+    rp.inlierThresholdEuclidean = 0.04; rp.inlierThresholdReprojection = 2.0; rp.inlierThresholdMahalanobis = 9.0;
+    rp.minimalInlierRatioThreshold = 0.2; rp.minimalNumberOfMatches = 15; rp.usedPairs = 3; rp.iterationCount = 0;
+
+    MatcherB200::MapSide map;
+    map.xyz = rd<double>("map_xyz.bin");
+    auto mdesc = rd<uint8_t>("map_desc.bin");
+    map.descriptors = cv::Mat((int)(mdesc.size() / 32), 32, CV_8U, mdesc.data());
+    map.octave = rd<int>("map_octave.bin");
+    map.detDist = rd<double>("map_detdist.bin");
+    auto cxyz = rd<float>("cur_xyz.bin");
+    auto cdesc = rd<uint8_t>("cur_desc.bin");
+    auto coct = rd<int>("cur_octave.bin");
+    std::vector<double> cdet = rd<double>("cur_detdist.bin");
+    std::vector<Eigen::Vector3f> cur3D(cxyz.size() / 3);
+    std::vector<cv::KeyPoint> curKp(cur3D.size());
+    for (size_t i = 0; i < cur3D.size(); ++i) { cur3D[i] = Eigen::Vector3f(cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2]); curKp[i].octave = coct[i]; }
+    cv::Mat curDesc((int)(cdesc.size() / 32), 32, CV_8U, cdesc.data());
+
+    Eigen::Matrix4f T;
+    std::vector<cv::DMatch> mm, mi;
+    double t0 = 0, ratio = 0;
+    for (int i = 0; i < warmup + frames; ++i) {
+        if (i == warmup) t0 = now_ms();
+        matcher.setSeed((uint64_t)i);
+        ratio = matcher.matchXYZCore(map, curDesc, cur3D, curKp, cdet, 0.12, 0.55, 1, rp, K, T, mm, mi);
+    }
+    const double map_ms = (now_ms() - t0) / frames;
+
+    // VO path on a frame pair
+    auto d1 = rd<uint8_t>("desc1.bin"), d2 = rd<uint8_t>("desc2.bin");
+    auto uv1 = rd<float>("uv1.bin"), uv2 = rd<float>("uv2.bin");
+    auto z1 = rd<uint16_t>("depth1.bin"), z2 = rd<uint16_t>("depth2.bin");
+    cv::Mat D1((int)(d1.size() / 32), 32, CV_8U, d1.data()), D2((int)(d2.size() / 32), 32, CV_8U, d2.data());
+    cv::Mat depth1(480, 640, CV_16U, z1.data()), depth2(480, 640, CV_16U, z2.data());
+    std::vector<cv::Point2f> p1(uv1.size() / 2), p2(uv2.size() / 2);
+    for (size_t i = 0; i < p1.size(); ++i) p1[i] = cv::Point2f(uv1[2 * i], uv1[2 * i + 1]);
+    for (size_t i = 0; i < p2.size(); ++i) p2[i] = cv::Point2f(uv2[2 * i], uv2[2 * i + 1]);
+    std::vector<Eigen::Vector3f> x1 = RGBD::keypoints2Dto3D(p1, depth1, K, 5000.0);
+    size_t vo_inl = 0, vo_matches = 0;
+    for (int i = 0; i < warmup + frames; ++i) {
+        if (i == warmup) t0 = now_ms();
+        std::vector<cv::DMatch> matches = matcher.performMatching(D1, D2);
+        std::vector<Eigen::Vector3f> x2 = RGBD::keypoints2Dto3D(p2, depth2, K, 5000.0);
+        RANSAC ransac(rp, K);
+        ransac.setSeed((uint64_t)i);
+        std::vector<cv::DMatch> inliers;
+        Eigen::Matrix4f Tv = ransac.estimateTransformation(x1, x2, matches, inliers);
+        (void)Tv;
+        vo_inl = inliers.size(); vo_matches = matches.size();
+    }
+    const double vo_ms = (now_ms() - t0) / frames;
+    printf("{\"frame_to_map_ms\": %.5f, \"map_matches\": %zu, \"map_inliers\": %zu, \"map_ratio\": %.4f, "
+           "\"vo_three_calls_ms\": %.5f, \"vo_matches\": %zu, \"vo_inliers\": %zu, \"frames\": %d, \"num_hyp\": %d}\n",
+           map_ms, mm.size(), mi.size(), ratio, vo_ms, vo_matches, vo_inl, frames, num_hyp);
+    return 0;
+}

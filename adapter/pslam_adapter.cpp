@@ -213,19 +213,25 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
         matchingXYZacceptRatioOfBestMatch = std::max(0.1, matchingXYZacceptRatioOfBestMatch - 0.05 * (computationNumber - 1));
     }
     const int N = (int)currentPoseKeyPoints.size(), M = (int)map.octave.size();
-    std::vector<int> curLevels((size_t)N), mapLevels((size_t)M);
-    for (int i = 0; i < N; ++i) {   // matcher.cpp:639-651: curDist = Vector3f::norm() (float) widened
-        const float x = currentPoseFeatures3D[i][0], y = currentPoseFeatures3D[i][1], z = currentPoseFeatures3D[i][2];
-        const float yy = y * y, zz = z * z;
-        const double curDist = std::sqrt(x * x + (yy + zz));   // float expression -> sqrtf -> double
-        curLevels[i] = predictedLevel(currentPoseKeyPoints[i].octave, currentPoseDetDists[i], curDist);
-    }
-    std::vector<float> mapXyz(3 * (size_t)M);
-    for (int j = 0; j < M; ++j) {   // matcher.cpp:682-692 (double norm of the double position), :665 (cast to float)
-        const double px = map.xyz[3 * j], py = map.xyz[3 * j + 1], pz = map.xyz[3 * j + 2];
-        const double curDist = std::sqrt(px * px + py * py + pz * pz);
-        mapLevels[j] = predictedLevel(map.octave[j], map.detDist[j], curDist);
-        mapXyz[3 * j] = (float)px; mapXyz[3 * j + 1] = (float)py; mapXyz[3 * j + 2] = (float)pz;
+    std::vector<int> curLevels, mapLevels, curOct;
+    std::vector<float> mapXyz;
+    if (hostLevels_) {
+        curLevels.resize((size_t)N); mapLevels.resize((size_t)M); mapXyz.resize(3 * (size_t)M);
+        for (int i = 0; i < N; ++i) {   // matcher.cpp:639-651: curDist = Vector3f::norm() (float) widened
+            const float x = currentPoseFeatures3D[i][0], y = currentPoseFeatures3D[i][1], z = currentPoseFeatures3D[i][2];
+            const float yy = y * y, zz = z * z;
+            const double curDist = std::sqrt(x * x + (yy + zz));   // float expression -> sqrtf -> double
+            curLevels[i] = predictedLevel(currentPoseKeyPoints[i].octave, currentPoseDetDists[i], curDist);
+        }
+        for (int j = 0; j < M; ++j) {   // matcher.cpp:682-692 (double norm of the double position), :665 (cast to float)
+            const double px = map.xyz[3 * j], py = map.xyz[3 * j + 1], pz = map.xyz[3 * j + 2];
+            const double curDist = std::sqrt(px * px + py * py + pz * pz);
+            mapLevels[j] = predictedLevel(map.octave[j], map.detDist[j], curDist);
+            mapXyz[3 * j] = (float)px; mapXyz[3 * j + 1] = (float)py; mapXyz[3 * j + 2] = (float)pz;
+        }
+    } else {
+        curOct.resize((size_t)N);
+        for (int i = 0; i < N; ++i) curOct[i] = currentPoseKeyPoints[i].octave;
     }
     std::vector<uint8_t> tm, tc;
     const uint8_t* md = contiguousBytes(map.descriptors, 32, tm);
@@ -246,19 +252,27 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     int r = PSLAM_ERR_NO_DEVICE;
     for (int attempt = 0; c && attempt < 6; ++attempt) {   // the reference's match vector is unbounded: grow on truncation
         mq.resize((size_t)cap); mt.resize((size_t)cap); mdist.resize((size_t)cap); inl.resize((size_t)cap);
-        r = pslam_frame_to_map(c, mapXyz.data(), md, mapLevels.data(), M, &currentPoseFeatures3D[0][0], cd, curLevels.data(), N,
-                               matchingXYZSphereRadius, matchingXYZacceptRatioOfBestMatch, xorDistance ? 1 : 0, &a, seed_, numHyp_,
-                               cap, mq.data(), mt.data(), mdist.data(), inl.data(), &res);
+        if (hostLevels_)
+            r = pslam_frame_to_map(c, mapXyz.data(), md, mapLevels.data(), M, &currentPoseFeatures3D[0][0], cd, curLevels.data(), N,
+                                   matchingXYZSphereRadius, matchingXYZacceptRatioOfBestMatch, xorDistance ? 1 : 0, &a, seed_,
+                                   numHyp_, cap, mq.data(), mt.data(), mdist.data(), inl.data(), &res);
+        else
+            r = pslam_frame_to_map_features(c, map.xyz.data(), md, map.octave.data(), map.detDist.data(), M,
+                                            &currentPoseFeatures3D[0][0], cd, curOct.data(), currentPoseDetDists.data(), N,
+                                            matchingXYZSphereRadius, matchingXYZacceptRatioOfBestMatch, xorDistance ? 1 : 0, &a,
+                                            seed_, numHyp_, cap, mq.data(), mt.data(), mdist.data(), inl.data(), &res);
         if (r != PSLAM_ERR_CAPACITY) break;
         cap = res.n_matches + 16;
     }
     estimatedTransformation = Eigen::Matrix4f::Identity();
     if (r != PSLAM_OK) { logError(c, "matchXYZ", r); return -1.0; }
     if (res.n_matches <= 0) return -1.0;   // matcher.cpp:755-756
+    matches.reserve((size_t)res.n_matches);
+    inlierMatches.reserve((size_t)res.n_inliers);
     for (int k = 0; k < res.n_matches; ++k) matches.push_back(cv::DMatch(mq[k], mt[k], -1, mdist[k]));
     for (int k = 0; k < res.n_inliers; ++k) inlierMatches.push_back(matches[(size_t)inl[k]]);
     std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
-    return RANSAC::pointInlierRatio(inlierMatches, matches);   // matcher.cpp:797
+    return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
 double MatcherB200::matchFeatureLoopClosureCore(cv::Mat descriptors0, const std::vector<Eigen::Vector3f>& points3D0,

@@ -90,6 +90,7 @@ int main(int argc, char** argv) {
     std::vector<cv::KeyPoint> curKp(cur3D.size());
     for (size_t i = 0; i < cur3D.size(); ++i) { cur3D[i] = Eigen::Vector3f(cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2]); curKp[i].octave = coct[i]; }
     for (int cn = 1; cn <= 2; ++cn) {
+        matcher.setHostLevels(cn == 2);   // first call: levels on the device, retry: host libm levels (both must agree with the oracle)
         Eigen::Matrix4f Tm;
         std::vector<cv::DMatch> mm, mi;
         matcher.setSeed(77);

@@ -276,6 +276,34 @@ def frontend_numbers(ctx, steps, warmup):
     return out
 
 
+def native_frontend_numbers(frames, warmup):
+    """The same front end driven from C++ through the adapter classes (adapter/frontend_bench): what a PUTSLAM
+    build would see per frame, without Python/ctypes in the timed loop."""
+    import tempfile
+    from putslam_b200 import synth
+    exe = os.path.join(ROOT, "adapter", "frontend_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "adapter/frontend_bench not built"}
+    mf = synth.map_frame(M=5000, N=1000, seed=0)
+    fp = synth.frame_pair(n=1000, seed=1)
+    with tempfile.TemporaryDirectory() as d:
+        for name, arr, dt in [("map_xyz", mf["map_xyz"], np.float64), ("map_desc", mf["map_desc"], np.uint8),
+                              ("map_octave", mf["map_octave"], np.int32), ("map_detdist", mf["map_detdist"], np.float64),
+                              ("cur_xyz", mf["cur_xyz"], np.float32), ("cur_desc", mf["cur_desc"], np.uint8),
+                              ("cur_octave", mf["cur_octave"], np.int32), ("cur_detdist", mf["cur_detdist"], np.float64),
+                              ("desc1", fp["desc1"], np.uint8), ("desc2", fp["desc2"], np.uint8), ("uv1", fp["uv1"], np.float32),
+                              ("uv2", fp["uv2"], np.float32), ("depth1", fp["depth1"], np.uint16), ("depth2", fp["depth2"], np.uint16)]:
+            np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
+        try:
+            out = subprocess.check_output([exe, d, str(frames), str(warmup), "4096"], text=True, timeout=300)
+            r = json.loads(out.strip().splitlines()[-1])
+        except Exception as e:  # noqa: BLE001
+            return {"unavailable": str(e)}
+    r["note"] = ("C++ adapter, host buffers: frame_to_map = MatcherB200::matchXYZCore incl. host-side level prediction and "
+                 "double->float marshalling; vo_three_calls = performMatching + keypoints2Dto3D + RANSAC as three separate calls")
+    return r
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -436,6 +464,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_sweep_baseline(sub)
         if world == 1 and not args.no_frontend:
             fe = frontend_numbers(ctx, max(10, args.steps), args.warmup)
+            fe["native_cpp"] = native_frontend_numbers(max(20, args.steps), args.warmup)
             if not args.no_cpu_baseline:
                 fe["cpu_baseline_c3"] = cpu_frontend_baseline()
             line["frontend"] = fe

@@ -213,6 +213,20 @@ PSLAM_API int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uin
                                  int* match_query_out, int* match_train_out, float* match_dist_out,
                                  int* inlier_idx_out, pslam_frame_result* result);
 
+/* Same pipeline from the raw feature attributes: map_xyz M x 3 DOUBLE (MapFeature.position), octave and detDist of the
+ * descriptor's view (ExtendedDescriptor.octave / .detDist), current keypoints' octave and detDist.  The predicted
+ * pyramid levels (matcher.cpp:639-651, 682-692) and the double->float cast (:665) then run on the device, which takes
+ * ~0.2 ms of pow()/log() per frame off the host.  The one case that depends on the last bit of the host's log() --
+ * detDist == curDist exactly -- is answered from tables built with the host libm, so the levels equal the host-computed
+ * ones (tests/test_gpu_parity.py::test_frame_to_map_device_levels). */
+PSLAM_API int pslam_frame_to_map_features(pslam_ctx* ctx, const double* map_xyz, const uint8_t* map_desc,
+                                          const int* map_octave, const double* map_det_dist, int M, const float* cur_xyz,
+                                          const uint8_t* cur_desc, const int* cur_octave, const double* cur_det_dist, int N,
+                                          double radius, double accept_ratio, int distance_mode,
+                                          const pslam_ransac_params* params, uint64_t seed, int num_hyp, int match_cap,
+                                          int* match_query_out, int* match_train_out, float* match_dist_out,
+                                          int* inlier_idx_out, pslam_frame_result* result);
+
 /* Loop-closure pair verification: Matcher::matchFeatureLoopClosure (src/Matcher/matcher.cpp:802-861) minus the
  * MapFeature marshalling: performMatching(desc0, desc1) -> RANSAC(xyz0, xyz1, matches) in one submission.
  * result->inlier_ratio follows the reference: 0 when either set has fewer than 10 features (:830-834), -1 when

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
-    "pslam_frame_to_map", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
+    "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_set_work_unit", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
@@ -336,6 +336,27 @@ class Context:
                                             C.byref(n)))
         k = n.value
         return kept[:k].copy(), xl[:k].copy(), uv[:k].copy(), ang[:k].copy()
+
+    def frame_to_map_features(self, map_xyz, map_desc, map_octave, map_detdist, cur_xyz, cur_desc, cur_octave, cur_detdist,
+                              radius=0.12, ratio=0.55, mode=0, params=None, seed=0, num_hyp=0, match_cap=16384):
+        mx = _arr(map_xyz, np.float64, 3); cx = _arr(cur_xyz, np.float32, 3)
+        md_ = _arr(map_desc, np.uint8); cd = _arr(cur_desc, np.uint8)
+        mo = _arr(map_octave, np.int32); co = _arr(cur_octave, np.int32)
+        mdd = _arr(map_detdist, np.float64); cdd = _arr(cur_detdist, np.float64)
+        params = params or default_ransac_params()
+        mq = np.empty(match_cap, np.int32); mt = np.empty(match_cap, np.int32); md = np.empty(match_cap, np.float32)
+        inl = np.empty(match_cap, np.int32)
+        res = FrameResult()
+        self._ck(self.lib.pslam_frame_to_map_features(self.h, _p(mx, C.c_double), _p(md_, C.c_uint8), _p(mo, C.c_int),
+                                                      _p(mdd, C.c_double), mo.size, _p(cx, C.c_float), _p(cd, C.c_uint8),
+                                                      _p(co, C.c_int), _p(cdd, C.c_double), co.size, C.c_double(radius),
+                                                      C.c_double(ratio), mode, C.byref(params), C.c_uint64(seed), num_hyp,
+                                                      match_cap, _p(mq, C.c_int), _p(mt, C.c_int), _p(md, C.c_float),
+                                                      _p(inl, C.c_int), C.byref(res)))
+        n = min(res.n_matches, match_cap)
+        return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
+                    T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
+                    inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used, n_filtered=res.n_filtered)
 
     def frame_to_map_resident(self):
         self._ck(self.lib.pslam_frame_to_map_resident(self.h))

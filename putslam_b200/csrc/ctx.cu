@@ -84,6 +84,10 @@ constexpr int kSplitMaxKeyframes = 4096;
 // what a *_resident re-run needs to replay a pipeline on the buffers already in HBM
 struct F2MState {
     bool valid = false;
+    // device-side level prediction (pslam_frame_to_map_features): raw attributes -> map_xyz / levels work buffers
+    bool device_levels = false;
+    const double* map_xyz_d; const int* map_oct; const double* map_det; const int* cur_oct; const double* cur_det;
+    float* map_xyz_w; int* map_level_w; int* cur_level_w;
     const float* map_xyz; const uint8_t* map_desc; const int* map_level; int M;
     const float* cur_xyz; const uint8_t* cur_desc; const int* cur_level; int N;
     float sq_radius_f; double ratio; int mode; int cap;
@@ -658,9 +662,33 @@ int pslam_kabsch_batch(pslam_ctx* ctx, const double* A, const double* B, const i
 }
 
 // ---- fused pipelines ----------------------------------------------------------------------------
+// host-libm tables for the device level prediction (see guided.cu)
+struct HostLevelTables {
+    double pow_tab[16];
+    int lvl_tab[16];
+    double log_sf;
+    HostLevelTables() {
+        const double scaleFactor = 1.2;
+        log_sf = std::log(scaleFactor);
+        for (int k = 0; k < 16; ++k) {
+            pow_tab[k] = pow(scaleFactor, k);
+            lvl_tab[k] = (int)std::ceil(std::log(pow_tab[k]) / log_sf);
+        }
+    }
+};
+static const HostLevelTables& level_tables() {
+    static const HostLevelTables t;
+    return t;
+}
+
 static int enqueue_f2m(pslam_ctx* ctx) {
     F2MState& s = ctx->f2m;
     int l = 0;
+    if (s.device_levels) {
+        const HostLevelTables& t = level_tables();
+        CK(launch_predict_levels(s.map_xyz_d, s.map_oct, s.map_det, s.M, s.cur_xyz, s.cur_oct, s.cur_det, s.N, t.pow_tab,
+                                 t.lvl_tab, t.log_sf, s.map_xyz_w, s.map_level_w, s.cur_level_w, ctx->stream, &l));
+    }
     CK(launch_guided_match(s.map_xyz, s.map_desc, s.map_level, s.M, s.cur_xyz, s.cur_desc, s.cur_level, s.N, s.sq_radius_f,
                            s.ratio, s.mode, s.count, s.best, s.cache, s.gout, s.cap, ctx->stream, &l));
     CK(launch_ransac(s.map_xyz, s.cur_xyz, s.gout + 2, s.gout + 2 + s.cap, s.gout, 0, s.rp, s.ws, ctx->sm_count,
@@ -669,11 +697,16 @@ static int enqueue_f2m(pslam_ctx* ctx) {
     return PSLAM_OK;
 }
 
-int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level, int M,
-                       const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N, double radius,
-                       double accept_ratio, int distance_mode, const pslam_ransac_params* params, uint64_t seed,
-                       int num_hyp, int match_cap, int* match_query_out, int* match_train_out, float* match_dist_out,
-                       int* inlier_idx_out, pslam_frame_result* result) {
+struct F2MRaw {   // raw feature attributes for the device-level path (NULL map_xyz_d = levels given by the caller)
+    const double* map_xyz_d = nullptr; const int* map_oct = nullptr; const double* map_det = nullptr;
+    const int* cur_oct = nullptr; const double* cur_det = nullptr;
+};
+static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level, int M,
+                             const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N, double radius,
+                             double accept_ratio, int distance_mode, const pslam_ransac_params* params, uint64_t seed,
+                             int num_hyp, int match_cap, int* match_query_out, int* match_train_out, float* match_dist_out,
+                             int* inlier_idx_out, pslam_frame_result* result, const F2MRaw& raw) {
+    const bool dev_levels = raw.map_xyz_d != nullptr;
     if (!ctx) return PSLAM_ERR_ARG;
     if (!result || M < 0 || N < 0 || match_cap <= 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map: bad argument");
     memset(result, 0, sizeof(*result));
@@ -684,14 +717,18 @@ int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_
     if (distance_mode != 0 && distance_mode != 1) return fail(ctx, PSLAM_ERR_ARG, "distance_mode must be 0 or 1");
     if (N > 12000) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "N above 12000 current keypoints");
     if (M == 0 || N == 0) return PSLAM_OK;  // no matches -> -1.0 (matcher.cpp:755)
-    if (!map_xyz || !map_desc || !map_level || !cur_xyz || !cur_desc || !cur_level || !match_query_out ||
-        !match_train_out || !match_dist_out || !inlier_idx_out)
+    if ((!dev_levels && (!map_xyz || !map_level || !cur_level)) ||
+        (dev_levels && (!raw.map_oct || !raw.map_det || !raw.cur_oct || !raw.cur_det)) || !map_desc || !cur_xyz || !cur_desc ||
+        !match_query_out || !match_train_out || !match_dist_out || !inlier_idx_out)
         return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map: null buffer");
     CK(cudaSetDevice(ctx->device));
     const int cap = match_cap;
     Arena in, out, work;
-    const size_t o_mx = in.take(12 * (size_t)M), o_md = in.take(32 * (size_t)M), o_ml = in.take(4 * (size_t)M);
+    // host-level path: map xyz (float) + levels are inputs; device-level path: map xyz (double), octaves, detDists
+    const size_t o_mx = in.take((dev_levels ? 24 : 12) * (size_t)M), o_md = in.take(32 * (size_t)M), o_ml = in.take(4 * (size_t)M);
     const size_t o_cx = in.take(12 * (size_t)N), o_cd = in.take(32 * (size_t)N), o_cl = in.take(4 * (size_t)N);
+    const size_t o_mdet = in.take(dev_levels ? 8 * (size_t)M : 8), o_cdet = in.take(dev_levels ? 8 * (size_t)N : 8);
+    const size_t o_wx = work.take(12 * (size_t)M), o_wml = work.take(4 * (size_t)M), o_wcl = work.take(4 * (size_t)N);
     const size_t o_g = out.take(sizeof(int) * (2 + 3 * (size_t)cap));
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
     const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
@@ -701,13 +738,31 @@ int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
     uint8_t* h = ctx->h_in.p;
-    memcpy(h + o_mx, map_xyz, 12 * (size_t)M); memcpy(h + o_md, map_desc, 32 * (size_t)M); memcpy(h + o_ml, map_level, 4 * (size_t)M);
-    memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N); memcpy(h + o_cl, cur_level, 4 * (size_t)N);
+    memcpy(h + o_md, map_desc, 32 * (size_t)M);
+    memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N);
+    if (dev_levels) {
+        memcpy(h + o_mx, raw.map_xyz_d, 24 * (size_t)M); memcpy(h + o_ml, raw.map_oct, 4 * (size_t)M);
+        memcpy(h + o_mdet, raw.map_det, 8 * (size_t)M);
+        memcpy(h + o_cl, raw.cur_oct, 4 * (size_t)N); memcpy(h + o_cdet, raw.cur_det, 8 * (size_t)N);
+    } else {
+        memcpy(h + o_mx, map_xyz, 12 * (size_t)M); memcpy(h + o_ml, map_level, 4 * (size_t)M);
+        memcpy(h + o_cl, cur_level, 4 * (size_t)N);
+    }
     CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* d = ctx->d_in.p;
     F2MState& s = ctx->f2m;
-    s.map_xyz = (const float*)(d + o_mx); s.map_desc = d + o_md; s.map_level = (const int*)(d + o_ml); s.M = M;
-    s.cur_xyz = (const float*)(d + o_cx); s.cur_desc = d + o_cd; s.cur_level = (const int*)(d + o_cl); s.N = N;
+    s.device_levels = dev_levels;
+    s.M = M; s.N = N;
+    s.map_desc = d + o_md; s.cur_xyz = (const float*)(d + o_cx); s.cur_desc = d + o_cd;
+    if (dev_levels) {
+        s.map_xyz_d = (const double*)(d + o_mx); s.map_oct = (const int*)(d + o_ml); s.map_det = (const double*)(d + o_mdet);
+        s.cur_oct = (const int*)(d + o_cl); s.cur_det = (const double*)(d + o_cdet);
+        s.map_xyz_w = (float*)(ctx->d_work.p + o_wx); s.map_level_w = (int*)(ctx->d_work.p + o_wml);
+        s.cur_level_w = (int*)(ctx->d_work.p + o_wcl);
+        s.map_xyz = s.map_xyz_w; s.map_level = s.map_level_w; s.cur_level = s.cur_level_w;
+    } else {
+        s.map_xyz = (const float*)(d + o_mx); s.map_level = (const int*)(d + o_ml); s.cur_level = (const int*)(d + o_cl);
+    }
     s.sq_radius_f = sq_threshold(float_at_least(radius)); s.ratio = accept_ratio; s.mode = distance_mode; s.cap = cap;
     s.count = (int*)(ctx->d_work.p + o_cnt); s.best = (int*)(ctx->d_work.p + o_best); s.cache = ctx->d_work.p + o_cache;
     s.gout = (int*)(ctx->d_out.p + o_g);
@@ -734,6 +789,35 @@ int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_
     for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
     result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
     return PSLAM_OK;
+}
+
+int pslam_frame_to_map(pslam_ctx* ctx, const float* map_xyz, const uint8_t* map_desc, const int* map_level, int M,
+                       const float* cur_xyz, const uint8_t* cur_desc, const int* cur_level, int N, double radius,
+                       double accept_ratio, int distance_mode, const pslam_ransac_params* params, uint64_t seed,
+                       int num_hyp, int match_cap, int* match_query_out, int* match_train_out, float* match_dist_out,
+                       int* inlier_idx_out, pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    return frame_to_map_core(ctx, map_xyz, map_desc, map_level, M, cur_xyz, cur_desc, cur_level, N, radius, accept_ratio,
+                             distance_mode, params, seed, num_hyp, match_cap, match_query_out, match_train_out,
+                             match_dist_out, inlier_idx_out, result, F2MRaw());
+}
+
+int pslam_frame_to_map_features(pslam_ctx* ctx, const double* map_xyz, const uint8_t* map_desc, const int* map_octave,
+                                const double* map_det_dist, int M, const float* cur_xyz, const uint8_t* cur_desc,
+                                const int* cur_octave, const double* cur_det_dist, int N, double radius, double accept_ratio,
+                                int distance_mode, const pslam_ransac_params* params, uint64_t seed, int num_hyp,
+                                int match_cap, int* match_query_out, int* match_train_out, float* match_dist_out,
+                                int* inlier_idx_out, pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (M > 0 && !map_xyz) return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map_features: null map positions");
+    F2MRaw raw;
+    raw.map_xyz_d = map_xyz; raw.map_oct = map_octave; raw.map_det = map_det_dist;
+    raw.cur_oct = cur_octave; raw.cur_det = cur_det_dist;
+    static const double dummy = 0.0;
+    if (M == 0) raw.map_xyz_d = &dummy;   // keeps the "device levels" path selected; the core returns before any use
+    return frame_to_map_core(ctx, nullptr, map_desc, nullptr, M, cur_xyz, cur_desc, nullptr, N, radius, accept_ratio,
+                             distance_mode, params, seed, num_hyp, match_cap, match_query_out, match_train_out,
+                             match_dist_out, inlier_idx_out, result, raw);
 }
 
 int pslam_frame_to_map_resident(pslam_ctx* ctx) {

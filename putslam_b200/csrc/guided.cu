@@ -208,6 +208,60 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
     if (tid == 0) { offsets[M] = carry; header[0] = carry; header[1] = perfect; }
 }
 
+// Predicted ORB pyramid levels (reference src/Matcher/matcher.cpp:639-651 for current keypoints, :682-692 for map
+// features) and the double->float cast of the map positions (:665), on the device.
+//   level = clamp(ceil(log(pow(1.2, octave) * detDist / curDist) / log(1.2)), 0, 7)       (all double)
+// pow(1.2, k) and the level for the exact case s == pow(1.2, k) come from host-libm tables, because that case --
+// detDist == curDist, common for keypoints matched in the frame they were detected in -- sits exactly on a ceil()
+// boundary and depends on the last bit of the host's log().  Everywhere else the argument is at least one float
+// ulp (6e-8) away from the boundary, eight orders of magnitude more than any log() implementation's error.
+struct LevelTables {
+    double pow_tab[16];     // pow(1.2, k) from the host libm
+    int lvl_tab[16];        // (int)ceil(log(pow(1.2, k)) / log(1.2)) from the host libm
+    double log_sf;          // log(1.2) from the host libm
+};
+__device__ __forceinline__ int predict_level(const LevelTables& T, int octave, double det_dist, double cur_dist) {
+    const double ps = (octave >= 0 && octave < 16) ? T.pow_tab[octave] : pow(1.2, (double)octave);
+    const double sfac = __ddiv_rn(ps * det_dist, cur_dist);
+    int lvl;
+    if (octave >= 0 && octave < 16 && sfac == ps) lvl = T.lvl_tab[octave];
+    else lvl = (int)ceil(__ddiv_rn(log(sfac), T.log_sf));
+    lvl = max(0, lvl);
+    return min(7, lvl);
+}
+__global__ void predict_levels_kernel(const double* __restrict__ map_xyz, const int* __restrict__ map_oct,
+                                      const double* __restrict__ map_det, int M, const float* __restrict__ cur_xyz,
+                                      const int* __restrict__ cur_oct, const double* __restrict__ cur_det, int N,
+                                      LevelTables T, float* __restrict__ map_xyz_f, int* __restrict__ map_level,
+                                      int* __restrict__ cur_level) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        const double x = map_xyz[3 * i], y = map_xyz[3 * i + 1], z = map_xyz[3 * i + 2];
+        const double cur_dist = __dsqrt_rn(x * x + y * y + z * z);
+        map_level[i] = predict_level(T, map_oct[i], map_det[i], cur_dist);
+        map_xyz_f[3 * i] = (float)x; map_xyz_f[3 * i + 1] = (float)y; map_xyz_f[3 * i + 2] = (float)z;
+    } else if (i < M + N) {
+        const int k = i - M;
+        const float x = cur_xyz[3 * k], y = cur_xyz[3 * k + 1], z = cur_xyz[3 * k + 2];
+        const double cur_dist = (double)norm3(x, y, z);     // Eigen Vector3f::norm(), widened
+        cur_level[k] = predict_level(T, cur_oct[k], cur_det[k], cur_dist);
+    }
+}
+
+cudaError_t launch_predict_levels(const double* d_map_xyz, const int* d_map_oct, const double* d_map_det, int M,
+                                  const float* d_cur_xyz, const int* d_cur_oct, const double* d_cur_det, int N,
+                                  const double* pow_tab, const int* lvl_tab, double log_sf, float* d_map_xyz_f,
+                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches) {
+    if (M + N <= 0) return cudaSuccess;
+    LevelTables T;
+    for (int k = 0; k < 16; ++k) { T.pow_tab[k] = pow_tab[k]; T.lvl_tab[k] = lvl_tab[k]; }
+    T.log_sf = log_sf;
+    predict_levels_kernel<<<(M + N + 255) / 256, 256, 0, st>>>(d_map_xyz, d_map_oct, d_map_det, M, d_cur_xyz, d_cur_oct,
+                                                               d_cur_det, N, T, d_map_xyz_f, d_map_level, d_cur_level);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 size_t guided_cache_bytes(int M) { return sizeof(uint2) * (size_t)kCacheCap * (size_t)(M > 0 ? M : 1); }
 
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,

@@ -39,6 +39,10 @@ cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsi
 
 // ---- guided.cu -------------------------------------------------------------------------------
 // d_out: int[2 + 3*cap] = {n_total, perfect, queryIdx[cap], trainIdx[cap], distance(float)[cap]}
+cudaError_t launch_predict_levels(const double* d_map_xyz, const int* d_map_oct, const double* d_map_det, int M,
+                                  const float* d_cur_xyz, const int* d_cur_oct, const double* d_cur_det, int N,
+                                  const double* pow_tab, const int* lvl_tab, double log_sf, float* d_map_xyz_f,
+                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches);
 size_t guided_cache_bytes(int M);
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,

@@ -395,3 +395,26 @@ def test_map_prepare(ctx, O):
     inside = uv[:, 0] >= 0
     assert inside.any() and (~inside).any() and (xl[inside, 2] >= 0.8).all()
     assert ctx.map_prepare(np.zeros((0, 3)), np.zeros((0, 3), np.float32), pose, prm)[0].size == 0
+
+
+def test_frame_to_map_device_levels(ctx, O):
+    """pslam_frame_to_map_features (levels predicted on the device) == pslam_frame_to_map with host-libm levels,
+    including current keypoints whose detDist equals their current distance exactly (the ceil() boundary case)."""
+    from putslam_b200 import host, synth
+    n_exact = 0
+    for seed in range(4):
+        mf = synth.map_frame(M=3000, N=800, n_reobs=500, seed=40 + seed)
+        cur_det = mf["cur_detdist"].copy()
+        x, y, z = mf["cur_xyz"][:, 0], mf["cur_xyz"][:, 1], mf["cur_xyz"][:, 2]
+        eig = np.sqrt((x * x + (y * y + z * z)).astype(np.float32)).astype(np.float64)
+        n_exact += int((cur_det == eig).sum())
+        cur_det[::5] *= 1.3                      # some keypoints described at another distance
+        ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+        cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], cur_det)
+        a = ctx.frame_to_map(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0, seed=seed)
+        b = ctx.frame_to_map_features(mf["map_xyz"], mf["map_desc"], mf["map_octave"], mf["map_detdist"], mf["cur_xyz"],
+                                      mf["cur_desc"], mf["cur_octave"], cur_det, 0.12, 0.55, 0, seed=seed)
+        for k in ("mq", "mt", "md", "inliers"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a["T"], b["T"]) and a["mq"].size > 300
+    assert n_exact > 100      # the exact-ratio case was really exercised
