@@ -275,6 +275,47 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
+double MatcherB200::matchCore(cv::Mat prevDescriptors, const std::vector<Eigen::Vector3f>& prevFeatures3D, cv::Mat descriptors,
+                              const std::vector<cv::KeyPoint>& keyPoints, cv::Mat depthImage, double depthImageScale,
+                              cv::Mat cameraMatrix, cv::Mat distCoeffs, const RANSAC::parameters& ransacParams,
+                              std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
+                              std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches,
+                              Eigen::Matrix4f& estimatedTransformation) {
+    matches.clear(); inlierMatches.clear();
+    estimatedTransformation = Eigen::Matrix4f::Identity();
+    const int nPrev = prevDescriptors.rows, nCur = descriptors.rows;
+    undistortedFeatures2D.assign((size_t)nCur, cv::Point2f());
+    features3D.assign((size_t)nCur, Eigen::Vector3f());
+    if (nCur == 0) return 0.0 / 0.0;   // pointInlierRatio of two empty sets
+    std::vector<uint8_t> tp, tc;
+    const uint8_t* pd = contiguousBytes(prevDescriptors, 32, tp);
+    const uint8_t* cd = contiguousBytes(descriptors, 32, tc);
+    std::vector<float> uv(2 * (size_t)nCur);
+    for (int i = 0; i < nCur; ++i) { uv[2 * i] = keyPoints[(size_t)i].pt.x; uv[2 * i + 1] = keyPoints[(size_t)i].pt.y; }
+    RANSAC::parameters rp = ransacParams;
+    rp.errorVersion = rp.errorVersionVO;   // matcher.cpp:491-492
+    pslam_camera cam = cameraFrom(cameraMatrix, &distCoeffs);
+    pslam_ransac_params a = toAbi(rp, cam.fx, cam.fy, cam.cx, cam.cy);
+    const int cap = std::max(1, std::min(nPrev, nCur));
+    std::vector<int> mq((size_t)cap), mt((size_t)cap), inl((size_t)cap);
+    std::vector<float> md((size_t)cap);
+    pslam_frame_result res;
+    pslam_ctx* c = dev_.ctx();
+    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
+    const int r = c ? pslam_frame_to_frame(c, pd, nPrev ? prevFeatures3D[0].data() : nullptr, nPrev, cd, uv.data(), nCur,
+                                           depthImage.ptr<uint16_t>(0), depthImage.cols, depthImage.rows, stride, &cam,
+                                           distCoeffs.empty() ? 0 : 1, depthImageScale, &a, seed_, numHyp_,
+                                           features3D[0].data(), &undistortedFeatures2D[0].x, nullptr, mq.data(), mt.data(),
+                                           md.data(), inl.data(), &res)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "match", r); return 0.0; }
+    matches.reserve((size_t)res.n_matches);
+    for (int k = 0; k < res.n_matches; ++k) matches.push_back(cv::DMatch(mq[k], mt[k], 0, md[k]));
+    for (int k = 0; k < res.n_inliers; ++k) inlierMatches.push_back(matches[(size_t)inl[k]]);
+    std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
+    return res.inlier_ratio;
+}
+
 double MatcherB200::matchFeatureLoopClosureCore(cv::Mat descriptors0, const std::vector<Eigen::Vector3f>& points3D0,
                                                 cv::Mat descriptors1, const std::vector<Eigen::Vector3f>& points3D1,
                                                 const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,

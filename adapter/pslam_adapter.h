@@ -100,6 +100,16 @@ public:
                         double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch, int computationNumber,
                         const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix, Eigen::Matrix4f& estimatedTransformation,
                         std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches, bool xorDistance = false);
+    // The numeric core of Matcher::match (src/Matcher/matcher.cpp:452-516, lines 470-496) in one device submission:
+    // performMatching(prevDescriptors, descriptors) -> removeImageDistortion + keypoints2Dto3D on the current keypoints
+    // -> RANSAC(prevFeatures3D, features3D, matches).  Returns pointInlierRatio (matcher.cpp:515).  Outputs are what
+    // match() keeps for the next frame (undistortedFeatures2D, features3D) plus matches / inliers / transform.
+    double matchCore(cv::Mat prevDescriptors, const std::vector<Eigen::Vector3f>& prevFeatures3D, cv::Mat descriptors,
+                     const std::vector<cv::KeyPoint>& keyPoints, cv::Mat depthImage, double depthImageScale,
+                     cv::Mat cameraMatrix, cv::Mat distCoeffs, const RANSAC::parameters& ransacParams,
+                     std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
+                     std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches,
+                     Eigen::Matrix4f& estimatedTransformation);
     // Matcher::matchFeatureLoopClosure (src/Matcher/matcher.cpp:802-861) after its MapFeature gathering loop (:809-827):
     // descriptors / 3-D points of the two frames -> paired feature indices, transform, and the value it returns
     // (0 for fewer than 10 features, -1.0 for no matches, else pointInlierRatio).

@@ -75,6 +75,19 @@ int main(int argc, char** argv) {
     std::vector<double> ratio{RANSAC::pointInlierRatio(inliers, matches), (double)ransac.hypothesesUsed(), ransac.bestInlierRatio()};
     wr("vo_ratio.bin", ratio);
 
+    // ---- the same VO step fused into one submission (MatcherB200::matchCore) ----
+    {
+        std::vector<cv::Point2f> undF; std::vector<Eigen::Vector3f> x2F; std::vector<cv::DMatch> mF, inF; Eigen::Matrix4f TF;
+        matcher.setSeed(4242);
+        const double rF = matcher.matchCore(descMat(d1), p1, descMat(d2), kp2, depth2, 5000.0, K, D, rp, undF, x2F, mF, inF, TF);
+        wrMatches("vof_matches", mF); wrMatches("vof_inliers", inF);
+        wr("vof_T.bin", std::vector<float>(TF.data(), TF.data() + 16));
+        std::vector<float> xf;
+        for (auto& p : x2F) { xf.push_back(p[0]); xf.push_back(p[1]); xf.push_back(p[2]); }
+        wr("vof_xyz2.bin", xf);
+        wr("vof_ratio.bin", std::vector<double>{rF});
+    }
+
     // ---- Matcher::matchXYZ path (matcher.cpp:606-797) ----
     MatcherB200::MapSide map;
     map.xyz = rd<double>("map_xyz.bin");

@@ -299,8 +299,10 @@ def native_frontend_numbers(frames, warmup):
             r = json.loads(out.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001
             return {"unavailable": str(e)}
-    r["note"] = ("C++ adapter, host buffers: frame_to_map = MatcherB200::matchXYZCore incl. host-side level prediction and "
-                 "double->float marshalling; vo_three_calls = performMatching + keypoints2Dto3D + RANSAC as three separate calls")
+    r["note"] = ("C++ adapter, host buffers in, results out, per frame: frame_to_map = MatcherB200::matchXYZCore (guided "
+                 "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); vo_three_calls = performMatching "
+                 "+ keypoints2Dto3D + RANSAC as three separate calls; vo_fused = MatcherB200::matchCore (one submission, "
+                 "adaptive RANSAC), 1000 keypoints, 640x480 depth image uploaded every frame")
     return r
 
 

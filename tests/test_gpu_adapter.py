@@ -58,6 +58,13 @@ def test_adapter_end_to_end(tmp_path, O):
     ratio, used, best = _rd(d, "vo_ratio.bin", np.float64)
     assert ratio == O.point_inlier_ratio(ot[ref["inliers"]], ot, 500) and int(used) == ref["hyp_used"] and best == ref["best_ratio"]
 
+    # ---- fused VO step (MatcherB200::matchCore) gives the same answer as the three separate calls ----
+    assert np.array_equal(_rd(d, "vof_matches_q.bin", np.int32), oq) and np.array_equal(_rd(d, "vof_matches_t.bin", np.int32), ot)
+    assert np.array_equal(_rd(d, "vof_inliers_q.bin", np.int32), oq[ref["inliers"]])
+    assert np.array_equal(bits(_rd(d, "vof_xyz2.bin", np.float32)), bits(x2.ravel()))
+    assert np.abs(_rd(d, "vof_T.bin", np.float32).reshape(4, 4).T - ref["T"]).max() <= 1e-5
+    assert _rd(d, "vof_ratio.bin", np.float64)[0] == ratio
+
     # ---- matchXYZ path, first call and first retry (wider gates) ----
     ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
     cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
