@@ -467,6 +467,14 @@ def run_ours(args):
         if world == 1 and not args.no_frontend:
             fe = frontend_numbers(ctx, max(10, args.steps), args.warmup)
             fe["native_cpp"] = native_frontend_numbers(max(20, args.steps), args.warmup)
+            try:   # configs[1]: the tracking loop over a synthetic sequence (first 200 frames here; bench/sequence.py runs all 1000)
+                sys.path.insert(0, os.path.join(ROOT, "bench"))
+                import sequence
+                ctx.close()
+                fe["c2_sequence"] = sequence.run(frames=200, check=0 if args.no_cpu_baseline else 5)
+                ctx = api.Context(local_rank)
+            except Exception as e:  # noqa: BLE001
+                fe["c2_sequence"] = {"unavailable": str(e)}
             if not args.no_cpu_baseline:
                 fe["cpu_baseline_c3"] = cpu_frontend_baseline()
             line["frontend"] = fe
