@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "geometry.cuh"
@@ -47,6 +48,8 @@ typedef int (*fn_ncclCommDestroy)(void*);
 typedef int (*fn_ncclAllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_ncclBroadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*fn_ncclGetErrorString)(int);
+struct NcclApi;
+void nccl_load(NcclApi* out);
 struct NcclApi {
     void* handle = nullptr;
     fn_ncclGetUniqueId GetUniqueId = nullptr;
@@ -59,15 +62,18 @@ struct NcclApi {
 };
 NcclApi* nccl_api() {
     static NcclApi api;
-    static bool tried = false;
-    if (tried) return &api;
-    tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] { nccl_load(&api); });
+    return &api;
+}
+void nccl_load(NcclApi* out) {
+    NcclApi& api = *out;
     const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
     for (const char* n : names) {
         api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (api.handle) break;
     }
-    if (!api.handle) return &api;
+    if (!api.handle) return;
     api.GetUniqueId = (fn_ncclGetUniqueId)dlsym(api.handle, "ncclGetUniqueId");
     api.CommInitRank = (fn_ncclCommInitRank)dlsym(api.handle, "ncclCommInitRank");
     api.CommDestroy = (fn_ncclCommDestroy)dlsym(api.handle, "ncclCommDestroy");
@@ -75,7 +81,6 @@ NcclApi* nccl_api() {
     api.Broadcast = (fn_ncclBroadcast)dlsym(api.handle, "ncclBroadcast");
     api.GetErrorString = (fn_ncclGetErrorString)dlsym(api.handle, "ncclGetErrorString");
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast;
-    return &api;
 }
 constexpr int kNcclUint8 = 1, kNcclInt32 = 2;
 // below this many keyframes per GPU the sweep uses 128-row tiles as work units (see hamming.cu, split form)

@@ -490,11 +490,10 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     // shared-memory staging of the winner's inliers for the refit: up to 8192 inliers (192 KB)
     int stage_cap = ws.m_cap < 8192 ? ws.m_cap : 8192;
     const size_t sel_smem = sizeof(float) * 6 * (size_t)stage_cap;
-    static bool sel_cfg = false;
-    if (!sel_cfg) {
+    // per-device function attribute; setting it again is harmless, so no cross-thread state is kept
+    {
         cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4);
         if (e != cudaSuccess) return e;
-        sel_cfg = true;
     }
     ransac_select_kernel<<<1, kSelThreads, sel_smem, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf,
                                                            P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,

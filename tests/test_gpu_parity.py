@@ -418,3 +418,44 @@ def test_frame_to_map_device_levels(ctx, O):
             assert np.array_equal(a[k], b[k]), k
         assert np.array_equal(a["T"], b["T"]) and a["mq"].size > 300
     assert n_exact > 100      # the exact-ratio case was really exercised
+
+
+def test_two_contexts_run_concurrently(O):
+    """SURVEY 8b threading: the tracking Matcher and the loop-closure Matcher are separate instances driven from two
+    threads; here two pslam_ctx (own stream, own arenas) work concurrently and both stay bit-exact."""
+    import threading
+    from putslam_b200 import api, host, synth
+    mf = synth.map_frame(M=3000, N=800, n_reobs=500, seed=5)
+    ml = host.map_levels(mf["map_xyz"], mf["map_octave"], mf["map_detdist"])
+    cl = host.current_levels(mf["cur_xyz"], mf["cur_octave"], mf["cur_detdist"])
+    q, t, d, _ = O.guided_match(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0)
+    ref_a = O.ransac(mf["map_xyz"].astype(np.float32), mf["cur_xyz"], q, t, seed=3)
+    db = synth.keyframe_db(n_kf=150, per_kf=500, n_query=600, n_planted=6, shared=200, seed=9)
+    ref_b = O.topk(O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=4), 8)
+    errors = []
+
+    def tracking():
+        try:
+            c = api.Context(0)
+            for _ in range(30):
+                r = c.frame_to_map(mf["map_xyz"], mf["map_desc"], ml, mf["cur_xyz"], mf["cur_desc"], cl, 0.12, 0.55, 0, seed=3)
+                assert np.array_equal(r["mq"], q) and np.array_equal(r["inliers"], ref_a["inliers"])
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(("tracking", repr(e)))
+
+    def loop_closure():
+        try:
+            c = api.Context(0)
+            c.lc_append(db["db"], db["kf_off"])
+            for _ in range(30):
+                ids, sc = c.lc_query(db["query"], tau=64, k=8)
+                assert np.array_equal(ids, ref_b[0]) and np.array_equal(sc, ref_b[1])
+            c.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(("loop_closure", repr(e)))
+
+    th = [threading.Thread(target=tracking), threading.Thread(target=loop_closure)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errors, errors

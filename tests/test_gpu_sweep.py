@@ -67,6 +67,16 @@ def test_lc_full_size_planted_recall(ctx):
     ctx.lc_query_resident(tau=64, k=20); ctx.sync()
     ids2, sc2 = ctx.lc_query(db["query"], tau=64, k=20)
     assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2)
+    # V2 at the same size (1e7 descriptors): the returned distances are the true Hamming distances of the returned
+    # indices, sorted, and every strong match lies inside a planted keyframe
+    idx, dist = ctx.lc_knn2(db["query"])
+    assert (idx >= 0).all() and (dist[:, 0] <= dist[:, 1]).all()
+    for col in (0, 1):
+        true = np.unpackbits(db["db"][idx[:, col]] ^ db["query"], axis=1).sum(1)
+        assert np.array_equal(true.astype(np.float32), dist[:, col])
+    strong = dist[:, 0] <= 40
+    assert strong.sum() >= 300 and np.isin(idx[strong, 0] // 1000, db["planted"]).all()
+    assert dist[~strong, 0].min() > 60      # random 256-bit descriptors: nothing closer by chance in 1e7
     _fresh(ctx)
 
 
