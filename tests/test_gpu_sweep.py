@@ -76,7 +76,9 @@ def test_lc_full_size_planted_recall(ctx):
         assert np.array_equal(true.astype(np.float32), dist[:, col])
     strong = dist[:, 0] <= 40
     assert strong.sum() >= 300 and np.isin(idx[strong, 0] // 1000, db["planted"]).all()
-    assert dist[~strong, 0].min() > 60      # random 256-bit descriptors: nothing closer by chance in 1e7
+    assert dist[:, 1].max() <= 100          # second neighbours are planted copies or the best of 1e7 random rows
+    if (~strong).any():
+        assert dist[~strong, 0].min() > 60  # random 256-bit descriptors: nothing closer by chance in 1e7
     _fresh(ctx)
 
 
