@@ -48,7 +48,8 @@ typedef enum {
 #define PSLAM_DESC_BYTES 32
 #define PSLAM_MAX_BF_ROWS 65535      /* pslam_match_bf_mutual / knn2: nq, nt <= 65535 (16-bit packed index) */
 #define PSLAM_LC_MAX_KF_DESC 4096    /* descriptors per keyframe in the loop-closure database */
-#define PSLAM_LC_MAX_QUERY 1024      /* query descriptors per loop-closure sweep */
+#define PSLAM_LC_MAX_QUERY 2048      /* query descriptors per loop-closure sweep; above 1024 the V1 sweep needs every
+                                        keyframe to hold at most 2048 descriptors */
 #define PSLAM_LC_MAX_TOPK 64
 
 /* ---- context ------------------------------------------------------------------------------ */

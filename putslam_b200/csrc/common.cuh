@@ -93,8 +93,12 @@ __device__ __forceinline__ uint32_t ham256_key(const uint32_t (&q)[8], const uin
     return r;
 }
 __device__ __forceinline__ uint32_t key_dist(uint32_t k) { return k >> kKeyDShift; }
-__device__ __forceinline__ uint32_t key_tidx(uint32_t k) { return (k >> kKeyQBits) & ((1u << kKeyTBits) - 1u); }
-__device__ __forceinline__ uint32_t key_qoff(uint32_t k) { return k & ((1u << kKeyQBits) - 1u); }
+// QB = bits of the query field; the train field takes the remaining kKeyDShift - QB bits (10/12 by default,
+// 11/11 for query sets of up to 2048 descriptors)
+template <int QB = kKeyQBits>
+__device__ __forceinline__ uint32_t key_tidx(uint32_t k) { return (k >> QB) & ((1u << (kKeyDShift - QB)) - 1u); }
+template <int QB = kKeyQBits>
+__device__ __forceinline__ uint32_t key_qoff(uint32_t k) { return k & ((1u << QB) - 1u); }
 
 __device__ __forceinline__ uint32_t ham256(const uint32_t (&q)[8], const uint4& ta, const uint4& tb) {
     return ham256_key(q, ta, tb, 0u) >> kKeyDShift;

@@ -128,6 +128,7 @@ struct pslam_ctx {
     DevBuf d_tile_start, d_split;
     int n_tiles = 0;
     bool tiles_dirty = true;
+    int max_kf_desc = 0;        // largest keyframe appended so far
     int lc_work_unit = 0;       // 0 auto, 1 keyframes, 2 tiles
     int kf_cap = 0, n_kf = 0, kf_id_base = 0;
     long long desc_id_base = 0;
@@ -1074,6 +1075,7 @@ int pslam_lc_db_append(pslam_ctx* ctx, const uint8_t* desc, const int64_t* kf_of
         const int64_t c = kf_off[k + 1] - kf_off[k];
         if (c < 0) return fail(ctx, PSLAM_ERR_ARG, "keyframe offsets must be non-decreasing");
         if (c > PSLAM_LC_MAX_KF_DESC) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "keyframe with %lld descriptors (max %d)", (long long)c, PSLAM_LC_MAX_KF_DESC);
+        if ((int)c > ctx->max_kf_desc) ctx->max_kf_desc = (int)c;
     }
     CK(cudaSetDevice(ctx->device));
     if (ctx->h_kf_off.empty()) ctx->h_kf_off.push_back(0);
@@ -1110,6 +1112,7 @@ int pslam_lc_db_clear(pslam_ctx* ctx) {
     ctx->n_kf = 0;
     ctx->h_kf_off.assign(1, 0);
     ctx->tiles_dirty = true;
+    ctx->max_kf_desc = 0;
     return PSLAM_OK;
 }
 
@@ -1157,6 +1160,9 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
 
 static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
     int l = 0;
+    if (ctx->lc_nq > 1024 && ctx->max_kf_desc > lc_max_kf_desc_wide())
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "more than 1024 query descriptors need keyframes of at most %d descriptors (largest: %d)",
+                    lc_max_kf_desc_wide(), ctx->max_kf_desc);
     // work-unit choice: whole keyframes when every CTA gets many of them, 128-row tiles otherwise
     const bool split = ctx->n_kf > 0 && (ctx->lc_work_unit == 2 || (ctx->lc_work_unit == 0 && ctx->n_kf < kSplitMaxKeyframes));
     if (split && ctx->tiles_dirty) {

@@ -45,7 +45,7 @@ struct QueryRegs {
 // One sub-tile: cnt (<= kTT) train descriptors in shared memory vs this thread's RQ queries, two train
 // descriptors per iteration so that the row update is a single 3-input min.
 //   rowmin[j] : running key for query j (min over train)   partial_w[tt] : this warp's min over its queries
-template <int RQ, int NT>
+template <int RQ, int NT, int QB = kKeyQBits>
 __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_t (&rowmin)[RQ],
                                              const uint4* __restrict__ tile, int cnt, uint32_t tbase,
                                              uint32_t* __restrict__ partial_w, int lane) {
@@ -53,7 +53,7 @@ __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_
 #pragma unroll 1
     for (; tt + 2 <= cnt; tt += 2) {
         const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1], a1 = tile[2 * tt + 2], b1 = tile[2 * tt + 3];
-        const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits, t1 = t0 + (1u << kKeyQBits);
+        const uint32_t t0 = (tbase + (uint32_t)tt) << QB, t1 = t0 + (1u << QB);
         uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_
     }
     if (tt < cnt) {
         const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1];
-        const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits;
+        const uint32_t t0 = (tbase + (uint32_t)tt) << QB;
         uint32_t c0 = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ void cursor_next(SweepCursor& c, const int64_t* __res
     }
 }
 
-template <int RQ, int NT>
+template <int RQ, int NT, int QB = kKeyQBits>
 __global__ void __launch_bounds__(NT, 512 / NT)
 lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db,
                 const int64_t* __restrict__ kf_off, int n_kf, int tau, int* __restrict__ scores) {
@@ -343,7 +343,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
         const int cnt = min(kTT, cons.cnt - tbase);
         uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
         mbar_wait(bars + stage, phase);
-        tile_compute<RQ, NT>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        tile_compute<RQ, NT, QB>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
         __syncthreads();
         if (tid < cnt) {
             uint32_t m = pbuf[tid];
@@ -359,7 +359,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
             for (int j = 0; j < RQ; ++j) {
                 const uint32_t rk = rowmin[j];
                 // the winner of the column this row points at must be this very (dist, t, q) key
-                if (Q.off[j] < kKeyInvalid && colmin[key_tidx(rk)] == rk && (int)key_dist(rk) <= tau) ++c;
+                if (Q.off[j] < kKeyInvalid && colmin[key_tidx<QB>(rk)] == rk && (int)key_dist(rk) <= tau) ++c;
                 rowmin[j] = 0xffffffffu;
             }
             c = (int)warp_add_u32((uint32_t)c);
@@ -397,7 +397,7 @@ __device__ __forceinline__ void split_item(int item, const int* __restrict__ til
     cnt = min(kTT, kcnt - tile * kTT);
 }
 
-template <int RQ, int NT>
+template <int RQ, int NT, int QB = kKeyQBits>
 __global__ void __launch_bounds__(NT, 512 / NT)
 lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict__ db,
                       const int64_t* __restrict__ kf_off, const int* __restrict__ tile_start, int n_kf, int n_tiles,
@@ -438,7 +438,7 @@ lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __re
         for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
         uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
         mbar_wait(bars + stage, phase);
-        tile_compute<RQ, NT>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        tile_compute<RQ, NT, QB>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
 #pragma unroll
         for (int j = 0; j < RQ; ++j) rowpart[(size_t)item * (RQ * NT) + j * NT + tid] = rowmin[j];
         __syncthreads();
@@ -453,7 +453,7 @@ lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __re
 
 // One CTA per keyframe: merge the row partials of its tiles, cross-check against the column keys, count.
 __global__ void __launch_bounds__(256)
-lc_sweep_finalize_kernel(const int* __restrict__ tile_start, const int64_t* __restrict__ kf_off, int nq, int row_stride,
+lc_sweep_finalize_kernel(const int* __restrict__ tile_start, const int64_t* __restrict__ kf_off, int nq, int row_stride, int qb,
                          const uint32_t* __restrict__ rowpart, const uint32_t* __restrict__ colmin_g, int tau,
                          int* __restrict__ scores) {
     __shared__ int s_cnt;
@@ -466,7 +466,8 @@ lc_sweep_finalize_kernel(const int* __restrict__ tile_start, const int64_t* __re
         for (int q = tid; q < nq; q += 256) {
             uint32_t rk = 0xffffffffu;
             for (int t = t0; t < t1; ++t) rk = min(rk, rowpart[(size_t)t * row_stride + q]);
-            if (rk != 0xffffffffu && colmin_g[(size_t)kf * kMaxKfDesc + key_tidx(rk)] == rk && (int)key_dist(rk) <= tau) ++c;
+            const uint32_t t = (rk >> qb) & ((1u << (kKeyDShift - qb)) - 1u);
+            if (rk != 0xffffffffu && colmin_g[(size_t)kf * kMaxKfDesc + t] == rk && (int)key_dist(rk) <= tau) ++c;
         }
     }
     c = (int)warp_add_u32((uint32_t)c);
@@ -624,7 +625,7 @@ __global__ void lc_knn2_merge_kernel(const ulonglong2* __restrict__ partial, int
 // exactly: everything above s* is taken, ties at s* are taken in id order (ordered compaction), and the
 // <= 64 selected keys are placed by rank counting.  A handful of block barriers instead of k passes.
 // out_pairs: k x {score, global keyframe id}; unused slots {-1, -1}.
-constexpr int kTopkMaxScore = 1024;
+constexpr int kTopkMaxScore = 2048;
 __global__ void __launch_bounds__(1024, 1)
 lc_topk_kernel(const int* __restrict__ scores, int n_kf, int kf_id_base, int k, int* __restrict__ out_pairs) {
     __shared__ int hist[kTopkMaxScore + 2];
@@ -802,7 +803,8 @@ static size_t lc_sweep_smem_nt() {
     return (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * (NT / 32) * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
 }
 int lc_max_kf_desc() { return kMaxKfDesc; }
-int lc_max_query() { return 1024; }
+int lc_max_query() { return 2048; }
+int lc_max_kf_desc_wide() { return 1 << (kKeyDShift - 11); }   // 2048 descriptors per keyframe when nq > 1024
 
 cudaError_t lc_sweep_configure() {
     cudaError_t e;
@@ -811,6 +813,8 @@ cudaError_t lc_sweep_configure() {
                                   (int)lc_sweep_smem_nt<NT>())) != cudaSuccess) return e;
     CFG(1, 256) CFG(2, 256) CFG(4, 256)
 #undef CFG
+    if ((e = cudaFuncSetAttribute(lc_sweep_kernel<4, 512, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)lc_sweep_smem_nt<512>())) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -820,6 +824,12 @@ cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db,
     const int rq = pick_rq(nq);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
+    if (nq > 1024) {   // up to 2048 queries: 512 threads x 4 queries, one CTA per SM, 11/11-bit index fields
+        int grid1 = sm_count < n_kf ? sm_count : n_kf;
+        lc_sweep_kernel<4, 512, 11><<<grid1, 512, lc_sweep_smem_nt<512>(), st>>>(q4, nq, db4, d_kf_off, n_kf, tau, d_scores);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     int grid = 2 * sm_count;
     if (grid > n_kf) grid = n_kf;
     const size_t smem = lc_sweep_smem_nt<256>();
@@ -830,7 +840,7 @@ cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db,
     return cudaGetLastError();
 }
 
-size_t lc_split_rowpart_bytes(int n_tiles) { return sizeof(uint32_t) * 1024 * (size_t)(n_tiles > 0 ? n_tiles : 1); }
+size_t lc_split_rowpart_bytes(int n_tiles) { return sizeof(uint32_t) * 2048 * (size_t)(n_tiles > 0 ? n_tiles : 1); }
 size_t lc_split_colmin_bytes(int n_kf) { return sizeof(uint32_t) * (size_t)kMaxKfDesc * (size_t)(n_kf > 0 ? n_kf : 1); }
 
 cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off,
@@ -840,6 +850,17 @@ cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t*
     const int rq = pick_rq(nq);
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
+    if (nq > 1024) {
+        int grid1 = sm_count < n_tiles ? sm_count : n_tiles;
+        if (n_tiles > 0) {
+            const size_t smem1 = (size_t)kStages * kTT * 32 + sizeof(uint32_t) * 2 * (512 / 32) * kTT + sizeof(uint64_t) * kStages + 16;
+            lc_sweep_split_kernel<4, 512, 11><<<grid1, 512, smem1, st>>>(q4, nq, db4, d_kf_off, d_tile_start, n_kf, n_tiles, d_rowpart, d_colmin);
+            if (launches) *launches += 1;
+        }
+        lc_sweep_finalize_kernel<<<n_kf, 256, 0, st>>>(d_tile_start, d_kf_off, nq, 2048, 11, d_rowpart, d_colmin, tau, d_scores);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     int grid = 2 * sm_count;
     if (grid > n_tiles) grid = n_tiles;
     if (n_tiles > 0) {
@@ -849,7 +870,7 @@ cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t*
         else lc_sweep_split_kernel<4, 256><<<grid, 256, smem, st>>>(q4, nq, db4, d_kf_off, d_tile_start, n_kf, n_tiles, d_rowpart, d_colmin);
         if (launches) *launches += 1;
     }
-    lc_sweep_finalize_kernel<<<n_kf, 256, 0, st>>>(d_tile_start, d_kf_off, nq, rq * 256, d_rowpart, d_colmin, tau, d_scores);
+    lc_sweep_finalize_kernel<<<n_kf, 256, 0, st>>>(d_tile_start, d_kf_off, nq, rq * 256, kKeyQBits, d_rowpart, d_colmin, tau, d_scores);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -892,6 +913,11 @@ cudaError_t launch_lc_knn2(const uint8_t* d_query, int nq, const uint8_t* d_db, 
     const uint4* db4 = reinterpret_cast<const uint4*>(d_db);
     const size_t smem = (size_t)kStages * kTT * 32 + sizeof(uint64_t) * kStages + 16;
     ulonglong2* part = reinterpret_cast<ulonglong2*>(d_partial);
+    if (nq > 1024) {
+        lc_knn2_kernel<4, 512><<<grid, 512, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     const int rq = pick_rq(nq);
     if (rq == 1) lc_knn2_kernel<1, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);
     else if (rq == 2) lc_knn2_kernel<2, 256><<<grid, 256, smem, st>>>(q4, nq, db4, n_desc, desc_id_base, chunk, part);

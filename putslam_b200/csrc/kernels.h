@@ -17,6 +17,7 @@ cudaError_t launch_knn2(const uint8_t* d_query, int nq, const uint8_t* d_train, 
 cudaError_t lc_sweep_configure();
 int lc_max_kf_desc();
 int lc_max_query();
+int lc_max_kf_desc_wide();
 cudaError_t launch_lc_sweep(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off, int n_kf,
                             int tau, int* d_scores, int sm_count, cudaStream_t st, int* launches);
 // split form (tile-granular work units) for small maps; tile_start[n_kf + 1] = prefix count of 128-row tiles

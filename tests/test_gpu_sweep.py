@@ -103,3 +103,30 @@ def test_lc_knn2_whole_db_vs_oracle(ctx, O, n_desc, nq):
     assert np.array_equal(idx2[oi >= 0], oi[oi >= 0].astype(np.int64) + 10 ** 10) and (idx2[oi < 0] == -1).all()
     ctx.lc_set_desc_base(0)
     _fresh(ctx)
+
+
+@pytest.mark.parametrize("nq", [1025, 1500, 2048])
+def test_lc_wide_query_sets(ctx, O, nq):
+    """More than 1024 query descriptors: 512-thread kernels with the 11/11-bit index split (keyframes <= 2048 rows)."""
+    from putslam_b200 import api, synth
+    db = synth.keyframe_db(n_kf=40, per_kf=1200, n_query=nq, n_planted=4, shared=500, seed=nq, ragged=True)
+    _fresh(ctx)
+    ctx.lc_append(db["db"], db["kf_off"])
+    ref = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=8)
+    for unit in (1, 2):
+        ctx.lc_set_work_unit(unit)
+        ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=8, want_scores=True)
+        assert np.array_equal(scores, ref), unit
+        assert np.array_equal(ids, O.topk(ref, 8)[0])
+    ctx.lc_set_work_unit(0)
+    idx, dist = ctx.lc_knn2(db["query"])
+    oi, od = O.knn2(db["query"], db["db"])
+    assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32))
+    # a keyframe above 2048 rows cannot be swept with a wide query set: loud error, not a wrong answer
+    big = np.random.default_rng(0).integers(0, 256, (3000, 32), dtype=np.uint8)
+    ctx.lc_append(big, np.array([0, 3000], np.int64))
+    with pytest.raises(api.PslamError) as ei:
+        ctx.lc_query(db["query"], tau=64, k=8)
+    assert ei.value.code == api.ERR_UNSUPPORTED
+    ids, sc = ctx.lc_query(db["query"][:1000], tau=64, k=8)      # still fine with <= 1024 queries
+    _fresh(ctx)
