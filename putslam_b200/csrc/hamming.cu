@@ -637,7 +637,14 @@ lc_topk_kernel(const int* __restrict__ scores, int n_kf, int kf_id_base, int k, 
     if (tid < 64) sel[tid] = 0ull;
     if (tid == 0) { s_nsel = 0; s_carry = 0; }
     __syncthreads();
-    for (int i = tid; i < n_kf; i += 1024) atomicAdd(hist + min(max(scores[i], 0), kTopkMaxScore + 1), 1);
+    // scores are heavily repeated (most keyframes score ~0): aggregate equal scores inside the warp first so that
+    // the shared-memory atomics do not serialise on a handful of bins
+    for (int base = 0; base < n_kf; base += 1024) {
+        const int i = base + tid;
+        const int sc = i < n_kf ? min(max(scores[i], 0), kTopkMaxScore + 1) : -1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, sc);
+        if (sc >= 0 && lane == __ffs(peers) - 1) atomicAdd(hist + sc, __popc(peers));
+    }
     __syncthreads();
     if (warp == 0) {  // cut = largest s with count(score >= s) >= k (or 0); above = count(score > cut)
         int acc = 0, cut = 0, above = 0;
