@@ -9,27 +9,6 @@
 
 constexpr int ITERS = 4096;
 
-template <int OP>
-__global__ void __launch_bounds__(1024) pipe_kernel(uint32_t* out, uint32_t seed, long long* clk) {
-    uint32_t a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
-    long long t0 = clock64();
-#pragma unroll 1
-    for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (OP == 0) a[i] = __popc(a[i]) + 0x55555u * 0 + a[i] * 0;            // placeholder, replaced below
-        }
-    }
-    long long t1 = clock64();
-    uint32_t s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s ^= a[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
-}
-
 // explicit variants (8 independent chains per thread)
 __global__ void __launch_bounds__(1024) popc_kernel(uint32_t* out, uint32_t seed, long long* clk) {
     uint32_t a[8];
