@@ -422,7 +422,9 @@ def run_ours(args):
         alg_peak = (popc_peak / 8.0) if popc_peak else 148 * 16 * 1.965 / 8.0
         hbm_side = hbm_peak * NQ / 32.0               # Gcmp/s the HBM stream could feed (32 B per DB descriptor)
         roofline = {
-            "bound": "int-pipe (POPC/LOP3), not hbm/tensor: 1000 comparisons per 32-byte descriptor read",
+            "bound": "int-pipe",
+            "bound_note": "integer pipes (LOP3 on the ALU pipe, POPC on the XU pipe), not hbm and not tensor: every 32-byte "
+                          "descriptor read from HBM feeds 1000 comparisons, so the HBM side of the roofline is ~350x higher",
             "kernel": "lc_sweep_kernel<4>",
             "achieved": ach_gcmps, "peak": min(alg_peak, hbm_side), "unit": "Gcmp/s",
             "frac": ach_gcmps / min(alg_peak, hbm_side),

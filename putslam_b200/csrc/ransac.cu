@@ -268,12 +268,18 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     if (tid == 0) { best_key = 0ull; s_win = -1; s_used = H; s_cnt = 0; carry = 0; }
     __syncthreads();
     if (adaptive) {
+        // the replay is sequential by definition; stage the counts in shared memory first so that thread 0 does not
+        // pay a global-memory latency per step (the adaptive bound is at most 487, USAC replay uses the budget H)
+        __shared__ int s_counts[1024];
+        const int n_stage_c = H < 1024 ? H : 1024;
+        for (int i = tid; i < n_stage_c; i += kSelThreads) s_counts[i] = counts[i];
+        __syncthreads();
         if (tid == 0) {
             int bound = H, win = -1, bc = 0;
             double best = 0.0;
             int i = 0;
             for (; i < bound; ++i) {
-                const int c = counts[i];
+                const int c = i < n_stage_c ? s_counts[i] : counts[i];
                 if (c < 0) continue;
                 const float ratio = __fdiv_rn((float)c, (float)mf);
                 if ((double)ratio > best) {
