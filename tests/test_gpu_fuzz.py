@@ -77,3 +77,27 @@ def test_fuzz_ransac(ctx, O):
         assert r["hyp_used"] == o["hyp_used"] and r["best_ratio"] == o["best_ratio"], (k, m, ev, num_hyp)
         assert np.array_equal(r["inliers"], o["inliers"]), (k, m, ev, num_hyp)
         assert np.allclose(r["T"], o["T"], atol=1e-5, rtol=0, equal_nan=True)
+
+
+def test_ransac_degenerate_geometry(ctx, O):
+    """Collinear / coplanar / coincident samples make the 3-point cross-covariance rank 1 or 0 (SURVEY 8c degenerate
+    cases): the per-hypothesis counts must still be bit-identical to the oracle."""
+    rng = np.random.default_rng(5)
+    m = 300
+    t = rng.uniform(0.5, 3.0, m)
+    line = np.stack([0.1 * t, 0.2 * t - 0.3, 0.8 + t], 1)                       # all points on one line
+    plane = np.stack([rng.uniform(-1, 1, m), rng.uniform(-1, 1, m), np.full(m, 2.0)], 1)
+    same = np.tile([[0.3, -0.2, 1.5]], (m, 1))                                   # all points coincide
+    grid = np.round(rng.uniform(0.5, 3, (m, 3)) * 4) / 4                         # many exactly repeated coordinates
+    for name, pts in (("line", line), ("plane", plane), ("same", same), ("grid", grid)):
+        prev = pts.astype(np.float32)
+        cur = (pts + np.array([0.01, -0.02, 0.03])).astype(np.float32)
+        if name == "plane":
+            cur[::3] += rng.normal(0, 0.2, (len(cur[::3]), 3)).astype(np.float32)
+        mq = np.arange(m, dtype=np.int32); mt = rng.permutation(m).astype(np.int32)
+        cur_p = np.empty_like(cur); cur_p[mt] = cur
+        r = ctx.ransac_estimate(prev, cur_p, mq, mt, seed=17, num_hyp=512, want_counts=True)
+        o = O.ransac(prev, cur_p, mq, mt, seed=17, num_hyp=512, want_counts=True)
+        assert np.array_equal(r["counts"][:512], o["counts"][:512]), name
+        assert np.array_equal(r["inliers"], o["inliers"]) and r["best_ratio"] == o["best_ratio"], name
+        assert np.allclose(r["T"], o["T"], atol=1e-5, rtol=0, equal_nan=True), name
