@@ -198,8 +198,24 @@ ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restr
         float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
         if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
         int c = 0;
-        for (int k = lane; k < mf; k += 32)
-            c += inlier_test(S, M.R, M.t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], false) ? 1 : 0;
+        // kU matches per lane per trip: the loads are issued before the first use, so the L1/L2 latency is paid once
+        // per trip instead of once per match (ncu: 78 % long-scoreboard stalls with one match per trip).  kU = 2 keeps
+        // the kernel at <= 72 registers, i.e. all 4096 hypothesis warps of the C3 configuration resident in one wave.
+        constexpr int kU = 2;
+        for (int k0 = lane; k0 < mf; k0 += 32 * kU) {
+            float a[kU][6];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int k = k0 + 32 * u;
+                const int kk = k < mf ? k : k0;   // clamp: a valid address, result discarded below
+                a[u][0] = px[kk]; a[u][1] = py[kk]; a[u][2] = pz[kk]; a[u][3] = cx[kk]; a[u][4] = cy[kk]; a[u][5] = cz[kk];
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const bool in = inlier_test(S, M.R, M.t, Ri, ti, a[u][0], a[u][1], a[u][2], a[u][3], a[u][4], a[u][5], false);
+                c += (in && (k0 + 32 * u < mf)) ? 1 : 0;
+            }
+        }
         c = (int)warp_add_u32((uint32_t)c);
         if (lane == 0) counts[h] = c;
     }
