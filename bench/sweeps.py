@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-ransac", action="store_true", help="hypothesis sweep only")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -84,6 +85,8 @@ def main():
         dist.barrier()
 
     # ---------------- database size sweep ----------------
+    if a.only_ransac:
+        a.max_db = 0
     rng = np.random.default_rng(1000 + rank)
     q = np.random.default_rng(5).integers(0, 256, (1000, 32), dtype=np.uint8)
     for n_db in [1e5, 1e6, 1e7, 1e8]:

@@ -96,12 +96,26 @@ PSLAM_API int pslam_information_matrices(pslam_ctx* ctx, const double* uvz, int 
 
 /* Uncertainty model 1: RGBD::computeNormals (include/putslam/RGBD/RGBD.h:91-95, src/RGBD/RGBD.cpp:101-144) followed
  * by DepthSensorModel::uncertinatyFromNormal (src/Grabber/depthSensorModel.cpp:62-76).  px = n x {u, v} integer
- * pixels; normals_out (nullable) n x 3, cov_out (nullable) n x 9 row-major, both double.  A pixel with fewer than
- * two neighbours that have depth yields NaN, as in the reference.  (Model 2, RGB gradients, is not provided: the
- * reference reads the 8-bit BGR patch as uint16, src/RGBD/RGBD.cpp:156-159.) */
+ * pixels; normals_out n x 3, cov_out n x 9 row-major, info_out n x 9 = cov.inverse() (what FeaturesMap attaches to
+ * the measurement, src/Map/featuresMap.cpp:115-117, 268-270); all double, all nullable.  A pixel with fewer than
+ * two neighbours that have depth yields NaN, as in the reference. */
 PSLAM_API int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_t* depth, int W, int H,
                                        int row_stride, const pslam_camera* cam, double depth_scale,
-                                       double scale_uncertainty_normal, double* normals_out, double* cov_out);
+                                       double scale_uncertainty_normal, double* normals_out, double* cov_out,
+                                       double* info_out);
+
+/* Uncertainty model 2: RGBD::computeRGBGradients (include/putslam/RGBD/RGBD.h:98-106, src/RGBD/RGBD.cpp:147-187)
+ * followed by DepthSensorModel::uncertinatyFromRGBGradient (src/Grabber/depthSensorModel.cpp:79-95).  rgb = H rows of
+ * rgb_row_bytes bytes, 3 bytes per pixel (CV_8UC3).  The reference reads the 3x3 colour patch through
+ * at<uint16_t>, i.e. as little-endian 16-bit words at byte offsets 3(u-1)+2c of rows v-1..v+1 (:156-159); that is
+ * reproduced, the Scharr sums are exact integers.  The direction offsets int(sqrt(2)*sin/cos(atan2(gy,gx)+pi/2)) are
+ * evaluated in integer form; on the diagonals |gx| == |gy|, where the truncation depends on the last bit of libm,
+ * they come from a table computed with the host libm when the context is created.  Pixels failing the border test
+ * (:154) get the un-normalised (1,1,1) of :162.  grad_out n x 3, cov_out / info_out n x 9 row-major; double, nullable. */
+PSLAM_API int pslam_gradient_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint8_t* rgb, int rgb_row_bytes,
+                                         const uint16_t* depth, int W, int H, int row_stride, const pslam_camera* cam,
+                                         double depth_scale, double scale_uncertainty_gradient, double* grad_out,
+                                         double* cov_out, double* info_out);
 
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB

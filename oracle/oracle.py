@@ -199,6 +199,39 @@ def uncertainty_from_normal(normal, scale):
     return cov.reshape(3, 3)
 
 
+def inverse3d(m):
+    m = np.ascontiguousarray(m, np.float64).reshape(9)
+    r = np.empty(9, np.float64)
+    lib().orc_inverse3d(_p(m, C.c_double), _p(r, C.c_double))
+    return r.reshape(3, 3)
+
+
+def compute_rgb_gradient(rgb, depth, u, v, fx, fy, cx, cy, depth_scale):
+    """RGBD::computeRGBGradient on an H x W x 3 uint8 image (read as uint16 words like the reference)"""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    H, W = depth.shape
+    assert rgb.shape == (H, W, 3)
+    g = np.empty(3, np.float64)
+    lib().orc_compute_rgb_gradient(_p(rgb, C.c_uint8), 3 * W, _p(depth, C.c_uint16), W, H, W, int(u), int(v),
+                                   C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_double(depth_scale),
+                                   _p(g, C.c_double))
+    return g
+
+
+def gradient_diag_table():
+    t = np.empty(16, np.int32)
+    lib().orc_gradient_diag_table(_p(t, C.c_int))
+    return t.reshape(4, 4)
+
+
+def uncertainty_from_gradient(grad, scale):
+    g = np.ascontiguousarray(grad, np.float64)
+    cov = np.empty(9, np.float64)
+    lib().orc_uncertainty_from_gradient(_p(g, C.c_double), C.c_double(scale), _p(cov, C.c_double))
+    return cov.reshape(3, 3)
+
+
 def map_prepare(xyz, view_axis, pose, fx, fy, cx, cy, img_w=640, img_h=480, max_angle=0.6, max_z=5.0):
     """-> (kept int32[n], xyz_local f64[n,3], uv f64[n,2], angles f64[n]); pose = 4x4 camera->global (numpy row-major)"""
     xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)

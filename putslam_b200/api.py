@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -164,17 +164,35 @@ class Context:
                                             C.byref(cov) if cov is not None else None))
         return dict(xyz=xyz, uv_undist=und, det_dist=dd, cov=covo)
 
-    def normal_uncertainty(self, px, depth, cam=None, depth_scale=5000.0, scale=0.8):
+    def normal_uncertainty(self, px, depth, cam=None, depth_scale=5000.0, scale=0.8, with_info=False):
         px = _arr(px, np.int32, 2)
         depth = np.ascontiguousarray(depth, np.uint16)
         H, W = depth.shape
         n = px.shape[0] if px.size else 0
         cam = cam or make_camera()
         nrm = np.empty((n, 3), np.float64); cov = np.empty((n, 3, 3), np.float64)
+        info = np.empty((n, 3, 3), np.float64) if with_info else None
         self._ck(self.lib.pslam_normal_uncertainty(self.h, _p(px, C.c_int), n, _p(depth, C.c_uint16), W, H, W, C.byref(cam),
                                                    C.c_double(depth_scale), C.c_double(scale), _p(nrm, C.c_double),
-                                                   _p(cov, C.c_double)))
-        return nrm, cov
+                                                   _p(cov, C.c_double), _p(info, C.c_double) if with_info else None))
+        return (nrm, cov, info) if with_info else (nrm, cov)
+
+    def gradient_uncertainty(self, px, rgb, depth, cam=None, depth_scale=5000.0, scale=0.8):
+        """uncertainty model 2 -> (grad n x 3, cov n x 3 x 3, info n x 3 x 3); rgb = H x W x 3 uint8"""
+        px = _arr(px, np.int32, 2)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        H, W = depth.shape
+        if rgb.shape != (H, W, 3):
+            raise ValueError("rgb must be H x W x 3 uint8 with the depth image's size")
+        n = px.shape[0] if px.size else 0
+        cam = cam or make_camera()
+        g = np.empty((n, 3), np.float64); cov = np.empty((n, 3, 3), np.float64); info = np.empty((n, 3, 3), np.float64)
+        self._ck(self.lib.pslam_gradient_uncertainty(self.h, _p(px, C.c_int), n, _p(rgb, C.c_uint8), 3 * W,
+                                                     _p(depth, C.c_uint16), W, H, W, C.byref(cam), C.c_double(depth_scale),
+                                                     C.c_double(scale), _p(g, C.c_double), _p(cov, C.c_double),
+                                                     _p(info, C.c_double)))
+        return g, cov, info
 
     def information_matrices(self, uvz, cov):
         uvz = _arr(uvz, np.float64, 3)

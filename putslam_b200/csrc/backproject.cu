@@ -175,12 +175,29 @@ __device__ __forceinline__ void matmul3(const double (&A)[9], const double (&B)[
         }
 }
 
+// cov and (optionally) cov.inverse() -- the information matrix FeaturesMap attaches for models 1 / 2
+// (reference src/Map/featuresMap.cpp:115-120, 268-273); Eigen's 3x3 cofactor inverse.
+__device__ __forceinline__ void store_cov_info(const double (&cov)[9], int i, double* __restrict__ cov_out,
+                                               double* __restrict__ info_out) {
+    if (cov_out) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) cov_out[9 * (size_t)i + a] = cov[a];
+    }
+    if (info_out) {
+        double inf[9];
+        inverse3d(cov, inf);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) info_out[9 * (size_t)i + a] = inf[a];
+    }
+}
+
 // Uncertainty model 1: RGBD::computeNormal (reference src/RGBD/RGBD.cpp:101-144) + DepthSensorModel::
 // uncertinatyFromNormal (src/Grabber/depthSensorModel.cpp:62-76).  px = n x {u, v} integer pixels
 // ((int)it->u, (int)it->v in RGBD::computeNormals, include/putslam/RGBD/RGBD.h:91-95).
 __global__ void normal_cov_kernel(const int* __restrict__ px, int n, const uint16_t* __restrict__ depth, int W, int H,
                                   int stride, pslam_camera cam, double depth_scale, double scale_unc,
-                                  double* __restrict__ normals, double* __restrict__ cov_out) {
+                                  double* __restrict__ normals, double* __restrict__ cov_out,
+                                  double* __restrict__ info_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int u = px[2 * i], v = px[2 * i + 1];
@@ -215,7 +232,7 @@ __global__ void normal_cov_kernel(const int* __restrict__ px, int n, const uint1
     double nr[3] = {__ddiv_rn(sx, (double)nv), __ddiv_rn(sy, (double)nv), __ddiv_rn(sz, (double)nv)};
     normalize3(nr);
     if (normals) { normals[3 * (size_t)i] = nr[0]; normals[3 * (size_t)i + 1] = nr[1]; normals[3 * (size_t)i + 2] = nr[2]; }
-    if (cov_out) {
+    if (cov_out || info_out) {
         double nn[3] = {nr[0], nr[1], nr[2]};
         double y[3] = {nn[1] * 0.0 - nn[2] * 0.0, nn[2] * 1.0 - nn[0] * 0.0, nn[0] * 0.0 - nn[1] * 1.0};
         normalize3(nn);
@@ -228,17 +245,100 @@ __global__ void normal_cov_kernel(const int* __restrict__ px, int n, const uint1
         matmul3(RS, S, RSS);
         inverse3d(R, Rinv);
         matmul3(RSS, Rinv, cov);
+        store_cov_info(cov, i, cov_out, info_out);
+    }
+}
+
+// Uncertainty model 2: RGBD::computeRGBGradient (reference src/RGBD/RGBD.cpp:147-187) + DepthSensorModel::
+// uncertinatyFromRGBGradient (src/Grabber/depthSensorModel.cpp:79-95).  The colour patch is read as 16-bit words at
+// byte offsets 2c of the patch rows, like the reference's at<uint16_t> (:156-159).  Direction offsets
+// coord1 = (int(sqrt2 sin a), int(sqrt2 cos a)), a = atan2(gy, gx) + pi/2, i.e. (trunc(sqrt2 gx/r), trunc(-sqrt2 gy/r)):
+// decided with exact integer comparisons; the diagonals |gx| == |gy| come from the host-libm table diag
+// (q = (gx<0) + 2(gy<0) -> {c1x, c1y, c2x, c2y}).
+struct GradDiag { int t[16]; };
+__global__ void gradient_cov_kernel(const int* __restrict__ px, int n, const uint8_t* __restrict__ rgb, int rgb_row_bytes,
+                                    const uint16_t* __restrict__ depth, int W, int H, int stride, pslam_camera cam,
+                                    double depth_scale, double scale_unc, GradDiag diag, double* __restrict__ grads,
+                                    double* __restrict__ cov_out, double* __restrict__ info_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int u = px[2 * i], v = px[2 * i + 1];
+    double g[3];
+    if (!((u - 1 > 0) && (v - 1 > 0) && (u + 1 < W) && (v + 1 < H))) {
+        g[0] = 1; g[1] = 1; g[2] = 1;
+    } else {
+        int p[3][3];
 #pragma unroll
-        for (int a = 0; a < 9; ++a) cov_out[9 * (size_t)i + a] = cov[a];
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint8_t* b = rgb + (size_t)(v - 1 + r) * rgb_row_bytes + 3 * (size_t)(u - 1) + 2 * c;
+                p[r][c] = (int)b[0] | ((int)b[1] << 8);
+            }
+        const int gx = -3 * p[0][0] - 10 * p[0][1] - 3 * p[0][2] + 3 * p[2][0] + 10 * p[2][1] + 3 * p[2][2];
+        const int gy = -3 * p[0][0] - 10 * p[1][0] - 3 * p[2][0] + 3 * p[0][2] + 10 * p[1][2] + 3 * p[2][2];
+        const int ax = gx < 0 ? -gx : gx, ay = gy < 0 ? -gy : gy;
+        int c1x, c1y, c2x, c2y;
+        if (ax == ay && ax != 0) {
+            const int q = (gx < 0 ? 1 : 0) + (gy < 0 ? 2 : 0);
+            c1x = diag.t[4 * q]; c1y = diag.t[4 * q + 1]; c2x = diag.t[4 * q + 2]; c2y = diag.t[4 * q + 3];
+        } else {
+            // sqrt2*|gx|/r >= 1  <=>  |gx| >= |gy|; gx == gy == 0 behaves like atan2(+0,+0) = 0 -> (1, 0)
+            c1x = (ax > ay || (ax == 0 && ay == 0)) ? (gx < 0 ? -1 : 1) : 0;
+            c1y = (ay > ax) ? (gy < 0 ? 1 : -1) : 0;
+            c2x = -c1x; c2y = -c1y;
+        }
+        float pc[3], pe[3], pb[3];
+        px_to_3d((float)u, (float)v, depth, W, H, stride, cam, depth_scale, pc);
+        px_to_3d((float)(u + c1x), (float)(v + c1y), depth, W, H, stride, cam, depth_scale, pe);
+        px_to_3d((float)(u + c2x), (float)(v + c2y), depth, W, H, stride, cam, depth_scale, pb);
+        if (pe[2] > 0.f && pb[2] != 0.f) {
+            g[0] = (double)(pe[0] - pb[0]); g[1] = (double)(pe[1] - pb[1]); g[2] = (double)(pe[2] - pb[2]);
+        } else if (pc[2] > 0.f && pb[2] != 0.f) {
+            g[0] = (double)(pc[0] - pb[0]); g[1] = (double)(pc[1] - pb[1]); g[2] = (double)(pc[2] - pb[2]);
+        } else if (pc[2] > 0.f && pe[2] != 0.f) {
+            g[0] = (double)(pe[0] - pc[0]); g[1] = (double)(pe[1] - pc[1]); g[2] = (double)(pe[2] - pc[2]);
+        } else {
+            g[0] = (double)c1x; g[1] = (double)c1y; g[2] = 0.0;
+        }
+        normalize3(g);
+    }
+    if (grads) { grads[3 * (size_t)i] = g[0]; grads[3 * (size_t)i + 1] = g[1]; grads[3 * (size_t)i + 2] = g[2]; }
+    if (cov_out || info_out) {
+        double y[3] = {0.0 * g[2] - 1.0 * g[1], 1.0 * g[0] - 0.0 * g[2], 0.0 * g[1] - 0.0 * g[0]};
+        normalize3(y);
+        double z[3] = {y[1] * g[2] - y[2] * g[1], y[2] * g[0] - y[0] * g[2], y[0] * g[1] - y[1] * g[0]};
+        normalize3(z);
+        const double R[9] = {g[0], y[0], z[0], g[1], y[1], z[1], g[2], y[2], z[2]};
+        const double S[9] = {1, 0, 0, 0, scale_unc, 0, 0, 0, 1};
+        double RS[9], RSS[9], Rinv[9], cov[9];
+        matmul3(R, S, RS);
+        matmul3(RS, S, RSS);
+        inverse3d(R, Rinv);
+        matmul3(RSS, Rinv, cov);
+        store_cov_info(cov, i, cov_out, info_out);
     }
 }
 
 cudaError_t launch_normal_cov(const int* d_px, int n, const uint16_t* d_depth, int W, int H, int stride,
                               const pslam_camera& cam, double depth_scale, double scale_unc, double* d_normals,
-                              double* d_cov, cudaStream_t st, int* launches) {
+                              double* d_cov, double* d_info, cudaStream_t st, int* launches) {
     if (n <= 0) return cudaSuccess;
     normal_cov_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_px, n, d_depth, W, H, stride, cam, depth_scale, scale_unc,
-                                                       d_normals, d_cov);
+                                                       d_normals, d_cov, d_info);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gradient_cov(const int* d_px, int n, const uint8_t* d_rgb, int rgb_row_bytes, const uint16_t* d_depth,
+                                int W, int H, int stride, const pslam_camera& cam, double depth_scale, double scale_unc,
+                                const int* diag16, double* d_grads, double* d_cov, double* d_info, cudaStream_t st,
+                                int* launches) {
+    if (n <= 0) return cudaSuccess;
+    GradDiag dg;
+    for (int k = 0; k < 16; ++k) dg.t[k] = diag16[k];
+    gradient_cov_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_px, n, d_rgb, rgb_row_bytes, d_depth, W, H, stride, cam,
+                                                         depth_scale, scale_unc, dg, d_grads, d_cov, d_info);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

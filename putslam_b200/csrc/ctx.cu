@@ -395,7 +395,7 @@ int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* de
 
 int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_t* depth, int W, int H, int row_stride,
                              const pslam_camera* cam, double depth_scale, double scale_uncertainty_normal,
-                             double* normals_out, double* cov_out) {
+                             double* normals_out, double* cov_out, double* info_out) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (n < 0 || (n > 0 && !px) || !depth || !cam || W <= 0 || H <= 0 || row_stride < W)
         return fail(ctx, PSLAM_ERR_ARG, "pslam_normal_uncertainty: bad argument");
@@ -403,7 +403,7 @@ int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_
     CK(cudaSetDevice(ctx->device));
     Arena in, out;
     const size_t o_px = in.take(8 * (size_t)n), o_depth = in.take(sizeof(uint16_t) * (size_t)H * row_stride);
-    const size_t o_n = out.take(24 * (size_t)n), o_cov = out.take(72 * (size_t)n);
+    const size_t o_n = out.take(24 * (size_t)n), o_cov = out.take(72 * (size_t)n), o_info = out.take(72 * (size_t)n);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     memcpy(ctx->h_in.p + o_px, px, 8 * (size_t)n);
@@ -412,12 +412,62 @@ int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_
     int l = 0;
     CK(launch_normal_cov((const int*)(ctx->d_in.p + o_px), n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H, row_stride, *cam,
                          depth_scale, scale_uncertainty_normal, (double*)(ctx->d_out.p + o_n), (double*)(ctx->d_out.p + o_cov),
-                         ctx->stream, &l));
+                         info_out ? (double*)(ctx->d_out.p + o_info) : nullptr, ctx->stream, &l));
     ctx->launches += l;
-    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, info_out ? out.off : o_info, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (normals_out) memcpy(normals_out, ctx->h_out.p + o_n, 24 * (size_t)n);
     if (cov_out) memcpy(cov_out, ctx->h_out.p + o_cov, 72 * (size_t)n);
+    if (info_out) memcpy(info_out, ctx->h_out.p + o_info, 72 * (size_t)n);
+    return PSLAM_OK;
+}
+
+// The libm-sensitive diagonals of RGBD::computeRGBGradient (reference src/RGBD/RGBD.cpp:164-166), evaluated once with
+// the host libm so that the device kernel truncates exactly like host code on this machine would.
+static void gradient_diag_table(int* out) {
+    for (int q = 0; q < 4; ++q) {
+        volatile double gx = (q & 1) ? -1.0 : 1.0, gy = (q & 2) ? -1.0 : 1.0;   // volatile: no compile-time folding
+        const double angle = atan2(gy, gx) + (M_PI / 2.0);
+        out[4 * q + 0] = (int)(sqrt(2.0) * sin(angle));
+        out[4 * q + 1] = (int)(sqrt(2.0) * cos(angle));
+        out[4 * q + 2] = (int)(sqrt(2.0) * sin(angle + M_PI));
+        out[4 * q + 3] = (int)(sqrt(2.0) * cos(angle + M_PI));
+    }
+}
+
+int pslam_gradient_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint8_t* rgb, int rgb_row_bytes,
+                               const uint16_t* depth, int W, int H, int row_stride, const pslam_camera* cam,
+                               double depth_scale, double scale_uncertainty_gradient, double* grad_out, double* cov_out,
+                               double* info_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n < 0 || (n > 0 && !px) || !rgb || !depth || !cam || W <= 0 || H <= 0 || row_stride < W || rgb_row_bytes < 3 * W)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_gradient_uncertainty: bad argument");
+    if (n == 0) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out;
+    const size_t o_px = in.take(8 * (size_t)n), o_depth = in.take(sizeof(uint16_t) * (size_t)H * row_stride);
+    const size_t o_rgb = in.take((size_t)H * rgb_row_bytes);
+    const size_t o_g = out.take(24 * (size_t)n), o_cov = out.take(72 * (size_t)n), o_info = out.take(72 * (size_t)n);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    memcpy(ctx->h_in.p + o_px, px, 8 * (size_t)n);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    memcpy(ctx->h_in.p + o_rgb, rgb, (size_t)H * rgb_row_bytes);
+    CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    int diag[16];
+    gradient_diag_table(diag);
+    int l = 0;
+    CK(launch_gradient_cov((const int*)(ctx->d_in.p + o_px), n, (const uint8_t*)(ctx->d_in.p + o_rgb), rgb_row_bytes,
+                           (const uint16_t*)(ctx->d_in.p + o_depth), W, H, row_stride, *cam, depth_scale,
+                           scale_uncertainty_gradient, diag, (double*)(ctx->d_out.p + o_g),
+                           (cov_out || !info_out) ? (double*)(ctx->d_out.p + o_cov) : nullptr,
+                           info_out ? (double*)(ctx->d_out.p + o_info) : nullptr, ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, info_out ? out.off : o_info, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (grad_out) memcpy(grad_out, ctx->h_out.p + o_g, 24 * (size_t)n);
+    if (cov_out) memcpy(cov_out, ctx->h_out.p + o_cov, 72 * (size_t)n);
+    if (info_out) memcpy(info_out, ctx->h_out.p + o_info, 72 * (size_t)n);
     return PSLAM_OK;
 }
 

@@ -88,7 +88,12 @@ cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth
 
 cudaError_t launch_normal_cov(const int* d_px, int n, const uint16_t* d_depth, int W, int H, int stride,
                               const pslam_camera& cam, double depth_scale, double scale_unc, double* d_normals,
-                              double* d_cov, cudaStream_t st, int* launches);
+                              double* d_cov, double* d_info, cudaStream_t st, int* launches);
+// diag16: the host-libm direction table of the diagonals (see gradient_cov_kernel)
+cudaError_t launch_gradient_cov(const int* d_px, int n, const uint8_t* d_rgb, int rgb_row_bytes, const uint16_t* d_depth,
+                                int W, int H, int stride, const pslam_camera& cam, double depth_scale, double scale_unc,
+                                const int* diag16, double* d_grads, double* d_cov, double* d_info, cudaStream_t st,
+                                int* launches);
 cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_params& cp, double* d_cov, double* d_info,
                                cudaStream_t st, int* launches);
 

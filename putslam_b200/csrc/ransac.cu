@@ -3,7 +3,7 @@
 //   ransac_filter_kernel  : drop matches with NaN / z outside [0.1, 6] and gather the surviving pairs
 //                           into SoA form (reference src/TransformEst/RANSAC.cpp:65-80)
 //   K4a ransac_model_kernel: one thread per hypothesis -- counter-based sample of 3 matches, 3-point Umeyama
-//   K4b ransac_score_kernel: one warp per hypothesis -- score every match, inlier count by warp reduction
+//   K4b ransac_score_kernel: one lane per hypothesis, matches broadcast from shared memory, integer RED per hypothesis
 //                           (reference RANSAC.cpp:87-150 loop body, :180-281, :325-436)
 //   K5 ransac_select_kernel: replay of saveBetterModel / iterationCount (RANSAC.cpp:438-461) over the
 //                           per-hypothesis counts, inlier list of the winner, Umeyama refit over all its
@@ -174,51 +174,63 @@ ransac_model_kernel(const float* __restrict__ pts, int m_cap, const int* __restr
     mp[2] = make_float4(M.R[8], M.t[0], M.t[1], M.t[2]);
 }
 
-// K4b: one WARP per hypothesis -- lanes stride over the matches, inlier count by warp reduction.
+// K4b: one LANE per hypothesis, the matches broadcast from shared memory.  A CTA owns 32 hypotheses (lane = hypothesis,
+// model in registers) and one slice of the match list (blockIdx.y); it stages the slice from the SoA arrays into
+// shared memory as {prev.xyz, cur.x | cur.yz}, and its 8 warps walk interleaved matches: every LDS is a warp-wide
+// broadcast that serves 32 hypothesis x match tests, so there is no global load and no warp reduction in the loop
+// (the previous warp-per-hypothesis layout spent 78 % of its cycles on the per-match global loads, ncu).  The 8 partial
+// counts per hypothesis are added in shared memory, then one integer RED per hypothesis into counts[] (zeroed by the
+// model kernel) -- integer sums, so the result does not depend on the order.
+constexpr int kScoreTile = 512;   // matches staged per pass: 12 KB
 __global__ void __launch_bounds__(kScoreThreads)
 ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ n_filtered, int min_matches,
                     Scorer S, int H, int* __restrict__ counts, const float* __restrict__ models) {
+    __shared__ float4 sA[kScoreTile];   // prev.x prev.y prev.z cur.x
+    __shared__ float2 sB[kScoreTile];   // cur.y cur.z
+    __shared__ int s_cnt[32];
     const int mf = *n_filtered;
     if (mf < min_matches || mf < 3) return;
-    const int lane = threadIdx.x & 31;
-    const int warps_total = gridDim.x * (kScoreThreads / 32);
-    const float* px = pts;
-    const float* py = pts + (size_t)m_cap;
-    const float* pz = pts + 2 * (size_t)m_cap;
-    const float* cx = pts + 3 * (size_t)m_cap;
-    const float* cy = pts + 4 * (size_t)m_cap;
-    const float* cz = pts + 5 * (size_t)m_cap;
-    for (int h = blockIdx.x * (kScoreThreads / 32) + (threadIdx.x >> 5); h < H; h += warps_total) {
-        if (counts[h] < 0) continue;   // degenerate model
-        Rigid3f M;
-        const float4* mp = reinterpret_cast<const float4*>(models + 12 * (size_t)h);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kScoreThreads / 32;
+    const int h = blockIdx.x * 32 + lane;
+    const int per = (mf + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int lo = blockIdx.y * per;
+    const int hi = min(mf, lo + per);
+    if (lo >= hi) return;
+
+    bool live = h < H;
+    if (live) live = counts[h] >= 0;   // -1: degenerate model
+    Rigid3f M;
+    {
+        const float4* mp = reinterpret_cast<const float4*>(models + 12 * (size_t)(h < H ? h : 0));
         const float4 m0 = mp[0], m1 = mp[1], m2 = mp[2];
         M.R[0] = m0.x; M.R[1] = m0.y; M.R[2] = m0.z; M.R[3] = m0.w; M.R[4] = m1.x; M.R[5] = m1.y; M.R[6] = m1.z;
         M.R[7] = m1.w; M.R[8] = m2.x; M.t[0] = m2.y; M.t[1] = m2.z; M.t[2] = m2.w; M.ok = true;
-        float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
-        if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
-        int c = 0;
-        // kU matches per lane per trip: the loads are issued before the first use, so the L1/L2 latency is paid once
-        // per trip instead of once per match (ncu: 78 % long-scoreboard stalls with one match per trip).  kU = 2 keeps
-        // the kernel at <= 72 registers, i.e. all 4096 hypothesis warps of the C3 configuration resident in one wave.
-        constexpr int kU = 2;
-        for (int k0 = lane; k0 < mf; k0 += 32 * kU) {
-            float a[kU][6];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int k = k0 + 32 * u;
-                const int kk = k < mf ? k : k0;   // clamp: a valid address, result discarded below
-                a[u][0] = px[kk]; a[u][1] = py[kk]; a[u][2] = pz[kk]; a[u][3] = cx[kk]; a[u][4] = cy[kk]; a[u][5] = cz[kk];
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const bool in = inlier_test(S, M.R, M.t, Ri, ti, a[u][0], a[u][1], a[u][2], a[u][3], a[u][4], a[u][5], false);
-                c += (in && (k0 + 32 * u < mf)) ? 1 : 0;
-            }
-        }
-        c = (int)warp_add_u32((uint32_t)c);
-        if (lane == 0) counts[h] = c;
     }
+    float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
+    if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
+    if (tid < 32) s_cnt[tid] = 0;
+
+    int c = 0;
+    for (int base = lo; base < hi; base += kScoreTile) {
+        const int nt = min(kScoreTile, hi - base);
+        __syncthreads();   // previous tile consumed (and s_cnt initialised)
+        for (int k = tid; k < nt; k += kScoreThreads) {
+            const int g = base + k;
+            sA[k] = make_float4(pts[g], pts[(size_t)m_cap + g], pts[2 * (size_t)m_cap + g], pts[3 * (size_t)m_cap + g]);
+            sB[k] = make_float2(pts[4 * (size_t)m_cap + g], pts[5 * (size_t)m_cap + g]);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k = warp; k < nt; k += kWarps) {
+            const float4 a = sA[k];
+            const float2 b = sB[k];
+            c += inlier_test(S, M.R, M.t, Ri, ti, a.x, a.y, a.z, a.w, b.x, b.y, false) ? 1 : 0;
+        }
+    }
+    if (live && c) atomicAdd(&s_cnt[lane], c);
+    __syncthreads();
+    if (tid < 32 && live && s_cnt[tid]) atomicAdd(&counts[h], s_cnt[tid]);
 }
 
 // computeRANSACIteration (reference RANSAC.cpp:457-461): int(log(1-0.98) / log(1 - w^3)).  The
@@ -501,14 +513,20 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     const int H = adaptive ? 487 : P.num_hyp;  // int(log(0.02)/log(1-0.2^3)), reference RANSAC.cpp:30
     ransac_filter_kernel<<<1, 1024, 0, st>>>(d_prev, d_cur, d_mq, d_mt, d_m, m_host, ws.m_cap, ws.pts, ws.keep,
                                              ws.n_filtered);
-    const int warps_per_cta = kScoreThreads / 32;
-    int grid = (H + warps_per_cta - 1) / warps_per_cta;
-    const int max_grid = sm_count * 8;
-    if (grid > max_grid) grid = max_grid;
     ransac_model_kernel<<<(H + kModelThreads - 1) / kModelThreads, kModelThreads, 0, st>>>(
         ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, P.seed_lo, P.seed_hi, H, ws.counts, ws.models);
-    ransac_score_kernel<<<grid, kScoreThreads, 0, st>>>(ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, H, ws.counts,
-                                                        ws.models);
+    // 32 hypotheses per CTA; the match list is cut into as many slices as put up to 4 CTAs on every SM, but
+    // no slice shorter than ~64 matches (the filtered count is only known on the device: bound it by the number of
+    // matches handed in, or by the capacity of the list when that number is device-resident too)
+    const int hyp_ctas = (H + 31) / 32;
+    int slices = (4 * sm_count) / hyp_ctas;   // rounded down: 4 CTAs of 256 threads x 64 registers fit an SM -> one wave
+    const int m_bound = d_m ? ws.m_cap : m_host;
+    const int max_slices = m_bound / 64 > 1 ? m_bound / 64 : 1;
+    if (slices > max_slices) slices = max_slices;
+    if (slices > 64) slices = 64;
+    if (slices < 1) slices = 1;
+    ransac_score_kernel<<<dim3((unsigned)hyp_ctas, (unsigned)slices), kScoreThreads, 0, st>>>(
+        ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, H, ws.counts, ws.models);
     // shared-memory staging of the winner's inliers for the refit: up to 8192 inliers (192 KB)
     int stage_cap = ws.m_cap < 8192 ? ws.m_cap : 8192;
     const size_t sel_smem = sizeof(float) * 6 * (size_t)stage_cap;

@@ -357,6 +357,54 @@ def test_normal_uncertainty(ctx, O):
     assert abs(np.abs(nrm[good[0]] @ nrm[good[1]]) - 1) < 1e-2
 
 
+def test_gradient_uncertainty(ctx, O):
+    """Uncertainty model 2: colour-gradient direction (uint16 reads of the 8-bit patch, like the reference) ->
+    3-D gradient -> covariance and information matrix.  Directions are integer decisions (bit-exact incl. the
+    libm-sensitive diagonals); float64 results within 1e-12 relative of the oracle."""
+    from putslam_b200 import synth
+    rng = np.random.default_rng(12)
+    H, W = 480, 640
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    rgb[200:260] = rng.integers(0, 2, (60, W, 3), dtype=np.uint8) * 255       # saturated block: many equal sums
+    uu, vv = np.meshgrid(np.arange(W), np.arange(H))
+    depth = np.rint((1.5 + 0.001 * uu + 0.0005 * vv) * 5000).astype(np.uint16)
+    depth[rng.random(depth.shape) < 0.25] = 0                                    # every fallback branch of :171-184
+    n = 600
+    px = np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], 1).astype(np.int32)
+    px[:6] = [[0, 0], [1, 7], [W - 1, 9], [9, H - 1], [2, 2], [W - 2, H - 2]]
+    # planted diagonals |gx| == |gy| in all four quadrants and three magnitudes
+    k = 6
+    for mag in (1, 300, 65535):
+        for (r, c) in [(2, 2), (0, 2), (2, 0), (0, 0)]:
+            u, v = 20 + 7 * k, 300 + k
+            rgb[v - 1:v + 2, u - 1:u + 3] = 0
+            base = 3 * (u - 1) + 2 * c
+            rgb[v - 1 + r].reshape(-1)[base:base + 2] = [mag & 255, mag >> 8]
+            px[k] = [u, v]; k += 1
+    g, cov, info = ctx.gradient_uncertainty(px, rgb, depth, scale=0.7)
+    n_border = n_nan = 0
+    for i in range(n):
+        rg = O.compute_rgb_gradient(rgb, depth, px[i, 0], px[i, 1], synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)
+        if np.isnan(rg).any():
+            assert np.isnan(g[i]).any(); n_nan += 1
+            continue
+        n_border += int((rg == 1.0).all())
+        assert np.allclose(g[i], rg, rtol=1e-12, atol=1e-15), (i, px[i], g[i], rg)
+        rc = O.uncertainty_from_gradient(rg, 0.7)
+        if np.isnan(rc).any():
+            assert np.isnan(cov[i]).any()
+            continue
+        assert np.allclose(cov[i], rc, rtol=1e-9, atol=1e-13), i
+        assert np.allclose(info[i], O.inverse3d(rc), rtol=1e-8, atol=1e-12), i
+    assert n_border >= 4 and n_nan < n // 4
+    # model 1 also hands back the information matrix
+    nrm, ncov, ninfo = ctx.normal_uncertainty(px[:50], depth, scale=0.8, with_info=True)
+    ok = ~np.isnan(ncov).any((1, 2))
+    assert ok.sum() > 5
+    for i in np.nonzero(ok)[0]:
+        assert np.allclose(ninfo[i], O.inverse3d(ncov[i]), rtol=1e-10, atol=1e-12)
+
+
 def test_ransac_usac_standard_stopping(ctx, O):
     """Alternative termination rule: USAC<T>::updateStandardStopping replayed over the scored hypotheses."""
     from putslam_b200 import synth

@@ -108,6 +108,60 @@ def test_normal_and_uncertainty_from_normal(O):
     assert np.isnan(O.compute_normal(depth, 300, 200, synth.FX, synth.FY, synth.CX, synth.CY, 5000.0)).all()
 
 
+def _py_rgb_gradient_dir(rgb, u, v):
+    """independent restatement of the direction part of RGBD::computeRGBGradient (src/RGBD/RGBD.cpp:154-166)"""
+    import math
+    row = lambda r: rgb[v - 1 + r].reshape(-1)[3 * (u - 1):3 * (u - 1) + 6].view("<u2").astype(np.int64)
+    p = np.stack([row(0), row(1), row(2)])
+    gx = -3 * p[0, 0] - 10 * p[0, 1] - 3 * p[0, 2] + 3 * p[2, 0] + 10 * p[2, 1] + 3 * p[2, 2]
+    gy = -3 * p[0, 0] - 10 * p[1, 0] - 3 * p[2, 0] + 3 * p[0, 2] + 10 * p[1, 2] + 3 * p[2, 2]
+    a = math.atan2(float(gy), float(gx)) + math.pi / 2.0
+    c1 = (int(math.sqrt(2) * math.sin(a)), int(math.sqrt(2) * math.cos(a)))
+    c2 = (int(math.sqrt(2) * math.sin(a + math.pi)), int(math.sqrt(2) * math.cos(a + math.pi)))
+    return int(gx), int(gy), c1, c2
+
+
+def test_rgb_gradient_and_uncertainty_from_gradient(O):
+    """Uncertainty model 2 (src/RGBD/RGBD.cpp:147-187, src/Grabber/depthSensorModel.cpp:79-95)."""
+    from putslam_b200 import synth
+    rng = np.random.default_rng(21)
+    H, W = 480, 640
+    rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    depth = np.full((H, W), 10000, np.uint16)                  # fronto-parallel wall at 2 m
+    cam = (synth.FX, synth.FY, synth.CX, synth.CY)
+    for _ in range(200):
+        u, v = int(rng.integers(2, W - 1)), int(rng.integers(2, H - 1))
+        gx, gy, c1, c2 = _py_rgb_gradient_dir(rgb, u, v)
+        g = O.compute_rgb_gradient(rgb, depth, u, v, *cam, 5000.0)
+        # on a wall both end points have depth: grad is the normalised 3-D difference of pixels u+c1 and u+c2
+        d = np.array([(c1[0] - c2[0]) / synth.FX, (c1[1] - c2[1]) / synth.FY, 0.0]) * 2.0
+        assert np.allclose(g, d / np.linalg.norm(d), atol=1e-5), (u, v, gx, gy, c1, c2, g)
+        assert abs(np.linalg.norm(g) - 1) < 1e-12
+    # border test (:154): u-1 > 0 ... else the un-normalised (1,1,1)
+    for u, v in [(0, 5), (1, 5), (5, 1), (W - 1, 5), (5, H - 1)]:
+        assert (O.compute_rgb_gradient(rgb, depth, u, v, *cam, 5000.0) == 1.0).all()
+    # no depth anywhere -> (coord1, 0) normalised
+    g = O.compute_rgb_gradient(rgb, np.zeros_like(depth), 100, 100, *cam, 5000.0)
+    _, _, c1, _ = _py_rgb_gradient_dir(rgb, 100, 100)
+    assert np.allclose(g, np.array([c1[0], c1[1], 0.0]) / np.hypot(*c1))
+    # the libm-sensitive diagonals: the table equals the direct evaluation, for any magnitude
+    tab = O.gradient_diag_table()
+    for k in (1, 7, 255, 65535):
+        for q, (r, c) in enumerate([(2, 2), (0, 2), (2, 0), (0, 0)]):      # q = (gx<0) + 2 (gy<0)
+            img = np.zeros((H, W, 3), np.uint8)
+            base = 3 * (50 - 1) + 2 * c
+            img[60 - 1 + r].reshape(-1)[base:base + 2] = [k & 255, k >> 8]
+            gx, gy, c1, c2 = _py_rgb_gradient_dir(img, 50, 60)
+            assert abs(gx) == abs(gy) == 3 * k and (gx < 0) + 2 * (gy < 0) == q
+            assert tuple(tab[q]) == c1 + c2
+    # cov = R S^2 R^-1 with S = diag(1, s, 1): eigenvalue s^2 along y = z x grad, 1 along grad
+    g = np.array([0.6, 0.0, 0.8])
+    cov = O.uncertainty_from_gradient(g, 0.8)
+    y = np.cross([0, 0, 1.0], g); y /= np.linalg.norm(y)
+    assert np.allclose(cov @ y, 0.64 * y, atol=1e-12) and np.allclose(cov @ g, g, atol=1e-12)
+    assert np.allclose(O.inverse3d(cov) @ cov, np.eye(3), atol=1e-12)
+
+
 def test_map_prepare_against_numpy(O):
     from putslam_b200 import synth
     rng = np.random.default_rng(3)
