@@ -66,6 +66,30 @@ int main(int argc, char** argv) {
     }
     const double map_ms = (now_ms() - t0) / frames;
 
+    // the same frame against the map resident in HBM: only the pose and the current keypoints are sent.  The map is in
+    // the camera frame here, so the pose is the identity, every view axis is the optical axis and all 5000 features
+    // pass the filters: the matching problem, and therefore the answer, is the one above.
+    std::vector<float> axes(3 * map.octave.size(), 0.f);
+    for (size_t j = 0; j < map.octave.size(); ++j) axes[3 * j + 2] = 1.f;
+    const bool up = matcher.uploadMapFeatures(0, map, axes);
+    const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    MatcherB200::MapFilter filt;
+    filt.maxZ = 1e9;
+    std::vector<int> kept;
+    std::vector<cv::DMatch> rm, ri;
+    Eigen::Matrix4f Tr;
+    double rratio = 0;
+    for (int i = 0; up && i < warmup + frames; ++i) {
+        if (i == warmup) t0 = now_ms();
+        matcher.setSeed((uint64_t)i);
+        rratio = matcher.matchXYZResident(eye, filt, curDesc, cur3D, curKp, cdet, 0.12, 0.55, 1, rp, K, Tr, kept, rm, ri);
+    }
+    const double res_ms = (now_ms() - t0) / frames;
+    bool same = up && rm.size() == mm.size() && ri.size() == mi.size() && rratio == ratio;
+    for (size_t k = 0; same && k < rm.size(); ++k)
+        same = rm[k].queryIdx == mm[k].queryIdx && rm[k].trainIdx == mm[k].trainIdx && rm[k].distance == mm[k].distance;
+    for (int k = 0; same && k < 16; ++k) same = Tr.data()[k] == T.data()[k];
+
     // VO path on a frame pair
     auto d1 = rd<uint8_t>("desc1.bin"), d2 = rd<uint8_t>("desc2.bin");
     auto uv1 = rd<float>("uv1.bin"), uv2 = rd<float>("uv2.bin");
@@ -102,9 +126,10 @@ int main(int argc, char** argv) {
         f_inl = in.size();
     }
     const double vo_fused_ms = (now_ms() - t0) / frames;
-    printf("{\"frame_to_map_ms\": %.5f, \"map_matches\": %zu, \"map_inliers\": %zu, \"map_ratio\": %.4f, "
+    printf("{\"frame_to_map_ms\": %.5f, \"frame_to_resident_map_ms\": %.5f, \"resident_kept\": %zu, "
+           "\"resident_equals_host_map\": %s, \"map_matches\": %zu, \"map_inliers\": %zu, \"map_ratio\": %.4f, "
            "\"vo_three_calls_ms\": %.5f, \"vo_fused_ms\": %.5f, \"vo_matches\": %zu, \"vo_inliers\": %zu, \"vo_fused_inliers\": %zu, "
            "\"frames\": %d, \"num_hyp\": %d}\n",
-           map_ms, mm.size(), mi.size(), ratio, vo_ms, vo_fused_ms, vo_matches, vo_inl, f_inl, frames, num_hyp);
+           map_ms, res_ms, kept.size(), same ? "true" : "false", mm.size(), mi.size(), ratio, vo_ms, vo_fused_ms, vo_matches, vo_inl, f_inl, frames, num_hyp);
     return 0;
 }

@@ -275,6 +275,109 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
+bool MatcherB200::uploadMapFeatures(int first, const MapSide& features, const std::vector<float>& viewAxis) {
+    pslam_ctx* c = dev_.ctx();
+    const int M = (int)features.octave.size();
+    if (!c) return false;
+    if ((int)features.xyz.size() != 3 * M || (int)features.detDist.size() != M || (int)viewAxis.size() != 3 * M ||
+        features.descriptors.rows != M) {
+        std::cerr << "[putslam_b200] uploadMapFeatures: inconsistent feature arrays" << std::endl;
+        return false;
+    }
+    std::vector<uint8_t> tm;
+    const uint8_t* md = contiguousBytes(features.descriptors, 32, tm);
+    const int r = pslam_map_write(c, first, M, features.xyz.data(), md, features.octave.data(), features.detDist.data(),
+                                  viewAxis.data());
+    if (r != PSLAM_OK) { logError(c, "uploadMapFeatures", r); return false; }
+    return true;
+}
+
+bool MatcherB200::updateMapPositions(int first, const std::vector<double>& xyz) {
+    pslam_ctx* c = dev_.ctx();
+    if (!c) return false;
+    const int r = pslam_map_write(c, first, (int)(xyz.size() / 3), xyz.data(), nullptr, nullptr, nullptr, nullptr);
+    if (r != PSLAM_OK) { logError(c, "updateMapPositions", r); return false; }
+    return true;
+}
+
+bool MatcherB200::truncateMap(int nFeatures) {
+    pslam_ctx* c = dev_.ctx();
+    if (!c) return false;
+    const int r = pslam_map_truncate(c, nFeatures);
+    if (r != PSLAM_OK) { logError(c, "truncateMap", r); return false; }
+    return true;
+}
+
+int MatcherB200::mapSize() {
+    pslam_ctx* c = dev_.ctx();
+    int n = 0;
+    if (c) pslam_map_size(c, &n);
+    return n;
+}
+
+double MatcherB200::matchXYZResident(const double cameraPose[16], const MapFilter& filter, cv::Mat currentPoseDescriptors,
+                                     std::vector<Eigen::Vector3f>& currentPoseFeatures3D,
+                                     std::vector<cv::KeyPoint>& currentPoseKeyPoints, std::vector<double>& currentPoseDetDists,
+                                     double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch,
+                                     int computationNumber, const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,
+                                     Eigen::Matrix4f& estimatedTransformation, std::vector<int>& keptFeatures,
+                                     std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches,
+                                     bool xorDistance) {
+    matches.clear();
+    inlierMatches.clear();
+    keptFeatures.clear();
+    estimatedTransformation = Eigen::Matrix4f::Identity();
+    if (computationNumber > 1) {   // matcher.cpp:619-622
+        matchingXYZSphereRadius += 0.02 * (computationNumber - 1);
+        matchingXYZacceptRatioOfBestMatch = std::max(0.1, matchingXYZacceptRatioOfBestMatch - 0.05 * (computationNumber - 1));
+    }
+    pslam_ctx* c = dev_.ctx();
+    if (!c) { logError(c, "matchXYZResident", PSLAM_ERR_NO_DEVICE); return -1.0; }
+    const int N = (int)currentPoseKeyPoints.size(), M = mapSize();
+    std::vector<int> curOct((size_t)N);
+    for (int i = 0; i < N; ++i) curOct[i] = currentPoseKeyPoints[i].octave;
+    std::vector<uint8_t> tc;
+    const uint8_t* cd = contiguousBytes(currentPoseDescriptors, 32, tc);
+    RANSAC::parameters rp = ransacParams;
+    rp.errorVersion = rp.errorVersionMap;   // matcher.cpp:760-761
+    float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+    if (!cameraMatrix.empty()) {
+        fx = cameraMatrix.at<float>(0, 0); fy = cameraMatrix.at<float>(1, 1);
+        cx = cameraMatrix.at<float>(0, 2); cy = cameraMatrix.at<float>(1, 2);
+    }
+    pslam_ransac_params a = toAbi(rp, fx, fy, cx, cy);
+    pslam_map_prepare_params prep;
+    prep.fx = filter.fx; prep.fy = filter.fy; prep.cx = filter.cx; prep.cy = filter.cy;
+    prep.image_w = filter.imageW; prep.image_h = filter.imageH;
+    prep.max_angle = filter.maxAngleBetweenFrames; prep.max_z = filter.maxZ;
+    int cap = std::max(2048, 2 * N);
+    std::vector<int> mq, mt, inl;
+    std::vector<float> mdist;
+    keptFeatures.resize((size_t)std::max(1, M));
+    int nKept = 0;
+    pslam_frame_result res;
+    int r = PSLAM_ERR_NO_DEVICE;
+    for (int attempt = 0; attempt < 6; ++attempt) {   // the reference's match vector is unbounded: grow on truncation
+        mq.resize((size_t)cap); mt.resize((size_t)cap); mdist.resize((size_t)cap); inl.resize((size_t)cap);
+        r = pslam_frame_to_resident_map(c, cameraPose, &prep, N ? &currentPoseFeatures3D[0][0] : nullptr, cd, curOct.data(),
+                                        currentPoseDetDists.data(), N, matchingXYZSphereRadius,
+                                        matchingXYZacceptRatioOfBestMatch, xorDistance ? 1 : 0, &a, seed_, numHyp_, cap,
+                                        keptFeatures.data(), &nKept, nullptr, nullptr, mq.data(), mt.data(), mdist.data(),
+                                        inl.data(), &res);
+        if (r != PSLAM_ERR_CAPACITY) break;
+        cap = res.n_matches + 16;
+    }
+    keptFeatures.resize((size_t)nKept);
+    if (r != PSLAM_OK) { logError(c, "matchXYZResident", r); return -1.0; }
+    if (res.n_matches <= 0) return -1.0;   // matcher.cpp:755-756
+    matches.reserve((size_t)res.n_matches);
+    inlierMatches.reserve((size_t)res.n_inliers);
+    for (int k = 0; k < res.n_matches; ++k) matches.push_back(cv::DMatch(mq[k], mt[k], -1, mdist[k]));
+    for (int k = 0; k < res.n_inliers; ++k) inlierMatches.push_back(matches[(size_t)inl[k]]);
+    std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
+    return res.inlier_ratio;
+}
+
 double MatcherB200::matchCore(cv::Mat prevDescriptors, const std::vector<Eigen::Vector3f>& prevFeatures3D, cv::Mat descriptors,
                               const std::vector<cv::KeyPoint>& keyPoints, cv::Mat depthImage, double depthImageScale,
                               cv::Mat cameraMatrix, cv::Mat distCoeffs, const RANSAC::parameters& ransacParams,

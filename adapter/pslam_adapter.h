@@ -100,6 +100,29 @@ public:
                         double matchingXYZSphereRadius, double matchingXYZacceptRatioOfBestMatch, int computationNumber,
                         const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix, Eigen::Matrix4f& estimatedTransformation,
                         std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches, bool xorDistance = false);
+    // ---- resident map (pslam_map_* / pslam_frame_to_resident_map): the covisible features stay in HBM ----
+    // uploadMapFeatures stores slots [first, first + M); viewAxis = M x 3 float, third column of the rotation of the
+    // view that holds each feature's descriptor (what FeaturesMap::findNearestFrame compares, featuresMap.cpp:528-563).
+    bool uploadMapFeatures(int first, const MapSide& features, const std::vector<float>& viewAxis);
+    // positions only, e.g. after FeaturesMap::updateMap moved the features (xyz = count x 3)
+    bool updateMapPositions(int first, const std::vector<double>& xyz);
+    bool truncateMap(int nFeatures);
+    int mapSize();
+    struct MapFilter {          // getAndFilterFeaturesFromMap's parameters (src/PUTSLAM/PUTSLAM.cpp:624-674)
+        double fx = 517.3, fy = 516.5, cx = 318.6, cy = 255.3, imageW = 640, imageH = 480;   // DepthSensorModel
+        double maxAngleBetweenFrames = 0.6;                                                     // matcherParameters
+        double maxZ = 5.0;                                                                      // PUTSLAM.cpp:662
+    };
+    // getAndFilterFeaturesFromMap's numeric part + matchXYZ in one submission.  cameraPose = Mat34::matrix() data
+    // (column-major 4x4, camera -> global).  keptFeatures lists the slots that passed the filters; matches'
+    // queryIdx index that list, as the reference's index the filtered mapFeatures vector.
+    double matchXYZResident(const double cameraPose[16], const MapFilter& filter, cv::Mat currentPoseDescriptors,
+                            std::vector<Eigen::Vector3f>& currentPoseFeatures3D, std::vector<cv::KeyPoint>& currentPoseKeyPoints,
+                            std::vector<double>& currentPoseDetDists, double matchingXYZSphereRadius,
+                            double matchingXYZacceptRatioOfBestMatch, int computationNumber,
+                            const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,
+                            Eigen::Matrix4f& estimatedTransformation, std::vector<int>& keptFeatures,
+                            std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches, bool xorDistance = false);
     // The numeric core of Matcher::match (src/Matcher/matcher.cpp:452-516, lines 470-496) in one device submission:
     // performMatching(prevDescriptors, descriptors) -> removeImageDistortion + keypoints2Dto3D on the current keypoints
     // -> RANSAC(prevFeatures3D, features3D, matches).  Returns pointInlierRatio (matcher.cpp:515).  Outputs are what

@@ -114,6 +114,35 @@ int main(int argc, char** argv) {
         wr(tag + "_ratio.bin", std::vector<double>{r});
     }
 
+    // ---- the same frame against the map resident in HBM (identity pose, every view axis = optical axis) ----
+    {
+        std::vector<float> axes(3 * map.octave.size(), 0.f);
+        for (size_t j = 0; j < map.octave.size(); ++j) axes[3 * j + 2] = 1.f;
+        const size_t half = map.octave.size() / 2;          // two uploads: the second appends
+        MatcherB200::MapSide a, b;
+        a.xyz.assign(map.xyz.begin(), map.xyz.begin() + 3 * half); b.xyz.assign(map.xyz.begin() + 3 * half, map.xyz.end());
+        a.octave.assign(map.octave.begin(), map.octave.begin() + half); b.octave.assign(map.octave.begin() + half, map.octave.end());
+        a.detDist.assign(map.detDist.begin(), map.detDist.begin() + half); b.detDist.assign(map.detDist.begin() + half, map.detDist.end());
+        a.descriptors = cv::Mat((int)half, 32, CV_8U, map.descriptors.data);
+        b.descriptors = cv::Mat((int)(map.octave.size() - half), 32, CV_8U, map.descriptors.data + 32 * half);
+        bool ok = matcher.uploadMapFeatures(0, a, std::vector<float>(axes.begin(), axes.begin() + 3 * half));
+        ok = ok && matcher.uploadMapFeatures((int)half, b, std::vector<float>(axes.begin() + 3 * half, axes.end()));
+        if (!ok || matcher.mapSize() != (int)map.octave.size()) { std::cerr << "resident map upload failed" << std::endl; return 3; }
+        const double eye[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        MatcherB200::MapFilter filt;
+        filt.maxZ = 1e9;
+        matcher.setHostLevels(false);
+        matcher.setSeed(77);
+        Eigen::Matrix4f Tm;
+        std::vector<cv::DMatch> mm, mi;
+        std::vector<int> kept;
+        const double r = matcher.matchXYZResident(eye, filt, descMat(cdesc), cur3D, curKp, cdet, 0.12, 0.55, 1, rp, K, Tm, kept, mm, mi);
+        wrMatches("mapr_matches", mm); wrMatches("mapr_inliers", mi);
+        wr("mapr_T.bin", std::vector<float>(Tm.data(), Tm.data() + 16));
+        wr("mapr_ratio.bin", std::vector<double>{r});
+        wr("mapr_kept.bin", kept);
+    }
+
     // ---- demoKabsch path (demoKabsch.cpp:1020): createKabschEstimator()->computeTransformation(A, B) ----
     auto A = rd<double>("kabsch_A.bin"), B = rd<double>("kabsch_B.bin");   // row-major n x 3
     const long n = (long)(A.size() / 3);

@@ -275,6 +275,37 @@ PSLAM_API int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const flo
                                 const double camera_pose[16], const pslam_map_prepare_params* params, int* kept_idx,
                                 double* xyz_local, double* uv, double* angles, int* n_out);
 
+/* ---- resident feature map ------------------------------------------------
+ * The map side of Matcher::matchXYZ kept in HBM in SoA form between frames, so that per frame only the camera pose
+ * and the current keypoints cross PCIe.  A slot holds what PUTSLAM::getAndFilterFeaturesFromMap and matchXYZ read
+ * of one MapFeature (include/putslam/Defs/putslam_defs.h:184-216): global position (double), and of the view that
+ * holds its descriptor (ExtendedDescriptor, :120-151) the 32-byte descriptor, octave, detDist and optical axis.
+ * Slots are the caller's feature indices.  pslam_map_write stores [first, first + count): a range that extends the
+ * map needs every array, a range inside it may pass NULL for attributes that did not change (e.g. only xyz after
+ * a pose-graph update, src/Map/featuresMap.cpp updateMap).  Buffers may be reused when the call returns. */
+PSLAM_API int pslam_map_reserve(pslam_ctx* ctx, int max_features);
+PSLAM_API int pslam_map_write(pslam_ctx* ctx, int first, int count, const double* xyz, const uint8_t* desc,
+                              const int* octave, const double* det_dist, const float* view_axis);
+PSLAM_API int pslam_map_truncate(pslam_ctx* ctx, int n_features);
+PSLAM_API int pslam_map_size(const pslam_ctx* ctx, int* n_features);
+
+/* One tracking frame against the resident map == pslam_map_prepare on the stored features followed by
+ * pslam_frame_to_map_features on the kept ones (PUTSLAM.cpp:624-674 then Matcher::matchXYZ, matcher.cpp:606-798),
+ * in one submission: filter + move to the camera frame (K8, which also gathers the kept descriptors), level
+ * prediction, guided matching, RANSAC.  kept_idx_out (capacity = map size) lists the slots that passed the filters,
+ * in slot order; match_query_out indexes that list, exactly as the reference's queryIdx indexes the filtered
+ * mapFeatures vector.  xyz_local_out / uv_out (nullable, capacity map size x 3 / x 2) are the camera-frame positions
+ * and projections moveMapFeaturesToLocalCordinateSystem writes back into the features.  Other arguments and
+ * results as pslam_frame_to_map_features. */
+PSLAM_API int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_pose[16],
+                                          const pslam_map_prepare_params* prep, const float* cur_xyz,
+                                          const uint8_t* cur_desc, const int* cur_octave, const double* cur_det_dist,
+                                          int N, double radius, double accept_ratio, int distance_mode,
+                                          const pslam_ransac_params* params, uint64_t seed, int num_hyp, int match_cap,
+                                          int* kept_idx_out, int* n_kept_out, double* xyz_local_out, double* uv_out,
+                                          int* match_query_out, int* match_train_out, float* match_dist_out,
+                                          int* inlier_idx_out, pslam_frame_result* result);
+
 /* ---- loop-closure sweep: query frame vs every keyframe of the map --------------------------
  * Generalises Matcher::matchFeatureLoopClosure's performMatching step (src/Matcher/matcher.cpp:802-861,
  * :835) from one FABMAP-proposed pair to all keyframes: score(k) = number of mutual-NN matches between

@@ -20,7 +20,7 @@ ABI_SYMBOLS = [
     "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
-    "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
+    "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_set_work_unit", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
@@ -375,6 +375,59 @@ class Context:
         return dict(mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(), inliers=inl[:res.n_inliers].copy(),
                     T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
                     inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used, n_filtered=res.n_filtered)
+
+    # ---- resident feature map ----
+    def map_reserve(self, n):
+        self._ck(self.lib.pslam_map_reserve(self.h, int(n)))
+
+    def map_write(self, first, xyz=None, desc=None, octave=None, detdist=None, view_axis=None, count=None):
+        x = None if xyz is None else _arr(xyz, np.float64, 3)
+        d = None if desc is None else _arr(desc, np.uint8)
+        o = None if octave is None else _arr(octave, np.int32)
+        t = None if detdist is None else _arr(detdist, np.float64)
+        a = None if view_axis is None else _arr(view_axis, np.float32, 3)
+        if count is None:
+            count = next(v.shape[0] if v.ndim > 1 else v.size for v in (x, o, t, a, d) if v is not None)
+        self._ck(self.lib.pslam_map_write(self.h, int(first), int(count), None if x is None else _p(x, C.c_double),
+                                          None if d is None else _p(d, C.c_uint8), None if o is None else _p(o, C.c_int),
+                                          None if t is None else _p(t, C.c_double), None if a is None else _p(a, C.c_float)))
+
+    def map_truncate(self, n):
+        self._ck(self.lib.pslam_map_truncate(self.h, int(n)))
+
+    def map_size(self):
+        n = C.c_int(0)
+        self._ck(self.lib.pslam_map_size(self.h, C.byref(n)))
+        return n.value
+
+    def frame_to_resident_map(self, pose, prep, cur_xyz, cur_desc, cur_octave, cur_detdist, radius=0.12, ratio=0.55, mode=0,
+                              params=None, seed=0, num_hyp=0, match_cap=16384, want_local=False):
+        """pose: numpy 4x4 (camera -> global); prep: MapPrepareParams.  mq indexes `kept`."""
+        cx = _arr(cur_xyz, np.float32, 3); cd = _arr(cur_desc, np.uint8)
+        co = _arr(cur_octave, np.int32); cdd = _arr(cur_detdist, np.float64)
+        pcm = np.ascontiguousarray(np.asarray(pose, np.float64).T)
+        params = params or default_ransac_params()
+        M = max(1, self.map_size())
+        kept = np.empty(M, np.int32); nk = C.c_int(0)
+        xl = np.empty((M, 3), np.float64) if want_local else None
+        uv = np.empty((M, 2), np.float64) if want_local else None
+        mq = np.empty(match_cap, np.int32); mt = np.empty(match_cap, np.int32); md = np.empty(match_cap, np.float32)
+        inl = np.empty(match_cap, np.int32)
+        res = FrameResult()
+        self._ck(self.lib.pslam_frame_to_resident_map(
+            self.h, _p(pcm, C.c_double), C.byref(prep), _p(cx, C.c_float), _p(cd, C.c_uint8), _p(co, C.c_int),
+            _p(cdd, C.c_double), co.size, C.c_double(radius), C.c_double(ratio), mode, C.byref(params), C.c_uint64(seed),
+            num_hyp, match_cap, _p(kept, C.c_int), C.byref(nk), _p(xl, C.c_double) if want_local else None,
+            _p(uv, C.c_double) if want_local else None, _p(mq, C.c_int), _p(mt, C.c_int), _p(md, C.c_float),
+            _p(inl, C.c_int), C.byref(res)))
+        n = min(res.n_matches, match_cap); k = nk.value
+        out = dict(kept=kept[:k].copy(), mq=mq[:n].copy(), mt=mt[:n].copy(), md=md[:n].copy(),
+                   inliers=inl[:res.n_inliers].copy(), T=np.array(res.T, np.float32).reshape(4, 4).T.copy(),
+                   best_ratio=res.best_ratio, inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used,
+                   n_filtered=res.n_filtered)
+        if want_local:
+            out["xyz_local"] = xl[:k].copy(); out["uv"] = uv[:k].copy()
+        return out
 
     def frame_to_map_resident(self):
         self._ck(self.lib.pslam_frame_to_map_resident(self.h))

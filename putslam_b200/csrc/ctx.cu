@@ -149,6 +149,13 @@ struct pslam_ctx {
     int last_H = 0;
     F2MState f2m;
     F2FState f2f;
+    // resident feature map (pslam_map_*): SoA, slot = caller's feature index
+    double* d_map_xyz = nullptr; uint8_t* d_map_desc = nullptr; int* d_map_oct = nullptr; double* d_map_det = nullptr;
+    float* d_map_axis = nullptr;
+    int map_cap = 0, map_n = 0;
+    // map_prepare_kernel's per-CTA counts (stamped with prep_epoch, so they are never reset)
+    unsigned long long* d_prep_counts = nullptr;
+    unsigned int prep_epoch = 0;
 };
 
 namespace {
@@ -329,6 +336,8 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
+    cudaFree(ctx->d_map_xyz); cudaFree(ctx->d_map_desc); cudaFree(ctx->d_map_oct); cudaFree(ctx->d_map_det);
+    cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts);
     if (ctx->ev_sweep0) cudaEventDestroy(ctx->ev_sweep0);
     if (ctx->ev_sweep1) cudaEventDestroy(ctx->ev_sweep1);
     cudaStreamDestroy(ctx->stream);
@@ -1044,6 +1053,17 @@ int pslam_frame_to_frame_resident(pslam_ctx* ctx) {
 }
 
 // ---- map-side preparation -------------------------------------------------------------------------
+static int next_prep_epoch(pslam_ctx* ctx, unsigned int* epoch) {
+    if (!ctx->d_prep_counts) {
+        const size_t bytes = sizeof(unsigned long long) * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1);
+        CK(cudaMalloc((void**)&ctx->d_prep_counts, bytes));
+        CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
+    }
+    if (++ctx->prep_epoch == 0) ctx->prep_epoch = 1;   // 0 is the value of a never-written slot
+    *epoch = ctx->prep_epoch;
+    return PSLAM_OK;
+}
+
 int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_axis, int M, const double camera_pose[16],
                       const pslam_map_prepare_params* params, int* kept_idx, double* xyz_local, double* uv, double* angles,
                       int* n_out) {
@@ -1063,11 +1083,13 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
     memcpy(ctx->h_in.p + o_a, view_axis, 12 * (size_t)M);
     CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
     int l = 0;
+    unsigned int epoch = 0;
+    TRY(next_prep_epoch(ctx, &epoch));
     CK(launch_map_prepare((const double*)(ctx->d_in.p + o_x), (const float*)(ctx->d_in.p + o_a), M, camera_pose, params->fx,
                           params->fy, params->cx, params->cy, params->image_w, params->image_h, params->max_angle,
                           params->max_z, (int*)(ctx->d_out.p + o_k), (double*)(ctx->d_out.p + o_xl),
                           (double*)(ctx->d_out.p + o_uv), (double*)(ctx->d_out.p + o_ang), (int*)(ctx->d_out.p + o_n),
-                          ctx->stream, &l));
+                          ctx->d_prep_counts, epoch, ctx->sm_count, ctx->stream, &l));
     ctx->launches += l;
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1077,6 +1099,183 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
     memcpy(uv, ctx->h_out.p + o_uv, 16 * (size_t)n);
     memcpy(angles, ctx->h_out.p + o_ang, 8 * (size_t)n);
     *n_out = n;
+    return PSLAM_OK;
+}
+
+// ---- resident feature map -------------------------------------------------------------------------
+// The map side of Matcher::matchXYZ kept in HBM between frames: per frame only the camera pose and
+// the current keypoints cross PCIe; the view-angle / depth filters, the move to the camera frame, the level
+// prediction, guided matching and RANSAC run back to back on the device.
+static int grow_map_array(pslam_ctx* ctx, void** p, size_t bytes_old, size_t bytes_new) {
+    void* np_ = nullptr;
+    CK(cudaMalloc(&np_, bytes_new));
+    if (*p && bytes_old) CK(cudaMemcpyAsync(np_, *p, bytes_old, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*p) CK(cudaFree(*p));
+    *p = np_;
+    return PSLAM_OK;
+}
+
+int pslam_map_reserve(pslam_ctx* ctx, int max_features) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (max_features < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_map_reserve: negative size");
+    if (max_features <= ctx->map_cap) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t o = (size_t)ctx->map_n, n = (size_t)max_features;
+    TRY(grow_map_array(ctx, (void**)&ctx->d_map_xyz, 24 * o, 24 * n));
+    TRY(grow_map_array(ctx, (void**)&ctx->d_map_desc, 32 * o, 32 * n));
+    TRY(grow_map_array(ctx, (void**)&ctx->d_map_oct, 4 * o, 4 * n));
+    TRY(grow_map_array(ctx, (void**)&ctx->d_map_det, 8 * o, 8 * n));
+    TRY(grow_map_array(ctx, (void**)&ctx->d_map_axis, 12 * o, 12 * n));
+    ctx->map_cap = max_features;
+    return PSLAM_OK;
+}
+
+int pslam_map_write(pslam_ctx* ctx, int first, int count, const double* xyz, const uint8_t* desc, const int* octave,
+                    const double* det_dist, const float* view_axis) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (first < 0 || count < 0 || first > ctx->map_n) return fail(ctx, PSLAM_ERR_ARG, "pslam_map_write: range must start inside or at the end of the map");
+    if (count == 0) return PSLAM_OK;
+    const bool extends = first + count > ctx->map_n;
+    if (extends && (!xyz || !desc || !octave || !det_dist || !view_axis))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_map_write: new features need every attribute");
+    if (first + count > ctx->map_cap) {
+        int want = ctx->map_cap + ctx->map_cap / 2;
+        if (want < first + count) want = first + count;
+        if (want < 1024) want = 1024;
+        TRY(pslam_map_reserve(ctx, want));
+    }
+    CK(cudaSetDevice(ctx->device));
+    Arena in;
+    const size_t c = (size_t)count;
+    const size_t o_x = in.take(24 * c), o_d = in.take(32 * c), o_o = in.take(4 * c), o_t = in.take(8 * c), o_a = in.take(12 * c);
+    TRY(ensure_host(ctx, ctx->h_in, in.off));
+    uint8_t* h = ctx->h_in.p;
+    const size_t f = (size_t)first;
+    if (xyz) { memcpy(h + o_x, xyz, 24 * c); CK(cudaMemcpyAsync(ctx->d_map_xyz + 3 * f, h + o_x, 24 * c, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (desc) { memcpy(h + o_d, desc, 32 * c); CK(cudaMemcpyAsync(ctx->d_map_desc + 32 * f, h + o_d, 32 * c, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (octave) { memcpy(h + o_o, octave, 4 * c); CK(cudaMemcpyAsync(ctx->d_map_oct + f, h + o_o, 4 * c, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (det_dist) { memcpy(h + o_t, det_dist, 8 * c); CK(cudaMemcpyAsync(ctx->d_map_det + f, h + o_t, 8 * c, cudaMemcpyHostToDevice, ctx->stream)); }
+    if (view_axis) { memcpy(h + o_a, view_axis, 12 * c); CK(cudaMemcpyAsync(ctx->d_map_axis + 3 * f, h + o_a, 12 * c, cudaMemcpyHostToDevice, ctx->stream)); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (extends) ctx->map_n = first + count;
+    return PSLAM_OK;
+}
+
+int pslam_map_truncate(pslam_ctx* ctx, int n) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n < 0 || n > ctx->map_n) return fail(ctx, PSLAM_ERR_ARG, "pslam_map_truncate: size outside [0, current size]");
+    ctx->map_n = n;
+    return PSLAM_OK;
+}
+
+int pslam_map_size(const pslam_ctx* ctx, int* n_features) {
+    if (!ctx || !n_features) return PSLAM_ERR_ARG;
+    *n_features = ctx->map_n;
+    return PSLAM_OK;
+}
+
+int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_pose[16], const pslam_map_prepare_params* prep,
+                                const float* cur_xyz, const uint8_t* cur_desc, const int* cur_octave,
+                                const double* cur_det_dist, int N, double radius, double accept_ratio, int distance_mode,
+                                const pslam_ransac_params* params, uint64_t seed, int num_hyp, int match_cap,
+                                int* kept_idx_out, int* n_kept_out, double* xyz_local_out, double* uv_out,
+                                int* match_query_out, int* match_train_out, float* match_dist_out, int* inlier_idx_out,
+                                pslam_frame_result* result) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!result || !camera_pose || !prep || !n_kept_out || N < 0 || match_cap <= 0)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_resident_map: bad argument");
+    memset(result, 0, sizeof(*result));
+    for (int i = 0; i < 16; ++i) result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    result->inlier_ratio = -1.0;
+    *n_kept_out = 0;
+    RansacDeviceParams rp;
+    TRY(make_ransac_params(ctx, params, seed, num_hyp, rp));
+    if (distance_mode != 0 && distance_mode != 1) return fail(ctx, PSLAM_ERR_ARG, "distance_mode must be 0 or 1");
+    if (N > 12000) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "N above 12000 current keypoints");
+    const int M = ctx->map_n;
+    if (M == 0) return PSLAM_OK;
+    if (!kept_idx_out || (N > 0 && (!cur_xyz || !cur_desc || !cur_octave || !cur_det_dist)) || !match_query_out ||
+        !match_train_out || !match_dist_out || !inlier_idx_out)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_resident_map: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    const int cap = match_cap;
+    const int Nn = N > 0 ? N : 1;
+    Arena in, out, work;
+    const size_t o_cx = in.take(12 * (size_t)Nn), o_cd = in.take(32 * (size_t)Nn), o_co = in.take(4 * (size_t)Nn);
+    const size_t o_cdet = in.take(8 * (size_t)Nn);
+    const size_t o_n = out.take(16), o_g = out.take(sizeof(int) * (2 + 3 * (size_t)cap));
+    const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
+    const size_t o_k = out.take(4 * (size_t)M), o_xl = out.take(24 * (size_t)M), o_uv = out.take(16 * (size_t)M);
+    const size_t o_ang = work.take(8 * (size_t)M), o_wd = work.take(32 * (size_t)M), o_wo = work.take(4 * (size_t)M);
+    const size_t o_wt = work.take(8 * (size_t)M), o_wx = work.take(12 * (size_t)M), o_wml = work.take(4 * (size_t)M);
+    const size_t o_wcl = work.take(4 * (size_t)Nn);
+    const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
+    const size_t o_cache = work.take(guided_cache_bytes(M));
+    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* h = ctx->h_in.p;
+    if (N > 0) {
+        memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N);
+        memcpy(h + o_co, cur_octave, 4 * (size_t)N); memcpy(h + o_cdet, cur_det_dist, 8 * (size_t)N);
+    }
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d = ctx->d_in.p; uint8_t* w = ctx->d_work.p; uint8_t* o = ctx->d_out.p;
+    int* d_n = (int*)(o + o_n);
+    int l = 0;
+    unsigned int epoch = 0;
+    TRY(next_prep_epoch(ctx, &epoch));
+    CK(launch_map_prepare(ctx->d_map_xyz, ctx->d_map_axis, M, camera_pose, prep->fx, prep->fy, prep->cx, prep->cy,
+                          prep->image_w, prep->image_h, prep->max_angle, prep->max_z, (int*)(o + o_k), (double*)(o + o_xl),
+                          (double*)(o + o_uv), (double*)(w + o_ang), d_n, ctx->d_prep_counts, epoch, ctx->sm_count,
+                          ctx->stream, &l, ctx->d_map_desc, w + o_wd, ctx->d_map_oct, (int*)(w + o_wo), ctx->d_map_det,
+                          (double*)(w + o_wt)));
+    int* gout = (int*)(o + o_g);
+    RansacWorkspace ws = bind_ransac(L, w, (int*)(o + o_res));
+    if (N > 0) {
+        const HostLevelTables& t = level_tables();
+        CK(launch_predict_levels((const double*)(o + o_xl), (const int*)(w + o_wo), (const double*)(w + o_wt), M,
+                                 (const float*)(d + o_cx), (const int*)(d + o_co), (const double*)(d + o_cdet), N, t.pow_tab,
+                                 t.lvl_tab, t.log_sf, (float*)(w + o_wx), (int*)(w + o_wml), (int*)(w + o_wcl), ctx->stream,
+                                 &l, d_n));
+        CK(launch_guided_match((const float*)(w + o_wx), w + o_wd, (const int*)(w + o_wml), M, (const float*)(d + o_cx),
+                               d + o_cd, (const int*)(w + o_wcl), N, sq_threshold(float_at_least(radius)), accept_ratio,
+                               distance_mode, (int*)(w + o_cnt), (int*)(w + o_best), w + o_cache, gout, cap, ctx->stream, &l,
+                               d_n));
+        CK(launch_ransac((const float*)(w + o_wx), (const float*)(d + o_cx), gout + 2, gout + 2 + cap, gout, 0, rp, ws,
+                         ctx->sm_count, ctx->stream, &l));
+        ctx->d_last_counts = ws.counts; ctx->last_H = ws.h_cap;
+    } else {
+        CK(cudaMemsetAsync(gout, 0, 8, ctx->stream));
+    }
+    ctx->launches += l;
+    ctx->f2m.valid = false;   // the work buffers of a previous pslam_frame_to_map were reused
+    const bool want_local = xyz_local_out || uv_out;
+    CK(cudaMemcpyAsync(ctx->h_out.p, o, want_local ? out.off : o_xl, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int nk = *(const int*)(ctx->h_out.p + o_n);
+    *n_kept_out = nk;
+    memcpy(kept_idx_out, ctx->h_out.p + o_k, 4 * (size_t)nk);
+    if (xyz_local_out) memcpy(xyz_local_out, ctx->h_out.p + o_xl, 24 * (size_t)nk);
+    if (uv_out) memcpy(uv_out, ctx->h_out.p + o_uv, 16 * (size_t)nk);
+    const int* g = (const int*)(ctx->h_out.p + o_g);
+    const int total = g[0];
+    const int n = total < cap ? total : cap;
+    result->n_matches = total;
+    if (n > 0) {
+        memcpy(match_query_out, g + 2, 4 * (size_t)n);
+        memcpy(match_train_out, g + 2 + cap, 4 * (size_t)n);
+        memcpy(match_dist_out, g + 2 + 2 * cap, 4 * (size_t)n);
+    }
+    if (total > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "guided matching produced %d matches, capacity %d", total, cap);
+    if (total == 0) return PSLAM_OK;
+    unpack_ransac_result((const int*)(ctx->h_out.p + o_res), result->T, inlier_idx_out, &result->n_inliers,
+                         &result->best_ratio, &result->hyp_used, &result->n_filtered);
+    std::vector<int> inl_t((size_t)result->n_inliers);
+    for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
+    result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
     return PSLAM_OK;
 }
 

@@ -31,7 +31,8 @@ struct GuidedArgs {
     const float* map_xyz;
     const uint4* map_desc;
     const int* map_level;
-    int M;
+    int M;                // number of map features, or their capacity when M_dev is set
+    const int* M_dev;     // device-resident count (map filtered on the device, mapprep.cu); nullptr = use M
     const float* cur_xyz;
     const uint4* cur_desc;
     const int* cur_level;
@@ -67,7 +68,8 @@ guided_collect_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const int gw = blockIdx.x * kGWarps + (threadIdx.x >> 5);
-    for (int j = gw; j < A.M; j += gridDim.x * kGWarps) {
+    const int M = A.M_dev ? min(*A.M_dev, A.M) : A.M;
+    for (int j = gw; j < M; j += gridDim.x * kGWarps) {
         const float px = A.map_xyz[3 * j], py = A.map_xyz[3 * j + 1], pz = A.map_xyz[3 * j + 2];
         const int lvl = A.map_level[j];
         const uint4* dj = A.map_desc + 2 * (size_t)j;
@@ -131,7 +133,7 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
     __shared__ int carry, perfect, n_ovf;
     __shared__ int ovf_list[1024];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = A.M;
+    const int M = A.M_dev ? min(*A.M_dev, A.M) : A.M;
     if (tid == 0) { carry = 0; perfect = 0; n_ovf = 0; }
     __syncthreads();
     int my_perfect = 0;
@@ -233,9 +235,10 @@ __global__ void predict_levels_kernel(const double* __restrict__ map_xyz, const 
                                       const double* __restrict__ map_det, int M, const float* __restrict__ cur_xyz,
                                       const int* __restrict__ cur_oct, const double* __restrict__ cur_det, int N,
                                       LevelTables T, float* __restrict__ map_xyz_f, int* __restrict__ map_level,
-                                      int* __restrict__ cur_level) {
+                                      int* __restrict__ cur_level, const int* __restrict__ M_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
+        if (M_dev && i >= *M_dev) return;   // M is the capacity; the filtered count lives on the device
         const double x = map_xyz[3 * i], y = map_xyz[3 * i + 1], z = map_xyz[3 * i + 2];
         const double cur_dist = __dsqrt_rn(x * x + y * y + z * z);
         map_level[i] = predict_level(T, map_oct[i], map_det[i], cur_dist);
@@ -251,13 +254,13 @@ __global__ void predict_levels_kernel(const double* __restrict__ map_xyz, const 
 cudaError_t launch_predict_levels(const double* d_map_xyz, const int* d_map_oct, const double* d_map_det, int M,
                                   const float* d_cur_xyz, const int* d_cur_oct, const double* d_cur_det, int N,
                                   const double* pow_tab, const int* lvl_tab, double log_sf, float* d_map_xyz_f,
-                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches) {
+                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches, const int* d_M) {
     if (M + N <= 0) return cudaSuccess;
     LevelTables T;
     for (int k = 0; k < 16; ++k) { T.pow_tab[k] = pow_tab[k]; T.lvl_tab[k] = lvl_tab[k]; }
     T.log_sf = log_sf;
     predict_levels_kernel<<<(M + N + 255) / 256, 256, 0, st>>>(d_map_xyz, d_map_oct, d_map_det, M, d_cur_xyz, d_cur_oct,
-                                                               d_cur_det, N, T, d_map_xyz_f, d_map_level, d_cur_level);
+                                                               d_cur_det, N, T, d_map_xyz_f, d_map_level, d_cur_level, d_M);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -267,9 +270,10 @@ size_t guided_cache_bytes(int M) { return sizeof(uint2) * (size_t)kCacheCap * (s
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
                                 float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
-                                int* d_out, int cap, cudaStream_t st, int* launches) {
+                                int* d_out, int cap, cudaStream_t st, int* launches, const int* d_M) {
     GuidedArgs A;
     A.map_xyz = d_map_xyz; A.map_desc = reinterpret_cast<const uint4*>(d_map_desc); A.map_level = d_map_level; A.M = M;
+    A.M_dev = d_M;
     A.cur_xyz = d_cur_xyz; A.cur_desc = reinterpret_cast<const uint4*>(d_cur_desc); A.cur_level = d_cur_level; A.N = N;
     A.sq_radius_f = sq_radius_f; A.accept_ratio = accept_ratio; A.mode = mode;
     // d_count: M counts followed by M+1 offsets

@@ -43,12 +43,13 @@ cudaError_t launch_lc_knn2_merge(const void* d_partial, int nparts, int nq, unsi
 cudaError_t launch_predict_levels(const double* d_map_xyz, const int* d_map_oct, const double* d_map_det, int M,
                                   const float* d_cur_xyz, const int* d_cur_oct, const double* d_cur_det, int N,
                                   const double* pow_tab, const int* lvl_tab, double log_sf, float* d_map_xyz_f,
-                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches);
+                                  int* d_map_level, int* d_cur_level, cudaStream_t st, int* launches,
+                                  const int* d_M = nullptr);   // d_M: device-resident feature count, M = capacity
 size_t guided_cache_bytes(int M);
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
                                 float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
-                                int* d_out, int cap, cudaStream_t st, int* launches);
+                                int* d_out, int cap, cudaStream_t st, int* launches, const int* d_M = nullptr);
 
 // ---- ransac.cu -------------------------------------------------------------------------------
 struct RansacDeviceParams {
@@ -105,6 +106,10 @@ cudaError_t launch_kabsch_batch(const double* d_A, const double* d_B, const int*
 cudaError_t launch_map_prepare(const double* d_xyz, const float* d_view_axis, int M, const double* pose_colmajor,
                                double fx, double fy, double cx, double cy, double img_w, double img_h, double max_angle,
                                double max_z, int* d_kept, double* d_xyz_local, double* d_uv, double* d_angles, int* d_n,
-                               cudaStream_t st, int* launches);
+                               unsigned long long* d_cta_counts /* >= sm_count slots, zeroed once */,
+                               unsigned int epoch /* != 0, different on every launch */, int sm_count, cudaStream_t st,
+                               int* launches, const uint8_t* d_desc_in = nullptr,
+                               uint8_t* d_desc_out = nullptr, const int* d_oct_in = nullptr, int* d_oct_out = nullptr,
+                               const double* d_det_in = nullptr, double* d_det_out = nullptr);
 
 }  // namespace pslam

@@ -81,6 +81,14 @@ def test_adapter_end_to_end(tmp_path, O):
         assert np.abs(Tm - r["T"]).max() <= 1e-5
         assert _rd(d, tag + "_ratio.bin", np.float64)[0] == O.point_inlier_ratio(t[r["inliers"]], t, 600)
 
+    # ---- resident map (uploadMapFeatures x2 + matchXYZResident, identity pose) == the host-buffer call ----
+    assert np.array_equal(_rd(d, "mapr_kept.bin", np.int32), np.arange(2000))
+    for f in ("matches_q", "matches_t", "inliers_q", "inliers_t"):
+        assert np.array_equal(_rd(d, f"mapr_{f}.bin", np.int32), _rd(d, f"map1_{f}.bin", np.int32)), f
+    assert np.array_equal(bits(_rd(d, "mapr_matches_d.bin", np.float32)), bits(_rd(d, "map1_matches_d.bin", np.float32)))
+    assert np.array_equal(bits(_rd(d, "mapr_T.bin", np.float32)), bits(_rd(d, "map1_T.bin", np.float32)))
+    assert _rd(d, "mapr_ratio.bin", np.float64)[0] == _rd(d, "map1_ratio.bin", np.float64)[0]
+
     # ---- Kabsch ----
     Tk = _rd(d, "kabsch_T.bin", np.float64).reshape(4, 4).T
     assert np.array_equal(bits(Tk[:3]), bits(O.kabsch(A, B)))
