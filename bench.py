@@ -300,7 +300,10 @@ def native_frontend_numbers(frames, warmup):
         except Exception as e:  # noqa: BLE001
             return {"unavailable": str(e)}
     r["note"] = ("C++ adapter, host buffers in, results out, per frame: frame_to_map = MatcherB200::matchXYZCore (guided "
-                 "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); vo_three_calls = performMatching "
+                 "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); frame_to_resident_map = "
+                 "MatcherB200::matchXYZResident, the same frame against the 5000-feature map kept in HBM (pose + current "
+                 "keypoints in, view-angle/depth filter + matching + RANSAC on the device; resident_equals_host_map checks "
+                 "the two answers are identical); vo_three_calls = performMatching "
                  "+ keypoints2Dto3D + RANSAC as three separate calls; vo_fused = MatcherB200::matchCore (one submission, "
                  "adaptive RANSAC), 1000 keypoints, 640x480 depth image uploaded every frame")
     return r
