@@ -31,6 +31,7 @@ __global__ void backproject_kernel(const float* __restrict__ uv, int n, const ui
                                    int stride, pslam_camera cam, int undistort, double depth_scale,
                                    float* __restrict__ uv_und, float* __restrict__ xyz, double* __restrict__ det_dist,
                                    double* __restrict__ cov, pslam_cov_params cp, int want_cov) {
+    chain_begin();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float u2 = uv[2 * i], v2 = uv[2 * i + 1];
@@ -358,9 +359,10 @@ cudaError_t launch_backproject(const float* d_uv, int n, const uint16_t* d_depth
     if (n <= 0) return cudaSuccess;
     pslam_cov_params cp = {};
     if (cov) cp = *cov;
-    backproject_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_uv, n, d_depth, W, H, stride, cam, undistort, depth_scale,
-                                                        d_uv_und, d_xyz, d_det_dist, d_cov, cp,
-                                                        (cov && d_cov) ? 1 : 0);
+    const cudaError_t e = launch_chained(backproject_kernel, dim3((unsigned)((n + 127) / 128)), dim3(128), 0, st, d_uv, n,
+                                         d_depth, W, H, stride, cam, undistort, depth_scale, d_uv_und, d_xyz, d_det_dist,
+                                         d_cov, cp, (cov && d_cov) ? 1 : 0);
+    if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -8,6 +8,30 @@
 #define PSLAM_SM_COUNT_HINT 148
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol, sm_90+).  A frame is a chain of short, latency-bound kernels on
+// one stream; launched with launch_chained(), kernel k+1 is scheduled while kernel k still runs and parks in
+// chain_begin() until k has completed and its writes are visible, so the launch latency (2-3 us per boundary) is
+// hidden.  Every chained kernel calls chain_begin() as its first statement in every thread: nothing is read or
+// written before the predecessor is done, and "k+1 complete" implies "k complete" along the whole chain.
+// After a kernel that was not launched this way (or a copy) the wait returns immediately.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void chain_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next kernel in the stream be scheduled
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // predecessor complete, memory visible
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier + TMA bulk copy (cp.async.bulk, SASS: UBLKCP).  Descriptor tiles are contiguous runs of
 // 32-byte rows, so the 1-D bulk form is the natural TMA shape: no tensor map needed.
 // ----------------------------------------------------------------------------------------------

@@ -176,6 +176,12 @@ int fail(pslam_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, PSLAM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// Stamped per-CTA sums of the grid-wide ordered compactions (mapprep.cu, guided.cu): slots [0, sm) belong to
+// map_prepare_kernel, [sm, 3 sm) to guided_emit_kernel.  Zeroed once; every launch gets a fresh non-zero epoch.
+int next_epoch(pslam_ctx* ctx, unsigned int* epoch);
+unsigned long long* prep_slots(pslam_ctx* ctx) { return ctx->d_prep_counts; }
+unsigned long long* emit_slots(pslam_ctx* ctx) { return ctx->d_prep_counts + (ctx->sm_count > 0 ? ctx->sm_count : 1); }
+
 int ensure_dev(pslam_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return PSLAM_OK;
     size_t want = bytes + bytes / 4 + 4096;
@@ -208,6 +214,18 @@ int ensure_host(pslam_ctx* ctx, HostBuf& b, size_t bytes) {
         int r__ = (x);             \
         if (r__ != PSLAM_OK) return r__; \
     } while (0)
+
+int next_epoch(pslam_ctx* ctx, unsigned int* epoch) {
+    if (!ctx->d_prep_counts) {
+        const size_t bytes = sizeof(unsigned long long) * 3 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1);
+        CK(cudaMalloc((void**)&ctx->d_prep_counts, bytes));
+        CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
+    }
+    if (++ctx->prep_epoch == 0) ctx->prep_epoch = 1;   // 0 is the value of a never-written slot
+    *epoch = ctx->prep_epoch;
+    return PSLAM_OK;
+}
+
 
 float float_at_least(double v) {  // smallest float >= v, so that (double)f < v  <=>  f < result
     float f = (float)v;
@@ -607,10 +625,13 @@ int pslam_match_guided_xyz(pslam_ctx* ctx, const float* map_xyz, const uint8_t* 
     CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* d = ctx->d_in.p;
     int l = 0;
+    unsigned int epoch = 0;
+    TRY(next_epoch(ctx, &epoch));
     CK(launch_guided_match((const float*)(d + o_mx), d + o_md, (const int*)(d + o_ml), M, (const float*)(d + o_cx),
                            d + o_cd, (const int*)(d + o_cl), N, sq_threshold(float_at_least(radius)), accept_ratio,
                            distance_mode, (int*)(ctx->d_work.p + o_cnt), (int*)(ctx->d_work.p + o_best),
-                           ctx->d_work.p + o_cache, (int*)(ctx->d_out.p + o_out), dcap, ctx->stream, &l));
+                           ctx->d_work.p + o_cache, (int*)(ctx->d_out.p + o_out), dcap, emit_slots(ctx), epoch,
+                           ctx->sm_count, ctx->stream, &l));
     ctx->launches += l;
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -754,8 +775,11 @@ static int enqueue_f2m(pslam_ctx* ctx) {
         CK(launch_predict_levels(s.map_xyz_d, s.map_oct, s.map_det, s.M, s.cur_xyz, s.cur_oct, s.cur_det, s.N, t.pow_tab,
                                  t.lvl_tab, t.log_sf, s.map_xyz_w, s.map_level_w, s.cur_level_w, ctx->stream, &l));
     }
+    unsigned int epoch = 0;
+    TRY(next_epoch(ctx, &epoch));
     CK(launch_guided_match(s.map_xyz, s.map_desc, s.map_level, s.M, s.cur_xyz, s.cur_desc, s.cur_level, s.N, s.sq_radius_f,
-                           s.ratio, s.mode, s.count, s.best, s.cache, s.gout, s.cap, ctx->stream, &l));
+                           s.ratio, s.mode, s.count, s.best, s.cache, s.gout, s.cap, emit_slots(ctx), epoch, ctx->sm_count,
+                           ctx->stream, &l));
     CK(launch_ransac(s.map_xyz, s.cur_xyz, s.gout + 2, s.gout + 2 + s.cap, s.gout, 0, s.rp, s.ws, ctx->sm_count,
                      ctx->stream, &l));
     ctx->launches += l;
@@ -1053,17 +1077,6 @@ int pslam_frame_to_frame_resident(pslam_ctx* ctx) {
 }
 
 // ---- map-side preparation -------------------------------------------------------------------------
-static int next_prep_epoch(pslam_ctx* ctx, unsigned int* epoch) {
-    if (!ctx->d_prep_counts) {
-        const size_t bytes = sizeof(unsigned long long) * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1);
-        CK(cudaMalloc((void**)&ctx->d_prep_counts, bytes));
-        CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
-    }
-    if (++ctx->prep_epoch == 0) ctx->prep_epoch = 1;   // 0 is the value of a never-written slot
-    *epoch = ctx->prep_epoch;
-    return PSLAM_OK;
-}
-
 int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_axis, int M, const double camera_pose[16],
                       const pslam_map_prepare_params* params, int* kept_idx, double* xyz_local, double* uv, double* angles,
                       int* n_out) {
@@ -1084,12 +1097,12 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
     CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
     int l = 0;
     unsigned int epoch = 0;
-    TRY(next_prep_epoch(ctx, &epoch));
+    TRY(next_epoch(ctx, &epoch));
     CK(launch_map_prepare((const double*)(ctx->d_in.p + o_x), (const float*)(ctx->d_in.p + o_a), M, camera_pose, params->fx,
                           params->fy, params->cx, params->cy, params->image_w, params->image_h, params->max_angle,
                           params->max_z, (int*)(ctx->d_out.p + o_k), (double*)(ctx->d_out.p + o_xl),
                           (double*)(ctx->d_out.p + o_uv), (double*)(ctx->d_out.p + o_ang), (int*)(ctx->d_out.p + o_n),
-                          ctx->d_prep_counts, epoch, ctx->sm_count, ctx->stream, &l));
+                          prep_slots(ctx), epoch, ctx->sm_count, ctx->stream, &l));
     ctx->launches += l;
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1226,24 +1239,26 @@ int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_pose[16], co
     int* d_n = (int*)(o + o_n);
     int l = 0;
     unsigned int epoch = 0;
-    TRY(next_prep_epoch(ctx, &epoch));
+    TRY(next_epoch(ctx, &epoch));
     CK(launch_map_prepare(ctx->d_map_xyz, ctx->d_map_axis, M, camera_pose, prep->fx, prep->fy, prep->cx, prep->cy,
                           prep->image_w, prep->image_h, prep->max_angle, prep->max_z, (int*)(o + o_k), (double*)(o + o_xl),
-                          (double*)(o + o_uv), (double*)(w + o_ang), d_n, ctx->d_prep_counts, epoch, ctx->sm_count,
+                          (double*)(o + o_uv), (double*)(w + o_ang), d_n, prep_slots(ctx), epoch, ctx->sm_count,
                           ctx->stream, &l, ctx->d_map_desc, w + o_wd, ctx->d_map_oct, (int*)(w + o_wo), ctx->d_map_det,
                           (double*)(w + o_wt)));
     int* gout = (int*)(o + o_g);
     RansacWorkspace ws = bind_ransac(L, w, (int*)(o + o_res));
     if (N > 0) {
         const HostLevelTables& t = level_tables();
+        unsigned int epoch2 = 0;
+        TRY(next_epoch(ctx, &epoch2));
         CK(launch_predict_levels((const double*)(o + o_xl), (const int*)(w + o_wo), (const double*)(w + o_wt), M,
                                  (const float*)(d + o_cx), (const int*)(d + o_co), (const double*)(d + o_cdet), N, t.pow_tab,
                                  t.lvl_tab, t.log_sf, (float*)(w + o_wx), (int*)(w + o_wml), (int*)(w + o_wcl), ctx->stream,
                                  &l, d_n));
         CK(launch_guided_match((const float*)(w + o_wx), w + o_wd, (const int*)(w + o_wml), M, (const float*)(d + o_cx),
                                d + o_cd, (const int*)(w + o_wcl), N, sq_threshold(float_at_least(radius)), accept_ratio,
-                               distance_mode, (int*)(w + o_cnt), (int*)(w + o_best), w + o_cache, gout, cap, ctx->stream, &l,
-                               d_n));
+                               distance_mode, (int*)(w + o_cnt), (int*)(w + o_best), w + o_cache, gout, cap, emit_slots(ctx),
+                               epoch2, ctx->sm_count, ctx->stream, &l, d_n));
         CK(launch_ransac((const float*)(w + o_wx), (const float*)(d + o_cx), gout + 2, gout + 2 + cap, gout, 0, rp, ws,
                          ctx->sm_count, ctx->stream, &l));
         ctx->d_last_counts = ws.counts; ctx->last_H = ws.h_cap;

@@ -60,6 +60,7 @@ __device__ __forceinline__ bool gate(const GuidedArgs& A, float px, float py, fl
 __global__ void __launch_bounds__(kGThreads)
 guided_collect_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict__ count, uint2* __restrict__ cache) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    chain_begin();
     float* sxyz = reinterpret_cast<float*>(smem_raw);
     int* slvl = reinterpret_cast<int*>(sxyz + 3 * (size_t)A.N);
     for (int i = threadIdx.x; i < 3 * A.N; i += kGThreads) sxyz[i] = A.cur_xyz[i];
@@ -122,43 +123,92 @@ guided_collect_kernel(GuidedArgs A, uint32_t* __restrict__ best, int* __restrict
     }
 }
 
-// Pass 2 (one CTA): exclusive scan of the counts, then every warp copies its features' cached matches to
-// their place in the (j, i)-ordered output; flagged features are recomputed.  header[0] = total,
-// header[1] = perfect matches (best value 0; reference matcher.cpp:729-731).
-__global__ void __launch_bounds__(1024, 1)
+// Pass 2 (grid): ordered emission.  Every CTA owns a contiguous range of map features: it sums the match counts of
+// its range, publishes the sum stamped with the launch's epoch, obtains its output offset from the stamped sums of all
+// preceding CTAs (decoupled look-back, see mapprep.cu), then scans its range 256 features at a time; the thread that
+// scanned feature j copies j's cached matches to their place in the (j, i)-ordered output, flagged features are
+// recomputed by whole warps.  header[0] = total, header[1] = perfect matches (best value 0; reference
+// matcher.cpp:729-731), both written by the last CTA.  The grid never exceeds the SM count (co-residency).
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads)
 guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* __restrict__ count,
                    const uint2* __restrict__ cache, int* __restrict__ offsets, int cap, int* __restrict__ header,
-                   int* __restrict__ out_q, int* __restrict__ out_t, float* __restrict__ out_d) {
-    __shared__ int warp_tot[32];
-    __shared__ int carry, perfect, n_ovf;
-    __shared__ int ovf_list[1024];
+                   int* __restrict__ out_q, int* __restrict__ out_t, float* __restrict__ out_d, int per_cta,
+                   unsigned long long* __restrict__ cta_sums /* 2 x gridDim.x: matches | perfect */, unsigned int epoch) {
+    constexpr int kW = kEmitThreads / 32;
+    __shared__ int warp_tot[kW], warp_perf[kW];
+    __shared__ int s_base, n_ovf;
+    __shared__ int ovf_list[kEmitThreads];
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int M = A.M_dev ? min(*A.M_dev, A.M) : A.M;
-    if (tid == 0) { carry = 0; perfect = 0; n_ovf = 0; }
-    __syncthreads();
-    int my_perfect = 0;
+    const int lo = min(M, (int)blockIdx.x * per_cta), hi = min(M, lo + per_cta);
     const uint32_t lt = (1u << lane) - 1u;
-    for (int base = 0; base < M; base += 1024) {
+
+    // range totals
+    int mine = 0, my_perfect = 0;
+    for (int j = lo + tid; j < hi; j += kEmitThreads) {
+        mine += count[j] & 0x7fffffff;
+        my_perfect += (best[j] >> 16) == 0u ? 1 : 0;
+    }
+    mine = (int)warp_add_u32((uint32_t)mine);
+    my_perfect = (int)warp_add_u32((uint32_t)my_perfect);
+    if (lane == 0) { warp_tot[warp] = mine; warp_perf[warp] = my_perfect; }
+    if (tid == 0) n_ovf = 0;
+    __syncthreads();
+    if (warp == 0) {
+        int total = 0, perfect = 0;
+#pragma unroll
+        for (int w = 0; w < kW; ++w) { total += warp_tot[w]; perfect += warp_perf[w]; }
+        volatile unsigned long long* sums = cta_sums;
+        volatile unsigned long long* perfs = cta_sums + gridDim.x;
+        if (lane == 0) {
+            sums[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)total;
+            perfs[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)perfect;
+        }
+        int before = 0, perf_before = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+            unsigned long long v, p;
+            do { v = sums[b]; } while ((unsigned int)(v >> 32) != epoch);
+            do { p = perfs[b]; } while ((unsigned int)(p >> 32) != epoch);
+            before += (int)(unsigned int)(v & 0xffffffffu);
+            perf_before += (int)(unsigned int)(p & 0xffffffffu);
+        }
+        before = (int)warp_add_u32((uint32_t)before);
+        perf_before = (int)warp_add_u32((uint32_t)perf_before);
+        if (lane == 0) {
+            s_base = before;
+            if (blockIdx.x == gridDim.x - 1) {
+                offsets[M] = before + total; header[0] = before + total; header[1] = perf_before + perfect;
+            }
+        }
+    }
+    __syncthreads();
+
+    int carry = s_base;
+    for (int base = lo; base < hi; base += kEmitThreads) {
         const int j = base + tid;
-        const int cj = (j < M) ? count[j] : 0;
+        const int cj = (j < hi) ? count[j] : 0;
         const int c = cj & 0x7fffffff;
-        if (j < M && (best[j] >> 16) == 0u) ++my_perfect;
         int incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
+        __syncthreads();   // warp_tot / ovf_list of the previous pass consumed
         if (lane == 31) warp_tot[warp] = incl;
+        if (tid == 0) n_ovf = 0;
         __syncthreads();
         int woff = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
+#pragma unroll
+        for (int w = 0; w < kW; ++w) {
             const int cw = warp_tot[w];
             if (w < warp) woff += cw;
             tot += cw;
         }
         const int off = carry + woff + incl - c;
-        if (j < M) {
+        if (j < hi) {
             offsets[j] = off;
             if (cj >= 0) {  // the thread that scanned feature j also copies its (few) cached matches
                 for (int e = 0; e < c; ++e) {
@@ -167,17 +217,15 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
                     if (pos < cap) { out_q[pos] = j; out_t[pos] = (int)m.x; out_d[pos] = (float)m.y; }
                 }
             } else if (c > 0) {
-                const int slot = atomicAdd(&n_ovf, 1);
-                if (slot < 1024) ovf_list[slot] = j;
+                ovf_list[atomicAdd(&n_ovf, 1)] = j;   // at most kEmitThreads flagged features per pass
             }
         }
-        __syncthreads();
-        if (tid == 0) carry += tot;
+        carry += tot;
         __syncthreads();
         // features with more candidates than the cache holds: recomputed by whole warps, in any order
         // (their output positions are fixed by `offsets`)
-        const int novf = n_ovf < 1024 ? n_ovf : 1024;
-        for (int a = warp; a < novf; a += 32) {
+        const int novf = n_ovf;
+        for (int a = warp; a < novf; a += kW) {
             const int jj = ovf_list[a];
             const float px = A.map_xyz[3 * jj], py = A.map_xyz[3 * jj + 1], pz = A.map_xyz[3 * jj + 2];
             const int lvl = A.map_level[jj];
@@ -200,14 +248,7 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
                 run += __popc(bal);
             }
         }
-        __syncthreads();
-        if (tid == 0) n_ovf = 0;
-        __syncthreads();
     }
-    my_perfect = (int)warp_add_u32((uint32_t)my_perfect);
-    if (lane == 0 && my_perfect) atomicAdd(&perfect, my_perfect);
-    __syncthreads();
-    if (tid == 0) { offsets[M] = carry; header[0] = carry; header[1] = perfect; }
 }
 
 // Predicted ORB pyramid levels (reference src/Matcher/matcher.cpp:639-651 for current keypoints, :682-692 for map
@@ -236,6 +277,7 @@ __global__ void predict_levels_kernel(const double* __restrict__ map_xyz, const 
                                       const int* __restrict__ cur_oct, const double* __restrict__ cur_det, int N,
                                       LevelTables T, float* __restrict__ map_xyz_f, int* __restrict__ map_level,
                                       int* __restrict__ cur_level, const int* __restrict__ M_dev) {
+    chain_begin();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
         if (M_dev && i >= *M_dev) return;   // M is the capacity; the filtered count lives on the device
@@ -259,8 +301,10 @@ cudaError_t launch_predict_levels(const double* d_map_xyz, const int* d_map_oct,
     LevelTables T;
     for (int k = 0; k < 16; ++k) { T.pow_tab[k] = pow_tab[k]; T.lvl_tab[k] = lvl_tab[k]; }
     T.log_sf = log_sf;
-    predict_levels_kernel<<<(M + N + 255) / 256, 256, 0, st>>>(d_map_xyz, d_map_oct, d_map_det, M, d_cur_xyz, d_cur_oct,
-                                                               d_cur_det, N, T, d_map_xyz_f, d_map_level, d_cur_level, d_M);
+    const cudaError_t e = launch_chained(predict_levels_kernel, dim3((unsigned)((M + N + 255) / 256)), dim3(256), 0, st,
+                                         d_map_xyz, d_map_oct, d_map_det, M, d_cur_xyz, d_cur_oct, d_cur_det, N, T,
+                                         d_map_xyz_f, d_map_level, d_cur_level, d_M);
+    if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -270,7 +314,8 @@ size_t guided_cache_bytes(int M) { return sizeof(uint2) * (size_t)kCacheCap * (s
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
                                 float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
-                                int* d_out, int cap, cudaStream_t st, int* launches, const int* d_M) {
+                                int* d_out, int cap, unsigned long long* d_cta_sums, unsigned int epoch, int sm_count,
+                                cudaStream_t st, int* launches, const int* d_M) {
     GuidedArgs A;
     A.map_xyz = d_map_xyz; A.map_desc = reinterpret_cast<const uint4*>(d_map_desc); A.map_level = d_map_level; A.M = M;
     A.M_dev = d_M;
@@ -289,10 +334,23 @@ cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_des
     if (smem > 48 * 1024) {
         if ((e = cudaFuncSetAttribute(guided_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     }
-    guided_collect_kernel<<<grid, kGThreads, smem, st>>>(A, reinterpret_cast<uint32_t*>(d_best), d_count,
-                                                         reinterpret_cast<uint2*>(d_cache));
-    guided_emit_kernel<<<1, 1024, 0, st>>>(A, reinterpret_cast<const uint32_t*>(d_best), d_count,
-                                           reinterpret_cast<const uint2*>(d_cache), d_offsets, cap, d_out, out_q, out_t, out_d);
+    if ((e = launch_chained(guided_collect_kernel, dim3((unsigned)grid), dim3(kGThreads), smem, st, A,
+                            reinterpret_cast<uint32_t*>(d_best), d_count, reinterpret_cast<uint2*>(d_cache))) != cudaSuccess)
+        return e;
+    // emission: contiguous feature ranges (a multiple of the CTA size), at most one CTA per SM
+    int egrid = (M + kEmitThreads - 1) / kEmitThreads;
+    if (egrid > sm_count) egrid = sm_count;
+    if (egrid < 1) egrid = 1;
+    int per_cta = (M + egrid - 1) / egrid;
+    per_cta = (per_cta + kEmitThreads - 1) / kEmitThreads * kEmitThreads;
+    if (per_cta < kEmitThreads) per_cta = kEmitThreads;
+    egrid = (M + per_cta - 1) / per_cta;
+    if (egrid < 1) egrid = 1;
+    if ((e = launch_chained(guided_emit_kernel, dim3((unsigned)egrid), dim3(kEmitThreads), 0, st, A,
+                            reinterpret_cast<const uint32_t*>(d_best), (const int*)d_count,
+                            reinterpret_cast<const uint2*>(d_cache), d_offsets, cap, d_out, out_q, out_t, out_d, per_cta,
+                            d_cta_sums, epoch)) != cudaSuccess)
+        return e;
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -96,6 +96,7 @@ bf_tile_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
     uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + (size_t)t_per_cta * 32);  // NW * kTT
     uint64_t* bar = reinterpret_cast<uint64_t*>(partial + NW * kTT);
 
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * t_per_cta;
     const int tcnt = min(t_per_cta, nt - t0);
@@ -144,6 +145,7 @@ bf_finalize_kernel(const uint32_t* __restrict__ rowmin_g, const uint32_t* __rest
                    int* __restrict__ out) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -768,10 +770,12 @@ cudaError_t launch_bf_mutual(const uint8_t* d_query, int nq, const uint8_t* d_tr
     const size_t smem = (size_t)tpc * 32 + sizeof(uint32_t) * (kNT / 32) * kTT + 16;
     const uint4* q4 = reinterpret_cast<const uint4*>(d_query);
     const uint4* t4 = reinterpret_cast<const uint4*>(d_train);
-    if (rq == 1) bf_tile_kernel<1, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
-    else if (rq == 2) bf_tile_kernel<2, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
-    else bf_tile_kernel<4, kNT><<<grid, kNT, smem, st>>>(q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
-    bf_finalize_kernel<<<1, 1024, 0, st>>>(d_rowmin, d_colmin, nq, cap, d_out);
+    if (rq == 1) e = launch_chained(bf_tile_kernel<1, kNT>, grid, dim3(kNT), smem, st, q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else if (rq == 2) e = launch_chained(bf_tile_kernel<2, kNT>, grid, dim3(kNT), smem, st, q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    else e = launch_chained(bf_tile_kernel<4, kNT>, grid, dim3(kNT), smem, st, q4, nq, t4, nt, tpc, d_rowmin, d_colmin);
+    if (e != cudaSuccess) return e;
+    if ((e = launch_chained(bf_finalize_kernel, dim3(1), dim3(1024), 0, st, (const uint32_t*)d_rowmin,
+                            (const uint32_t*)d_colmin, nq, cap, d_out)) != cudaSuccess) return e;
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -49,7 +49,9 @@ size_t guided_cache_bytes(int M);
 cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_desc, const int* d_map_level, int M,
                                 const float* d_cur_xyz, const uint8_t* d_cur_desc, const int* d_cur_level, int N,
                                 float sq_radius_f, double accept_ratio, int mode, int* d_count, int* d_best, void* d_cache,
-                                int* d_out, int cap, cudaStream_t st, int* launches, const int* d_M = nullptr);
+                                int* d_out, int cap, unsigned long long* d_cta_sums /* >= 2 x sm_count slots, zeroed once */,
+                                unsigned int epoch /* != 0, different on every launch */, int sm_count, cudaStream_t st,
+                                int* launches, const int* d_M = nullptr);
 
 // ---- ransac.cu -------------------------------------------------------------------------------
 struct RansacDeviceParams {

@@ -72,6 +72,7 @@ map_prepare_kernel(const double* __restrict__ xyz, const float* __restrict__ vie
                    unsigned long long* __restrict__ cta_counts, unsigned int epoch) {
     __shared__ int warp_tot[kPrepThreads / 32];
     __shared__ int s_base;
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lo = blockIdx.x * per_cta, hi = min(M, lo + per_cta);
 
@@ -183,8 +184,10 @@ cudaError_t launch_map_prepare(const double* d_xyz, const float* d_view_axis, in
     per_cta = (per_cta + kPrepThreads - 1) / kPrepThreads * kPrepThreads;
     grid = (M + per_cta - 1) / per_cta;
     if (grid < 1) grid = 1;
-    map_prepare_kernel<<<grid, kPrepThreads, 0, st>>>(d_xyz, d_view_axis, M, per_cta, A, d_kept, d_xyz_local, d_uv, d_angles,
-                                                      d_n, G, d_cta_counts, epoch);
+    const cudaError_t e = launch_chained(map_prepare_kernel, dim3((unsigned)grid), dim3(kPrepThreads), 0, st, d_xyz,
+                                         d_view_axis, M, per_cta, A, d_kept, d_xyz_local, d_uv, d_angles, d_n, G,
+                                         d_cta_counts, epoch);
+    if (e != cudaSuccess) return e;
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

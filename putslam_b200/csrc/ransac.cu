@@ -32,6 +32,7 @@ ransac_filter_kernel(const float* __restrict__ prev, const float* __restrict__ c
                      float* __restrict__ pts, int* __restrict__ keep, int* __restrict__ n_filtered) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int m = d_m ? *d_m : m_host;
     if (m > m_cap) m = m_cap;
@@ -162,6 +163,7 @@ constexpr int kModelThreads = 64;
 __global__ void __launch_bounds__(kModelThreads)
 ransac_model_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ n_filtered, int min_matches,
                     uint32_t seed_lo, uint32_t seed_hi, int H, int* __restrict__ counts, float* __restrict__ models) {
+    chain_begin();
     const int mf = *n_filtered;
     if (mf < min_matches || mf < 3) return;
     const int h = blockIdx.x * kModelThreads + threadIdx.x;
@@ -188,6 +190,7 @@ ransac_score_kernel(const float* __restrict__ pts, int m_cap, const int* __restr
     __shared__ float4 sA[kScoreTile];   // prev.x prev.y prev.z cur.x
     __shared__ float2 sB[kScoreTile];   // cur.y cur.z
     __shared__ int s_cnt[32];
+    chain_begin();
     const int mf = *n_filtered;
     if (mf < min_matches || mf < 3) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -275,6 +278,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     __shared__ float s_R[9], s_t[3];
     __shared__ int s_ok;
 
+    chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mf = *n_filtered;
     float* Tout = reinterpret_cast<float*>(result + 4);
@@ -333,7 +337,14 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
                 if (key > loc) loc = key;
             }
         }
-        if (loc) atomicMax(&best_key, loc);
+        // warp maximum first: a 64-bit shared atomicMax is a CAS loop, and 1024 threads contending on one address
+        // made this step the longest of the kernel
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, loc, d);
+            if (o > loc) loc = o;
+        }
+        if (lane == 0 && loc) atomicMax(&best_key, loc);
         __syncthreads();
         if (tid == 0 && best_key) {
             s_cnt = (int)(best_key >> 32);
@@ -511,10 +522,12 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     // budget); plain fixed-H is a parallel first-max
     const int adaptive = P.num_hyp <= 0 ? 1 : (P.stop_rule == 1 ? 2 : 0);
     const int H = adaptive ? 487 : P.num_hyp;  // int(log(0.02)/log(1-0.2^3)), reference RANSAC.cpp:30
-    ransac_filter_kernel<<<1, 1024, 0, st>>>(d_prev, d_cur, d_mq, d_mt, d_m, m_host, ws.m_cap, ws.pts, ws.keep,
-                                             ws.n_filtered);
-    ransac_model_kernel<<<(H + kModelThreads - 1) / kModelThreads, kModelThreads, 0, st>>>(
-        ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, P.seed_lo, P.seed_hi, H, ws.counts, ws.models);
+    cudaError_t e;
+    if ((e = launch_chained(ransac_filter_kernel, dim3(1), dim3(1024), 0, st, d_prev, d_cur, d_mq, d_mt, d_m, m_host,
+                            ws.m_cap, ws.pts, ws.keep, ws.n_filtered)) != cudaSuccess) return e;
+    if ((e = launch_chained(ransac_model_kernel, dim3((unsigned)((H + kModelThreads - 1) / kModelThreads)),
+                            dim3(kModelThreads), 0, st, (const float*)ws.pts, ws.m_cap, (const int*)ws.n_filtered,
+                            P.min_matches, P.seed_lo, P.seed_hi, H, ws.counts, ws.models)) != cudaSuccess) return e;
     // 32 hypotheses per CTA; the match list is cut into as many slices as put up to 4 CTAs on every SM, but
     // no slice shorter than ~64 matches (the filtered count is only known on the device: bound it by the number of
     // matches handed in, or by the capacity of the list when that number is device-resident too)
@@ -525,20 +538,20 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     if (slices > max_slices) slices = max_slices;
     if (slices > 64) slices = 64;
     if (slices < 1) slices = 1;
-    ransac_score_kernel<<<dim3((unsigned)hyp_ctas, (unsigned)slices), kScoreThreads, 0, st>>>(
-        ws.pts, ws.m_cap, ws.n_filtered, P.min_matches, S, H, ws.counts, ws.models);
+    if ((e = launch_chained(ransac_score_kernel, dim3((unsigned)hyp_ctas, (unsigned)slices), dim3(kScoreThreads), 0, st,
+                            (const float*)ws.pts, ws.m_cap, (const int*)ws.n_filtered, P.min_matches, S, H, ws.counts,
+                            (const float*)ws.models)) != cudaSuccess) return e;
     // shared-memory staging of the winner's inliers for the refit: up to 8192 inliers (192 KB)
     int stage_cap = ws.m_cap < 8192 ? ws.m_cap : 8192;
     const size_t sel_smem = sizeof(float) * 6 * (size_t)stage_cap;
     // per-device function attribute; setting it again is harmless, so no cross-thread state is kept
-    {
-        cudaError_t e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4);
-        if (e != cudaSuccess) return e;
-    }
-    ransac_select_kernel<<<1, kSelThreads, sel_smem, st>>>(ws.pts, ws.m_cap, ws.keep, ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf,
-                                                           P.min_matches, P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
-                                                           ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap,
-                                                           ws.result);
+    if ((e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4)) != cudaSuccess)
+        return e;
+    if ((e = launch_chained(ransac_select_kernel, dim3(1), dim3(kSelThreads), sel_smem, st, ws.pts, ws.m_cap, ws.keep,
+                            ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf, P.min_matches,
+                            P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
+                            ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap, ws.result)) != cudaSuccess)
+        return e;
     if (launches) *launches += 4;
     return cudaGetLastError();
 }
