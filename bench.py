@@ -66,6 +66,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout=15.0):
+        """block until nvidia-smi has delivered its first sample (its start-up on a fresh box can take seconds)"""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.lines and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
     def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -367,12 +373,12 @@ def run_ours(args):
     # ---- device-timed value: kernels + collective, inputs resident in HBM ----
     total_desc = float(db["kf_off"][-1])
     cmps_per_step = NQ * total_desc
-    for i in range(args.warmup):
-        flush_l2(); ctx.lc_query_sharded_resident(TAU, TOPK)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    for i in range(args.warmup):
+        flush_l2(); ctx.lc_query_sharded_resident(TAU, TOPK)
+    sampler.wait_first()
+    barrier()
     launches0 = ctx.launches
     t_wall0 = time.perf_counter()
     dev_ms, sweep_ms = 0.0, []
