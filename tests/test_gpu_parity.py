@@ -162,6 +162,36 @@ def test_guided_match_many_candidates(ctx, O):
     assert q.size > 700
 
 
+def test_guided_match_depth_bins_adversarial(ctx, O):
+    """The matcher sorts the current keypoints into depth bins (0.125 m, z in [0, 8)) and visits only the bins a
+    feature's sphere reaches: coordinates outside the binned range, NaN / infinite depths, every keypoint in one bin,
+    features exactly on bin edges, radii from one bin to the whole range and a NaN radius must all give the
+    reference's answer."""
+    rng = np.random.default_rng(77)
+    M, N = 900, 700
+    zs = np.concatenate([rng.uniform(-1.0, 0.2, 80), rng.uniform(7.5, 12.0, 80), np.full(150, 2.0),
+                         np.arange(60) * 0.125, rng.uniform(0.5, 6.0, N - 370)])
+    cur = np.stack([rng.uniform(-1, 1, N), rng.uniform(-1, 1, N), zs], 1).astype(np.float32)
+    cur[5, 2] = np.nan; cur[6, 2] = np.inf; cur[7, 2] = -np.inf; cur[8, 0] = np.nan
+    src = rng.integers(0, N, M)
+    mxyz = cur[src].astype(np.float64) + rng.normal(0, 0.03, (M, 3))
+    mxyz[::7] = cur[src[::7]]                                   # exact coincidences, incl. the bin-edge depths
+    mxyz[3] = [0.0, 0.0, np.nan]; mxyz[4] = [0.0, 0.0, 1e9]; mxyz[9] = [0.0, 0.0, -1e9]
+    cur_desc = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    map_desc = cur_desc[src] ^ (rng.random((M, 32)) < 0.02).astype(np.uint8)
+    ml = rng.integers(0, 8, M).astype(np.int32); cl = np.clip(ml[rng.integers(0, M, N)] + rng.integers(-1, 2, N), 0, 7).astype(np.int32)
+    n_total = 0
+    with np.errstate(invalid="ignore"):
+        for mode in (0, 1):
+            for radius, ratio in ((0.05, 0.55), (0.12, 0.55), (0.3, 0.3), (1.5, 0.8), (20.0, 0.9), (float("nan"), 0.5)):
+                out = ctx.match_guided_xyz(mxyz, map_desc, ml, cur, cur_desc, cl, radius, ratio, mode, cap=700000)
+                q, t, d, perfect = O.guided_match(mxyz, map_desc, ml, cur, cur_desc, cl, radius, ratio, mode)
+                assert out["total"] == q.size and out["perfect"] == perfect, (mode, radius)
+                assert np.array_equal(out["q"], q) and np.array_equal(out["t"], t) and np.array_equal(out["d"], d), (mode, radius)
+                n_total += q.size
+    assert n_total > 5000
+
+
 def test_guided_match_capacity_and_empty(ctx, O):
     from putslam_b200 import host, synth
     mf = synth.map_frame(M=600, N=300, n_reobs=200, seed=9)
