@@ -300,7 +300,7 @@ def inverse4(m):
     return r
 
 
-def ransac(prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False):
+def ransac(prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False, counts_cap=None):
     """-> dict(T[4,4] f32, inliers int32[], best_ratio, hyp_used, counts)"""
     prev = np.ascontiguousarray(prev, np.float32).reshape(-1, 3)
     cur = np.ascontiguousarray(cur, np.float32).reshape(-1, 3)
@@ -311,7 +311,7 @@ def ransac(prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False)
     T = np.empty((4, 4), np.float32)
     inl = np.empty(max(1, m), np.int32)
     n_inl = C.c_int(0); best = C.c_double(0); used = C.c_int(0)
-    cap = max(num_hyp, 487) if want_counts else 0
+    cap = (counts_cap or max(num_hyp, 487)) if want_counts else 0
     counts = np.full(max(1, cap), -2, np.int32)
     lib().orc_ransac(_p(prev, C.c_float), prev.shape[0], _p(cur, C.c_float), cur.shape[0],
                      _p(mq, C.c_int), _p(mt, C.c_int), m, C.byref(params), C.c_uint64(seed), num_hyp,

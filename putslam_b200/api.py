@@ -242,7 +242,7 @@ class Context:
                     truncated=(r == ERR_CAPACITY))
 
     # ---- stage 3 ----
-    def ransac_estimate(self, prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False):
+    def ransac_estimate(self, prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False, counts_cap=None):
         prev = _arr(prev, np.float32, 3); cur = _arr(cur, np.float32, 3)
         mq = _arr(mq, np.int32); mt = _arr(mt, np.int32)
         m = mq.size
@@ -256,7 +256,7 @@ class Context:
                                                 C.byref(used)))
         counts = None
         if want_counts:
-            cap = max(num_hyp, 487)
+            cap = counts_cap or max(num_hyp, 487)
             counts = np.empty(cap, np.int32); n = C.c_int(0)
             self._ck(self.lib.pslam_ransac_last_counts(self.h, _p(counts, C.c_int), cap, C.byref(n)))
             counts = counts[:n.value]

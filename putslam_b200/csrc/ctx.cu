@@ -243,6 +243,16 @@ float sq_threshold(float thr_f) {  // smallest float T such that sqrtf(T) >= thr
     return t;
 }
 
+// computeRANSACIteration (reference src/TransformEst/RANSAC.cpp:457-461) with the host libm; the conversion to int
+// saturates (the reference's is undefined behaviour out of range -- DESIGN.md, deliberate divergences)
+int ransac_iterations_host(double w) {
+    const double v = log(1 - 0.98) / log(1 - pow(w, 3.0));
+    if (v != v) return (int)0x80000000;
+    if (v >= 2147483648.0) return 0x7fffffff;
+    if (v <= -2147483649.0) return (int)0x80000000;
+    return (int)v;
+}
+
 int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t seed, int num_hyp, RansacDeviceParams& o) {
     if (!p) return fail(ctx, PSLAM_ERR_ARG, "ransac params is NULL");
     if (p->used_pairs != 3) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "used_pairs must be 3 (got %d)", p->used_pairs);
@@ -262,6 +272,7 @@ int make_ransac_params(pslam_ctx* ctx, const pslam_ransac_params* p, uint64_t se
     o.num_hyp = num_hyp;
     o.stop_rule = ctx->stop_rule;
     o.usac_conf = ctx->usac_conf;
+    o.iters_min_ratio = ransac_iterations_host(p->minimal_inlier_ratio_threshold);
     return PSLAM_OK;
 }
 
@@ -270,10 +281,10 @@ struct RansacLayout {
     size_t pts, keep, nfil, counts, models, result;
     int m_cap, h_cap;
 };
-RansacLayout plan_ransac(Arena& A, int m_cap, int num_hyp) {
+RansacLayout plan_ransac(Arena& A, int m_cap, const RansacDeviceParams& rp) {
     RansacLayout L;
     L.m_cap = m_cap > 0 ? m_cap : 1;
-    L.h_cap = num_hyp > 0 ? num_hyp : 487;
+    L.h_cap = ransac_hypothesis_budget(rp);
     L.pts = A.take(sizeof(float) * 6 * (size_t)L.m_cap);
     L.keep = A.take(sizeof(int) * 2 * (size_t)L.m_cap);
     L.nfil = A.take(sizeof(int) * 4);
@@ -308,12 +319,22 @@ double point_inlier_ratio(const int* inl_t, int n_inl, const int* all_t, int n_a
 
 void unpack_ransac_result(const int* res, float* T_out, int* inl_out, int* n_inl, double* best, int* used, int* nfil) {
     const int n = res[0];
+    double ratio = 0.0;
+    memcpy(&ratio, res + 20, sizeof(double));
     if (n_inl) *n_inl = n;
-    if (used) *used = res[1];
+    if (used) {
+        *used = res[1];
+        if (res[1] < 0) {   // adaptive reference rule: the loop bound after the last improvement, finished here (kernels.h)
+            const int b = ransac_iterations_host(ratio);
+            int bound = res[24] < b ? res[24] : b;
+            if (bound > res[26]) bound = res[26];   // hypotheses actually scored
+            *used = res[25] + 1 > bound ? res[25] + 1 : bound;
+        }
+    }
     if (nfil) *nfil = res[2];
     if (T_out) memcpy(T_out, res + 4, sizeof(float) * 16);
-    if (best) memcpy(best, res + 20, sizeof(double));
-    if (inl_out && n > 0) memcpy(inl_out, res + 24, sizeof(int) * (size_t)n);
+    if (best) *best = ratio;
+    if (inl_out && n > 0) memcpy(inl_out, res + kRansacHdrInts, sizeof(int) * (size_t)n);
 }
 
 }  // namespace
@@ -672,7 +693,7 @@ int pslam_ransac_estimate(pslam_ctx* ctx, const float* prev, int n_prev, const f
     const size_t o_p = in.take(12 * (size_t)n_prev), o_c = in.take(12 * (size_t)n_cur);
     const size_t o_mq = in.take(4 * (size_t)m), o_mt = in.take(4 * (size_t)m);
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(m));
-    RansacLayout L = plan_ransac(work, m, num_hyp);
+    RansacLayout L = plan_ransac(work, m, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -822,7 +843,7 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
     const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
     const size_t o_cache = work.take(guided_cache_bytes(M));
-    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    RansacLayout L = plan_ransac(work, cap, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -958,7 +979,7 @@ int pslam_frame_to_frame(pslam_ctx* ctx, const uint8_t* prev_desc, const float* 
     const size_t o_m = out.take(sizeof(int) * (1 + 3 * (size_t)cap));
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
     const size_t o_row = work.take(4 * (size_t)np), o_col = work.take(4 * (size_t)n_cur);
-    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    RansacLayout L = plan_ransac(work, cap, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -1033,7 +1054,7 @@ int pslam_loop_closure_pair(pslam_ctx* ctx, const uint8_t* desc0, const float* x
     const size_t o_m = out.take(sizeof(int) * (1 + 3 * (size_t)cap));
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
     const size_t o_row = work.take(4 * (size_t)n0), o_col = work.take(4 * (size_t)n1);
-    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    RansacLayout L = plan_ransac(work, cap, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -1225,7 +1246,7 @@ int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_pose[16], co
     const size_t o_wcl = work.take(4 * (size_t)Nn);
     const size_t o_cnt = work.take(sizeof(int) * (2 * (size_t)M + 1)), o_best = work.take(sizeof(int) * (size_t)M);
     const size_t o_cache = work.take(guided_cache_bytes(M));
-    RansacLayout L = plan_ransac(work, cap, num_hyp);
+    RansacLayout L = plan_ransac(work, cap, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));

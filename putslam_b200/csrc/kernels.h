@@ -54,6 +54,13 @@ cudaError_t launch_guided_match(const float* d_map_xyz, const uint8_t* d_map_des
                                 int* launches, const int* d_M = nullptr);
 
 // ---- ransac.cu -------------------------------------------------------------------------------
+// result header of the RANSAC pipeline (ints): [0] n_inliers  [1] hyp_used, or -1 = "finish on the host" (adaptive
+// reference rule: hyp_used = max(last + 1, min([24], iterations(best_ratio))), evaluated with the host libm like the
+// reference)  [2] n_filtered  [3] best_count  [4..19] T (col-major float)  [20..21] best_ratio (double)
+// [22] winner hypothesis  [23] flags  [24] iterations(minimalInlierRatioThreshold)  [25] last improving hypothesis
+// [26] hypotheses scored  [27] spare  [28..] inlier match indices
+constexpr int kRansacHdrInts = 28;
+
 struct RansacDeviceParams {
     int error_version;
     float thr_euclid_f;       // smallest float >= inlierThresholdEuclidean (float<double compare, exact)
@@ -67,7 +74,19 @@ struct RansacDeviceParams {
     int num_hyp;              // 0 = adaptive (reference bound 487, shrinking), >0 fixed
     int stop_rule;            // 0 = reference RANSAC rule, 1 = USAC standard stopping (capped by the budget)
     double usac_conf;
+    int iters_min_ratio;      // computeRANSACIteration(minimalInlierRatioThreshold), evaluated on the host
 };
+// Hypotheses scored per call.  Fixed mode: num_hyp.  Adaptive mode: the reference's loop starts with the bound
+// computeRANSACIteration(0.20) = 487 (RANSAC.cpp:30) and, after the first improvement, never exceeds
+// computeRANSACIteration(minimalInlierRatioThreshold) (:450-453) -- which is larger than 487 for thresholds below 0.2.
+// All of them are scored in one launch (capped at 2^20), the replay then decides how many "were run".
+// USAC stopping without an explicit budget keeps the 487 cap.
+inline int ransac_hypothesis_budget(const RansacDeviceParams& P) {
+    if (P.num_hyp > 0) return P.num_hyp;
+    int h = 487;
+    if (P.stop_rule != 1 && P.iters_min_ratio > h) h = P.iters_min_ratio;
+    return h < (1 << 20) ? h : (1 << 20);
+}
 struct RansacWorkspace {
     // all device pointers; sized for m_cap matches and h_cap hypotheses
     float* pts;        // 6 * m_cap : filtered prev xyz | cur xyz as SoA px,py,pz,cx,cy,cz

@@ -19,9 +19,7 @@
 
 namespace pslam {
 
-constexpr int kHdrInts = 24;  // result header: see layout below
-// result layout (ints): [0] n_inliers  [1] hyp_used  [2] n_filtered  [3] best_count  [4..19] T (col-major float)
-//                       [20..21] best_ratio (double)  [22] winner hypothesis  [23] flags   [24..] inlier match idx
+constexpr int kHdrInts = kRansacHdrInts;  // result header: layout in kernels.h
 
 size_t ransac_result_ints(int m_cap) { return (size_t)kHdrInts + (size_t)(m_cap > 0 ? m_cap : 1); }
 
@@ -30,48 +28,57 @@ __global__ void __launch_bounds__(1024, 1)
 ransac_filter_kernel(const float* __restrict__ prev, const float* __restrict__ cur, const int* __restrict__ mq,
                      const int* __restrict__ mt, const int* __restrict__ d_m, int m_host, int m_cap,
                      float* __restrict__ pts, int* __restrict__ keep, int* __restrict__ n_filtered) {
-    __shared__ int warp_tot[32];
-    __shared__ int carry;
+    // Ordered compaction, 2048 matches per pass: every thread takes match k of the first 1024 and match k + 1024 of the
+    // second, two ballots per warp, one barrier pair per pass (a pass is all latency -- dependent loads and barriers --
+    // so the second match per thread is almost free; 1000-2000 matches, the usual frame, need one pass).
+    __shared__ int warp_tot[2][32];
     chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int m = d_m ? *d_m : m_host;
     if (m > m_cap) m = m_cap;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < m; base += 1024) {
-        const int k = base + tid;
-        bool ok = false;
-        float p[3] = {0, 0, 0}, c[3] = {0, 0, 0};
-        if (k < m) {
-            const int qi = mq[k], ti = mt[k];
+    int carry = 0;   // identical in every thread
+    for (int base = 0; base < m; base += 2048) {
+        bool ok[2] = {false, false};
+        float p[2][3], c[2][3];
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { p[a] = prev[3 * qi + a]; c[a] = cur[3 * ti + a]; }
-            const bool bad = isnan(p[0]) || isnan(p[1]) || isnan(p[2]) || isnan(c[0]) || isnan(c[1]) || isnan(c[2]) ||
-                             (double)p[2] < 0.1 || p[2] > 6.f || (double)c[2] < 0.1 || c[2] > 6.f;
-            ok = !bad;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        const int wpre = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            const int cw = warp_tot[w];
-            if (w < warp) woff += cw;
-            tot += cw;
-        }
-        if (ok) {
-            const int pos = carry + woff + wpre;
-            keep[pos] = k;
+        for (int h = 0; h < 2; ++h) {
+            const int k = base + 1024 * h + tid;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                pts[(size_t)a * m_cap + pos] = p[a];
-                pts[(size_t)(3 + a) * m_cap + pos] = c[a];
+            for (int a = 0; a < 3; ++a) { p[h][a] = 0.f; c[h][a] = 0.f; }
+            if (k < m) {
+                const int qi = mq[k], ti = mt[k];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { p[h][a] = prev[3 * qi + a]; c[h][a] = cur[3 * ti + a]; }
+                const bool bad = isnan(p[h][0]) || isnan(p[h][1]) || isnan(p[h][2]) || isnan(c[h][0]) || isnan(c[h][1]) ||
+                                 isnan(c[h][2]) || (double)p[h][2] < 0.1 || p[h][2] > 6.f || (double)c[h][2] < 0.1 ||
+                                 c[h][2] > 6.f;
+                ok[h] = !bad;
             }
         }
+        const uint32_t bal0 = __ballot_sync(0xffffffffu, ok[0]), bal1 = __ballot_sync(0xffffffffu, ok[1]);
+        __syncthreads();   // warp_tot of the previous pass consumed
+        if (lane == 0) { warp_tot[0][warp] = __popc(bal0); warp_tot[1][warp] = __popc(bal1); }
         __syncthreads();
-        if (tid == 0) carry += tot;
-        __syncthreads();
+        int woff0 = 0, woff1 = 0, tot0 = 0, tot1 = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c0 = warp_tot[0][w], c1 = warp_tot[1][w];
+            if (w < warp) { woff0 += c0; woff1 += c1; }
+            tot0 += c0; tot1 += c1;
+        }
+        const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                const int pos = h == 0 ? carry + woff0 + __popc(bal0 & lt) : carry + tot0 + woff1 + __popc(bal1 & lt);
+                keep[pos] = base + 1024 * h + tid;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    pts[(size_t)a * m_cap + pos] = p[h][a];
+                    pts[(size_t)(3 + a) * m_cap + pos] = c[h][a];
+                }
+            }
+        }
+        carry += tot0 + tot1;
     }
     if (tid == 0) *n_filtered = carry;
 }
@@ -261,24 +268,91 @@ __device__ __forceinline__ unsigned usac_standard_stopping(unsigned inl, unsigne
     return (unsigned)ceil(log(1 - conf) / log(1 - prob));
 }
 
+// Sequential (order-exact) float sums over shared-memory columns.  The additions form one dependent chain -- that is
+// the definition of the result -- but the loads and the per-element products do not have to sit on it: batch k+1 is
+// fetched (and multiplied) while batch k is added.  The empty asm statements pin the loads of the next batch in front
+// of the additions of the current one (left alone, ptxas reuses the registers and issues the loads after the chain,
+// which then waits a shared-memory latency per batch: 11.7 cycles per element measured, FADD latency is 4).
+constexpr int kSumBatch = 8;
+__device__ __forceinline__ float seq_sum(const float* __restrict__ col, int n) {
+    float s = 0.f;
+    int k = 0;
+    if (n >= 2 * kSumBatch) {
+        float a[kSumBatch], b[kSumBatch];
+#pragma unroll
+        for (int u = 0; u < kSumBatch; ++u) a[u] = col[u];
+        for (; k + 2 * kSumBatch <= n; k += 2 * kSumBatch) {
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) b[u] = col[k + kSumBatch + u];
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) s = s + a[u];
+            const int k2 = (k + 3 * kSumBatch <= n) ? k + 2 * kSumBatch : 0;   // clamped prefetch, unused past the end
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) a[u] = col[k2 + u];
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) s = s + b[u];
+        }
+    }
+    for (; k < n; ++k) s = s + col[k];
+    return s;
+}
+// sum_k (d[k] - dmean) * (c[k] - cmean), same order
+__device__ __forceinline__ float seq_cov_sum(const float* __restrict__ d, float dmean, const float* __restrict__ c, float cmean,
+                                             int n) {
+    float s = 0.f;
+    int k = 0;
+    if (n >= 2 * kSumBatch) {
+        float a[kSumBatch], b[kSumBatch];
+#pragma unroll
+        for (int u = 0; u < kSumBatch; ++u) a[u] = (d[u] - dmean) * (c[u] - cmean);
+        for (; k + 2 * kSumBatch <= n; k += 2 * kSumBatch) {
+            float rd[kSumBatch], rc[kSumBatch];
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) { rd[u] = d[k + kSumBatch + u]; rc[u] = c[k + kSumBatch + u]; }
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) { s = s + a[u]; b[u] = (rd[u] - dmean) * (rc[u] - cmean); }
+            const int k2 = (k + 3 * kSumBatch <= n) ? k + 2 * kSumBatch : 0;
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) { rd[u] = d[k2 + u]; rc[u] = c[k2 + u]; }
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int u = 0; u < kSumBatch; ++u) { s = s + b[u]; a[u] = (rd[u] - dmean) * (rc[u] - cmean); }
+        }
+    }
+    for (; k < n; ++k) s = s + (d[k] - dmean) * (c[k] - cmean);
+    return s;
+}
+
 constexpr int kSelThreads = 1024;
+
+// phase clocks of the selection kernel (debug builds only: make -C putslam_b200/csrc dbg)
+#ifdef PSLAM_SELECT_TIMING
+__device__ long long g_sel_clk[16];
+#define SEL_CLK(k) do { if (threadIdx.x == 0) g_sel_clk[k] = clock64(); } while (0)
+#else
+#define SEL_CLK(k) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kSelThreads, 1)
 ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
                      const int* __restrict__ n_filtered, const int* __restrict__ counts,
                      const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
-                     int min_matches, double min_ratio, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
+                     int min_matches, double min_ratio, int iters_min, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
                      int* __restrict__ inl_tmp /* m_cap scratch */, int stage_cap, int* __restrict__ result) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     __shared__ unsigned long long best_key;
-    __shared__ int s_win, s_used, s_cnt;
+    __shared__ int s_win, s_used, s_cnt, s_last;
     __shared__ float s_mean[6];
     __shared__ float s_sig[9];
     __shared__ float s_R[9], s_t[3];
     __shared__ int s_ok;
 
     chain_begin();
+    SEL_CLK(0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mf = *n_filtered;
     float* Tout = reinterpret_cast<float*>(result + 4);
@@ -288,6 +362,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         if (tid < 16) Tout[tid] = (tid % 5 == 0) ? 1.f : 0.f;
         if (tid == 0) {
             result[0] = 0; result[1] = used; result[2] = mf; result[3] = 0; result[22] = -1; result[23] = 0;
+            result[24] = iters_min; result[25] = -1; result[26] = H;
             *reinterpret_cast<double*>(result + 20) = 0.0;
         }
     };
@@ -297,35 +372,114 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     }
 
     // ---- winner: replay of the sequential loop over the scored hypotheses ----
-    if (tid == 0) { best_key = 0ull; s_win = -1; s_used = H; s_cnt = 0; carry = 0; }
+    if (tid == 0) { best_key = 0ull; s_win = -1; s_used = H; s_cnt = 0; s_last = -1; carry = 0; }
     __syncthreads();
     if (adaptive) {
-        // the replay is sequential by definition; stage the counts in shared memory first so that thread 0 does not
-        // pay a global-memory latency per step (the adaptive bound is at most 487, USAC replay uses the budget H)
-        __shared__ int s_counts[1024];
-        const int n_stage_c = H < 1024 ? H : 1024;
-        for (int i = tid; i < n_stage_c; i += kSelThreads) s_counts[i] = counts[i];
-        __syncthreads();
-        if (tid == 0) {
-            int bound = H, win = -1, bc = 0;
-            double best = 0.0;
-            int i = 0;
-            for (; i < bound; ++i) {
-                const int c = i < n_stage_c ? s_counts[i] : counts[i];
-                if (c < 0) continue;
-                const float ratio = __fdiv_rn((float)c, (float)mf);
-                if ((double)ratio > best) {
-                    best = (double)ratio; win = i; bc = c;
-                    if (stop_rule == 1) {
-                        const unsigned b = usac_standard_stopping((unsigned)c, (unsigned)mf, usac_conf, (unsigned)H);
-                        bound = (int)(b < (unsigned)H ? b : (unsigned)H);
-                    } else if (adaptive == 1) {
-                        const int a = ransac_iterations(min_ratio), b = ransac_iterations(best);
-                        bound = a < b ? a : b;
+        // Replay of the reference's sequential loop  for (i = 0; i < iterationCount; ++i) { if (ratio_i > best) {...} }.
+        // Its state only changes at "records", hypotheses whose count exceeds every earlier count (float(c)/float(mf) is
+        // non-decreasing in c, so ratio_i > best implies c_i > all earlier c).  All threads find the records of a
+        // 1024-hypothesis chunk with a prefix maximum and compact them in order; thread 0 then replays just those
+        // (re-checking the float comparison, updating the bound exactly like saveBetterModel / updateStandardStopping).
+        __shared__ int s_rec_idx[kSelThreads], s_rec_c[kSelThreads];
+        __shared__ int s_wmax[32], s_wcnt[32];
+        __shared__ int s_runmax, s_bound, s_done;
+        // the reference's loop starts with computeRANSACIteration(0.20) = 487 (RANSAC.cpp:30); H is larger when
+        // minimalInlierRatioThreshold < 0.2 lets the bound grow after the first improvement (kernels.h)
+        const int bound0 = (adaptive == 1 && H > 487) ? 487 : H;
+        if (tid == 0) { s_runmax = 0; s_bound = bound0; s_done = 0; }
+        // thread 0's replay state.  With the reference rule the bound after an improvement is
+        // min(iters_min, computeRANSACIteration(best)): two double-precision log/pow chains (~5k cycles) per record if
+        // evaluated eagerly.  Only the comparison "record index < bound" needs it, so a float estimate with a +-0.1 % +-2
+        // bracket decides, the exact value is computed only inside the bracket, and hyp_used itself is finished on the
+        // host (kernels.h), with the libm the reference would use.
+        const bool lazy = adaptive == 1 && stop_rule != 1;
+        int bound_lo = bound0, bound_hi = bound0;   // bracket of the current bound (equal when it is known exactly)
+        int win = -1, bc = 0, last = -1;
+        double best = 0.0;
+        for (int base = 0; base < H; base += kSelThreads) {
+            __syncthreads();
+            if (s_done || base >= s_bound) break;
+            const int idx = base + tid;
+            const int c = idx < H ? counts[idx] : -1;
+            const int cc = c > 0 ? c : 0;          // degenerate (-1) and empty hypotheses can never be records
+            int incl = cc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d && o > incl) incl = o;
+            }
+            int prev = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) prev = 0;
+            if (lane == 31) s_wmax[warp] = incl;
+            __syncthreads();
+            int before = s_runmax, chunk_max = 0;
+            for (int w = 0; w < 32; ++w) {
+                const int m = s_wmax[w];
+                if (w < warp && m > before) before = m;
+                if (m > chunk_max) chunk_max = m;
+            }
+            if (prev > before) before = prev;
+            const bool rec = cc > before;
+            const uint32_t bal = __ballot_sync(0xffffffffu, rec);
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = 0, nrec = 0;
+            for (int w = 0; w < 32; ++w) {
+                const int n = s_wcnt[w];
+                if (w < warp) off += n;
+                nrec += n;
+            }
+            if (rec) {
+                const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                s_rec_idx[pos] = idx; s_rec_c[pos] = c;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int r = 0; r < nrec; ++r) {
+                    const int i = s_rec_idx[r];
+                    if (i >= bound_hi) { s_done = 1; break; }
+                    if (i >= bound_lo) {   // inside the bracket: evaluate the bound exactly
+                        const int b = ransac_iterations(best);
+                        bound_lo = bound_hi = iters_min < b ? iters_min : b;
+                        if (bound_hi > H) bound_lo = bound_hi = H;
+                        if (i >= bound_hi) { s_done = 1; break; }
+                    }
+                    const int ci = s_rec_c[r];
+                    const float ratio = __fdiv_rn((float)ci, (float)mf);
+                    if ((double)ratio > best) {
+                        best = (double)ratio; win = i; bc = ci; last = i;
+                        if (stop_rule == 1) {
+                            const unsigned b = usac_standard_stopping((unsigned)ci, (unsigned)mf, usac_conf, (unsigned)H);
+                            bound_lo = bound_hi = (int)(b < (unsigned)H ? b : (unsigned)H);
+                        } else if (lazy) {
+                            // float estimate of log(0.02) / log(1 - w^3)
+                            const float x = ratio * ratio * ratio;
+                            const float bf = __fdiv_rn(-3.912023005f, log1pf(-x));
+                            if (x < 1.f && bf >= 0.f && bf < 1.0e9f) {
+                                bound_lo = (int)floorf(bf * 0.999f) - 2;
+                                bound_hi = (int)ceilf(bf * 1.001f) + 2;
+                            } else if (x < 1.f && bf >= 1.0e9f) {
+                                bound_lo = bound_hi = 0x7fffffff;     // far beyond iters_min either way
+                            } else {
+                                const int b = ransac_iterations(best);
+                                bound_lo = bound_hi = b;
+                            }
+                            if (bound_lo > iters_min) bound_lo = iters_min;
+                            if (bound_hi > iters_min) bound_hi = iters_min;
+                        }
+                        if (bound_lo > H) bound_lo = H;   // only H hypotheses were scored
+                        if (bound_hi > H) bound_hi = H;
                     }
                 }
+                if (chunk_max > s_runmax) s_runmax = chunk_max;
+                s_bound = bound_hi;
             }
-            s_win = win; s_used = i; s_cnt = bc;
+        }
+        if (tid == 0) {
+            // the sequential loop leaves at the first i >= bound, and it is at last + 1 when the bound drops behind it
+            s_win = win; s_cnt = bc; s_last = last;
+            if (lazy && win >= 0) s_used = -1;   // host: max(last + 1, min(iters_min, computeRANSACIteration(best)))
+            else s_used = (last + 1 > bound_hi) ? last + 1 : bound_hi;
         }
     } else {
         // fixed bound: first maximum of float(c)/float(mf) == first maximum of c (monotone, c <= mf < 2^24)
@@ -352,6 +506,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         }
     }
     __syncthreads();
+    SEL_CLK(1);
     const int win = s_win, used = s_used, best_cnt = s_cnt;
     if (win < 0) {  // no hypothesis scored above zero: refit on the empty set fails -> identity (RANSAC.cpp:152-164)
         write_identity(used);
@@ -376,26 +531,37 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     M.ok = true;
     float Ri[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ti[3] = {0, 0, 0};
     if (S.ev == 1 || S.ev == 2) model_inverse(M, Ri, ti);
-    for (int base = 0; base < mf; base += kSelThreads) {
-        const int k = base + tid;
-        const bool in = (k < mf) && inlier_test(S, M.R, M.t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], false);
-        const uint32_t bal = __ballot_sync(0xffffffffu, in);
-        const int wpre = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-        for (int w = 0; w < 32; ++w) {
-            const int cw = warp_tot[w];
-            if (w < warp) woff += cw;
-            tot += cw;
+    {   // ordered compaction, 2 x 1024 matches per pass (see ransac_filter_kernel)
+        __shared__ int wt2[2][32];
+        int run = 0;   // identical in every thread
+        for (int base = 0; base < mf; base += 2 * kSelThreads) {
+            bool in[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = base + kSelThreads * h + tid;
+                in[h] = (k < mf) && inlier_test(S, M.R, M.t, Ri, ti, px[k], py[k], pz[k], cx[k], cy[k], cz[k], false);
+            }
+            const uint32_t bal0 = __ballot_sync(0xffffffffu, in[0]), bal1 = __ballot_sync(0xffffffffu, in[1]);
+            __syncthreads();
+            if (lane == 0) { wt2[0][warp] = __popc(bal0); wt2[1][warp] = __popc(bal1); }
+            __syncthreads();
+            int woff0 = 0, woff1 = 0, tot0 = 0, tot1 = 0;
+            for (int w = 0; w < 32; ++w) {
+                const int c0 = wt2[0][w], c1 = wt2[1][w];
+                if (w < warp) { woff0 += c0; woff1 += c1; }
+                tot0 += c0; tot1 += c1;
+            }
+            const uint32_t ltm = (1u << lane) - 1u;
+            if (in[0]) inl_tmp[run + woff0 + __popc(bal0 & ltm)] = base + tid;
+            if (in[1]) inl_tmp[run + tot0 + woff1 + __popc(bal1 & ltm)] = base + kSelThreads + tid;
+            run += tot0 + tot1;
         }
-        if (in) inl_tmp[carry + woff + wpre] = k;
-        __syncthreads();
-        if (tid == 0) carry += tot;
+        if (tid == 0) carry = run;
         __syncthreads();
     }
     const int n_in = carry;
     __syncthreads();
+    SEL_CLK(2);
 
     // ---- refit: Umeyama over all inliers; every sum is a sequential float chain, one thread per chain ----
     // The inlier coordinates are first gathered into shared memory (all threads, coalesced index reads) so
@@ -408,13 +574,12 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         for (int a = 0; a < 6; ++a) s_pts[a * n_stage + k] = pts[(size_t)a * m_cap + id];
     }
     __syncthreads();
+    SEL_CLK(3);
     const float one_over_n = __fdiv_rn(1.f, (float)n_in);
     if (tid < 6) {
         float s = 0.f;
         if (n_stage) {
-            const float* col = s_pts + tid * n_stage;
-#pragma unroll 8
-            for (int k = 0; k < n_in; ++k) s = s + col[k];
+            s = seq_sum(s_pts + tid * n_stage, n_in);
         } else {
             const float* col = pts + (size_t)tid * m_cap;  // 0..2 prev (dst), 3..5 cur (src)
             for (int k = 0; k < n_in; ++k) s = s + col[inl_tmp[k]];
@@ -422,15 +587,13 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         s_mean[tid] = s * one_over_n;
     }
     __syncthreads();
+    SEL_CLK(4);
     if (tid < 9) {
         const int i = tid / 3, j = tid % 3;
         const float dmean = s_mean[i], smean = s_mean[3 + j];
         float s = 0.f;
         if (n_stage) {
-            const float* dcol = s_pts + i * n_stage;
-            const float* scol = s_pts + (3 + j) * n_stage;
-#pragma unroll 8
-            for (int k = 0; k < n_in; ++k) s = s + (dcol[k] - dmean) * (scol[k] - smean);
+            s = seq_cov_sum(s_pts + i * n_stage, dmean, s_pts + (3 + j) * n_stage, smean, n_in);
         } else {
             const float* dcol = pts + (size_t)i * m_cap;
             const float* scol = pts + (size_t)(3 + j) * m_cap;
@@ -442,6 +605,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         s_sig[tid] = one_over_n * s;
     }
     __syncthreads();
+    SEL_CLK(5);
     if (tid == 0) {
         float sig[9], sm[3], dm[3];
 #pragma unroll
@@ -463,6 +627,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
 #pragma unroll
     for (int i = 0; i < 3; ++i) t[i] = s_t[i];
 
+    SEL_CLK(6);
     // ---- Euclidean recount restricted to the winner's inliers (RANSAC.cpp:155-157), ordered ----
     const bool gate = !(best_ratio < min_ratio);  // RANSAC.cpp:161
     for (int base = 0; base < n_in; base += kSelThreads) {
@@ -488,6 +653,7 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         if (tid == 0) carry += tot;
         __syncthreads();
     }
+    SEL_CLK(7);
     if (tid < 16) {  // column-major 4x4 (Eigen::Matrix4f layout)
         const int r = tid % 4, c = tid / 4;
         float v = (r == c) ? 1.f : 0.f;
@@ -502,6 +668,9 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
         result[1] = used;
         result[2] = mf;
         result[3] = best_cnt;
+        result[24] = iters_min;
+        result[25] = s_last;
+        result[26] = H;
         *reinterpret_cast<double*>(result + 20) = best_ratio;
         result[22] = win;
         result[23] = s_ok;
@@ -521,7 +690,7 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     // sequential replay is needed for the reference's adaptive bound and for USAC stopping (2 = replay with a fixed
     // budget); plain fixed-H is a parallel first-max
     const int adaptive = P.num_hyp <= 0 ? 1 : (P.stop_rule == 1 ? 2 : 0);
-    const int H = adaptive ? 487 : P.num_hyp;  // int(log(0.02)/log(1-0.2^3)), reference RANSAC.cpp:30
+    const int H = ransac_hypothesis_budget(P);   // adaptive: 487 = int(log(0.02)/log(1-0.2^3)) (RANSAC.cpp:30) or more
     cudaError_t e;
     if ((e = launch_chained(ransac_filter_kernel, dim3(1), dim3(1024), 0, st, d_prev, d_cur, d_mq, d_mt, d_m, m_host,
                             ws.m_cap, ws.pts, ws.keep, ws.n_filtered)) != cudaSuccess) return e;
@@ -549,11 +718,17 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
         return e;
     if ((e = launch_chained(ransac_select_kernel, dim3(1), dim3(kSelThreads), sel_smem, st, ws.pts, ws.m_cap, ws.keep,
                             ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf, P.min_matches,
-                            P.min_inlier_ratio, S, P.seed_lo, P.seed_hi,
+                            P.min_inlier_ratio, P.iters_min_ratio, S, P.seed_lo, P.seed_hi,
                             ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap, ws.result)) != cudaSuccess)
         return e;
     if (launches) *launches += 4;
     return cudaGetLastError();
 }
+
+#ifdef PSLAM_SELECT_TIMING
+extern "C" __attribute__((visibility("default"))) int pslam_debug_select_clocks(long long* out16) {
+    return (int)cudaMemcpyFromSymbol(out16, g_sel_clk, sizeof(long long) * 16);
+}
+#endif
 
 }  // namespace pslam

@@ -435,6 +435,28 @@ def test_gradient_uncertainty(ctx, O):
         assert np.allclose(ninfo[i], O.inverse3d(ncov[i]), rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("min_ratio,inlier_frac", [(0.1, 0.55), (0.1, 0.12), (0.05, 0.08), (0.3, 0.55), (0.2, 0.03)])
+def test_ransac_adaptive_bound_follows_min_ratio(ctx, O, min_ratio, inlier_frac):
+    """Adaptive mode with minimalInlierRatioThreshold != 0.2: the loop starts at 487 iterations and after the first
+    improvement is bounded by computeRANSACIteration(minimalInlierRatioThreshold) -- 3910 at 0.1, 31k at 0.05 -- so with
+    few inliers it runs far beyond 487 hypotheses.  hyp_used (finished on the host), the counts of every hypothesis the
+    loop visited, the inlier set and the pose follow the oracle."""
+    from putslam_b200 import api, synth
+    for seed in range(3):
+        mc = synth.matched_clouds(m=600, inlier_frac=inlier_frac, seed=50 + seed)
+        pa = api.default_ransac_params(0); pa.minimal_inlier_ratio_threshold = min_ratio
+        po = O.default_ransac_params(0); po.minimal_inlier_ratio_threshold = min_ratio
+        r = ctx.ransac_estimate(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=pa, seed=7 + seed, num_hyp=0, want_counts=True,
+                                counts_cap=40000)
+        o = O.ransac(mc["prev"], mc["cur"], mc["mq"], mc["mt"], params=po, seed=7 + seed, num_hyp=0, want_counts=True,
+                     counts_cap=40000)
+        n = o["hyp_used"]
+        assert r["hyp_used"] == n, (r["hyp_used"], n)
+        assert np.array_equal(r["counts"][:n], o["counts"][:n])
+        assert r["best_ratio"] == o["best_ratio"] and np.array_equal(r["inliers"], o["inliers"])
+        assert_pose_close(r["T"], o["T"].astype(np.float64))
+
+
 def test_ransac_usac_standard_stopping(ctx, O):
     """Alternative termination rule: USAC<T>::updateStandardStopping replayed over the scored hypotheses."""
     from putslam_b200 import synth
