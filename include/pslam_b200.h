@@ -163,7 +163,10 @@ typedef struct {
  * prev: n_prev x 3, cur: n_cur x 3 float; match k pairs prev[match_query[k]] with cur[match_train[k]].
  * Hypothesis i samples 3 matches with Philox4x32-10(key = seed, counter = {block, i, 0, 0}) % m with
  * rejection (pslam_ransac_sample reproduces the draw on the host).  num_hyp = 0: the reference's
- * adaptive loop (bound 487, shrinking as better models appear); num_hyp > 0: exactly that many.
+ * adaptive loop: the bound starts at computeRANSACIteration(0.20) = 487 (RANSAC.cpp:30) and after every improvement
+ * becomes min(computeRANSACIteration(minimalInlierRatioThreshold), computeRANSACIteration(best)) (:450-453); all
+ * hypotheses the loop can reach -- max(487, computeRANSACIteration(minimalInlierRatioThreshold)), at most 2^20 -- are
+ * scored in one launch and the loop is replayed over their counts.  num_hyp > 0: exactly that many.
  * T_out: column-major 4x4, prev ~= R*cur + t.  inlier_idx_out (capacity m): indices into the match list,
  * ascending.  Failure conventions are the reference's: too few matches or best ratio below the
  * threshold -> identity and zero inliers, return value still PSLAM_OK. */
