@@ -5,6 +5,7 @@ arithmetic of the reference's matching and undistortion calls:
   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2)            (north_star ratio-test extension)
   cv::Mat a - b (saturating) + cv::norm(NORM_HAMMING)  src/Matcher/matcher.cpp:719-721
   cv::undistortPoints                                  src/RGBD/RGBD.cpp:268,298
+  cv::ORB::compute (provided keypoints)                src/Matcher/matcherOpenCV.cpp:181-195
 
 Run in the build container (cv2 4.13.0):  python tests/golden/make_golden.py
 The vectors are small on purpose; the oracle (oracle/oracle.c) and the CUDA path are both checked
@@ -68,8 +69,48 @@ def undistort_cases():
     return dict(K=K, dist=d, uv=uv, normalized=und.astype(np.float32), uv_undist=out)
 
 
+def orb_scene(rng, H, W, colour=False):
+    """deterministic test image with structure at several scales (blobs, bars, texture), uint8"""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    img = 96 + 40 * np.sin(xx / 9.0) * np.cos(yy / 13.0) + 30 * np.sin((xx + 2 * yy) / 37.0)
+    for _ in range(60):
+        cx, cy, r, a = rng.uniform(0, W), rng.uniform(0, H), rng.uniform(2, 18), rng.uniform(-70, 70)
+        img += a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * r * r))
+    img += rng.normal(0, 6, (H, W))
+    g = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    if not colour:
+        return g
+    return np.stack([g, np.roll(g, 3, 1), 255 - np.roll(g, 5, 0)], 2).copy()
+
+
+def orb_cases():
+    """cv::ORB::compute with caller-provided keypoints (MatcherOpenCV::describeFeatures,
+    src/Matcher/matcherOpenCV.cpp:181-195): kept/reordered keypoint indices and descriptors from cv2."""
+    rng = np.random.default_rng(31)
+    orb = cv2.ORB_create()
+    out = {}
+    for name, H, W, colour, n in (("gray", 240, 320, False, 400), ("bgr", 150, 200, True, 150)):
+        img = orb_scene(rng, H, W, colour)
+        xy = np.stack([rng.uniform(20, W - 20, n), rng.uniform(20, H - 20, n)], 1).astype(np.float32)
+        # rounding boundary of the border filter (30.5 -> 30, 31.5 -> 32) and exact edges
+        xy[:6] = [[30.5, 100.0], [31.5, 100.0], [W - 31.5, 80.0], [W - 30.5, 80.0], [100.0, 30.5], [100.0, H - 31.5]]
+        octave = rng.integers(0, 8, n).astype(np.int32)
+        angle = rng.uniform(0, 360, n).astype(np.float32)
+        angle[6:10] = [0.0, 90.0, 180.0, 359.99]
+        kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(xy, angle, octave)]
+        k2, d2 = orb.compute(img, kps)
+        # identify the surviving keypoints: (x, y, octave, angle) is unique per keypoint
+        key = {(float(k.pt[0]), float(k.pt[1]), k.octave, float(k.angle)): i for i, k in enumerate(kps)}
+        order = np.array([key[(float(k.pt[0]), float(k.pt[1]), k.octave, float(k.angle))] for k in k2], np.int32)
+        out.update({name + "_img": img, name + "_xy": xy, name + "_octave": octave, name + "_angle": angle,
+                    name + "_order": order, name + "_desc": d2})
+    out["names"] = np.array(["gray", "bgr"])
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "bf_cv2.npz"), **bf_cases())
     np.savez_compressed(os.path.join(HERE, "satsub_cv2.npz"), **satsub_cases())
     np.savez_compressed(os.path.join(HERE, "undistort_cv2.npz"), **undistort_cases())
+    np.savez_compressed(os.path.join(HERE, "orb_cv2.npz"), **orb_cases())
     print("cv2", cv2.__version__, "golden vectors written to", HERE)

@@ -349,3 +349,72 @@ def test_lc_scores_and_topk(O):
 
 def test_point_inlier_ratio(O):
     assert O.point_inlier_ratio([1, 1, 2], [1, 2, 3, 3, 4], 10) == 2 / 4
+
+
+# ---------------------------------------------------------------- ORB descriptors (describeFeatures seam)
+def test_orb_oracle_matches_cv2_golden(golden):
+    """oracle/orb_oracle.py against cv::ORB::compute outputs recorded from cv2 4.13.0: kept/reordered keypoints and
+    every descriptor bit."""
+    from oracle import orb_oracle as OO
+    g = golden["orb_cv2"]
+    for name in g["names"]:
+        order, desc = OO.describe(g[f"{name}_img"], g[f"{name}_xy"], g[f"{name}_octave"], g[f"{name}_angle"])
+        assert np.array_equal(order, g[f"{name}_order"]), name
+        assert np.array_equal(desc, g[f"{name}_desc"]), name
+        assert 0.5 * len(g[f"{name}_xy"]) < order.size < len(g[f"{name}_xy"])        # the border filter was exercised
+
+
+def test_orb_stages_against_live_cv2():
+    """each stage of the restatement against the library call it stands for, on fresh inputs"""
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(41)
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    smooth = cv2.GaussianBlur(img, (0, 0), 2.0)
+    # 1. gray conversion
+    bgr = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    assert np.array_equal(OO.bgr2gray(bgr), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    # 3. the resize cascade: every level size ORB uses for 640x480, plus odd shapes
+    prev = img
+    for l in range(1, 8):
+        w, h = OO.level_size(640, 480, l)
+        ref = cv2.resize(prev, (w, h), interpolation=cv2.INTER_LINEAR_EXACT)
+        assert np.array_equal(OO.resize_linear_exact(prev, w, h), ref), l
+        prev = ref
+    assert [OO.level_size(640, 480, l) for l in (1, 2, 7)] == [(533, 400), (444, 333), (179, 134)]
+    for (sw, sh, dw, dh) in [(101, 77, 84, 64), (64, 64, 53, 53), (33, 200, 28, 167)]:
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        assert np.array_equal(OO.resize_linear_exact(src, dw, dh), cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT))
+    # 4. the blur ORB applies to a pyramid level (sub-matrix => float separable filter): same kernel, same pixels
+    kf = cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel()
+    assert np.array_equal(kf, OO.GAUSS7)
+    for im in (img, smooth):
+        ref = cv2.sepFilter2D(im, cv2.CV_8U, kf, kf, borderType=cv2.BORDER_REFLECT_101)
+        assert np.array_equal(OO.gaussian7_submatrix(im), ref)
+    # 2 + 5. whole path, full-size frame, 600 keypoints over all octaves
+    n = 600
+    xy = np.stack([rng.uniform(10, 630, n), rng.uniform(10, 470, n)], 1).astype(np.float32)
+    octave = rng.integers(0, 8, n).astype(np.int32); angle = rng.uniform(0, 360, n).astype(np.float32)
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(xy, angle, octave)]
+    k2, d2 = cv2.ORB_create().compute(smooth, kps)
+    order, desc = OO.describe(smooth, xy, octave, angle)
+    assert order.size == len(k2)
+    assert all(float(k.pt[0]) == float(xy[i, 0]) and k.octave == octave[i] for k, i in zip(k2, order))
+    assert np.array_equal(desc, d2)
+    # keypoints already sorted by level keep their order; an empty list gives an empty result
+    srt = np.argsort(octave, kind="stable")
+    o2, d3 = OO.describe(smooth, xy[srt], octave[srt], angle[srt])
+    assert np.array_equal(srt[o2], order) and np.array_equal(d3, desc)
+    assert OO.describe(smooth, np.zeros((0, 2)), np.zeros(0, np.int32), np.zeros(0))[0].size == 0
+
+
+def test_orb_pattern_tables_agree():
+    """the device's copy of the sampling pattern (putslam_b200/csrc/orb_pattern.inc) equals the oracle's"""
+    import os
+    import re
+    from oracle import orb_oracle as OO
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "putslam_b200", "csrc", "orb_pattern.inc")).read()
+    nums = [int(x) for line in txt.splitlines() if not line.lstrip().startswith("//") for x in re.findall(r"-?\d+", line)]
+    assert len(nums) == 1024 and np.array_equal(np.array(nums).reshape(256, 4), OO.PATTERN)
+    assert OO.PATTERN[0].tolist() == [8, -3, 9, 5] and np.abs(OO.PATTERN).max() == 13
