@@ -117,6 +117,22 @@ PSLAM_API int pslam_gradient_uncertainty(pslam_ctx* ctx, const int* px, int n, c
                                          double depth_scale, double scale_uncertainty_gradient, double* grad_out,
                                          double* cov_out, double* info_out);
 
+/* ---- descriptor production (second half) -----------------------------------
+ * pslam_orb_describe replaces MatcherOpenCV::describeFeatures for the ORB descriptor (virtual, include/putslam/Matcher/
+ * matcher.h:405-422; src/Matcher/matcherOpenCV.cpp:181-195 == cv::ORB::create()->compute(rgbImage, features,
+ * descriptors) with OpenCV's defaults: 8 levels, scale 1.2, patch 31, edge threshold 31, WTA_K 2).
+ * image: H rows of row_bytes; channels 1 (gray) or 3 (BGR order as stored -- ORB converts with COLOR_BGR2GRAY).
+ * Keypoints: kp_xy n x 2 float (cv::KeyPoint::pt), kp_octave, kp_angle_deg (cv::KeyPoint::angle).  Like cv::ORB::compute,
+ * keypoints whose rounded position is closer than 31 px to the image border are dropped and the rest are regrouped by
+ * octave (stable): order_out (capacity n) receives the indices of the surviving keypoints in output order -- the caller
+ * permutes its keypoint vector with it, as ORB does to `features` -- and desc_out (capacity n x 32) one 32-byte
+ * descriptor per surviving keypoint in that order.  cos / sin of the keypoint angles are evaluated on the host
+ * (double libm, rounded to float, as OpenCV does) and the sampling itself on the device.  Octaves 0 .. 11; every
+ * pyramid level must stay larger than 32 x 32 pixels. */
+PSLAM_API int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels,
+                                 const float* kp_xy, const int* kp_octave, const float* kp_angle_deg, int n,
+                                 int* order_out, int* n_out, uint8_t* desc_out);
+
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
  * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==

@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -201,6 +201,21 @@ class Context:
         self._ck(self.lib.pslam_information_matrices(self.h, _p(uvz, C.c_double), n, C.byref(cov), _p(info, C.c_double),
                                                      _p(covo, C.c_double)))
         return info, covo
+
+    # ---- descriptor production ----
+    def orb_describe(self, image, xy, octave, angle_deg):
+        """cv::ORB::compute with provided keypoints -> (order int32[n_out] into the input keypoints, desc uint8[n_out, 32]).
+        image: H x W uint8 (gray) or H x W x 3 uint8 (BGR)."""
+        img = np.ascontiguousarray(image, np.uint8)
+        ch = 3 if img.ndim == 3 else 1
+        H, W = img.shape[:2]
+        xy = _arr(xy, np.float32, 2); oc = _arr(octave, np.int32); an = _arr(angle_deg, np.float32)
+        n = oc.size
+        order = np.empty(max(1, n), np.int32); desc = np.empty((max(1, n), 32), np.uint8); n_out = C.c_int(0)
+        self._ck(self.lib.pslam_orb_describe(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, _p(xy, C.c_float), _p(oc, C.c_int),
+                                             _p(an, C.c_float), n, _p(order, C.c_int), C.byref(n_out), _p(desc, C.c_uint8)))
+        k = n_out.value
+        return order[:k].copy(), desc[:k].copy()
 
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):

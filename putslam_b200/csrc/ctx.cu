@@ -153,6 +153,10 @@ struct pslam_ctx {
     double* d_map_xyz = nullptr; uint8_t* d_map_desc = nullptr; int* d_map_oct = nullptr; double* d_map_det = nullptr;
     float* d_map_axis = nullptr;
     int map_cap = 0, map_n = 0;
+    // ORB descriptor path: resize coefficient tables + sampling pattern, cached per image size / level count
+    DevBuf d_orb_tab;
+    int orb_W = 0, orb_H = 0, orb_levels = 0;
+    bool orb_constants = false;
     // map_prepare_kernel's per-CTA counts (stamped with prep_epoch, so they are never reset)
     unsigned long long* d_prep_counts = nullptr;
     unsigned int prep_epoch = 0;
@@ -376,7 +380,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
     cudaFree(ctx->d_map_xyz); cudaFree(ctx->d_map_desc); cudaFree(ctx->d_map_oct); cudaFree(ctx->d_map_det);
-    cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts);
+    cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts); cudaFree(ctx->d_orb_tab.p);
     if (ctx->ev_sweep0) cudaEventDestroy(ctx->ev_sweep0);
     if (ctx->ev_sweep1) cudaEventDestroy(ctx->ev_sweep1);
     cudaStreamDestroy(ctx->stream);
@@ -1133,6 +1137,102 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
     memcpy(uv, ctx->h_out.p + o_uv, 16 * (size_t)n);
     memcpy(angles, ctx->h_out.p + o_ang, 8 * (size_t)n);
     *n_out = n;
+    return PSLAM_OK;
+}
+
+// ---- ORB descriptors ---------------------------------------------------------------------------------
+int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels, const float* kp_xy,
+                       const int* kp_octave, const float* kp_angle_deg, int n, int* order_out, int* n_out,
+                       uint8_t* desc_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || n < 0 || !image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: bad argument");
+    *n_out = 0;
+    if (n == 0) return PSLAM_OK;
+    if (!kp_xy || !kp_octave || !kp_angle_deg || !order_out || !desc_out)
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: null buffer");
+    // level count from all provided keypoints (cv::ORB::compute does this before it filters them)
+    int nlev = 0;
+    for (int i = 0; i < n; ++i) {
+        if (kp_octave[i] < 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: negative octave");
+        if (kp_octave[i] + 1 > nlev) nlev = kp_octave[i] + 1;
+    }
+    if (nlev > kOrbMaxLevels) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_orb_describe: octave above %d", kOrbMaxLevels - 1);
+    OrbPlan P;
+    orb_plan(W, H, nlev, &P);
+    if (P.w[nlev - 1] <= 32 || P.h[nlev - 1] <= 32)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_orb_describe: pyramid level %d is %d x %d (must exceed 32 x 32)", nlev - 1,
+                    P.w[nlev - 1], P.h[nlev - 1]);
+    // KeyPointsFilter::runByImageBorder(edgeThreshold = 31) on the rounded position, then a stable regroup by octave
+    std::vector<int> order;
+    order.reserve((size_t)n);
+    for (int l = 0; l < nlev; ++l)
+        for (int i = 0; i < n; ++i) {
+            if (kp_octave[i] != l) continue;
+            const long ix = lrintf(kp_xy[2 * i]), iy = lrintf(kp_xy[2 * i + 1]);   // cvRound: half to even
+            if (ix >= 31 && ix < W - 31 && iy >= 31 && iy < H - 31) order.push_back(i);
+        }
+    const int m = (int)order.size();
+    *n_out = m;
+    if (m == 0) return PSLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    Arena in, out, work;
+    const size_t img_bytes = (size_t)channels * W * H;
+    const size_t o_rec = in.take(20 * (size_t)m), o_bgr = in.take(channels == 3 ? img_bytes : 16);
+    const size_t o_desc = out.take(32 * (size_t)m);
+    const size_t o_plain = work.take(P.plain_bytes), o_ext = work.take(P.ext_bytes), o_row = work.take(4 * P.row_floats);
+    TRY(ensure_host(ctx, ctx->h_in, in.off + (channels == 1 ? img_bytes + 256 : 0)));
+    TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    // coefficient tables + pattern: rebuilt only when the image size or the level count changes
+    if (ctx->orb_W != W || ctx->orb_H != H || ctx->orb_levels != nlev || !ctx->orb_constants) {
+        Arena t;
+        const size_t o_pat = t.take(1024), o_tab = t.take(4 * P.tab_ints);
+        TRY(ensure_dev(ctx, ctx->d_orb_tab, t.off));
+        std::vector<int> tab(P.tab_ints > 0 ? P.tab_ints : 1);
+        orb_fill_tables(P, tab.data());
+        CK(orb_upload_constants(ctx->d_orb_tab.p + o_pat, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_orb_tab.p + o_tab, tab.data(), 4 * P.tab_ints, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // `tab` is pageable and dies here
+        ctx->orb_W = W; ctx->orb_H = H; ctx->orb_levels = nlev; ctx->orb_constants = true;
+    }
+    const uint8_t* d_pat = ctx->d_orb_tab.p;
+    const int* d_tab = (const int*)(ctx->d_orb_tab.p + 1024);
+    // per-keypoint record: level pixel, level, a = (float)cos(angle), b = (float)sin(angle)
+    uint8_t* h = ctx->h_in.p;
+    int* rec = (int*)(h + o_rec);
+    for (int k = 0; k < m; ++k) {
+        const int i = order[(size_t)k], l = kp_octave[i];
+        const float inv = 1.f / orb_level_scale(l);
+        float angle = kp_angle_deg[i];
+        angle *= (float)(3.141592653589793238462643383279502884 / 180.f);
+        const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+        rec[5 * k] = (int)lrintf(kp_xy[2 * i] * inv);
+        rec[5 * k + 1] = (int)lrintf(kp_xy[2 * i + 1] * inv);
+        rec[5 * k + 2] = l;
+        memcpy(&rec[5 * k + 3], &a, 4); memcpy(&rec[5 * k + 4], &b, 4);
+        order_out[k] = i;
+    }
+    uint8_t* d_plain = ctx->d_work.p + o_plain;
+    if (channels == 3) {
+        for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
+        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    } else {   // gray: level 0 goes straight into the pyramid buffer
+        uint8_t* hg = h + in.off;
+        for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
+        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_plain, hg, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int l = 0;
+    CK(launch_orb_describe(channels == 3 ? ctx->d_in.p + o_bgr : nullptr, W, H, 3 * W, P, d_plain, ctx->d_work.p + o_ext,
+                           (float*)(ctx->d_work.p + o_row), d_tab, d_pat, (const int*)(ctx->d_in.p + o_rec), m,
+                           ctx->d_out.p + o_desc, ctx->stream, &l));
+    ctx->launches += l;
+    ctx->f2m.valid = false; ctx->f2f.valid = false;   // the work arena of a previous frame call was reused
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(desc_out, ctx->h_out.p + o_desc, 32 * (size_t)m);
     return PSLAM_OK;
 }
 

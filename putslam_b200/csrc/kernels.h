@@ -133,4 +133,21 @@ cudaError_t launch_map_prepare(const double* d_xyz, const float* d_view_axis, in
                                uint8_t* d_desc_out = nullptr, const int* d_oct_in = nullptr, int* d_oct_out = nullptr,
                                const double* d_det_in = nullptr, double* d_det_out = nullptr);
 
+// ---- orb.cu ----------------------------------------------------------------------------------
+constexpr int kOrbMaxLevels = 12;
+struct OrbPlan {   // geometry of the pyramid of one image size (offsets in bytes / elements from the buffer bases)
+    int n;
+    int w[kOrbMaxLevels], h[kOrbMaxLevels];
+    int plain_off[kOrbMaxLevels], ext_off[kOrbMaxLevels], tab_off[kOrbMaxLevels];
+    int pix_start[kOrbMaxLevels + 1], ext_start[kOrbMaxLevels + 1];
+    size_t plain_bytes, ext_bytes, row_floats, tab_ints;
+};
+float orb_level_scale(int level);
+size_t orb_plan(int W, int H, int nlevels, OrbPlan* P);
+void orb_fill_tables(const OrbPlan& P, int* tab /* P.tab_ints */);
+cudaError_t orb_upload_constants(void* d_pattern /* 1024 bytes */, cudaStream_t st);
+cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
+                                uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
+                                int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches);
+
 }  // namespace pslam

@@ -1,0 +1,240 @@
+// orb.cu -- K9: ORB descriptors for caller-provided keypoints, i.e. what MatcherOpenCV::describeFeatures obtains from
+// `descriptorExtractor->compute(rgbImage, features, descriptors)` with cv::ORB::create() defaults (reference
+// src/Matcher/matcherOpenCV.cpp:83-84,181-195).  The arithmetic is OpenCV's (un-vendored dependency); it is restated
+// and pinned bit for bit against cv2 4.13.0 by the test suite's numpy restatement.  On the device:
+//   orb_gray_kernel        COLOR_BGR2GRAY, fixed point (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+//   orb_resize_kernel      level l from level l-1, INTER_LINEAR_EXACT: 8.8 coefficient tables (host, double precision),
+//                          horizontal 8.8, vertical 16.16, round half up -- integer, one launch per level (a cascade)
+//   orb_blur_rows_kernel   all levels in one launch: 7-tap float row pass, s = k0*x0, s = fma(k_i, x_i, s)
+//   orb_frame_blur_kernel  all levels in one launch: every pixel of the framed level -- interior = column pass
+//                          s = k3*c, s = fma(k_{3+d}, below + above, s), round-half-even, saturate; 32-pixel frame =
+//                          BORDER_REFLECT_101 of the unblurred level (ORB blurs the sub-matrix in place, the frame keeps
+//                          the unblurred pixels, and rotated patches of coarse-level keypoints do reach into it)
+//   orb_describe_kernel    one warp per keypoint, one descriptor byte per lane: 8 tests x 2 rotated, rounded sample points
+// Images are a few hundred KB: every kernel is latency-bound, the pyramid lives in L2 between them.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+__constant__ float c_gauss7[7];   // getGaussianKernel(7, 2, CV_32F)
+static const uint32_t kGauss7Bits[7] = {0x3d8fafb1u, 0x3e06387eu, 0x3e434a39u, 0x3e5d4ae0u, 0x3e434a39u, 0x3e06387eu, 0x3d8fafb1u};
+
+static const signed char kPatternHost[1024] = {
+#include "orb_pattern.inc"
+};
+
+__device__ __forceinline__ int reflect101(int i, int n) {   // valid for -n < i < 2n - 1 (frames are 32 px, levels >= 33)
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void orb_gray_kernel(const uint8_t* __restrict__ bgr, int W, int H, int row_bytes, uint8_t* __restrict__ gray) {
+    chain_begin();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W || y >= H) return;
+    const uint8_t* p = bgr + (size_t)y * row_bytes + 3 * (size_t)x;
+    gray[(size_t)y * W + x] = (uint8_t)(((int)p[0] * 3735 + (int)p[1] * 19235 + (int)p[2] * 9798 + (1 << 14)) >> 15);
+}
+
+// xtab / ytab: per destination index {source offset, weight of the first sample (8.8)}; second weight = 256 - first
+__global__ void orb_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int src_stride, uint8_t* __restrict__ dst,
+                                  int dw, int dh, const int2* __restrict__ xtab, const int2* __restrict__ ytab) {
+    chain_begin();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int2 cx = xtab[x], cy = ytab[y];
+    const int x0 = cx.x, x1 = min(cx.x + 1, sw - 1), y0 = cy.x, y1 = min(cy.x + 1, sh - 1);
+    const uint8_t* r0 = src + (size_t)y0 * src_stride;
+    const uint8_t* r1 = src + (size_t)y1 * src_stride;
+    const uint32_t h0 = (uint32_t)cx.y * r0[x0] + (uint32_t)(256 - cx.y) * r0[x1];
+    const uint32_t h1 = (uint32_t)cx.y * r1[x0] + (uint32_t)(256 - cx.y) * r1[x1];
+    const uint32_t v = (uint32_t)cy.y * h0 + (uint32_t)(256 - cy.y) * h1;
+    dst[(size_t)y * dw + x] = (uint8_t)((v + 32768u) >> 16);
+}
+
+struct OrbLevels {
+    int n;
+    int w[kOrbMaxLevels], h[kOrbMaxLevels];
+    int plain_off[kOrbMaxLevels];    // level image (w x h, tight), bytes from the pyramid base
+    int ext_off[kOrbMaxLevels];      // framed level ((w + 64) x (h + 64), tight)
+    int pix_start[kOrbMaxLevels + 1];   // prefix of w*h        (row-pass launch)
+    int ext_start[kOrbMaxLevels + 1];   // prefix of (w+64)(h+64) (frame/blur launch)
+};
+
+__global__ void orb_blur_rows_kernel(OrbLevels L, const uint8_t* __restrict__ plain, float* __restrict__ rowbuf) {
+    chain_begin();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L.pix_start[L.n]) return;
+    int l = 0;
+    while (g >= L.pix_start[l + 1]) ++l;
+    const int p = g - L.pix_start[l], w = L.w[l];
+    const int y = p / w, x = p - y * w;
+    const uint8_t* row = plain + L.plain_off[l] + (size_t)y * w;
+    float s = __fmul_rn(c_gauss7[0], (float)row[reflect101(x - 3, w)]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) s = __fmaf_rn(c_gauss7[i], (float)row[reflect101(x - 3 + i, w)], s);
+    rowbuf[g] = s;
+}
+
+constexpr int kOrbBorder = 32;
+__global__ void orb_frame_blur_kernel(OrbLevels L, const uint8_t* __restrict__ plain, const float* __restrict__ rowbuf,
+                                      uint8_t* __restrict__ ext) {
+    chain_begin();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L.ext_start[L.n]) return;
+    int l = 0;
+    while (g >= L.ext_start[l + 1]) ++l;
+    const int p = g - L.ext_start[l], w = L.w[l], h = L.h[l], ew = w + 2 * kOrbBorder;
+    const int ey = p / ew, ex = p - ey * ew;
+    const int x = ex - kOrbBorder, y = ey - kOrbBorder;
+    uint8_t out;
+    if (x >= 0 && x < w && y >= 0 && y < h) {
+        const float* col = rowbuf + L.pix_start[l] + x;
+        float v = __fadd_rn(__fmul_rn(c_gauss7[3], col[(size_t)y * w]), 0.f);
+#pragma unroll
+        for (int d = 1; d <= 3; ++d) {
+            const float t = __fadd_rn(col[(size_t)reflect101(y + d, h) * w], col[(size_t)reflect101(y - d, h) * w]);
+            v = __fmaf_rn(c_gauss7[3 + d], t, v);
+        }
+        const int r = __float2int_rn(v);
+        out = (uint8_t)min(max(r, 0), 255);
+    } else {
+        out = plain[L.plain_off[l] + (size_t)reflect101(y, h) * w + reflect101(x, w)];
+    }
+    ext[L.ext_off[l] + p] = out;
+}
+
+// rec: per kept keypoint {cx, cy (level pixel, frame not included), level, a bits, b bits}
+__global__ void __launch_bounds__(256)
+orb_describe_kernel(OrbLevels L, const uint8_t* __restrict__ ext, const int* __restrict__ rec, int n,
+                    const char4* __restrict__ pattern, uint8_t* __restrict__ desc) {
+    __shared__ char4 spat[256];
+    chain_begin();
+    spat[threadIdx.x] = pattern[threadIdx.x];
+    __syncthreads();
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const int cx = rec[5 * k], cy = rec[5 * k + 1], l = rec[5 * k + 2];
+    const float a = __int_as_float(rec[5 * k + 3]), b = __int_as_float(rec[5 * k + 4]);
+    const int ew = L.w[l] + 2 * kOrbBorder;
+    const uint8_t* centre = ext + L.ext_off[l] + (size_t)(cy + kOrbBorder) * ew + (cx + kOrbBorder);
+    uint32_t byte = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const char4 pt = spat[8 * lane + t];
+        const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int v0 = centre[iy0 * ew + ix0], v1 = centre[iy1 * ew + ix1];
+        byte |= (v0 < v1 ? 1u : 0u) << t;
+    }
+    desc[32 * (size_t)k + lane] = (uint8_t)byte;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+float orb_level_scale(int level) { return (float)pow((double)1.2f, (double)level); }   // ORB's getScale()
+
+void orb_level_size(int W, int H, int level, int* w, int* h) {
+    const float s = orb_level_scale(level);
+    *w = (int)nearbyintf((float)W / s);   // cvRound(float): round half to even
+    *h = (int)nearbyintf((float)H / s);
+}
+
+// interpolationLinear<uchar>::getCoeffs (OpenCV resize, INTER_LINEAR_EXACT): {offset, first weight in 8.8}
+void orb_linear_exact_table(int src, int dst, int* tab /* 2 * dst */) {
+    const double scale = 1.0 / ((double)dst / (double)src);
+    for (int d = 0; d < dst; ++d) {
+        const double fval = scale * ((double)d + 0.5) - 0.5;
+        const double fl = floor(fval);
+        int off = 0, c0 = 256;
+        if (fl >= 0 && src > 1) {
+            if (fl < (double)(src - 1)) {
+                off = (int)fl;
+                c0 = 256 - (int)nearbyint((fval - fl) * 256.0);
+            } else {
+                off = src - 1;
+            }
+        }
+        tab[2 * d] = off; tab[2 * d + 1] = c0;
+    }
+}
+
+size_t orb_plan(int W, int H, int nlevels, OrbPlan* P) {
+    P->n = nlevels;
+    size_t plain = 0, ext = 0, pix = 0, tab = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        orb_level_size(W, H, l, &P->w[l], &P->h[l]);
+        P->plain_off[l] = (int)plain; P->ext_off[l] = (int)ext; P->pix_start[l] = (int)pix; P->ext_start[l] = (int)ext;
+        P->tab_off[l] = (int)tab;
+        plain += (size_t)P->w[l] * P->h[l];
+        ext += (size_t)(P->w[l] + 64) * (P->h[l] + 64);
+        pix += (size_t)P->w[l] * P->h[l];
+        tab += 2 * (size_t)(P->w[l] + P->h[l]);
+    }
+    P->pix_start[nlevels] = (int)pix; P->ext_start[nlevels] = (int)ext;
+    P->plain_bytes = plain; P->ext_bytes = ext; P->row_floats = pix; P->tab_ints = tab;
+    return plain + ext + 4 * pix + 4 * tab;
+}
+
+void orb_fill_tables(const OrbPlan& P, int* tab) {
+    for (int l = 1; l < P.n; ++l) {
+        orb_linear_exact_table(P.w[l - 1], P.w[l], tab + P.tab_off[l]);
+        orb_linear_exact_table(P.h[l - 1], P.h[l], tab + P.tab_off[l] + 2 * P.w[l]);
+    }
+}
+
+cudaError_t orb_upload_constants(void* d_pattern, cudaStream_t st) {
+    float k[7];
+    memcpy(k, kGauss7Bits, sizeof(k));
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_gauss7, k, sizeof(k), 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(d_pattern, kPatternHost, 1024, cudaMemcpyHostToDevice, st);
+}
+
+// d_bgr: H rows of row_bytes (3 bytes per pixel), or nullptr when level 0 (tight W x H gray) is already in d_plain
+cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
+                                uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
+                                int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches) {
+    OrbLevels L;
+    L.n = P.n;
+    for (int l = 0; l < P.n; ++l) {
+        L.w[l] = P.w[l]; L.h[l] = P.h[l]; L.plain_off[l] = P.plain_off[l]; L.ext_off[l] = P.ext_off[l];
+        L.pix_start[l] = P.pix_start[l]; L.ext_start[l] = P.ext_start[l];
+    }
+    L.pix_start[P.n] = P.pix_start[P.n]; L.ext_start[P.n] = P.ext_start[P.n];
+    cudaError_t e;
+    int nl = 0;
+    if (d_bgr) {   // level 0 from the colour image
+        if ((e = launch_chained(orb_gray_kernel, dim3((unsigned)((W + 255) / 256), (unsigned)H), dim3(256), 0, st, d_bgr, W, H,
+                                row_bytes, d_plain)) != cudaSuccess) return e;
+        ++nl;
+    }
+    for (int l = 1; l < P.n; ++l) {
+        const int2* xt = reinterpret_cast<const int2*>(d_tab + P.tab_off[l]);
+        const int2* yt = reinterpret_cast<const int2*>(d_tab + P.tab_off[l] + 2 * P.w[l]);
+        if ((e = launch_chained(orb_resize_kernel, dim3((unsigned)((P.w[l] + 255) / 256), (unsigned)P.h[l]), dim3(256), 0, st,
+                                (const uint8_t*)(d_plain + P.plain_off[l - 1]), P.w[l - 1], P.h[l - 1], P.w[l - 1],
+                                d_plain + P.plain_off[l], P.w[l], P.h[l], xt, yt)) != cudaSuccess) return e;
+        ++nl;
+    }
+    if ((e = launch_chained(orb_blur_rows_kernel, dim3((unsigned)((P.row_floats + 255) / 256)), dim3(256), 0, st, L,
+                            (const uint8_t*)d_plain, d_rowbuf)) != cudaSuccess) return e;
+    if ((e = launch_chained(orb_frame_blur_kernel, dim3((unsigned)((P.ext_bytes + 255) / 256)), dim3(256), 0, st, L,
+                            (const uint8_t*)d_plain, (const float*)d_rowbuf, d_ext)) != cudaSuccess) return e;
+    nl += 2;
+    if (n_kp > 0) {
+        if ((e = launch_chained(orb_describe_kernel, dim3((unsigned)((n_kp + 7) / 8)), dim3(256), 0, st, L, (const uint8_t*)d_ext,
+                                d_rec, n_kp, reinterpret_cast<const char4*>(d_pattern), d_desc)) != cudaSuccess) return e;
+        ++nl;
+    }
+    if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+}  // namespace pslam

@@ -1,0 +1,76 @@
+"""GPU parity tests (-m gpu) of the ORB descriptor path (pslam_orb_describe == cv::ORB::compute with provided keypoints,
+the reference's MatcherOpenCV::describeFeatures, src/Matcher/matcherOpenCV.cpp:181-195): surviving keypoints, their
+order and every descriptor bit against the cv2 golden vectors, the oracle and live cv2."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_orb_describe_golden_cv2(ctx, golden):
+    g = golden["orb_cv2"]
+    for name in g["names"]:
+        order, desc = ctx.orb_describe(g[f"{name}_img"], g[f"{name}_xy"], g[f"{name}_octave"], g[f"{name}_angle"])
+        assert np.array_equal(order, g[f"{name}_order"]), name
+        assert np.array_equal(desc, g[f"{name}_desc"]), name
+
+
+def scene(rng, H, W):
+    import cv2
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 2.0)
+    return cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+
+
+@pytest.mark.parametrize("W,H,n,max_oct", [(640, 480, 1000, 7), (641, 479, 500, 7), (320, 240, 300, 5), (1280, 720, 800, 11),
+                                            (200, 150, 100, 7)])
+def test_orb_describe_vs_oracle_and_live_cv2(ctx, W, H, n, max_oct):
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(W * 31 + H)
+    img = scene(rng, H, W)
+    xy = np.stack([rng.uniform(5, W - 5, n), rng.uniform(5, H - 5, n)], 1).astype(np.float32)
+    octave = rng.integers(0, max_oct + 1, n).astype(np.int32)
+    angle = rng.uniform(0, 360, n).astype(np.float32)
+    order, desc = ctx.orb_describe(img, xy, octave, angle)
+    eo, ed = OO.describe(img, xy, octave, angle)
+    assert np.array_equal(order, eo) and 0 < order.size < n
+    assert np.array_equal(desc, ed)
+    if max_oct <= 7:   # cv::ORB::compute itself (levels beyond nlevels are handled by the same code in OpenCV too)
+        kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(xy, angle, octave)]
+        k2, d2 = cv2.ORB_create().compute(img, kps)
+        assert len(k2) == order.size and np.array_equal(desc, d2)
+        assert all(float(k.pt[0]) == float(xy[i, 0]) and float(k.pt[1]) == float(xy[i, 1]) for k, i in zip(k2, order))
+    # a second call with another level count on the same context (tables are rebuilt), then the first again
+    o2, d2b = ctx.orb_describe(img, xy[octave < 3], octave[octave < 3], angle[octave < 3])
+    e2, ed2 = OO.describe(img, xy[octave < 3], octave[octave < 3], angle[octave < 3])
+    assert np.array_equal(o2, e2) and np.array_equal(d2b, ed2)
+    o3, d3 = ctx.orb_describe(img, xy, octave, angle)
+    assert np.array_equal(o3, order) and np.array_equal(d3, desc)
+
+
+def test_orb_describe_colour_stride_and_edges(ctx):
+    import cv2
+    from oracle import orb_oracle as OO
+    from putslam_b200 import api
+    rng = np.random.default_rng(9)
+    g = scene(rng, 240, 320)
+    bgr = np.stack([g, np.roll(g, 4, 1), 255 - g], 2).copy()
+    n = 200
+    xy = np.stack([rng.uniform(25, 295, n), rng.uniform(25, 215, n)], 1).astype(np.float32)
+    xy[:4] = [[30.5, 100.0], [31.5, 100.0], [288.5, 80.0], [289.5, 80.0]]
+    octave = rng.integers(0, 8, n).astype(np.int32); angle = rng.uniform(0, 360, n).astype(np.float32)
+    order, desc = ctx.orb_describe(bgr, xy, octave, angle)
+    eo, ed = OO.describe(bgr, xy, octave, angle)
+    assert np.array_equal(order, eo) and np.array_equal(desc, ed)
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(xy, angle, octave)]
+    _, d2 = cv2.ORB_create().compute(bgr, kps)
+    assert np.array_equal(desc, d2)
+    # every keypoint outside the border band -> nothing left; no keypoints -> nothing to do; bad octave -> error
+    o, d = ctx.orb_describe(g, np.array([[5.0, 5.0], [318.0, 200.0]], np.float32), [0, 1], [0.0, 10.0])
+    assert o.size == 0 and d.shape == (0, 32)
+    o, d = ctx.orb_describe(g, np.zeros((0, 2), np.float32), np.zeros(0, np.int32), np.zeros(0, np.float32))
+    assert o.size == 0
+    with pytest.raises(api.PslamError):
+        ctx.orb_describe(g, np.array([[100.0, 100.0]], np.float32), [12], [0.0])
+    with pytest.raises(api.PslamError):
+        ctx.orb_describe(g[:60, :80].copy(), np.array([[40.0, 30.0]], np.float32), [7], [0.0])      # level 7 would be 22 x 17
