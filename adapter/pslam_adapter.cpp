@@ -275,6 +275,44 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
+cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint>& features) {
+    cv::Mat descriptors;
+    pslam_ctx* c = dev_.ctx();
+    const int n = (int)features.size();
+    if (!c || rgbImage.empty() || n == 0) {
+        if (!c) logError(c, "describeFeatures", PSLAM_ERR_NO_DEVICE);
+        features.clear();   // cv::ORB::compute leaves no keypoints when it cannot describe any
+        return descriptors;
+    }
+    std::vector<float> xy(2 * (size_t)n), ang((size_t)n);
+    std::vector<int> oct((size_t)n), order((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        xy[2 * i] = features[i].pt.x; xy[2 * i + 1] = features[i].pt.y;
+        oct[i] = features[i].octave; ang[i] = features[i].angle;
+    }
+    descriptors.create(n, 32, CV_8U);
+    int nOut = 0;
+#ifdef PSLAM_USE_REAL_HEADERS
+    const int rowBytes = (int)rgbImage.step[0];
+#else
+    const int rowBytes = (int)rgbImage.step0;
+#endif
+    const int r = pslam_orb_describe(c, rgbImage.data, rgbImage.cols, rgbImage.rows, rowBytes, rgbImage.channels(), xy.data(),
+                                     oct.data(), ang.data(), n, order.data(), &nOut, descriptors.data);
+    if (r != PSLAM_OK) {
+        logError(c, "describeFeatures", r);
+        features.clear();
+        return cv::Mat();
+    }
+    std::vector<cv::KeyPoint> kept((size_t)nOut);
+    for (int k = 0; k < nOut; ++k) kept[(size_t)k] = features[(size_t)order[(size_t)k]];
+    features.swap(kept);
+    if (nOut == 0) return cv::Mat();
+    cv::Mat out(nOut, 32, CV_8U);
+    std::memcpy(out.data, descriptors.data, 32 * (size_t)nOut);
+    return out;
+}
+
 bool MatcherB200::uploadMapFeatures(int first, const MapSide& features, const std::vector<float>& viewAxis) {
     pslam_ctx* c = dev_.ctx();
     const int M = (int)features.octave.size();

@@ -84,6 +84,12 @@ public:
     explicit MatcherB200(int device = 0) : dev_(device) {}
     // MatcherOpenCV::performMatching (src/Matcher/matcherOpenCV.cpp:198-206), NORM_HAMMING + crossCheck
     std::vector<cv::DMatch> performMatching(cv::Mat prevDescriptors, cv::Mat descriptors);
+    // MatcherOpenCV::describeFeatures for descriptor == "ORB" (src/Matcher/matcherOpenCV.cpp:181-195):
+    // cv::ORB::create()->compute(rgbImage, features, descriptors).  rgbImage: CV_8UC3 (converted like ORB does, with
+    // COLOR_BGR2GRAY on the stored channel order) or CV_8UC1.  `features` is filtered and reordered exactly as
+    // cv::ORB::compute does it (keypoints within 31 px of the border dropped, the rest regrouped by octave); returns
+    // one 32-byte row per remaining feature.
+    cv::Mat describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint>& features);
     // knnMatch(k=2) + Lowe ratio (north_star extension): matches with d1 < ratio * d2
     std::vector<cv::DMatch> performMatchingRatio(cv::Mat prevDescriptors, cv::Mat descriptors, float ratio);
 

@@ -143,6 +143,27 @@ int main(int argc, char** argv) {
         wr("mapr_kept.bin", kept);
     }
 
+    // ---- describeFeatures (matcherOpenCV.cpp:181-195): ORB descriptors for provided keypoints, colour image ----
+    {
+        std::ifstream probe(g_dir + "/orb_bgr.bin", std::ios::binary);
+        if (probe) {
+            auto bgr = rd<uint8_t>("orb_bgr.bin");
+            auto dims = rd<int>("orb_dims.bin");                  // H, W
+            auto kxy = rd<float>("orb_xy.bin"); auto koct = rd<int>("orb_octave.bin"); auto kang = rd<float>("orb_angle.bin");
+            cv::Mat img(dims[0], dims[1], CV_8UC3, bgr.data());
+            std::vector<cv::KeyPoint> feats(koct.size());
+            for (size_t i = 0; i < feats.size(); ++i) {
+                feats[i].pt = cv::Point2f(kxy[2 * i], kxy[2 * i + 1]); feats[i].octave = koct[i]; feats[i].angle = kang[i];
+                feats[i].class_id = (int)i;                        // to recover the permutation
+            }
+            cv::Mat d = matcher.describeFeatures(img, feats);
+            std::vector<int> order(feats.size());
+            for (size_t i = 0; i < feats.size(); ++i) order[i] = feats[i].class_id;
+            wr("orb_order.bin", order);
+            wr("orb_desc.bin", std::vector<uint8_t>(d.data, d.data + 32 * (size_t)d.rows));
+        }
+    }
+
     // ---- demoKabsch path (demoKabsch.cpp:1020): createKabschEstimator()->computeTransformation(A, B) ----
     auto A = rd<double>("kabsch_A.bin"), B = rd<double>("kabsch_B.bin");   // row-major n x 3
     const long n = (long)(A.size() / 3);

@@ -6,7 +6,7 @@
 //   cv::DMatch        {int queryIdx, trainIdx, imgIdx; float distance}        (OpenCV core/types.hpp)
 //   cv::Point2f       {float x, y}
 //   cv::KeyPoint      {Point2f pt; float size, angle, response; int octave, class_id}
-//   cv::Mat           rows, cols, data, step[0], isContinuous(), type(), ptr<T>(row), at<T>(r, c)
+//   cv::Mat           rows, cols, data, step[0], isContinuous(), type(), channels(), ptr<T>(row), at<T>(r, c)
 //   Eigen::Vector3f   3 packed floats;   Eigen::Matrix4f  16 floats, column-major
 //   Eigen::MatrixXd   dynamic, column-major double, rows()/cols()/data()/operator()(r, c)
 #pragma once
@@ -22,12 +22,14 @@
 #include <vector>
 
 namespace cv {
-enum { CV_8U_ = 0, CV_16U_ = 2, CV_32F_ = 5 };
+enum { CV_8U_ = 0, CV_16U_ = 2, CV_32F_ = 5, CV_8UC3_ = 16 };   // OpenCV's CV_MAKETYPE values
 #ifndef CV_8U
 #define CV_8U cv::CV_8U_
 #define CV_16U cv::CV_16U_
 #define CV_32F cv::CV_32F_
 #define CV_32FC1 cv::CV_32F_
+#define CV_8UC1 cv::CV_8U_
+#define CV_8UC3 cv::CV_8UC3_
 #endif
 struct DMatch {
     int queryIdx = -1, trainIdx = -1, imgIdx = -1;
@@ -63,7 +65,8 @@ public:
         data = store_->data();
     }
     int type() const { return type_; }
-    size_t elemSize() const { return type_ == CV_8U_ ? 1 : (type_ == CV_16U_ ? 2 : 4); }
+    size_t elemSize() const { return type_ == CV_8U_ ? 1 : (type_ == CV_16U_ ? 2 : (type_ == CV_8UC3_ ? 3 : 4)); }
+    int channels() const { return type_ == CV_8UC3_ ? 3 : 1; }
     bool isContinuous() const { return step0 == (size_t)cols * elemSize(); }
     bool empty() const { return rows == 0 || cols == 0 || !data; }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + step0 * (size_t)r); }

@@ -279,7 +279,47 @@ def frontend_numbers(ctx, steps, warmup):
     out["c2_frame_to_frame"] = {"e2e_ms_per_frame": t_acc / max(1, n_done) * 1e3, "keypoints": 1000,
                                 "mean_inliers": float(np.mean(inl)) if inl else 0.0,
                                 "ransac": "adaptive (reference bound 487)"}
+    out["orb_describe"] = orb_describe_numbers(ctx, steps, warmup)
     return out
+
+
+def orb_describe_numbers(ctx, steps, warmup):
+    """describeFeatures (cv::ORB::compute with provided keypoints): 640x480 gray frame, 1000 keypoints over 8 octaves,
+    host image + keypoints in, descriptors out; cv2's own compute on the host beside it (the reference's call)."""
+    rng = np.random.default_rng(77)
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float64)
+    img = 110 + 50 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + 40 * np.sin((xx + 3 * yy) / 29.0) + rng.normal(0, 10, (480, 640))
+    img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    n = 1000
+    xy = np.stack([rng.uniform(35, 604, n), rng.uniform(35, 444, n)], 1).astype(np.float32)
+    octave = rng.integers(0, 8, n).astype(np.int32); angle = rng.uniform(0, 360, n).astype(np.float32)
+    for _ in range(warmup):
+        order, desc = ctx.orb_describe(img, xy, octave, angle)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        order, desc = ctx.orb_describe(img, xy, octave, angle)
+    res = {"e2e_ms_per_frame": (time.perf_counter() - t0) / steps * 1e3, "keypoints": n, "described": int(order.size),
+           "image": "640x480 gray, uploaded every frame", "h2d_bytes": int(img.size + 20 * order.size),
+           "d2h_bytes": int(32 * order.size)}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(xy, angle, octave)]
+        orb = cv2.ORB_create()
+        k2, d2 = orb.compute(img, kps)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orb.compute(img, kps)
+        res["cv2_compute_ms_1_thread"] = (time.perf_counter() - t0) / 5 * 1e3
+        cv2.setNumThreads(0)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orb.compute(img, kps)
+        res["cv2_compute_ms_all_threads"] = (time.perf_counter() - t0) / 5 * 1e3
+        res["bit_exact_vs_cv2"] = bool(len(k2) == order.size and np.array_equal(d2, desc))
+    except Exception as e:  # noqa: BLE001
+        res["cv2"] = f"unavailable: {e}"
+    return res
 
 
 def native_frontend_numbers(frames, warmup):
@@ -292,7 +332,13 @@ def native_frontend_numbers(frames, warmup):
         return {"unavailable": "adapter/frontend_bench not built"}
     mf = synth.map_frame(M=5000, N=1000, seed=0)
     fp = synth.frame_pair(n=1000, seed=1)
+    rng = np.random.default_rng(77)
+    orb_img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    orb_xy = np.stack([rng.uniform(35, 604, 1000), rng.uniform(35, 444, 1000)], 1)
     with tempfile.TemporaryDirectory() as d:
+        for name, arr, dt in [("orb_img", orb_img, np.uint8), ("orb_xy", orb_xy, np.float32),
+                              ("orb_octave", rng.integers(0, 8, 1000), np.int32), ("orb_angle", rng.uniform(0, 360, 1000), np.float32)]:
+            np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
         for name, arr, dt in [("map_xyz", mf["map_xyz"], np.float64), ("map_desc", mf["map_desc"], np.uint8),
                               ("map_octave", mf["map_octave"], np.int32), ("map_detdist", mf["map_detdist"], np.float64),
                               ("cur_xyz", mf["cur_xyz"], np.float32), ("cur_desc", mf["cur_desc"], np.uint8),

@@ -1164,15 +1164,23 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
         return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_orb_describe: pyramid level %d is %d x %d (must exceed 32 x 32)", nlev - 1,
                     P.w[nlev - 1], P.h[nlev - 1]);
     // KeyPointsFilter::runByImageBorder(edgeThreshold = 31) on the rounded position, then a stable regroup by octave
-    std::vector<int> order;
-    order.reserve((size_t)n);
-    for (int l = 0; l < nlev; ++l)
-        for (int i = 0; i < n; ++i) {
-            if (kp_octave[i] != l) continue;
-            const long ix = lrintf(kp_xy[2 * i]), iy = lrintf(kp_xy[2 * i + 1]);   // cvRound: half to even
-            if (ix >= 31 && ix < W - 31 && iy >= 31 && iy < H - 31) order.push_back(i);
-        }
-    const int m = (int)order.size();
+    std::vector<int> order((size_t)n);
+    int start[kOrbMaxLevels + 1] = {0};
+    auto inside = [&](int i) {
+        const long ix = lrintf(kp_xy[2 * i]), iy = lrintf(kp_xy[2 * i + 1]);   // cvRound: half to even
+        return ix >= 31 && ix < W - 31 && iy >= 31 && iy < H - 31;
+    };
+    for (int i = 0; i < n; ++i) order[(size_t)i] = inside(i) ? kp_octave[i] : -1;   // scratch: level or -1
+    for (int i = 0; i < n; ++i) if (order[(size_t)i] >= 0) ++start[order[(size_t)i] + 1];
+    for (int l = 0; l < nlev; ++l) start[l + 1] += start[l];
+    const int m = start[nlev];
+    {   // counting sort by level, input order kept inside a level
+        std::vector<int> sorted((size_t)(m > 0 ? m : 1));
+        int cur[kOrbMaxLevels];
+        for (int l = 0; l < nlev; ++l) cur[l] = start[l];
+        for (int i = 0; i < n; ++i) if (order[(size_t)i] >= 0) sorted[(size_t)cur[order[(size_t)i]]++] = i;
+        order.swap(sorted);
+    }
     *n_out = m;
     if (m == 0) return PSLAM_OK;
     CK(cudaSetDevice(ctx->device));
@@ -1207,7 +1215,9 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
         const float inv = 1.f / orb_level_scale(l);
         float angle = kp_angle_deg[i];
         angle *= (float)(3.141592653589793238462643383279502884 / 180.f);
-        const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+        double sn, cs;
+        sincos((double)angle, &sn, &cs);   // glibc: the same kernels as sin() and cos()
+        const float a = (float)cs, b = (float)sn;
         rec[5 * k] = (int)lrintf(kp_xy[2 * i] * inv);
         rec[5 * k + 1] = (int)lrintf(kp_xy[2 * i + 1] * inv);
         rec[5 * k + 2] = l;
@@ -1216,11 +1226,13 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
     }
     uint8_t* d_plain = ctx->d_work.p + o_plain;
     if (channels == 3) {
-        for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
+        if (row_bytes == 3 * W) memcpy(h + o_bgr, image, img_bytes);
+        else for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
         CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
     } else {   // gray: level 0 goes straight into the pyramid buffer
         uint8_t* hg = h + in.off;
-        for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
+        if (row_bytes == W) memcpy(hg, image, img_bytes);
+        else for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
         CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_plain, hg, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }

@@ -27,6 +27,11 @@ def test_adapter_end_to_end(tmp_path, O):
     rng = np.random.default_rng(23)
     A = rng.uniform(-1.5, 1.5, (100, 3))
     B = A @ synth.rot_from_rotvec([0.2, 0.1, -0.3]).T + [0.1, 0.2, -0.3] + rng.normal(0, [0.01, 0.02, 0.03], (100, 3))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orb_cv2.npz"))
+    np.array(g["bgr_img"].shape[:2], np.int32).tofile(os.path.join(d, "orb_dims.bin"))
+    for name, arr, dt in [("orb_bgr", g["bgr_img"], np.uint8), ("orb_xy", g["bgr_xy"], np.float32),
+                          ("orb_octave", g["bgr_octave"], np.int32), ("orb_angle", g["bgr_angle"], np.float32)]:
+        np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
     for name, arr, dt in [("desc1", fp["desc1"], np.uint8), ("desc2", fp["desc2"], np.uint8), ("uv1", fp["uv1"], np.float32),
                           ("uv2", fp["uv2"], np.float32), ("depth1", fp["depth1"], np.uint16), ("depth2", fp["depth2"], np.uint16),
                           ("map_xyz", mf["map_xyz"], np.float64), ("map_desc", mf["map_desc"], np.uint8),
@@ -88,6 +93,10 @@ def test_adapter_end_to_end(tmp_path, O):
     assert np.array_equal(bits(_rd(d, "mapr_matches_d.bin", np.float32)), bits(_rd(d, "map1_matches_d.bin", np.float32)))
     assert np.array_equal(bits(_rd(d, "mapr_T.bin", np.float32)), bits(_rd(d, "map1_T.bin", np.float32)))
     assert _rd(d, "mapr_ratio.bin", np.float64)[0] == _rd(d, "map1_ratio.bin", np.float64)[0]
+
+    # ---- describeFeatures: the cv2 golden vectors (colour image), features reordered like cv::ORB::compute does ----
+    assert np.array_equal(_rd(d, "orb_order.bin", np.int32), g["bgr_order"])
+    assert np.array_equal(_rd(d, "orb_desc.bin", np.uint8).reshape(-1, 32), g["bgr_desc"])
 
     # ---- Kabsch ----
     Tk = _rd(d, "kabsch_T.bin", np.float64).reshape(4, 4).T
