@@ -161,3 +161,176 @@ def describe(image, xy, octave, angle_deg):
         bits = (ext[cy + y0, cx + x0] < ext[cy + y1, cx + x1]).astype(np.uint8)
         desc[j] = np.packbits(bits, bitorder="little")
     return order, desc
+
+
+# ======================================================================================================================
+# Detection: what cv::ORB::create()->detect(gray) does (OpenCV 4.13 features2d, computeKeyPoints), the call inside
+# MatcherOpenCV::detectFeatures (reference src/Matcher/matcherOpenCV.cpp:118-176, `featureDetector->detect(roi, kps)`).
+#   per pyramid level (unblurred): FAST-9/16, threshold 20, 3x3 non-maximum suppression on the corner score
+#   -> drop keypoints closer than 31 px to the level's border -> retainBest(2 n_l) by FAST score (ties with the n-th
+#   kept) -> Harris response (7x7 block of Sobel-like derivatives, k = 0.04, float32) -> retainBest(n_l) by Harris
+#   -> intensity-centroid angle (circular patch of radius 15, fastAtan2) -> position * level scale, size = 31 * scale.
+# n_l: nfeatures split over the levels by the factor 1/1.2 (float32 arithmetic, cvRound), remainder on the last level.
+# The functions below return the keypoints of a level in RASTER order; OpenCV's own order inside a level is whatever
+# std::nth_element / std::partition leave behind (the product reproduces it by running the same libstdc++ algorithms
+# on the host; tests compare that order with cv2 directly, and sets / values with this restatement).
+# ======================================================================================================================
+FAST_RING = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+             (-3, 0), (-3, 1), (-2, 2), (-1, 3)]          # (dx, dy), OpenCV's makeOffsets order for patternSize 16
+
+
+def fast_score_map(img, threshold=20):
+    """corner score of every pixel (0 = not a FAST-9 corner at `threshold`): the largest t for which 9 contiguous ring
+    pixels are all brighter than v + t or all darker than v - t (cv::cornerScore<16>)"""
+    H, W = img.shape
+    out = np.zeros((H, W), np.int32)
+    if H < 7 or W < 7:
+        return out
+    I = img.astype(np.int32)
+    c = I[3:H - 3, 3:W - 3]
+    d = np.stack([c - I[3 + dy:H - 3 + dy, 3 + dx:W - 3 + dx] for (dx, dy) in FAST_RING], 0)
+    ext = np.concatenate([d, d[:8]], 0)
+    amin = np.full_like(c, -(1 << 20)); bmax = np.full_like(c, 1 << 20)
+    for k in range(16):
+        seg = ext[k:k + 9]
+        amin = np.maximum(amin, seg.min(0))
+        bmax = np.minimum(bmax, seg.max(0))
+    corner = (amin > threshold) | (bmax < -threshold)
+    out[3:H - 3, 3:W - 3] = np.where(corner, np.maximum(amin, -bmax) - 1, 0)
+    return out
+
+
+def fast_nms(score):
+    """(x, y, score) of the corners that beat all 8 neighbours strictly, raster order (cv::FAST with nonmaxSuppression)"""
+    H, W = score.shape
+    p = np.pad(score, 1)
+    nb = np.max(np.stack([p[1 + dy:H + 1 + dy, 1 + dx:W + 1 + dx] for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)], 0), 0)
+    ys, xs = np.nonzero((score > 0) & (score > nb))
+    return [(int(x), int(y), int(score[y, x])) for y, x in zip(ys, xs)]
+
+
+def features_per_level(nfeatures=500, nlevels=8):
+    factor = f32(1.0 / float(f32(1.2)))
+    nd = f32(nfeatures) * (f32(1) - factor) / (f32(1) - f32(math.pow(float(factor), float(nlevels))))
+    out, s = [], 0
+    for _ in range(nlevels - 1):
+        n = int(np.rint(nd)); out.append(n); s += n
+        nd = f32(nd * factor)
+    out.append(max(nfeatures - s, 0))
+    return out
+
+
+def umax_table(half=15):
+    umax = [0] * (half + 2)
+    vmax = int(math.floor(half * math.sqrt(2.0) / 2 + 1)); vmin = int(math.ceil(half * math.sqrt(2.0) / 2))
+    for v in range(vmax + 1):
+        umax[v] = int(np.rint(math.sqrt(half * half - v * v)))
+    v0 = 0
+    for v in range(half, vmin - 1, -1):
+        while umax[v0] == umax[v0 + 1]:
+            v0 += 1
+        umax[v] = v0; v0 += 1
+    return umax
+
+
+UMAX = umax_table()
+
+
+def retain_best_set(kps, n, key):
+    """KeyPointsFilter::retainBest as a set: the n best plus everything tied with the n-th (input order kept)"""
+    if n < 0 or len(kps) <= n:
+        return list(kps)
+    if n == 0:
+        return []
+    r = sorted((key(k) for k in kps), reverse=True)[n - 1]
+    return [k for k in kps if key(k) >= r]
+
+
+def harris_response(level, x, y):
+    """HarrisResponses(blockSize 7, k 0.04): int sums of Ix^2, Iy^2, IxIy over the 7x7 block, then float32"""
+    p = level[y - 4:y + 5, x - 4:x + 5].astype(np.int64)
+    Ix = (p[1:-1, 2:] - p[1:-1, :-2]) * 2 + (p[:-2, 2:] - p[:-2, :-2]) + (p[2:, 2:] - p[2:, :-2])
+    Iy = (p[2:, 1:-1] - p[:-2, 1:-1]) * 2 + (p[2:, :-2] - p[:-2, :-2]) + (p[2:, 2:] - p[:-2, 2:])
+    a, b, c = f32(int((Ix * Ix).sum())), f32(int((Iy * Iy).sum())), f32(int((Ix * Iy).sum()))
+    scale = f32(1.0) / (f32(4 * 7) * f32(255.0))
+    s4 = f32(f32(f32(scale * scale) * scale) * scale)
+    apb = f32(a + b)
+    return f32(f32(f32(f32(a * b) - f32(c * c)) - f32(f32(f32(0.04) * apb) * apb)) * s4)
+
+
+_P1 = f32(0.9997878412794807) * f32(180 / math.pi); _P3 = f32(-0.3258083974640975) * f32(180 / math.pi)
+_P5 = f32(0.1555786518463281) * f32(180 / math.pi); _P7 = f32(-0.04432655554792128) * f32(180 / math.pi)
+_EPS = f32(2.220446049250313e-16)
+
+
+def fast_atan2(y, x):
+    """cv::fastAtan2 (degrees, 7th-order odd polynomial), float32 without fused operations"""
+    y = f32(y); x = f32(x)
+    ax, ay = abs(x), abs(y)
+    if ax >= ay:
+        c = f32(ay / f32(ax + _EPS)); c2 = f32(c * c)
+        a = f32(f32(f32(f32(f32(f32(f32(_P7 * c2) + _P5) * c2) + _P3) * c2) + _P1) * c)
+    else:
+        c = f32(ax / f32(ay + _EPS)); c2 = f32(c * c)
+        a = f32(f32(90.0) - f32(f32(f32(f32(f32(f32(f32(_P7 * c2) + _P5) * c2) + _P3) * c2) + _P1) * c))
+    if x < 0:
+        a = f32(f32(180.0) - a)
+    if y < 0:
+        a = f32(f32(360.0) - a)
+    return a
+
+
+def ic_moments(level, x, y):
+    """m_01, m_10 of the circular patch of radius 15 (ICAngles)"""
+    I = level.astype(np.int64)
+    u = np.arange(-15, 16)
+    m10 = int((u * I[y, x - 15:x + 16]).sum()); m01 = 0
+    for v in range(1, 16):
+        d = UMAX[v]
+        plus = I[y + v, x - d:x + d + 1]; minus = I[y - v, x - d:x + d + 1]
+        m01 += v * int((plus - minus).sum())
+        m10 += int((np.arange(-d, d + 1) * (plus + minus)).sum())
+    return m01, m10
+
+
+def detect_levels(gray, nlevels=8):
+    """the unblurred pyramid levels detection works on"""
+    H, W = gray.shape
+    levels = [gray]
+    for l in range(1, nlevels):
+        w, h = level_size(W, H, l)
+        levels.append(resize_linear_exact(levels[-1], w, h))
+    return levels
+
+
+def fast_candidates(level, threshold=20, edge=EDGE_THRESHOLD):
+    """FAST corners of one level after non-max suppression and the border filter, raster order: (x, y, score)"""
+    h, w = level.shape
+    return [(x, y, s) for (x, y, s) in fast_nms(fast_score_map(level, threshold)) if edge <= x < w - edge and edge <= y < h - edge]
+
+
+def detect_candidates(gray, nlevels=8):
+    """every level's candidates with all the values OpenCV may need later (what the device hands to the host):
+    (level, x, y, fast_score, harris float32, angle float32), raster order inside a level"""
+    out = []
+    for l, lev in enumerate(detect_levels(gray, nlevels)):
+        for (x, y, s) in fast_candidates(lev):
+            m01, m10 = ic_moments(lev, x, y)
+            out.append((l, x, y, s, harris_response(lev, x, y), fast_atan2(m01, m10)))
+    return out
+
+
+def detect(gray, nfeatures=500, nlevels=8):
+    """cv::ORB::detect as a set per level (raster order inside a level):
+    -> list of (x float32, y float32, size float32, angle float32, response float32, octave)"""
+    npl = features_per_level(nfeatures, nlevels)
+    out = []
+    for l, lev in enumerate(detect_levels(gray, nlevels)):
+        kps = retain_best_set(fast_candidates(lev), 2 * npl[l], key=lambda c: c[2])
+        kps = [(x, y, harris_response(lev, x, y)) for (x, y, s) in kps]
+        kps = retain_best_set(kps, npl[l], key=lambda c: float(c[2]))
+        sc = level_scale(l)
+        for (x, y, hr) in kps:
+            m01, m10 = ic_moments(lev, x, y)
+            out.append((f32(f32(x) * sc), f32(f32(y) * sc), f32(f32(31.0) * sc), fast_atan2(m01, m10), hr, l))
+    return out

@@ -6,6 +6,7 @@ arithmetic of the reference's matching and undistortion calls:
   cv::Mat a - b (saturating) + cv::norm(NORM_HAMMING)  src/Matcher/matcher.cpp:719-721
   cv::undistortPoints                                  src/RGBD/RGBD.cpp:268,298
   cv::ORB::compute (provided keypoints)                src/Matcher/matcherOpenCV.cpp:181-195
+  cv::ORB::detect                                      src/Matcher/matcherOpenCV.cpp:118-176
 
 Run in the build container (cv2 4.13.0):  python tests/golden/make_golden.py
 The vectors are small on purpose; the oracle (oracle/oracle.c) and the CUDA path are both checked
@@ -108,9 +109,29 @@ def orb_cases():
     return out
 
 
+def orb_detect_cases():
+    """cv::ORB::detect (the call inside MatcherOpenCV::detectFeatures, src/Matcher/matcherOpenCV.cpp:118-176), keypoints
+    in OpenCV's own output order: x, y, size, angle, response (float32) and octave."""
+    rng = np.random.default_rng(47)
+    out = {}
+    names = []
+    for name, H, W, nf in (("d500", 240, 320, 500), ("d150", 200, 260, 150)):
+        img = orb_scene(rng, H, W)
+        img = np.clip(img.astype(np.int32) + rng.integers(-25, 26, img.shape), 0, 255).astype(np.uint8)   # more corners
+        kps = cv2.ORB_create(nfeatures=nf).detect(img)
+        out[name + "_img"] = img
+        out[name + "_nfeatures"] = np.int32(nf)
+        out[name + "_kp"] = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kps], np.float32)
+        out[name + "_octave"] = np.array([k.octave for k in kps], np.int32)
+        names.append(name)
+    out["names"] = np.array(names)
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "bf_cv2.npz"), **bf_cases())
     np.savez_compressed(os.path.join(HERE, "satsub_cv2.npz"), **satsub_cases())
     np.savez_compressed(os.path.join(HERE, "undistort_cv2.npz"), **undistort_cases())
     np.savez_compressed(os.path.join(HERE, "orb_cv2.npz"), **orb_cases())
+    np.savez_compressed(os.path.join(HERE, "orb_detect_cv2.npz"), **orb_detect_cases())
     print("cv2", cv2.__version__, "golden vectors written to", HERE)

@@ -418,3 +418,46 @@ def test_orb_pattern_tables_agree():
     nums = [int(x) for line in txt.splitlines() if not line.lstrip().startswith("//") for x in re.findall(r"-?\d+", line)]
     assert len(nums) == 1024 and np.array_equal(np.array(nums).reshape(256, 4), OO.PATTERN)
     assert OO.PATTERN[0].tolist() == [8, -3, 9, 5] and np.abs(OO.PATTERN).max() == 13
+
+
+def _kp_set(kp, octave):
+    return {(float(r[0]), float(r[1]), int(o)): (float(r[2]), float(r[3]), float(r[4])) for r, o in zip(kp, octave)}
+
+
+def test_orb_detect_oracle_matches_cv2_golden(golden):
+    """cv::ORB::detect recorded from cv2 4.13.0: the oracle yields the same keypoints (position, octave) with the same
+    size, angle and Harris response, level by level (OpenCV's order inside a level is an artefact of nth_element)."""
+    from oracle import orb_oracle as OO
+    g = golden["orb_detect_cv2"]
+    for name in g["names"]:
+        mine = OO.detect(g[f"{name}_img"], int(g[f"{name}_nfeatures"]))
+        ref = _kp_set(g[f"{name}_kp"], g[f"{name}_octave"])
+        got = {(float(m[0]), float(m[1]), int(m[5])): (float(m[2]), float(m[3]), float(m[4])) for m in mine}
+        assert got == ref, name
+        assert [m[5] for m in mine] == sorted(m[5] for m in mine)                       # grouped by level
+        assert np.array_equal(np.bincount(g[f"{name}_octave"]), np.bincount([m[5] for m in mine]))
+
+
+def test_orb_detect_stages_against_live_cv2():
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(53)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (240, 320), dtype=np.uint8), (0, 0), 1.4)
+    img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    # FAST-9/16 with non-maximum suppression: positions, raster order and corner scores
+    ref = [(int(k.pt[0]), int(k.pt[1]), int(k.response)) for k in cv2.FastFeatureDetector_create(20, True).detect(img)]
+    assert OO.fast_nms(OO.fast_score_map(img, 20)) == ref and len(ref) > 200
+    # fastAtan2
+    for _ in range(20000):
+        y = float(rng.integers(-300000, 300000)); x = float(rng.integers(-300000, 300000))
+        assert float(OO.fast_atan2(y, x)) == cv2.fastAtan2(y, x)
+    assert float(OO.fast_atan2(0.0, 0.0)) == cv2.fastAtan2(0.0, 0.0)
+    # the split of nfeatures over the levels and the circular patch
+    assert OO.features_per_level(500, 8) == [109, 90, 75, 63, 52, 44, 36, 31] and sum(OO.features_per_level(1000, 8)) == 1000
+    assert OO.UMAX[:16] == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    # whole detector, several feature budgets
+    for nf in (60, 500, 1500):
+        kps = cv2.ORB_create(nfeatures=nf).detect(img)
+        ref = _kp_set(np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kps], np.float32), [k.octave for k in kps])
+        got = {(float(m[0]), float(m[1]), int(m[5])): (float(m[2]), float(m[3]), float(m[4])) for m in OO.detect(img, nf)}
+        assert got == ref, nf
