@@ -133,6 +133,20 @@ PSLAM_API int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, in
                                  const float* kp_xy, const int* kp_octave, const float* kp_angle_deg, int n,
                                  int* order_out, int* n_out, uint8_t* desc_out);
 
+/* pslam_orb_detect == cv::ORB::create(nfeatures)->detect(image), the detector call inside MatcherOpenCV::detectFeatures
+ * (src/Matcher/matcherOpenCV.cpp:62-63,118-176; OpenCV defaults: 8 levels, scale 1.2, edge threshold 31, patch 31, Harris
+ * score, FAST threshold 20).  image: channels 1 (gray) or 3; colour_order 0 = convert with COLOR_BGR2GRAY (what ORB does
+ * to a colour input), 1 = COLOR_RGB2GRAY (what detectFeatures does first, :122).  Per pyramid level the device computes
+ * the FAST-9/16 corner scores, non-maximum suppression, the 31-px border filter, and for every surviving corner the
+ * Harris response and the intensity-centroid angle; OpenCV's two retainBest passes per level run on the host with the
+ * same libstdc++ algorithms (nth_element, partition), so the keypoints come out in OpenCV's order.
+ * Outputs (capacity cap each; n_out receives the count, PSLAM_ERR_CAPACITY if it exceeds cap): kp_xy n x 2 (pt),
+ * kp_size, kp_angle (degrees), kp_response (Harris), kp_octave; class_id is -1 for all, as in OpenCV.  Levels narrower
+ * than 63 pixels simply yield no keypoints (nothing is farther than 31 px from their border). */
+PSLAM_API int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels,
+                               int colour_order, int nfeatures, float* kp_xy, float* kp_size, float* kp_angle,
+                               float* kp_response, int* kp_octave, int cap, int* n_out);
+
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
  * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==

@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -216,6 +216,21 @@ class Context:
                                              _p(an, C.c_float), n, _p(order, C.c_int), C.byref(n_out), _p(desc, C.c_uint8)))
         k = n_out.value
         return order[:k].copy(), desc[:k].copy()
+
+    def orb_detect(self, image, nfeatures=500, colour_order=0, cap=None):
+        """cv::ORB::create(nfeatures).detect(image) -> dict(xy [n,2], size, angle, response float32[n], octave int32[n]),
+        in OpenCV's output order.  image: H x W (gray) or H x W x 3 uint8; colour_order 0 = BGR2GRAY, 1 = RGB2GRAY."""
+        img = np.ascontiguousarray(image, np.uint8)
+        ch = 3 if img.ndim == 3 else 1
+        H, W = img.shape[:2]
+        cap = int(cap if cap is not None else max(16, 4 * nfeatures + 64))
+        xy = np.empty((cap, 2), np.float32); size = np.empty(cap, np.float32); ang = np.empty(cap, np.float32)
+        resp = np.empty(cap, np.float32); octv = np.empty(cap, np.int32); n = C.c_int(0)
+        self._ck(self.lib.pslam_orb_detect(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, int(colour_order), int(nfeatures),
+                                           _p(xy, C.c_float), _p(size, C.c_float), _p(ang, C.c_float), _p(resp, C.c_float),
+                                           _p(octv, C.c_int), cap, C.byref(n)))
+        k = n.value
+        return dict(xy=xy[:k].copy(), size=size[:k].copy(), angle=ang[:k].copy(), response=resp[:k].copy(), octave=octv[:k].copy())
 
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 #include "geometry.cuh"
@@ -1141,6 +1142,23 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
 }
 
 // ---- ORB descriptors ---------------------------------------------------------------------------------
+// resize coefficient tables + sampling pattern + constants: rebuilt only when the image size or the level count changes
+// (layout of d_orb_tab: 1024 bytes of pattern, then the tables)
+static int orb_prepare_tables(pslam_ctx* ctx, int W, int H, int nlev, const OrbPlan& P) {
+    if (ctx->orb_W == W && ctx->orb_H == H && ctx->orb_levels == nlev && ctx->orb_constants) return PSLAM_OK;
+    Arena t;
+    const size_t o_pat = t.take(1024), o_tab = t.take(4 * P.tab_ints);
+    if (o_tab != 1024) return fail(ctx, PSLAM_ERR_CUDA, "orb table layout");
+    TRY(ensure_dev(ctx, ctx->d_orb_tab, t.off));
+    std::vector<int> tab(P.tab_ints > 0 ? P.tab_ints : 1);
+    orb_fill_tables(P, tab.data());
+    CK(orb_upload_constants(ctx->d_orb_tab.p + o_pat, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_orb_tab.p + o_tab, tab.data(), 4 * P.tab_ints, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // `tab` is pageable and dies here
+    ctx->orb_W = W; ctx->orb_H = H; ctx->orb_levels = nlev; ctx->orb_constants = true;
+    return PSLAM_OK;
+}
+
 int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels, const float* kp_xy,
                        const int* kp_octave, const float* kp_angle_deg, int n, int* order_out, int* n_out,
                        uint8_t* desc_out) {
@@ -1193,18 +1211,7 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
     TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
-    // coefficient tables + pattern: rebuilt only when the image size or the level count changes
-    if (ctx->orb_W != W || ctx->orb_H != H || ctx->orb_levels != nlev || !ctx->orb_constants) {
-        Arena t;
-        const size_t o_pat = t.take(1024), o_tab = t.take(4 * P.tab_ints);
-        TRY(ensure_dev(ctx, ctx->d_orb_tab, t.off));
-        std::vector<int> tab(P.tab_ints > 0 ? P.tab_ints : 1);
-        orb_fill_tables(P, tab.data());
-        CK(orb_upload_constants(ctx->d_orb_tab.p + o_pat, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_orb_tab.p + o_tab, tab.data(), 4 * P.tab_ints, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // `tab` is pageable and dies here
-        ctx->orb_W = W; ctx->orb_H = H; ctx->orb_levels = nlev; ctx->orb_constants = true;
-    }
+    TRY(orb_prepare_tables(ctx, W, H, nlev, P));
     const uint8_t* d_pat = ctx->d_orb_tab.p;
     const int* d_tab = (const int*)(ctx->d_orb_tab.p + 1024);
     // per-keypoint record: level pixel, level, a = (float)cos(angle), b = (float)sin(angle)
@@ -1245,6 +1252,124 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memcpy(desc_out, ctx->h_out.p + o_desc, 32 * (size_t)m);
+    return PSLAM_OK;
+}
+
+// KeyPointsFilter::retainBest (OpenCV features2d, keypoint.cpp) on the detector's working records: the n best by
+// response, plus everything tied with the n-th; the order left behind is that of std::nth_element + std::partition,
+// which is what OpenCV's own output order is made of
+struct OrbKp {
+    float x, y, response;   // level pixel, current response (FAST score, later Harris)
+    float harris, angle;
+};
+static void orb_retain_best(std::vector<OrbKp>& k, int n) {
+    if (n >= 0 && k.size() > (size_t)n) {
+        if (n == 0) { k.clear(); return; }
+        std::nth_element(k.begin(), k.begin() + n - 1, k.end(), [](const OrbKp& a, const OrbKp& b) { return a.response > b.response; });
+        const float ambiguous = k[(size_t)n - 1].response;
+        auto new_end = std::partition(k.begin() + n, k.end(), [ambiguous](const OrbKp& a) { return a.response >= ambiguous; });
+        k.resize((size_t)(new_end - k.begin()));
+    }
+}
+
+int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels, int colour_order,
+                     int nfeatures, float* kp_xy, float* kp_size, float* kp_angle, float* kp_response, int* kp_octave, int cap,
+                     int* n_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || !image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W || nfeatures < 0 ||
+        cap < 0 || (colour_order != 0 && colour_order != 1))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_detect: bad argument");
+    *n_out = 0;
+    if (cap > 0 && (!kp_xy || !kp_size || !kp_angle || !kp_response || !kp_octave))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_detect: null buffer");
+    const int nlev = 8;
+    OrbPlan P;
+    orb_plan(W, H, nlev, &P);
+    if (P.w[nlev - 1] < 1 || P.h[nlev - 1] < 1)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "pslam_orb_detect: image too small for an 8-level pyramid");
+    CK(cudaSetDevice(ctx->device));
+    // computeKeyPoints: nfeatures split over the levels by 1 / scaleFactor (float arithmetic, cvRound), rest on the last
+    int per_level[8];
+    {
+        const float factor = (float)(1.0 / (double)1.2f);
+        float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlev));
+        int sum = 0;
+        for (int l = 0; l < nlev - 1; ++l) {
+            per_level[l] = (int)lrintf(nd);
+            sum += per_level[l];
+            nd *= factor;
+        }
+        per_level[nlev - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    }
+    // corners after non-max suppression: strict 3x3 maxima, so at most one per 2x2 block of any level
+    const int ccap = (int)(P.row_floats / 4 + 64);
+    const int first = 12288;                  // records fetched with the header; the rest only if there are more
+    Arena in, out, work;
+    const size_t img_bytes = (size_t)channels * W * H;
+    const size_t o_bgr = in.take(channels == 3 ? img_bytes : 16);
+    const size_t o_hdr = out.take(16), o_cand = out.take(24 * (size_t)ccap);
+    const size_t o_plain = work.take(P.plain_bytes), o_score = work.take(P.row_floats);
+    TRY(ensure_host(ctx, ctx->h_in, in.off + (channels == 1 ? img_bytes + 256 : 0)));
+    TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    TRY(orb_prepare_tables(ctx, W, H, nlev, P));
+    const int* d_tab = (const int*)(ctx->d_orb_tab.p + 1024);
+    uint8_t* h = ctx->h_in.p;
+    uint8_t* d_plain = ctx->d_work.p + o_plain;
+    if (channels == 3) {
+        if (row_bytes == 3 * W) memcpy(h + o_bgr, image, img_bytes);
+        else for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
+        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        uint8_t* hg = h + in.off;
+        if (row_bytes == W) memcpy(hg, image, img_bytes);
+        else for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
+        CK(cudaMemcpyAsync(d_plain, hg, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    unsigned int epoch = 0;
+    TRY(next_epoch(ctx, &epoch));
+    int l = 0;
+    CK(launch_orb_detect(channels == 3 ? ctx->d_in.p + o_bgr : nullptr, colour_order, W, H, 3 * W, P, d_plain,
+                         ctx->d_work.p + o_score, d_tab, 20, (int*)(ctx->d_out.p + o_cand), ccap, (int*)(ctx->d_out.p + o_hdr),
+                         prep_slots(ctx), epoch, ctx->sm_count, ctx->stream, &l));
+    ctx->launches += l;
+    ctx->f2m.valid = false; ctx->f2f.valid = false;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, o_cand + 24 * (size_t)first, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int found = *(const int*)(ctx->h_out.p + o_hdr);
+    if (found > ccap)
+        return fail(ctx, PSLAM_ERR_CAPACITY, "pslam_orb_detect: %d FAST corners after suppression, device buffer holds %d", found, ccap);
+    if (found > first) {
+        CK(cudaMemcpyAsync(ctx->h_out.p + o_cand + 24 * (size_t)first, ctx->d_out.p + o_cand + 24 * (size_t)first,
+                           24 * (size_t)(found - first), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int* rec = (const int*)(ctx->h_out.p + o_cand);
+    int n = 0, pos = 0;
+    std::vector<OrbKp> kp;
+    for (int lev = 0; lev < nlev; ++lev) {
+        kp.clear();
+        for (; pos < found && rec[6 * pos] == lev; ++pos) {
+            OrbKp k;
+            k.x = (float)rec[6 * pos + 1]; k.y = (float)rec[6 * pos + 2]; k.response = (float)rec[6 * pos + 3];
+            memcpy(&k.harris, &rec[6 * pos + 4], 4); memcpy(&k.angle, &rec[6 * pos + 5], 4);
+            kp.push_back(k);
+        }
+        orb_retain_best(kp, 2 * per_level[lev]);          // "keep more points than necessary as FAST does not give amazing corners"
+        for (OrbKp& k : kp) k.response = k.harris;
+        orb_retain_best(kp, per_level[lev]);
+        const float sf = orb_level_scale(lev);
+        for (const OrbKp& k : kp) {
+            if (n < cap) {
+                kp_xy[2 * n] = k.x * sf; kp_xy[2 * n + 1] = k.y * sf;
+                kp_size[n] = 31 * sf; kp_angle[n] = k.angle; kp_response[n] = k.response; kp_octave[n] = lev;
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
+    if (n > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "pslam_orb_detect: %d keypoints, capacity %d", n, cap);
     return PSLAM_OK;
 }
 

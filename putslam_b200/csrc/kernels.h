@@ -146,6 +146,12 @@ float orb_level_scale(int level);
 size_t orb_plan(int W, int H, int nlevels, OrbPlan* P);
 void orb_fill_tables(const OrbPlan& P, int* tab /* P.tab_ints */);
 cudaError_t orb_upload_constants(void* d_pattern /* 1024 bytes */, cudaStream_t st);
+// detection: candidates = 6 ints each {level, x, y, FAST score, Harris bits, angle bits}, raster order per level;
+// d_header[0] = number found (may exceed cap; only cap are stored).  d_bgr / rgb_order as orb_gray_kernel.
+cudaError_t launch_orb_detect(const uint8_t* d_bgr, int rgb_order, int W, int H, int row_bytes, const OrbPlan& P,
+                              uint8_t* d_plain, uint8_t* d_score, const int* d_tab, int fast_threshold, int* d_cand, int cap,
+                              int* d_header, unsigned long long* d_cta_counts, unsigned int epoch, int sm_count,
+                              cudaStream_t st, int* launches);
 cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
                                 uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
                                 int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches);

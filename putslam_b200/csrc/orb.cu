@@ -32,12 +32,15 @@ __device__ __forceinline__ int reflect101(int i, int n) {   // valid for -n < i 
     return i;
 }
 
-__global__ void orb_gray_kernel(const uint8_t* __restrict__ bgr, int W, int H, int row_bytes, uint8_t* __restrict__ gray) {
+// rgb_order 0: COLOR_BGR2GRAY (what cv::ORB does to a colour input); 1: COLOR_RGB2GRAY (detectFeatures, :122)
+__global__ void orb_gray_kernel(const uint8_t* __restrict__ bgr, int W, int H, int row_bytes, uint8_t* __restrict__ gray,
+                                int rgb_order) {
     chain_begin();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W || y >= H) return;
     const uint8_t* p = bgr + (size_t)y * row_bytes + 3 * (size_t)x;
-    gray[(size_t)y * W + x] = (uint8_t)(((int)p[0] * 3735 + (int)p[1] * 19235 + (int)p[2] * 9798 + (1 << 14)) >> 15);
+    const int c0 = rgb_order ? p[2] : p[0], c2 = rgb_order ? p[0] : p[2];
+    gray[(size_t)y * W + x] = (uint8_t)((c0 * 3735 + (int)p[1] * 19235 + c2 * 9798 + (1 << 14)) >> 15);
 }
 
 // xtab / ytab: per destination index {source offset, weight of the first sample (8.8)}; second weight = 256 - first
@@ -137,6 +140,191 @@ orb_describe_kernel(OrbLevels L, const uint8_t* __restrict__ ext, const int* __r
     desc[32 * (size_t)k + lane] = (uint8_t)byte;
 }
 
+// ---- K10: detection (cv::ORB::detect == the call inside MatcherOpenCV::detectFeatures, reference
+// src/Matcher/matcherOpenCV.cpp:118-176).  Device: FAST-9/16 corner score of every pixel of every (unblurred) level,
+// 3x3 non-maximum suppression + 31-px border filter + ordered (raster) compaction, Harris response and
+// intensity-centroid angle of every surviving corner.  Host (ctx.cu): OpenCV's two retainBest passes per level with the
+// same libstdc++ algorithms, so that even the order inside a level is OpenCV's.
+__constant__ int c_umax[16];
+static const int kUmaxHost[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// score = largest t for which 9 contiguous ring pixels are all > v + t or all < v - t (cv::cornerScore<16>); 0 unless
+// that holds for `threshold`.  Window minima by doubling: w2, w4, w8, then w9 = min(w8[k], d[k + 8]).
+__global__ void orb_fast_score_kernel(OrbLevels L, const uint8_t* __restrict__ plain, uint8_t* __restrict__ score,
+                                      int threshold) {
+    chain_begin();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L.pix_start[L.n]) return;
+    int l = 0;
+    while (g >= L.pix_start[l + 1]) ++l;
+    const int p = g - L.pix_start[l], w = L.w[l], h = L.h[l];
+    const int y = p / w, x = p - y * w;
+    uint8_t out = 0;
+    if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+        const uint8_t* c = plain + L.plain_off[l] + (size_t)y * w + x;
+        const int v = c[0];
+        int d[16];
+        d[0] = v - c[3 * w];          d[1] = v - c[3 * w + 1];      d[2] = v - c[2 * w + 2];      d[3] = v - c[w + 3];
+        d[4] = v - c[3];              d[5] = v - c[-w + 3];         d[6] = v - c[-2 * w + 2];     d[7] = v - c[-3 * w + 1];
+        d[8] = v - c[-3 * w];         d[9] = v - c[-3 * w - 1];     d[10] = v - c[-2 * w - 2];    d[11] = v - c[-w - 3];
+        d[12] = v - c[-3];            d[13] = v - c[w - 3];         d[14] = v - c[2 * w - 2];     d[15] = v - c[3 * w - 1];
+        int lo[16], hi[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo[k] = min(d[k], d[(k + 1) & 15]); hi[k] = max(d[k], d[(k + 1) & 15]); }
+        int lo4[16], hi4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo[k], lo[(k + 2) & 15]); hi4[k] = max(hi[k], hi[(k + 2) & 15]); }
+        int amin = -(1 << 20), bmax = 1 << 20;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+            const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+            amin = max(amin, lo9);
+            bmax = min(bmax, hi9);
+        }
+        if (amin > threshold || bmax < -threshold) out = (uint8_t)(max(amin, -bmax) - 1);
+    }
+    score[g] = out;
+}
+
+__device__ __forceinline__ bool orb_is_candidate(const OrbLevels& L, const uint8_t* __restrict__ score, int g, int& lvl,
+                                                 int& x, int& y, int& sc) {
+    int l = 0;
+    while (g >= L.pix_start[l + 1]) ++l;
+    const int p = g - L.pix_start[l], w = L.w[l], h = L.h[l];
+    y = p / w; x = p - y * w; lvl = l;
+    if (x < 31 || x >= w - 31 || y < 31 || y >= h - 31) return false;   // runByImageBorder(edgeThreshold) on the level
+    const uint8_t* s = score + g;
+    sc = s[0];
+    if (sc == 0) return false;
+    return sc > s[-1] && sc > s[1] && sc > s[-w - 1] && sc > s[-w] && sc > s[-w + 1] && sc > s[w - 1] && sc > s[w] &&
+           sc > s[w + 1];
+}
+
+// cand: 6 ints per candidate {level, x, y, FAST score, Harris bits, angle bits}; header[0] = count (may exceed cap)
+__global__ void __launch_bounds__(256)
+orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_cta, int* __restrict__ cand, int cap,
+                      int* __restrict__ header, unsigned long long* __restrict__ cta_counts, unsigned int epoch) {
+    __shared__ int warp_tot[8];
+    __shared__ int s_base;
+    chain_begin();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = L.pix_start[L.n];
+    const int lo = min(total, (int)blockIdx.x * per_cta), hi = min(total, lo + per_cta);
+    int mine = 0;
+    for (int g = lo + tid; g < hi; g += 256) {
+        int l, x, y, sc;
+        mine += orb_is_candidate(L, score, g, l, x, y, sc) ? 1 : 0;
+    }
+    mine = (int)warp_add_u32((uint32_t)mine);
+    if (lane == 0) warp_tot[warp] = mine;
+    __syncthreads();
+    if (warp == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+        volatile unsigned long long* sums = cta_counts;
+        if (lane == 0) sums[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)tot;
+        int before = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+            unsigned long long v;
+            do { v = sums[b]; } while ((unsigned int)(v >> 32) != epoch);
+            before += (int)(unsigned int)(v & 0xffffffffu);
+        }
+        before = (int)warp_add_u32((uint32_t)before);
+        if (lane == 0) {
+            s_base = before;
+            if (blockIdx.x == gridDim.x - 1) header[0] = before + tot;
+        }
+    }
+    __syncthreads();
+    int carry = s_base;
+    for (int base = lo; base < hi; base += 256) {
+        const int g = base + tid;
+        int l = 0, x = 0, y = 0, sc = 0;
+        const bool is = g < hi && orb_is_candidate(L, score, g, l, x, y, sc);
+        const uint32_t bal = __ballot_sync(0xffffffffu, is);
+        __syncthreads();
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int c = warp_tot[w];
+            if (w < warp) woff += c;
+            tot += c;
+        }
+        if (is) {
+            const int pos = carry + woff + __popc(bal & ((1u << lane) - 1u));
+            if (pos < cap) {
+                int* r = cand + 6 * (size_t)pos;
+                r[0] = l; r[1] = x; r[2] = y; r[3] = sc;
+            }
+        }
+        carry += tot;
+    }
+}
+
+// cv::fastAtan2 (degrees): 7th-order odd polynomial, float32, no fused operations (the library is built with -fmad=false)
+__device__ __forceinline__ float orb_fast_atan2(float y, float x) {
+    const float rad = (float)(180.0 / 3.141592653589793238462643383279502884);
+    const float p1 = 0.9997878412794807f * rad, p3 = -0.3258083974640975f * rad, p5 = 0.1555786518463281f * rad,
+                p7 = -0.04432655554792128f * rad;
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, ax + eps); c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = __fdiv_rn(ax, ay + eps); c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// one warp per candidate: HarrisResponses (block 7, k 0.04) and the ICAngles moments, integer sums by warp reduction
+__global__ void __launch_bounds__(256)
+orb_harris_angle_kernel(OrbLevels L, const uint8_t* __restrict__ plain, int* __restrict__ cand, int cap,
+                        const int* __restrict__ header) {
+    chain_begin();
+    const int n = min(header[0], cap);
+    const int lane = threadIdx.x & 31;
+    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < n; k += gridDim.x * 8) {
+        int* r = cand + 6 * (size_t)k;
+        const int l = r[0], x = r[1], y = r[2], w = L.w[l];
+        const uint8_t* c = plain + L.plain_off[l] + (size_t)y * w + x;
+        int a = 0, b = 0, cc = 0;
+        for (int q = lane; q < 49; q += 32) {
+            const int i = q / 7 - 3, j = q % 7 - 3;
+            const uint8_t* p = c + i * w + j;
+            const int Ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-w + 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[w - 1]);
+            const int Iy = ((int)p[w] - (int)p[-w]) * 2 + ((int)p[w - 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[-w + 1]);
+            a += Ix * Ix; b += Iy * Iy; cc += Ix * Iy;
+        }
+        int m01 = 0, m10 = 0;
+        if (lane < 31) {
+            const int v = lane - 15, d = c_umax[v < 0 ? -v : v];
+            const uint8_t* row = c + v * w;
+            int s = 0, su = 0;
+            for (int u = -d; u <= d; ++u) { const int val = row[u]; s += val; su += u * val; }
+            m01 = v * s; m10 = su;
+        }
+        a = (int)warp_add_u32((uint32_t)a); b = (int)warp_add_u32((uint32_t)b); cc = (int)warp_add_u32((uint32_t)cc);
+        m01 = (int)warp_add_u32((uint32_t)m01); m10 = (int)warp_add_u32((uint32_t)m10);
+        if (lane == 0) {
+            const float scale = __fdiv_rn(1.f, (float)(4 * 7) * 255.f);
+            const float s4 = scale * scale * scale * scale;
+            const float fa = (float)a, fb = (float)b, fc = (float)cc;
+            const float resp = (fa * fb - fc * fc - 0.04f * (fa + fb) * (fa + fb)) * s4;
+            r[4] = __float_as_int(resp);
+            r[5] = __float_as_int(orb_fast_atan2((float)m01, (float)m10));
+        }
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 float orb_level_scale(int level) { return (float)pow((double)1.2f, (double)level); }   // ORB's getScale()
 
@@ -194,26 +382,18 @@ cudaError_t orb_upload_constants(void* d_pattern, cudaStream_t st) {
     memcpy(k, kGauss7Bits, sizeof(k));
     cudaError_t e = cudaMemcpyToSymbolAsync(c_gauss7, k, sizeof(k), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbolAsync(c_umax, kUmaxHost, sizeof(kUmaxHost), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     return cudaMemcpyAsync(d_pattern, kPatternHost, 1024, cudaMemcpyHostToDevice, st);
 }
 
-// d_bgr: H rows of row_bytes (3 bytes per pixel), or nullptr when level 0 (tight W x H gray) is already in d_plain
-cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
-                                uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
-                                int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches) {
-    OrbLevels L;
-    L.n = P.n;
-    for (int l = 0; l < P.n; ++l) {
-        L.w[l] = P.w[l]; L.h[l] = P.h[l]; L.plain_off[l] = P.plain_off[l]; L.ext_off[l] = P.ext_off[l];
-        L.pix_start[l] = P.pix_start[l]; L.ext_start[l] = P.ext_start[l];
-    }
-    L.pix_start[P.n] = P.pix_start[P.n]; L.ext_start[P.n] = P.ext_start[P.n];
+// the (unblurred) pyramid: level 0 in d_plain (or made from d_bgr), levels 1.. by the resize cascade
+static cudaError_t launch_orb_pyramid(const uint8_t* d_bgr, int rgb_order, int W, int H, int row_bytes, const OrbPlan& P,
+                                      uint8_t* d_plain, const int* d_tab, cudaStream_t st, int* nl) {
     cudaError_t e;
-    int nl = 0;
-    if (d_bgr) {   // level 0 from the colour image
+    if (d_bgr) {
         if ((e = launch_chained(orb_gray_kernel, dim3((unsigned)((W + 255) / 256), (unsigned)H), dim3(256), 0, st, d_bgr, W, H,
-                                row_bytes, d_plain)) != cudaSuccess) return e;
-        ++nl;
+                                row_bytes, d_plain, rgb_order)) != cudaSuccess) return e;
+        ++*nl;
     }
     for (int l = 1; l < P.n; ++l) {
         const int2* xt = reinterpret_cast<const int2*>(d_tab + P.tab_off[l]);
@@ -221,8 +401,29 @@ cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_byte
         if ((e = launch_chained(orb_resize_kernel, dim3((unsigned)((P.w[l] + 255) / 256), (unsigned)P.h[l]), dim3(256), 0, st,
                                 (const uint8_t*)(d_plain + P.plain_off[l - 1]), P.w[l - 1], P.h[l - 1], P.w[l - 1],
                                 d_plain + P.plain_off[l], P.w[l], P.h[l], xt, yt)) != cudaSuccess) return e;
-        ++nl;
+        ++*nl;
     }
+    return cudaSuccess;
+}
+
+static void orb_levels_from_plan(const OrbPlan& P, OrbLevels& L) {
+    L.n = P.n;
+    for (int l = 0; l < P.n; ++l) {
+        L.w[l] = P.w[l]; L.h[l] = P.h[l]; L.plain_off[l] = P.plain_off[l]; L.ext_off[l] = P.ext_off[l];
+        L.pix_start[l] = P.pix_start[l]; L.ext_start[l] = P.ext_start[l];
+    }
+    L.pix_start[P.n] = P.pix_start[P.n]; L.ext_start[P.n] = P.ext_start[P.n];
+}
+
+// d_bgr: H rows of row_bytes (3 bytes per pixel), or nullptr when level 0 (tight W x H gray) is already in d_plain
+cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
+                                uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
+                                int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches) {
+    OrbLevels L;
+    orb_levels_from_plan(P, L);
+    int nl = 0;
+    cudaError_t e = launch_orb_pyramid(d_bgr, 0, W, H, row_bytes, P, d_plain, d_tab, st, &nl);
+    if (e != cudaSuccess) return e;
     if ((e = launch_chained(orb_blur_rows_kernel, dim3((unsigned)((P.row_floats + 255) / 256)), dim3(256), 0, st, L,
                             (const uint8_t*)d_plain, d_rowbuf)) != cudaSuccess) return e;
     if ((e = launch_chained(orb_frame_blur_kernel, dim3((unsigned)((P.ext_bytes + 255) / 256)), dim3(256), 0, st, L,
@@ -234,6 +435,33 @@ cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_byte
         ++nl;
     }
     if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_orb_detect(const uint8_t* d_bgr, int rgb_order, int W, int H, int row_bytes, const OrbPlan& P,
+                              uint8_t* d_plain, uint8_t* d_score, const int* d_tab, int fast_threshold, int* d_cand, int cap,
+                              int* d_header, unsigned long long* d_cta_counts, unsigned int epoch, int sm_count,
+                              cudaStream_t st, int* launches) {
+    OrbLevels L;
+    orb_levels_from_plan(P, L);
+    int nl = 0;
+    cudaError_t e = launch_orb_pyramid(d_bgr, rgb_order, W, H, row_bytes, P, d_plain, d_tab, st, &nl);
+    if (e != cudaSuccess) return e;
+    const int total = (int)P.row_floats;
+    if ((e = launch_chained(orb_fast_score_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, L,
+                            (const uint8_t*)d_plain, d_score, fast_threshold)) != cudaSuccess) return e;
+    int grid = sm_count > 0 ? sm_count : 1;
+    int per_cta = (total + grid - 1) / grid;
+    per_cta = (per_cta + 255) / 256 * 256;
+    grid = (total + per_cta - 1) / per_cta;
+    if (grid < 1) grid = 1;
+    if ((e = launch_chained(orb_candidates_kernel, dim3((unsigned)grid), dim3(256), 0, st, L, (const uint8_t*)d_score, per_cta,
+                            d_cand, cap, d_header, d_cta_counts, epoch)) != cudaSuccess) return e;
+    int hgrid = (cap + 7) / 8;
+    if (hgrid > 8 * (sm_count > 0 ? sm_count : 1)) hgrid = 8 * (sm_count > 0 ? sm_count : 1);
+    if ((e = launch_chained(orb_harris_angle_kernel, dim3((unsigned)hgrid), dim3(256), 0, st, L, (const uint8_t*)d_plain, d_cand,
+                            cap, (const int*)d_header)) != cudaSuccess) return e;
+    if (launches) *launches += nl + 3;
     return cudaGetLastError();
 }
 

@@ -74,3 +74,79 @@ def test_orb_describe_colour_stride_and_edges(ctx):
         ctx.orb_describe(g, np.array([[100.0, 100.0]], np.float32), [12], [0.0])
     with pytest.raises(api.PslamError):
         ctx.orb_describe(g[:60, :80].copy(), np.array([[40.0, 30.0]], np.float32), [7], [0.0])      # level 7 would be 22 x 17
+
+
+# ---------------------------------------------------------------- detection
+def _rows(d):
+    return np.column_stack([d["xy"], d["size"], d["angle"], d["response"]]).astype(np.float32), d["octave"]
+
+
+def test_orb_detect_golden_cv2(ctx, golden):
+    """cv::ORB::detect recorded from cv2: same keypoints, same values, SAME ORDER (the host half runs OpenCV's
+    retainBest with the same libstdc++ algorithms)"""
+    g = golden["orb_detect_cv2"]
+    for name in g["names"]:
+        kp, octave = _rows(ctx.orb_detect(g[f"{name}_img"], int(g[f"{name}_nfeatures"])))
+        assert np.array_equal(octave, g[f"{name}_octave"]), name
+        assert np.array_equal(kp.view(np.uint32), g[f"{name}_kp"].view(np.uint32)), name
+
+
+@pytest.mark.parametrize("W,H,nf,sigma", [(640, 480, 500, 1.6), (640, 480, 2000, 1.2), (641, 479, 300, 2.0), (1280, 720, 1000, 1.5),
+                                           (512, 512, 50, 1.0)])
+def test_orb_detect_vs_live_cv2_and_oracle(ctx, W, H, nf, sigma):
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(W + 7 * H + nf)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), sigma)
+    img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    out = ctx.orb_detect(img, nf)
+    ref = cv2.ORB_create(nfeatures=nf).detect(img)
+    assert len(ref) == out["octave"].size and len(ref) > 0.5 * nf
+    rk = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in ref], np.float32)
+    kp, octave = _rows(out)
+    assert np.array_equal(octave, [k.octave for k in ref])
+    assert np.array_equal(kp.view(np.uint32), rk.view(np.uint32))            # order included
+    if W * H <= 640 * 480:
+        mine = OO.detect(img, nf)
+        got = {(float(m[0]), float(m[1]), int(m[5])): (float(m[2]), float(m[3]), float(m[4])) for m in mine}
+        dev = {(float(r[0]), float(r[1]), int(o)): (float(r[2]), float(r[3]), float(r[4])) for r, o in zip(kp, octave)}
+        assert got == dev
+
+
+def test_orb_detect_candidates_vs_oracle(ctx):
+    """nfeatures large enough that nothing is culled: every FAST corner that survives suppression and the border filter
+    comes back, with the oracle's Harris response and angle"""
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(12)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (300, 400), dtype=np.uint8), (0, 0), 1.8)
+    img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    out = ctx.orb_detect(img, 200000, cap=300000)
+    cands = OO.detect_candidates(img)
+    assert len(cands) == out["octave"].size and len(cands) > 300
+    got = {(float(x), float(y), int(o)): (float(a), float(r)) for (x, y), a, r, o in zip(out["xy"], out["angle"], out["response"], out["octave"])}
+    for (l, x, y, s, hr, ang) in cands:
+        sc = OO.level_scale(l)
+        key = (float(np.float32(x) * sc), float(np.float32(y) * sc), l)
+        assert got[key] == (float(ang), float(hr)), (l, x, y)
+
+
+def test_orb_detect_colour_and_edges(ctx):
+    import cv2
+    from putslam_b200 import api
+    rng = np.random.default_rng(3)
+    g = cv2.GaussianBlur(rng.integers(0, 256, (480, 640), dtype=np.uint8), (0, 0), 1.5)
+    rgb = np.stack([g, np.roll(g, 2, 1), 255 - np.roll(g, 3, 0)], 2).copy()
+    for order, code in ((0, cv2.COLOR_BGR2GRAY), (1, cv2.COLOR_RGB2GRAY)):
+        out = ctx.orb_detect(rgb, 400, colour_order=order)
+        ref = cv2.ORB_create(nfeatures=400).detect(cv2.cvtColor(rgb, code))
+        rk = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in ref], np.float32)
+        assert np.array_equal(_rows(out)[0].view(np.uint32), rk.view(np.uint32)) and len(ref) > 100
+    flat = np.full((480, 640), 128, np.uint8)
+    assert ctx.orb_detect(flat, 500)["octave"].size == 0                      # no corners at all
+    assert ctx.orb_detect(g, 0)["octave"].size == 0                           # zero budget
+    small = ctx.orb_detect(g[:100, :120].copy(), 100)                         # upper levels narrower than the border band
+    ref = cv2.ORB_create(nfeatures=100).detect(g[:100, :120].copy())
+    assert small["octave"].size == len(ref) and (small["octave"] <= 2).all()
+    with pytest.raises(api.PslamError):
+        ctx.orb_detect(g, 500, cap=10)                                        # more keypoints than the caller's buffers hold
