@@ -275,6 +275,51 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
+std::vector<cv::KeyPoint> MatcherB200::detectFeatures(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures) {
+    std::vector<cv::KeyPoint> raw_keypoints;
+    pslam_ctx* c = dev_.ctx();
+    if (!c || rgbImage.empty() || gridCols <= 0 || gridRows <= 0) {
+        if (!c) logError(c, "detectFeatures", PSLAM_ERR_NO_DEVICE);
+        return raw_keypoints;
+    }
+    const auto compare_response = [](const cv::KeyPoint& p1, const cv::KeyPoint& p2) { return p1.response > p2.response; };
+    const int W = rgbImage.cols, H = rgbImage.rows, ch = rgbImage.channels();
+#ifdef PSLAM_USE_REAL_HEADERS
+    const int rowBytes = (int)rgbImage.step[0];
+#else
+    const int rowBytes = (int)rgbImage.step0;
+#endif
+    const int maximalFeaturesInROI = maximalTrackedFeatures * 3 / (gridCols * gridRows);
+    const int cap = 4096;                     // cv::ORB::create() keeps 500 per call; tied responses can add a few
+    std::vector<float> xy(2 * (size_t)cap), size((size_t)cap), angle((size_t)cap), response((size_t)cap);
+    std::vector<int> octave((size_t)cap);
+    for (int k = 0; k < gridCols; k++) {
+        for (int i = 0; i < gridRows; i++) {
+            const int x0 = k * W / gridCols, y0 = i * H / gridRows, w = W / gridCols, h = H / gridRows;
+            int n = 0;
+            const int r = pslam_orb_detect(c, rgbImage.data + (size_t)y0 * rowBytes + (size_t)x0 * ch, w, h, rowBytes, ch,
+                                           /*COLOR_RGB2GRAY, :122*/ 1, 500, xy.data(), size.data(), angle.data(), response.data(),
+                                           octave.data(), cap, &n);
+            if (r != PSLAM_OK) { logError(c, "detectFeatures", r); continue; }
+            std::vector<cv::KeyPoint> keypointsInROI((size_t)n);
+            for (int j = 0; j < n; ++j) {
+                cv::KeyPoint& kp = keypointsInROI[(size_t)j];
+                kp.pt = cv::Point2f(xy[2 * j], xy[2 * j + 1]);
+                kp.size = size[j]; kp.angle = angle[j]; kp.response = response[j]; kp.octave = octave[j]; kp.class_id = -1;
+            }
+            std::sort(keypointsInROI.begin(), keypointsInROI.end(), compare_response);
+            for (size_t j = 0; j < keypointsInROI.size() && (int)j < maximalFeaturesInROI; j++) {
+                keypointsInROI[j].pt.x += float(x0);
+                keypointsInROI[j].pt.y += float(y0);
+                raw_keypoints.push_back(keypointsInROI[j]);
+            }
+        }
+    }
+    std::sort(raw_keypoints.begin(), raw_keypoints.end(), compare_response);
+    if ((int)raw_keypoints.size() > maximalTrackedFeatures) raw_keypoints.resize((size_t)maximalTrackedFeatures);
+    return raw_keypoints;
+}
+
 cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint>& features) {
     cv::Mat descriptors;
     pslam_ctx* c = dev_.ctx();

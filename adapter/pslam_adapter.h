@@ -84,6 +84,12 @@ public:
     explicit MatcherB200(int device = 0) : dev_(device) {}
     // MatcherOpenCV::performMatching (src/Matcher/matcherOpenCV.cpp:198-206), NORM_HAMMING + crossCheck
     std::vector<cv::DMatch> performMatching(cv::Mat prevDescriptors, cv::Mat descriptors);
+    // MatcherOpenCV::detectFeatures for detector == "ORB" (src/Matcher/matcherOpenCV.cpp:118-176): RGB -> gray, the image
+    // cut into gridCols x gridRows cells, cv::ORB::create()->detect on every cell (pslam_orb_detect), per cell the best
+    // maximalTrackedFeatures * 3 / (gridCols * gridRows) by response, all cells merged, sorted by response and cut to
+    // maximalTrackedFeatures.  The sorts are std::sort with the reference's comparator (matcherOpenCV.h:84-87).
+    std::vector<cv::KeyPoint> detectFeatures(cv::Mat rgbImage, int gridCols = 1, int gridRows = 1,
+                                             int maximalTrackedFeatures = 500);
     // MatcherOpenCV::describeFeatures for descriptor == "ORB" (src/Matcher/matcherOpenCV.cpp:181-195):
     // cv::ORB::create()->compute(rgbImage, features, descriptors).  rgbImage: CV_8UC3 (converted like ORB does, with
     // COLOR_BGR2GRAY on the stored channel order) or CV_8UC1.  `features` is filtered and reordered exactly as

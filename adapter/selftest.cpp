@@ -164,6 +164,27 @@ int main(int argc, char** argv) {
         }
     }
 
+    // ---- detectFeatures (matcherOpenCV.cpp:118-176) on a colour frame, 1 x 1 (shipped config) and 2 x 2 grids ----
+    {
+        std::ifstream probe(g_dir + "/det_rgb.bin", std::ios::binary);
+        if (probe) {
+            auto rgb = rd<uint8_t>("det_rgb.bin");
+            auto dims = rd<int>("det_dims.bin");
+            cv::Mat img(dims[0], dims[1], CV_8UC3, rgb.data());
+            for (int gridn = 1; gridn <= 2; ++gridn) {
+                std::vector<cv::KeyPoint> kps = matcher.detectFeatures(img, gridn, gridn, 500);
+                std::vector<float> rows;
+                std::vector<int> octs;
+                for (const cv::KeyPoint& k : kps) {
+                    rows.push_back(k.pt.x); rows.push_back(k.pt.y); rows.push_back(k.size); rows.push_back(k.angle);
+                    rows.push_back(k.response); octs.push_back(k.octave);
+                }
+                wr("det" + std::to_string(gridn) + "_kp.bin", rows);
+                wr("det" + std::to_string(gridn) + "_octave.bin", octs);
+            }
+        }
+    }
+
     // ---- demoKabsch path (demoKabsch.cpp:1020): createKabschEstimator()->computeTransformation(A, B) ----
     auto A = rd<double>("kabsch_A.bin"), B = rd<double>("kabsch_B.bin");   // row-major n x 3
     const long n = (long)(A.size() / 3);

@@ -283,13 +283,22 @@ def frontend_numbers(ctx, steps, warmup):
     return out
 
 
+def orb_bench_image(rng):
+    """640x480 gray frame with structure at several scales and sensor-like noise (a few thousand FAST corners)"""
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float64)
+    img = 110 + 50 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + 40 * np.sin((xx + 3 * yy) / 29.0)
+    for _ in range(150):
+        cx, cy, r, a = rng.uniform(0, 640), rng.uniform(0, 480), rng.uniform(1.5, 12), rng.uniform(-80, 80)
+        img += a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * r * r))
+    img += rng.normal(0, 6, (480, 640))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
 def orb_describe_numbers(ctx, steps, warmup):
     """describeFeatures (cv::ORB::compute with provided keypoints): 640x480 gray frame, 1000 keypoints over 8 octaves,
     host image + keypoints in, descriptors out; cv2's own compute on the host beside it (the reference's call)."""
     rng = np.random.default_rng(77)
-    yy, xx = np.mgrid[0:480, 0:640].astype(np.float64)
-    img = 110 + 50 * np.sin(xx / 11.0) * np.cos(yy / 7.0) + 40 * np.sin((xx + 3 * yy) / 29.0) + rng.normal(0, 10, (480, 640))
-    img = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    img = orb_bench_image(rng)
     n = 1000
     xy = np.stack([rng.uniform(35, 604, n), rng.uniform(35, 444, n)], 1).astype(np.float32)
     octave = rng.integers(0, 8, n).astype(np.int32); angle = rng.uniform(0, 360, n).astype(np.float32)
@@ -319,6 +328,34 @@ def orb_describe_numbers(ctx, steps, warmup):
         res["bit_exact_vs_cv2"] = bool(len(k2) == order.size and np.array_equal(d2, desc))
     except Exception as e:  # noqa: BLE001
         res["cv2"] = f"unavailable: {e}"
+    # detection on the same frame: cv::ORB::create()->detect (500 features), keypoints back on the host
+    for _ in range(warmup):
+        det = ctx.orb_detect(img, 500)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        det = ctx.orb_detect(img, 500)
+    dres = {"e2e_ms_per_frame": (time.perf_counter() - t0) / steps * 1e3, "keypoints": int(det["octave"].size), "nfeatures": 500}
+    try:
+        import cv2
+        orb = cv2.ORB_create()
+        ref = orb.detect(img)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orb.detect(img)
+        dres["cv2_detect_ms_all_threads"] = (time.perf_counter() - t0) / 5 * 1e3
+        cv2.setNumThreads(1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            orb.detect(img)
+        dres["cv2_detect_ms_1_thread"] = (time.perf_counter() - t0) / 5 * 1e3
+        cv2.setNumThreads(0)
+        rk = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in ref], np.float32)
+        mk = np.column_stack([det["xy"], det["size"], det["angle"], det["response"]]).astype(np.float32)
+        dres["bit_exact_vs_cv2_order_included"] = bool(rk.shape == mk.shape and np.array_equal(rk.view(np.uint32), mk.view(np.uint32))
+                                                        and np.array_equal(det["octave"], [k.octave for k in ref]))
+    except Exception as e:  # noqa: BLE001
+        dres["cv2"] = f"unavailable: {e}"
+    res["detect"] = dres
     return res
 
 
@@ -333,7 +370,7 @@ def native_frontend_numbers(frames, warmup):
     mf = synth.map_frame(M=5000, N=1000, seed=0)
     fp = synth.frame_pair(n=1000, seed=1)
     rng = np.random.default_rng(77)
-    orb_img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    orb_img = orb_bench_image(rng)
     orb_xy = np.stack([rng.uniform(35, 604, 1000), rng.uniform(35, 444, 1000)], 1)
     with tempfile.TemporaryDirectory() as d:
         for name, arr, dt in [("orb_img", orb_img, np.uint8), ("orb_xy", orb_xy, np.float32),

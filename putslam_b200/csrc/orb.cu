@@ -164,6 +164,11 @@ __global__ void orb_fast_score_kernel(OrbLevels L, const uint8_t* __restrict__ p
         const uint8_t* c = plain + L.plain_off[l] + (size_t)y * w + x;
         const int v = c[0];
         int d[16];
+        // any 9 contiguous ring pixels contain at least two of the four compass points: most pixels stop here
+        d[0] = v - c[3 * w]; d[4] = v - c[3]; d[8] = v - c[-3 * w]; d[12] = v - c[-3];
+        const int nb = (d[0] > threshold) + (d[4] > threshold) + (d[8] > threshold) + (d[12] > threshold);
+        const int nd = (d[0] < -threshold) + (d[4] < -threshold) + (d[8] < -threshold) + (d[12] < -threshold);
+        if (nb < 2 && nd < 2) { score[g] = 0; return; }
         d[0] = v - c[3 * w];          d[1] = v - c[3 * w + 1];      d[2] = v - c[2 * w + 2];      d[3] = v - c[w + 3];
         d[4] = v - c[3];              d[5] = v - c[-w + 3];         d[6] = v - c[-2 * w + 2];     d[7] = v - c[-3 * w + 1];
         d[8] = v - c[-3 * w];         d[9] = v - c[-3 * w - 1];     d[10] = v - c[-2 * w - 2];    d[11] = v - c[-w - 3];
@@ -189,40 +194,59 @@ __global__ void orb_fast_score_kernel(OrbLevels L, const uint8_t* __restrict__ p
 
 __device__ __forceinline__ bool orb_is_candidate(const OrbLevels& L, const uint8_t* __restrict__ score, int g, int& lvl,
                                                  int& x, int& y, int& sc) {
+    const uint8_t* s = score + g;
+    sc = s[0];
+    if (sc == 0) return false;                 // not a corner: the common case, decided by one coalesced byte
     int l = 0;
     while (g >= L.pix_start[l + 1]) ++l;
     const int p = g - L.pix_start[l], w = L.w[l], h = L.h[l];
     y = p / w; x = p - y * w; lvl = l;
     if (x < 31 || x >= w - 31 || y < 31 || y >= h - 31) return false;   // runByImageBorder(edgeThreshold) on the level
-    const uint8_t* s = score + g;
-    sc = s[0];
-    if (sc == 0) return false;
     return sc > s[-1] && sc > s[1] && sc > s[-w - 1] && sc > s[-w] && sc > s[-w + 1] && sc > s[w - 1] && sc > s[w] &&
            sc > s[w + 1];
 }
 
-// cand: 6 ints per candidate {level, x, y, FAST score, Harris bits, angle bits}; header[0] = count (may exceed cap)
-__global__ void __launch_bounds__(256)
+// cand: 6 ints per candidate {level, x, y, FAST score, Harris bits, angle bits}; header[0] = count (may exceed cap).
+// Grid-wide ordered (raster) compaction, same scheme as map_prepare_kernel: contiguous pixel ranges per CTA (grid <= SM
+// count), pass 1 counts, stamped per-CTA counts + look-back give the offset, pass 2 writes.  Every thread takes four
+// consecutive score bytes with one 32-bit load (zero = no corner, the common case); per-thread counts are scanned with
+// shuffles.  (First version: one byte per thread per trip, 30 dependent trips per pass -> 47 us.)
+constexpr int kCandThreads = 1024;
+__device__ __forceinline__ int orb_quad_candidates(const OrbLevels& L, const uint8_t* __restrict__ score, int g, int hi,
+                                                   int (&rec)[2][4]) {
+    const uint32_t word = *reinterpret_cast<const uint32_t*>(score + g);   // g is a multiple of 4, the buffer is padded
+    if (word == 0u) return 0;
+    int n = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int l, x, y, sc;
+        if (((word >> (8 * q)) & 0xffu) != 0u && g + q < hi && orb_is_candidate(L, score, g + q, l, x, y, sc)) {
+            if (n < 2) { rec[n][0] = l; rec[n][1] = x; rec[n][2] = y; rec[n][3] = sc; }   // two strict 3x3 maxima cannot be adjacent
+            ++n;
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kCandThreads)
 orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_cta, int* __restrict__ cand, int cap,
                       int* __restrict__ header, unsigned long long* __restrict__ cta_counts, unsigned int epoch) {
-    __shared__ int warp_tot[8];
+    constexpr int kW = kCandThreads / 32;
+    __shared__ int warp_tot[kW];
     __shared__ int s_base;
     chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = L.pix_start[L.n];
-    const int lo = min(total, (int)blockIdx.x * per_cta), hi = min(total, lo + per_cta);
+    const int lo = min(total, (int)blockIdx.x * per_cta), hi = min(total, lo + per_cta);   // per_cta is a multiple of 4096
+    int rec[2][4];
     int mine = 0;
-    for (int g = lo + tid; g < hi; g += 256) {
-        int l, x, y, sc;
-        mine += orb_is_candidate(L, score, g, l, x, y, sc) ? 1 : 0;
-    }
+    for (int g = lo + 4 * tid; g < hi; g += 4 * kCandThreads) mine += orb_quad_candidates(L, score, g, hi, rec);
     mine = (int)warp_add_u32((uint32_t)mine);
     if (lane == 0) warp_tot[warp] = mine;
     __syncthreads();
     if (warp == 0) {
-        int tot = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+        int tot = warp_tot[lane];   // kW == 32
+        tot = (int)warp_add_u32((uint32_t)tot);
         volatile unsigned long long* sums = cta_counts;
         if (lane == 0) sums[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)tot;
         int before = 0;
@@ -239,26 +263,30 @@ orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_ct
     }
     __syncthreads();
     int carry = s_base;
-    for (int base = lo; base < hi; base += 256) {
-        const int g = base + tid;
-        int l = 0, x = 0, y = 0, sc = 0;
-        const bool is = g < hi && orb_is_candidate(L, score, g, l, x, y, sc);
-        const uint32_t bal = __ballot_sync(0xffffffffu, is);
+    for (int base = lo; base < hi; base += 4 * kCandThreads) {
+        const int g = base + 4 * tid;
+        const int n = g < hi ? orb_quad_candidates(L, score, g, hi, rec) : 0;
+        int incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
         __syncthreads();
-        if (lane == 0) warp_tot[warp] = __popc(bal);
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         int woff = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < kW; ++w) {
             const int c = warp_tot[w];
             if (w < warp) woff += c;
             tot += c;
         }
-        if (is) {
-            const int pos = carry + woff + __popc(bal & ((1u << lane) - 1u));
+        int pos = carry + woff + incl - n;
+        for (int q = 0; q < n && q < 2; ++q, ++pos) {
             if (pos < cap) {
                 int* r = cand + 6 * (size_t)pos;
-                r[0] = l; r[1] = x; r[2] = y; r[3] = sc;
+                r[0] = rec[q][0]; r[1] = rec[q][1]; r[2] = rec[q][2]; r[3] = rec[q][3];
             }
         }
         carry += tot;
@@ -452,10 +480,10 @@ cudaError_t launch_orb_detect(const uint8_t* d_bgr, int rgb_order, int W, int H,
                             (const uint8_t*)d_plain, d_score, fast_threshold)) != cudaSuccess) return e;
     int grid = sm_count > 0 ? sm_count : 1;
     int per_cta = (total + grid - 1) / grid;
-    per_cta = (per_cta + 255) / 256 * 256;
+    per_cta = (per_cta + 4 * kCandThreads - 1) / (4 * kCandThreads) * (4 * kCandThreads);
     grid = (total + per_cta - 1) / per_cta;
     if (grid < 1) grid = 1;
-    if ((e = launch_chained(orb_candidates_kernel, dim3((unsigned)grid), dim3(256), 0, st, L, (const uint8_t*)d_score, per_cta,
+    if ((e = launch_chained(orb_candidates_kernel, dim3((unsigned)grid), dim3(kCandThreads), 0, st, L, (const uint8_t*)d_score, per_cta,
                             d_cand, cap, d_header, d_cta_counts, epoch)) != cudaSuccess) return e;
     int hgrid = (cap + 7) / 8;
     if (hgrid > 8 * (sm_count > 0 ? sm_count : 1)) hgrid = 8 * (sm_count > 0 ? sm_count : 1);

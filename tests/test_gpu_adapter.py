@@ -32,6 +32,12 @@ def test_adapter_end_to_end(tmp_path, O):
     for name, arr, dt in [("orb_bgr", g["bgr_img"], np.uint8), ("orb_xy", g["bgr_xy"], np.float32),
                           ("orb_octave", g["bgr_octave"], np.int32), ("orb_angle", g["bgr_angle"], np.float32)]:
         np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
+    import cv2
+    det_rng = np.random.default_rng(61)
+    det_gray = cv2.GaussianBlur(det_rng.integers(0, 256, (480, 640), dtype=np.uint8), (0, 0), 1.5)
+    det_rgb = np.stack([det_gray, np.roll(det_gray, 3, 1), 255 - np.roll(det_gray, 2, 0)], 2).copy()
+    np.array(det_rgb.shape[:2], np.int32).tofile(os.path.join(d, "det_dims.bin"))
+    det_rgb.tofile(os.path.join(d, "det_rgb.bin"))
     for name, arr, dt in [("desc1", fp["desc1"], np.uint8), ("desc2", fp["desc2"], np.uint8), ("uv1", fp["uv1"], np.float32),
                           ("uv2", fp["uv2"], np.float32), ("depth1", fp["depth1"], np.uint16), ("depth2", fp["depth2"], np.uint16),
                           ("map_xyz", mf["map_xyz"], np.float64), ("map_desc", mf["map_desc"], np.uint8),
@@ -97,6 +103,25 @@ def test_adapter_end_to_end(tmp_path, O):
     # ---- describeFeatures: the cv2 golden vectors (colour image), features reordered like cv::ORB::compute does ----
     assert np.array_equal(_rd(d, "orb_order.bin", np.int32), g["bgr_order"])
     assert np.array_equal(_rd(d, "orb_desc.bin", np.uint8).reshape(-1, 32), g["bgr_desc"])
+
+    # ---- detectFeatures: the reference's wrapper restated with cv2 (responses are distinct, so the sorts are unambiguous) ----
+    gray = cv2.cvtColor(det_rgb, cv2.COLOR_RGB2GRAY)
+    for gridn in (1, 2):
+        per_roi = 500 * 3 // (gridn * gridn)
+        raw = []
+        for k in range(gridn):
+            for i in range(gridn):
+                x0, y0, w, h = k * 640 // gridn, i * 480 // gridn, 640 // gridn, 480 // gridn
+                kps = cv2.ORB_create().detect(np.ascontiguousarray(gray[y0:y0 + h, x0:x0 + w]))
+                kps = sorted(kps, key=lambda q: -q.response)[:per_roi]
+                raw += [(np.float32(q.pt[0]) + np.float32(x0), np.float32(q.pt[1]) + np.float32(y0), q.size, q.angle, q.response,
+                         q.octave) for q in kps]
+        raw = sorted(raw, key=lambda q: -q[4])[:500]
+        assert len({q[4] for q in raw}) == len(raw)
+        exp = np.array([q[:5] for q in raw], np.float32)
+        got = _rd(d, f"det{gridn}_kp.bin", np.float32).reshape(-1, 5)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), gridn
+        assert np.array_equal(_rd(d, f"det{gridn}_octave.bin", np.int32), [q[5] for q in raw])
 
     # ---- Kabsch ----
     Tk = _rd(d, "kabsch_T.bin", np.float64).reshape(4, 4).T
