@@ -275,6 +275,51 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
     return res.inlier_ratio;   // == RANSAC::pointInlierRatio(inlierMatches, matches), matcher.cpp:797 (computed with a bitmap)
 }
 
+// ---- DBScan ------------------------------------------------------------------------------------------------------------
+void DBScan::run(std::vector<cv::KeyPoint>& pts) {
+    const int n = (int)pts.size();
+    // (float)cv::norm(a.pt - b.pt) < eps : float differences, double sqrt of the double sum of squares, rounded to float,
+    // compared in double (dbscan.cpp:90-92 and the `dist[..] < eps` tests)
+    const auto close = [&](int a, int b) {
+        const float dx = pts[(size_t)a].pt.x - pts[(size_t)b].pt.x, dy = pts[(size_t)a].pt.y - pts[(size_t)b].pt.y;
+        return (double)(float)std::sqrt((double)dx * dx + (double)dy * dy) < eps_;
+    };
+    label_.assign((size_t)n, 0);                 // 0: not labelled yet
+    std::vector<char> seen((size_t)n, 0);
+    std::vector<int> frontier, fresh;
+    int next = 1;
+    for (int seed = 0; seed < n; ++seed) {
+        if (seen[(size_t)seed]) continue;
+        seen[(size_t)seed] = 1;
+        frontier.clear();
+        for (int k = 0; k < n; ++k) if (close(seed, k)) frontier.push_back(k);      // the seed itself and visited points count
+        if ((int)frontier.size() < minPts_) { label_[(size_t)seed] = -1; continue; }
+        label_[(size_t)seed] = next;
+        // the frontier grows while it is walked; a point that was noise keeps its -1 (dbscan.cpp:45-46)
+        for (size_t j = 0; j < frontier.size(); ++j) {
+            const int x = frontier[j];
+            if (!seen[(size_t)x]) {
+                seen[(size_t)x] = 1;
+                fresh.clear();
+                for (int k = 0; k < n; ++k) if (!seen[(size_t)k] && close(x, k)) fresh.push_back(k);
+                if ((int)fresh.size() >= minPts_) frontier.insert(frontier.end(), fresh.begin(), fresh.end());
+            }
+            if (label_[(size_t)x] == 0) label_[(size_t)x] = next;
+        }
+        ++next;
+    }
+    // the first perCluster_ members of every cluster stay, in list order; noise stays
+    std::vector<int> taken((size_t)next, 0);
+    size_t out = 0;
+    for (int i = 0; i < n; ++i) {
+        const int c = label_[(size_t)i];
+        if (c > 0 && taken[(size_t)c]++ >= perCluster_) continue;
+        if (out != (size_t)i) pts[out] = pts[(size_t)i];
+        ++out;
+    }
+    pts.resize(out);
+}
+
 std::vector<cv::KeyPoint> MatcherB200::detectFeatures(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures) {
     std::vector<cv::KeyPoint> raw_keypoints;
     pslam_ctx* c = dev_.ctx();

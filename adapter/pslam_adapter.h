@@ -165,6 +165,24 @@ private:
     bool hostLevels_ = false;
 };
 
+// DBScan (include/putslam/Matcher/dbscan.h:14-41, src/Matcher/dbscan.cpp): the de-clustering pass the reference runs on
+// every detected keypoint list (Matcher::detectInitFeatures / match / matchXYZ, src/Matcher/matcher.cpp:24-26,459-461,
+// 561-563) -- of every group of keypoints chained together by distances below eps, only the first featuresFromCluster (in
+// list order) survive.  Same constructor and run() as the reference class.  It is a sequential graph walk over a few
+// hundred keypoints (the cluster a border keypoint joins depends on the visiting order), so it stays on the host; the
+// pairwise distances are evaluated on demand instead of through the reference's N x N matrix.
+class DBScan {
+public:
+    DBScan(double eps = 10, int minPts = 2, int featuresFromCluster = 1) : eps_(eps), minPts_(minPts), perCluster_(featuresFromCluster) {}
+    void run(std::vector<cv::KeyPoint>& clusteringSet);
+    // cluster label per input keypoint of the last run(): -1 noise, > 0 cluster id (in order of creation)
+    const std::vector<int>& labels() const { return label_; }
+private:
+    double eps_;
+    int minPts_, perCluster_;
+    std::vector<int> label_;
+};
+
 // putslam::TransformEst / KabschEst (transformEst.h:16-26, kabschEst.h:21-41).  Mat34 is
 // Eigen::Transform<double,3,Affine>; its 4x4 column-major matrix is exposed here as double[16].
 struct Mat34 {

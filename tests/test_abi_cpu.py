@@ -70,3 +70,46 @@ def test_host_merge_and_shards():
     ids, sc = host.merge_topk([(5, 3), (9, 7), (5, 1), (-1, -1), (9, 2)], 4)
     assert ids.tolist() == [2, 7, 1, 3] and sc.tolist() == [9, 9, 5, 5]
     assert host.retry_gates(0.12, 0.55, 3) == (0.12 + 0.04, 0.55 - 0.1)
+
+
+def test_dbscan_against_the_reference_build(tmp_path):
+    """putslam_b200::DBScan (adapter, host C++) against the REFERENCE's own DBScan, compiled from the reference tree into
+    oracle/_ref (src/Matcher/dbscan.cpp with a three-symbol OpenCV stand-in, oracle/Makefile target `ref`): same
+    survivors in the same order for random and clustered keypoint lists, several eps / minPts / per-cluster settings."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    from oracle import oracle
+    oracle.build()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_dbscan.so")
+    cli = os.path.join(ROOT, "adapter", "dbscan_cli")
+    assert os.path.exists(ref_so), "oracle/_ref/libref_dbscan.so missing (make -C oracle ref needs /root/reference)"
+    assert os.path.exists(cli), "adapter/dbscan_cli not built (run __graft_entry__.build())"
+    ref = C.CDLL(ref_so)
+    rng = np.random.default_rng(99)
+    n_removed = 0
+    for trial in range(40):
+        n = int(rng.integers(0, 600))
+        kind = trial % 4
+        if kind == 0:                                   # uniform
+            xy = rng.uniform(0, 640, (n, 2))
+        elif kind == 1:                                 # tight clusters + background (multi-octave duplicates)
+            centres = rng.uniform(20, 620, (max(1, n // 6), 2))
+            xy = centres[rng.integers(0, len(centres), n)] + rng.normal(0, 0.6, (n, 2))
+        elif kind == 2:                                 # chains: points along lines with spacing around eps
+            t = np.sort(rng.uniform(0, 300, n)); xy = np.stack([t, 0.3 * t + rng.normal(0, 0.4, n)], 1)
+        else:                                           # exact duplicates and integer grid (distances exactly eps)
+            xy = rng.integers(0, 25, (n, 2)).astype(np.float64)
+        xy = np.ascontiguousarray(xy, np.float32)
+        rng.shuffle(xy)
+        for eps, min_pts, per in ((1.0, 2, 1), (3.0, 2, 1), (2.0, 3, 2), (10.0, 2, 1), (1.0, 1, 1)):
+            kept = np.empty(max(1, n), np.int32)
+            m = ref.orc_ref_dbscan(xy.ctypes.data_as(C.POINTER(C.c_float)), n, C.c_double(eps), min_pts, per,
+                                   kept.ctypes.data_as(C.POINTER(C.c_int)))
+            fin, fout = str(tmp_path / "xy.bin"), str(tmp_path / "kept.bin")
+            xy.tofile(fin)
+            subprocess.check_call([cli, fin, repr(eps), str(min_pts), str(per), fout])
+            got = np.fromfile(fout, np.int32)
+            assert np.array_equal(got, kept[:m]), (trial, eps, min_pts, per)
+            n_removed += n - m
+    assert n_removed > 1000          # the de-clustering really removed keypoints
