@@ -389,7 +389,9 @@ def native_frontend_numbers(frames, warmup):
         except Exception as e:  # noqa: BLE001
             return {"unavailable": str(e)}
     r["note"] = ("C++ adapter, host buffers in, results out, per frame: frame_to_map = MatcherB200::matchXYZCore (guided "
-                 "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); frame_to_resident_map = "
+                 "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); orb_* = MatcherB200::detectFeatures / describeFeatures on a 640x480 frame (gray, "
+                 "and orb_detect_describe_rgb_frame_ms on a 3-channel frame, 921 KB uploaded by each of the two calls); "
+                 "frame_to_resident_map = "
                  "MatcherB200::matchXYZResident, the same frame against the 5000-feature map kept in HBM (pose + current "
                  "keypoints in, view-angle/depth filter + matching + RANSAC on the device; resident_equals_host_map checks "
                  "the two answers are identical); vo_three_calls = performMatching "
