@@ -335,6 +335,10 @@ std::vector<cv::KeyPoint> MatcherB200::detectFeatures(cv::Mat rgbImage, int grid
     const int rowBytes = (int)rgbImage.step0;
 #endif
     const int maximalFeaturesInROI = maximalTrackedFeatures * 3 / (gridCols * gridRows);
+    lastFrameData_ = nullptr;
+    if (gridCols == 1 && gridRows == 1) {   // the whole frame goes to the device in one piece: describeFeatures may reuse it
+        lastFrameData_ = rgbImage.data; lastFrameRows_ = H; lastFrameCols_ = W; lastFrameStep_ = rowBytes; lastFrameCh_ = ch;
+    }
     const int cap = 4096;                     // cv::ORB::create() keeps 500 per call; tied responses can add a few
     std::vector<float> xy(2 * (size_t)cap), size((size_t)cap), angle((size_t)cap), response((size_t)cap);
     std::vector<int> octave((size_t)cap);
@@ -387,7 +391,10 @@ cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint
 #else
     const int rowBytes = (int)rgbImage.step0;
 #endif
-    const int r = pslam_orb_describe(c, rgbImage.data, rgbImage.cols, rgbImage.rows, rowBytes, rgbImage.channels(), xy.data(),
+    const bool resident = reuseFrame_ && lastFrameData_ == rgbImage.data && lastFrameRows_ == rgbImage.rows &&
+                          lastFrameCols_ == rgbImage.cols && lastFrameStep_ == rowBytes && lastFrameCh_ == rgbImage.channels();
+    const int r = pslam_orb_describe(c, resident ? nullptr : rgbImage.data, rgbImage.cols, rgbImage.rows, rowBytes,
+                                     rgbImage.channels(), xy.data(),
                                      oct.data(), ang.data(), n, order.data(), &nOut, descriptors.data);
     if (r != PSLAM_OK) {
         logError(c, "describeFeatures", r);

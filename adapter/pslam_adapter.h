@@ -96,6 +96,10 @@ public:
     // cv::ORB::compute does it (keypoints within 31 px of the border dropped, the rest regrouped by octave); returns
     // one 32-byte row per remaining feature.
     cv::Mat describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint>& features);
+    // Opt-in: when describeFeatures is called with the very Mat (same data pointer, size, step) the last full-frame
+    // detectFeatures saw, skip the second upload and describe on the frame already in HBM.  The caller promises not to
+    // modify the pixels between the two calls (Matcher::match does not, src/Matcher/matcher.cpp:457-467).
+    void setReuseDetectedFrame(bool on) { reuseFrame_ = on; }
     // knnMatch(k=2) + Lowe ratio (north_star extension): matches with d1 < ratio * d2
     std::vector<cv::DMatch> performMatchingRatio(cv::Mat prevDescriptors, cv::Mat descriptors, float ratio);
 
@@ -163,6 +167,9 @@ private:
     uint64_t seed_ = 0x5eed5eedULL;
     int numHyp_ = 0;
     bool hostLevels_ = false;
+    bool reuseFrame_ = false;
+    const unsigned char* lastFrameData_ = nullptr;   // frame of the last 1 x 1 detectFeatures
+    int lastFrameRows_ = 0, lastFrameCols_ = 0, lastFrameStep_ = 0, lastFrameCh_ = 0;
 };
 
 // DBScan (include/putslam/Matcher/dbscan.h:14-41, src/Matcher/dbscan.cpp): the de-clustering pass the reference runs on

@@ -390,7 +390,8 @@ def native_frontend_numbers(frames, warmup):
             return {"unavailable": str(e)}
     r["note"] = ("C++ adapter, host buffers in, results out, per frame: frame_to_map = MatcherB200::matchXYZCore (guided "
                  "matching + 4096-hypothesis RANSAC, pyramid levels predicted on the device); orb_* = MatcherB200::detectFeatures / describeFeatures on a 640x480 frame (gray, "
-                 "and orb_detect_describe_rgb_frame_ms on a 3-channel frame, 921 KB uploaded by each of the two calls); "
+                 "and orb_detect_describe_rgb_frame_ms on a 3-channel frame, 921 KB uploaded by each of the two calls; "
+                 "*_one_upload_ms with setReuseDetectedFrame); "
                  "frame_to_resident_map = "
                  "MatcherB200::matchXYZResident, the same frame against the 5000-feature map kept in HBM (pose + current "
                  "keypoints in, view-angle/depth filter + matching + RANSAC on the device; resident_equals_host_map checks "

@@ -128,7 +128,10 @@ PSLAM_API int pslam_gradient_uncertainty(pslam_ctx* ctx, const int* px, int n, c
  * permutes its keypoint vector with it, as ORB does to `features` -- and desc_out (capacity n x 32) one 32-byte
  * descriptor per surviving keypoint in that order.  cos / sin of the keypoint angles are evaluated on the host
  * (double libm, rounded to float, as OpenCV does) and the sampling itself on the device.  Octaves 0 .. 11; every
- * pyramid level must stay larger than 32 x 32 pixels. */
+ * pyramid level must stay larger than 32 x 32 pixels.
+ * image == NULL: describe on the frame this context uploaded last (the preceding pslam_orb_detect or pslam_orb_describe
+ * with the same W, H and channels) -- detectFeatures followed by describeFeatures on one frame then uploads it once.
+ * The gray conversion is still this call's own (BGR order), exactly as when the image is passed again. */
 PSLAM_API int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels,
                                  const float* kp_xy, const int* kp_octave, const float* kp_angle_deg, int n,
                                  int* order_out, int* n_out, uint8_t* desc_out);

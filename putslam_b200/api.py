@@ -203,16 +203,23 @@ class Context:
         return info, covo
 
     # ---- descriptor production ----
-    def orb_describe(self, image, xy, octave, angle_deg):
+    def orb_describe(self, image, xy, octave, angle_deg, resident_shape=None):
         """cv::ORB::compute with provided keypoints -> (order int32[n_out] into the input keypoints, desc uint8[n_out, 32]).
-        image: H x W uint8 (gray) or H x W x 3 uint8 (BGR)."""
-        img = np.ascontiguousarray(image, np.uint8)
-        ch = 3 if img.ndim == 3 else 1
-        H, W = img.shape[:2]
+        image: H x W uint8 (gray) or H x W x 3 uint8 (BGR); None + resident_shape=(H, W[, 3]) = the frame uploaded by the
+        previous orb_detect / orb_describe call on this context."""
+        if image is None:
+            img = None
+            ch = 3 if len(resident_shape) == 3 else 1
+            H, W = resident_shape[:2]
+        else:
+            img = np.ascontiguousarray(image, np.uint8)
+            ch = 3 if img.ndim == 3 else 1
+            H, W = img.shape[:2]
         xy = _arr(xy, np.float32, 2); oc = _arr(octave, np.int32); an = _arr(angle_deg, np.float32)
         n = oc.size
         order = np.empty(max(1, n), np.int32); desc = np.empty((max(1, n), 32), np.uint8); n_out = C.c_int(0)
-        self._ck(self.lib.pslam_orb_describe(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, _p(xy, C.c_float), _p(oc, C.c_int),
+        self._ck(self.lib.pslam_orb_describe(self.h, _p(img, C.c_uint8) if img is not None else None, W, H, ch * W, ch,
+                                             _p(xy, C.c_float), _p(oc, C.c_int),
                                              _p(an, C.c_float), n, _p(order, C.c_int), C.byref(n_out), _p(desc, C.c_uint8)))
         k = n_out.value
         return order[:k].copy(), desc[:k].copy()

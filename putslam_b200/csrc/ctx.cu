@@ -158,6 +158,11 @@ struct pslam_ctx {
     DevBuf d_orb_tab;
     int orb_W = 0, orb_H = 0, orb_levels = 0;
     bool orb_constants = false;
+    // the frame of the last pslam_orb_detect / pslam_orb_describe, as uploaded (tight rows): pslam_orb_describe with a
+    // NULL image works on it, so that detect -> describe of one frame uploads it once
+    DevBuf d_orb_frame;
+    int orbf_W = 0, orbf_H = 0, orbf_ch = 0;
+    bool orbf_valid = false;
     // map_prepare_kernel's per-CTA counts (stamped with prep_epoch, so they are never reset)
     unsigned long long* d_prep_counts = nullptr;
     unsigned int prep_epoch = 0;
@@ -381,7 +386,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
     cudaFree(ctx->d_map_xyz); cudaFree(ctx->d_map_desc); cudaFree(ctx->d_map_oct); cudaFree(ctx->d_map_det);
-    cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts); cudaFree(ctx->d_orb_tab.p);
+    cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts); cudaFree(ctx->d_orb_tab.p); cudaFree(ctx->d_orb_frame.p);
     if (ctx->ev_sweep0) cudaEventDestroy(ctx->ev_sweep0);
     if (ctx->ev_sweep1) cudaEventDestroy(ctx->ev_sweep1);
     cudaStreamDestroy(ctx->stream);
@@ -1141,6 +1146,18 @@ int pslam_map_prepare(pslam_ctx* ctx, const double* map_xyz, const float* view_a
     return PSLAM_OK;
 }
 
+// the caller's frame, packed to tight rows through the pinned staging area `stage`, into the context's resident frame
+static int orb_upload_frame(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels, uint8_t* stage) {
+    const size_t row = (size_t)channels * W, bytes = row * H;
+    ctx->orbf_valid = false;
+    TRY(ensure_dev(ctx, ctx->d_orb_frame, bytes));
+    if ((size_t)row_bytes == row) memcpy(stage, image, bytes);
+    else for (int y = 0; y < H; ++y) memcpy(stage + (size_t)y * row, image + (size_t)y * row_bytes, row);
+    CK(cudaMemcpyAsync(ctx->d_orb_frame.p, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->orbf_W = W; ctx->orbf_H = H; ctx->orbf_ch = channels; ctx->orbf_valid = true;
+    return PSLAM_OK;
+}
+
 // ---- ORB descriptors ---------------------------------------------------------------------------------
 // resize coefficient tables + sampling pattern + constants: rebuilt only when the image size or the level count changes
 // (layout of d_orb_tab: 1024 bytes of pattern, then the tables)
@@ -1163,9 +1180,12 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
                        const int* kp_octave, const float* kp_angle_deg, int n, int* order_out, int* n_out,
                        uint8_t* desc_out) {
     if (!ctx) return PSLAM_ERR_ARG;
-    if (!n_out || n < 0 || !image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W)
+    if (!n_out || n < 0 || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || (image && row_bytes < channels * W))
         return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: bad argument");
     *n_out = 0;
+    if (!image && !(ctx->orbf_valid && ctx->orbf_W == W && ctx->orbf_H == H && ctx->orbf_ch == channels))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: no resident frame of %d x %d x %d (image == NULL needs a preceding "
+                    "pslam_orb_detect / pslam_orb_describe of that frame on this context)", W, H, channels);
     if (n == 0) return PSLAM_OK;
     if (!kp_xy || !kp_octave || !kp_angle_deg || !order_out || !desc_out)
         return fail(ctx, PSLAM_ERR_ARG, "pslam_orb_describe: null buffer");
@@ -1204,10 +1224,10 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
     CK(cudaSetDevice(ctx->device));
     Arena in, out, work;
     const size_t img_bytes = (size_t)channels * W * H;
-    const size_t o_rec = in.take(20 * (size_t)m), o_bgr = in.take(channels == 3 ? img_bytes : 16);
+    const size_t o_rec = in.take(20 * (size_t)m);
     const size_t o_desc = out.take(32 * (size_t)m);
     const size_t o_plain = work.take(P.plain_bytes), o_ext = work.take(P.ext_bytes), o_row = work.take(4 * P.row_floats);
-    TRY(ensure_host(ctx, ctx->h_in, in.off + (channels == 1 ? img_bytes + 256 : 0)));
+    TRY(ensure_host(ctx, ctx->h_in, in.off + (image ? img_bytes + 256 : 0)));
     TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
@@ -1232,19 +1252,12 @@ int pslam_orb_describe(pslam_ctx* ctx, const uint8_t* image, int W, int H, int r
         order_out[k] = i;
     }
     uint8_t* d_plain = ctx->d_work.p + o_plain;
-    if (channels == 3) {
-        if (row_bytes == 3 * W) memcpy(h + o_bgr, image, img_bytes);
-        else for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
-        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
-    } else {   // gray: level 0 goes straight into the pyramid buffer
-        uint8_t* hg = h + in.off;
-        if (row_bytes == W) memcpy(hg, image, img_bytes);
-        else for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
-        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(d_plain, hg, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    if (image) TRY(orb_upload_frame(ctx, image, W, H, row_bytes, channels, h + in.off));
+    if (channels == 1)   // gray: the frame is level 0
+        CK(cudaMemcpyAsync(d_plain, ctx->d_orb_frame.p, img_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     int l = 0;
-    CK(launch_orb_describe(channels == 3 ? ctx->d_in.p + o_bgr : nullptr, W, H, 3 * W, P, d_plain, ctx->d_work.p + o_ext,
+    CK(launch_orb_describe(channels == 3 ? ctx->d_orb_frame.p : nullptr, W, H, 3 * W, P, d_plain, ctx->d_work.p + o_ext,
                            (float*)(ctx->d_work.p + o_row), d_tab, d_pat, (const int*)(ctx->d_in.p + o_rec), m,
                            ctx->d_out.p + o_desc, ctx->stream, &l));
     ctx->launches += l;
@@ -1306,31 +1319,21 @@ int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row
     const int first = 12288;                  // records fetched with the header; the rest only if there are more
     Arena in, out, work;
     const size_t img_bytes = (size_t)channels * W * H;
-    const size_t o_bgr = in.take(channels == 3 ? img_bytes : 16);
     const size_t o_hdr = out.take(16), o_cand = out.take(24 * (size_t)ccap);
     const size_t o_plain = work.take(P.plain_bytes), o_score = work.take(P.row_floats);
-    TRY(ensure_host(ctx, ctx->h_in, in.off + (channels == 1 ? img_bytes + 256 : 0)));
-    TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_in, img_bytes + 256));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
     TRY(orb_prepare_tables(ctx, W, H, nlev, P));
     const int* d_tab = (const int*)(ctx->d_orb_tab.p + 1024);
-    uint8_t* h = ctx->h_in.p;
     uint8_t* d_plain = ctx->d_work.p + o_plain;
-    if (channels == 3) {
-        if (row_bytes == 3 * W) memcpy(h + o_bgr, image, img_bytes);
-        else for (int y = 0; y < H; ++y) memcpy(h + o_bgr + (size_t)y * 3 * W, image + (size_t)y * row_bytes, 3 * (size_t)W);
-        CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        uint8_t* hg = h + in.off;
-        if (row_bytes == W) memcpy(hg, image, img_bytes);
-        else for (int y = 0; y < H; ++y) memcpy(hg + (size_t)y * W, image + (size_t)y * row_bytes, (size_t)W);
-        CK(cudaMemcpyAsync(d_plain, hg, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    TRY(orb_upload_frame(ctx, image, W, H, row_bytes, channels, ctx->h_in.p));
+    if (channels == 1)
+        CK(cudaMemcpyAsync(d_plain, ctx->d_orb_frame.p, img_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     unsigned int epoch = 0;
     TRY(next_epoch(ctx, &epoch));
     int l = 0;
-    CK(launch_orb_detect(channels == 3 ? ctx->d_in.p + o_bgr : nullptr, colour_order, W, H, 3 * W, P, d_plain,
+    CK(launch_orb_detect(channels == 3 ? ctx->d_orb_frame.p : nullptr, colour_order, W, H, 3 * W, P, d_plain,
                          ctx->d_work.p + o_score, d_tab, 20, (int*)(ctx->d_out.p + o_cand), ccap, (int*)(ctx->d_out.p + o_hdr),
                          prep_slots(ctx), epoch, ctx->sm_count, ctx->stream, &l));
     ctx->launches += l;

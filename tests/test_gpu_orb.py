@@ -150,3 +150,32 @@ def test_orb_detect_colour_and_edges(ctx):
     assert small["octave"].size == len(ref) and (small["octave"] <= 2).all()
     with pytest.raises(api.PslamError):
         ctx.orb_detect(g, 500, cap=10)                                        # more keypoints than the caller's buffers hold
+
+
+def test_orb_describe_on_the_resident_frame(ctx):
+    """image == NULL: describe on the frame the preceding detect uploaded (gray and colour; the colour frame is detected
+    with RGB2GRAY and described with BGR2GRAY, like the reference's two calls), same answer as passing the image again"""
+    import cv2
+    from putslam_b200 import api
+    rng = np.random.default_rng(21)
+    g = cv2.GaussianBlur(rng.integers(0, 256, (480, 640), dtype=np.uint8), (0, 0), 1.5)
+    rgb = np.stack([g, np.roll(g, 3, 1), 255 - np.roll(g, 2, 0)], 2).copy()
+    for img, order_flag in ((g, 0), (rgb, 1)):
+        det = ctx.orb_detect(img, 500, colour_order=order_flag)
+        again = ctx.orb_describe(img, det["xy"], det["octave"], det["angle"])
+        det = ctx.orb_detect(img, 500, colour_order=order_flag)                 # fresh upload, then describe without image
+        res = ctx.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=img.shape)
+        assert np.array_equal(res[0], again[0]) and np.array_equal(res[1], again[1]) and res[0].size > 200
+        twice = ctx.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=img.shape)
+        assert np.array_equal(twice[1], again[1])
+        kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, int(o)) for (x, y), a, o in zip(det["xy"], det["angle"], det["octave"])]
+        _, d2 = cv2.ORB_create().compute(img, kps)
+        assert np.array_equal(res[1], d2)
+    with pytest.raises(api.PslamError):                                          # resident frame has another shape
+        ctx.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=(240, 320))
+    fresh = api.Context(0)
+    try:
+        with pytest.raises(api.PslamError):                                      # nothing uploaded yet on this context
+            fresh.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=rgb.shape)
+    finally:
+        fresh.close()
