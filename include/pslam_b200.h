@@ -150,6 +150,14 @@ PSLAM_API int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int 
                                int colour_order, int nfeatures, float* kp_xy, float* kp_size, float* kp_angle,
                                float* kp_response, int* kp_octave, int cap, int* n_out);
 
+/* pslam_fast_detect == cv::FastFeatureDetector::create(threshold, true)->detect(image) (TYPE_9_16), the detector option
+ * "FAST" of MatcherOpenCV (src/Matcher/matcherOpenCV.cpp:60-61 with OpenCV's default threshold 10): keypoints in raster
+ * order, kp_xy n x 2 (integer pixel positions as float), kp_response = corner score; size 7, angle -1, octave 0 are
+ * constants of the detector.  threshold 1 .. 254.  image / channels / colour_order as pslam_orb_detect.  PSLAM_ERR_CAPACITY when more than cap
+ * corners are found (n_out still receives the count). */
+PSLAM_API int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels,
+                                int colour_order, int threshold, float* kp_xy, float* kp_response, int cap, int* n_out);
+
 /* ---- stage 2: Hamming matching --------------------------------------------------------------
  * pslam_match_bf_mutual replaces MatcherOpenCV::performMatching for ORB/LDB
  * (include/putslam/Matcher/matcher.h:412-413, src/Matcher/matcherOpenCV.cpp:198-206 ==

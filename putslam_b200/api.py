@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -238,6 +238,16 @@ class Context:
                                            _p(octv, C.c_int), cap, C.byref(n)))
         k = n.value
         return dict(xy=xy[:k].copy(), size=size[:k].copy(), angle=ang[:k].copy(), response=resp[:k].copy(), octave=octv[:k].copy())
+
+    def fast_detect(self, image, threshold=10, colour_order=0, cap=200000):
+        """cv::FastFeatureDetector::create(threshold, True).detect(image) -> (xy float32[n, 2], response float32[n]), raster order"""
+        img = np.ascontiguousarray(image, np.uint8)
+        ch = 3 if img.ndim == 3 else 1
+        H, W = img.shape[:2]
+        xy = np.empty((max(1, cap), 2), np.float32); resp = np.empty(max(1, cap), np.float32); n = C.c_int(0)
+        self._ck(self.lib.pslam_fast_detect(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, int(colour_order), int(threshold),
+                                            _p(xy, C.c_float), _p(resp, C.c_float), cap, C.byref(n)))
+        return xy[:n.value].copy(), resp[:n.value].copy()
 
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):

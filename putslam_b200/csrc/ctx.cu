@@ -1376,6 +1376,56 @@ int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row
     return PSLAM_OK;
 }
 
+int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row_bytes, int channels, int colour_order,
+                      int threshold, float* kp_xy, float* kp_response, int cap, int* n_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!n_out || !image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W || cap < 0 ||
+        threshold < 1 || threshold > 254 || (colour_order != 0 && colour_order != 1) || (cap > 0 && (!kp_xy || !kp_response)))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_fast_detect: bad argument");
+    *n_out = 0;
+    CK(cudaSetDevice(ctx->device));
+    OrbPlan P;
+    orb_plan(W, H, 1, &P);
+    const int ccap = (int)(P.row_floats / 4 + 64);
+    const int first = 16384;
+    Arena out, work;
+    const size_t img_bytes = (size_t)channels * W * H;
+    const size_t o_hdr = out.take(16), o_cand = out.take(24 * (size_t)ccap);
+    const size_t o_plain = work.take(P.plain_bytes), o_score = work.take(P.row_floats);
+    TRY(ensure_host(ctx, ctx->h_in, img_bytes + 256));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_work, work.off));
+    uint8_t* d_plain = ctx->d_work.p + o_plain;
+    TRY(orb_upload_frame(ctx, image, W, H, row_bytes, channels, ctx->h_in.p));
+    if (channels == 1)
+        CK(cudaMemcpyAsync(d_plain, ctx->d_orb_frame.p, img_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    unsigned int epoch = 0;
+    TRY(next_epoch(ctx, &epoch));
+    int l = 0;
+    CK(launch_fast_detect(channels == 3 ? ctx->d_orb_frame.p : nullptr, colour_order, W, H, 3 * W, P, d_plain,
+                          ctx->d_work.p + o_score, threshold, (int*)(ctx->d_out.p + o_cand), ccap, (int*)(ctx->d_out.p + o_hdr),
+                          prep_slots(ctx), epoch, ctx->sm_count, ctx->stream, &l));
+    ctx->launches += l;
+    ctx->f2m.valid = false; ctx->f2f.valid = false;
+    const size_t head = o_cand + 24 * (size_t)(first < ccap ? first : ccap);
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, head, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int found = *(const int*)(ctx->h_out.p + o_hdr);
+    if (found > first) {
+        CK(cudaMemcpyAsync(ctx->h_out.p + head, ctx->d_out.p + head, 24 * (size_t)(found - first), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const int* rec = (const int*)(ctx->h_out.p + o_cand);
+    const int n = found < cap ? found : cap;
+    for (int k = 0; k < n; ++k) {
+        kp_xy[2 * k] = (float)rec[6 * k + 1]; kp_xy[2 * k + 1] = (float)rec[6 * k + 2];
+        kp_response[k] = (float)rec[6 * k + 3];
+    }
+    *n_out = found;
+    if (found > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "pslam_fast_detect: %d corners, capacity %d", found, cap);
+    return PSLAM_OK;
+}
+
 // ---- resident feature map -------------------------------------------------------------------------
 // The map side of Matcher::matchXYZ kept in HBM between frames: per frame only the camera pose and
 // the current keypoints cross PCIe; the view-angle / depth filters, the move to the camera frame, the level

@@ -152,6 +152,10 @@ cudaError_t launch_orb_detect(const uint8_t* d_bgr, int rgb_order, int W, int H,
                               uint8_t* d_plain, uint8_t* d_score, const int* d_tab, int fast_threshold, int* d_cand, int cap,
                               int* d_header, unsigned long long* d_cta_counts, unsigned int epoch, int sm_count,
                               cudaStream_t st, int* launches);
+cudaError_t launch_fast_detect(const uint8_t* d_bgr, int rgb_order, int W, int H, int row_bytes, const OrbPlan& P,
+                               uint8_t* d_plain, uint8_t* d_score, int threshold, int* d_cand, int cap, int* d_header,
+                               unsigned long long* d_cta_counts, unsigned int epoch, int sm_count, cudaStream_t st,
+                               int* launches);
 cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
                                 uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
                                 int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches);

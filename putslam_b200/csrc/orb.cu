@@ -66,6 +66,7 @@ struct OrbLevels {
     int ext_off[kOrbMaxLevels];      // framed level ((w + 64) x (h + 64), tight)
     int pix_start[kOrbMaxLevels + 1];   // prefix of w*h        (row-pass launch)
     int ext_start[kOrbMaxLevels + 1];   // prefix of (w+64)(h+64) (frame/blur launch)
+    int edge;                           // border band of the corner filter: 31 for ORB (edgeThreshold), 0 for plain cv::FAST
 };
 
 __global__ void orb_blur_rows_kernel(OrbLevels L, const uint8_t* __restrict__ plain, float* __restrict__ rowbuf) {
@@ -201,7 +202,7 @@ __device__ __forceinline__ bool orb_is_candidate(const OrbLevels& L, const uint8
     while (g >= L.pix_start[l + 1]) ++l;
     const int p = g - L.pix_start[l], w = L.w[l], h = L.h[l];
     y = p / w; x = p - y * w; lvl = l;
-    if (x < 31 || x >= w - 31 || y < 31 || y >= h - 31) return false;   // runByImageBorder(edgeThreshold) on the level
+    if (x < L.edge || x >= w - L.edge || y < L.edge || y >= h - L.edge) return false;   // runByImageBorder(edgeThreshold)
     return sc > s[-1] && sc > s[1] && sc > s[-w - 1] && sc > s[-w] && sc > s[-w + 1] && sc > s[w - 1] && sc > s[w] &&
            sc > s[w + 1];
 }
@@ -441,6 +442,7 @@ static void orb_levels_from_plan(const OrbPlan& P, OrbLevels& L) {
         L.pix_start[l] = P.pix_start[l]; L.ext_start[l] = P.ext_start[l];
     }
     L.pix_start[P.n] = P.pix_start[P.n]; L.ext_start[P.n] = P.ext_start[P.n];
+    L.edge = 31;
 }
 
 // d_bgr: H rows of row_bytes (3 bytes per pixel), or nullptr when level 0 (tight W x H gray) is already in d_plain
@@ -490,6 +492,36 @@ cudaError_t launch_orb_detect(const uint8_t* d_bgr, int rgb_order, int W, int H,
     if ((e = launch_chained(orb_harris_angle_kernel, dim3((unsigned)hgrid), dim3(256), 0, st, L, (const uint8_t*)d_plain, d_cand,
                             cap, (const int*)d_header)) != cudaSuccess) return e;
     if (launches) *launches += nl + 3;
+    return cudaGetLastError();
+}
+
+// cv::FAST(image, keypoints, threshold, nonmaxSuppression = true, TYPE_9_16) on one (gray) image: score map, strict 3x3
+// maxima in raster order.  Records as launch_orb_detect ({0, x, y, score, -, -}).
+cudaError_t launch_fast_detect(const uint8_t* d_bgr, int rgb_order, int W, int H, int row_bytes, const OrbPlan& P,
+                               uint8_t* d_plain, uint8_t* d_score, int threshold, int* d_cand, int cap, int* d_header,
+                               unsigned long long* d_cta_counts, unsigned int epoch, int sm_count, cudaStream_t st,
+                               int* launches) {
+    OrbLevels L;
+    orb_levels_from_plan(P, L);
+    L.edge = 0;
+    int nl = 0;
+    cudaError_t e;
+    if (d_bgr) {
+        if ((e = launch_chained(orb_gray_kernel, dim3((unsigned)((W + 255) / 256), (unsigned)H), dim3(256), 0, st, d_bgr, W, H,
+                                row_bytes, d_plain, rgb_order)) != cudaSuccess) return e;
+        ++nl;
+    }
+    const int total = (int)P.row_floats;
+    if ((e = launch_chained(orb_fast_score_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, L,
+                            (const uint8_t*)d_plain, d_score, threshold)) != cudaSuccess) return e;
+    int grid = sm_count > 0 ? sm_count : 1;
+    int per_cta = (total + grid - 1) / grid;
+    per_cta = (per_cta + 4 * kCandThreads - 1) / (4 * kCandThreads) * (4 * kCandThreads);
+    grid = (total + per_cta - 1) / per_cta;
+    if (grid < 1) grid = 1;
+    if ((e = launch_chained(orb_candidates_kernel, dim3((unsigned)grid), dim3(kCandThreads), 0, st, L, (const uint8_t*)d_score, per_cta,
+                            d_cand, cap, d_header, d_cta_counts, epoch)) != cudaSuccess) return e;
+    if (launches) *launches += nl + 2;
     return cudaGetLastError();
 }
 

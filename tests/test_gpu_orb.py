@@ -179,3 +179,26 @@ def test_orb_describe_on_the_resident_frame(ctx):
             fresh.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=rgb.shape)
     finally:
         fresh.close()
+
+
+@pytest.mark.parametrize("W,H,threshold,sigma", [(640, 480, 10, 1.5), (640, 480, 20, 1.0), (333, 217, 10, 2.0), (1280, 720, 40, 1.2), (64, 48, 5, 0.8)])
+def test_fast_detect_vs_live_cv2(ctx, W, H, threshold, sigma):
+    """detector option "FAST": cv::FastFeatureDetector (9_16, non-max suppression): positions, raster order, scores"""
+    import cv2
+    from oracle import orb_oracle as OO
+    rng = np.random.default_rng(W + H + threshold)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), sigma)
+    img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    xy, resp = ctx.fast_detect(img, threshold)
+    ref = cv2.FastFeatureDetector_create(threshold, True).detect(img)
+    assert len(ref) == resp.size and len(ref) > 10
+    assert np.array_equal(xy, np.array([k.pt for k in ref], np.float32))
+    assert np.array_equal(resp, np.array([k.response for k in ref], np.float32))
+    if W * H <= 640 * 480:
+        mine = OO.fast_nms(OO.fast_score_map(img, threshold))
+        assert [(int(x), int(y), int(r)) for (x, y), r in zip(xy, resp)] == mine
+    rgb = np.stack([img, np.roll(img, 1, 0), np.roll(img, 2, 1)], 2).copy()
+    xy3, r3 = ctx.fast_detect(rgb, threshold, colour_order=1)
+    ref3 = cv2.FastFeatureDetector_create(threshold, True).detect(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(xy3, np.array([k.pt for k in ref3], np.float32).reshape(-1, 2))
+    assert np.array_equal(r3, np.array([k.response for k in ref3], np.float32))
