@@ -321,6 +321,15 @@ void DBScan::run(std::vector<cv::KeyPoint>& pts) {
 }
 
 std::vector<cv::KeyPoint> MatcherB200::detectFeatures(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures) {
+    return detectGrid(rgbImage, gridCols, gridRows, maximalTrackedFeatures, false);
+}
+std::vector<cv::KeyPoint> MatcherB200::detectFeaturesFAST(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures) {
+    return detectGrid(rgbImage, gridCols, gridRows, maximalTrackedFeatures, true);
+}
+
+// MatcherOpenCV::detectFeatures (src/Matcher/matcherOpenCV.cpp:118-176) around the device detector
+std::vector<cv::KeyPoint> MatcherB200::detectGrid(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures,
+                                                  bool fast) {
     std::vector<cv::KeyPoint> raw_keypoints;
     pslam_ctx* c = dev_.ctx();
     if (!c || rgbImage.empty() || gridCols <= 0 || gridRows <= 0) {
@@ -336,25 +345,32 @@ std::vector<cv::KeyPoint> MatcherB200::detectFeatures(cv::Mat rgbImage, int grid
 #endif
     const int maximalFeaturesInROI = maximalTrackedFeatures * 3 / (gridCols * gridRows);
     lastFrameData_ = nullptr;
-    if (gridCols == 1 && gridRows == 1) {   // the whole frame goes to the device in one piece: describeFeatures may reuse it
+    if (!fast && gridCols == 1 && gridRows == 1) {   // the whole frame goes to the device in one piece: describeFeatures may reuse it
         lastFrameData_ = rgbImage.data; lastFrameRows_ = H; lastFrameCols_ = W; lastFrameStep_ = rowBytes; lastFrameCh_ = ch;
     }
-    const int cap = 4096;                     // cv::ORB::create() keeps 500 per call; tied responses can add a few
-    std::vector<float> xy(2 * (size_t)cap), size((size_t)cap), angle((size_t)cap), response((size_t)cap);
-    std::vector<int> octave((size_t)cap);
+    // cv::ORB::create() keeps 500 per call (tied responses can add a few); cv::FAST has no budget: strict 3x3 maxima,
+    // at most one per 2x2 pixels
+    const int w = W / gridCols, h = H / gridRows;
+    const int cap = fast ? w * h / 4 + 64 : 4096;
+    std::vector<float> xy(2 * (size_t)cap), size(fast ? 1 : (size_t)cap), angle(fast ? 1 : (size_t)cap), response((size_t)cap);
+    std::vector<int> octave(fast ? 1 : (size_t)cap);
     for (int k = 0; k < gridCols; k++) {
         for (int i = 0; i < gridRows; i++) {
-            const int x0 = k * W / gridCols, y0 = i * H / gridRows, w = W / gridCols, h = H / gridRows;
+            const int x0 = k * W / gridCols, y0 = i * H / gridRows;
+            const unsigned char* roi = rgbImage.data + (size_t)y0 * rowBytes + (size_t)x0 * ch;
             int n = 0;
-            const int r = pslam_orb_detect(c, rgbImage.data + (size_t)y0 * rowBytes + (size_t)x0 * ch, w, h, rowBytes, ch,
-                                           /*COLOR_RGB2GRAY, :122*/ 1, 500, xy.data(), size.data(), angle.data(), response.data(),
-                                           octave.data(), cap, &n);
+            const int r = fast ? pslam_fast_detect(c, roi, w, h, rowBytes, ch, /*COLOR_RGB2GRAY, :122*/ 1, 10, xy.data(), response.data(),
+                                                   cap, &n)
+                               : pslam_orb_detect(c, roi, w, h, rowBytes, ch, 1, 500, xy.data(), size.data(), angle.data(),
+                                                  response.data(), octave.data(), cap, &n);
             if (r != PSLAM_OK) { logError(c, "detectFeatures", r); continue; }
             std::vector<cv::KeyPoint> keypointsInROI((size_t)n);
             for (int j = 0; j < n; ++j) {
                 cv::KeyPoint& kp = keypointsInROI[(size_t)j];
                 kp.pt = cv::Point2f(xy[2 * j], xy[2 * j + 1]);
-                kp.size = size[j]; kp.angle = angle[j]; kp.response = response[j]; kp.octave = octave[j]; kp.class_id = -1;
+                kp.response = response[j]; kp.class_id = -1;
+                if (fast) { kp.size = 7.f; kp.angle = -1.f; kp.octave = 0; }
+                else { kp.size = size[j]; kp.angle = angle[j]; kp.octave = octave[j]; }
             }
             std::sort(keypointsInROI.begin(), keypointsInROI.end(), compare_response);
             for (size_t j = 0; j < keypointsInROI.size() && (int)j < maximalFeaturesInROI; j++) {

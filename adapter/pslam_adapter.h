@@ -90,6 +90,10 @@ public:
     // maximalTrackedFeatures.  The sorts are std::sort with the reference's comparator (matcherOpenCV.h:84-87).
     std::vector<cv::KeyPoint> detectFeatures(cv::Mat rgbImage, int gridCols = 1, int gridRows = 1,
                                              int maximalTrackedFeatures = 500);
+    // the same wrapper for detector == "FAST" (matcherOpenCV.cpp:60-61: cv::FastFeatureDetector::create(), threshold 10,
+    // non-maximum suppression, 9_16): pslam_fast_detect per grid cell
+    std::vector<cv::KeyPoint> detectFeaturesFAST(cv::Mat rgbImage, int gridCols = 1, int gridRows = 1,
+                                                 int maximalTrackedFeatures = 500);
     // MatcherOpenCV::describeFeatures for descriptor == "ORB" (src/Matcher/matcherOpenCV.cpp:181-195):
     // cv::ORB::create()->compute(rgbImage, features, descriptors).  rgbImage: CV_8UC3 (converted like ORB does, with
     // COLOR_BGR2GRAY on the stored channel order) or CV_8UC1.  `features` is filtered and reordered exactly as
@@ -167,6 +171,7 @@ private:
     uint64_t seed_ = 0x5eed5eedULL;
     int numHyp_ = 0;
     bool hostLevels_ = false;
+    std::vector<cv::KeyPoint> detectGrid(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures, bool fast);
     bool reuseFrame_ = false;
     const unsigned char* lastFrameData_ = nullptr;   // frame of the last 1 x 1 detectFeatures
     int lastFrameRows_ = 0, lastFrameCols_ = 0, lastFrameStep_ = 0, lastFrameCh_ = 0;

@@ -182,6 +182,15 @@ int main(int argc, char** argv) {
                 wr("det" + std::to_string(gridn) + "_kp.bin", rows);
                 wr("det" + std::to_string(gridn) + "_octave.bin", octs);
             }
+            {   // detector == "FAST"
+                std::vector<cv::KeyPoint> kps = matcher.detectFeaturesFAST(img, 1, 1, 500);
+                std::vector<float> rows;
+                for (const cv::KeyPoint& k : kps) {
+                    rows.push_back(k.pt.x); rows.push_back(k.pt.y); rows.push_back(k.size); rows.push_back(k.angle);
+                    rows.push_back(k.response); rows.push_back((float)k.octave);
+                }
+                wr("detfast_kp.bin", rows);
+            }
         }
     }
 

@@ -123,6 +123,16 @@ def test_adapter_end_to_end(tmp_path, O):
         assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), gridn
         assert np.array_equal(_rd(d, f"det{gridn}_octave.bin", np.int32), [q[5] for q in raw])
 
+    # detector == "FAST": the 500 strongest cv::FAST corners (scores are integers, so the cut falls inside a group of ties
+    # whose order is std::sort's; everything above the cut must be there, sorted, and every entry must be a cv2 corner)
+    fk = _rd(d, "detfast_kp.bin", np.float32).reshape(-1, 6)
+    ref = {(k.pt[0], k.pt[1]): k.response for k in cv2.FastFeatureDetector_create(10, True).detect(gray)}
+    assert fk.shape[0] == 500 and (np.diff(fk[:, 4]) <= 0).all()
+    assert all(ref.get((r[0], r[1])) == r[4] for r in fk) and len({(r[0], r[1]) for r in fk}) == 500
+    assert (fk[:, 2] == 7).all() and (fk[:, 3] == -1).all() and (fk[:, 5] == 0).all()
+    cut = fk[-1, 4]
+    assert {p for p, v in ref.items() if v > cut} <= {(r[0], r[1]) for r in fk}
+
     # ---- Kabsch ----
     Tk = _rd(d, "kabsch_T.bin", np.float64).reshape(4, 4).T
     assert np.array_equal(bits(Tk[:3]), bits(O.kabsch(A, B)))
