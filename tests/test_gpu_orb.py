@@ -202,3 +202,31 @@ def test_fast_detect_vs_live_cv2(ctx, W, H, threshold, sigma):
     ref3 = cv2.FastFeatureDetector_create(threshold, True).detect(cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY))
     assert np.array_equal(xy3, np.array([k.pt for k in ref3], np.float32).reshape(-1, 2))
     assert np.array_equal(r3, np.array([k.response for k in ref3], np.float32))
+
+
+def test_pixels_to_matches_pipeline(ctx):
+    """The front end from pixels: detectFeatures -> describeFeatures on two frames of one scene (the second shifted by a
+    known amount), then performMatching.  Every stage equals OpenCV's output, and the matches recover the shift."""
+    import cv2
+    import bench
+    a = bench.orb_bench_image(np.random.default_rng(5))
+    dx, dy = 9, -6
+    b = np.roll(np.roll(a, dy, 0), dx, 1)
+    b = np.clip(b.astype(np.int32) + np.random.default_rng(6).integers(-3, 4, b.shape), 0, 255).astype(np.uint8)   # sensor noise
+    frames = []
+    for img in (a, b):
+        det = ctx.orb_detect(img, 500)
+        order, desc = ctx.orb_describe(None, det["xy"], det["octave"], det["angle"], resident_shape=img.shape)
+        ref_kp = cv2.ORB_create().detect(img)
+        ref_kp, ref_desc = cv2.ORB_create().compute(img, ref_kp)
+        assert np.array_equal(desc, ref_desc) and len(ref_kp) == order.size
+        assert all(float(k.pt[0]) == float(det["xy"][i, 0]) and float(k.pt[1]) == float(det["xy"][i, 1]) for k, i in zip(ref_kp, order))
+        frames.append((det["xy"][order], desc))
+    (xa, da), (xb, db) = frames
+    mq, mt, md = ctx.match_bf_mutual(da, db)
+    ref = cv2.BFMatcher(cv2.NORM_HAMMING, True).match(da, db)
+    assert np.array_equal(mq, [m.queryIdx for m in ref]) and np.array_equal(mt, [m.trainIdx for m in ref])
+    assert np.array_equal(md, np.array([m.distance for m in ref], np.float32))
+    shift = xb[mt] - xa[mq]
+    good = (np.abs(shift[:, 0] - dx) < 2.5) & (np.abs(shift[:, 1] - dy) < 2.5)
+    assert mq.size > 150 and good.mean() > 0.6, (mq.size, good.mean())
