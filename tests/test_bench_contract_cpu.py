@@ -25,3 +25,27 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_bench_lines_carry_the_contract():
+    """the bench lines committed under profiles/ (measured on B200) hold every key of the contract, with sane values"""
+    for name in ("bench_r1_final_n1.json", "bench_r1_late_n1.json", "bench_r1_final_n8.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        line = json.loads(open(p).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert key in line, (name, key)
+        assert line["unit"] == "Gcmp/s" and line["value"] > 500 * line["n_gpus"] and line["higher_is_better"] is True
+        assert line["warmup"] >= 3 and line["gpu_launches"] > 0 and line["vs_baseline"] is None
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+        r = line["roofline"]
+        assert r["bound"] in ("hbm", "tensor", "int-pipe") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
+        assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        assert "workload" in line["config"] and "model" not in line["config"]
+        if line["n_gpus"] == 1:
+            assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    late = json.loads(open(os.path.join(ROOT, "profiles", "bench_r1_late_n1.json")).read().strip().splitlines()[-1])
+    fe = late["frontend"]
+    assert fe["orb_describe"]["bit_exact_vs_cv2"] is True and fe["orb_describe"]["detect"]["bit_exact_vs_cv2_order_included"] is True
+    assert fe["native_cpp"]["resident_equals_host_map"] is True and fe["native_cpp"]["frame_to_map_ms"] < 1.0   # north_star: < 1 ms
+    assert fe["c2_sequence"]["parity_bit_exact"] is True
