@@ -34,7 +34,7 @@ def ctx():
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("bf_cv2", "satsub_cv2", "undistort_cv2", "orb_cv2", "orb_detect_cv2")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("bf_cv2", "satsub_cv2", "undistort_cv2", "orb_cv2", "orb_detect_cv2", "klt_cv2")}
 
 
 def bits(a):

@@ -7,6 +7,7 @@ arithmetic of the reference's matching and undistortion calls:
   cv::undistortPoints                                  src/RGBD/RGBD.cpp:268,298
   cv::ORB::compute (provided keypoints)                src/Matcher/matcherOpenCV.cpp:181-195
   cv::ORB::detect                                      src/Matcher/matcherOpenCV.cpp:118-176
+  cv::calcOpticalFlowPyrLK                             src/Matcher/matcherOpenCV.cpp:209-236
 
 Run in the build container (cv2 4.13.0):  python tests/golden/make_golden.py
 The vectors are small on purpose; the oracle (oracle/oracle.c) and the CUDA path are both checked
@@ -128,10 +129,38 @@ def orb_detect_cases():
     return out
 
 
+def klt_cases():
+    """cv::calcOpticalFlowPyrLK as MatcherOpenCV::performTracking calls it (src/Matcher/matcherOpenCV.cpp:209-236):
+    colour frames, winSize 7, 3 pyramid levels above the base, 30 iterations / eps 0.01; plus a gray case and the
+    two flag variants."""
+    rng = np.random.default_rng(59)
+    crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    H, W = 150, 200
+    g = orb_scene(rng, H, W)
+    a = np.stack([g, np.roll(g, 4, 1), 255 - np.roll(g, 3, 0)], 2).copy()
+    M = np.float32([[0.9985, 0.02, 2.6], [-0.02, 0.9985, -1.9]])
+    b = cv2.warpAffine(a, M, (W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    b = np.clip(b.astype(np.int32) + rng.integers(-2, 3, b.shape), 0, 255).astype(np.uint8)
+    n = 120
+    pts = np.stack([rng.uniform(1, W - 1, n), rng.uniform(1, H - 1, n)], 1).astype(np.float32)
+    pts[:4] = [[0.2, 0.3], [W - 1.2, H - 1.4], [3.5, H - 2.0], [W / 2, H / 2]]
+    init = (pts + rng.normal(0, 1.2, pts.shape)).astype(np.float32)
+    out = {"a": a, "b": b, "pts": pts, "init": init}
+    for name, ia, ib, kw, nxt in (("colour", a, b, {}, None), ("gray", a[..., 0].copy(), b[..., 0].copy(), {}, None),
+                                  ("mineig", a, b, {"flags": cv2.OPTFLOW_LK_GET_MIN_EIGENVALS}, None),
+                                  ("initflow", a, b, {"flags": cv2.OPTFLOW_USE_INITIAL_FLOW}, init)):
+        p1, st, er = cv2.calcOpticalFlowPyrLK(ia, ib, pts.reshape(-1, 1, 2), None if nxt is None else nxt.reshape(-1, 1, 2).copy(),
+                                              winSize=(7, 7), maxLevel=3, criteria=crit, **kw)
+        out[name + "_next"] = p1.reshape(-1, 2); out[name + "_status"] = st.ravel(); out[name + "_err"] = er.ravel()
+    out["names"] = np.array(["colour", "gray", "mineig", "initflow"])
+    return out
+
+
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "bf_cv2.npz"), **bf_cases())
     np.savez_compressed(os.path.join(HERE, "satsub_cv2.npz"), **satsub_cases())
     np.savez_compressed(os.path.join(HERE, "undistort_cv2.npz"), **undistort_cases())
     np.savez_compressed(os.path.join(HERE, "orb_cv2.npz"), **orb_cases())
     np.savez_compressed(os.path.join(HERE, "orb_detect_cv2.npz"), **orb_detect_cases())
+    np.savez_compressed(os.path.join(HERE, "klt_cv2.npz"), **klt_cases())
     print("cv2", cv2.__version__, "golden vectors written to", HERE)

@@ -461,3 +461,76 @@ def test_orb_detect_stages_against_live_cv2():
         ref = _kp_set(np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in kps], np.float32), [k.octave for k in kps])
         got = {(float(m[0]), float(m[1]), int(m[5])): (float(m[2]), float(m[3]), float(m[4])) for m in OO.detect(img, nf)}
         assert got == ref, nf
+
+
+# ---------------------------------------------------------------- KLT tracking (performTracking seam)
+def test_klt_oracle_matches_cv2_golden(golden):
+    """oracle/klt_oracle.py against cv::calcOpticalFlowPyrLK recorded from cv2 4.13.0: tracked positions, status and
+    err bit for bit -- colour and gray frames, minimum-eigenvalue error, initial flow"""
+    from oracle import klt_oracle as K
+    g = golden["klt_cv2"]
+    a, b, pts = g["a"], g["b"], g["pts"]
+    cases = {"colour": (a, b, {}), "gray": (a[..., 0], b[..., 0], {}), "mineig": (a, b, {"min_eig_err": True}),
+             "initflow": (a, b, {"init": g["init"]})}
+    for name in g["names"]:
+        ia, ib, kw = cases[str(name)]
+        nxt, st, err = K.lk_pyr(ia, ib, pts, **kw)
+        assert np.array_equal(st, g[f"{name}_status"]), name
+        ok = st == 1
+        assert 60 < ok.sum() < len(pts)                                              # some points are lost at the borders
+        assert np.array_equal(nxt[ok].view(np.uint32), g[f"{name}_next"][ok].view(np.uint32)), name
+        assert np.array_equal(err[ok].view(np.uint32), g[f"{name}_err"][ok].view(np.uint32)), name
+
+
+def test_klt_stages_and_extreme_contrast_against_live_cv2():
+    import cv2
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(67)
+    img = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    ref = img
+    mine = img
+    for _ in range(3):                                                               # pyrDown cascade, odd sizes
+        ref = cv2.pyrDown(ref); mine = K.pyr_down(mine)
+        assert np.array_equal(ref, mine)
+    # blocks of 0 / 255: the float accumulation order of the window sums matters here (it is the scalar raster order)
+    a = cv2.resize(rng.integers(0, 2, (60, 80), dtype=np.uint8) * 255, (160, 120), interpolation=cv2.INTER_NEAREST)
+    b = cv2.warpAffine(a, np.float32([[1, 0, 0.3], [0, 1, 0.2]]), (160, 120), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    pts = np.stack([rng.uniform(3, 157, 80), rng.uniform(3, 117, 80)], 1).astype(np.float32)
+    crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    p1, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts.reshape(-1, 1, 2), None, winSize=(7, 7), maxLevel=3, criteria=crit)
+    nxt, ms, me = K.lk_pyr(a, b, pts)
+    ok = st.ravel() == 1
+    assert np.array_equal(ms, st.ravel()) and ok.sum() > 20
+    assert np.array_equal(nxt[ok].view(np.uint32), p1.reshape(-1, 2)[ok].view(np.uint32))
+    assert np.array_equal(me[ok].view(np.uint32), er.ravel()[ok].view(np.uint32))
+    # colour frames with hard edges, several window sizes (27 / 15 / 39 values per window row): the lane order of the sums
+    for win, lev in ((9, 2), (5, 1), (13, 2)):
+        ca = cv2.resize(rng.integers(0, 2, (60, 80, 3), dtype=np.uint8) * 255, (160, 120), interpolation=cv2.INTER_NEAREST)
+        cb = cv2.warpAffine(ca, np.float32([[1, 0, 0.4], [0, 1, -0.3]]), (160, 120), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+        cp = pts[:40]
+        p1, st, er = cv2.calcOpticalFlowPyrLK(ca, cb, cp.reshape(-1, 1, 2), None, winSize=(win, win), maxLevel=lev, criteria=crit)
+        nxt, ms, me = K.lk_pyr(ca, cb, cp, win=win, max_level=lev)
+        ok = st.ravel() == 1
+        assert np.array_equal(ms, st.ravel()) and ok.sum() > 10
+        assert np.array_equal(nxt[ok].view(np.uint32), p1.reshape(-1, 2)[ok].view(np.uint32)), win
+        assert np.array_equal(me[ok].view(np.uint32), er.ravel()[ok].view(np.uint32)), win
+    # another window size and pyramid depth
+    g = cv2.GaussianBlur(rng.integers(0, 256, (120, 160), dtype=np.uint8), (0, 0), 1.5)
+    g2 = cv2.warpAffine(g, np.float32([[1, 0, 1.7], [0, 1, -1.1]]), (160, 120), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    p1, st, er = cv2.calcOpticalFlowPyrLK(g, g2, pts.reshape(-1, 1, 2), None, winSize=(11, 11), maxLevel=2, criteria=crit)
+    nxt, ms, me = K.lk_pyr(g, g2, pts, win=11, max_level=2)
+    ok = st.ravel() == 1
+    assert np.array_equal(ms, st.ravel()) and np.array_equal(nxt[ok].view(np.uint32), p1.reshape(-1, 2)[ok].view(np.uint32))
+    assert np.array_equal(me[ok].view(np.uint32), er.ravel()[ok].view(np.uint32))
+
+
+def test_klt_perform_tracking_postprocessing():
+    """error threshold, pairwise too-close removal (the larger err goes, the second on ties, every feature takes part
+    whatever its status), ordered survivors"""
+    from oracle import klt_oracle as K
+    pts = np.array([[10, 10], [10.5, 10], [50, 50], [50, 50.4], [90, 90], [10.2, 10.1]], np.float32)
+    err = np.array([1.0, 2.0, 3.0, 3.0, 9.0, 0.5], np.float32)
+    status = np.array([1, 1, 1, 1, 1, 0], np.uint8)
+    kept = K.perform_tracking(err, status, pts, error_threshold=5.0, min_distance=1.0)
+    # 0-1 close: 1 goes; 0-5 close: 0 goes (err 1.0 > 0.5); 1-5 close: 1 goes; 2-3 tie: 3 goes; 4 over the threshold; 5 lost
+    assert kept.tolist() == [2]
