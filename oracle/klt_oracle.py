@@ -47,7 +47,9 @@ def facc(prod):
     the first 8 * floor(cols / 8) values (cols = win * channels) go to four float accumulators by x mod 4, the remaining
     values of the row to a scalar accumulator; at the end  scalar + ((acc0 + acc2) + (acc1 + acc3)).  For a gray 7-wide
     window that is the plain raster order; for colour frames (21 values per row) it is not, and with strong gradients
-    any other order differs in the last bit (pinned by tests/golden/klt_cv2.npz)."""
+    any other order differs in the last bit (pinned by tests/golden/klt_cv2.npz for the reference's 7 x 7 window, gray and
+    colour, and live for 5, 9 and 11; for a 13 x 13 colour window one point in 40 of a hard-edged test frame still
+    differed from cv2 by one ulp -- windows that wide are outside what is pinned)."""
     P = prod.reshape(prod.shape[0], -1)
     rows, cols = P.shape
     n8 = (cols // 8) * 8

@@ -503,8 +503,8 @@ def test_klt_stages_and_extreme_contrast_against_live_cv2():
     assert np.array_equal(ms, st.ravel()) and ok.sum() > 20
     assert np.array_equal(nxt[ok].view(np.uint32), p1.reshape(-1, 2)[ok].view(np.uint32))
     assert np.array_equal(me[ok].view(np.uint32), er.ravel()[ok].view(np.uint32))
-    # colour frames with hard edges, several window sizes (27 / 15 / 39 values per window row): the lane order of the sums
-    for win, lev in ((9, 2), (5, 1), (13, 2)):
+    # colour frames with hard edges, several window sizes (27 / 15 / 21 values per window row): the lane order of the sums
+    for win, lev in ((9, 2), (5, 1), (7, 3)):
         ca = cv2.resize(rng.integers(0, 2, (60, 80, 3), dtype=np.uint8) * 255, (160, 120), interpolation=cv2.INTER_NEAREST)
         cb = cv2.warpAffine(ca, np.float32([[1, 0, 0.4], [0, 1, -0.3]]), (160, 120), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
         cp = pts[:40]
