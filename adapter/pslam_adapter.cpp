@@ -426,6 +426,65 @@ cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint
     return out;
 }
 
+std::vector<cv::DMatch> MatcherB200::performTracking(cv::Mat prevImg, cv::Mat img, std::vector<cv::Point2f>& prevFeatures,
+                                                     std::vector<cv::Point2f>& features, std::vector<cv::KeyPoint>& prevKeyPoints,
+                                                     std::vector<cv::KeyPoint>& keyPoints, std::vector<double>& prevDetDists,
+                                                     std::vector<double>& detDists) {
+    std::vector<cv::DMatch> matches;
+    pslam_ctx* c = dev_.ctx();
+    const int n = (int)prevFeatures.size();
+    const TrackingParams& tp = tracking_;
+    const bool init = tp.useInitialFlow > 0;
+    auto giveUp = [&](int code) {
+        if (code != PSLAM_OK) logError(c, "performTracking", code);
+        features.clear(); keyPoints.clear(); detDists.clear();
+        lastTrackedData_ = nullptr;
+        return matches;
+    };
+    if (!c) return giveUp(PSLAM_ERR_NO_DEVICE);
+    if (prevImg.empty() || img.empty() || prevImg.rows != img.rows || prevImg.cols != img.cols || prevImg.channels() != img.channels() ||
+        (init && (int)features.size() != n) || (int)prevKeyPoints.size() != n || (int)prevDetDists.size() != n)
+        return giveUp(PSLAM_ERR_ARG);
+#ifdef PSLAM_USE_REAL_HEADERS
+    const int rowBytes = (int)img.step[0], prevRowBytes = (int)prevImg.step[0];
+#else
+    const int rowBytes = (int)img.step0, prevRowBytes = (int)prevImg.step0;
+#endif
+    if (prevRowBytes != rowBytes) return giveUp(PSLAM_ERR_ARG);
+    std::vector<float> prevXY(2 * (size_t)n + 2), curXY(2 * (size_t)n + 2), err((size_t)n + 1);
+    std::vector<unsigned char> status((size_t)n + 1);
+    std::vector<int> kept((size_t)n + 1);
+    for (int i = 0; i < n; ++i) {
+        prevXY[2 * i] = prevFeatures[(size_t)i].x; prevXY[2 * i + 1] = prevFeatures[(size_t)i].y;
+        if (init) { curXY[2 * i] = features[(size_t)i].x; curXY[2 * i + 1] = features[(size_t)i].y; }
+    }
+    const int flags = (init ? PSLAM_KLT_USE_INITIAL_FLOW : 0) | (tp.trackingErrorType > 0 ? PSLAM_KLT_GET_MIN_EIGENVALS : 0);
+    const bool resident = reuseTracked_ && lastTrackedData_ == prevImg.data && lastTrackedRows_ == prevImg.rows &&
+                          lastTrackedCols_ == prevImg.cols && lastTrackedStep_ == prevRowBytes && lastTrackedCh_ == prevImg.channels() &&
+                          lastTrackedLevels_ >= tp.maxLevels;
+    int nKept = 0;
+    const int r = pslam_klt_perform_tracking(c, resident ? nullptr : prevImg.data, img.data, img.cols, img.rows, rowBytes,
+                                             img.channels(), prevXY.data(), curXY.data(), n, tp.winSize, tp.maxLevels,
+                                             3 /* CV_TERMCRIT_ITER | CV_TERMCRIT_EPS */, tp.maxIter, tp.eps, flags,
+                                             tp.trackingMinEigThreshold, tp.trackingErrorThreshold,
+                                             tp.minimalReprojDistanceNewTrackingFeatures, status.data(), err.data(), kept.data(),
+                                             &nKept);
+    if (r != PSLAM_OK) return giveUp(r);
+    lastTrackedData_ = img.data; lastTrackedRows_ = img.rows; lastTrackedCols_ = img.cols; lastTrackedStep_ = rowBytes;
+    lastTrackedCh_ = img.channels(); lastTrackedLevels_ = tp.maxLevels;
+    features.resize((size_t)nKept); keyPoints.resize((size_t)nKept); detDists.resize((size_t)nKept);
+    matches.reserve((size_t)nKept);
+    for (int j = 0; j < nKept; ++j) {
+        const int i = kept[(size_t)j];
+        features[(size_t)j] = cv::Point2f(curXY[2 * i], curXY[2 * i + 1]);
+        keyPoints[(size_t)j] = prevKeyPoints[(size_t)i];        // keyPoints = prevKeyPoints with the new positions (:238-242)
+        keyPoints[(size_t)j].pt = features[(size_t)j];
+        detDists[(size_t)j] = prevDetDists[(size_t)i];
+        matches.push_back(cv::DMatch(i, j, 0));
+    }
+    return matches;
+}
+
 bool MatcherB200::uploadMapFeatures(int first, const MapSide& features, const std::vector<float>& viewAxis) {
     pslam_ctx* c = dev_.ctx();
     const int M = (int)features.octave.size();

@@ -100,6 +100,28 @@ public:
     // cv::ORB::compute does it (keypoints within 31 px of the border dropped, the rest regrouped by octave); returns
     // one 32-byte row per remaining feature.
     cv::Mat describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint>& features);
+    // MatcherOpenCV::performTracking (src/Matcher/matcherOpenCV.cpp:209-300; virtual, matcher.h:415-422) in one
+    // submission (pslam_klt_perform_tracking): pyramidal Lucas-Kanade of prevFeatures from prevImg to img, err threshold,
+    // pairwise too-close removal; features / keyPoints / detDists come back compacted to the survivors, the result is
+    // DMatch(index in prevFeatures, index in features, 0) like the reference's.  With useInitialFlow `features` must hold
+    // one guess per previous feature on entry (OpenCV's requirement).  On a device error: no matches, empty outputs,
+    // message on std::cerr.
+    struct TrackingParams {   // MatcherParameters::OpenCVParams fields (matcher.h:44-61), shipped defaults
+        int winSize = 7, maxLevels = 3, maxIter = 30;     // resources/putslammatcherOpenCVParameters.xml:64
+        double eps = 0.01;
+        int useInitialFlow = 0, trackingErrorType = 0;
+        double trackingErrorThreshold = 25.0, trackingMinEigThreshold = 0.0;
+        double minimalReprojDistanceNewTrackingFeatures = 3.0;
+    };
+    void setTrackingParams(const TrackingParams& p) { tracking_ = p; }
+    std::vector<cv::DMatch> performTracking(cv::Mat prevImg, cv::Mat img, std::vector<cv::Point2f>& prevFeatures,
+                                            std::vector<cv::Point2f>& features, std::vector<cv::KeyPoint>& prevKeyPoints,
+                                            std::vector<cv::KeyPoint>& keyPoints, std::vector<double>& prevDetDists,
+                                            std::vector<double>& detDists);
+    // Opt-in: Matcher::trackKLT passes prevRgbImage = the frame it tracked INTO one call earlier (matcher.cpp:151-152).
+    // When on, and prevImg is the very Mat (data pointer, size, step) the last performTracking received as img, the
+    // previous frame is not uploaded again: its pyramid is still in HBM.  Same promise as setReuseDetectedFrame.
+    void setReuseTrackedFrame(bool on) { reuseTracked_ = on; }
     // Opt-in: when describeFeatures is called with the very Mat (same data pointer, size, step) the last full-frame
     // detectFeatures saw, skip the second upload and describe on the frame already in HBM.  The caller promises not to
     // modify the pixels between the two calls (Matcher::match does not, src/Matcher/matcher.cpp:457-467).
@@ -173,6 +195,10 @@ private:
     bool hostLevels_ = false;
     std::vector<cv::KeyPoint> detectGrid(cv::Mat rgbImage, int gridCols, int gridRows, int maximalTrackedFeatures, bool fast);
     bool reuseFrame_ = false;
+    TrackingParams tracking_;
+    bool reuseTracked_ = false;
+    const unsigned char* lastTrackedData_ = nullptr;   // img of the last performTracking
+    int lastTrackedRows_ = 0, lastTrackedCols_ = 0, lastTrackedStep_ = 0, lastTrackedCh_ = 0, lastTrackedLevels_ = 0;
     const unsigned char* lastFrameData_ = nullptr;   // frame of the last 1 x 1 detectFeatures
     int lastFrameRows_ = 0, lastFrameCols_ = 0, lastFrameStep_ = 0, lastFrameCh_ = 0;
 };

@@ -37,9 +37,55 @@ static void wrMatches(const std::string& name, const std::vector<cv::DMatch>& m)
     wr(name + "_q.bin", q); wr(name + "_t.bin", t); wr(name + "_img.bin", img); wr(name + "_d.bin", d);
 }
 
+// ---- Matcher::trackKLT's tracking step (matcher.cpp:151-158): performTracking over a three-frame sequence ----
+// frame 0 -> 1 uploads both frames; 1 -> 2 passes the Mat it tracked into as prevImg (prevRgbImage), whose pyramid is
+// still resident; the third call (useInitialFlow, min-eigenvalue error) goes 0 -> 2 with fresh uploads.
+static int kltSection() {
+    auto dims = rd<int>("klt_dims.bin");                            // H, W, channels
+    auto f0 = rd<uint8_t>("klt_f0.bin"), f1 = rd<uint8_t>("klt_f1.bin"), f2 = rd<uint8_t>("klt_f2.bin");
+    auto xy = rd<float>("klt_xy.bin");
+    const int type = dims[2] == 3 ? CV_8UC3 : CV_8U;
+    cv::Mat m0(dims[0], dims[1], type, f0.data()), m1(dims[0], dims[1], type, f1.data()), m2(dims[0], dims[1], type, f2.data());
+    MatcherB200 matcher(0);
+    matcher.setReuseTrackedFrame(true);
+    std::vector<cv::Point2f> prev(xy.size() / 2), cur;
+    std::vector<cv::KeyPoint> prevKp(prev.size()), curKp;
+    std::vector<double> prevDet(prev.size()), curDet;
+    for (size_t i = 0; i < prev.size(); ++i) {
+        prev[i] = cv::Point2f(xy[2 * i], xy[2 * i + 1]);
+        prevKp[i].pt = prev[i]; prevKp[i].class_id = (int)i; prevKp[i].octave = (int)(i % 5); prevDet[i] = 0.25 * (double)i;
+    }
+    auto dump = [&](const std::string& tag, const std::vector<cv::DMatch>& m) {
+        wrMatches(tag, m);
+        std::vector<float> p; std::vector<int> ids, octs;
+        for (size_t j = 0; j < cur.size(); ++j) {
+            p.push_back(cur[j].x); p.push_back(cur[j].y); p.push_back(curKp[j].pt.x); p.push_back(curKp[j].pt.y);
+            ids.push_back(curKp[j].class_id); octs.push_back(curKp[j].octave);
+        }
+        wr(tag + "_xy.bin", p); wr(tag + "_id.bin", ids); wr(tag + "_oct.bin", octs); wr(tag + "_det.bin", curDet);
+    };
+    std::vector<cv::DMatch> m01 = matcher.performTracking(m0, m1, prev, cur, prevKp, curKp, prevDet, curDet);
+    dump("klt01", m01);
+    std::vector<cv::Point2f> prev1 = cur;
+    std::vector<cv::KeyPoint> prevKp1 = curKp;
+    std::vector<double> prevDet1 = curDet;
+    std::vector<cv::DMatch> m12 = matcher.performTracking(m1, m2, prev1, cur, prevKp1, curKp, prevDet1, curDet);
+    dump("klt12", m12);
+    MatcherB200::TrackingParams tp;
+    tp.useInitialFlow = 1; tp.trackingErrorType = 1; tp.trackingErrorThreshold = 1e9; tp.trackingMinEigThreshold = 1e-3;
+    tp.minimalReprojDistanceNewTrackingFeatures = 1.5; tp.winSize = 9; tp.maxLevels = 2;
+    matcher.setTrackingParams(tp);
+    cur = prev;                                                     // the guess: no motion
+    std::vector<cv::DMatch> m02 = matcher.performTracking(m0, m2, prev, cur, prevKp, curKp, prevDet, curDet);
+    dump("klt02", m02);
+    std::cout << "adapter_selftest klt ok: " << m01.size() << " / " << m12.size() << " / " << m02.size() << " tracked" << std::endl;
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { std::cerr << "usage: adapter_selftest <dir>" << std::endl; return 2; }
+    if (argc < 2) { std::cerr << "usage: adapter_selftest <dir> [klt]" << std::endl; return 2; }
     g_dir = argv[1];
+    if (argc > 2 && std::string(argv[2]) == "klt") return kltSection();
     float Kf[9] = {517.3f, 0, 318.6f, 0, 516.5f, 255.3f, 0, 0, 1};
     float Df[5] = {-0.0410f, 0.3286f, 0.0087f, 0.0051f, -0.5643f};
     cv::Mat K(3, 3, CV_32FC1, Kf), D(1, 5, CV_32FC1, Df);

@@ -280,7 +280,62 @@ def frontend_numbers(ctx, steps, warmup):
                                 "mean_inliers": float(np.mean(inl)) if inl else 0.0,
                                 "ransac": "adaptive (reference bound 487)"}
     out["orb_describe"] = orb_describe_numbers(ctx, steps, warmup)
+    try:
+        out["klt_tracking"] = klt_numbers(ctx, steps, warmup)
+    except Exception as e:  # noqa: BLE001 -- a side measurement must not take the headline line down
+        out["klt_tracking"] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def klt_numbers(ctx, steps, warmup):
+    """performTracking (cv::calcOpticalFlowPyrLK + threshold + pairwise too-close rule) with the reference's parameters
+    (window 7, 3 levels, 30 / 0.01, thresholds 25 / 0 / 3 px) on 640x480 3-channel frames, 1000 points; host frames
+    in, positions / status / err / survivors out; cv2's own call on the host beside it."""
+    rng = np.random.default_rng(78)
+    g = orb_bench_image(rng)
+    f0 = np.stack([g, np.roll(g, 3, 1), 255 - np.roll(g, 2, 0)], 2).copy()
+    f1 = np.roll(np.roll(f0, 2, 1), 1, 0).copy()
+    f1 = np.clip(f1.astype(np.int32) + rng.integers(-2, 3, f1.shape), 0, 255).astype(np.uint8)
+    n = 1000
+    pts = np.stack([rng.uniform(8, 631, n), rng.uniform(8, 471, n)], 1).astype(np.float32)
+    kw = dict(min_eig_threshold=0.0, prune=(25.0, 3.0))
+    for _ in range(warmup):
+        r = ctx.klt_track(f0, f1, pts, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = ctx.klt_track(f0, f1, pts, **kw)
+    res = {"e2e_ms_per_frame_both_frames_uploaded": (time.perf_counter() - t0) / steps * 1e3, "points": n,
+           "tracked": int(r["status"].sum()), "kept": int(r["kept"].size), "image": "640x480x3",
+           "h2d_bytes": int(2 * f0.size + 8 * n), "d2h_bytes": int(14 * n)}
+    # a tracked sequence: the previous frame's pyramid stays in HBM, one frame uploaded per call (frames alternate)
+    ctx.klt_track(f0, f1, pts, **kw)
+    seq = [f0, f1]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ctx.klt_track(None, seq[i % 2], pts, **kw)
+    res["e2e_ms_per_frame_previous_resident"] = (time.perf_counter() - t0) / steps * 1e3
+    try:
+        import cv2
+        crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01)
+        args = dict(winSize=(7, 7), maxLevel=3, criteria=crit, minEigThreshold=0.0)
+        p1, st, er = cv2.calcOpticalFlowPyrLK(f0, f1, pts.reshape(-1, 1, 2), None, **args)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cv2.calcOpticalFlowPyrLK(f0, f1, pts.reshape(-1, 1, 2), None, **args)
+        res["cv2_ms_all_threads"] = (time.perf_counter() - t0) / 5 * 1e3
+        cv2.setNumThreads(1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            cv2.calcOpticalFlowPyrLK(f0, f1, pts.reshape(-1, 1, 2), None, **args)
+        res["cv2_ms_1_thread"] = (time.perf_counter() - t0) / 5 * 1e3
+        cv2.setNumThreads(0)
+        ok = st.ravel() == 1
+        res["bit_exact_vs_cv2"] = bool(np.array_equal(r["status"], st.ravel())
+                                       and np.array_equal(r["xy"][ok].view(np.uint32), p1.reshape(-1, 2)[ok].view(np.uint32))
+                                       and np.array_equal(r["err"][ok].view(np.uint32), er.ravel()[ok].view(np.uint32)))
+    except Exception as e:  # noqa: BLE001
+        res["cv2"] = f"unavailable: {e}"
+    return res
 
 
 def orb_bench_image(rng):

@@ -350,6 +350,42 @@ PSLAM_API int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_po
                                           int* match_query_out, int* match_train_out, float* match_dist_out,
                                           int* inlier_idx_out, pslam_frame_result* result);
 
+/* ---- KLT tracking: the performTracking seam ------------------------------
+ * pslam_klt_track == cv::calcOpticalFlowPyrLK(prevImg, img, prevPts, nextPts, status, err, Size(win, win), max_level,
+ * TermCriteria(criteria_type, max_iter, eps), flags, min_eig_threshold) as MatcherOpenCV::performTracking calls it
+ * (src/Matcher/matcherOpenCV.cpp:209-241, on the colour frames: src/Matcher/matcher.cpp:151-158): pyramids of both
+ * frames (cv::pyrDown), then every point from the coarsest level to the base -- Scharr gradients, 2^14 fixed-point
+ * bilinear windows, the 2 x 2 normal equations, Newton steps -- with OpenCV's arithmetic, so cur_xy / status / err equal
+ * OpenCV's bit for bit (tests/golden/klt_cv2.npz).
+ *   prev_image  NULL: the previous frame is the cur_image of the preceding pslam_klt_* call on this context (same size
+ *               and channels, at least as many pyramid levels) -- its pyramid is still resident, so a tracked
+ *               sequence uploads every frame once.
+ *   channels    1 or 3 (the reference tracks on the 3-channel frames); rows of row_bytes >= channels * W bytes.
+ *   cur_xy      n x 2, in/out: read as the initial guess when flags has PSLAM_KLT_USE_INITIAL_FLOW.
+ *   win         odd or even, 3 .. 21 (reference: 7); max_level 0 .. 7 (reference: 3; like OpenCV the pyramid ends
+ *               where the next level would not exceed the window).
+ *   criteria_type  bit 0: max_iter counts (else 30), bit 1: eps counts (else 0.01) -- cv::TermCriteria::COUNT / EPS;
+ *               max_iter is clamped to [0, 100] and eps to [0, 10] as OpenCV does.
+ *   err         mean absolute window difference in grey levels, or the minimum eigenvalue with
+ *               PSLAM_KLT_GET_MIN_EIGENVALS; status 1 = tracked. */
+enum { PSLAM_KLT_USE_INITIAL_FLOW = 4, PSLAM_KLT_GET_MIN_EIGENVALS = 8 };   /* cv::OPTFLOW_* values */
+PSLAM_API int pslam_klt_track(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H,
+                              int row_bytes, int channels, const float* prev_xy, float* cur_xy, int n, int win,
+                              int max_level, int criteria_type, int max_iter, double eps, int flags,
+                              double min_eig_threshold, uint8_t* status, float* err);
+
+/* pslam_klt_perform_tracking == the whole of MatcherOpenCV::performTracking (matcherOpenCV.cpp:209-300) in one
+ * submission: pslam_klt_track, then status cleared where err > error_threshold (:247-251), then of every pair of tracked
+ * positions (all features, whatever their status) closer than min_distance the one with the larger err is dropped, the
+ * second on ties (:254-266; N^2 / 2 pair tests on the device).  kept_idx_out (capacity n) lists the surviving feature
+ * indices in order: survivor j is DMatch(kept_idx_out[j], j, 0) and row j of the compacted features / keyPoints /
+ * detDists (:269-290).  cur_xy, status (as returned by the tracker, before the threshold) and err cover all n. */
+PSLAM_API int pslam_klt_perform_tracking(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H,
+                                         int row_bytes, int channels, const float* prev_xy, float* cur_xy, int n, int win,
+                                         int max_level, int criteria_type, int max_iter, double eps, int flags,
+                                         double min_eig_threshold, double error_threshold, double min_distance,
+                                         uint8_t* status, float* err, int* kept_idx_out, int* n_kept_out);
+
 /* ---- loop-closure sweep: query frame vs every keyframe of the map --------------------------
  * Generalises Matcher::matchFeatureLoopClosure's performMatching step (src/Matcher/matcher.cpp:802-861,
  * :835) from one FABMAP-proposed pair to all keyframes: score(k) = number of mutual-NN matches between

@@ -42,22 +42,29 @@ def weights(a, b):
     w01 = int(np.rint(f32(a * f32(f32(1) - b)) * f32(1 << 14)))
     w10 = int(np.rint(f32(f32(f32(1) - a) * b) * f32(1 << 14)))
     return w00, w01, w10, (1 << 14) - w00 - w01 - w10
-def facc(prod):
-    """float32 sum of the window's integer products in the order OpenCV's SSE2-shaped loop leaves: in every window row
+def facc(prod, paired=False):
+    """float32 sum of the window's integer products in the order OpenCV's 128-bit vector loop leaves: in every window row
     the first 8 * floor(cols / 8) values (cols = win * channels) go to four float accumulators by x mod 4, the remaining
-    values of the row to a scalar accumulator; at the end  scalar + ((acc0 + acc2) + (acc1 + acc3)).  For a gray 7-wide
-    window that is the plain raster order; for colour frames (21 values per row) it is not, and with strong gradients
-    any other order differs in the last bit (pinned by tests/golden/klt_cv2.npz for the reference's 7 x 7 window, gray and
-    colour, and live for 5, 9 and 11; for a 13 x 13 colour window one point in 40 of a hard-edged test frame still
-    differed from cv2 by one ulp -- windows that wide are outside what is pinned)."""
+    values of the row to a scalar accumulator; at the end  scalar + ((acc0 + acc2) + (acc1 + acc3)).
+    paired=False (the A11 / A12 / A22 sums): every product is converted and added on its own.
+    paired=True  (the b1 / b2 sums of the Newton steps): within each group of 8 the products x and x + 4 are first added
+    as integers (a 16-bit multiply-add instruction produces both at once), then converted and added -- one rounding
+    instead of two.  For a gray 7-wide window both are the plain raster order.  Pinned by tests/golden/klt_cv2.npz for
+    the reference's 7 x 7 window and live against cv2 for windows 3 ... 21, gray and colour, on hard-edged frames (where
+    any other order differs in the last bit)."""
     P = prod.reshape(prod.shape[0], -1)
     rows, cols = P.shape
     n8 = (cols // 8) * 8
     acc = [f32(0)] * 4
     s = f32(0)
     for y in range(rows):
-        for x in range(n8):
-            acc[x & 3] = f32(acc[x & 3] + f32(int(P[y, x])))
+        if paired:
+            for x0 in range(0, n8, 8):
+                for k in range(4):
+                    acc[k] = f32(acc[k] + f32(int(P[y, x0 + k]) + int(P[y, x0 + k + 4])))
+        else:
+            for x in range(n8):
+                acc[x & 3] = f32(acc[x & 3] + f32(int(P[y, x])))
         for x in range(n8, cols):
             s = f32(s + f32(int(P[y, x])))
     return f32(s + f32(f32(acc[0] + acc[2]) + f32(acc[1] + acc[3])))
@@ -66,8 +73,15 @@ def facc(prod):
 def lk_pyr(I0, J0, pts, win=7, max_level=3, max_iter=30, eps=0.01, min_eig_thr=1e-4, init=None, min_eig_err=False):
     if I0.ndim == 2: I0 = I0[..., None]; J0 = J0[..., None]
     cn = I0.shape[2]
+    # calcOpticalFlowPyrLK's normalisation of the criteria (count to [0, 100], epsilon to [0, 10]) and
+    # buildOpticalFlowPyramid's depth: the pyramid ends where the next level would not exceed the window
+    max_iter = min(max(int(max_iter), 0), 100); eps = min(max(float(eps), 0.0), 10.0)
     Is, Js = [I0], [J0]
     for l in range(max_level):
+        h, w = Is[-1].shape[:2]
+        if (w + 1) // 2 <= win or (h + 1) // 2 <= win:
+            max_level = l
+            break
         Is.append(pyr_down(Is[-1])); Js.append(pyr_down(Js[-1]))
     n = len(pts)
     nxt = np.zeros((n, 2), np.float32) if init is None else np.array(init, np.float32).copy()
@@ -101,7 +115,7 @@ def lk_pyr(I0, J0, pts, win=7, max_level=3, max_iter=30, eps=0.01, min_eig_thr=1
             D = f32(f32(A11 * A22) - f32(A12 * A12))
             minEig = f32(f32(f32(A22 + A11) - f32(np.sqrt(f32(f32(f32(A11 - A22) * f32(A11 - A22)) + f32(f32(f32(4) * A12) * A12))))) / f32(2 * win * win))
             if min_eig_err: err[i] = minEig
-            if minEig < min_eig_thr or D < np.finfo(np.float32).eps:
+            if float(minEig) < min_eig_thr or D < np.finfo(np.float32).eps:                       # threshold is a double
                 if level == 0: status[i] = 0
                 continue
             D = f32(f32(1) / D)
@@ -114,12 +128,12 @@ def lk_pyr(I0, J0, pts, win=7, max_level=3, max_iter=30, eps=0.01, min_eig_thr=1
                     break
                 ws2 = weights(f32(nx - f32(jx)), f32(ny - f32(jy)))
                 diff = interp(Jp, jx, jy, ws2, 9) - Iw
-                b1 = f32(facc(diff * Ix) * FLT_SCALE); b2 = f32(facc(diff * Iy) * FLT_SCALE)
+                b1 = f32(facc(diff * Ix, True) * FLT_SCALE); b2 = f32(facc(diff * Iy, True) * FLT_SCALE)
                 dx = f32(f32(f32(A12 * b2) - f32(A22 * b1)) * D); dy = f32(f32(f32(A12 * b1) - f32(A11 * b2)) * D)
                 nx = f32(nx + dx); ny = f32(ny + dy)
                 nxt[i] = (f32(nx + half), f32(ny + half))
                 if float(dx) * float(dx) + float(dy) * float(dy) <= eps * eps: break
-                if j > 0 and abs(float(dx) + float(pdx)) < 0.01 and abs(float(dy) + float(pdy)) < 0.01:
+                if j > 0 and abs(float(f32(dx + pdx))) < 0.01 and abs(float(f32(dy + pdy))) < 0.01:   # float sum, double compare
                     nxt[i] = (f32(nxt[i, 0] - f32(dx * f32(0.5))), f32(nxt[i, 1] - f32(dy * f32(0.5)))); break
                 pdx, pdy = dx, dy
             if status[i] and level == 0 and not min_eig_err:

@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_klt_track", "pslam_klt_perform_tracking", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -248,6 +248,36 @@ class Context:
         self._ck(self.lib.pslam_fast_detect(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, int(colour_order), int(threshold),
                                             _p(xy, C.c_float), _p(resp, C.c_float), cap, C.byref(n)))
         return xy[:n.value].copy(), resp[:n.value].copy()
+
+    # ---- KLT tracking (performTracking seam) ----
+    KLT_USE_INITIAL_FLOW, KLT_GET_MIN_EIGENVALS = 4, 8
+
+    def klt_track(self, prev_image, cur_image, prev_xy, init_xy=None, win=7, max_level=3, max_iter=30, eps=0.01,
+                  criteria_type=3, min_eig_err=False, min_eig_threshold=1e-4, prune=None):
+        """cv::calcOpticalFlowPyrLK(prev_image, cur_image, prev_xy, ...) -> dict(xy float32[n, 2], status uint8[n],
+        err float32[n]); prev_image None = the current frame of the previous klt call on this context.
+        prune=(error_threshold, min_distance): the whole of MatcherOpenCV::performTracking, adds kept int32[m]."""
+        cur = np.ascontiguousarray(cur_image, np.uint8)
+        prev = None if prev_image is None else np.ascontiguousarray(prev_image, np.uint8)
+        if prev is not None and prev.shape != cur.shape:
+            raise ValueError("klt_track: frames differ in shape")
+        ch = 3 if cur.ndim == 3 else 1
+        H, W = cur.shape[:2]
+        p = _arr(prev_xy, np.float32, 2); n = len(p)
+        flags = (self.KLT_GET_MIN_EIGENVALS if min_eig_err else 0) | (self.KLT_USE_INITIAL_FLOW if init_xy is not None else 0)
+        xy = np.zeros((max(n, 1), 2), np.float32)
+        if init_xy is not None:
+            xy[:n] = _arr(init_xy, np.float32, 2)
+        st = np.zeros(max(n, 1), np.uint8); err = np.zeros(max(n, 1), np.float32)
+        common = (self.h, _p(prev, C.c_uint8), _p(cur, C.c_uint8), W, H, ch * W, ch, _p(p, C.c_float), _p(xy, C.c_float), n,
+                  int(win), int(max_level), int(criteria_type), int(max_iter), C.c_double(eps), flags, C.c_double(min_eig_threshold))
+        if prune is None:
+            self._ck(self.lib.pslam_klt_track(*common, _p(st, C.c_uint8), _p(err, C.c_float)))
+            return dict(xy=xy[:n].copy(), status=st[:n].copy(), err=err[:n].copy())
+        kept = np.zeros(max(n, 1), np.int32); m = C.c_int(0)
+        self._ck(self.lib.pslam_klt_perform_tracking(*common, C.c_double(prune[0]), C.c_double(prune[1]), _p(st, C.c_uint8),
+                                                     _p(err, C.c_float), _p(kept, C.c_int), C.byref(m)))
+        return dict(xy=xy[:n].copy(), status=st[:n].copy(), err=err[:n].copy(), kept=kept[:m.value].copy())
 
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):

@@ -163,6 +163,10 @@ struct pslam_ctx {
     DevBuf d_orb_frame;
     int orbf_W = 0, orbf_H = 0, orbf_ch = 0;
     bool orbf_valid = false;
+    // KLT: the pyramids of the two frames of the last pslam_klt_* call; klt_cur = the buffer holding its current frame
+    // (the previous frame of the next call), -1 = none
+    DevBuf d_klt_pyr[2];
+    int klt_cur = -1, klt_W = 0, klt_H = 0, klt_cn = 0, klt_levels = 0;
     // map_prepare_kernel's per-CTA counts (stamped with prep_epoch, so they are never reset)
     unsigned long long* d_prep_counts = nullptr;
     unsigned int prep_epoch = 0;
@@ -387,6 +391,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaFree(ctx->d_lc_pairs);
     cudaFree(ctx->d_map_xyz); cudaFree(ctx->d_map_desc); cudaFree(ctx->d_map_oct); cudaFree(ctx->d_map_det);
     cudaFree(ctx->d_map_axis); cudaFree(ctx->d_prep_counts); cudaFree(ctx->d_orb_tab.p); cudaFree(ctx->d_orb_frame.p);
+    cudaFree(ctx->d_klt_pyr[0].p); cudaFree(ctx->d_klt_pyr[1].p);
     if (ctx->ev_sweep0) cudaEventDestroy(ctx->ev_sweep0);
     if (ctx->ev_sweep1) cudaEventDestroy(ctx->ev_sweep1);
     cudaStreamDestroy(ctx->stream);
@@ -1424,6 +1429,126 @@ int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int ro
     *n_out = found;
     if (found > cap) return fail(ctx, PSLAM_ERR_CAPACITY, "pslam_fast_detect: %d corners, capacity %d", found, cap);
     return PSLAM_OK;
+}
+
+// ---- KLT tracking (MatcherOpenCV::performTracking, reference src/Matcher/matcherOpenCV.cpp:209-300) ----------------
+static double sq_threshold_d(double d) {   // smallest double T with sqrt(T) >= d: sqrt(s) < d  <=>  s < T
+    if (!(d > 0.)) return 0.;              // nothing is closer than a non-positive (or NaN) distance
+    if (isinf(d)) return INFINITY;
+    double t = d * d;
+    if (isinf(t)) t = 1.7976931348623157e308;
+    while (t > 0. && sqrt(t) >= d) t = nextafter(t, 0.);
+    while (sqrt(t) < d) t = nextafter(t, INFINITY);
+    return t;
+}
+static void pack_rows(uint8_t* dst, const uint8_t* src, size_t row, int H, int row_bytes) {
+    if ((size_t)row_bytes == row) memcpy(dst, src, row * H);
+    else for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * row, src + (size_t)y * row_bytes, row);
+}
+static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H,
+                   int row_bytes, int channels, const float* prev_xy, float* cur_xy, int n, int win, int max_level,
+                   int criteria_type, int max_iter, double eps, int flags, double min_eig_threshold, bool prune,
+                   double error_threshold, double min_distance, uint8_t* status, float* err, int* kept_idx_out,
+                   int* n_kept_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (n_kept_out) *n_kept_out = 0;
+    if (!cur_image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W || n < 0 ||
+        (n > 0 && (!prev_xy || !cur_xy || !status || !err)) || (prune && (!n_kept_out || (n > 0 && !kept_idx_out))) ||
+        (flags & ~(PSLAM_KLT_USE_INITIAL_FLOW | PSLAM_KLT_GET_MIN_EIGENVALS)) || (criteria_type & ~3))
+        return fail(ctx, PSLAM_ERR_ARG, "%s: bad argument", who);
+    if (win < 3 || win > kKltMaxWin || max_level < 0 || max_level >= kKltMaxLevels)
+        return fail(ctx, PSLAM_ERR_UNSUPPORTED, "%s: window %d (3 .. %d) / max_level %d (0 .. %d)", who, win, kKltMaxWin, max_level,
+                    kKltMaxLevels - 1);
+    CK(cudaSetDevice(ctx->device));
+    KltPlan plan, full;
+    klt_plan(W, H, channels, win, max_level, &plan);
+    klt_plan(W, H, channels, 0, kKltMaxLevels - 1, &full);       // buffer layout: independent of window and depth
+    const bool same_shape = ctx->klt_cur >= 0 && ctx->klt_W == W && ctx->klt_H == H && ctx->klt_cn == channels;
+    if (!prev_image && !(same_shape && ctx->klt_levels >= plan.n_levels))
+        return fail(ctx, PSLAM_ERR_ARG, "%s: prev_image == NULL needs a preceding pslam_klt_* call on this context with a "
+                    "%d x %d x %d frame and at least %d pyramid levels", who, W, H, channels, plan.n_levels);
+    const int jbuf = prev_image ? 0 : 1 - ctx->klt_cur, ibuf = 1 - jbuf;
+    const size_t row = (size_t)channels * W, img_bytes = row * H;
+    Arena in, out;
+    const size_t o_img_j = in.take(img_bytes), o_img_i = in.take(prev_image ? img_bytes : 0);
+    const size_t o_prev = in.take(8 * (size_t)n), o_init = in.take(8 * (size_t)n);
+    const size_t o_xy = out.take(8 * (size_t)n), o_err = out.take(4 * (size_t)n), o_st = out.take((size_t)n), o_keep = out.take((size_t)n);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_host(ctx, ctx->h_out, out.off));
+    TRY(ensure_dev(ctx, ctx->d_in, in.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    ctx->klt_cur = -1;                                            // until this call has succeeded
+    TRY(ensure_dev(ctx, ctx->d_klt_pyr[0], full.bytes)); TRY(ensure_dev(ctx, ctx->d_klt_pyr[1], full.bytes));
+    uint8_t* h = ctx->h_in.p;
+    pack_rows(h + o_img_j, cur_image, row, H, row_bytes);
+    if (prev_image) pack_rows(h + o_img_i, prev_image, row, H, row_bytes);
+    const bool init = (flags & PSLAM_KLT_USE_INITIAL_FLOW) != 0;
+    if (n > 0) {
+        memcpy(h + o_prev, prev_xy, 8 * (size_t)n);
+        if (init) memcpy(h + o_init, cur_xy, 8 * (size_t)n);
+    }
+    uint8_t* pyrI = ctx->d_klt_pyr[ibuf].p;
+    uint8_t* pyrJ = ctx->d_klt_pyr[jbuf].p;
+    CK(cudaMemcpyAsync(pyrJ, h + o_img_j, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (prev_image) CK(cudaMemcpyAsync(pyrI, h + o_img_i, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_in.p + o_prev, h + o_prev, (init ? o_init + 8 * (size_t)n : o_prev + 8 * (size_t)n) - o_prev,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    int l = 0;
+    CK(launch_klt_pyramid(prev_image ? pyrI : nullptr, pyrJ, plan, channels, ctx->stream, &l));
+    float* d_xy = (float*)(ctx->d_out.p + o_xy);
+    if (n > 0) {
+        if (init) CK(cudaMemcpyAsync(d_xy, ctx->d_in.p + o_init, 8 * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        KltParams P;
+        memset(&P, 0, sizeof(P));
+        P.n_levels = plan.n_levels; P.win = win; P.cn = channels;
+        klt_criteria(criteria_type & 1, max_iter, criteria_type & 2, eps, &P.max_iter, &P.eps_sq);
+        P.min_eig_thr = min_eig_threshold;
+        P.use_initial_flow = init ? 1 : 0;
+        P.min_eig_err = (flags & PSLAM_KLT_GET_MIN_EIGENVALS) ? 1 : 0;
+        for (int k = 0; k < plan.n_levels; ++k) {
+            P.lv[k].I = pyrI + full.off[k]; P.lv[k].J = pyrJ + full.off[k];
+            P.lv[k].w = plan.w[k]; P.lv[k].h = plan.h[k];
+        }
+        CK(launch_klt_track(P, (const float*)(ctx->d_in.p + o_prev), d_xy, n, ctx->d_out.p + o_st, (float*)(ctx->d_out.p + o_err),
+                            ctx->stream, &l));
+        if (prune)
+            CK(launch_klt_prune(d_xy, (const float*)(ctx->d_out.p + o_err), ctx->d_out.p + o_st, n, error_threshold,
+                                sq_threshold_d(min_distance), ctx->d_out.p + o_keep, ctx->stream, &l));
+        CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, prune ? out.off : o_keep, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->launches += l;
+    ctx->f2m.valid = false; ctx->f2f.valid = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->klt_cur = jbuf; ctx->klt_W = W; ctx->klt_H = H; ctx->klt_cn = channels;
+    // the previous frame's buffer keeps the levels it was built with; the reusable depth is that of the current frame
+    ctx->klt_levels = plan.n_levels;
+    if (n > 0) {
+        memcpy(cur_xy, ctx->h_out.p + o_xy, 8 * (size_t)n);
+        memcpy(err, ctx->h_out.p + o_err, 4 * (size_t)n);
+        memcpy(status, ctx->h_out.p + o_st, (size_t)n);
+        if (prune) {
+            const uint8_t* keep = ctx->h_out.p + o_keep;
+            int m = 0;
+            for (int i = 0; i < n; ++i) if (keep[i]) kept_idx_out[m++] = i;
+            *n_kept_out = m;
+        }
+    }
+    return PSLAM_OK;
+}
+
+int pslam_klt_track(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H, int row_bytes,
+                    int channels, const float* prev_xy, float* cur_xy, int n, int win, int max_level, int criteria_type,
+                    int max_iter, double eps, int flags, double min_eig_threshold, uint8_t* status, float* err) {
+    return klt_run(ctx, "pslam_klt_track", prev_image, cur_image, W, H, row_bytes, channels, prev_xy, cur_xy, n, win, max_level,
+                   criteria_type, max_iter, eps, flags, min_eig_threshold, false, 0., 0., status, err, nullptr, nullptr);
+}
+
+int pslam_klt_perform_tracking(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H, int row_bytes,
+                               int channels, const float* prev_xy, float* cur_xy, int n, int win, int max_level,
+                               int criteria_type, int max_iter, double eps, int flags, double min_eig_threshold,
+                               double error_threshold, double min_distance, uint8_t* status, float* err, int* kept_idx_out,
+                               int* n_kept_out) {
+    return klt_run(ctx, "pslam_klt_perform_tracking", prev_image, cur_image, W, H, row_bytes, channels, prev_xy, cur_xy, n, win,
+                   max_level, criteria_type, max_iter, eps, flags, min_eig_threshold, true, error_threshold, min_distance, status,
+                   err, kept_idx_out, n_kept_out);
 }
 
 // ---- resident feature map -------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/pslam_b200.h"
+#include "klt_point.cuh"
 
 namespace pslam {
 
@@ -159,5 +160,14 @@ cudaError_t launch_fast_detect(const uint8_t* d_bgr, int rgb_order, int W, int H
 cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_bytes, const OrbPlan& P, uint8_t* d_plain,
                                 uint8_t* d_ext, float* d_rowbuf, const int* d_tab, const void* d_pattern, const int* d_rec,
                                 int n_kp, uint8_t* d_desc, cudaStream_t st, int* launches);
+
+// ---- klt.cu ----------------------------------------------------------------------------------
+// level 0 of each pyramid holds the frame; builds levels 1.. of the current frame (d_pyrJ) and, unless d_pyrI is
+// nullptr, of the previous frame
+cudaError_t launch_klt_pyramid(uint8_t* d_pyrI, uint8_t* d_pyrJ, const KltPlan& P, int cn, cudaStream_t st, int* launches);
+cudaError_t launch_klt_track(const KltParams& P, const float* d_prev_xy, float* d_cur_xy, int n, uint8_t* d_status,
+                             float* d_err, cudaStream_t st, int* launches);
+cudaError_t launch_klt_prune(const float* d_xy, const float* d_err, const uint8_t* d_status, int n, double err_thr,
+                             double sq_thr, uint8_t* d_keep, cudaStream_t st, int* launches);
 
 }  // namespace pslam

@@ -1,0 +1,117 @@
+// klt.cu -- K11/K12: the KLT tracking seam, MatcherOpenCV::performTracking (reference src/Matcher/matcherOpenCV.cpp:209-300;
+// virtual, include/putslam/Matcher/matcher.h:415-422; called by Matcher::trackKLT, src/Matcher/matcher.cpp:133-160).
+//   klt_pyrdown_kernel   level l+1 of both frames' pyramids from level l (cv::pyrDown, integer): one launch per level
+//   klt_track_kernel     cv::calcOpticalFlowPyrLK: ONE launch for all points and all levels -- a point's levels depend
+//                        on each other, the points do not, so a warp takes a point from the coarsest level to the base
+//                        (OpenCV runs one parallel_for per level); Scharr gradients are computed on the fly for the
+//                        8 x 8 pixels a window touches instead of for whole images (klt_point.cuh)
+//   klt_prune_kernel     the rest of performTracking: err threshold, and of every pair of tracked positions closer than
+//                        minimalReprojDistanceNewTrackingFeatures the one with the larger err is dropped (:247-266) --
+//                        N^2 / 2 pair tests, one thread per feature over shared-memory tiles of the others
+// Frames are at most a few MB and stay in L2 between the kernels; all three are latency-bound.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pslam {
+
+__global__ void __launch_bounds__(256)
+klt_pyrdown_kernel(const uint8_t* __restrict__ src0, uint8_t* __restrict__ dst0, const uint8_t* __restrict__ src1,
+                   uint8_t* __restrict__ dst1, int w, int h, int cn, int ow, int oh) {
+    chain_begin();
+    const uint8_t* src = blockIdx.z ? src1 : src0;
+    uint8_t* dst = blockIdx.z ? dst1 : dst0;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y;   // e = ox * cn + c
+    if (e >= ow * cn) return;
+    const int ox = e / cn, c = e - ox * cn;
+    dst[(size_t)oy * ow * cn + e] = klt_pyrdown_px(src, w, h, cn, ox, oy, c);
+}
+
+cudaError_t launch_klt_pyramid(uint8_t* d_pyrI, uint8_t* d_pyrJ, const KltPlan& P, int cn, cudaStream_t st, int* launches) {
+    // d_pyrI == nullptr: the previous frame's pyramid is already there (it was the current frame of the last call)
+    for (int l = 1; l < P.n_levels; ++l) {
+        const int w = P.w[l - 1], h = P.h[l - 1], ow = P.w[l], oh = P.h[l];
+        dim3 grid((ow * cn + 255) / 256, oh, d_pyrI ? 2 : 1);
+        cudaError_t e = launch_chained(klt_pyrdown_kernel, grid, dim3(256), 0, st, (const uint8_t*)(d_pyrJ + P.off[l - 1]),
+                                       d_pyrJ + P.off[l], (const uint8_t*)(d_pyrI ? d_pyrI + P.off[l - 1] : nullptr),
+                                       d_pyrI ? d_pyrI + P.off[l] : nullptr, w, h, cn, ow, oh);
+        if (e != cudaSuccess) return e;
+        ++*launches;
+    }
+    return cudaSuccess;
+}
+
+template <int WIN_T, int CN_T>
+__global__ void __launch_bounds__(128)
+klt_track_kernel(const __grid_constant__ KltParams P, const float* __restrict__ prev_xy, float* __restrict__ cur_xy, int n,
+                 uint8_t* __restrict__ status, float* __restrict__ err, int work_bytes) {
+    extern __shared__ __align__(16) uint8_t klt_smem[];
+    chain_begin();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (i >= n) return;                                  // whole warps leave together
+    const KltWork W = klt_carve(klt_smem + (size_t)warp * work_bytes, P.win, P.cn);
+    float nx = 0.f, ny = 0.f, e;
+    uint8_t st;
+    if (P.use_initial_flow) { nx = cur_xy[2 * i]; ny = cur_xy[2 * i + 1]; }
+    klt_track_point<WIN_T, CN_T>(P, W, prev_xy[2 * i], prev_xy[2 * i + 1], nx, ny, st, e);
+    if (lane == 0) {
+        cur_xy[2 * i] = nx; cur_xy[2 * i + 1] = ny;
+        status[i] = st; err[i] = e;
+    }
+}
+
+cudaError_t launch_klt_track(const KltParams& P, const float* d_prev_xy, float* d_cur_xy, int n, uint8_t* d_status,
+                             float* d_err, cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    const int work = (int)klt_work_bytes(P.win, P.cn);
+    int warps = 4;
+    while (warps > 1 && (size_t)warps * work > 48 * 1024) warps >>= 1;
+    if ((size_t)warps * work > 48 * 1024) return cudaErrorInvalidValue;
+    void (*k)(const KltParams, const float*, float*, int, uint8_t*, float*, int) = klt_track_kernel<0, 0>;
+    if (P.win == 7 && P.cn == 3) k = klt_track_kernel<7, 3>;        // the reference's configuration
+    else if (P.win == 7 && P.cn == 1) k = klt_track_kernel<7, 1>;
+    cudaError_t e = launch_chained(k, dim3((n + warps - 1) / warps), dim3(32 * warps), (size_t)warps * work, st, P, d_prev_xy,
+                                   d_cur_xy, n, d_status, d_err, work);
+    if (e == cudaSuccess) ++*launches;
+    return e;
+}
+
+// keep[i] = status[i] && !(err[i] > err_thr) && no closer-than-threshold neighbour wins against i (klt_pair_removes).
+constexpr int kPruneTile = 1024;
+__global__ void __launch_bounds__(128)
+klt_prune_kernel(const float2* __restrict__ xy, const float* __restrict__ err, const uint8_t* __restrict__ status, int n,
+                 double err_thr, double sq_thr, uint8_t* __restrict__ keep) {
+    __shared__ float2 sxy[kPruneTile];
+    __shared__ float serr[kPruneTile];
+    chain_begin();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    float2 p = make_float2(0.f, 0.f);
+    float ei = 0.f;
+    if (live) { p = xy[i]; ei = err[i]; }
+    bool removed = false;
+    for (int base = 0; base < n; base += kPruneTile) {
+        const int m = min(kPruneTile, n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) { sxy[t] = xy[base + t]; serr[t] = err[base + t]; }
+        __syncthreads();
+        if (live && !removed) {
+            for (int t = 0; t < m; ++t) {
+                const float2 q = sxy[t];
+                if (klt_pair_removes(i, base + t, p.x, p.y, ei, q.x, q.y, serr[t], sq_thr)) { removed = true; break; }
+            }
+        }
+    }
+    if (live) keep[i] = (uint8_t)(status[i] != 0 && !((double)ei > err_thr) && !removed);
+}
+
+cudaError_t launch_klt_prune(const float* d_xy, const float* d_err, const uint8_t* d_status, int n, double err_thr,
+                             double sq_thr, uint8_t* d_keep, cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    cudaError_t e = launch_chained(klt_prune_kernel, dim3((n + 127) / 128), dim3(128), 0, st, (const float2*)d_xy, d_err,
+                                   d_status, n, err_thr, sq_thr, d_keep);
+    if (e == cudaSuccess) ++*launches;
+    return e;
+}
+
+}  // namespace pslam

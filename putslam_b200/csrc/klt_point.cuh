@@ -1,0 +1,383 @@
+// klt_point.cuh -- K11: pyramidal Lucas-Kanade for ONE point, executed by ONE WARP (klt.cu).
+//
+// Replaces the cv::calcOpticalFlowPyrLK call of MatcherOpenCV::performTracking (reference
+// src/Matcher/matcherOpenCV.cpp:209-241; window / level / criteria parameters from
+// resources/putslammatcherOpenCVParameters.xml:64).  The arithmetic is OpenCV's (un-vendored dependency); the result is
+// required to equal cv2's bit for bit (positions, status, err), so every float operation below is a single IEEE
+// rounding in OpenCV's operation order, and the window sums run in the accumulator order OpenCV's vector loop leaves
+// behind (klt_chain / klt_combine).
+//
+// Work split of a warp: the window (win x win x channels values, 147 for the reference's 7 x 7 colour window) is spread
+// over the lanes for the loads, the Scharr gradient, and the fixed-point bilinear interpolation; the five ordered
+// partial sums of each of A11, A12, A22 (then b1, b2 per Newton step) are five independent dependent-add chains, one
+// lane each; the 2 x 2 solve is done redundantly by every lane, so all control flow is warp-uniform.  Lanes exchange
+// data only through the warp's shared-memory workspace between KLT_LANES sections -- which is also what lets the very
+// same source run as a loop over 32 "lanes" on a CPU for the kernel's unit test (tests/klt_emul.cpp; test
+// infrastructure, not a product path -- the library has no CPU route).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KLT_HD __host__ __device__ __forceinline__
+#else
+#define KLT_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define KLT_LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u);
+#define KLT_LANES_END } __syncwarp();
+#else
+#define KLT_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define KLT_LANES_END }
+#endif
+
+namespace pslam {
+
+constexpr int kKltMaxLevels = 8;     // base + 7 (a 640 x 480 frame with a 7 x 7 window stops at level 6 anyway)
+constexpr int kKltMaxWin = 21;
+constexpr int kKltWBits = 14;        // bilinear weights in 2^14 fixed point
+
+struct KltLevel {
+    const uint8_t* I;                // previous frame, level image, tight rows of w * cn bytes
+    const uint8_t* J;                // current frame
+    int w, h;
+};
+struct KltParams {
+    int n_levels;                    // max level + 1
+    int win, cn;
+    int max_iter;
+    double eps_sq;                   // criteria.epsilon squared (double, like OpenCV)
+    double min_eig_thr;
+    int use_initial_flow;            // OPTFLOW_USE_INITIAL_FLOW
+    int min_eig_err;                 // OPTFLOW_LK_GET_MIN_EIGENVALS
+    KltLevel lv[kKltMaxLevels];
+};
+
+struct KltPlan {   // pyramid of one frame: level l is w[l] x h[l] x cn bytes (tight rows) at off[l]
+    int n_levels;
+    int w[kKltMaxLevels], h[kKltMaxLevels];
+    size_t off[kKltMaxLevels];
+    size_t bytes;
+};
+// cv::buildOpticalFlowPyramid: the pyramid ends at the first level whose successor would not exceed the window.
+// Returns the number of levels used for `max_level`.
+inline int klt_plan(int W, int H, int cn, int win, int max_level, KltPlan* P) {
+    int w = W, h = H, n = 0;
+    size_t off = 0;
+    for (int level = 0; level <= max_level && level < kKltMaxLevels; ++level) {
+        P->w[level] = w; P->h[level] = h; P->off[level] = off;
+        off = (off + (size_t)w * h * cn + 255) & ~(size_t)255;
+        n = level + 1;
+        w = (w + 1) / 2; h = (h + 1) / 2;
+        if (w <= win || h <= win) break;
+    }
+    P->n_levels = n;
+    P->bytes = off;
+    return n;
+}
+// the termination criteria as calcOpticalFlowPyrLK normalises them: count clamped to [0, 100], epsilon to [0, 10] and
+// squared; a criterion that is not selected gets OpenCV's substitute (30 iterations / 0.01)
+inline void klt_criteria(int use_count, int max_iter, int use_eps, double eps, int* iters, double* eps_sq) {
+    int c = use_count ? max_iter : 30;
+    c = c < 0 ? 0 : (c > 100 ? 100 : c);
+    double e = use_eps ? eps : 0.01;
+    e = e < 0. ? 0. : (e > 10. ? 10. : e);
+    *iters = c;
+    *eps_sq = e * e;
+}
+
+// per-warp workspace (shared memory on the device)
+struct KltWork {
+    uint8_t* pI;                     // (win + 3)^2 * cn : previous-frame patch, one pixel of margin for the gradient
+    uint8_t* pJ;                     // (win + 1)^2 * cn : current-frame patch
+    int16_t *gx, *gy;                // (win + 1)^2 * cn : Scharr gradient of the previous frame
+    int16_t *Iw, *Ix, *Iy, *df;      // win^2 * cn       : interpolated window, its gradient, J - I
+    float* chain;                    // 16
+    int* part;                       // 32
+};
+KLT_HD size_t klt_work_bytes(int win, int cn) {
+    const size_t nP = (size_t)(win + 3) * (win + 3) * cn, nG = (size_t)(win + 1) * (win + 1) * cn, nW = (size_t)win * win * cn;
+    size_t b = ((nP + 3) & ~(size_t)3) + ((nG + 3) & ~(size_t)3);
+    b += 2 * 2 * ((nG + 1) & ~(size_t)1) + 4 * 2 * ((nW + 1) & ~(size_t)1);
+    b += 16 * sizeof(float) + 32 * sizeof(int);
+    return (b + 15) & ~(size_t)15;
+}
+KLT_HD KltWork klt_carve(uint8_t* base, int win, int cn) {
+    const size_t nP = (size_t)(win + 3) * (win + 3) * cn, nG = (size_t)(win + 1) * (win + 1) * cn, nW = (size_t)win * win * cn;
+    KltWork w;
+    w.pI = base; base += (nP + 3) & ~(size_t)3;
+    w.pJ = base; base += (nG + 3) & ~(size_t)3;
+    const size_t g2 = (nG + 1) & ~(size_t)1, w2 = (nW + 1) & ~(size_t)1;
+    w.gx = (int16_t*)base; base += 2 * g2;
+    w.gy = (int16_t*)base; base += 2 * g2;
+    w.Iw = (int16_t*)base; base += 2 * w2;
+    w.Ix = (int16_t*)base; base += 2 * w2;
+    w.Iy = (int16_t*)base; base += 2 * w2;
+    w.df = (int16_t*)base; base += 2 * w2;
+    w.chain = (float*)base; base += 16 * sizeof(float);
+    w.part = (int*)base;
+    return w;
+}
+
+// cv::borderInterpolate(p, n, BORDER_REFLECT_101)
+KLT_HD int klt_reflect101(int p, int n) {
+    if ((unsigned)p < (unsigned)n) return p;
+    if (n == 1) return 0;
+    do {
+        p = p < 0 ? -p : 2 * n - 2 - p;
+    } while ((unsigned)p >= (unsigned)n);
+    return p;
+}
+KLT_HD int klt_round(float v) {       // cvRound: nearest, ties to even
+#if defined(__CUDA_ARCH__)
+    return __float2int_rn(v);
+#else
+    return (int)lrintf(v);
+#endif
+}
+KLT_HD int klt_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// cv::pyrDown, 8-bit: 5 x 5 kernel [1 4 6 4 1] (x) [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8; integer, so the
+// order of the 25 terms is free.  (ox, oy) = output pixel, c = channel.
+KLT_HD uint8_t klt_pyrdown_px(const uint8_t* src, int w, int h, int cn, int ox, int oy, int c) {
+    const int k[5] = {1, 4, 6, 4, 1};
+    int xs[5];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 5; ++j) xs[j] = klt_reflect101(2 * ox - 2 + j, w) * cn + c;
+    int v = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 5; ++i) {
+        const uint8_t* row = src + (size_t)klt_reflect101(2 * oy - 2 + i, h) * w * cn;
+        const int r = (int)row[xs[0]] + (int)row[xs[4]] + 4 * ((int)row[xs[1]] + (int)row[xs[3]]) + 6 * (int)row[xs[2]];
+        v += k[i] * r;
+    }
+    return (uint8_t)((v + 128) >> 8);
+}
+
+struct KltWeights { int w00, w01, w10, w11; };
+KLT_HD KltWeights klt_weights(float a, float b) {
+    const float one = 1.f, s = (float)(1 << kKltWBits);
+    KltWeights w;
+    w.w00 = klt_round(((one - a) * (one - b)) * s);
+    w.w01 = klt_round((a * (one - b)) * s);
+    w.w10 = klt_round(((one - a) * b) * s);
+    w.w11 = (1 << kKltWBits) - w.w00 - w.w01 - w.w10;
+    return w;
+}
+
+// One of the five ordered partial sums of  sum_i a[i] * b[i]  over a window of `rows` rows of `cols` values:
+// k = 0..3: the values x < 8 * floor(cols / 8) of every row with x mod 4 == k; k = 4: the remaining values of every row;
+// each in raster order, float accumulation of the float-converted integer products.
+KLT_HD float klt_chain(const int16_t* a, const int16_t* b, int rows, int cols, int k) {
+    const int n8 = (cols / 8) * 8;
+    float s = 0.f;
+    for (int y = 0; y < rows; ++y) {
+        const int16_t* ra = a + y * cols;
+        const int16_t* rb = b + y * cols;
+        if (k < 4) {
+            for (int x = k; x < n8; x += 4) s = s + (float)((int)ra[x] * (int)rb[x]);
+        } else {
+            for (int x = n8; x < cols; ++x) s = s + (float)((int)ra[x] * (int)rb[x]);
+        }
+    }
+    return s;
+}
+// the same five partial sums as OpenCV's mismatch loop forms them: within every group of 8 values the products x and
+// x + 4 are added as integers (one multiply-add instruction pair) before the float conversion and accumulation
+KLT_HD float klt_chain_paired(const int16_t* a, const int16_t* b, int rows, int cols, int k) {
+    const int n8 = (cols / 8) * 8;
+    float s = 0.f;
+    for (int y = 0; y < rows; ++y) {
+        const int16_t* ra = a + y * cols;
+        const int16_t* rb = b + y * cols;
+        if (k < 4) {
+            for (int x = k; x < n8; x += 8) s = s + (float)((int)ra[x] * (int)rb[x] + (int)ra[x + 4] * (int)rb[x + 4]);
+        } else {
+            for (int x = n8; x < cols; ++x) s = s + (float)((int)ra[x] * (int)rb[x]);
+        }
+    }
+    return s;
+}
+KLT_HD float klt_combine(const float* c) { return c[4] + ((c[0] + c[2]) + (c[1] + c[3])); }
+
+// performTracking's pairwise rule (matcherOpenCV.cpp:254-266), seen from feature i: does the pair (i, j) remove i?
+// The reference visits pairs a < b and drops a when err[a] > err[b], otherwise b (ties and NaNs included).  Closeness:
+// sqrt(dx^2 + dy^2) < d in double on float differences (cv::norm(Point2f)); sq_thr is the smallest double whose square
+// root is >= d, which turns it into an exact comparison of the squared distance.
+KLT_HD bool klt_pair_removes(int i, int j, float xi, float yi, float ei, float xj, float yj, float ej, double sq_thr) {
+    if (i == j) return false;
+    const float dx = xi - xj, dy = yi - yj;    // the square does not see which way round the reference subtracts
+    const double s = (double)dx * (double)dx + (double)dy * (double)dy;
+    if (!(s < sq_thr)) return false;
+    return j > i ? (ei > ej) : !(ej > ei);
+}
+
+// Tracks one point through all levels.  Everything outside the KLT_LANES sections is warp-uniform.
+//   (ptx, pty)  position in the previous frame (level 0)
+//   (nxx, nxy)  in: initial guess when P.use_initial_flow; out: tracked position
+//   WIN_T, CN_T window size / channel count known at compile time (0: taken from P) -- the index arithmetic of the lane
+//               loops then compiles to constant divisions
+template <int WIN_T, int CN_T>
+KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, float pty, float& nxx, float& nxy,
+                            uint8_t& status, float& err) {
+    const int win = WIN_T ? WIN_T : P.win, cn = CN_T ? CN_T : P.cn, cols = win * cn, nW = win * cols;
+    const int gcols = (win + 1) * cn, nG = (win + 1) * gcols;
+    const int pcols = (win + 3) * cn, nP = (win + 3) * pcols;
+    const int max_level = P.n_levels - 1;
+    const float half = (float)((win - 1) * 0.5);
+    const float flt_scale = 1.f / (float)(1 << 20);
+    status = 1;
+    err = 0.f;
+    if (!P.use_initial_flow) { nxx = 0.f; nxy = 0.f; }
+
+    for (int level = max_level; level >= 0; --level) {
+        const uint8_t* I = P.lv[level].I;
+        const uint8_t* J = P.lv[level].J;
+        const int w = P.lv[level].w, h = P.lv[level].h;
+        const float scale = (float)(1.0 / (double)(1 << level));
+        float px = ptx * scale, py = pty * scale;
+        float nx, ny;
+        if (level == max_level) {
+            if (P.use_initial_flow) { nx = nxx * scale; ny = nxy * scale; }
+            else { nx = px; ny = py; }
+        } else {
+            nx = nxx * 2.f; ny = nxy * 2.f;
+        }
+        nxx = nx; nxy = ny;
+        px = px - half; py = py - half;
+        const int ix = (int)floorf(px), iy = (int)floorf(py);
+        if (ix < -win || ix >= w || iy < -win || iy >= h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        const KltWeights wi = klt_weights(px - (float)ix, py - (float)iy);
+
+        // previous-frame patch, pixels (ix - 1 .. ix + win + 1) x (iy - 1 .. iy + win + 1), reflected at the borders
+        KLT_LANES_BEGIN
+        for (int i = lane; i < nP; i += 32) {
+            const int yy = i / pcols, r = i - yy * pcols, xx = r / cn, c = r - xx * cn;
+            const int sx = klt_reflect101(ix - 1 + xx, w), sy = klt_reflect101(iy - 1 + yy, h);
+            W.pI[i] = I[((size_t)sy * w + sx) * cn + c];
+        }
+        KLT_LANES_END
+        // Scharr gradient at the (win + 1)^2 pixels the window touches; zero outside the image
+        KLT_LANES_BEGIN
+        for (int i = lane; i < nG; i += 32) {
+            const int yy = i / gcols, r = i - yy * gcols, xx = r / cn;
+            int dx = 0, dy = 0;
+            if ((unsigned)(ix + xx) < (unsigned)w && (unsigned)(iy + yy) < (unsigned)h) {
+                const uint8_t* p = W.pI + (yy + 1) * pcols + cn + r;   // centre: patch (yy + 1, xx + 1), channel c
+                const int a00 = p[-pcols - cn], a01 = p[-pcols], a02 = p[-pcols + cn];
+                const int a10 = p[-cn], a12 = p[cn];
+                const int a20 = p[pcols - cn], a21 = p[pcols], a22 = p[pcols + cn];
+                dx = (3 * (a02 + a22) + 10 * a12) - (3 * (a00 + a20) + 10 * a10);
+                dy = 3 * ((a20 - a00) + (a22 - a02)) + 10 * (a21 - a01);
+            }
+            W.gx[i] = (int16_t)dx;
+            W.gy[i] = (int16_t)dy;
+        }
+        KLT_LANES_END
+        // window of I (5 fractional bits kept) and of its gradient at the sub-pixel position
+        KLT_LANES_BEGIN
+        for (int i = lane; i < nW; i += 32) {
+            const int y = i / cols, r = i - y * cols;
+            const uint8_t* p = W.pI + (y + 1) * pcols + cn + r;
+            W.Iw[i] = (int16_t)klt_descale(p[0] * wi.w00 + p[cn] * wi.w01 + p[pcols] * wi.w10 + p[pcols + cn] * wi.w11, kKltWBits - 5);
+            const int g = y * gcols + r;
+            W.Ix[i] = (int16_t)klt_descale(W.gx[g] * wi.w00 + W.gx[g + cn] * wi.w01 + W.gx[g + gcols] * wi.w10 + W.gx[g + gcols + cn] * wi.w11, kKltWBits);
+            W.Iy[i] = (int16_t)klt_descale(W.gy[g] * wi.w00 + W.gy[g + cn] * wi.w01 + W.gy[g + gcols] * wi.w10 + W.gy[g + gcols + cn] * wi.w11, kKltWBits);
+        }
+        KLT_LANES_END
+        KLT_LANES_BEGIN
+        if (lane < 15) {
+            const int s = lane / 5, k = lane - 5 * s;
+            W.chain[lane] = klt_chain(s == 2 ? W.Iy : W.Ix, s == 0 ? W.Ix : W.Iy, win, cols, k);
+        }
+        KLT_LANES_END
+        const float A11 = klt_combine(W.chain) * flt_scale, A12 = klt_combine(W.chain + 5) * flt_scale,
+                    A22 = klt_combine(W.chain + 10) * flt_scale;
+        float D = A11 * A22 - A12 * A12;
+        const float dA = A11 - A22;
+        const float min_eig = ((A22 + A11) - sqrtf(dA * dA + (4.f * A12) * A12)) / (float)(2 * win * win);
+        if (P.min_eig_err) err = min_eig;
+        if ((double)min_eig < P.min_eig_thr || D < 1.1920928955078125e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+        nx = nx - half; ny = ny - half;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < P.max_iter; ++j) {
+            const int jx = (int)floorf(nx), jy = (int)floorf(ny);
+            if (jx < -win || jx >= w || jy < -win || jy >= h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            const KltWeights wj = klt_weights(nx - (float)jx, ny - (float)jy);
+            KLT_LANES_BEGIN
+            for (int i = lane; i < nG; i += 32) {
+                const int yy = i / gcols, r = i - yy * gcols, xx = r / cn, c = r - xx * cn;
+                const int sx = klt_reflect101(jx + xx, w), sy = klt_reflect101(jy + yy, h);
+                W.pJ[i] = J[((size_t)sy * w + sx) * cn + c];
+            }
+            KLT_LANES_END
+            KLT_LANES_BEGIN
+            for (int i = lane; i < nW; i += 32) {
+                const int y = i / cols, r = i - y * cols;
+                const uint8_t* p = W.pJ + y * gcols + r;
+                W.df[i] = (int16_t)(klt_descale(p[0] * wj.w00 + p[cn] * wj.w01 + p[gcols] * wj.w10 + p[gcols + cn] * wj.w11, kKltWBits - 5) - (int)W.Iw[i]);
+            }
+            KLT_LANES_END
+            KLT_LANES_BEGIN
+            if (lane < 10) {
+                const int s = lane / 5, k = lane - 5 * s;
+                W.chain[lane] = klt_chain_paired(W.df, s == 0 ? W.Ix : W.Iy, win, cols, k);
+            }
+            KLT_LANES_END
+            const float b1 = klt_combine(W.chain) * flt_scale, b2 = klt_combine(W.chain + 5) * flt_scale;
+            const float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+            nx = nx + dx; ny = ny + dy;
+            nxx = nx + half; nxy = ny + half;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= P.eps_sq) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                nxx = nxx - dx * 0.5f; nxy = nxy - dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0 && !P.min_eig_err) {
+            // err = mean |J - I| over the window at the final position, in 1/32 grey levels -> grey levels
+            const float qx = nxx - half, qy = nxy - half;
+            const int jx = (int)floorf(qx), jy = (int)floorf(qy);
+            if (jx < -win || jx >= w || jy < -win || jy >= h) { status = 0; continue; }
+            const KltWeights wj = klt_weights(qx - (float)jx, qy - (float)jy);
+            KLT_LANES_BEGIN
+            for (int i = lane; i < nG; i += 32) {
+                const int yy = i / gcols, r = i - yy * gcols, xx = r / cn, c = r - xx * cn;
+                const int sx = klt_reflect101(jx + xx, w), sy = klt_reflect101(jy + yy, h);
+                W.pJ[i] = J[((size_t)sy * w + sx) * cn + c];
+            }
+            KLT_LANES_END
+            KLT_LANES_BEGIN
+            int e = 0;   // sum of |diff| <= 21 * 21 * 3 * 8160 < 2^24: exact as an integer, equal to OpenCV's float sum
+            for (int i = lane; i < nW; i += 32) {
+                const int y = i / cols, r = i - y * cols;
+                const uint8_t* p = W.pJ + y * gcols + r;
+                const int d = klt_descale(p[0] * wj.w00 + p[cn] * wj.w01 + p[gcols] * wj.w10 + p[gcols + cn] * wj.w11, kKltWBits - 5) - (int)W.Iw[i];
+                e += d < 0 ? -d : d;
+            }
+            W.part[lane] = e;
+            KLT_LANES_END
+            int e = 0;
+            for (int l = 0; l < 32; ++l) e += W.part[l];
+            err = ((float)e * 1.f) / (float)(32 * win * cn * win);
+        }
+    }
+}
+
+}  // namespace pslam

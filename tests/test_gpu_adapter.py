@@ -138,3 +138,50 @@ def test_adapter_end_to_end(tmp_path, O):
     assert np.array_equal(bits(Tk[:3]), bits(O.kabsch(A, B)))
     assert np.array_equal(Tk[3], [0, 0, 0, 1])
     assert np.array_equal(_rd(d, "kabsch_T_empty.bin", np.float64).reshape(4, 4).T, np.eye(4))
+
+
+def test_adapter_perform_tracking(tmp_path, golden):
+    """MatcherB200::performTracking (reference MatcherOpenCV::performTracking, src/Matcher/matcherOpenCV.cpp:209-300) driven
+    like Matcher::trackKLT drives it over a three-frame sequence -- second call on the resident previous frame, third with
+    useInitialFlow + minimum-eigenvalue error and another window -- against the oracle: matches, compacted features,
+    key points (attributes carried over, positions replaced) and detDists."""
+    import cv2
+    from oracle import klt_oracle as K
+    assert os.path.exists(EXE), "adapter_selftest not built (run __graft_entry__.build())"
+    d = str(tmp_path)
+    g = golden["klt_cv2"]
+    f0, f1 = g["a"], g["b"]
+    H, W = f0.shape[:2]
+    f2 = cv2.warpAffine(f1, np.float32([[1, 0, 1.6], [0, 1, 0.9]]), (W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    pts = g["pts"].copy()
+    pts = np.concatenate([pts, pts[:30] + np.float32(0.75), pts[:10]])          # near-duplicates and exact duplicates
+    np.array([H, W, 3], np.int32).tofile(os.path.join(d, "klt_dims.bin"))
+    for name, arr in (("klt_f0", f0), ("klt_f1", f1), ("klt_f2", f2)):
+        np.ascontiguousarray(arr, np.uint8).tofile(os.path.join(d, name + ".bin"))
+    pts.tofile(os.path.join(d, "klt_xy.bin"))
+    out = subprocess.run([EXE, d, "klt"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+    def check(tag, nxt, kept, ids):
+        assert np.array_equal(_rd(d, tag + "_q.bin", np.int32), kept)
+        assert np.array_equal(_rd(d, tag + "_t.bin", np.int32), np.arange(len(kept)))
+        assert (_rd(d, tag + "_d.bin", np.float32) == 0).all() and (_rd(d, tag + "_img.bin", np.int32) == -1).all()
+        xy = _rd(d, tag + "_xy.bin", np.float32).reshape(-1, 4)
+        assert np.array_equal(bits(xy[:, :2]), bits(nxt[kept])) and np.array_equal(bits(xy[:, 2:]), bits(nxt[kept]))
+        assert np.array_equal(_rd(d, tag + "_id.bin", np.int32), ids)
+        assert np.array_equal(_rd(d, tag + "_oct.bin", np.int32), ids % 5)
+        assert np.array_equal(_rd(d, tag + "_det.bin", np.float64), 0.25 * ids)
+
+    n01, s01, e01 = K.lk_pyr(f0, f1, pts, min_eig_thr=0.0)
+    k01 = K.perform_tracking(e01, s01, n01, 25.0, 3.0)
+    assert 40 < len(k01) < len(pts)
+    check("klt01", n01, k01, k01)
+    p1 = n01[k01]
+    n12, s12, e12 = K.lk_pyr(f1, f2, p1, min_eig_thr=0.0)
+    k12 = K.perform_tracking(e12, s12, n12, 25.0, 3.0)
+    assert 30 < len(k12) <= len(k01)
+    check("klt12", n12, k12, k01[k12])
+    n02, s02, e02 = K.lk_pyr(f0, f2, pts, win=9, max_level=2, min_eig_thr=1e-3, init=pts, min_eig_err=True)
+    k02 = K.perform_tracking(e02, s02, n02, 1e9, 1.5)
+    assert 30 < len(k02) < len(pts)
+    check("klt02", n02, k02, k02)

@@ -1,0 +1,69 @@
+"""The KLT device routine (putslam_b200/csrc/klt_point.cuh) run on the CPU with its lanes as a loop (tests/klt_emul.py),
+against the cv2 golden vectors and the oracle.  This checks the kernel SOURCE without a GPU; the parity tests of the
+kernel as it runs on the B200 are tests/test_gpu_klt.py."""
+import numpy as np
+
+from conftest import bits
+import klt_emul as E
+
+
+def test_klt_kernel_source_matches_cv2_golden(golden):
+    g = golden["klt_cv2"]
+    a, b, pts = g["a"], g["b"], g["pts"]
+    cases = {"colour": (a, b, {}), "gray": (a[..., 0], b[..., 0], {}), "mineig": (a, b, {"min_eig_err": True}),
+             "initflow": (a, b, {"init": g["init"]})}
+    for spec in (True, False):                       # the compile-time 7 x 7 instantiations and the generic one
+        for name in g["names"]:
+            ia, ib, kw = cases[str(name)]
+            nxt, st, err, levels = E.track(ia, ib, pts, specialised=spec, **kw)
+            assert levels == 4
+            assert np.array_equal(st, g[f"{name}_status"]), name
+            ok = st == 1
+            assert np.array_equal(bits(nxt[ok]), bits(g[f"{name}_next"][ok])), name
+            assert np.array_equal(bits(err[ok]), bits(g[f"{name}_err"][ok])), name
+
+
+def test_klt_kernel_source_matches_oracle_everywhere():
+    """every output of every point, lost ones included (cv2 only defines the tracked ones): hard-edged frames, windows
+    other than the reference's, points outside the frame, pyramid cut short by a small frame, clamped criteria"""
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(71)
+    up = lambda m: np.repeat(np.repeat(m, 2, 0), 2, 1)
+    for win, lev, cn, shape in ((9, 2, 1, (40, 52)), (13, 1, 3, (40, 52)), (7, 3, 3, (38, 50)), (4, 2, 3, (30, 30)), (7, 5, 1, (9, 20))):
+        a = up(rng.integers(0, 2, shape + ((cn,) if cn == 3 else ()), dtype=np.uint8) * 255)
+        b = np.roll(a, 1, 1); b[::3] = np.roll(b[::3], 1, 0)
+        b = ((a.astype(np.int32) + b) // 2).astype(np.uint8)
+        H, W = a.shape[:2]
+        pts = np.stack([rng.uniform(-3, W + 3, 36), rng.uniform(-3, H + 3, 36)], 1).astype(np.float32)
+        for kw in ({}, {"min_eig_err": True, "max_iter": 200, "eps": 0.0}, {"init": pts + np.float32(0.7)}):
+            o_n, o_s, o_e = K.lk_pyr(a, b, pts, win=win, max_level=lev, **kw)
+            e_n, e_s, e_e, _ = E.track(a, b, pts, win=win, max_level=lev, **kw)
+            assert np.array_equal(e_s, o_s), (win, cn, kw.keys())
+            assert np.array_equal(bits(e_n), bits(o_n)), (win, cn, kw.keys())
+            assert np.array_equal(bits(e_e), bits(o_e)), (win, cn, kw.keys())
+            assert 0 < o_s.sum()
+
+
+def test_klt_pyrdown_source_matches_oracle():
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(72)
+    for shape in ((97, 131, 3), (5, 7), (1, 9, 3), (2, 2), (33, 1)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        ref = K.pyr_down(img if img.ndim == 3 else img[..., None])
+        assert np.array_equal(E.pyr_down(img).reshape(ref.shape), ref), shape
+
+
+def test_klt_prune_source_matches_oracle():
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(73)
+    pts = np.array([[10, 10], [10.5, 10], [50, 50], [50, 50.4], [90, 90], [10.2, 10.1]], np.float32)
+    err = np.array([1.0, 2.0, 3.0, 3.0, 9.0, 0.5], np.float32)
+    status = np.array([1, 1, 1, 1, 1, 0], np.uint8)
+    assert E.prune(pts, err, status, 5.0, 1.0).tolist() == [2]
+    for n, d in ((300, 3.0), (500, 0.0), (200, 1e9), (64, 5.0)):
+        xy = rng.uniform(0, 60, (n, 2)).astype(np.float32)
+        xy[1] = xy[0]; xy[3] = xy[2] + np.float32(3.0) * np.array([0.6, 0.8], np.float32)   # coincident / on the threshold
+        e = rng.choice(np.arange(0, 40, dtype=np.float32), n)                               # many ties
+        e[5] = np.nan
+        st = (rng.uniform(size=n) < 0.9).astype(np.uint8)
+        assert np.array_equal(E.prune(xy, e, st, 25.0, d), K.perform_tracking(e, st, xy, 25.0, d)), (n, d)
