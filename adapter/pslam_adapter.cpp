@@ -629,6 +629,78 @@ double MatcherB200::matchCore(cv::Mat prevDescriptors, const std::vector<Eigen::
     return res.inlier_ratio;
 }
 
+double MatcherB200::trackKLTCore(cv::Mat prevRgbImage, cv::Mat rgbImage, const std::vector<cv::Point2f>& prevFeaturesDistorted,
+                                 const std::vector<Eigen::Vector3f>& prevFeatures3D, const std::vector<cv::KeyPoint>& prevKeyPoints,
+                                 const std::vector<double>& prevDetDists, cv::Mat depthImage, double depthImageScale,
+                                 cv::Mat cameraMatrix, cv::Mat distCoeffs, const RANSAC::parameters& ransacParams,
+                                 std::vector<cv::Point2f>& distortedFeatures2D, std::vector<cv::Point2f>& undistortedFeatures2D,
+                                 std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
+                                 std::vector<double>& detDists, std::vector<cv::DMatch>& matches,
+                                 std::vector<cv::DMatch>& inlierMatches, Eigen::Matrix4f& estimatedTransformation) {
+    distortedFeatures2D.clear(); undistortedFeatures2D.clear(); features3D.clear(); keyPoints.clear(); detDists.clear();
+    matches.clear(); inlierMatches.clear();
+    estimatedTransformation = Eigen::Matrix4f::Identity();
+    const int n = (int)prevFeaturesDistorted.size();
+    if (n == 0) return 0.0;                                    // "No features so identity()" (matcher.cpp:146-148)
+    pslam_ctx* c = dev_.ctx();
+    const TrackingParams& tp = tracking_;
+    if (!c) { logError(c, "trackKLT", PSLAM_ERR_NO_DEVICE); return 0.0; }
+    if (prevRgbImage.empty() || rgbImage.empty() || depthImage.empty() || prevRgbImage.rows != rgbImage.rows ||
+        prevRgbImage.cols != rgbImage.cols || prevRgbImage.channels() != rgbImage.channels() || depthImage.rows != rgbImage.rows ||
+        depthImage.cols != rgbImage.cols || (int)prevFeatures3D.size() != n || (int)prevKeyPoints.size() != n ||
+        (int)prevDetDists.size() != n || tp.useInitialFlow > 0) {   // trackKLT passes an empty `features`: no initial flow
+        logError(c, "trackKLT", PSLAM_ERR_ARG);
+        return 0.0;
+    }
+#ifdef PSLAM_USE_REAL_HEADERS
+    const int rowBytes = (int)rgbImage.step[0], prevRowBytes = (int)prevRgbImage.step[0];
+    const int stride = (int)(depthImage.step[0] / sizeof(uint16_t));
+#else
+    const int rowBytes = (int)rgbImage.step0, prevRowBytes = (int)prevRgbImage.step0;
+    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
+#endif
+    if (prevRowBytes != rowBytes) { logError(c, "trackKLT", PSLAM_ERR_ARG); return 0.0; }
+    RANSAC::parameters rp = ransacParams;
+    rp.errorVersion = rp.errorVersionVO;                       // matcher.cpp:196-197
+    pslam_camera cam = cameraFrom(cameraMatrix, &distCoeffs);
+    pslam_ransac_params a = toAbi(rp, cam.fx, cam.fy, cam.cx, cam.cy);
+    std::vector<float> prevXY(2 * (size_t)n), curXY(2 * (size_t)n), err((size_t)n), und(2 * (size_t)n), xyz(3 * (size_t)n);
+    std::vector<double> dd((size_t)n);
+    std::vector<unsigned char> status((size_t)n);
+    std::vector<int> kept((size_t)n), inl((size_t)n);
+    for (int i = 0; i < n; ++i) { prevXY[2 * i] = prevFeaturesDistorted[(size_t)i].x; prevXY[2 * i + 1] = prevFeaturesDistorted[(size_t)i].y; }
+    const bool resident = reuseTracked_ && lastTrackedData_ == prevRgbImage.data && lastTrackedRows_ == prevRgbImage.rows &&
+                          lastTrackedCols_ == prevRgbImage.cols && lastTrackedStep_ == prevRowBytes &&
+                          lastTrackedCh_ == prevRgbImage.channels() && lastTrackedLevels_ >= tp.maxLevels;
+    int nKept = 0;
+    pslam_frame_result res;
+    const int r = pslam_klt_frame(c, resident ? nullptr : prevRgbImage.data, rgbImage.data, rgbImage.cols, rgbImage.rows, rowBytes,
+                                  rgbImage.channels(), prevXY.data(), prevFeatures3D[0].data(), curXY.data(), n, tp.winSize,
+                                  tp.maxLevels, 3, tp.maxIter, tp.eps, tp.trackingErrorType > 0 ? PSLAM_KLT_GET_MIN_EIGENVALS : 0,
+                                  tp.trackingMinEigThreshold, tp.trackingErrorThreshold, tp.minimalReprojDistanceNewTrackingFeatures,
+                                  depthImage.ptr<uint16_t>(0), stride, &cam, distCoeffs.empty() ? 0 : 1, depthImageScale, &a, seed_,
+                                  numHyp_, status.data(), err.data(), kept.data(), &nKept, und.data(), xyz.data(), dd.data(),
+                                  inl.data(), &res);
+    if (r != PSLAM_OK) { logError(c, "trackKLT", r); lastTrackedData_ = nullptr; return 0.0; }
+    lastTrackedData_ = rgbImage.data; lastTrackedRows_ = rgbImage.rows; lastTrackedCols_ = rgbImage.cols; lastTrackedStep_ = rowBytes;
+    lastTrackedCh_ = rgbImage.channels(); lastTrackedLevels_ = tp.maxLevels;
+    distortedFeatures2D.resize((size_t)nKept); undistortedFeatures2D.resize((size_t)nKept); features3D.resize((size_t)nKept);
+    keyPoints.resize((size_t)nKept); detDists.resize((size_t)nKept); matches.reserve((size_t)nKept);
+    for (int j = 0; j < nKept; ++j) {
+        const int i = kept[(size_t)j];
+        distortedFeatures2D[(size_t)j] = cv::Point2f(curXY[2 * i], curXY[2 * i + 1]);
+        undistortedFeatures2D[(size_t)j] = cv::Point2f(und[2 * j], und[2 * j + 1]);
+        features3D[(size_t)j] = Eigen::Vector3f(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]);
+        keyPoints[(size_t)j] = prevKeyPoints[(size_t)i];
+        keyPoints[(size_t)j].pt = distortedFeatures2D[(size_t)j];
+        detDists[(size_t)j] = prevDetDists[(size_t)i];          // performTracking carries the detection distance over (:243)
+        matches.push_back(cv::DMatch(i, j, 0));
+    }
+    for (int k = 0; k < res.n_inliers; ++k) inlierMatches.push_back(matches[(size_t)inl[k]]);
+    std::memcpy(estimatedTransformation.data(), res.T, sizeof(res.T));
+    return nKept > 0 ? res.inlier_ratio : 0.0;
+}
+
 double MatcherB200::matchFeatureLoopClosureCore(cv::Mat descriptors0, const std::vector<Eigen::Vector3f>& points3D0,
                                                 cv::Mat descriptors1, const std::vector<Eigen::Vector3f>& points3D1,
                                                 const RANSAC::parameters& ransacParams, cv::Mat cameraMatrix,

@@ -175,6 +175,20 @@ public:
                      std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
                      std::vector<cv::DMatch>& matches, std::vector<cv::DMatch>& inlierMatches,
                      Eigen::Matrix4f& estimatedTransformation);
+    // The numeric core of Matcher::trackKLT (src/Matcher/matcher.cpp:133-207, lines 151-207; removeTooCloseFeatures off as
+    // shipped) in one device submission (pslam_klt_frame): performTracking(prevRgbImage, rgbImage, prevFeaturesDistorted,
+    // ...) -> removeImageDistortion + keypoints2Dto3D on the survivors -> RANSAC(prevFeatures3D, features3D, matches),
+    // errorVersion = errorVersionVO (:196-197).  Outputs are the vectors trackKLT works on afterwards: the compacted
+    // distorted / undistorted positions, 3-D points, key points and detDists, the DMatch(i, j, 0) list, the inliers and
+    // the transformation.  Returns what trackKLT returns: pointInlierRatio(inlierMatches, matches), 0 without matches.
+    // Uses the parameters of setTrackingParams and the frame reuse of setReuseTrackedFrame.
+    double trackKLTCore(cv::Mat prevRgbImage, cv::Mat rgbImage, const std::vector<cv::Point2f>& prevFeaturesDistorted,
+                        const std::vector<Eigen::Vector3f>& prevFeatures3D, const std::vector<cv::KeyPoint>& prevKeyPoints,
+                        const std::vector<double>& prevDetDists, cv::Mat depthImage, double depthImageScale, cv::Mat cameraMatrix,
+                        cv::Mat distCoeffs, const RANSAC::parameters& ransacParams, std::vector<cv::Point2f>& distortedFeatures2D,
+                        std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
+                        std::vector<cv::KeyPoint>& keyPoints, std::vector<double>& detDists, std::vector<cv::DMatch>& matches,
+                        std::vector<cv::DMatch>& inlierMatches, Eigen::Matrix4f& estimatedTransformation);
     // Matcher::matchFeatureLoopClosure (src/Matcher/matcher.cpp:802-861) after its MapFeature gathering loop (:809-827):
     // descriptors / 3-D points of the two frames -> paired feature indices, transform, and the value it returns
     // (0 for fewer than 10 features, -1.0 for no matches, else pointInlierRatio).

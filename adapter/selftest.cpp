@@ -78,6 +78,37 @@ static int kltSection() {
     cur = prev;                                                     // the guess: no motion
     std::vector<cv::DMatch> m02 = matcher.performTracking(m0, m2, prev, cur, prevKp, curKp, prevDet, curDet);
     dump("klt02", m02);
+    // ---- the fused frame (MatcherB200::trackKLTCore == Matcher::trackKLT lines 151-207), shipped parameters ----
+    std::ifstream probe(g_dir + "/klt_depth1.bin", std::ios::binary);
+    if (probe) {
+        auto z1 = rd<uint16_t>("klt_depth1.bin");
+        auto pxyz = rd<float>("klt_prev_xyz.bin");
+        auto camv = rd<float>("klt_cam.bin");                       // fx fy cx cy
+        float Kf[9] = {camv[0], 0, camv[2], 0, camv[1], camv[3], 0, 0, 1};
+        float Df[5] = {-0.0410f, 0.3286f, 0.0087f, 0.0051f, -0.5643f};
+        cv::Mat K(3, 3, CV_32FC1, Kf), D(1, 5, CV_32FC1, Df);
+        cv::Mat depth1(dims[0], dims[1], CV_16U, z1.data());
+        std::vector<Eigen::Vector3f> prev3D(prev.size());
+        for (size_t i = 0; i < prev3D.size(); ++i) prev3D[i] = Eigen::Vector3f(pxyz[3 * i], pxyz[3 * i + 1], pxyz[3 * i + 2]);
+        RANSAC::parameters rp;
+        rp.verbose = 0; rp.errorVersion = 2; rp.errorVersionVO = 0; rp.errorVersionMap = 0;
+        rp.inlierThresholdEuclidean = 0.04; rp.inlierThresholdReprojection = 2.0; rp.inlierThresholdMahalanobis = 9.0;
+        rp.minimalInlierRatioThreshold = 0.2; rp.minimalNumberOfMatches = 15; rp.usedPairs = 3; rp.iterationCount = 0;
+        MatcherB200 fused(0);
+        fused.setSeed(99);
+        std::vector<cv::Point2f> dist2D, und2D; std::vector<Eigen::Vector3f> f3D; std::vector<cv::DMatch> mF, inF;
+        Eigen::Matrix4f TF;
+        const double ratio = fused.trackKLTCore(m0, m1, prev, prev3D, prevKp, prevDet, depth1, 5000.0, K, D, rp, dist2D, und2D, f3D,
+                                                curKp, curDet, mF, inF, TF);
+        cur = dist2D;
+        dump("kltf", mF);
+        wrMatches("kltf_inliers", inF);
+        std::vector<float> u, x;
+        for (size_t j = 0; j < und2D.size(); ++j) { u.push_back(und2D[j].x); u.push_back(und2D[j].y); x.push_back(f3D[j][0]); x.push_back(f3D[j][1]); x.push_back(f3D[j][2]); }
+        wr("kltf_und.bin", u); wr("kltf_xyz.bin", x);
+        wr("kltf_T.bin", std::vector<float>(TF.data(), TF.data() + 16));
+        wr("kltf_ratio.bin", std::vector<double>{ratio});
+    }
     std::cout << "adapter_selftest klt ok: " << m01.size() << " / " << m12.size() << " / " << m02.size() << " tracked" << std::endl;
     return 0;
 }

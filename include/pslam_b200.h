@@ -386,6 +386,27 @@ PSLAM_API int pslam_klt_perform_tracking(pslam_ctx* ctx, const uint8_t* prev_ima
                                          double min_eig_threshold, double error_threshold, double min_distance,
                                          uint8_t* status, float* err, int* kept_idx_out, int* n_kept_out);
 
+/* One tracking frame of the VO_TRACKING mode == the data-parallel part of Matcher::trackKLT (src/Matcher/matcher.cpp:
+ * 151-207) in one submission: performTracking (as pslam_klt_perform_tracking), RGBD::removeImageDistortion and
+ * RGBD::keypoints2Dto3D on the survivors (as pslam_backproject; undistort = 0 skips the first), then
+ * RANSAC::estimateTransformation(prevFeatures3D, features3D, matches, inliers) with matches = DMatch(kept[j], j, 0)
+ * (as pslam_ransac_estimate).  The survivors' list, positions and 3-D points stay in HBM between the steps.
+ *   prev_xyz            n x 3, the previous frame's 3-D features (prevFeatures3D), row i belongs to prev_xy row i
+ *   kept_*_out          capacity n rows; row j belongs to survivor j = feature kept_idx_out[j]: undistorted position
+ *                       (nullable), 3-D point, detection distance |p| (nullable)
+ *   inlier_idx_out      capacity n: indices j into the survivor list
+ *   result              n_matches = survivors, T = estimated transformation (column-major, identity when RANSAC rejects),
+ *                       inlier_ratio = RANSAC::pointInlierRatio(inliers, matches) (0 without survivors), as trackKLT returns
+ * Other arguments as pslam_klt_perform_tracking / pslam_frame_to_frame. */
+PSLAM_API int pslam_klt_frame(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H, int row_bytes,
+                              int channels, const float* prev_xy, const float* prev_xyz, float* cur_xy, int n, int win,
+                              int max_level, int criteria_type, int max_iter, double eps, int flags,
+                              double min_eig_threshold, double error_threshold, double min_distance, const uint16_t* depth,
+                              int depth_row_stride, const pslam_camera* cam, int undistort, double depth_scale,
+                              const pslam_ransac_params* params, uint64_t seed, int num_hyp, uint8_t* status, float* err,
+                              int* kept_idx_out, int* n_kept_out, float* kept_uv_undist_out, float* kept_xyz_out,
+                              double* kept_det_dist_out, int* inlier_idx_out, pslam_frame_result* result);
+
 /* ---- loop-closure sweep: query frame vs every keyframe of the map --------------------------
  * Generalises Matcher::matchFeatureLoopClosure's performMatching step (src/Matcher/matcher.cpp:802-861,
  * :835) from one FABMAP-proposed pair to all keyframes: score(k) = number of mutual-NN matches between

@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_klt_track", "pslam_klt_perform_tracking", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_klt_track", "pslam_klt_perform_tracking", "pslam_klt_frame", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -278,6 +278,42 @@ class Context:
         self._ck(self.lib.pslam_klt_perform_tracking(*common, C.c_double(prune[0]), C.c_double(prune[1]), _p(st, C.c_uint8),
                                                      _p(err, C.c_float), _p(kept, C.c_int), C.byref(m)))
         return dict(xy=xy[:n].copy(), status=st[:n].copy(), err=err[:n].copy(), kept=kept[:m.value].copy())
+
+    def klt_frame(self, prev_image, cur_image, prev_xy, prev_xyz, depth, cam=None, undistort=False, depth_scale=5000.0,
+                  params=None, seed=0, num_hyp=0, win=7, max_level=3, max_iter=30, eps=0.01, criteria_type=3,
+                  min_eig_err=False, min_eig_threshold=0.0, error_threshold=25.0, min_distance=3.0, init_xy=None):
+        """the data-parallel part of Matcher::trackKLT in one submission: track -> threshold / too-close rule ->
+        undistort + back-project the survivors -> RANSAC against prev_xyz.  Defaults = the reference's shipped parameters."""
+        cur = np.ascontiguousarray(cur_image, np.uint8)
+        prev = None if prev_image is None else np.ascontiguousarray(prev_image, np.uint8)
+        ch = 3 if cur.ndim == 3 else 1
+        H, W = cur.shape[:2]
+        depth = np.ascontiguousarray(depth, np.uint16)
+        if depth.shape != (H, W):
+            raise ValueError("klt_frame: depth image and frame differ in size")
+        p = _arr(prev_xy, np.float32, 2); px = _arr(prev_xyz, np.float32, 3); n = len(p)
+        cam = cam or make_camera(); params = params or default_ransac_params()
+        flags = (self.KLT_GET_MIN_EIGENVALS if min_eig_err else 0) | (self.KLT_USE_INITIAL_FLOW if init_xy is not None else 0)
+        m1 = max(n, 1)
+        xy = np.zeros((m1, 2), np.float32)
+        if init_xy is not None:
+            xy[:n] = _arr(init_xy, np.float32, 2)
+        st = np.zeros(m1, np.uint8); err = np.zeros(m1, np.float32); kept = np.zeros(m1, np.int32); m = C.c_int(0)
+        und = np.zeros((m1, 2), np.float32); xyz = np.zeros((m1, 3), np.float32); dd = np.zeros(m1, np.float64)
+        inl = np.zeros(m1, np.int32); res = FrameResult()
+        self._ck(self.lib.pslam_klt_frame(self.h, _p(prev, C.c_uint8), _p(cur, C.c_uint8), W, H, ch * W, ch, _p(p, C.c_float),
+                                          _p(px, C.c_float), _p(xy, C.c_float), n, int(win), int(max_level), int(criteria_type),
+                                          int(max_iter), C.c_double(eps), flags, C.c_double(min_eig_threshold),
+                                          C.c_double(error_threshold), C.c_double(min_distance), _p(depth, C.c_uint16), W,
+                                          C.byref(cam), int(bool(undistort)), C.c_double(depth_scale), C.byref(params),
+                                          C.c_uint64(seed), int(num_hyp), _p(st, C.c_uint8), _p(err, C.c_float),
+                                          _p(kept, C.c_int), C.byref(m), _p(und, C.c_float), _p(xyz, C.c_float),
+                                          _p(dd, C.c_double), _p(inl, C.c_int), C.byref(res)))
+        k = m.value
+        return dict(xy=xy[:n].copy(), status=st[:n].copy(), err=err[:n].copy(), kept=kept[:k].copy(), uv_undist=und[:k].copy(),
+                    xyz=xyz[:k].copy(), det_dist=dd[:k].copy(), inliers=inl[:res.n_inliers].copy(),
+                    T=np.array(res.T, np.float32).reshape(4, 4).T.copy(), best_ratio=res.best_ratio,
+                    inlier_ratio=res.inlier_ratio, hyp_used=res.hyp_used, n_filtered=res.n_filtered, n_matches=res.n_matches)
 
     # ---- stage 2 ----
     def match_bf_mutual(self, query, train):

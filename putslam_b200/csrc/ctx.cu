@@ -1445,13 +1445,28 @@ static void pack_rows(uint8_t* dst, const uint8_t* src, size_t row, int H, int r
     if ((size_t)row_bytes == row) memcpy(dst, src, row * H);
     else for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * row, src + (size_t)y * row_bytes, row);
 }
+// the steps Matcher::trackKLT runs on performTracking's survivors (matcher.cpp:160-207), for pslam_klt_frame
+struct KltFrameArgs {
+    const float* prev_xyz; const uint16_t* depth; int depth_stride; const pslam_camera* cam; int undistort; double depth_scale;
+    const pslam_ransac_params* rparams; uint64_t seed; int num_hyp;
+    float* uv_und_out; float* xyz_out; double* det_dist_out; int* inlier_idx_out; pslam_frame_result* result;
+};
 static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H,
                    int row_bytes, int channels, const float* prev_xy, float* cur_xy, int n, int win, int max_level,
                    int criteria_type, int max_iter, double eps, int flags, double min_eig_threshold, bool prune,
                    double error_threshold, double min_distance, uint8_t* status, float* err, int* kept_idx_out,
-                   int* n_kept_out) {
+                   int* n_kept_out, const KltFrameArgs* fr = nullptr) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (n_kept_out) *n_kept_out = 0;
+    RansacDeviceParams rp = {};
+    if (fr) {
+        if (!fr->result) return fail(ctx, PSLAM_ERR_ARG, "%s: bad argument", who);
+        memset(fr->result, 0, sizeof(*fr->result));
+        for (int i = 0; i < 16; ++i) fr->result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
+        if (!fr->cam || !fr->depth || fr->depth_stride < W || (n > 0 && (!fr->prev_xyz || !fr->xyz_out || !fr->inlier_idx_out)))
+            return fail(ctx, PSLAM_ERR_ARG, "%s: bad argument", who);
+        TRY(make_ransac_params(ctx, fr->rparams, fr->seed, fr->num_hyp, rp));
+    }
     if (!cur_image || W <= 0 || H <= 0 || (channels != 1 && channels != 3) || row_bytes < channels * W || n < 0 ||
         (n > 0 && (!prev_xy || !cur_xy || !status || !err)) || (prune && (!n_kept_out || (n > 0 && !kept_idx_out))) ||
         (flags & ~(PSLAM_KLT_USE_INITIAL_FLOW | PSLAM_KLT_GET_MIN_EIGENVALS)) || (criteria_type & ~3))
@@ -1473,8 +1488,20 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
     const size_t o_img_j = in.take(img_bytes), o_img_i = in.take(prev_image ? img_bytes : 0);
     const size_t o_prev = in.take(8 * (size_t)n), o_init = in.take(8 * (size_t)n);
     const size_t o_xy = out.take(8 * (size_t)n), o_err = out.take(4 * (size_t)n), o_st = out.take((size_t)n), o_keep = out.take((size_t)n);
+    // fused frame: previous 3-D points and the depth image in; survivors' match list, compacted positions, their
+    // undistorted / back-projected form and the RANSAC result out
+    const int cap = n > 0 ? n : 1;
+    const size_t depth_bytes = fr ? sizeof(uint16_t) * (size_t)H * fr->depth_stride : 0;
+    const size_t o_pxyz = in.take(fr ? 12 * (size_t)n : 0), o_depth = in.take(depth_bytes);
+    const size_t o_m = out.take(fr ? sizeof(int) * (1 + 3 * (size_t)cap) : 0), o_cxy = out.take(fr ? 8 * (size_t)cap : 0);
+    const size_t o_und = out.take(fr ? 8 * (size_t)cap : 0), o_xyz = out.take(fr ? 12 * (size_t)cap : 0);
+    const size_t o_dd = out.take(fr ? 8 * (size_t)cap : 0), o_res = out.take(fr ? sizeof(int) * ransac_result_ints(cap) : 0);
+    Arena work;
+    RansacLayout RL = {};
+    if (fr) RL = plan_ransac(work, cap, rp);
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_host(ctx, ctx->h_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_in, in.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    if (fr) TRY(ensure_dev(ctx, ctx->d_work, work.off));
     ctx->klt_cur = -1;                                            // until this call has succeeded
     TRY(ensure_dev(ctx, ctx->d_klt_pyr[0], full.bytes)); TRY(ensure_dev(ctx, ctx->d_klt_pyr[1], full.bytes));
     uint8_t* h = ctx->h_in.p;
@@ -1491,6 +1518,11 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
     if (prev_image) CK(cudaMemcpyAsync(pyrI, h + o_img_i, img_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (n > 0) CK(cudaMemcpyAsync(ctx->d_in.p + o_prev, h + o_prev, (init ? o_init + 8 * (size_t)n : o_prev + 8 * (size_t)n) - o_prev,
                                   cudaMemcpyHostToDevice, ctx->stream));
+    if (fr && n > 0) {
+        memcpy(h + o_pxyz, fr->prev_xyz, 12 * (size_t)n);
+        memcpy(h + o_depth, fr->depth, depth_bytes);
+        CK(cudaMemcpyAsync(ctx->d_in.p + o_pxyz, h + o_pxyz, o_depth + depth_bytes - o_pxyz, cudaMemcpyHostToDevice, ctx->stream));
+    }
     int l = 0;
     CK(launch_klt_pyramid(prev_image ? pyrI : nullptr, pyrJ, plan, channels, ctx->stream, &l));
     float* d_xy = (float*)(ctx->d_out.p + o_xy);
@@ -1512,6 +1544,19 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
         if (prune)
             CK(launch_klt_prune(d_xy, (const float*)(ctx->d_out.p + o_err), ctx->d_out.p + o_st, n, error_threshold,
                                 sq_threshold_d(min_distance), ctx->d_out.p + o_keep, ctx->stream, &l));
+        if (fr) {
+            int* mout = (int*)(ctx->d_out.p + o_m);
+            float* cxy = (float*)(ctx->d_out.p + o_cxy);
+            float* xyz = (float*)(ctx->d_out.p + o_xyz);
+            CK(launch_klt_compact(ctx->d_out.p + o_keep, d_xy, n, cap, mout, cxy, ctx->stream, &l));
+            CK(launch_backproject(cxy, n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H, fr->depth_stride, *fr->cam, fr->undistort,
+                                  fr->depth_scale, (float*)(ctx->d_out.p + o_und), xyz, (double*)(ctx->d_out.p + o_dd), nullptr,
+                                  nullptr, ctx->stream, &l));
+            RansacWorkspace ws = bind_ransac(RL, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+            CK(launch_ransac((const float*)(ctx->d_in.p + o_pxyz), xyz, mout + 1, mout + 1 + cap, mout, 0, rp, ws, ctx->sm_count,
+                             ctx->stream, &l));
+            ctx->d_last_counts = ws.counts; ctx->last_H = ws.h_cap;
+        }
         CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, prune ? out.off : o_keep, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->launches += l;
@@ -1529,6 +1574,21 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
             int m = 0;
             for (int i = 0; i < n; ++i) if (keep[i]) kept_idx_out[m++] = i;
             *n_kept_out = m;
+        }
+        if (fr) {
+            const int* mo = (const int*)(ctx->h_out.p + o_m);
+            const int m = mo[0];
+            if (m != *n_kept_out || memcmp(mo + 1, kept_idx_out, 4 * (size_t)m) != 0)
+                return fail(ctx, PSLAM_ERR_CUDA, "%s: device compaction disagrees with the keep flags", who);
+            pslam_frame_result* R = fr->result;
+            R->n_matches = m;
+            if (fr->uv_und_out) memcpy(fr->uv_und_out, ctx->h_out.p + o_und, 8 * (size_t)m);
+            memcpy(fr->xyz_out, ctx->h_out.p + o_xyz, 12 * (size_t)m);
+            if (fr->det_dist_out) memcpy(fr->det_dist_out, ctx->h_out.p + o_dd, 8 * (size_t)m);
+            unpack_ransac_result((const int*)(ctx->h_out.p + o_res), R->T, fr->inlier_idx_out, &R->n_inliers, &R->best_ratio,
+                                 &R->hyp_used, &R->n_filtered);
+            // pointInlierRatio over trainIdx (RANSAC.h:56-66): survivor j has trainIdx j, every one distinct
+            R->inlier_ratio = m > 0 ? (double)R->n_inliers / (double)m : 0.0;
         }
     }
     return PSLAM_OK;
@@ -1549,6 +1609,20 @@ int pslam_klt_perform_tracking(pslam_ctx* ctx, const uint8_t* prev_image, const 
     return klt_run(ctx, "pslam_klt_perform_tracking", prev_image, cur_image, W, H, row_bytes, channels, prev_xy, cur_xy, n, win,
                    max_level, criteria_type, max_iter, eps, flags, min_eig_threshold, true, error_threshold, min_distance, status,
                    err, kept_idx_out, n_kept_out);
+}
+
+int pslam_klt_frame(pslam_ctx* ctx, const uint8_t* prev_image, const uint8_t* cur_image, int W, int H, int row_bytes, int channels,
+                    const float* prev_xy, const float* prev_xyz, float* cur_xy, int n, int win, int max_level, int criteria_type,
+                    int max_iter, double eps, int flags, double min_eig_threshold, double error_threshold, double min_distance,
+                    const uint16_t* depth, int depth_row_stride, const pslam_camera* cam, int undistort, double depth_scale,
+                    const pslam_ransac_params* params, uint64_t seed, int num_hyp, uint8_t* status, float* err,
+                    int* kept_idx_out, int* n_kept_out, float* kept_uv_undist_out, float* kept_xyz_out,
+                    double* kept_det_dist_out, int* inlier_idx_out, pslam_frame_result* result) {
+    KltFrameArgs fr = {prev_xyz, depth, depth_row_stride, cam, undistort, depth_scale, params, seed, num_hyp,
+                       kept_uv_undist_out, kept_xyz_out, kept_det_dist_out, inlier_idx_out, result};
+    return klt_run(ctx, "pslam_klt_frame", prev_image, cur_image, W, H, row_bytes, channels, prev_xy, cur_xy, n, win, max_level,
+                   criteria_type, max_iter, eps, flags, min_eig_threshold, true, error_threshold, min_distance, status, err,
+                   kept_idx_out, n_kept_out, &fr);
 }
 
 // ---- resident feature map -------------------------------------------------------------------------

@@ -114,4 +114,52 @@ cudaError_t launch_klt_prune(const float* d_xy, const float* d_err, const uint8_
     return e;
 }
 
+// Ordered compaction of the survivors for the fused tracking frame (pslam_klt_frame): survivor j is feature kept[j].
+// mout = {m, queryIdx[cap] = kept[j], trainIdx[cap] = j, distance[cap] = 0}: the DMatch(i, j, 0) list performTracking
+// returns (matcherOpenCV.cpp:269-277), in the layout the RANSAC launcher reads match lists from; cxy[j] = xy[kept[j]]
+// (the compacted `features`), zero beyond m so that the back-projection launched over all cap slots reads defined values.
+// One CTA: n is a frame's feature count (a few thousand at most) and the order is the point.
+__global__ void __launch_bounds__(1024)
+klt_compact_kernel(const uint8_t* __restrict__ keep, const float2* __restrict__ xy, int n, int cap, int* __restrict__ mout,
+                   float2* __restrict__ cxy) {
+    __shared__ int warp_count[32];
+    __shared__ int running;
+    chain_begin();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const bool k = i < n && keep[i] != 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        int before = running;
+        for (int w = 0; w < warp; ++w) before += warp_count[w];
+        if (k) {
+            const int j = before + __popc(ballot & ((1u << lane) - 1u));
+            mout[1 + j] = i; mout[1 + cap + j] = j; mout[1 + 2 * cap + j] = 0;
+            cxy[j] = xy[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = running;
+            for (int w = 0; w < 32; ++w) t += warp_count[w];
+            running = t;
+        }
+        __syncthreads();
+    }
+    const int m = running;
+    if (tid == 0) mout[0] = m;
+    for (int j = m + tid; j < cap; j += 1024) cxy[j] = make_float2(0.f, 0.f);
+}
+
+cudaError_t launch_klt_compact(const uint8_t* d_keep, const float* d_xy, int n, int cap, int* d_mout, float* d_cxy,
+                               cudaStream_t st, int* launches) {
+    cudaError_t e = launch_chained(klt_compact_kernel, dim3(1), dim3(1024), 0, st, d_keep, (const float2*)d_xy, n, cap, d_mout,
+                                   (float2*)d_cxy);
+    if (e == cudaSuccess) ++*launches;
+    return e;
+}
+
 }  // namespace pslam

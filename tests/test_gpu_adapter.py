@@ -14,6 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "adapter", "adapter_selftest")
 
 
+def oracle_mod():
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
 def _rd(d, name, dt):
     return np.fromfile(os.path.join(d, name), dtype=dt)
 
@@ -159,6 +165,16 @@ def test_adapter_perform_tracking(tmp_path, golden):
     for name, arr in (("klt_f0", f0), ("klt_f1", f1), ("klt_f2", f2)):
         np.ascontiguousarray(arr, np.uint8).tofile(os.path.join(d, name + ".bin"))
     pts.tofile(os.path.join(d, "klt_xy.bin"))
+    # inputs of the fused frame (trackKLTCore): depth of frame 1, 3-D points of frame 0, intrinsics of a 200 x 150 camera
+    from putslam_b200 import synth
+    O = oracle_mod()
+    drng = np.random.default_rng(3)
+    fx, fy, cx, cy = 160.0, 160.0, 99.5, 74.5
+    depth0 = (9000 + drng.integers(-3, 4, (H, W))).astype(np.uint16)
+    depth1 = (9000 + drng.integers(-3, 4, (H, W))).astype(np.uint16)
+    prev_xyz, _ = O.backproject(O.undistort(pts, fx, fy, cx, cy, synth.DIST), depth0, fx, fy, cx, cy, 5000.0)
+    depth1.tofile(os.path.join(d, "klt_depth1.bin")); prev_xyz.tofile(os.path.join(d, "klt_prev_xyz.bin"))
+    np.array([fx, fy, cx, cy], np.float32).tofile(os.path.join(d, "klt_cam.bin"))
     out = subprocess.run([EXE, d, "klt"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
 
@@ -185,3 +201,14 @@ def test_adapter_perform_tracking(tmp_path, golden):
     k02 = K.perform_tracking(e02, s02, n02, 1e9, 1.5)
     assert 30 < len(k02) < len(pts)
     check("klt02", n02, k02, k02)
+    # fused frame 0 -> 1: the same survivors, then undistort / back-project / RANSAC as the oracle composes them
+    check("kltf", n01, k01, k01)
+    und1 = O.undistort(n01[k01], fx, fy, cx, cy, synth.DIST)
+    xyz1, _ = O.backproject(und1, depth1, fx, fy, cx, cy, 5000.0)
+    assert np.array_equal(bits(_rd(d, "kltf_und.bin", np.float32)), bits(np.ascontiguousarray(und1, np.float32).ravel()))
+    assert np.array_equal(bits(_rd(d, "kltf_xyz.bin", np.float32)), bits(xyz1.ravel()))
+    ref = O.ransac(prev_xyz, xyz1, k01.astype(np.int32), np.arange(len(k01), dtype=np.int32), seed=99)
+    assert np.array_equal(_rd(d, "kltf_inliers_q.bin", np.int32), k01[ref["inliers"]])
+    assert np.array_equal(_rd(d, "kltf_inliers_t.bin", np.int32), ref["inliers"])
+    assert np.abs(_rd(d, "kltf_T.bin", np.float32).reshape(4, 4).T - ref["T"]).max() <= 1e-5
+    assert _rd(d, "kltf_ratio.bin", np.float64)[0] == len(ref["inliers"]) / len(k01)

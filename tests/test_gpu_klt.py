@@ -136,3 +136,67 @@ def test_klt_argument_errors(ctx):
         assert not r["status"].any()
     finally:
         fresh.close()
+
+
+def _klt_frame_case(rng, n=260, H=240, W=320):
+    import cv2
+    g = cv2.GaussianBlur(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), (0, 0), 1.6)
+    f0 = cv2.normalize(g, None, 0, 255, cv2.NORM_MINMAX)
+    M = np.float32([[1, 0, 2.3], [0, 1, -1.4]])                     # camera slides parallel to a wall 2 m away
+    f1 = cv2.warpAffine(f0, M, (W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    f1 = np.clip(f1.astype(np.int32) + rng.integers(-2, 3, f1.shape), 0, 255).astype(np.uint8)
+    depth0 = (10000 + rng.integers(-3, 4, (H, W))).astype(np.uint16)
+    depth1 = (10000 + rng.integers(-3, 4, (H, W))).astype(np.uint16)
+    depth1[::37, ::11] = 0                                          # holes: invalid depth is filtered inside RANSAC
+    pts = np.stack([rng.uniform(6, W - 7, n), rng.uniform(6, H - 7, n)], 1).astype(np.float32)
+    pts[200:230] = pts[:30] + np.float32(0.6)                       # too close to others
+    return f0, f1, depth0, depth1, pts
+
+
+@pytest.mark.parametrize("undistort", [False, True])
+def test_klt_frame_vs_oracle_chain(ctx, O, undistort):
+    """pslam_klt_frame == performTracking -> removeImageDistortion -> keypoints2Dto3D -> RANSAC::estimateTransformation
+    composed from the oracle's restatements of the reference functions (Matcher::trackKLT, matcher.cpp:151-207)"""
+    from oracle import klt_oracle as K
+    from putslam_b200 import synth
+    rng = np.random.default_rng(31 + int(undistort))
+    f0, f1, depth0, depth1, pts = _klt_frame_case(rng)
+    fx, fy, cx, cy = synth.FX / 2, synth.FY / 2, synth.CX / 2, synth.CY / 2
+    from putslam_b200 import api
+    cam = api.make_camera(fx, fy, cx, cy)
+    prm = api.default_ransac_params()
+    prm.fx, prm.fy, prm.cx, prm.cy = fx, fy, cx, cy
+    und0 = O.undistort(pts, fx, fy, cx, cy, synth.DIST) if undistort else pts
+    prev_xyz, _ = O.backproject(und0, depth0, fx, fy, cx, cy, 5000.0)
+    prev_xyz[::3] += rng.normal(0, 0.3, prev_xyz[::3].shape).astype(np.float32)   # a third of the 3-D points are outliers
+    r = ctx.klt_frame(f0, f1, pts, prev_xyz, depth1, cam=cam, undistort=undistort, params=prm, seed=5)
+    # the oracle chain
+    nxt, st, err = K.lk_pyr(f0, f1, pts, min_eig_thr=0.0)
+    kept = K.perform_tracking(err, st, nxt, 25.0, 3.0)
+    assert 150 < len(kept) < len(pts)
+    assert np.array_equal(r["status"], st) and np.array_equal(bits(r["xy"]), bits(nxt)) and np.array_equal(bits(r["err"]), bits(err))
+    assert np.array_equal(r["kept"], kept) and r["n_matches"] == len(kept)
+    und1 = O.undistort(nxt[kept], fx, fy, cx, cy, synth.DIST) if undistort else nxt[kept]
+    xyz1, dd = O.backproject(und1, depth1, fx, fy, cx, cy, 5000.0)
+    assert np.array_equal(bits(r["uv_undist"]), bits(np.ascontiguousarray(und1, np.float32)))
+    assert np.array_equal(bits(r["xyz"]), bits(xyz1)) and np.array_equal(bits(r["det_dist"]), bits(dd))
+    ref = O.ransac(prev_xyz, xyz1, kept.astype(np.int32), np.arange(len(kept), dtype=np.int32), params=None, seed=5)
+    assert np.array_equal(r["inliers"], ref["inliers"]) and 100 < len(ref["inliers"]) < 0.8 * len(kept)
+    assert np.abs(r["T"] - ref["T"]).max() <= 1e-5                  # 1e-5 m / 1e-5 rad (north_star)
+    assert r["hyp_used"] == ref["hyp_used"] and r["best_ratio"] == ref["best_ratio"]
+    assert r["inlier_ratio"] == len(ref["inliers"]) / len(kept)
+    # the separate calls give the same survivors
+    sep = ctx.klt_track(f0, f1, pts, min_eig_threshold=0.0, prune=(25.0, 3.0))
+    assert np.array_equal(sep["kept"], r["kept"])
+
+
+def test_klt_frame_degenerate(ctx, O):
+    """no features; and a flat frame where nothing is tracked: identity, no inliers, ratio 0 (trackKLT's own values)"""
+    a = np.full((60, 80, 3), 90, np.uint8)
+    depth = np.full((60, 80), 10000, np.uint16)
+    r = ctx.klt_frame(a, a, np.zeros((0, 2), np.float32), np.zeros((0, 3), np.float32), depth)
+    assert len(r["kept"]) == 0 and np.array_equal(r["T"], np.eye(4, dtype=np.float32)) and r["inlier_ratio"] == 0.0
+    pts = np.array([[10, 10], [40, 30], [70, 50]], np.float32)
+    r = ctx.klt_frame(a, a, pts, np.ones((3, 3), np.float32), depth, min_eig_threshold=1e-4)
+    assert not r["status"].any() and len(r["kept"]) == 0 and len(r["inliers"]) == 0
+    assert np.array_equal(r["T"], np.eye(4, dtype=np.float32)) and r["inlier_ratio"] == 0.0
