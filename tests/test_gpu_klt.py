@@ -87,10 +87,11 @@ def test_klt_track_full_frame_live_cv2_and_resident_previous_frame(ctx):
     check(f1, f2, p1, r2)
     # row stride: a view into a wider buffer must be packed by the library
     wide = np.zeros((480, 700, 3), np.uint8); wide[:, :640] = f1
+    wide0 = np.zeros((480, 700, 3), np.uint8); wide0[:, :640] = f0            # one row stride serves both frames
     from putslam_b200 import api
     import ctypes as C
     xy = np.zeros((1000, 2), np.float32); st = np.zeros(1000, np.uint8); err = np.zeros(1000, np.float32)
-    rc = ctx.lib.pslam_klt_track(ctx.h, api._p(f0, C.c_uint8), api._p(wide, C.c_uint8), 640, 480, 2100, 3, api._p(pts, C.c_float),
+    rc = ctx.lib.pslam_klt_track(ctx.h, api._p(wide0, C.c_uint8), api._p(wide, C.c_uint8), 640, 480, 2100, 3, api._p(pts, C.c_float),
                                  api._p(xy, C.c_float), 1000, 7, 3, 3, 30, C.c_double(0.01), 0, C.c_double(0.0),
                                  api._p(st, C.c_uint8), api._p(err, C.c_float))
     assert rc == 0 and np.array_equal(st, r["status"]) and np.array_equal(bits(xy), bits(r["xy"]))
