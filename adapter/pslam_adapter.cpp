@@ -757,6 +757,41 @@ Mat34& KabschEst::computeTransformation(const Eigen::MatrixXd& setA, const Eigen
     return transformation;
 }
 
+const Mat66& TransformEst::uncertaintyImpl(const Eigen::MatrixXd& setA, std::vector<Mat33>& ua, const Eigen::MatrixXd& setB,
+                                           std::vector<Mat33>& ub, Mat34& T, int parametrization) {
+    uncertainty.setZero();
+    const int n = (int)setA.rows();
+    pslam_ctx* c = defaultDevice().ctx();
+    if (n == 0 || (int)setB.rows() != n || (int)ua.size() != n || (int)ub.size() != n) {
+        logError(c, "TransformEst::computeUncertainty", PSLAM_ERR_ARG);
+        return uncertainty;
+    }
+    std::vector<double> A(3 * (size_t)n), B(3 * (size_t)n), CA(9 * (size_t)n), CB(9 * (size_t)n);
+    for (int r = 0; r < n; ++r) {
+        for (int k = 0; k < 3; ++k) { A[3 * r + k] = setA(r, k); B[3 * r + k] = setB(r, k); }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) { CA[9 * r + 3 * i + j] = ua[(size_t)r](i, j); CB[9 * r + 3 * i + j] = ub[(size_t)r](i, j); }
+    }
+    int off[2] = {0, n}, ok = 0;
+    double T12[12];
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 3; ++row) T12[3 * col + row] = T.m[4 * col + row];
+    const int r = c ? pslam_transform_uncertainty_batch(c, A.data(), B.data(), CA.data(), CB.data(), off, T12, 1, parametrization,
+                                                        uncertainty.m, &ok)
+                    : PSLAM_ERR_NO_DEVICE;
+    if (r != PSLAM_OK) { logError(c, "TransformEst::computeUncertainty", r); uncertainty.setZero(); }
+    else if (!ok) std::cerr << "putslam_b200: TransformEst::computeUncertainty: singular Hessian" << std::endl;
+    return uncertainty;
+}
+const Mat66& TransformEst::computeUncertainty(const Eigen::MatrixXd& setA, std::vector<Mat33>& setAUncertainty,
+                                              const Eigen::MatrixXd& setB, std::vector<Mat33>& setBUncertainty, Mat34& T) {
+    return uncertaintyImpl(setA, setAUncertainty, setB, setBUncertainty, T, PSLAM_UNCERTAINTY_EULER);
+}
+const Mat66& TransformEst::computeUncertaintyG2O(const Eigen::MatrixXd& setA, std::vector<Mat33>& setAUncertainty,
+                                                 const Eigen::MatrixXd& setB, std::vector<Mat33>& setBUncertainty, Mat34& T) {
+    return uncertaintyImpl(setA, setAUncertainty, setB, setBUncertainty, T, PSLAM_UNCERTAINTY_QUATERNION);
+}
+
 static std::unique_ptr<KabschEst> kabsch;
 TransformEst* createKabschEstimator(void) {
     kabsch.reset(new KabschEst());

@@ -243,13 +243,37 @@ struct Mat34 {
     void setIdentity() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0; }
     double operator()(int r, int c) const { return m[4 * c + r]; }
 };
+struct Mat33 {   // Eigen::Matrix<double,3,3>, column-major
+    double m[9];
+    Mat33() { for (int i = 0; i < 9; ++i) m[i] = 0.0; }
+    double& operator()(int r, int c) { return m[3 * c + r]; }
+    double operator()(int r, int c) const { return m[3 * c + r]; }
+};
+struct Mat66 {   // Eigen::Matrix<double,6,6>, column-major
+    double m[36];
+    Mat66() { setZero(); }
+    void setZero() { for (int i = 0; i < 36; ++i) m[i] = 0.0; }
+    double operator()(int r, int c) const { return m[6 * c + r]; }
+};
 class TransformEst {
 public:
     virtual const std::string& getName() const = 0;
     virtual Mat34& computeTransformation(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB) = 0;
     virtual ~TransformEst() {}
+    // transformEst.h:29-144: 6 x 6 covariance of (x, y, z, roll, pitch, yaw) of `transformation` (setA ~ R setB + t) from the
+    // per-point covariances; returns a reference to the member, like the reference.  Zero matrix + message on std::cerr when
+    // the device call fails or the Hessian is singular.
+    virtual const Mat66& computeUncertainty(const Eigen::MatrixXd& setA, std::vector<Mat33>& setAUncertainty,
+                                            const Eigen::MatrixXd& setB, std::vector<Mat33>& setBUncertainty, Mat34& transformation);
+    // transformEst.h:147-272: the same over (x, y, z, qx, qy, qz)
+    virtual const Mat66& computeUncertaintyG2O(const Eigen::MatrixXd& setA, std::vector<Mat33>& setAUncertainty,
+                                               const Eigen::MatrixXd& setB, std::vector<Mat33>& setBUncertainty, Mat34& transformation);
 protected:
     Mat34 transformation;
+    Mat66 uncertainty;
+private:
+    const Mat66& uncertaintyImpl(const Eigen::MatrixXd& setA, std::vector<Mat33>& ua, const Eigen::MatrixXd& setB,
+                                 std::vector<Mat33>& ub, Mat34& T, int parametrization);
 };
 class KabschEst : public TransformEst {
 public:

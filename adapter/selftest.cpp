@@ -113,10 +113,34 @@ static int kltSection() {
     return 0;
 }
 
+// ---- demoKabsch.cpp:1020-1028: trans = est->computeTransformation(setA, setB); est->computeUncertainty(...) ----
+static int uncSection() {
+    auto A = rd<double>("kabsch_A.bin"), B = rd<double>("kabsch_B.bin");   // row-major n x 3, B ~ R A + t
+    auto ca = rd<double>("unc_CA.bin"), cb = rd<double>("unc_CB.bin");     // n x 3 x 3 row-major
+    const long n = (long)(A.size() / 3);
+    Eigen::MatrixXd setA(n, 3), setB(n, 3);
+    for (long r = 0; r < n; ++r) for (int c = 0; c < 3; ++c) { setA(r, c) = A[3 * r + c]; setB(r, c) = B[3 * r + c]; }
+    std::vector<Mat33> ua((size_t)n), ub((size_t)n);
+    for (long r = 0; r < n; ++r)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) { ua[(size_t)r](i, j) = ca[9 * r + 3 * i + j]; ub[(size_t)r](i, j) = cb[9 * r + 3 * i + j]; }
+    TransformEst* est = createKabschEstimator();
+    Mat34 trans = est->computeTransformation(setA, setB);
+    wr("unc_T.bin", std::vector<double>(trans.m, trans.m + 16));
+    // the estimator maps A onto B (B ~ R A + t), so B plays the role of computeUncertainty's setA
+    const Mat66& u1 = est->computeUncertainty(setB, ub, setA, ua, trans);
+    wr("unc_euler.bin", std::vector<double>(u1.m, u1.m + 36));
+    const Mat66& u2 = est->computeUncertaintyG2O(setB, ub, setA, ua, trans);
+    wr("unc_quat.bin", std::vector<double>(u2.m, u2.m + 36));
+    std::cout << "adapter_selftest unc ok" << std::endl;
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { std::cerr << "usage: adapter_selftest <dir> [klt]" << std::endl; return 2; }
+    if (argc < 2) { std::cerr << "usage: adapter_selftest <dir> [klt|unc]" << std::endl; return 2; }
     g_dir = argv[1];
     if (argc > 2 && std::string(argv[2]) == "klt") return kltSection();
+    if (argc > 2 && std::string(argv[2]) == "unc") return uncSection();
     float Kf[9] = {517.3f, 0, 318.6f, 0, 516.5f, 255.3f, 0, 0, 1};
     float Df[5] = {-0.0410f, 0.3286f, 0.0087f, 0.0051f, -0.5643f};
     cv::Mat K(3, 3, CV_32FC1, Kf), D(1, 5, CV_32FC1, Df);

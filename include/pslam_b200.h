@@ -350,6 +350,22 @@ PSLAM_API int pslam_frame_to_resident_map(pslam_ctx* ctx, const double camera_po
                                           int* match_query_out, int* match_train_out, float* match_dist_out,
                                           int* inlier_idx_out, pslam_frame_result* result);
 
+/* Replaces TransformEst::computeUncertainty (parametrization EULER: 6 x 6 covariance over x, y, z, roll, pitch, yaw;
+ * include/putslam/TransformEst/transformEst.h:29-144) and computeUncertaintyG2O (QUATERNION: x, y, z, qx, qy, qz; :147-272)
+ * for a batch of independent problems (callers demos/demoKabsch.cpp:655,731,1028):
+ * U = H^-1 G^T Cx G H^-1 with H = d2J/dtheta2 and G = d2J/dtheta dX of J = sum |a_i - R b_i - t|^2 at the given
+ * transformation, Cx = the block-diagonal covariance of the points.  Layouts as pslam_kabsch_batch:
+ *   A, B        concatenated n_i x 3 ROW-major points (setA, setB), offsets[batch + 1]
+ *   covA, covB  n_i x 9, one ROW-major 3 x 3 per point (setAUncertainty, setBUncertainty)
+ *   T           batch x 12, column-major 3 x 4 with A ~= R*B + t   (the Mat34 passed as `transformation`)
+ *   U_out       batch x 36, column-major 6 x 6 (Mat66)
+ *   ok_out      nullable, batch: 0 where the set is empty or the Hessian is singular (U = 0 there; Eigen's inverse()
+ *               would return non-finite values) */
+enum { PSLAM_UNCERTAINTY_EULER = 0, PSLAM_UNCERTAINTY_QUATERNION = 1 };
+PSLAM_API int pslam_transform_uncertainty_batch(pslam_ctx* ctx, const double* A, const double* B, const double* covA,
+                                                const double* covB, const int* offsets, const double* T, int batch,
+                                                int parametrization, double* U_out, int* ok_out);
+
 /* ---- KLT tracking: the performTracking seam ------------------------------
  * pslam_klt_track == cv::calcOpticalFlowPyrLK(prevImg, img, prevPts, nextPts, status, err, Size(win, win), max_level,
  * TermCriteria(criteria_type, max_iter, eps), flags, min_eig_threshold) as MatcherOpenCV::performTracking calls it

@@ -44,6 +44,10 @@ def euler_derivatives(w, x, y, z):
     roll = math.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
     pitch = math.asin(2 * (w * y - z * x))
     yaw = math.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+    return euler_derivatives_from_angles(roll, pitch, yaw)
+
+
+def euler_derivatives_from_angles(roll, pitch, yaw):
     def axis(a, k):       # rotation about axis k and its first / second derivative
         c, s = math.cos(a), math.sin(a)
         i, j = (k + 1) % 3, (k + 2) % 3

@@ -17,7 +17,7 @@ ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NCCL, ERR_NO_DEVICE = -1, 
 # every symbol include/pslam_b200.h declares (tests check the library exports exactly these)
 ABI_SYMBOLS = [
     "pslam_ctx_create", "pslam_ctx_destroy", "pslam_last_error", "pslam_version", "pslam_ctx_stream",
-    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_klt_track", "pslam_klt_perform_tracking", "pslam_klt_frame", "pslam_match_bf_mutual",
+    "pslam_ctx_sync", "pslam_kernel_launches", "pslam_sm_count", "pslam_backproject", "pslam_information_matrices", "pslam_normal_uncertainty", "pslam_gradient_uncertainty", "pslam_orb_describe", "pslam_orb_detect", "pslam_fast_detect", "pslam_klt_track", "pslam_klt_perform_tracking", "pslam_klt_frame", "pslam_transform_uncertainty_batch", "pslam_match_bf_mutual",
     "pslam_match_knn2", "pslam_match_guided_xyz", "pslam_ransac_estimate", "pslam_ransac_set_stopping", "pslam_ransac_last_counts",
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
@@ -248,6 +248,23 @@ class Context:
         self._ck(self.lib.pslam_fast_detect(self.h, _p(img, C.c_uint8), W, H, ch * W, ch, int(colour_order), int(threshold),
                                             _p(xy, C.c_float), _p(resp, C.c_float), cap, C.byref(n)))
         return xy[:n.value].copy(), resp[:n.value].copy()
+
+    def transform_uncertainty(self, A_list, B_list, covA_list, covB_list, T_list, mode="euler"):
+        """TransformEst::computeUncertainty ("euler") / computeUncertaintyG2O ("quat") for a batch: lists of n_i x 3 points,
+        n_i x 3 x 3 covariances and 4 x 4 (or 3 x 4) transforms with A ~ R B + t -> (U [batch, 6, 6], ok [batch])"""
+        batch = len(A_list)
+        off = np.zeros(batch + 1, np.int32)
+        for i, a in enumerate(A_list):
+            off[i + 1] = off[i] + len(a)
+        cat = lambda L, w: (np.concatenate([np.asarray(x, np.float64).reshape(-1, w) for x in L]) if off[-1] else np.zeros((0, w)))
+        A = np.ascontiguousarray(cat(A_list, 3)); B = np.ascontiguousarray(cat(B_list, 3))
+        CA = np.ascontiguousarray(cat(covA_list, 9)); CB = np.ascontiguousarray(cat(covB_list, 9))
+        T = np.ascontiguousarray(np.stack([np.asarray(t, np.float64)[:3, :4].T.ravel() for t in T_list])) if batch else np.zeros((0, 12))
+        U = np.zeros((max(batch, 1), 36), np.float64); ok = np.zeros(max(batch, 1), np.int32)
+        self._ck(self.lib.pslam_transform_uncertainty_batch(self.h, _p(A, C.c_double), _p(B, C.c_double), _p(CA, C.c_double),
+                                                            _p(CB, C.c_double), _p(off, C.c_int), _p(T, C.c_double), batch,
+                                                            0 if mode == "euler" else 1, _p(U, C.c_double), _p(ok, C.c_int)))
+        return U[:batch].reshape(batch, 6, 6).transpose(0, 2, 1).copy(), ok[:batch].copy()
 
     # ---- KLT tracking (performTracking seam) ----
     KLT_USE_INITIAL_FLOW, KLT_GET_MIN_EIGENVALS = 4, 8

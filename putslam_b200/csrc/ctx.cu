@@ -783,6 +783,52 @@ int pslam_kabsch_batch(pslam_ctx* ctx, const double* A, const double* B, const i
     return PSLAM_OK;
 }
 
+int pslam_transform_uncertainty_batch(pslam_ctx* ctx, const double* A, const double* B, const double* covA, const double* covB,
+                                      const int* offsets, const double* T, int batch, int parametrization, double* U_out,
+                                      int* ok_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (batch < 0 || (batch > 0 && (!offsets || !T || !U_out)) || (parametrization != PSLAM_UNCERTAINTY_EULER &&
+                                                                    parametrization != PSLAM_UNCERTAINTY_QUATERNION))
+        return fail(ctx, PSLAM_ERR_ARG, "pslam_transform_uncertainty_batch: bad argument");
+    if (batch == 0) return PSLAM_OK;
+    const int total = offsets[batch];
+    for (int b = 0; b < batch; ++b)
+        if (offsets[b] < 0 || offsets[b + 1] < offsets[b]) return fail(ctx, PSLAM_ERR_ARG, "pslam_transform_uncertainty_batch: offsets not ascending");
+    if (total > 0 && (!A || !B || !covA || !covB)) return fail(ctx, PSLAM_ERR_ARG, "pslam_transform_uncertainty_batch: null point buffer");
+    CK(cudaSetDevice(ctx->device));
+    const size_t tot = (size_t)(total > 0 ? total : 1);
+    Arena in, out;
+    const size_t o_a = in.take(24 * tot), o_b = in.take(24 * tot), o_ca = in.take(72 * tot), o_cb = in.take(72 * tot);
+    const size_t o_off = in.take(4 * (size_t)(batch + 1)), o_t = in.take(96 * (size_t)batch);
+    const size_t o_u = out.take(288 * (size_t)batch), o_ok = out.take(4 * (size_t)batch);
+    TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
+    TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
+    ctx->f2m.valid = false; ctx->f2f.valid = false;   // the arenas are reused
+    uint8_t* h = ctx->h_in.p;
+    if (total > 0) {
+        memcpy(h + o_a, A, 24 * (size_t)total); memcpy(h + o_b, B, 24 * (size_t)total);
+        memcpy(h + o_ca, covA, 72 * (size_t)total); memcpy(h + o_cb, covB, 72 * (size_t)total);
+    }
+    memcpy(h + o_off, offsets, 4 * (size_t)(batch + 1));
+    memcpy(h + o_t, T, 96 * (size_t)batch);
+    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* d = ctx->d_in.p;
+    int l = 0;
+    CK(launch_uncertainty_batch((const double*)(d + o_a), (const double*)(d + o_b), (const double*)(d + o_ca),
+                                (const double*)(d + o_cb), (const int*)(d + o_off), (const double*)(d + o_t), batch,
+                                parametrization, (double*)(ctx->d_out.p + o_u), (int*)(ctx->d_out.p + o_ok), ctx->stream, &l));
+    ctx->launches += l;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // device result is row-major; the ABI is column-major (Eigen's Mat66 layout)
+    const double* u = (const double*)(ctx->h_out.p + o_u);
+    for (int b = 0; b < batch; ++b)
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) U_out[36 * (size_t)b + 6 * j + i] = u[36 * (size_t)b + 6 * i + j];
+    if (ok_out) memcpy(ok_out, ctx->h_out.p + o_ok, 4 * (size_t)batch);
+    return PSLAM_OK;
+}
+
 // ---- fused pipelines ----------------------------------------------------------------------------
 // host-libm tables for the device level prediction (see guided.cu)
 struct HostLevelTables {

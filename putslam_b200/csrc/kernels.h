@@ -124,6 +124,12 @@ cudaError_t launch_information(const double* d_uvz, int n, const pslam_cov_param
 cudaError_t launch_kabsch_batch(const double* d_A, const double* d_B, const int* d_off, int batch, double* d_T,
                                 cudaStream_t st, int* launches);
 
+// ---- uncertainty.cu --------------------------------------------------------------------------
+// mode 0: Euler angles (computeUncertainty), 1: quaternion vector part (computeUncertaintyG2O); see uncertainty.cu
+cudaError_t launch_uncertainty_batch(const double* d_A, const double* d_B, const double* d_CA, const double* d_CB,
+                                     const int* d_off, const double* d_T, int batch, int mode, double* d_U, int* d_ok,
+                                     cudaStream_t st, int* launches);
+
 // ---- mapprep.cu ------------------------------------------------------------------------------
 cudaError_t launch_map_prepare(const double* d_xyz, const float* d_view_axis, int M, const double* pose_colmajor,
                                double fx, double fy, double cx, double cy, double img_w, double img_h, double max_angle,

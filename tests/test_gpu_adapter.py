@@ -212,3 +212,28 @@ def test_adapter_perform_tracking(tmp_path, golden):
     assert np.array_equal(_rd(d, "kltf_inliers_t.bin", np.int32), ref["inliers"])
     assert np.abs(_rd(d, "kltf_T.bin", np.float32).reshape(4, 4).T - ref["T"]).max() <= 1e-5
     assert _rd(d, "kltf_ratio.bin", np.float64)[0] == len(ref["inliers"]) / len(k01)
+
+
+def test_adapter_compute_uncertainty(tmp_path):
+    """KabschEst::computeTransformation followed by TransformEst::computeUncertainty / computeUncertaintyG2O, the call
+    sequence of demos/demoKabsch.cpp:1020-1028, against the oracle evaluated at the transformation the adapter returned"""
+    from oracle import uncertainty_oracle as Uo
+    from putslam_b200 import synth
+    assert os.path.exists(EXE), "adapter_selftest not built (run __graft_entry__.build())"
+    d = str(tmp_path)
+    rng = np.random.default_rng(29)
+    n = 100
+    A = rng.uniform(-1.5, 1.5, (n, 3))
+    B = A @ synth.rot_from_rotvec([0.2, 0.1, -0.3]).T + [0.1, 0.2, -0.3] + rng.normal(0, [0.01, 0.02, 0.03], (n, 3))
+    L = rng.normal(0, 0.01, (2, n, 3, 3))
+    CA = L[0] @ L[0].transpose(0, 2, 1); CB = L[1] @ L[1].transpose(0, 2, 1)
+    for name, arr in (("kabsch_A", A), ("kabsch_B", B), ("unc_CA", CA), ("unc_CB", CB)):
+        np.ascontiguousarray(arr, np.float64).tofile(os.path.join(d, name + ".bin"))
+    out = subprocess.run([EXE, d, "unc"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    T = _rd(d, "unc_T.bin", np.float64).reshape(4, 4).T                      # column-major Mat34, B ~ R A + t
+    assert np.abs(B - (A @ T[:3, :3].T + T[:3, 3])).max() < 0.2
+    for mode in ("euler", "quat"):
+        U = _rd(d, f"unc_{mode}.bin", np.float64).reshape(6, 6).T
+        ref, _, _ = Uo.compute_uncertainty(B, A, CB, CA, T, mode)            # setA := B, setB := A (B ~ R A + t)
+        assert np.abs(U - ref).max() < 1e-9 * np.abs(ref).max(), mode
