@@ -1487,6 +1487,10 @@ static double sq_threshold_d(double d) {   // smallest double T with sqrt(T) >= 
     while (sqrt(t) < d) t = nextafter(t, INFINITY);
     return t;
 }
+static float prune_limit(double d) {       // smallest float >= d (pre-test of klt_pair_removes); +inf disables the pre-test
+    if (!(d > 0.)) return 0.f;             // nothing is close anyway (sq_threshold_d gives 0): everything is discarded early
+    return float_at_least(d);
+}
 static void pack_rows(uint8_t* dst, const uint8_t* src, size_t row, int H, int row_bytes) {
     if ((size_t)row_bytes == row) memcpy(dst, src, row * H);
     else for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * row, src + (size_t)y * row_bytes, row);
@@ -1589,7 +1593,7 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
                             ctx->stream, &l));
         if (prune)
             CK(launch_klt_prune(d_xy, (const float*)(ctx->d_out.p + o_err), ctx->d_out.p + o_st, n, error_threshold,
-                                sq_threshold_d(min_distance), ctx->d_out.p + o_keep, ctx->stream, &l));
+                                sq_threshold_d(min_distance), prune_limit(min_distance), ctx->d_out.p + o_keep, ctx->stream, &l));
         if (fr) {
             int* mout = (int*)(ctx->d_out.p + o_m);
             float* cxy = (float*)(ctx->d_out.p + o_cxy);

@@ -173,8 +173,9 @@ cudaError_t launch_orb_describe(const uint8_t* d_bgr, int W, int H, int row_byte
 cudaError_t launch_klt_pyramid(uint8_t* d_pyrI, uint8_t* d_pyrJ, const KltPlan& P, int cn, cudaStream_t st, int* launches);
 cudaError_t launch_klt_track(const KltParams& P, const float* d_prev_xy, float* d_cur_xy, int n, uint8_t* d_status,
                              float* d_err, cudaStream_t st, int* launches);
+// sq_thr: smallest double whose square root reaches the distance threshold; lim: smallest float >= that threshold
 cudaError_t launch_klt_prune(const float* d_xy, const float* d_err, const uint8_t* d_status, int n, double err_thr,
-                             double sq_thr, uint8_t* d_keep, cudaStream_t st, int* launches);
+                             double sq_thr, float lim, uint8_t* d_keep, cudaStream_t st, int* launches);
 // d_mout: int[1 + 3 * cap] = {m, kept[cap], j[cap], 0[cap]} (match-list layout of the RANSAC launcher), d_cxy: cap x 2
 cudaError_t launch_klt_compact(const uint8_t* d_keep, const float* d_xy, int n, int cap, int* d_mout, float* d_cxy,
                                cudaStream_t st, int* launches);

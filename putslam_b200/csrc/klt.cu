@@ -7,7 +7,7 @@
 //                        8 x 8 pixels a window touches instead of for whole images (klt_point.cuh)
 //   klt_prune_kernel     the rest of performTracking: err threshold, and of every pair of tracked positions closer than
 //                        minimalReprojDistanceNewTrackingFeatures the one with the larger err is dropped (:247-266) --
-//                        N^2 / 2 pair tests, one thread per feature over shared-memory tiles of the others
+//                        N^2 pair tests, one warp per feature
 // Frames are at most a few MB and stay in L2 between the kernels; all three are latency-bound.
 #include "common.cuh"
 #include "kernels.h"
@@ -77,39 +77,23 @@ cudaError_t launch_klt_track(const KltParams& P, const float* d_prev_xy, float* 
 }
 
 // keep[i] = status[i] && !(err[i] > err_thr) && no closer-than-threshold neighbour wins against i (klt_pair_removes).
-constexpr int kPruneTile = 1024;
+// One warp per feature: the lanes share the n - 1 pair tests (the positions are 12 KB per 1000 features and stay in L1),
+// a float pre-test discards the pairs that are far apart, a warp vote collects the verdict.
 __global__ void __launch_bounds__(128)
-klt_prune_kernel(const float2* __restrict__ xy, const float* __restrict__ err, const uint8_t* __restrict__ status, int n,
-                 double err_thr, double sq_thr, uint8_t* __restrict__ keep) {
-    __shared__ float2 sxy[kPruneTile];
-    __shared__ float serr[kPruneTile];
+klt_prune_kernel(const float* __restrict__ xy, const float* __restrict__ err, const uint8_t* __restrict__ status, int n,
+                 double err_thr, double sq_thr, float lim, uint8_t* __restrict__ keep) {
     chain_begin();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    float2 p = make_float2(0.f, 0.f);
-    float ei = 0.f;
-    if (live) { p = xy[i]; ei = err[i]; }
-    bool removed = false;
-    for (int base = 0; base < n; base += kPruneTile) {
-        const int m = min(kPruneTile, n - base);
-        __syncthreads();
-        for (int t = threadIdx.x; t < m; t += blockDim.x) { sxy[t] = xy[base + t]; serr[t] = err[base + t]; }
-        __syncthreads();
-        if (live && !removed) {
-            for (int t = 0; t < m; ++t) {
-                const float2 q = sxy[t];
-                if (klt_pair_removes(i, base + t, p.x, p.y, ei, q.x, q.y, serr[t], sq_thr)) { removed = true; break; }
-            }
-        }
-    }
-    if (live) keep[i] = (uint8_t)(status[i] != 0 && !((double)ei > err_thr) && !removed);
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;                                  // whole warps leave together
+    const bool removed = __any_sync(0xffffffffu, klt_prune_lane(i, lane, n, xy, err, sq_thr, lim));
+    if (lane == 0) keep[i] = (uint8_t)(status[i] != 0 && !((double)err[i] > err_thr) && !removed);
 }
 
 cudaError_t launch_klt_prune(const float* d_xy, const float* d_err, const uint8_t* d_status, int n, double err_thr,
-                             double sq_thr, uint8_t* d_keep, cudaStream_t st, int* launches) {
+                             double sq_thr, float lim, uint8_t* d_keep, cudaStream_t st, int* launches) {
     if (n <= 0) return cudaSuccess;
-    cudaError_t e = launch_chained(klt_prune_kernel, dim3((n + 127) / 128), dim3(128), 0, st, (const float2*)d_xy, d_err,
-                                   d_status, n, err_thr, sq_thr, d_keep);
+    cudaError_t e = launch_chained(klt_prune_kernel, dim3((n + 3) / 4), dim3(128), 0, st, d_xy, d_err, d_status, n, err_thr,
+                                   sq_thr, lim, d_keep);
     if (e == cudaSuccess) ++*launches;
     return e;
 }

@@ -27,9 +27,11 @@
 #if defined(__CUDA_ARCH__)
 #define KLT_LANES_BEGIN { const int lane = (int)(threadIdx.x & 31u);
 #define KLT_LANES_END } __syncwarp();
+#define KLT_UNROLL _Pragma("unroll")
 #else
 #define KLT_LANES_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define KLT_LANES_END }
+#define KLT_UNROLL
 #endif
 
 namespace pslam {
@@ -92,15 +94,16 @@ struct KltWork {
     uint8_t* pI;                     // (win + 3)^2 * cn : previous-frame patch, one pixel of margin for the gradient
     uint8_t* pJ;                     // (win + 1)^2 * cn : current-frame patch
     int16_t *gx, *gy;                // (win + 1)^2 * cn : Scharr gradient of the previous frame
-    int16_t *Iw, *Ix, *Iy, *df;      // win^2 * cn       : interpolated window, its gradient, J - I
+    int16_t *Iw, *Ix, *Iy;           // win^2 * cn       : interpolated window and its gradient
+    float* prod;                     // 3 * win^2 * cn   : float-converted products, laid out chain by chain (klt_slot)
     float* chain;                    // 16
     int* part;                       // 32
 };
 KLT_HD size_t klt_work_bytes(int win, int cn) {
     const size_t nP = (size_t)(win + 3) * (win + 3) * cn, nG = (size_t)(win + 1) * (win + 1) * cn, nW = (size_t)win * win * cn;
     size_t b = ((nP + 3) & ~(size_t)3) + ((nG + 3) & ~(size_t)3);
-    b += 2 * 2 * ((nG + 1) & ~(size_t)1) + 4 * 2 * ((nW + 1) & ~(size_t)1);
-    b += 16 * sizeof(float) + 32 * sizeof(int);
+    b += 2 * 2 * ((nG + 1) & ~(size_t)1) + 3 * 2 * ((nW + 1) & ~(size_t)1);
+    b += 3 * nW * sizeof(float) + 16 * sizeof(float) + 32 * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 KLT_HD KltWork klt_carve(uint8_t* base, int win, int cn) {
@@ -114,7 +117,7 @@ KLT_HD KltWork klt_carve(uint8_t* base, int win, int cn) {
     w.Iw = (int16_t*)base; base += 2 * w2;
     w.Ix = (int16_t*)base; base += 2 * w2;
     w.Iy = (int16_t*)base; base += 2 * w2;
-    w.df = (int16_t*)base; base += 2 * w2;
+    w.prod = (float*)base; base += 3 * nW * sizeof(float);
     w.chain = (float*)base; base += 16 * sizeof(float);
     w.part = (int*)base;
     return w;
@@ -170,51 +173,60 @@ KLT_HD KltWeights klt_weights(float a, float b) {
     return w;
 }
 
-// One of the five ordered partial sums of  sum_i a[i] * b[i]  over a window of `rows` rows of `cols` values:
-// k = 0..3: the values x < 8 * floor(cols / 8) of every row with x mod 4 == k; k = 4: the remaining values of every row;
-// each in raster order, float accumulation of the float-converted integer products.
-KLT_HD float klt_chain(const int16_t* a, const int16_t* b, int rows, int cols, int k) {
-    const int n8 = (cols / 8) * 8;
+// The window sums.  OpenCV's 128-bit loop leaves every sum  sum_i a[i] * b[i]  over a window of `rows` rows of `cols`
+// values as five ordered partial sums ("chains"): chain k = 0..3 takes the values x < n8 = 8 * floor(cols / 8) of every
+// row with x mod 4 == k, chain 4 the remaining values of every row, each in raster order, float accumulation of the
+// float-converted integer products; the result is  chain4 + ((chain0 + chain2) + (chain1 + chain3))  (klt_combine).
+//   A11 / A12 / A22: every product is converted and added on its own        -> klt_slot
+//   b1 / b2 (the Newton steps): within each group of 8 the products x and x + 4 are first added as integers (a 16-bit
+//   multiply-add instruction yields both), then converted and added           -> klt_slot_paired
+// The lanes that compute the products store them as floats at the position they have in their chain, so that the lane
+// that owns a chain reads it front to back: `len` dependent float adds and nothing else on the critical path.
+KLT_HD int klt_slot(int y, int x, int rows, int cols) {
+    const int n8 = (cols / 8) * 8, q = n8 >> 2;
+    return x < n8 ? (x & 3) * rows * q + y * q + (x >> 2) : 4 * rows * q + y * (cols - n8) + (x - n8);
+}
+// unit g of row y: g < n8 / 2 is the pair (x, x + 4) with x = 8 * (g / 4) + g % 4, the rest are the single tail values
+KLT_HD int klt_units_per_row(int cols) { return ((cols / 8) * 8) / 2 + cols - (cols / 8) * 8; }
+KLT_HD int klt_slot_paired(int y, int g, int rows, int cols) {
+    const int n8 = (cols / 8) * 8, qp = n8 >> 3, h8 = n8 >> 1;
+    return g < h8 ? (g & 3) * rows * qp + y * qp + (g >> 2) : 4 * rows * qp + y * (cols - n8) + (g - h8);
+}
+KLT_HD float klt_chain_sum(const float* p, int len) {
     float s = 0.f;
-    for (int y = 0; y < rows; ++y) {
-        const int16_t* ra = a + y * cols;
-        const int16_t* rb = b + y * cols;
-        if (k < 4) {
-            for (int x = k; x < n8; x += 4) s = s + (float)((int)ra[x] * (int)rb[x]);
-        } else {
-            for (int x = n8; x < cols; ++x) s = s + (float)((int)ra[x] * (int)rb[x]);
-        }
-    }
+    KLT_UNROLL
+    for (int t = 0; t < len; ++t) s = s + p[t];
     return s;
 }
-// the same five partial sums as OpenCV's mismatch loop forms them: within every group of 8 values the products x and
-// x + 4 are added as integers (one multiply-add instruction pair) before the float conversion and accumulation
-KLT_HD float klt_chain_paired(const int16_t* a, const int16_t* b, int rows, int cols, int k) {
-    const int n8 = (cols / 8) * 8;
-    float s = 0.f;
-    for (int y = 0; y < rows; ++y) {
-        const int16_t* ra = a + y * cols;
-        const int16_t* rb = b + y * cols;
-        if (k < 4) {
-            for (int x = k; x < n8; x += 8) s = s + (float)((int)ra[x] * (int)rb[x] + (int)ra[x + 4] * (int)rb[x + 4]);
-        } else {
-            for (int x = n8; x < cols; ++x) s = s + (float)((int)ra[x] * (int)rb[x]);
-        }
-    }
-    return s;
+// chain k of a sum stored with klt_slot (paired = 0) or klt_slot_paired (1)
+KLT_HD float klt_chain(const float* base, int k, int rows, int cols, int paired) {
+    const int n8 = (cols / 8) * 8, q = paired ? n8 >> 3 : n8 >> 2;
+    if (k < 4) return klt_chain_sum(base + k * rows * q, rows * q);
+    return klt_chain_sum(base + 4 * rows * q, rows * (cols - n8));
 }
 KLT_HD float klt_combine(const float* c) { return c[4] + ((c[0] + c[2]) + (c[1] + c[3])); }
 
 // performTracking's pairwise rule (matcherOpenCV.cpp:254-266), seen from feature i: does the pair (i, j) remove i?
 // The reference visits pairs a < b and drops a when err[a] > err[b], otherwise b (ties and NaNs included).  Closeness:
 // sqrt(dx^2 + dy^2) < d in double on float differences (cv::norm(Point2f)); sq_thr is the smallest double whose square
-// root is >= d, which turns it into an exact comparison of the squared distance.
-KLT_HD bool klt_pair_removes(int i, int j, float xi, float yi, float ei, float xj, float yj, float ej, double sq_thr) {
-    if (i == j) return false;
+// root is >= d, which turns it into an exact comparison of the squared distance.  lim = the smallest float >= d: a pair
+// with |dx| >= lim or |dy| >= lim cannot be close (the rounded sum of squares is never below either square), so the
+// double arithmetic is only done for the few candidates.
+KLT_HD bool klt_pair_removes(int i, int j, float xi, float yi, float ei, float xj, float yj, float ej, double sq_thr, float lim) {
     const float dx = xi - xj, dy = yi - yj;    // the square does not see which way round the reference subtracts
+    if (fabsf(dx) >= lim || fabsf(dy) >= lim || i == j) return false;
     const double s = (double)dx * (double)dx + (double)dy * (double)dy;
     if (!(s < sq_thr)) return false;
     return j > i ? (ei > ej) : !(ej > ei);
+}
+// lane's share of feature i's pair tests (features lane, lane + 32, ...): true when one of them removes i.
+// Feature i goes when any lane says so.
+KLT_HD bool klt_prune_lane(int i, int lane, int n, const float* xy, const float* err, double sq_thr, float lim) {
+    const float xi = xy[2 * i], yi = xy[2 * i + 1], ei = err[i];
+    bool removed = false;
+    for (int j = lane; j < n; j += 32)
+        removed = removed || klt_pair_removes(i, j, xi, yi, ei, xy[2 * j], xy[2 * j + 1], err[j], sq_thr, lim);
+    return removed;
 }
 
 // Tracks one point through all levels.  Everything outside the KLT_LANES sections is warp-uniform.
@@ -228,6 +240,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
     const int win = WIN_T ? WIN_T : P.win, cn = CN_T ? CN_T : P.cn, cols = win * cn, nW = win * cols;
     const int gcols = (win + 1) * cn, nG = (win + 1) * gcols;
     const int pcols = (win + 3) * cn, nP = (win + 3) * pcols;
+    const int n8 = (cols / 8) * 8, h8 = n8 >> 1, upr = klt_units_per_row(cols), nU = win * upr;
     const int max_level = P.n_levels - 1;
     const float half = (float)((win - 1) * 0.5);
     const float flt_scale = 1.f / (float)(1 << 20);
@@ -259,6 +272,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
 
         // previous-frame patch, pixels (ix - 1 .. ix + win + 1) x (iy - 1 .. iy + win + 1), reflected at the borders
         KLT_LANES_BEGIN
+        KLT_UNROLL
         for (int i = lane; i < nP; i += 32) {
             const int yy = i / pcols, r = i - yy * pcols, xx = r / cn, c = r - xx * cn;
             const int sx = klt_reflect101(ix - 1 + xx, w), sy = klt_reflect101(iy - 1 + yy, h);
@@ -267,6 +281,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
         KLT_LANES_END
         // Scharr gradient at the (win + 1)^2 pixels the window touches; zero outside the image
         KLT_LANES_BEGIN
+        KLT_UNROLL
         for (int i = lane; i < nG; i += 32) {
             const int yy = i / gcols, r = i - yy * gcols, xx = r / cn;
             int dx = 0, dy = 0;
@@ -284,6 +299,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
         KLT_LANES_END
         // window of I (5 fractional bits kept) and of its gradient at the sub-pixel position
         KLT_LANES_BEGIN
+        KLT_UNROLL
         for (int i = lane; i < nW; i += 32) {
             const int y = i / cols, r = i - y * cols;
             const uint8_t* p = W.pI + (y + 1) * pcols + cn + r;
@@ -291,12 +307,16 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
             const int g = y * gcols + r;
             W.Ix[i] = (int16_t)klt_descale(W.gx[g] * wi.w00 + W.gx[g + cn] * wi.w01 + W.gx[g + gcols] * wi.w10 + W.gx[g + gcols + cn] * wi.w11, kKltWBits);
             W.Iy[i] = (int16_t)klt_descale(W.gy[g] * wi.w00 + W.gy[g + cn] * wi.w01 + W.gy[g + gcols] * wi.w10 + W.gy[g + gcols + cn] * wi.w11, kKltWBits);
+            const int vx = W.Ix[i], vy = W.Iy[i], slot = klt_slot(y, r, win, cols);
+            W.prod[slot] = (float)(vx * vx);
+            W.prod[nW + slot] = (float)(vx * vy);
+            W.prod[2 * nW + slot] = (float)(vy * vy);
         }
         KLT_LANES_END
         KLT_LANES_BEGIN
         if (lane < 15) {
             const int s = lane / 5, k = lane - 5 * s;
-            W.chain[lane] = klt_chain(s == 2 ? W.Iy : W.Ix, s == 0 ? W.Ix : W.Iy, win, cols, k);
+            W.chain[lane] = klt_chain(W.prod + s * nW, k, win, cols, 0);
         }
         KLT_LANES_END
         const float A11 = klt_combine(W.chain) * flt_scale, A12 = klt_combine(W.chain + 5) * flt_scale,
@@ -320,23 +340,37 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
             }
             const KltWeights wj = klt_weights(nx - (float)jx, ny - (float)jy);
             KLT_LANES_BEGIN
+            KLT_UNROLL
             for (int i = lane; i < nG; i += 32) {
                 const int yy = i / gcols, r = i - yy * gcols, xx = r / cn, c = r - xx * cn;
                 const int sx = klt_reflect101(jx + xx, w), sy = klt_reflect101(jy + yy, h);
                 W.pJ[i] = J[((size_t)sy * w + sx) * cn + c];
             }
             KLT_LANES_END
+            // J - I at the window positions times the gradient, unit by unit (a pair x, x + 4 or a single tail value)
             KLT_LANES_BEGIN
-            for (int i = lane; i < nW; i += 32) {
-                const int y = i / cols, r = i - y * cols;
-                const uint8_t* p = W.pJ + y * gcols + r;
-                W.df[i] = (int16_t)(klt_descale(p[0] * wj.w00 + p[cn] * wj.w01 + p[gcols] * wj.w10 + p[gcols + cn] * wj.w11, kKltWBits - 5) - (int)W.Iw[i]);
+            KLT_UNROLL
+            for (int u = lane; u < nU; u += 32) {
+                const int y = u / upr, g = u - y * upr;
+                const bool pair = g < h8;
+                const int x0 = pair ? ((g >> 2) << 3) + (g & 3) : n8 + (g - h8);
+                const uint8_t* p = W.pJ + y * gcols + x0;
+                const int i0 = y * cols + x0;
+                const int d0 = klt_descale(p[0] * wj.w00 + p[cn] * wj.w01 + p[gcols] * wj.w10 + p[gcols + cn] * wj.w11, kKltWBits - 5) - (int)W.Iw[i0];
+                int s1 = d0 * (int)W.Ix[i0], s2 = d0 * (int)W.Iy[i0];
+                if (pair) {
+                    const int d1 = klt_descale(p[4] * wj.w00 + p[4 + cn] * wj.w01 + p[4 + gcols] * wj.w10 + p[4 + gcols + cn] * wj.w11, kKltWBits - 5) - (int)W.Iw[i0 + 4];
+                    s1 += d1 * (int)W.Ix[i0 + 4]; s2 += d1 * (int)W.Iy[i0 + 4];
+                }
+                const int slot = klt_slot_paired(y, g, win, cols);
+                W.prod[slot] = (float)s1;
+                W.prod[nW + slot] = (float)s2;
             }
             KLT_LANES_END
             KLT_LANES_BEGIN
             if (lane < 10) {
                 const int s = lane / 5, k = lane - 5 * s;
-                W.chain[lane] = klt_chain_paired(W.df, s == 0 ? W.Ix : W.Iy, win, cols, k);
+                W.chain[lane] = klt_chain(W.prod + s * nW, k, win, cols, 1);
             }
             KLT_LANES_END
             const float b1 = klt_combine(W.chain) * flt_scale, b2 = klt_combine(W.chain + 5) * flt_scale;
@@ -357,6 +391,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
             if (jx < -win || jx >= w || jy < -win || jy >= h) { status = 0; continue; }
             const KltWeights wj = klt_weights(qx - (float)jx, qy - (float)jy);
             KLT_LANES_BEGIN
+            KLT_UNROLL
             for (int i = lane; i < nG; i += 32) {
                 const int yy = i / gcols, r = i - yy * gcols, xx = r / cn, c = r - xx * cn;
                 const int sx = klt_reflect101(jx + xx, w), sy = klt_reflect101(jy + yy, h);

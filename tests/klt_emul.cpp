@@ -60,13 +60,12 @@ extern "C" int klt_emul_track(const uint8_t* I0, const uint8_t* J0, int W, int H
     return 0;
 }
 
-// klt_prune_kernel's decision per feature, through the same predicate (klt_pair_removes)
+// klt_prune_kernel's decision per feature: the 32 lanes' shares of the pair tests (klt_prune_lane), OR-ed like the warp vote
 extern "C" int klt_emul_prune(const float* xy, const float* err, const uint8_t* status, int n, double err_thr, double sq_thr,
-                              uint8_t* keep) {
+                              float lim, uint8_t* keep) {
     for (int i = 0; i < n; ++i) {
         bool removed = false;
-        for (int j = 0; j < n && !removed; ++j)
-            removed = klt_pair_removes(i, j, xy[2 * i], xy[2 * i + 1], err[i], xy[2 * j], xy[2 * j + 1], err[j], sq_thr);
+        for (int lane = 0; lane < 32; ++lane) removed = klt_prune_lane(i, lane, n, xy, err, sq_thr, lim) || removed;
         keep[i] = (uint8_t)(status[i] != 0 && !((double)err[i] > err_thr) && !removed);
     }
     return 0;

@@ -24,7 +24,7 @@ def load():
         _lib = C.CDLL(OUT)
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
         _lib.klt_emul_track.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci, ci, ci, ci, cd, ci, cd, vp, vp, ci, C.POINTER(ci)]
-        _lib.klt_emul_prune.argtypes = [vp, vp, vp, ci, cd, cd, vp]
+        _lib.klt_emul_prune.argtypes = [vp, vp, vp, ci, cd, cd, C.c_float, vp]
         _lib.klt_emul_pyrdown.argtypes = [vp, ci, ci, ci, vp]
     return _lib
 
@@ -62,10 +62,19 @@ def sq_threshold(d):
     return float(t)
 
 
+def prune_limit(d):
+    """smallest float >= d, 0 for d <= 0 or NaN (the library's host side, prune_limit in ctx.cu)"""
+    if not d > 0: return 0.0
+    f = np.float32(d)
+    if float(f) < d: f = np.nextafter(f, np.float32(np.inf))
+    return float(f)
+
+
 def prune(xy, err, status, err_thr, min_distance):
     L = load()
     xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2); n = len(xy)
     err = np.ascontiguousarray(err, np.float32); status = np.ascontiguousarray(status, np.uint8)
     keep = np.zeros(n, np.uint8)
-    L.klt_emul_prune(xy.ctypes.data, err.ctypes.data, status.ctypes.data, n, err_thr, sq_threshold(min_distance), keep.ctypes.data)
+    L.klt_emul_prune(xy.ctypes.data, err.ctypes.data, status.ctypes.data, n, err_thr, sq_threshold(min_distance),
+                     prune_limit(min_distance), keep.ctypes.data)
     return np.nonzero(keep)[0]
