@@ -67,3 +67,46 @@ def test_klt_prune_source_matches_oracle():
         e[5] = np.nan
         st = (rng.uniform(size=n) < 0.9).astype(np.uint8)
         assert np.array_equal(E.prune(xy, e, st, 25.0, d), K.perform_tracking(e, st, xy, 25.0, d)), (n, d)
+
+
+def test_klt_kernel_source_fuzz_against_live_cv2():
+    """250 random configurations -- frame sizes 8 .. 260 (pyramids cut short), windows 3 .. 21, 0 .. 5 levels, gray and
+    colour, noise / blurred / hard-edged / striped frames, both flags, thresholds, clamped criteria, points outside the
+    frame -- every tracked point bit-identical to cv2 and every status equal"""
+    import cv2
+    rng = np.random.default_rng(2026)
+    checked = 0
+    for it in range(250):
+        H = int(rng.integers(8, 200)); W = int(rng.integers(8, 260)); cn = int(rng.choice([1, 3]))
+        win = int(rng.integers(3, 22)); lev = int(rng.integers(0, 6)); kind = int(rng.integers(0, 4))
+        shape = (H, W, 3) if cn == 3 else (H, W)
+        if kind == 0:
+            a = rng.integers(0, 256, shape, dtype=np.uint8)
+        elif kind == 1:
+            a = cv2.GaussianBlur(rng.integers(0, 256, shape, dtype=np.uint8), (0, 0), float(rng.uniform(0.6, 3)))
+        elif kind == 2:
+            small = rng.integers(0, 2, ((H + 3) // 4, (W + 3) // 4) + ((3,) if cn == 3 else ()), dtype=np.uint8) * 255
+            a = np.ascontiguousarray(np.repeat(np.repeat(small, 4, 0), 4, 1)[:H, :W])
+        else:
+            a = np.full(shape, int(rng.integers(0, 256)), np.uint8); a[::5] = 255 - a[::5]
+        M = np.float32([[1 + rng.normal(0, 0.01), rng.normal(0, 0.01), rng.normal(0, 2)],
+                        [rng.normal(0, 0.01), 1 + rng.normal(0, 0.01), rng.normal(0, 2)]])
+        b = cv2.warpAffine(a, M, (W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+        if rng.uniform() < 0.5:
+            b = np.clip(b.astype(np.int32) + rng.integers(-4, 5, b.shape), 0, 255).astype(np.uint8)
+        pts = np.stack([rng.uniform(-5, W + 5, 40), rng.uniform(-5, H + 5, 40)], 1).astype(np.float32)
+        flags = int(rng.integers(0, 4)); thr = float(rng.choice([0.0, 1e-4, 1e-3, 0.05]))
+        max_iter = int(rng.choice([0, 1, 5, 30, 100, 150])); eps = float(rng.choice([0.0, 0.01, 0.3, 20.0]))
+        init = (pts + rng.normal(0, 1.5, pts.shape)).astype(np.float32) if flags & 1 else None
+        cvf = (cv2.OPTFLOW_USE_INITIAL_FLOW if flags & 1 else 0) | (cv2.OPTFLOW_LK_GET_MIN_EIGENVALS if flags & 2 else 0)
+        p1, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts.reshape(-1, 1, 2), None if init is None else init.reshape(-1, 1, 2).copy(),
+                                              winSize=(win, win), maxLevel=lev, criteria=(3, max_iter, eps), flags=cvf, minEigThreshold=thr)
+        nxt, ms, me, _ = E.track(a, b, pts, win=win, max_level=lev, max_iter=max_iter, eps=eps, init=init,
+                                 min_eig_err=bool(flags & 2), min_eig_thr=thr)
+        st = st.ravel(); ok = st == 1
+        where = (it, H, W, cn, win, lev, kind, flags)
+        assert np.array_equal(ms, st), where
+        assert np.array_equal(bits(nxt[ok]), bits(p1.reshape(-1, 2)[ok])), where
+        assert np.array_equal(bits(me[ok]), bits(er.ravel()[ok])), where
+        checked += int(ok.sum())
+    assert checked > 3000
