@@ -7,6 +7,7 @@
 #include <iostream>
 #include <memory>
 #include <set>
+#include <unordered_map>
 
 namespace putslam_b200 {
 
@@ -756,6 +757,197 @@ Mat34& KabschEst::computeTransformation(const Eigen::MatrixXd& setA, const Eigen
         for (int row = 0; row < 3; ++row) transformation.m[4 * col + row] = T[3 * col + row];
     return transformation;
 }
+
+// ---- host-side steps of Matcher::trackKLT (see pslam_adapter.h) ------------------------------------------------------
+namespace tracking {
+namespace {
+// cv::norm(Point2f) / the explicit sqrt(u*u + v*v) of the reference: float differences, double arithmetic
+inline bool close2D(const cv::Point2f& a, const cv::Point2f& b, double thr) {
+    const double u = a.x - b.x, v = a.y - b.y;
+    return std::sqrt(u * u + v * v) < thr;
+}
+inline bool close3D(const Eigen::Vector3f& a, const Eigen::Vector3f& b, double thr) {
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return std::sqrt(x * x + y * y + z * z) < thr;
+}
+// Uniform grid over points already seen; cells are 0.1 % wider than the threshold, so two points whose (float-rounded)
+// distance is below the threshold always lie in neighbouring cells.  The grid only proposes candidates -- hash
+// collisions add some, never lose one -- and the caller evaluates the exact predicate.
+template <int DIM>
+struct Grid {
+    bool usable;
+    double inv;
+    std::unordered_map<long long, std::vector<int>> cells;
+    explicit Grid(double thr) : usable(thr > 0 && std::isfinite(thr)), inv(usable ? 1.0 / (thr * 1.001) : 0.0) {}
+    bool cell(const float* p, long long* c) const {
+        for (int d = 0; d < DIM; ++d) {
+            const double q = (double)p[d] * inv;
+            if (!(std::fabs(q) < 1e15)) return false;     // NaN / inf / absurdly far: never close to anything
+            c[d] = (long long)std::floor(q);
+        }
+        return true;
+    }
+    static long long key(const long long* c) {
+        long long k = 0;
+        for (int d = 0; d < DIM; ++d) k = k * 1000003LL + c[d];
+        return k;
+    }
+    void insert(const float* p, int id) {
+        long long c[DIM];
+        if (cell(p, c)) cells[key(c)].push_back(id);
+    }
+    template <typename F>
+    bool any(const float* p, F pred) const {                // pred(id) over all candidates until one holds
+        long long c[DIM], n[DIM];
+        if (!cell(p, c)) return false;
+        const int total = DIM == 2 ? 9 : 27;
+        for (int t = 0; t < total; ++t) {
+            int r = t;
+            for (int d = 0; d < DIM; ++d) { n[d] = c[d] + (r % 3) - 1; r /= 3; }
+            auto it = cells.find(key(n));
+            if (it == cells.end()) continue;
+            for (int id : it->second) if (pred(id)) return true;
+        }
+        return false;
+    }
+};
+template <typename T>
+void compact(std::vector<T>& v, const std::vector<char>& gone) {
+    size_t o = 0;
+    for (size_t i = 0; i < v.size(); ++i) if (!gone[i]) v[o++] = v[i];
+    v.resize(o);
+}
+}  // namespace
+
+std::set<int> removeTooCloseFeatures(std::vector<cv::Point2f>& distortedFeatures2D, std::vector<cv::Point2f>& undistortedFeatures2D,
+                                     std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
+                                     std::vector<double>& detDists, std::vector<cv::DMatch>& matches, double minEuclid,
+                                     double minReproj, bool bruteForce) {
+    std::set<int> featuresToRemove;
+    const size_t n = features3D.size();
+    if (undistortedFeatures2D.size() != n || distortedFeatures2D.size() != n || keyPoints.size() != n || detDists.size() != n) {
+        std::cerr << "putslam_b200: removeTooCloseFeatures: vectors differ in size" << std::endl;
+        return featuresToRemove;
+    }
+    std::vector<char> gone(n, 0);
+    // the grids need finite thresholds and coordinates; anything else (an infinite threshold, NaN / inf / absurdly far
+    // positions) takes the reference's plain double loop
+    Grid<2> g2(minReproj);
+    Grid<3> g3(minEuclid);
+    bool gridOK = !bruteForce && (g2.usable || !(minReproj > 0)) && (g3.usable || !(minEuclid > 0));
+    for (size_t j = 0; gridOK && j < n; ++j) {
+        const float p2[2] = {undistortedFeatures2D[j].x, undistortedFeatures2D[j].y};
+        const float p3[3] = {features3D[j][0], features3D[j][1], features3D[j][2]};
+        long long c[3];
+        gridOK = (!g2.usable || g2.cell(p2, c)) && (!g3.usable || g3.cell(p3, c));
+    }
+    if (!gridOK) {
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = i + 1; j < n; ++j)
+                if (close3D(features3D[i], features3D[j], minEuclid) || close2D(undistortedFeatures2D[i], undistortedFeatures2D[j], minReproj))
+                    gone[j] = 1;
+    } else {
+        for (size_t j = 0; j < n; ++j) {
+            const float p2[2] = {undistortedFeatures2D[j].x, undistortedFeatures2D[j].y};
+            const float p3[3] = {features3D[j][0], features3D[j][1], features3D[j][2]};
+            // every earlier feature counts, removed or not (the reference's loops do not skip removed ones)
+            if (g2.usable && g2.any(p2, [&](int i) { return close2D(undistortedFeatures2D[(size_t)i], undistortedFeatures2D[j], minReproj); })) gone[j] = 1;
+            else if (g3.usable && g3.any(p3, [&](int i) { return close3D(features3D[(size_t)i], features3D[j], minEuclid); })) gone[j] = 1;
+            if (g2.usable) g2.insert(p2, (int)j);
+            if (g3.usable) g3.insert(p3, (int)j);
+        }
+    }
+    for (size_t j = 0; j < n; ++j) if (gone[j]) featuresToRemove.insert((int)j);
+    compact(distortedFeatures2D, gone); compact(undistortedFeatures2D, gone); compact(features3D, gone);
+    compact(keyPoints, gone); compact(detDists, gone);
+    matches.erase(std::remove_if(matches.begin(), matches.end(),
+                                 [&](const cv::DMatch& o) { return featuresToRemove.find(o.trainIdx) != featuresToRemove.end(); }),
+                  matches.end());
+    return featuresToRemove;
+}
+
+void mergeTrackedFeatures(std::vector<cv::Point2f>& undistortedFeatures2D, const std::vector<cv::Point2f>& featuresSandBoxUndistorted,
+                          std::vector<cv::Point2f>& distortedFeatures2D, const std::vector<cv::Point2f>& featuresSandBoxDistorted,
+                          std::vector<Eigen::Vector3f>& features3D, const std::vector<Eigen::Vector3f>& features3DSandBox,
+                          std::vector<cv::KeyPoint>& keyPoints, const std::vector<cv::KeyPoint>& keyPointsSandBox,
+                          std::vector<double>& detDists, const std::vector<double>& detDistsSandBox, double minReproj,
+                          bool bruteForce) {
+    const size_t m = featuresSandBoxUndistorted.size();
+    if (featuresSandBoxDistorted.size() != m || features3DSandBox.size() != m || keyPointsSandBox.size() != m || detDistsSandBox.size() != m) {
+        std::cerr << "putslam_b200: mergeTrackedFeatures: vectors differ in size" << std::endl;
+        return;
+    }
+    Grid<2> g(minReproj);
+    bool grid = !bruteForce && g.usable;
+    long long cc[2];
+    for (size_t j = 0; grid && j < undistortedFeatures2D.size(); ++j) {
+        const float p[2] = {undistortedFeatures2D[j].x, undistortedFeatures2D[j].y};
+        grid = g.cell(p, cc);
+    }
+    for (size_t i = 0; grid && i < m; ++i) {
+        const float p[2] = {featuresSandBoxUndistorted[i].x, featuresSandBoxUndistorted[i].y};
+        grid = g.cell(p, cc);
+    }
+    if (grid)
+        for (size_t j = 0; j < undistortedFeatures2D.size(); ++j) {
+            const float p[2] = {undistortedFeatures2D[j].x, undistortedFeatures2D[j].y};
+            g.insert(p, (int)j);
+        }
+    for (size_t i = 0; i < m; ++i) {
+        const cv::Point2f& c = featuresSandBoxUndistorted[i];
+        const float p[2] = {c.x, c.y};
+        bool addFeature = true;
+        if (grid) {
+            addFeature = !g.any(p, [&](int j) { return close2D(c, undistortedFeatures2D[(size_t)j], minReproj); });
+        } else if (minReproj > 0 || minReproj != minReproj) {   // (a non-positive threshold rejects nothing)
+            for (size_t j = 0; j < undistortedFeatures2D.size(); ++j)
+                if (close2D(c, undistortedFeatures2D[j], minReproj)) { addFeature = false; break; }
+        }
+        if (addFeature) {
+            if (grid) g.insert(p, (int)undistortedFeatures2D.size());
+            undistortedFeatures2D.push_back(c);
+            distortedFeatures2D.push_back(featuresSandBoxDistorted[i]);
+            features3D.push_back(features3DSandBox[i]);
+            keyPoints.push_back(keyPointsSandBox[i]);
+            detDists.push_back(detDistsSandBox[i]);
+        }
+    }
+}
+
+std::vector<cv::KeyPoint> predictDescriptionLevels(std::vector<cv::Point2f>& distortedFeatures2D,
+                                                   std::vector<cv::Point2f>& undistortedFeatures2D,
+                                                   std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
+                                                   std::vector<double>& detDists) {
+    const int nLevels = 8;                                   // Matcher::nLevels (matcher.h:27)
+    std::vector<cv::KeyPoint> descKeyPoints = keyPoints;
+    const size_t n = keyPoints.size();
+    if (distortedFeatures2D.size() != n || undistortedFeatures2D.size() != n || features3D.size() != n || detDists.size() != n) {
+        std::cerr << "putslam_b200: predictDescriptionLevels: vectors differ in size" << std::endl;
+        return descKeyPoints;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        // std::sqrt of a float expression: float arithmetic, float square root, then widened (matcher.cpp:287-290)
+        const float x = features3D[i][0], y = features3D[i][1], z = features3D[i][2];
+        const double curDist = (double)std::sqrt(x * x + y * y + z * z);
+        descKeyPoints[i].octave = predictedLevel(descKeyPoints[i].octave, detDists[i], curDist);
+    }
+    std::vector<size_t> order;
+    order.reserve(n);
+    for (int l = 0; l < nLevels; ++l)
+        for (size_t i = 0; i < n; ++i) if (descKeyPoints[i].octave == l) order.push_back(i);
+    std::vector<cv::Point2f> tmpDistorted, tmpUndistorted;
+    std::vector<Eigen::Vector3f> tmp3D;
+    std::vector<cv::KeyPoint> tmpKeyPoints;
+    std::vector<double> tmpDetDists;
+    for (size_t i : order) {
+        tmpDistorted.push_back(distortedFeatures2D[i]); tmpUndistorted.push_back(undistortedFeatures2D[i]);
+        tmp3D.push_back(features3D[i]); tmpKeyPoints.push_back(keyPoints[i]); tmpDetDists.push_back(detDists[i]);
+    }
+    tmpDistorted.swap(distortedFeatures2D); tmpUndistorted.swap(undistortedFeatures2D); tmp3D.swap(features3D);
+    tmpKeyPoints.swap(keyPoints); tmpDetDists.swap(detDists);
+    return descKeyPoints;
+}
+}  // namespace tracking
 
 const Mat66& TransformEst::uncertaintyImpl(const Eigen::MatrixXd& setA, std::vector<Mat33>& ua, const Eigen::MatrixXd& setB,
                                            std::vector<Mat33>& ub, Mat34& T, int parametrization) {

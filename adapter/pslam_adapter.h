@@ -13,6 +13,7 @@
 // transform + no inliers" / "no matches".  Any C-ABI error is logged to std::cerr and mapped to exactly
 // those values.  There is no CPU fallback.
 #pragma once
+#include <set>
 #include <string>
 #include <utility>
 #include <vector>
@@ -234,6 +235,37 @@ private:
     int minPts_, perCluster_;
     std::vector<int> label_;
 };
+
+// Host-side steps of Matcher::trackKLT around the device calls (src/Matcher/matcher.cpp:96-131,262-322,886-974).  They are
+// sequential, order-dependent list edits on a few hundred features and stay on the host like the reference's; the O(N^2)
+// scans are replaced by uniform-grid neighbour queries that evaluate the reference's exact predicate on the candidates,
+// so the results are identical (tests/test_abi_cpu.py compares them with the brute-force form and a numpy restatement).
+namespace tracking {
+// Matcher::removeTooCloseFeatures (matcher.cpp:886-974): feature j goes when some i < j (removed or not) is closer than
+// minimalEuclidDistance in 3-D or than minimalReprojDistance in the undistorted image; the five vectors are compacted,
+// matches whose trainIdx was removed are erased (trainIdx is NOT renumbered -- as in the reference).  Returns the set.
+std::set<int> removeTooCloseFeatures(std::vector<cv::Point2f>& distortedFeatures2D, std::vector<cv::Point2f>& undistortedFeatures2D,
+                                     std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
+                                     std::vector<double>& detDists, std::vector<cv::DMatch>& matches,
+                                     double minimalEuclidDistanceNewTrackingFeatures, double minimalReprojDistanceNewTrackingFeatures,
+                                     bool bruteForce = false);
+// Matcher::mergeTrackedFeatures (matcher.cpp:96-131): every newly detected feature that is not closer than
+// minimalReprojDistance (undistorted image) to a feature already in the list -- tracked or just added -- is appended.
+void mergeTrackedFeatures(std::vector<cv::Point2f>& undistortedFeatures2D, const std::vector<cv::Point2f>& featuresSandBoxUndistorted,
+                          std::vector<cv::Point2f>& distortedFeatures2D, const std::vector<cv::Point2f>& featuresSandBoxDistorted,
+                          std::vector<Eigen::Vector3f>& features3D, const std::vector<Eigen::Vector3f>& features3DSandBox,
+                          std::vector<cv::KeyPoint>& keyPoints, const std::vector<cv::KeyPoint>& keyPointsSandBox,
+                          std::vector<double>& detDists, const std::vector<double>& detDistsSandBox,
+                          double minimalReprojDistanceNewTrackingFeatures, bool bruteForce = false);
+// matcher.cpp:281-340 up to the describeFeatures call: descKeyPoints = keyPoints with octave := the pyramid level predicted
+// from the detection distance and the current distance (host libm, like the reference), then all vectors regrouped by that
+// level, stably.  Returns descKeyPoints in the ORIGINAL order, as the reference holds it at that point: describeFeatures
+// (cv::ORB::compute) regroups it by octave itself, which is exactly the order the five vectors were just given.
+std::vector<cv::KeyPoint> predictDescriptionLevels(std::vector<cv::Point2f>& distortedFeatures2D,
+                                                   std::vector<cv::Point2f>& undistortedFeatures2D,
+                                                   std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
+                                                   std::vector<double>& detDists);
+}  // namespace tracking
 
 // putslam::TransformEst / KabschEst (transformEst.h:16-26, kabschEst.h:21-41).  Mat34 is
 // Eigen::Transform<double,3,Affine>; its 4x4 column-major matrix is exposed here as double[16].

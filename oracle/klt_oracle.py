@@ -168,3 +168,52 @@ def perform_tracking(err, status, pts, error_threshold, min_distance):
             else:
                 remove[j] = True
     return np.nonzero((st != 0) & ~remove)[0]
+
+
+# ---- the host-side list edits of Matcher::trackKLT ------------------------------------------------------------------
+def remove_too_close(und, xyz, min_euclid, min_reproj):
+    """Matcher::removeTooCloseFeatures (src/Matcher/matcher.cpp:886-974): feature j is removed when some i < j (removed or
+    not) is closer than min_euclid in 3-D or than min_reproj in the undistorted image; float differences, double norms.
+    -> sorted indices removed"""
+    und = np.asarray(und, np.float32).reshape(-1, 2); xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    gone = np.zeros(len(und), bool)
+    for i in range(len(und)):
+        d3 = (xyz[i] - xyz[i + 1:]).astype(np.float64); d2 = (und[i] - und[i + 1:]).astype(np.float64)
+        dist3 = np.sqrt(d3[:, 0] * d3[:, 0] + d3[:, 1] * d3[:, 1] + d3[:, 2] * d3[:, 2])
+        dist2 = np.sqrt(d2[:, 0] * d2[:, 0] + d2[:, 1] * d2[:, 1])
+        gone[i + 1:] |= (dist3 < min_euclid) | (dist2 < min_reproj)
+    return np.nonzero(gone)[0]
+
+
+def merge_tracked(und, sandbox_und, min_reproj):
+    """Matcher::mergeTrackedFeatures (matcher.cpp:96-131): a newly detected feature is appended unless some feature already
+    in the list (tracked, or appended before it) is closer than min_reproj in the undistorted image.
+    -> indices of the sandbox features appended, in order"""
+    cur = [np.asarray(p, np.float32) for p in np.asarray(und, np.float32).reshape(-1, 2)]
+    added = []
+    for i, c in enumerate(np.asarray(sandbox_und, np.float32).reshape(-1, 2)):
+        if cur:
+            d = (c - np.array(cur, np.float32)).astype(np.float64)
+            if (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < min_reproj).any():
+                continue
+        cur.append(c); added.append(i)
+    return np.array(added, np.int64)
+
+
+def predict_description_levels(xyz, octave, det_dist, scale_factor=1.2, n_levels=8):
+    """matcher.cpp:281-322: level = clamp(ceil(log(scale^octave * detDist / |p|) / log(scale)), 0, n_levels - 1) with |p| a
+    float norm ((x*x + y*y) + z*z, float square root), everything else double with the C library's pow / log -- and the
+    stable regrouping by that level.  -> (levels per original index, order = original indices level by level)"""
+    import math
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    lv = np.zeros(len(xyz), np.int32)
+    for i, (p, o, d) in enumerate(zip(xyz, octave, det_dist)):
+        cur = float(np.sqrt(f32(f32(f32(p[0] * p[0]) + f32(p[1] * p[1])) + f32(p[2] * p[2]))))
+        with np.errstate(all="ignore"):
+            s = np.float64(math.pow(scale_factor, int(o))) * np.float64(d) / np.float64(cur)
+            v = np.ceil(np.log(s) / math.log(scale_factor))
+        # (int) of a NaN / out-of-range double is undefined in C; x86-64 yields INT_MIN, which the clamps turn into 0
+        c = int(v) if np.isfinite(v) and abs(v) < 2 ** 31 else -2 ** 31
+        lv[i] = min(n_levels - 1, max(0, c))
+    order = np.concatenate([np.nonzero(lv == l)[0] for l in range(n_levels)]) if len(lv) else np.zeros(0, np.int64)
+    return lv, order

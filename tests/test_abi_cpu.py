@@ -2,6 +2,7 @@
 without a GPU (no CPU fallback), and its host-only entry points agree with the oracle."""
 import ctypes as C
 import os
+import subprocess
 import re
 
 import numpy as np
@@ -113,3 +114,92 @@ def test_dbscan_against_the_reference_build(tmp_path):
             assert np.array_equal(got, kept[:m]), (trial, eps, min_pts, per)
             n_removed += n - m
     assert n_removed > 1000          # the de-clustering really removed keypoints
+
+
+def _tracking_cli(tmp_path, arrays, *args):
+    cli = os.path.join(ROOT, "adapter", "tracking_cli")
+    assert os.path.exists(cli), "adapter/tracking_cli not built (run __graft_entry__.build())"
+    d = str(tmp_path)
+    for name, (arr, dt) in arrays.items():
+        np.ascontiguousarray(arr, dt).tofile(os.path.join(d, name + ".bin"))
+    subprocess.check_call([cli, d] + [str(a) for a in args])
+    return lambda name, dt: np.fromfile(os.path.join(d, name + ".bin"), dt)
+
+
+def _tracked_lists(rng, n, spread):
+    und = rng.uniform(0, spread, (n, 2)).astype(np.float32)
+    if n > 20:
+        und[5] = und[3]; und[9] = und[3] + np.float32(0.5); und[n - 1] = und[0]          # exact and near duplicates
+    dist = (und + rng.normal(0, 0.3, und.shape)).astype(np.float32)
+    z = rng.uniform(0.8, 5.0, n)
+    xyz = np.stack([(und[:, 0] - spread / 2) / 500.0 * z, (und[:, 1] - spread / 2) / 500.0 * z, z], 1).astype(np.float32)
+    octv = rng.integers(0, 8, n).astype(np.int32)
+    det = rng.uniform(0.5, 6.0, n)
+    return und, dist, xyz, octv, det
+
+
+def test_tracking_remove_too_close_matches_the_reference_rule(tmp_path):
+    """putslam_b200::tracking::removeTooCloseFeatures (grid-accelerated and brute-force) against the numpy restatement of
+    Matcher::removeTooCloseFeatures (src/Matcher/matcher.cpp:886-974): same removed set, same compacted lists, matches
+    erased by trainIdx without renumbering"""
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(41)
+    for n, spread, e3, r2 in ((400, 120.0, 0.01, 3.0), (300, 60.0, 0.05, 1.0), (200, 500.0, 0.0, 0.0), (50, 30.0, 1e9, 2.0),
+                              (0, 10.0, 0.01, 3.0), (120, 40.0, 0.02, float("inf"))):
+        und, dist, xyz, octv, det = _tracked_lists(rng, n, spread)
+        matches = np.stack([rng.integers(0, 1000, n), rng.permutation(n)], 1).astype(np.int32) if n else np.zeros((0, 2), np.int32)
+        gone = K.remove_too_close(und, xyz, e3, r2)
+        keep = np.setdiff1d(np.arange(n), gone)
+        for brute in (0, 1):
+            rd = _tracking_cli(tmp_path, {"und": (und, np.float32), "dist": (dist, np.float32), "xyz": (xyz, np.float32),
+                                          "oct": (octv, np.int32), "det": (det, np.float64), "matches": (matches, np.int32)},
+                               "remove", repr(e3), repr(r2), brute)
+            assert np.array_equal(rd("removed", np.int32), gone), (n, brute)
+            assert np.array_equal(rd("id", np.int32), keep), (n, brute)
+            rows = rd("rows", np.float32).reshape(-1, 8)
+            assert np.array_equal(rows[:, :2], und[keep]) and np.array_equal(rows[:, 2:4], dist[keep]) and np.array_equal(rows[:, 4:7], xyz[keep])
+            assert np.array_equal(rd("matches_out", np.int32).reshape(-1, 2), matches[~np.isin(matches[:, 1], gone)]), (n, brute)
+        if n >= 200 and r2 > 0:
+            assert 0 < len(gone) < n
+
+
+def test_tracking_merge_matches_the_reference_rule(tmp_path):
+    """mergeTrackedFeatures (matcher.cpp:96-131): greedy, order-dependent -- a rejected candidate does not block later ones,
+    an accepted one does"""
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(43)
+    for n, m, spread, thr in ((150, 500, 200.0, 3.0), (0, 300, 60.0, 5.0), (100, 0, 50.0, 3.0), (80, 200, 100.0, 0.0), (60, 400, 30.0, 2.5),
+                              (40, 60, 50.0, float("inf"))):
+        und, dist, xyz, octv, det = _tracked_lists(rng, n, spread)
+        s_und, s_dist, s_xyz, s_oct, s_det = _tracked_lists(rng, m, spread)
+        if m > 10 and n > 10:
+            s_und[2] = und[1]                                                          # on top of a tracked feature
+            s_und[4] = s_und[3] + np.float32(0.25)                                     # next to an earlier candidate
+        added = K.merge_tracked(und, s_und, thr)
+        for brute in (0, 1):
+            rd = _tracking_cli(tmp_path, {"und": (und, np.float32), "dist": (dist, np.float32), "xyz": (xyz, np.float32),
+                                          "oct": (octv, np.int32), "det": (det, np.float64), "s_und": (s_und, np.float32),
+                                          "s_dist": (s_dist, np.float32), "s_xyz": (s_xyz, np.float32), "s_oct": (s_oct, np.int32),
+                                          "s_det": (s_det, np.float64)}, "merge", repr(thr), brute)
+            assert np.array_equal(rd("id", np.int32), np.concatenate([np.arange(n), n + added])), (n, m, brute)
+            rows = rd("rows", np.float32).reshape(-1, 8)
+            assert np.array_equal(rows[n:, :2], s_und[added]) and np.array_equal(rows[n:, 4:7], s_xyz[added])
+        if m >= 200 and thr > 0:
+            assert 0 < len(added) < m
+        if thr == float("inf"):
+            assert len(added) == 0
+
+
+def test_tracking_description_levels_match_the_reference_rule(tmp_path):
+    """matcher.cpp:281-322: predicted pyramid level (host libm) and the stable regrouping by level"""
+    from oracle import klt_oracle as K
+    rng = np.random.default_rng(44)
+    und, dist, xyz, octv, det = _tracked_lists(rng, 500, 300.0)
+    det[:50] = np.sqrt((xyz[:50].astype(np.float64) ** 2).sum(1))                      # ratio 1: ceil(log(1.2^k)/log(1.2)) is ulp-sensitive
+    det[50] = 0.0; xyz[51] = 0.0                                                       # log(0), division by zero
+    lv, order = K.predict_description_levels(xyz, octv, det)
+    rd = _tracking_cli(tmp_path, {"und": (und, np.float32), "dist": (dist, np.float32), "xyz": (xyz, np.float32),
+                                  "oct": (octv, np.int32), "det": (det, np.float64)}, "levels")
+    assert np.array_equal(rd("desc_oct", np.int32), lv)
+    assert np.array_equal(rd("id", np.int32), order)
+    assert len(np.unique(lv)) == 8
