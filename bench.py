@@ -314,6 +314,27 @@ def klt_numbers(ctx, steps, warmup):
     for i in range(steps):
         ctx.klt_track(None, seq[i % 2], pts, **kw)
     res["e2e_ms_per_frame_previous_resident"] = (time.perf_counter() - t0) / steps * 1e3
+    # the whole tracking branch of Matcher::trackKLT as one submission (pslam_klt_frame): track -> threshold / too-close
+    # rule -> undistort + back-project the survivors -> RANSAC against the previous frame's 3-D points (adaptive, the
+    # reference's bound); the frames show a wall 2 m away sliding by (2, 1) px, so the motion is rigid
+    try:
+        from putslam_b200 import api
+        depth = (10000 + rng.integers(-3, 4, (480, 640))).astype(np.uint16)
+        cam = api.make_camera()
+        first = ctx.frame_to_frame(None, None, np.zeros((n, 32), np.uint8), pts, depth, cam=cam, undistort=True)
+        prev_xyz = first["xyz"]
+        ctx.klt_track(f0, f1, pts, **kw)
+        for i in range(warmup):
+            fr = ctx.klt_frame(None, seq[i % 2], pts, prev_xyz, depth, cam=cam, undistort=True, seed=i)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fr = ctx.klt_frame(None, seq[i % 2], pts, prev_xyz, depth, cam=cam, undistort=True, seed=i)
+        res["fused_frame"] = {"e2e_ms_per_frame_previous_resident": (time.perf_counter() - t0) / steps * 1e3,
+                              "survivors": int(fr["kept"].size), "inliers": int(fr["inliers"].size),
+                              "h2d_bytes": int(f0.size + depth.nbytes + 20 * n),
+                              "what": "pslam_klt_frame: performTracking + removeImageDistortion + keypoints2Dto3D + RANSAC"}
+    except Exception as e:  # noqa: BLE001
+        res["fused_frame"] = {"error": f"{type(e).__name__}: {e}"}
     try:
         import cv2
         crit = (cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01)

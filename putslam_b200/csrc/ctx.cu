@@ -1368,7 +1368,7 @@ int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row
     // corners after non-max suppression: strict 3x3 maxima, so at most one per 2x2 block of any level
     const int ccap = (int)(P.row_floats / 4 + 64);
     const int first = 12288;                  // records fetched with the header; the rest only if there are more
-    Arena in, out, work;
+    Arena out, work;
     const size_t img_bytes = (size_t)channels * W * H;
     const size_t o_hdr = out.take(16), o_cand = out.take(24 * (size_t)ccap);
     const size_t o_plain = work.take(P.plain_bytes), o_score = work.take(P.row_floats);
