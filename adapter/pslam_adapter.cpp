@@ -984,6 +984,19 @@ const Mat66& TransformEst::computeUncertaintyG2O(const Eigen::MatrixXd& setA, st
     return uncertaintyImpl(setA, setAUncertainty, setB, setBUncertainty, T, PSLAM_UNCERTAINTY_QUATERNION);
 }
 
+const Mat66& TransformEst::computeUncertaintyStrasdat(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB, Mat34& T) {
+    uncertainty.setZero();
+    for (int i = 0; i < 6; ++i) uncertainty.m[7 * i] = 1.0;
+    double depthAv = 0;
+    for (long i = 0; i < (long)setA.rows(); ++i) {
+        depthAv += std::sqrt(std::pow(setA(i, 0), 2.0) + std::pow(setA(i, 1), 2.0) + std::pow(setA(i, 2), 2.0));
+        depthAv += std::sqrt(std::pow(setB(i, 0), 2.0) + std::pow(setB(i, 1), 2.0) + std::pow(setB(i, 2), 2.0));
+    }
+    depthAv /= 2 * (double)setA.rows();
+    for (int k = 0; k < 3; ++k) uncertainty.m[7 * k] = std::pow(T(k, 3) / depthAv, 2.0);
+    return uncertainty;
+}
+
 static std::unique_ptr<KabschEst> kabsch;
 TransformEst* createKabschEstimator(void) {
     kabsch.reset(new KabschEst());

@@ -300,6 +300,9 @@ public:
     // transformEst.h:147-272: the same over (x, y, z, qx, qy, qz)
     virtual const Mat66& computeUncertaintyG2O(const Eigen::MatrixXd& setA, std::vector<Mat33>& setAUncertainty,
                                                const Eigen::MatrixXd& setB, std::vector<Mat33>& setBUncertainty, Mat34& transformation);
+    // transformEst.h:343-356 (demoKabsch.cpp:351,438): identity with (t / mean point distance)^2 on the translation
+    // diagonal.  A 2n-term host sum -- there is nothing to offload.
+    virtual const Mat66& computeUncertaintyStrasdat(const Eigen::MatrixXd& setA, const Eigen::MatrixXd& setB, Mat34& transformation);
 protected:
     Mat34 transformation;
     Mat66 uncertainty;

@@ -4,6 +4,7 @@
 // usage: tracking_cli <dir> remove <minEuclid> <minReproj> <brute 0|1>
 //        tracking_cli <dir> merge  <minReproj> <brute 0|1>
 //        tracking_cli <dir> levels
+//        tracking_cli <dir> strasdat      (TransformEst::computeUncertaintyStrasdat, host arithmetic)
 // inputs (float32 unless noted): und.bin n x 2, dist.bin n x 2, xyz.bin n x 3, oct.bin int32 n, det.bin float64 n,
 // matches.bin int32 m x 2 (remove), s_und.bin / s_dist.bin / s_xyz.bin / s_oct.bin / s_det.bin (merge);
 // outputs: id.bin (int32: original index of every surviving / appended feature, sandbox features numbered from n),
@@ -72,6 +73,20 @@ int main(int argc, char** argv) {
     if (argc < 3) { std::cerr << "usage: tracking_cli <dir> remove|merge|levels ..." << std::endl; return 2; }
     g_dir = argv[1];
     const std::string op = argv[2];
+    if (op == "strasdat") {   // A.bin, B.bin: n x 3 float64 row-major; T.bin: 4 x 4 float64 row-major -> U.bin 6 x 6 row-major
+        auto A = rd<double>("A.bin"), B = rd<double>("B.bin"), T = rd<double>("T.bin");
+        const long n = (long)(A.size() / 3);
+        Eigen::MatrixXd setA(n, 3), setB(n, 3);
+        for (long r = 0; r < n; ++r) for (int c = 0; c < 3; ++c) { setA(r, c) = A[3 * r + c]; setB(r, c) = B[3 * r + c]; }
+        Mat34 trans;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) trans.m[4 * j + i] = T[4 * i + j];
+        KabschEst est;
+        const Mat66& u = est.computeUncertaintyStrasdat(setA, setB, trans);
+        std::vector<double> out(36);
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[6 * i + j] = u(i, j);
+        wr("U.bin", out);
+        return 0;
+    }
     Lists L = load("", 0);
     if (op == "remove" && argc >= 6) {
         auto mm = rd<int>("matches.bin");

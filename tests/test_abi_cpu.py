@@ -203,3 +203,16 @@ def test_tracking_description_levels_match_the_reference_rule(tmp_path):
     assert np.array_equal(rd("desc_oct", np.int32), lv)
     assert np.array_equal(rd("id", np.int32), order)
     assert len(np.unique(lv)) == 8
+
+
+def test_uncertainty_strasdat_host_rule(tmp_path):
+    """TransformEst::computeUncertaintyStrasdat (include/putslam/TransformEst/transformEst.h:343-356): identity with
+    (t_k / mean point distance over both sets)^2 on the translation diagonal"""
+    rng = np.random.default_rng(47)
+    A = rng.uniform(-2, 2, (60, 3)); B = rng.uniform(-2, 2, (60, 3))
+    T = np.eye(4); T[:3, 3] = [0.3, -0.2, 0.05]
+    rd = _tracking_cli(tmp_path, {"A": (A, np.float64), "B": (B, np.float64), "T": (T, np.float64)}, "strasdat")
+    U = rd("U", np.float64).reshape(6, 6)
+    depth = (np.sqrt((A * A).sum(1)).sum() + np.sqrt((B * B).sum(1)).sum()) / (2 * len(A))
+    ref = np.eye(6); ref[[0, 1, 2], [0, 1, 2]] = (T[:3, 3] / depth) ** 2
+    assert np.allclose(U, ref, rtol=1e-13, atol=0)
