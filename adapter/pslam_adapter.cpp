@@ -812,6 +812,13 @@ struct Grid {
     }
 };
 template <typename T>
+void permute(std::vector<T>& v, const std::vector<size_t>& order) {   // v := v[order]
+    std::vector<T> out;
+    out.reserve(order.size());
+    for (size_t i : order) out.push_back(v[i]);
+    v.swap(out);
+}
+template <typename T>
 void compact(std::vector<T>& v, const std::vector<char>& gone) {
     size_t o = 0;
     for (size_t i = 0; i < v.size(); ++i) if (!gone[i]) v[o++] = v[i];
@@ -935,16 +942,8 @@ std::vector<cv::KeyPoint> predictDescriptionLevels(std::vector<cv::Point2f>& dis
     order.reserve(n);
     for (int l = 0; l < nLevels; ++l)
         for (size_t i = 0; i < n; ++i) if (descKeyPoints[i].octave == l) order.push_back(i);
-    std::vector<cv::Point2f> tmpDistorted, tmpUndistorted;
-    std::vector<Eigen::Vector3f> tmp3D;
-    std::vector<cv::KeyPoint> tmpKeyPoints;
-    std::vector<double> tmpDetDists;
-    for (size_t i : order) {
-        tmpDistorted.push_back(distortedFeatures2D[i]); tmpUndistorted.push_back(undistortedFeatures2D[i]);
-        tmp3D.push_back(features3D[i]); tmpKeyPoints.push_back(keyPoints[i]); tmpDetDists.push_back(detDists[i]);
-    }
-    tmpDistorted.swap(distortedFeatures2D); tmpUndistorted.swap(undistortedFeatures2D); tmp3D.swap(features3D);
-    tmpKeyPoints.swap(keyPoints); tmpDetDists.swap(detDists);
+    permute(distortedFeatures2D, order); permute(undistortedFeatures2D, order); permute(features3D, order);
+    permute(keyPoints, order); permute(detDists, order);
     return descKeyPoints;
 }
 }  // namespace tracking
