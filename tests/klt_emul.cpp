@@ -70,3 +70,6 @@ extern "C" int klt_emul_prune(const float* xy, const float* err, const uint8_t* 
     }
     return 0;
 }
+
+// shared-memory bytes one warp needs (launch_klt_track sizes its CTAs with this)
+extern "C" int klt_emul_work_bytes(int win, int cn) { return (int)klt_work_bytes(win, cn); }

@@ -110,3 +110,13 @@ def test_klt_kernel_source_fuzz_against_live_cv2():
         assert np.array_equal(bits(me[ok]), bits(er.ravel()[ok])), where
         checked += int(ok.sum())
     assert checked > 3000
+
+
+def test_klt_workspace_fits_the_default_shared_memory_for_every_supported_window():
+    """launch_klt_track gives every warp klt_work_bytes(win, cn) of shared memory and fails above 48 KB per CTA: the whole
+    supported range (window 3 .. 21, 1 or 3 channels) must fit with at least one warp; the reference's 7 x 7 x 3 with four"""
+    L = E.load()
+    for cn in (1, 3):
+        for win in range(3, 22):
+            assert L.klt_emul_work_bytes(win, cn) <= 48 * 1024, (win, cn)
+    assert 4 * L.klt_emul_work_bytes(7, 3) <= 48 * 1024
