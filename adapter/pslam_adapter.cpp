@@ -946,6 +946,22 @@ std::vector<cv::KeyPoint> predictDescriptionLevels(std::vector<cv::Point2f>& dis
     permute(keyPoints, order); permute(detDists, order);
     return descKeyPoints;
 }
+
+void dropUndescribed(const std::vector<cv::KeyPoint>& descKeyPoints, std::vector<cv::Point2f>& distortedFeatures2D,
+                     std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
+                     std::vector<cv::KeyPoint>& keyPoints, std::vector<double>& detDists) {
+    const size_t n = keyPoints.size();
+    if (descKeyPoints.size() == n) return;                   // matcher.cpp:342
+    if (distortedFeatures2D.size() != n || undistortedFeatures2D.size() != n || features3D.size() != n || detDists.size() != n) {
+        std::cerr << "putslam_b200: dropUndescribed: vectors differ in size" << std::endl;
+        return;
+    }
+    std::vector<char> gone(n, 1);
+    for (size_t i = 0, j = 0; i < n && j < descKeyPoints.size(); ++i)
+        if (close2D(keyPoints[i].pt, descKeyPoints[j].pt, 0.0001)) { gone[i] = 0; ++j; }
+    compact(distortedFeatures2D, gone); compact(undistortedFeatures2D, gone); compact(features3D, gone);
+    compact(keyPoints, gone); compact(detDists, gone);
+}
 }  // namespace tracking
 
 const Mat66& TransformEst::uncertaintyImpl(const Eigen::MatrixXd& setA, std::vector<Mat33>& ua, const Eigen::MatrixXd& setB,

@@ -265,6 +265,12 @@ std::vector<cv::KeyPoint> predictDescriptionLevels(std::vector<cv::Point2f>& dis
                                                    std::vector<cv::Point2f>& undistortedFeatures2D,
                                                    std::vector<Eigen::Vector3f>& features3D, std::vector<cv::KeyPoint>& keyPoints,
                                                    std::vector<double>& detDists);
+// matcher.cpp:341-380, the "unlucky case" after describeFeatures: cv::ORB::compute drops key points too close to the border,
+// so descKeyPoints may have come back shorter; the five vectors keep exactly the features whose position still appears
+// in descKeyPoints (sequential two-pointer walk, |pt - pt| < 0.0001 as in the reference).  No-op when nothing was dropped.
+void dropUndescribed(const std::vector<cv::KeyPoint>& descKeyPoints, std::vector<cv::Point2f>& distortedFeatures2D,
+                     std::vector<cv::Point2f>& undistortedFeatures2D, std::vector<Eigen::Vector3f>& features3D,
+                     std::vector<cv::KeyPoint>& keyPoints, std::vector<double>& detDists);
 }  // namespace tracking
 
 // putslam::TransformEst / KabschEst (transformEst.h:16-26, kabschEst.h:21-41).  Mat34 is

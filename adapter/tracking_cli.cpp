@@ -4,6 +4,7 @@
 // usage: tracking_cli <dir> remove <minEuclid> <minReproj> <brute 0|1>
 //        tracking_cli <dir> merge  <minReproj> <brute 0|1>
 //        tracking_cli <dir> levels
+//        tracking_cli <dir> undescribed   (the features whose key point survived describeFeatures)
 //        tracking_cli <dir> strasdat      (TransformEst::computeUncertaintyStrasdat, host arithmetic)
 // inputs (float32 unless noted): und.bin n x 2, dist.bin n x 2, xyz.bin n x 3, oct.bin int32 n, det.bin float64 n,
 // matches.bin int32 m x 2 (remove), s_und.bin / s_dist.bin / s_xyz.bin / s_oct.bin / s_det.bin (merge);
@@ -110,6 +111,13 @@ int main(int argc, char** argv) {
         std::vector<int> oc;
         for (const cv::KeyPoint& k : desc) oc.push_back(k.octave);
         wr("desc_oct.bin", oc);
+        return dump(L);
+    }
+    if (op == "undescribed") {   // desc_xy.bin: positions of the key points describeFeatures returned (m x 2 float32)
+        auto dxy = rd<float>("desc_xy.bin");
+        std::vector<cv::KeyPoint> desc(dxy.size() / 2);
+        for (size_t j = 0; j < desc.size(); ++j) desc[j].pt = cv::Point2f(dxy[2 * j], dxy[2 * j + 1]);
+        tracking::dropUndescribed(desc, L.dist, L.und, L.xyz, L.kp, L.det);
         return dump(L);
     }
     std::cerr << "bad arguments" << std::endl;

@@ -216,3 +216,27 @@ def test_uncertainty_strasdat_host_rule(tmp_path):
     depth = (np.sqrt((A * A).sum(1)).sum() + np.sqrt((B * B).sum(1)).sum()) / (2 * len(A))
     ref = np.eye(6); ref[[0, 1, 2], [0, 1, 2]] = (T[:3, 3] / depth) ** 2
     assert np.allclose(U, ref, rtol=1e-13, atol=0)
+
+
+def test_tracking_drop_undescribed_matches_the_reference_walk(tmp_path):
+    """matcher.cpp:341-380: after cv::ORB::compute dropped border key points the feature lists keep the features whose
+    position is still present -- a sequential two-pointer walk, so a dropped duplicate position keeps the FIRST of the two"""
+    rng = np.random.default_rng(48)
+    und, dist, xyz, octv, det = _tracked_lists(rng, 300, 200.0)
+    dist[7] = dist[6]                                                                  # same key-point position twice
+    kept = np.sort(rng.choice(300, 240, replace=False))
+    kept = kept[kept != 7]                                                             # the second of the pair was dropped
+    if 6 not in kept: kept = np.sort(np.append(kept, 6))
+    rd = _tracking_cli(tmp_path, {"und": (und, np.float32), "dist": (dist, np.float32), "xyz": (xyz, np.float32),
+                                  "oct": (octv, np.int32), "det": (det, np.float64), "desc_xy": (dist[kept], np.float32)}, "undescribed")
+    # restatement of the walk
+    exp, j = [], 0
+    for i in range(300):
+        if j == len(kept): break
+        d = dist[i].astype(np.float32) - dist[kept[j]].astype(np.float32)
+        if np.sqrt(float(d[0]) ** 2 + float(d[1]) ** 2) < 0.0001:
+            exp.append(i); j += 1
+    assert np.array_equal(rd("id", np.int32), exp) and np.array_equal(exp, kept)
+    # nothing dropped: untouched
+    rd = _tracking_cli(tmp_path, {"desc_xy": (dist, np.float32)}, "undescribed")
+    assert np.array_equal(rd("id", np.int32), np.arange(300))
