@@ -139,6 +139,9 @@ KLT_HD int klt_round(float v) {       // cvRound: nearest, ties to even
     return (int)lrintf(v);
 #endif
 }
+// cvFloor.  A NaN coordinate must end up outside every image, as it does in OpenCV (its conversion yields INT_MIN); the C
+// cast of a NaN is undefined on the host and 0 on the device.  Values beyond the int range are out of the image either way.
+KLT_HD int klt_floor(float v) { return v != v ? (int)0x80000000 : (int)floorf(v); }
 KLT_HD int klt_descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
 // cv::pyrDown, 8-bit: 5 x 5 kernel [1 4 6 4 1] (x) [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8; integer, so the
@@ -263,7 +266,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
         }
         nxx = nx; nxy = ny;
         px = px - half; py = py - half;
-        const int ix = (int)floorf(px), iy = (int)floorf(py);
+        const int ix = klt_floor(px), iy = klt_floor(py);
         if (ix < -win || ix >= w || iy < -win || iy >= h) {
             if (level == 0) { status = 0; err = 0.f; }
             continue;
@@ -333,7 +336,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
         nx = nx - half; ny = ny - half;
         float pdx = 0.f, pdy = 0.f;
         for (int j = 0; j < P.max_iter; ++j) {
-            const int jx = (int)floorf(nx), jy = (int)floorf(ny);
+            const int jx = klt_floor(nx), jy = klt_floor(ny);
             if (jx < -win || jx >= w || jy < -win || jy >= h) {
                 if (level == 0) status = 0;
                 break;
@@ -387,7 +390,7 @@ KLT_HD void klt_track_point(const KltParams& P, const KltWork& W, float ptx, flo
         if (status && level == 0 && !P.min_eig_err) {
             // err = mean |J - I| over the window at the final position, in 1/32 grey levels -> grey levels
             const float qx = nxx - half, qy = nxy - half;
-            const int jx = (int)floorf(qx), jy = (int)floorf(qy);
+            const int jx = klt_floor(qx), jy = klt_floor(qy);
             if (jx < -win || jx >= w || jy < -win || jy >= h) { status = 0; continue; }
             const KltWeights wj = klt_weights(qx - (float)jx, qy - (float)jy);
             KLT_LANES_BEGIN

@@ -120,3 +120,22 @@ def test_klt_workspace_fits_the_default_shared_memory_for_every_supported_window
         for win in range(3, 22):
             assert L.klt_emul_work_bytes(win, cn) <= 48 * 1024, (win, cn)
     assert 4 * L.klt_emul_work_bytes(7, 3) <= 48 * 1024
+
+
+def test_klt_kernel_source_non_finite_points_are_lost_like_in_cv2():
+    """NaN / infinite / absurdly large positions and initial guesses: status 0 and err 0, as cv2 reports them (its float ->
+    int conversion puts them outside every image; klt_floor does the same on host and device)"""
+    import cv2
+    rng = np.random.default_rng(1)
+    a = cv2.GaussianBlur(rng.integers(0, 256, (60, 80, 3), dtype=np.uint8), (0, 0), 1.5); b = np.roll(a, 1, 1)
+    pts = np.array([[np.nan, 10], [20, np.nan], [np.inf, 5], [-np.inf, 5], [1e30, 1e30], [-1e30, 3], [30, 30]], np.float32)
+    crit = (3, 30, 0.01)
+    _, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts.reshape(-1, 1, 2), None, winSize=(7, 7), maxLevel=3, criteria=crit)
+    _, s, e, _ = E.track(a, b, pts)
+    assert np.array_equal(s, st.ravel()) and s.tolist() == [0, 0, 0, 0, 0, 0, 1] and np.array_equal(bits(e), bits(er.ravel()))
+    init = pts.copy(); init[6] = [np.nan, np.nan]
+    good = np.tile(np.float32([[30, 30]]), (7, 1))
+    _, st, _ = cv2.calcOpticalFlowPyrLK(a, b, good.reshape(-1, 1, 2), init.reshape(-1, 1, 2).copy(), winSize=(7, 7), maxLevel=3,
+                                        criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+    _, s, _, _ = E.track(a, b, good, init=init)
+    assert np.array_equal(s, st.ravel()) and not s.any()
