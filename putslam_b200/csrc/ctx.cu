@@ -1389,7 +1389,9 @@ int pslam_orb_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int row
                          prep_slots(ctx), epoch, ctx->sm_count, ctx->stream, &l));
     ctx->launches += l;
     ctx->f2m.valid = false; ctx->f2f.valid = false;
-    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, o_cand + 24 * (size_t)first, cudaMemcpyDeviceToHost, ctx->stream));
+    // the buffers hold ccap records: a small image (ccap < first) must not fetch past them
+    const int head_recs = first < ccap ? first : ccap;
+    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, o_cand + 24 * (size_t)head_recs, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int found = *(const int*)(ctx->h_out.p + o_hdr);
     if (found > ccap)
@@ -1462,6 +1464,8 @@ int pslam_fast_detect(pslam_ctx* ctx, const uint8_t* image, int W, int H, int ro
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, head, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int found = *(const int*)(ctx->h_out.p + o_hdr);
+    if (found > ccap)
+        return fail(ctx, PSLAM_ERR_CAPACITY, "pslam_fast_detect: %d corners after suppression, device buffer holds %d", found, ccap);
     if (found > first) {
         CK(cudaMemcpyAsync(ctx->h_out.p + head, ctx->d_out.p + head, 24 * (size_t)(found - first), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));

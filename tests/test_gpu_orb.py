@@ -230,3 +230,31 @@ def test_pixels_to_matches_pipeline(ctx):
     shift = xb[mt] - xa[mq]
     good = (np.abs(shift[:, 0] - dx) < 2.5) & (np.abs(shift[:, 1] - dy) < 2.5)
     assert mq.size > 150 and good.mean() > 0.6, (mq.size, good.mean())
+
+
+@pytest.mark.parametrize("W,H", [(100, 100), (88, 72), (80, 60)])
+def test_orb_and_fast_detect_small_image_first_call_on_a_fresh_context(W, H):
+    """A small image as the FIRST call of a context: the candidate buffers hold fewer records than the fixed first
+    read-back chunk, which must be clamped (a detectFeatures grid cell such as 80x60 takes this path)."""
+    import cv2
+    from putslam_b200 import api
+    rng = np.random.default_rng(W * H)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (H, W), dtype=np.uint8), (0, 0), 1.2)
+    img = cv2.normalize(img, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
+    for which in ("orb", "fast"):
+        fresh = api.Context(0)
+        try:
+            if which == "orb":
+                out = fresh.orb_detect(img, 200)
+                ref = cv2.ORB_create(nfeatures=200).detect(img)
+                kp, octave = _rows(out)
+                rk = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in ref], np.float32).reshape(-1, 5)
+                assert np.array_equal(octave, np.array([k.octave for k in ref], octave.dtype))
+                assert np.array_equal(kp.view(np.uint32), rk.view(np.uint32))
+            else:
+                xy, resp = fresh.fast_detect(img, 10)
+                ref = cv2.FastFeatureDetector_create(10, True).detect(img)
+                assert np.array_equal(xy, np.array([k.pt for k in ref], np.float32).reshape(-1, 2))
+                assert np.array_equal(resp, np.array([k.response for k in ref], np.float32))
+        finally:
+            fresh.close()
