@@ -23,6 +23,9 @@
 //   SHIM_JACOBI_THRESHOLD32 0 (default): 3.3 sweep threshold max(considerAsZero, 2 eps * maxDiagEntry) with the input
 //                           scaled by its largest coefficient.  1: Eigen 3.2 (no scaling, threshold 2 eps *
 //                           max(|w_pp|, |w_qq|)).
+//   SHIM_JACOBI_SWEEP_ALT   1: the sweep visits the index pairs in the opposite order (p = n-1..1, q = p-1..0) -- not an
+//                           Eigen version, a perturbation that bounds the sensitivity to the SVD's rounding path.
+//   SHIM_UMEYAMA_F64        1: float umeyama evaluated in double and rounded once -- the "ideal" answer.
 #ifndef PSLAM_REF_SHIM_EIGEN_H
 #define PSLAM_REF_SHIM_EIGEN_H
 
@@ -44,6 +47,12 @@
 #endif
 #ifndef SHIM_JACOBI_THRESHOLD32
 #define SHIM_JACOBI_THRESHOLD32 0
+#endif
+#ifndef SHIM_JACOBI_SWEEP_ALT
+#define SHIM_JACOBI_SWEEP_ALT 0
+#endif
+#ifndef SHIM_UMEYAMA_F64
+#define SHIM_UMEYAMA_F64 0
 #endif
 
 namespace Eigen {
@@ -187,6 +196,10 @@ public:
     T operator[](Index i) const { return (*this)(i); }
     template <typename O> View& operator=(const Base<O>& o) {
         auto v = o.eval();                       // aliasing-safe
+        if ((r == 1 || c == 1) && v.rows() == c && v.cols() == r) {     // Eigen transposes a vector assigned to a vector
+            for (Index k = 0; k < r * c; ++k) (*this)(k) = v.coeff(k);
+            return *this;
+        }
         assert(v.rows() == r && v.cols() == c);
         for (Index j = 0; j < c; ++j) for (Index i = 0; i < r; ++i) ref(i, j) = v.coeff(i, j);
         return *this;
@@ -348,7 +361,9 @@ Matrix<typename A::Scalar, A::Rows, Bq::Cols> operator*(const Base<A>& a, const 
     typedef typename A::Scalar T;
     assert(a.cols() == b.rows());
     Matrix<T, A::Rows, Bq::Cols> r(a.rows(), b.cols(), 0);
-    const bool fixed_inner = (A::Cols != Dynamic) && (Bq::Rows != Dynamic);
+    // the summed expression lhs.row(i).transpose().cwiseProduct(rhs.col(j)) takes its compile-time size from its LEFT operand
+    // (traits<CwiseBinaryOp>: Ancestor = Lhs), so the reduction is unrolled iff the left matrix has a fixed column count
+    const bool fixed_inner = (A::Cols != Dynamic);
     const Index n = a.cols();
     for (Index j = 0; j < b.cols(); ++j)
         for (Index i = 0; i < a.rows(); ++i)
@@ -524,8 +539,13 @@ private:
         bool finished = false;
         while (!finished) {
             finished = true;
+#if SHIM_JACOBI_SWEEP_ALT
+            for (Index p = n - 1; p >= 1; --p)
+                for (Index q = p - 1; q >= 0; --q) {
+#else
             for (Index p = 1; p < n; ++p)
                 for (Index q = 0; q < p; ++q) {
+#endif
 #if SHIM_JACOBI_THRESHOLD32
                     const T threshold = std::max(considerAsZero, precision * std::max(abs(W(p, p)), abs(W(q, q))));
 #else
@@ -583,6 +603,12 @@ Matrix<typename A::Scalar, Dynamic, Dynamic> umeyama(const Base<A>& src, const B
     typedef typename A::Scalar T;
     typedef Matrix<T, Dynamic, Dynamic> Mx;
     const Index m = src.rows(), n = src.cols();
+#if SHIM_UMEYAMA_F64
+    if (sizeof(T) == sizeof(float)) {
+        const Matrix<double, Dynamic, Dynamic> sd = src.template cast<double>(), dd = dst.template cast<double>();
+        return Mx(umeyama(sd, dd, with_scaling).template cast<T>());
+    }
+#endif
     const T one_over_n = T(1) / static_cast<T>(n);
     // src.rowwise().sum() * one_over_n  (dynamic number of columns: left to right)
     Mx src_mean(m, 1, 0), dst_mean(m, 1, 0);

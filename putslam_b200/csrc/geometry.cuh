@@ -178,6 +178,35 @@ __device__ __forceinline__ T det3(const T (&m)[9]) {
     return a - b + c;
 }
 
+// MatrixXd::determinant() of a dynamic-size matrix = partialPivLu().determinant() (what kabschEst.cpp:53 evaluates on its
+// MatrixXd A): first-max partial pivoting, column divided by the pivot, rank-1 update, sign * ((u00 * u11) * u22).
+__device__ __forceinline__ double det3_lu(const double (&m)[9]) {
+    double a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = m[i];
+    double sign = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double best = fabs(a[3 * k + k]);
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) if (fabs(a[3 * i + k]) > best) { best = fabs(a[3 * i + k]); p = i; }
+        if (p != k) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { const double t = a[3 * k + j]; a[3 * k + j] = a[3 * p + j]; a[3 * p + j] = t; }
+            sign = -sign;
+        }
+        if (a[3 * k + k] == 0.0) continue;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            a[3 * i + k] = __ddiv_rn(a[3 * i + k], a[3 * k + k]);
+#pragma unroll
+            for (int j = k + 1; j < 3; ++j) a[3 * i + j] = a[3 * i + j] - a[3 * i + k] * a[3 * k + j];
+        }
+    }
+    return ((sign * a[0]) * a[4]) * a[8];
+}
+
 // Rigid transform stored as R (row-major 3x3) and t.
 struct Rigid3f {
     float R[9];
@@ -242,12 +271,13 @@ __device__ __forceinline__ Rigid3f umeyama3(const float (&src)[3][3], const floa
     return umeyama_from_sigma(sig, sm, dm);
 }
 
-// ((r0*x0 + r1*x1) + r2*x2) + t
+// (r0*x0 + (r1*x1 + r2*x2)) + t : Eigen 3.3's Matrix3f * Vector3f coefficient is a fixed-size sum of three products,
+// i.e. the unrolled binary split c0 + (c1 + c2) (the reference needs Eigen >= 3.3; checked against the reference build)
 __device__ __forceinline__ void rigid_apply(const float (&R)[9], const float (&t)[3], float x, float y, float z,
                                             float& ox, float& oy, float& oz) {
-    float s = R[0] * x; s = s + R[1] * y; s = s + R[2] * z; ox = s + t[0];
-    s = R[3] * x; s = s + R[4] * y; s = s + R[5] * z; oy = s + t[1];
-    s = R[6] * x; s = s + R[7] * y; s = s + R[8] * z; oz = s + t[2];
+    ox = (R[0] * x + (R[1] * y + R[2] * z)) + t[0];
+    oy = (R[3] * x + (R[4] * y + R[5] * z)) + t[1];
+    oz = (R[6] * x + (R[7] * y + R[8] * z)) + t[2];
 }
 
 // squared norm in the x^2 + (y^2 + z^2) association, then IEEE sqrt

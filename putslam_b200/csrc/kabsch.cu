@@ -44,7 +44,7 @@ kabsch_batch_kernel(const double* __restrict__ A, const double* __restrict__ B, 
 #pragma unroll
         for (int i = 0; i < 9; ++i) H[i] = Hs[i];
         svd3<double>(H, Us, S, Vs);
-        const double det = det3<double>(H);
+        const double det = det3_lu(H);
         const double d = (det != 0.0) ? det : 1.0;
         const double sg = (double)((d > 0.0) - (d < 0.0));
         double R[9];
@@ -52,17 +52,18 @@ kabsch_batch_kernel(const double* __restrict__ A, const double* __restrict__ B, 
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                double s = (Vs[3 * i + 0] * 1.0) * Us[3 * j + 0];
-                s = s + (Vs[3 * i + 1] * 1.0) * Us[3 * j + 1];
-                s = s + (Vs[3 * i + 2] * sg) * Us[3 * j + 2];
-                R[3 * i + j] = s;
+                // fixed inner size 3 -> c0 + (c1 + c2) (Eigen 3.3 unrolled redux; checked against the reference build)
+                const double a = (Vs[3 * i + 0] * 1.0) * Us[3 * j + 0];
+                const double b2 = (Vs[3 * i + 1] * 1.0) * Us[3 * j + 1];
+                const double c2 = (Vs[3 * i + 2] * sg) * Us[3 * j + 2];
+                R[3 * i + j] = a + (b2 + c2);
             }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            double s = R[3 * i + 0] * (-c[0]);
-            s = s + R[3 * i + 1] * (-c[1]);
-            s = s + R[3 * i + 2] * (-c[2]);
-            s = s + c[3 + i];
+            const double a = R[3 * i + 0] * (-c[0]);
+            const double b2 = R[3 * i + 1] * (-c[1]);
+            const double c2 = R[3 * i + 2] * (-c[2]);
+            const double s = (a + (b2 + c2)) + c[3 + i];
 #pragma unroll
             for (int j = 0; j < 3; ++j) Tb[4 * i + j] = R[3 * i + j];
             Tb[4 * i + 3] = s;
