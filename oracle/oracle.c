@@ -10,16 +10,21 @@
  * -std=c++11 for baseline x86-64: scalar IEEE-754, no FMA; CMakeLists.txt:23,147).
  *
  * PARITY STATUS
- *   pinned   : brute-force cross-check matching, knn-2, the saturating-subtract
- *              "Hamming" of matchXYZ, undistortPoints -- all checked bit-exactly against
- *              the real OpenCV (cv2 4.13) the reference calls; golden vectors in
- *              tests/golden/ (generated by tests/golden/make_golden.py).
- *   UNPINNED : Eigen::umeyama / JacobiSVD arithmetic order (RANSAC.cpp:225, kabschEst.cpp:47).
- *              Eigen is not vendored by the reference and not present in this image, and the
- *              reference holds no golden vectors for it ("parity unpinned").  The restatement
- *              follows Eigen 3.3's published algorithms (two-sided Jacobi SVD, Umeyama eq.
- *              38-43) with the operation order written out below; it is checked against
- *              float64 numpy SVD to 1e-5, not bit-for-bit against an Eigen build.
+ *   pinned to the real OpenCV (cv2 4.13, golden vectors in tests/golden/): brute-force cross-check
+ *              matching, knn-2, the saturating-subtract "Hamming" of matchXYZ, undistortPoints.
+ *   pinned to the REFERENCE'S OWN COMPILED CODE (oracle/_ref/libref_frontend.so = RANSAC.cpp, RGBD.cpp,
+ *              kabschEst.cpp, depthSensorModel.cpp, matcher.cpp, dbscan.cpp compiled from /root/reference
+ *              against the Eigen / OpenCV stand-ins of oracle/ref_shim; tests/test_ref_build_cpu.py):
+ *              the RANSAC driver (filter, adaptive bound, strict >, refit + Euclidean recount, rejection),
+ *              all four live error versions, the guided gate and level prediction of matchXYZ, Matcher::match,
+ *              matchFeatureLoopClosure, back-projection / projection, the sensor-model covariances, normals and
+ *              RGB gradients, Kabsch, the transform covariance, the list edits of trackKLT -- inlier index sets,
+ *              hypotheses drawn and poses equal bit for bit over 240 seeded RANSAC cases.
+ *   NOT pinned (Eigen is neither vendored by the reference nor present in this image): the arithmetic ORDER
+ *              inside Eigen's own operations (fixed-size sums, umeyama's scaling, JacobiSVD's threshold and sweep
+ *              order).  The stand-in and this file model Eigen 3.3 (the reference needs >= 3.3: Eigen::Index);
+ *              profiles/umeyama_sensitivity.json bounds the rest: over 630 C1-C3 frames no Eigen-version
+ *              variant changes a final inlier set or the number of hypotheses, poses move < 4e-6 m / 1e-6 rad.
  */
 #define _DEFAULT_SOURCE   /* M_PI under -std=c11 */
 #include <math.h>

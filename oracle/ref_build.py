@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-VARIANTS = ("", "_seq", "_scalelhs", "_jac32", "_sweep", "_f64")
+VARIANTS = ("", "_seq", "_scalelhs", "_jac32", "_sweep", "_f64", "_allseq")
 
 
 class RansacArgs(C.Structure):

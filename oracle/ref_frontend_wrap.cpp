@@ -568,8 +568,9 @@ REF_API int ref_merge_tracked(const float* undist_xy, int n, const float* sandbo
 }
 
 REF_API const char* ref_shim_model(void) {
-    static char buf[160];
-    std::snprintf(buf, sizeof(buf), "fixed_redux_tree=%d umeyama_scale_lhs=%d jacobi_threshold32=%d", SHIM_FIXED_REDUX_TREE,
-                  SHIM_UMEYAMA_SCALE_LHS, SHIM_JACOBI_THRESHOLD32);
+    static char buf[256];
+    std::snprintf(buf, sizeof(buf), "fixed_redux_tree=%d product_coeff_seq=%d umeyama_scale_lhs=%d jacobi_threshold32=%d jacobi_sweep_alt=%d umeyama_f64=%d",
+                  SHIM_FIXED_REDUX_TREE, SHIM_PRODUCT_COEFF_SEQ, SHIM_UMEYAMA_SCALE_LHS, SHIM_JACOBI_THRESHOLD32, SHIM_JACOBI_SWEEP_ALT,
+                  SHIM_UMEYAMA_F64);
     return buf;
 }

@@ -14,9 +14,12 @@
 // Eigen's lazy evaluation yields the same per-coefficient expressions for the uses in those files.
 //
 // Compile-time switches (used by tools/umeyama_sensitivity.py to bound what cannot be pinned here):
-//   SHIM_FIXED_REDUX_TREE   1 (default): fixed-size reductions (sum, dot, norm, the inner product of small fixed
-//                           products) split in halves like Eigen 3.3's redux_novec_unroller: c0 + (c1 + c2),
-//                           (c0 + c1) + (c2 + c3).  0: strictly left to right (Eigen 3.2's product_coeff_impl).
+//   SHIM_FIXED_REDUX_TREE   1 (default): fixed-size reductions (sum, dot, norm, and -- through .sum() -- the inner
+//                           product of small fixed products) split in halves like redux_novec_unroller: c0 + (c1 + c2),
+//                           (c0 + c1) + (c2 + c3).  0: every reduction strictly left to right -- NO Eigen version does
+//                           that to norm(); kept to show how sharp the level gate of matchXYZ is.
+//   SHIM_PRODUCT_COEFF_SEQ  0 (default): product coefficients are (row . col).sum() (Eigen 3.3).  1: left to right
+//                           (Eigen 3.2's product_coeff_impl) while norm()/sum() keep the halving both versions have.
 //   SHIM_UMEYAMA_SCALE_LHS  0 (default): sigma = one_over_n * (dst_demean * src_demean^T) (scalar factored out of the
 //                           product: GEMM path alpha, and the lazy path since 3.3.8).  1: (one_over_n * dst_demean) *
 //                           src_demean^T (lazy path of 3.3.0-3.3.7 for n + 6 < 20).
@@ -41,6 +44,9 @@
 
 #ifndef SHIM_FIXED_REDUX_TREE
 #define SHIM_FIXED_REDUX_TREE 1
+#endif
+#ifndef SHIM_PRODUCT_COEFF_SEQ
+#define SHIM_PRODUCT_COEFF_SEQ 0
 #endif
 #ifndef SHIM_UMEYAMA_SCALE_LHS
 #define SHIM_UMEYAMA_SCALE_LHS 0
@@ -367,7 +373,7 @@ Matrix<typename A::Scalar, A::Rows, Bq::Cols> operator*(const Base<A>& a, const 
     const Index n = a.cols();
     for (Index j = 0; j < b.cols(); ++j)
         for (Index i = 0; i < a.rows(); ++i)
-            r.ref(i, j) = shim::reduce<T>([&](Index k) { return a.coeff(i, k) * b.coeff(k, j); }, n, fixed_inner);
+            r.ref(i, j) = shim::reduce<T>([&](Index k) { return a.coeff(i, k) * b.coeff(k, j); }, n, fixed_inner && !SHIM_PRODUCT_COEFF_SEQ);
     return r;
 }
 

@@ -1,0 +1,124 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the REFERENCE'S OWN COMPILED CODE
+(oracle/_ref/libref_frontend.so = the reference's RANSAC.cpp, RGBD.cpp, kabschEst.cpp, matcher.cpp ... compiled from
+/root/reference against the stand-ins of oracle/ref_shim; the prebuilt library travels to the GPU box).  The other GPU
+tests hold the device to the oracle (oracle.c), tests/test_ref_build_cpu.py holds the oracle to this library; here the two
+ends meet directly: same inputs, same Philox sample stream (replayed through rand() on the reference side)."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+from oracle import ref_build as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_frontend.so not present")]
+
+
+def _api_params(api, p):
+    q = api.default_ransac_params(p.error_version)
+    q.inlier_threshold_euclidean = p.inlier_threshold_euclidean; q.inlier_threshold_reprojection = p.inlier_threshold_reprojection
+    q.minimal_inlier_ratio_threshold = p.minimal_inlier_ratio_threshold; q.minimal_number_of_matches = p.minimal_number_of_matches
+    return q
+
+
+def assert_pose(T, Tr):
+    """north_star: 1e-5 m translation, 1e-5 rad rotation"""
+    T = np.asarray(T, np.float64); Tr = np.asarray(Tr, np.float64)
+    assert np.abs(T[:3, 3] - Tr[:3, 3]).max() <= 1e-5
+    Rd = T[:3, :3] @ Tr[:3, :3].T
+    assert np.arccos(np.clip((np.trace(Rd) - 1) / 2, -1, 1)) <= 1e-5
+
+
+def test_ransac_device_equals_reference_build(ctx, O):
+    """pslam_ransac_estimate == RANSAC::estimateTransformation compiled from RANSAC.cpp: inlier sets, hyp_used, pose"""
+    from putslam_b200 import api, synth
+    rng = np.random.default_rng(0)
+    for case in range(80):
+        m = int(rng.choice([16, 40, 100, 300, 600, 800])); frac = float(rng.choice([0.15, 0.25, 0.4, 0.6, 0.8]))
+        ev = [0, 1, 2, 4][case % 4]
+        mc = synth.matched_clouds(m=m, inlier_frac=frac, seed=3000 + case, sigma=float(rng.choice([0.002, 0.01, 0.02])))
+        prev, cur = mc["prev"].copy(), mc["cur"].copy()
+        k = rng.integers(0, m, 3)
+        prev[k[0], 2] = 7.0; cur[k[1], 0] = np.nan; prev[k[2], 2] = 0.05
+        p = O.default_ransac_params(ev)
+        out = ctx.ransac_estimate(prev, cur, mc["mq"], mc["mt"], params=_api_params(api, p), seed=case)
+        r = R.ransac(prev, cur, mc["mq"], mc["mt"], args=R.from_oracle_params(p), seed=case)
+        assert np.array_equal(out["inliers"], r["inliers"]), case
+        assert out["hyp_used"] == r["hyp_used"], case
+        assert_pose(out["T"], r["T"])
+
+
+def test_frame_to_map_device_equals_reference_build(ctx, O):
+    """pslam_frame_to_map_features (levels, gates, quirk distance, accept ratio, RANSAC, pointInlierRatio on the device) ==
+    Matcher::matchXYZ compiled from matcher.cpp, at C3's size: 1000 key points against 5000 map features"""
+    from putslam_b200 import synth
+    for seed in range(3):
+        mf = synth.map_frame(M=5000, N=1000, seed=60 + seed)
+        for comp in (1, 3):
+            radius = 0.12 + 0.02 * (comp - 1); ratio = max(0.1, 0.55 - 0.05 * (comp - 1))
+            out = ctx.frame_to_map_features(mf["map_xyz"], mf["map_desc"], mf["map_octave"], mf["map_detdist"], mf["cur_xyz"],
+                                            mf["cur_desc"], mf["cur_octave"], mf["cur_detdist"], radius, ratio, 0, seed=seed)
+            r = R.match_xyz(mf["map_xyz"], mf["map_desc"], mf["map_octave"], mf["map_detdist"], mf["cur_xyz"], mf["cur_desc"],
+                            mf["cur_octave"], mf["cur_detdist"], computation_number=comp, seed=seed)
+            assert out["mq"].size == r["n_matches"]
+            assert np.array_equal(np.stack([out["mq"][out["inliers"]], out["mt"][out["inliers"]]], 1), r["pairs"])
+            assert out["hyp_used"] == r["hyp_used"] and out["inlier_ratio"] == r["ratio"]
+            assert_pose(out["T"], r["T"])
+            assert r["pairs"].shape[0] > 300
+
+
+def test_frame_to_frame_device_equals_reference_build(ctx, O):
+    """pslam_frame_to_frame (match -> undistort -> back-project -> RANSAC in one submission) == Matcher::match compiled from
+    matcher.cpp with a scripted detector"""
+    from putslam_b200 import api, synth
+    for seed in range(4):
+        distorted = bool(seed % 2)
+        fp = synth.frame_pair(n=500, seed=70 + seed, distorted=distorted)
+        dist = synth.DIST if distorted else (0, 0, 0, 0, 0)
+        cam = api.make_camera(dist=dist)
+        und = [O.undistort(uv, synth.FX, synth.FY, synth.CX, synth.CY, dist) for uv in (fp["uv1"], fp["uv2"])]
+        keep = [(u[:, 0] < 638.4) & (u[:, 1] < 478.4) for u in und]          # off the roundSize out-of-bounds quirk
+        uv1, d1 = fp["uv1"][keep[0]], fp["desc1"][keep[0]]; uv2, d2 = fp["uv2"][keep[1]], fp["desc2"][keep[1]]
+        first = ctx.frame_to_frame(None, None, d1, uv1, fp["depth1"], cam=cam, undistort=True)
+        ev = (0, 2, 4, 1)[seed]
+        out = ctx.frame_to_frame(d1, first["xyz"], d2, uv2, fp["depth2"], cam=cam, undistort=True,
+                                 params=api.default_ransac_params(ev), seed=seed)
+        a = R.matcher_args(ransac=R.from_oracle_params(O.default_ransac_params(ev)), dist=dist)
+        r = R.match_vo(d1, first["xyz"], uv2, np.zeros(len(uv2), np.int32), d2, fp["depth2"], args=a, seed=seed)
+        assert np.array_equal(bits(out["xyz"]), bits(r["xyz"])) and np.array_equal(bits(out["uv_undist"]), bits(r["uv"]))
+        assert np.array_equal(np.stack([out["mq"][out["inliers"]], out["mt"][out["inliers"]]], 1), r["inliers"])
+        assert out["hyp_used"] == r["hyp_used"] and out["inlier_ratio"] == r["ratio"]
+        assert_pose(out["T"], r["T"])
+
+
+def test_loop_closure_pair_device_equals_reference_build(ctx, O):
+    from putslam_b200 import synth
+    cam = (synth.FX, synth.FY, synth.CX, synth.CY)
+    for seed, n in ((3, 400), (4, 35), (5, 9)):
+        fp = synth.frame_pair(n=n, seed=seed)
+        x1, _ = O.backproject(fp["uv1"], fp["depth1"], *cam, 5000.0); x2, _ = O.backproject(fp["uv2"], fp["depth2"], *cam, 5000.0)
+        out = ctx.loop_closure_pair(fp["desc1"], x1, fp["desc2"], x2, seed=9)
+        r = R.loop_closure(fp["desc1"], x1.astype(np.float64), fp["desc2"], x2.astype(np.float64), seed=9)
+        assert np.array_equal(np.stack([out["mq"][out["inliers"]], out["mt"][out["inliers"]]], 1).reshape(-1, 2), r["pairs"])
+        assert out["inlier_ratio"] == r["ret"]
+        assert_pose(out["T"], r["T"])
+
+
+def test_kabsch_and_backprojection_device_equal_reference_build(ctx, O):
+    from putslam_b200 import synth
+    rng = np.random.default_rng(4)
+    A_list, B_list = [], []
+    for n in (3, 4, 10, 100, 400):
+        for _ in range(6):
+            A = rng.uniform(-2, 2, (n, 3))
+            B = A @ synth.rot_from_rotvec(rng.standard_normal(3) * 0.4).T + rng.uniform(-1, 1, 3) + rng.normal(0, 0.01, (n, 3))
+            A_list.append(A); B_list.append(B)
+    T = ctx.kabsch_batch(A_list, B_list)
+    for A, B, t in zip(A_list, B_list, T):
+        assert np.array_equal(bits(np.ascontiguousarray(t)), bits(R.kabsch(A, B)))
+    for seed in range(3):
+        fp = synth.frame_pair(n=600, seed=seed, distorted=True)
+        und = O.undistort(fp["uv1"], synth.FX, synth.FY, synth.CX, synth.CY, synth.DIST)
+        uv = fp["uv1"][(und[:, 0] < 638.4) & (und[:, 1] < 478.4)]
+        out = ctx.backproject(uv, fp["depth1"], undistort=True)
+        used, xyz, dd = R.backproject(uv, fp["depth1"], dist5=synth.DIST)
+        assert np.array_equal(bits(out["xyz"]), bits(xyz)) and np.array_equal(bits(out["det_dist"]), bits(dd))

@@ -319,8 +319,9 @@ def test_loop_closure_equals_reference_build(O):
 
 
 def test_reference_build_variants_are_what_they_say():
-    for v, want in (("", "fixed_redux_tree=1 umeyama_scale_lhs=0 jacobi_threshold32=0"), ("_seq", "fixed_redux_tree=0"),
-                    ("_scalelhs", "umeyama_scale_lhs=1"), ("_jac32", "jacobi_threshold32=1")):
+    for v, want in (("", "fixed_redux_tree=1 product_coeff_seq=0 umeyama_scale_lhs=0 jacobi_threshold32=0 jacobi_sweep_alt=0 umeyama_f64=0"),
+                    ("_seq", "product_coeff_seq=1"), ("_scalelhs", "umeyama_scale_lhs=1"), ("_jac32", "jacobi_threshold32=1"),
+                    ("_sweep", "jacobi_sweep_alt=1"), ("_f64", "umeyama_f64=1"), ("_allseq", "fixed_redux_tree=0")):
         if R.available(v):
             assert want in R.shim_model(v)
 

@@ -1,12 +1,16 @@
 """How much of the bit-exact inlier-set claim rests on what cannot be pinned here (Eigen's internal arithmetic order)?
 
-The reference's RANSAC.cpp / matcher.cpp are compiled against the Eigen stand-in (oracle/ref_shim) in six variants
+The reference's RANSAC.cpp / matcher.cpp are compiled against the Eigen stand-in (oracle/ref_shim) in seven variants
 (oracle/Makefile): the default model (Eigen 3.3) and one perturbed choice each --
-    _seq       fixed-size sums left to right instead of Eigen 3.3's halving (R*x, norms, 4x4 inverse determinant)
+    _seq       product coefficients summed left to right (Eigen 3.2) instead of 3.3's (row . col).sum() halving: R*x + t
     _scalelhs  umeyama: (1/n * dst_demean) * src_demean^T instead of 1/n * (dst_demean * src_demean^T)
     _jac32     JacobiSVD with Eigen 3.2's threshold / no input scaling
     _sweep     JacobiSVD visiting the index pairs in the opposite order
     _f64       umeyama evaluated in float64 and rounded once
+    _allseq    EVERY fixed-size reduction left to right, norm() included -- no Eigen version does that; it shows how sharp
+               the level gate of matchXYZ is: a key point matched in the frame that detected it has detDist / |x| = 1 +- 1 ulp
+               (matcher.cpp:53-55 sums left to right in float, Vector3f::norm() halves), and ceil(log(1.2^k * that) / log 1.2)
+               is k or k + 1 on that ulp
 For synthetic frames of the configurations C1-C3 this script runs every variant on identical inputs and the
 identical sample stream and reports the fraction of frames whose FINAL INLIER SET, number of hypotheses drawn (hyp_used) or
 pose (beyond 1e-5 m / 1e-5 rad) differ from the default build, and how far the poses move.  Needs oracle/_ref (built where
@@ -31,8 +35,10 @@ CAM = (synth.FX, synth.FY, synth.CX, synth.CY)
 
 
 def rot_angle(Ta, Tb):
-    Rd = Ta[:3, :3].astype(np.float64) @ Tb[:3, :3].astype(np.float64).T
-    return float(np.arccos(np.clip((np.trace(Rd) - 1) / 2, -1, 1)))
+    # angle of Ra Rb^T through the chord ||Ra - Rb||_F = 2 sqrt(2) sin(angle / 2): well conditioned near zero, and the
+    # float32 rotations' own departure from orthogonality (1e-7) does not show up as 1e-3 rad the way arccos(trace) does
+    d = np.linalg.norm(Ta[:3, :3].astype(np.float64) - Tb[:3, :3].astype(np.float64))
+    return float(2 * np.arcsin(min(1.0, d / (2 * np.sqrt(2)))))
 
 
 def frames_c12(n_kp, count, base_seed):
@@ -59,7 +65,6 @@ def main():
     ap.add_argument("--c1", type=int, default=200); ap.add_argument("--c2", type=int, default=100); ap.add_argument("--c3", type=int, default=30)
     a = ap.parse_args()
     variants = [v for v in R.VARIANTS if R.available(v)]
-    new = lambda: dict(frames=0, inlier_set_differs=0, hyp_used_differs=0, pose_beyond_1e_5=0)  # noqa: E731
     res = {"variants": {v or "default": R.shim_model(v) for v in variants}, "configs": {}}
     t0 = time.time()
     for name, n_kp, count, base in (("C1_frame_pair_500", 500, a.c1, 0), ("C2_frame_pair_1000", 1000, a.c2, 5000)):
