@@ -24,8 +24,8 @@ def assert_pose(T, Tr):
     """north_star: 1e-5 m translation, 1e-5 rad rotation"""
     T = np.asarray(T, np.float64); Tr = np.asarray(Tr, np.float64)
     assert np.abs(T[:3, 3] - Tr[:3, 3]).max() <= 1e-5
-    Rd = T[:3, :3] @ Tr[:3, :3].T
-    assert np.arccos(np.clip((np.trace(Rd) - 1) / 2, -1, 1)) <= 1e-5
+    # rotation angle through the chord ||R - Rr||_F = 2 sqrt(2) sin(angle / 2) (arccos of the trace has sqrt(eps) resolution)
+    assert 2 * np.arcsin(min(1.0, np.linalg.norm(T[:3, :3] - Tr[:3, :3]) / (2 * np.sqrt(2)))) <= 1e-5
 
 
 def test_ransac_device_equals_reference_build(ctx, O):
