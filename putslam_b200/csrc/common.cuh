@@ -116,6 +116,49 @@ __device__ __forceinline__ uint32_t ham256_key(const uint32_t (&q)[8], const uin
     r = __popc(c3) * (4u << kKeyDShift) + r;
     return r;
 }
+// ----------------------------------------------------------------------------------------------
+// The same distance on RE-ENCODED rows: 13 LOP3 + 4 POPC, result identical bit for bit.
+//   A carry-save adder over three XORed words x0, x1, x2 needs sum = x0^x1^x2 and carry = maj(x0, x1, x2).  XOR is
+//   linear, so sum = (q0^q1^q2) ^ (t0^t1^t2): if every descriptor row stores e2 = w0^w1^w2 in place of w2, the sum
+//   is ONE xor of two stored words and x2 itself is never formed; the carry is a 3-input function of (x0, x1, sum)
+//   because x2 = sum^x0^x1: maj(a, b, a^b^c) = LUT 0xD4.  The same holds one level up: s2 = s0^s1^x6 =
+//   (q0^..^q6) ^ (t0^..^t6), and c2 = maj(s0, s1, x6) = LUT_0xD4(s0, s1, s2).  Encoded row (an invertible linear map
+//   of the original 8 words, so still 32 bytes):
+//       e = ( w0, w1, w0^w1^w2, w3, w4, w3^w4^w5, w0^w1^w2^w3^w4^w5^w6, w7 )
+//   per pair: x0 x1 s0 | c0 | x3 x4 s1 | c1 | s2 | c2 | x7 | s3 c3  = 13 LOP3 (16 before), 4 POPC, weights 1,1,2,4.
+//   The resident keyframe map is encoded once when descriptors are appended; a query is encoded when it is loaded
+//   into registers.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lop3_maj_sum(uint32_t a, uint32_t b, uint32_t sum) {   // maj(a, b, a^b^sum)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(r) : "r"(a), "r"(b), "r"(sum));
+    return r;
+}
+__host__ __device__ __forceinline__ void ham256_encode(uint32_t (&w)[8]) {
+    const uint32_t e2 = w[0] ^ w[1] ^ w[2], e5 = w[3] ^ w[4] ^ w[5];
+    w[6] = e2 ^ e5 ^ w[6];
+    w[2] = e2;
+    w[5] = e5;
+}
+__device__ __forceinline__ uint32_t ham256_key_enc(const uint32_t (&q)[8], const uint4& ta, const uint4& tb, uint32_t low) {
+    const uint32_t x0 = q[0] ^ ta.x, x1 = q[1] ^ ta.y, s0 = q[2] ^ ta.z;
+    const uint32_t x3 = q[3] ^ ta.w, x4 = q[4] ^ tb.x, s1 = q[5] ^ tb.y;
+    const uint32_t s2 = q[6] ^ tb.z, x7 = q[7] ^ tb.w;
+    const uint32_t c0 = lop3_maj_sum(x0, x1, s0);
+    const uint32_t c1 = lop3_maj_sum(x3, x4, s1);
+    const uint32_t c2 = lop3_maj_sum(s0, s1, s2);
+    const uint32_t s3 = lop3_xor3(c0, c1, c2), c3 = lop3_maj(c0, c1, c2);
+    uint32_t r = low;
+    r = __popc(s2) * (1u << kKeyDShift) + r;
+    r = __popc(x7) * (1u << kKeyDShift) + r;
+    r = __popc(s3) * (2u << kKeyDShift) + r;
+    r = __popc(c3) * (4u << kKeyDShift) + r;
+    return r;
+}
+template <bool ENC>
+__device__ __forceinline__ uint32_t ham256_key_t(const uint32_t (&q)[8], const uint4& ta, const uint4& tb, uint32_t low) {
+    return ENC ? ham256_key_enc(q, ta, tb, low) : ham256_key(q, ta, tb, low);
+}
 __device__ __forceinline__ uint32_t key_dist(uint32_t k) { return k >> kKeyDShift; }
 // QB = bits of the query field; the train field takes the remaining kKeyDShift - QB bits (10/12 by default,
 // 11/11 for query sets of up to 2048 descriptors)

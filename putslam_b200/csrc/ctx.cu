@@ -1923,6 +1923,12 @@ int pslam_lc_db_append(pslam_ctx* ctx, const uint8_t* desc, const int64_t* kf_of
         CK(cudaMemcpyAsync(ctx->d_db + (size_t)ctx->db_n * 32 + done, ctx->h_in.p, b, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    // the map is kept in the re-encoded row form the sweep kernels compare in (common.cuh ham256_key_enc); once per append
+    if (nd > 0) {
+        int l = 0;
+        CK(launch_lc_encode_rows(ctx->d_db + (size_t)ctx->db_n * 32, (long long)nd, ctx->stream, &l));
+        ctx->launches += l;
+    }
     const int64_t base = ctx->db_n - kf_off[0];
     for (int k = 1; k <= n_kf; ++k) ctx->h_kf_off.push_back(kf_off[k] + base);
     CK(cudaMemcpyAsync(ctx->d_kf_off + ctx->n_kf, ctx->h_kf_off.data() + ctx->n_kf, sizeof(int64_t) * ((size_t)n_kf + 1),

@@ -26,6 +26,8 @@ template <int RQ, int NT>
 struct QueryRegs {
     uint32_t v[RQ][8];
     uint32_t off[RQ];
+    // ENC: re-encode the rows for ham256_key_enc (the train side must be encoded too: the resident keyframe map is)
+    template <bool ENC = false>
     __device__ __forceinline__ void load(const uint4* __restrict__ query, int nq, int qbase, int tid) {
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
@@ -37,15 +39,17 @@ struct QueryRegs {
             }
             v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
             v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+            if (ENC) ham256_encode(v[j]);
             off[j] = (uint32_t)(j * NT + tid) | ((q < nq) ? 0u : kKeyInvalid);
         }
     }
 };
 
 // One sub-tile: cnt (<= kTT) train descriptors in shared memory vs this thread's RQ queries, two train
-// descriptors per iteration so that the row update is a single 3-input min.
+// descriptors per iteration so that the row update is a single 3-input min; the column keys of a train fold two
+// queries per 3-input min as well (1 min per pair in all).
 //   rowmin[j] : running key for query j (min over train)   partial_w[tt] : this warp's min over its queries
-template <int RQ, int NT, int QB = kKeyQBits>
+template <int RQ, int NT, int QB = kKeyQBits, bool ENC = false>
 __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_t (&rowmin)[RQ],
                                              const uint4* __restrict__ tile, int cnt, uint32_t tbase,
                                              uint32_t* __restrict__ partial_w, int lane) {
@@ -54,14 +58,19 @@ __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_
     for (; tt + 2 <= cnt; tt += 2) {
         const uint4 a0 = tile[2 * tt], b0 = tile[2 * tt + 1], a1 = tile[2 * tt + 2], b1 = tile[2 * tt + 3];
         const uint32_t t0 = (tbase + (uint32_t)tt) << QB, t1 = t0 + (1u << QB);
-        uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu;
+        uint32_t k0[RQ], k1[RQ];
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
-            const uint32_t k0 = ham256_key(Q.v[j], a0, b0, Q.off[j] + t0);
-            const uint32_t k1 = ham256_key(Q.v[j], a1, b1, Q.off[j] + t1);
-            rowmin[j] = __vimin3_u32(rowmin[j], k0, k1);
-            c0 = min(c0, k0);
-            c1 = min(c1, k1);
+            k0[j] = ham256_key_t<ENC>(Q.v[j], a0, b0, Q.off[j] + t0);
+            k1[j] = ham256_key_t<ENC>(Q.v[j], a1, b1, Q.off[j] + t1);
+            rowmin[j] = __vimin3_u32(rowmin[j], k0[j], k1[j]);
+        }
+        uint32_t c0 = k0[0], c1 = k1[0];
+        if (RQ % 2 == 0) { c0 = min(c0, k0[1]); c1 = min(c1, k1[1]); }
+#pragma unroll
+        for (int j = 2 - (RQ & 1); j + 1 < RQ; j += 2) {
+            c0 = __vimin3_u32(c0, k0[j], k0[j + 1]);
+            c1 = __vimin3_u32(c1, k1[j], k1[j + 1]);
         }
         c0 = warp_min_u32(c0);
         c1 = warp_min_u32(c1);
@@ -73,13 +82,24 @@ __device__ __forceinline__ void tile_compute(const QueryRegs<RQ, NT>& Q, uint32_
         uint32_t c0 = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < RQ; ++j) {
-            const uint32_t k0 = ham256_key(Q.v[j], a0, b0, Q.off[j] + t0);
+            const uint32_t k0 = ham256_key_t<ENC>(Q.v[j], a0, b0, Q.off[j] + t0);
             rowmin[j] = min(rowmin[j], k0);
             c0 = min(c0, k0);
         }
         c0 = warp_min_u32(c0);
         if (lane == 0) partial_w[tt] = c0;
     }
+}
+
+// In-place re-encoding of descriptor rows for ham256_key_enc (run once when keyframe descriptors are appended).
+__global__ void lc_encode_rows_kernel(uint4* __restrict__ rows, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 a = rows[2 * i], b = rows[2 * i + 1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    ham256_encode(w);
+    rows[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+    rows[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,7 +323,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
         *score_s = 0;
     }
     QueryRegs<RQ, NT> Q;
-    Q.load(query, nq, 0, tid);
+    Q.template load<true>(query, nq, 0, tid);         // the resident map is stored re-encoded (ham256_key_enc)
     uint32_t rowmin[RQ];
 #pragma unroll
     for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
@@ -345,7 +365,7 @@ lc_sweep_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict
         const int cnt = min(kTT, cons.cnt - tbase);
         uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
         mbar_wait(bars + stage, phase);
-        tile_compute<RQ, NT, QB>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        tile_compute<RQ, NT, QB, true>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
         __syncthreads();
         if (tid < cnt) {
             uint32_t m = pbuf[tid];
@@ -415,7 +435,7 @@ lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __re
         fence_mbar_init();
     }
     QueryRegs<RQ, NT> Q;
-    Q.load(query, nq, 0, tid);
+    Q.template load<true>(query, nq, 0, tid);
     __syncthreads();
     const int my_items = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     auto issue = [&](int a) {
@@ -440,7 +460,7 @@ lc_sweep_split_kernel(const uint4* __restrict__ query, int nq, const uint4* __re
         for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
         uint32_t* pbuf = partial + (it & 1) * (NW * kTT);
         mbar_wait(bars + stage, phase);
-        tile_compute<RQ, NT, QB>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
+        tile_compute<RQ, NT, QB, true>(Q, rowmin, stages + (size_t)stage * kTT * 2, cnt, (uint32_t)tbase, pbuf + warp * kTT, lane);
 #pragma unroll
         for (int j = 0; j < RQ; ++j) rowpart[(size_t)item * (RQ * NT) + j * NT + tid] = rowmin[j];
         __syncthreads();
@@ -508,7 +528,7 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
         fence_mbar_init();
     }
     QueryRegs<RQ, NT> Q;
-    Q.load(query, nq, 0, tid);
+    Q.template load<true>(query, nq, 0, tid);
     unsigned long long g1[RQ], g2[RQ];
 #pragma unroll
     for (int j = 0; j < RQ; ++j) g1[j] = g2[j] = ~0ull;
@@ -563,8 +583,8 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
             const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits, t1 = t0 + (1u << kKeyQBits);
 #pragma unroll
             for (int j = 0; j < RQ; ++j) {
-                const uint32_t k0 = ham256_key(Q.v[j], a0, b0, t0);
-                const uint32_t k1 = ham256_key(Q.v[j], a1, b1, t1);
+                const uint32_t k0 = ham256_key_enc(Q.v[j], a0, b0, t0);
+                const uint32_t k1 = ham256_key_enc(Q.v[j], a1, b1, t1);
                 const uint32_t lo = min(k0, k1), hi = max(k0, k1);
                 const uint32_t mid = max(m1[j], lo);
                 m1[j] = min(m1[j], lo);
@@ -576,7 +596,7 @@ lc_knn2_kernel(const uint4* __restrict__ query, int nq, const uint4* __restrict_
             const uint32_t t0 = (tbase + (uint32_t)tt) << kKeyQBits;
 #pragma unroll
             for (int j = 0; j < RQ; ++j) {
-                const uint32_t k0 = ham256_key(Q.v[j], a0, b0, t0);
+                const uint32_t k0 = ham256_key_enc(Q.v[j], a0, b0, t0);
                 m2[j] = min(m2[j], max(m1[j], k0));
                 m1[j] = min(m1[j], k0);
             }
@@ -882,6 +902,13 @@ cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t*
         if (launches) *launches += 1;
     }
     lc_sweep_finalize_kernel<<<n_kf, 256, 0, st>>>(d_tile_start, d_kf_off, nq, rq * 256, kKeyQBits, d_rowpart, d_colmin, tau, d_scores);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lc_encode_rows(uint8_t* d_rows, long long n, cudaStream_t st, int* launches) {
+    if (n <= 0) return cudaSuccess;
+    lc_encode_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint4*>(d_rows), n);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

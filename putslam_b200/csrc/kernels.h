@@ -27,6 +27,8 @@ size_t lc_split_colmin_bytes(int n_kf);
 cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off,
                                   const int* d_tile_start, int n_kf, int n_tiles, int tau, uint32_t* d_rowpart,
                                   uint32_t* d_colmin, int* d_scores, int sm_count, cudaStream_t st, int* launches);
+// in-place re-encoding of n descriptor rows (32 B each) for the encoded Hamming compare of the sweep kernels
+cudaError_t launch_lc_encode_rows(uint8_t* d_rows, long long n, cudaStream_t st, int* launches);
 cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
                            int* launches);
 cudaError_t launch_lc_merge_topk(const int* d_gathered, int n_pairs, int k, int* d_out_pairs, cudaStream_t st,
