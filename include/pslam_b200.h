@@ -461,6 +461,10 @@ PSLAM_API int pslam_comm_destroy(pslam_ctx* ctx);
 PSLAM_API int pslam_lc_query_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int tau, int k,
                                      int* out_kf_ids, int* out_scores);
 PSLAM_API int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k);
+/* As pslam_lc_query_sharded_resident, but the query that is resident on `root` (from its last pslam_lc_query_sharded call)
+ * is first broadcast to the other ranks: the whole exchange of a sharded query -- broadcast, sweep, top-k, gather, merge --
+ * enqueued on the ctx stream without any host copy (root < 0: no broadcast). */
+PSLAM_API int pslam_lc_query_sharded_resident_bcast(pslam_ctx* ctx, int root, int tau, int k);
 
 /* Per-query-descriptor 2-NN against the whole resident database (SURVEY 8e variant V2; the oracle is
  * cv::BFMatcher::knnMatch(query, whole_db, 2)): out_idx nq x 2 GLOBAL descriptor indices (int64, -1 = none;

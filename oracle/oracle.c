@@ -1117,6 +1117,80 @@ ORC_API int orc_ransac(const float *prev, int n1, const float *cur, int n2, cons
     return 0;
 }
 
+/* All-cores variant of the fixed-H mode of orc_ransac (SURVEY 8d "OpenMP-over-hypotheses"): the H hypotheses are
+ * independent, so models and inlier COUNTS are evaluated in parallel; the reference's selection (first strict maximum),
+ * the refit and the recount then run once.  Same answer as orc_ransac(..., num_hyp = H) -- used only as the all-cores
+ * CPU baseline of bench.py.  Returns 0. */
+ORC_API int orc_ransac_fixed_mt(const float *prev, int n1, const float *cur, int n2, const int *mq, const int *mt,
+                                int m, const orc_ransac_params *P, uint64_t seed, int num_hyp, int threads, float *T_out,
+                                int *inl_idx, int *n_inl_out, double *best_ratio_out) {
+    (void)n1; (void)n2;
+    for (int i = 0; i < 16; ++i) T_out[i] = (i % 5 == 0) ? 1.f : 0.f;
+    *n_inl_out = 0;
+    if (best_ratio_out) *best_ratio_out = 0.0;
+    int *keep = (int *)malloc(sizeof(int) * (size_t)(m > 0 ? m : 1));
+    int mf = 0;
+    for (int k = 0; k < m; ++k) {
+        const float *p = prev + 3 * mq[k], *c = cur + 3 * mt[k];
+        int bad = isnan(p[0]) || isnan(p[1]) || isnan(p[2]) || isnan(c[0]) || isnan(c[1]) || isnan(c[2]) ||
+                  p[2] < 0.1 || p[2] > 6 || c[2] < 0.1 || c[2] > 6;
+        if (!bad) keep[mf++] = k;
+    }
+    if (mf < P->minimal_number_of_matches || num_hyp <= 0) { free(keep); return 0; }
+    int *fq = (int *)malloc(sizeof(int) * (size_t)mf), *ft = (int *)malloc(sizeof(int) * (size_t)mf);
+    for (int k = 0; k < mf; ++k) { fq[k] = mq[keep[k]]; ft[k] = mt[keep[k]]; }
+    int *counts = (int *)malloc(sizeof(int) * (size_t)num_hyp);
+    float *models = (float *)malloc(sizeof(float) * 16 * (size_t)num_hyp);
+    if (threads < 1) threads = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(threads)
+#endif
+    for (int i = 0; i < num_hyp; ++i) {
+        int s[3];
+        orc_sample3(seed, (uint32_t)i, mf, s);
+        int sq[3] = {fq[s[0]], fq[s[1]], fq[s[2]]}, st[3] = {ft[s[0]], ft[s[1]], ft[s[2]]};
+        float *T = models + 16 * (size_t)i, Tinv[16];
+        counts[i] = -1;
+        if (!umeyama_idx(prev, sq, cur, st, 3, T)) continue;
+        if (P->error_version == 1 || P->error_version == 2) inverse4(T, Tinv);
+        int cnt = 0;
+        for (int k = 0; k < mf; ++k) cnt += is_inlier(T, Tinv, prev + 3 * fq[k], cur + 3 * ft[k], P, 0);
+        counts[i] = cnt;
+    }
+    int win = -1;
+    double bestInlierRatio = 0.0;
+    for (int i = 0; i < num_hyp; ++i) {
+        if (counts[i] < 0) continue;
+        float r = (float)counts[i] / (float)mf;
+        if ((double)r > bestInlierRatio) { bestInlierRatio = r; win = i; }
+    }
+    float bestT[16];
+    for (int i = 0; i < 16; ++i) bestT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    int *best_inl = (int *)malloc(sizeof(int) * (size_t)mf), n_best = 0;
+    if (win >= 0) {
+        float *T = models + 16 * (size_t)win, Tinv[16];
+        if (P->error_version == 1 || P->error_version == 2) inverse4(T, Tinv);
+        for (int k = 0; k < mf; ++k)
+            if (is_inlier(T, Tinv, prev + 3 * fq[k], cur + 3 * ft[k], P, 0)) best_inl[n_best++] = k;
+    }
+    int *rq = (int *)malloc(sizeof(int) * (size_t)(n_best > 0 ? n_best : 1));
+    int *rt = (int *)malloc(sizeof(int) * (size_t)(n_best > 0 ? n_best : 1));
+    for (int k = 0; k < n_best; ++k) { rq[k] = fq[best_inl[k]]; rt[k] = ft[best_inl[k]]; }
+    umeyama_idx(prev, rq, cur, rt, n_best, bestT);
+    int n_final = 0;
+    for (int k = 0; k < n_best; ++k)
+        if (is_inlier(bestT, NULL, prev + 3 * rq[k], cur + 3 * rt[k], P, 1)) inl_idx[n_final++] = keep[best_inl[k]];
+    if (bestInlierRatio < P->minimal_inlier_ratio_threshold) {
+        for (int a = 0; a < 16; ++a) bestT[a] = (a % 5 == 0) ? 1.f : 0.f;
+        n_final = 0;
+    }
+    memcpy(T_out, bestT, sizeof(bestT));
+    *n_inl_out = n_final;
+    if (best_ratio_out) *best_ratio_out = bestInlierRatio;
+    free(keep); free(fq); free(ft); free(counts); free(models); free(best_inl); free(rq); free(rt);
+    return 0;
+}
+
 /* RANSAC::pointInlierRatio (include/putslam/TransformEst/RANSAC.h:56-66):
  * |unique trainIdx of inliers| / |unique trainIdx of all (unfiltered) matches|. */
 ORC_API double orc_point_inlier_ratio(const int *inl_t, int n_inl, const int *all_t, int n_all, int n_train) {

@@ -321,6 +321,23 @@ def ransac(prev, cur, mq, mt, params=None, seed=0, num_hyp=0, want_counts=False,
                 counts=counts[:cap] if want_counts else None)
 
 
+def ransac_fixed_mt(prev, cur, mq, mt, params=None, seed=0, num_hyp=4096, threads=0):
+    """all-cores (OpenMP over hypotheses) fixed-H RANSAC; same answer as ransac(..., num_hyp=H) -> dict(T, inliers, best_ratio)"""
+    prev = np.ascontiguousarray(prev, np.float32).reshape(-1, 3)
+    cur = np.ascontiguousarray(cur, np.float32).reshape(-1, 3)
+    mq = np.ascontiguousarray(mq, np.int32); mt = np.ascontiguousarray(mt, np.int32)
+    m = mq.size
+    if params is None:
+        params = default_ransac_params()
+    T = np.empty((4, 4), np.float32)
+    inl = np.empty(max(1, m), np.int32)
+    n_inl = C.c_int(0); best = C.c_double(0)
+    lib().orc_ransac_fixed_mt(_p(prev, C.c_float), prev.shape[0], _p(cur, C.c_float), cur.shape[0], _p(mq, C.c_int), _p(mt, C.c_int),
+                              m, C.byref(params), C.c_uint64(seed), int(num_hyp), int(threads or num_threads()), _p(T, C.c_float),
+                              _p(inl, C.c_int), C.byref(n_inl), C.byref(best))
+    return dict(T=T, inliers=inl[:n_inl.value].copy(), best_ratio=best.value)
+
+
 def point_inlier_ratio(inl_t, all_t, n_train):
     inl_t = np.ascontiguousarray(inl_t, np.int32); all_t = np.ascontiguousarray(all_t, np.int32)
     return lib().orc_point_inlier_ratio(_p(inl_t, C.c_int), inl_t.size, _p(all_t, C.c_int), all_t.size, n_train)

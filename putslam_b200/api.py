@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_set_work_unit", "pslam_lc_query",
     "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
-    "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_knn2", "pslam_lc_set_desc_base",
+    "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_query_sharded_resident_bcast", "pslam_lc_knn2", "pslam_lc_set_desc_base",
     "pslam_lc_knn2_sharded", "pslam_lc_knn2_resident",
 ]
 
@@ -636,8 +636,12 @@ class Context:
     def lc_knn2_resident(self, sharded=False):
         self._ck(self.lib.pslam_lc_knn2_resident(self.h, int(bool(sharded))))
 
-    def lc_query_sharded_resident(self, tau=64, k=16):
-        self._ck(self.lib.pslam_lc_query_sharded_resident(self.h, tau, k))
+    def lc_query_sharded_resident(self, tau=64, k=16, root=None):
+        """replay on the resident query; root >= 0: broadcast it from that rank first (the whole sharded exchange on the device)"""
+        if root is None:
+            self._ck(self.lib.pslam_lc_query_sharded_resident(self.h, tau, k))
+        else:
+            self._ck(self.lib.pslam_lc_query_sharded_resident_bcast(self.h, int(root), tau, k))
 
 
 def comm_unique_id():

@@ -2156,6 +2156,15 @@ int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k) {
     return lc_enqueue_sharded(ctx, -1, tau, k);
 }
 
+int pslam_lc_query_sharded_resident_bcast(pslam_ctx* ctx, int root, int tau, int k) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->lc_nq <= 0 || !ctx->lc_configured) return fail(ctx, PSLAM_ERR_ARG, "no resident query");
+    if (ctx->world > 1 && !ctx->comm) return fail(ctx, PSLAM_ERR_NCCL, "communicator not initialised");
+    if (root >= ctx->world) return fail(ctx, PSLAM_ERR_ARG, "root outside the communicator");
+    CK(cudaSetDevice(ctx->device));
+    return lc_enqueue_sharded(ctx, root, tau, k);
+}
+
 int pslam_lc_set_desc_base(pslam_ctx* ctx, int64_t desc_id_base) {
     if (!ctx) return PSLAM_ERR_ARG;
     ctx->desc_id_base = desc_id_base;

@@ -8,8 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--n-kf", "48"], capture_output=True, text=True, timeout=600, cwd=ROOT)   # a small map: the CPU suite stays short
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -18,6 +18,8 @@ def test_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "Gcmp/s" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
+    assert line["config"]["whole_map_per_step"] is True and line["config"]["keyframes_per_step"] == 48
+    assert "cv2_gcmps" in line["cpu_baseline"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -28,6 +28,23 @@ def assert_pose(T, Tr):
     assert 2 * np.arcsin(min(1.0, np.linalg.norm(T[:3, :3] - Tr[:3, :3]) / (2 * np.sqrt(2)))) <= 1e-5
 
 
+def hits_iteration_overflow(counts, m_filtered):
+    """RANSAC::computeRANSACIteration converts log(0.02) / log(1 - w^3) to int; for w^3 < ~1.8e-9 (a best-so-far model with
+    1 or 2 inliers among > 820 matches) the quotient exceeds INT_MAX and the conversion is UNDEFINED BEHAVIOUR: the x86-64
+    reference build gets INT_MIN and leaves the loop at once (identity, no inliers), this library saturates and goes on
+    (divergence 2).  -> True when a run with these per-hypothesis counts passes through that case."""
+    best = 0.0
+    for c in counts:
+        if c < 0:
+            continue
+        w = float(np.float32(c) / np.float32(m_filtered))
+        if w > best:
+            best = w
+            if w ** 3 < 1e-300 or np.log(1 - 0.98) / np.log1p(-(w ** 3)) >= 2147483648.0:
+                return True
+    return False
+
+
 def test_ransac_device_equals_reference_build(ctx, O):
     """pslam_ransac_estimate == RANSAC::estimateTransformation compiled from RANSAC.cpp: inlier sets, hyp_used, pose"""
     from putslam_b200 import api, synth
@@ -51,6 +68,7 @@ def test_frame_to_map_device_equals_reference_build(ctx, O):
     """pslam_frame_to_map_features (levels, gates, quirk distance, accept ratio, RANSAC, pointInlierRatio on the device) ==
     Matcher::matchXYZ compiled from matcher.cpp, at C3's size: 1000 key points against 5000 map features"""
     from putslam_b200 import synth
+    n_ub = 0
     for seed in range(3):
         mf = synth.map_frame(M=5000, N=1000, seed=60 + seed)
         for comp in (1, 3):
@@ -60,10 +78,16 @@ def test_frame_to_map_device_equals_reference_build(ctx, O):
             r = R.match_xyz(mf["map_xyz"], mf["map_desc"], mf["map_octave"], mf["map_detdist"], mf["cur_xyz"], mf["cur_desc"],
                             mf["cur_octave"], mf["cur_detdist"], computation_number=comp, seed=seed)
             assert out["mq"].size == r["n_matches"]
+            chk = O.ransac(mf["map_xyz"].astype(np.float32), mf["cur_xyz"], out["mq"], out["mt"], seed=seed, want_counts=True)
+            if hits_iteration_overflow(chk["counts"][:chk["hyp_used"]], out["n_filtered"]):
+                n_ub += 1                       # the reference's int conversion overflowed: it gave up after that hypothesis
+                assert r["pairs"].shape[0] == 0 and r["hyp_used"] < out["hyp_used"] and np.array_equal(r["T"], np.eye(4, dtype=np.float32))
+                continue
             assert np.array_equal(np.stack([out["mq"][out["inliers"]], out["mt"][out["inliers"]]], 1), r["pairs"])
             assert out["hyp_used"] == r["hyp_used"] and out["inlier_ratio"] == r["ratio"]
             assert_pose(out["T"], r["T"])
             assert r["pairs"].shape[0] > 300
+    assert n_ub <= 2
 
 
 def test_frame_to_frame_device_equals_reference_build(ctx, O):
