@@ -85,7 +85,6 @@ void nccl_load(NcclApi* out) {
 }
 constexpr int kNcclUint8 = 1, kNcclInt32 = 2;
 // below this many keyframes per GPU the sweep uses 128-row tiles as work units (see hamming.cu, split form)
-constexpr int kSplitMaxKeyframes = 4096;
 
 // what a *_resident re-run needs to replay a pipeline on the buffers already in HBM
 struct F2MState {
@@ -130,7 +129,16 @@ struct pslam_ctx {
     int n_tiles = 0;
     bool tiles_dirty = true;
     int max_kf_desc = 0;        // largest keyframe appended so far
-    int lc_work_unit = 0;       // 0 auto, 1 keyframes, 2 tiles
+    int lc_work_unit = 0;       // 0 range form (contiguous tile ranges, fused tail), 1 keyframes, 2 tiles (round-1 forms)
+    DevBuf d_range;             // range form: row pieces | column pieces of the keyframes cut by CTA ranges
+    int* d_kf_done = nullptr;   // per-keyframe tile counters of those keyframes (zero between launches)
+    unsigned int* d_cta_done = nullptr;
+    // peer exchange of the sharded sweep (CUDA IPC over NVLink); p2p false -> NCCL all-gather + merge kernel
+    int* d_xchg = nullptr;
+    int* peer_xchg[64] = {nullptr};
+    bool p2p = false;
+    uint32_t lc_epoch = 0, lc_qepoch = 0;
+    bool lc_query_in_xchg = false;   // the resident query of this rank was pushed into the exchange buffer by the root
     int kf_cap = 0, n_kf = 0, kf_id_base = 0;
     long long desc_id_base = 0;
     DevBuf d_knn;  // V2 sweep scratch: per-CTA partials | merged keys | gathered keys | idx | dist
@@ -385,7 +393,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
     cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p); cudaFree(ctx->d_knn.p);
-    cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p);
+    cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p); cudaFree(ctx->d_range.p); cudaFree(ctx->d_kf_done); cudaFree(ctx->d_cta_done);
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
@@ -1879,6 +1887,12 @@ int pslam_lc_db_reserve(pslam_ctx* ctx, int64_t max_descriptors, int max_keyfram
         int* ns = nullptr;
         CK(cudaMalloc((void**)&no, sizeof(int64_t) * ((size_t)max_keyframes + 1)));
         CK(cudaMalloc((void**)&ns, sizeof(int) * ((size_t)max_keyframes + 1)));
+        int* nk = nullptr;
+        CK(cudaMalloc((void**)&nk, sizeof(int) * ((size_t)max_keyframes + 1)));
+        CK(cudaMemsetAsync(nk, 0, sizeof(int) * ((size_t)max_keyframes + 1), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_kf_done) CK(cudaFree(ctx->d_kf_done));
+        ctx->d_kf_done = nk;
         if (ctx->d_kf_off) {
             CK(cudaMemcpyAsync(no, ctx->d_kf_off, sizeof(int64_t) * ((size_t)ctx->n_kf + 1), cudaMemcpyDeviceToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -1961,6 +1975,7 @@ int pslam_lc_set_work_unit(pslam_ctx* ctx, int mode) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (mode < 0 || mode > 2) return fail(ctx, PSLAM_ERR_ARG, "work unit mode must be 0, 1 or 2");
     ctx->lc_work_unit = mode;
+    ctx->tiles_dirty = true;
     return PSLAM_OK;
 }
 
@@ -1976,6 +1991,9 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->lc_configured) {
         CK(lc_sweep_configure());
+        CK(lc_sweep_range_configure());
+        CK(cudaMalloc((void**)&ctx->d_cta_done, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(ctx->d_cta_done, 0, sizeof(unsigned int), ctx->stream));
         CK(cudaMalloc((void**)&ctx->d_lc_query, (size_t)PSLAM_LC_MAX_QUERY * 32));
         CK(cudaMalloc((void**)&ctx->d_lc_pairs, sizeof(int) * 2 * PSLAM_LC_MAX_TOPK * (2 + 64)));
         CK(cudaEventCreate(&ctx->ev_sweep0));
@@ -1987,34 +2005,76 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
         TRY(ensure_host(ctx, ctx->h_in, (size_t)nq * 32));
         memcpy(ctx->h_in.p, query, (size_t)nq * 32);
         CK(cudaMemcpyAsync(ctx->d_lc_query, ctx->h_in.p, (size_t)nq * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->lc_query_in_xchg = false;
     }
     ctx->lc_nq = nq;
     return PSLAM_OK;
 }
 
-static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k) {
+// tile prefix counts of the keyframes (host mirror -> device), recomputed after appends
+static int lc_refresh_tiles(pslam_ctx* ctx) {
+    if (!ctx->tiles_dirty) return PSLAM_OK;
+    std::vector<int> ts((size_t)ctx->n_kf + 1, 0);
+    for (int k = 0; k < ctx->n_kf; ++k)
+        ts[(size_t)k + 1] = ts[(size_t)k] + (int)((ctx->h_kf_off[(size_t)k + 1] - ctx->h_kf_off[(size_t)k] + 127) / 128);
+    ctx->n_tiles = ts[(size_t)ctx->n_kf];
+    const bool keep_f2m = ctx->f2m.valid, keep_f2f = ctx->f2f.valid;   // these buffers are not the frame arenas
+    TRY(ensure_dev(ctx, ctx->d_tile_start, sizeof(int) * ts.size()));
+    if (ctx->lc_work_unit == 2) {
+        const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
+        TRY(ensure_dev(ctx, ctx->d_split, o_col + lc_split_colmin_bytes(ctx->n_kf)));
+    }
+    ctx->f2m.valid = keep_f2m; ctx->f2f.valid = keep_f2f;
+    CK(cudaMemcpyAsync(ctx->d_tile_start.p, ts.data(), sizeof(int) * ts.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // ts is a stack-lifetime host buffer
+    ctx->tiles_dirty = false;
+    return PSLAM_OK;
+}
+
+static int* lc_merged_pairs(pslam_ctx* ctx) { return ctx->d_lc_pairs + 2 * PSLAM_LC_MAX_TOPK + 2 * PSLAM_LC_MAX_TOPK * 64; }
+
+// One sweep of the resident query over this ctx's keyframes + local top-k.  exchange: the peer exchange and merge of the
+// per-rank top-k run in the kernel's tail (range form with peer access only); pushed_query: the query sits in the exchange
+// buffer (pushed by the root rank) and the kernel waits for its flag.
+static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k, bool exchange = false, bool pushed_query = false) {
+    const bool query_in_xchg = pushed_query || (ctx->lc_query_in_xchg && ctx->lc_work_unit == 0 && ctx->d_xchg);
     int l = 0;
     if (ctx->lc_nq > 1024 && ctx->max_kf_desc > lc_max_kf_desc_wide())
         return fail(ctx, PSLAM_ERR_UNSUPPORTED, "more than 1024 query descriptors need keyframes of at most %d descriptors (largest: %d)",
                     lc_max_kf_desc_wide(), ctx->max_kf_desc);
-    // work-unit choice: whole keyframes when every CTA gets many of them, 128-row tiles otherwise
-    const bool split = ctx->n_kf > 0 && (ctx->lc_work_unit == 2 || (ctx->lc_work_unit == 0 && ctx->n_kf < kSplitMaxKeyframes));
-    if (split && ctx->tiles_dirty) {
-        std::vector<int> ts((size_t)ctx->n_kf + 1, 0);
-        for (int k = 0; k < ctx->n_kf; ++k)
-            ts[(size_t)k + 1] = ts[(size_t)k] + (int)((ctx->h_kf_off[(size_t)k + 1] - ctx->h_kf_off[(size_t)k] + 127) / 128);
-        ctx->n_tiles = ts[(size_t)ctx->n_kf];
-        const bool keep_f2m = ctx->f2m.valid, keep_f2f = ctx->f2f.valid;   // these buffers are not the frame arenas
-        TRY(ensure_dev(ctx, ctx->d_tile_start, sizeof(int) * ts.size()));
-        const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
-        TRY(ensure_dev(ctx, ctx->d_split, o_col + lc_split_colmin_bytes(ctx->n_kf)));
+    TRY(lc_refresh_tiles(ctx));
+    if (ctx->lc_work_unit == 0) {
+        // range form: contiguous 128-row tile ranges per CTA, keyframes cut by a range are merged by the last piece,
+        // the last CTA computes the top-k (and the peer exchange) -- one launch
+        const int grid = lc_range_grid(ctx->lc_nq, ctx->n_tiles, ctx->sm_count);
+        const size_t o_col = (lc_range_rowpart_bytes(grid) + 255) & ~(size_t)255;
+        const bool keep_f2m = ctx->f2m.valid, keep_f2f = ctx->f2f.valid;
+        TRY(ensure_dev(ctx, ctx->d_range, o_col + lc_range_colpart_bytes(grid)));
         ctx->f2m.valid = keep_f2m; ctx->f2f.valid = keep_f2f;
-        CK(cudaMemcpyAsync(ctx->d_tile_start.p, ts.data(), sizeof(int) * ts.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));   // ts is a stack-lifetime host buffer
-        ctx->tiles_dirty = false;
+        LcSweepArgs a;
+        a.query = reinterpret_cast<const uint4*>(query_in_xchg ? (const uint8_t*)(ctx->d_xchg + kLcXchgQueryOff) : ctx->d_lc_query);
+        a.nq = ctx->lc_nq;
+        a.db = reinterpret_cast<const uint4*>(ctx->d_db); a.kf_off = ctx->d_kf_off; a.tile_start = (const int*)ctx->d_tile_start.p;
+        a.n_kf = ctx->n_kf; a.n_tiles = ctx->n_tiles; a.tau = tau;
+        a.scores = ctx->d_scores;
+        a.rowpart = (uint32_t*)ctx->d_range.p; a.colpart = (uint32_t*)(ctx->d_range.p + o_col); a.kf_done = ctx->d_kf_done;
+        a.cta_done = ctx->d_cta_done;
+        a.kf_id_base = ctx->kf_id_base; a.k = k;
+        a.out_pairs = ctx->d_lc_pairs; a.out_merged = lc_merged_pairs(ctx);
+        a.x.world = ctx->world; a.x.rank = ctx->rank; a.x.epoch = ctx->lc_epoch;
+        a.x.local = exchange ? ctx->d_xchg : nullptr;
+        for (int r = 0; r < kLcMaxRanks; ++r) a.x.peer[r] = (exchange && r < ctx->world) ? ctx->peer_xchg[r] : nullptr;
+        a.qflag = pushed_query ? reinterpret_cast<const uint32_t*>(ctx->d_xchg) + kLcXchgQFlagOff : nullptr;
+        a.qepoch = ctx->lc_qepoch;
+        CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
+        CK(launch_lc_sweep_range(a, grid, ctx->stream, &l));
+        CK(cudaEventRecord(ctx->ev_sweep1, ctx->stream));
+        ctx->launches += l;
+        return PSLAM_OK;
     }
+    // round-1 forms, kept behind pslam_lc_set_work_unit: whole keyframes per CTA (1) / 128-row tiles + finalize (2)
     CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
-    if (split) {
+    if (ctx->lc_work_unit == 2) {
         const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
         CK(launch_lc_sweep_split(ctx->d_lc_query, ctx->lc_nq, ctx->d_db, ctx->d_kf_off, (const int*)ctx->d_tile_start.p,
                                  ctx->n_kf, ctx->n_tiles, tau, (uint32_t*)ctx->d_split.p, (uint32_t*)(ctx->d_split.p + o_col),
@@ -2081,6 +2141,72 @@ int pslam_comm_unique_id(uint8_t id_out[128]) {
     return PSLAM_OK;
 }
 
+// Peer exchange buffers of the sharded sweep: every rank allocates one (cudaMalloc), the CUDA IPC handles travel through
+// ncclAllGather, every rank opens its peers' buffers (NVLink / NVSwitch peer access) and the ranks agree -- again through an
+// all-gather -- whether ALL of them succeeded.  PSLAM_LC_P2P=0 in the environment keeps the NCCL path.
+static void lc_peer_teardown(pslam_ctx* ctx) {
+    for (int r = 0; r < 64; ++r) {
+        if (ctx->peer_xchg[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_xchg[r]);
+        ctx->peer_xchg[r] = nullptr;
+    }
+    if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+    ctx->d_xchg = nullptr;
+    ctx->p2p = false;
+    ctx->lc_query_in_xchg = false;
+}
+static int lc_peer_setup(pslam_ctx* ctx) {
+    lc_peer_teardown(ctx);
+    ctx->lc_epoch = 0; ctx->lc_qepoch = 0;
+    if (ctx->world <= 1) return PSLAM_OK;
+    NcclApi* api = nccl_api();
+    const char* env = getenv("PSLAM_LC_P2P");
+    int want = !(env && env[0] == '0');
+    const int W = ctx->world;
+    uint8_t* d_tmp = nullptr;
+    if (cudaMalloc((void**)&d_tmp, 128 * (size_t)(W + 1)) != cudaSuccess) return PSLAM_OK;
+    std::vector<uint8_t> h(128 * (size_t)(W + 1), 0);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (want) {
+        if (cudaMalloc((void**)&ctx->d_xchg, sizeof(int) * kLcXchgWords) != cudaSuccess) { ctx->d_xchg = nullptr; want = 0; }
+        else if (cudaMemset(ctx->d_xchg, 0, sizeof(int) * kLcXchgWords) != cudaSuccess || cudaIpcGetMemHandle(&mine, ctx->d_xchg) != cudaSuccess) want = 0;
+        cudaGetLastError();
+    }
+    // round 1: handles (64 bytes) + the rank's own verdict so far
+    memcpy(h.data(), &mine, sizeof(mine));
+    h[64] = (uint8_t)want;
+    bool ok = cudaMemcpyAsync(d_tmp, h.data(), 128, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+              api->AllGather(d_tmp, d_tmp + 128, 128, kNcclUint8, ctx->comm, ctx->stream) == 0 &&
+              cudaMemcpyAsync(h.data() + 128, d_tmp + 128, 128 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    int all = ok ? 1 : 0;
+    for (int r = 0; r < W && all; ++r) all = h[128 + 128 * (size_t)r + 64] ? 1 : 0;
+    int opened = all;
+    if (all) {
+        for (int r = 0; r < W; ++r) {
+            if (r == ctx->rank) { ctx->peer_xchg[r] = ctx->d_xchg; continue; }
+            cudaIpcMemHandle_t hr;
+            memcpy(&hr, h.data() + 128 + 128 * (size_t)r, sizeof(hr));
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+            ctx->peer_xchg[r] = (int*)p;
+        }
+    }
+    // round 2: did every rank open every buffer?
+    if (ok) {
+        h[0] = (uint8_t)opened;
+        ok = cudaMemcpyAsync(d_tmp, h.data(), 128, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+             api->AllGather(d_tmp, d_tmp + 128, 128, kNcclUint8, ctx->comm, ctx->stream) == 0 &&
+             cudaMemcpyAsync(h.data() + 128, d_tmp + 128, 128 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+             cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+        for (int r = 0; r < W && ok; ++r) if (!h[128 + 128 * (size_t)r]) opened = 0;
+    }
+    cudaFree(d_tmp);
+    if (!ok || !opened) { lc_peer_teardown(ctx); return PSLAM_OK; }
+    ctx->p2p = true;
+    return PSLAM_OK;
+}
+
 int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (!id || world < 1 || rank < 0 || rank >= world || world > 64) return fail(ctx, PSLAM_ERR_ARG, "pslam_comm_init: bad argument");
@@ -2094,6 +2220,7 @@ int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world) 
     if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
     ctx->rank = rank;
     ctx->world = world;
+    lc_peer_setup(ctx);          // best effort: without peer access the NCCL all-gather path is used
     return PSLAM_OK;
 }
 
@@ -2102,6 +2229,7 @@ int pslam_comm_destroy(pslam_ctx* ctx) {
     if (ctx->comm && nccl_api()->ok) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        lc_peer_teardown(ctx);
         nccl_api()->CommDestroy(ctx->comm);
     }
     ctx->comm = nullptr;
@@ -2112,15 +2240,36 @@ int pslam_comm_destroy(pslam_ctx* ctx) {
 
 static int lc_enqueue_sharded(pslam_ctx* ctx, int root, int tau, int k) {
     NcclApi* api = nccl_api();
-    if (ctx->world > 1 && root >= 0) {
-        const int r = api->Broadcast(ctx->d_lc_query, ctx->d_lc_query, (size_t)ctx->lc_nq * 32, kNcclUint8, root, ctx->comm, ctx->stream);
-        if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
+    if (ctx->world <= 1) return lc_enqueue_local(ctx, tau, k);
+    const bool peer = ctx->p2p && ctx->lc_work_unit == 0;
+    ++ctx->lc_epoch;
+    bool pushed = false;
+    if (root >= 0) {
+        if (peer) {
+            // the root writes the query into every rank's exchange buffer over NVLink and raises the query flags; the sweep
+            // kernels wait for the flag (no collective launch on the critical path)
+            ++ctx->lc_qepoch;
+            pushed = true;
+            ctx->lc_query_in_xchg = true;
+            if (ctx->rank == root) {
+                LcExchange x;
+                x.world = ctx->world; x.rank = ctx->rank; x.epoch = ctx->lc_epoch; x.local = ctx->d_xchg;
+                for (int r = 0; r < kLcMaxRanks; ++r) x.peer[r] = r < ctx->world ? ctx->peer_xchg[r] : nullptr;
+                int l = 0;
+                CK(launch_lc_push_query(ctx->d_lc_query, ctx->lc_nq, x, ctx->lc_qepoch, ctx->stream, &l));
+                ctx->launches += l;
+            }
+        } else {
+            const int r = api->Broadcast(ctx->d_lc_query, ctx->d_lc_query, (size_t)ctx->lc_nq * 32, kNcclUint8, root, ctx->comm, ctx->stream);
+            if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
+            ctx->lc_query_in_xchg = false;
+        }
     }
-    TRY(lc_enqueue_local(ctx, tau, k));
-    if (ctx->world > 1) {
+    TRY(lc_enqueue_local(ctx, tau, k, peer, pushed));
+    if (!peer) {
         int* local = ctx->d_lc_pairs;
         int* gathered = ctx->d_lc_pairs + 2 * PSLAM_LC_MAX_TOPK;
-        int* merged = gathered + 2 * PSLAM_LC_MAX_TOPK * 64;
+        int* merged = lc_merged_pairs(ctx);
         const int r = api->AllGather(local, gathered, 2 * (size_t)k, kNcclInt32, ctx->comm, ctx->stream);
         if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclAllGather: %s", api->GetErrorString ? api->GetErrorString(r) : "error");
         int l = 0;

@@ -27,6 +27,43 @@ size_t lc_split_colmin_bytes(int n_kf);
 cudaError_t launch_lc_sweep_split(const uint8_t* d_query, int nq, const uint8_t* d_db, const int64_t* d_kf_off,
                                   const int* d_tile_start, int n_kf, int n_tiles, int tau, uint32_t* d_rowpart,
                                   uint32_t* d_colmin, int* d_scores, int sm_count, cudaStream_t st, int* launches);
+// ---- lc_sweep.cu: range-form sweep with the fused tail (local top-k, peer exchange, merge) ---------------------------
+// Exchange buffer of one rank (cudaMalloc'ed, opened by the peers through CUDA IPC), in 4-byte words:
+//   [kLcXchgPairsOff ...)  pairs  [2 banks][kLcMaxRanks][2 * kLcMaxTopk] int   {score, id} written by rank r into slot r
+//   [kLcXchgFlagsOff ...)  flags  [2 banks][kLcMaxRanks] uint32               = epoch of the query the slot belongs to
+//   [kLcXchgQFlagOff]      qflag  uint32                                       = epoch of the query in the query buffer
+//   [kLcXchgQueryOff ...)  query  2048 x 32 B                                  pushed by the root rank
+constexpr int kLcMaxRanks = 64;
+constexpr int kLcMaxTopk = 64;
+constexpr size_t kLcXchgPairsOff = 0;
+constexpr size_t kLcXchgFlagsOff = kLcXchgPairsOff + 2 * (size_t)kLcMaxRanks * 2 * kLcMaxTopk;
+constexpr size_t kLcXchgQFlagOff = kLcXchgFlagsOff + 2 * (size_t)kLcMaxRanks;
+constexpr size_t kLcXchgQueryOff = ((kLcXchgQFlagOff + 1 + 63) / 64) * 64;           // 256-byte aligned
+constexpr size_t kLcXchgWords = kLcXchgQueryOff + 2048 * 8;
+struct LcExchange {
+    int world = 1, rank = 0;
+    uint32_t epoch = 0;              // of this query; bank = epoch & 1
+    int* local = nullptr;            // this rank's exchange buffer (null: no peer exchange, NCCL path)
+    int* peer[kLcMaxRanks];          // every rank's buffer as seen from this GPU (peer[rank] == local)
+};
+struct LcSweepArgs {
+    const uint4* query; int nq;
+    const uint4* db; const int64_t* kf_off; const int* tile_start; int n_kf, n_tiles, tau;
+    int* scores;
+    uint32_t* rowpart; uint32_t* colpart; int* kf_done;      // pieces of the keyframes cut by a CTA's tile range
+    unsigned int* cta_done;                                  // grid-wide completion counter (zero between launches)
+    int kf_id_base, k;
+    int* out_pairs;                                          // local top-k: k x {score, id}
+    int* out_merged;                                         // global top-k after the peer exchange
+    LcExchange x;
+    const uint32_t* qflag; uint32_t qepoch;                  // wait for the pushed query (null: the query is already here)
+};
+cudaError_t lc_sweep_range_configure();
+int lc_range_grid(int nq, int n_tiles, int sm_count);
+size_t lc_range_rowpart_bytes(int grid);
+size_t lc_range_colpart_bytes(int grid);
+cudaError_t launch_lc_sweep_range(const LcSweepArgs& a, int grid, cudaStream_t st, int* launches);
+cudaError_t launch_lc_push_query(const uint8_t* d_query, int nq, const LcExchange& x, uint32_t qepoch, cudaStream_t st, int* launches);
 // in-place re-encoding of n descriptor rows (32 B each) for the encoded Hamming compare of the sweep kernels
 cudaError_t launch_lc_encode_rows(uint8_t* d_rows, long long n, cudaStream_t st, int* launches);
 cudaError_t launch_lc_topk(const int* d_scores, int n_kf, int kf_id_base, int k, int* d_out_pairs, cudaStream_t st,
