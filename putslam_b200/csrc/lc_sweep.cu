@@ -26,10 +26,10 @@
 
 namespace pslam {
 
-__device__ __forceinline__ long long range_begin(int c, int grid, int n_tiles) { return ((long long)c * n_tiles) / grid; }
+__device__ __forceinline__ int range_begin(int c, int grid, int n_tiles) { return (int)(((long long)c * n_tiles) / grid); }
 // CTA that owns tile g: the largest c with range_begin(c) <= g
-__device__ __forceinline__ int range_owner(long long g, int grid, int n_tiles) {
-    int c = (int)((g * grid) / n_tiles);
+__device__ __forceinline__ int range_owner(int g, int grid, int n_tiles) {
+    int c = (int)(((long long)g * grid) / n_tiles);
     if (c >= grid) c = grid - 1;
     while (c + 1 < grid && range_begin(c + 1, grid, n_tiles) <= g) ++c;
     while (c > 0 && range_begin(c, grid, n_tiles) > g) --c;
@@ -37,8 +37,7 @@ __device__ __forceinline__ int range_owner(long long g, int grid, int n_tiles) {
 }
 
 struct RangeCursor {  // walks the tiles [g, g_end) of one CTA in order
-    int kf, tile, ntiles, cnt;
-    long long g;
+    int kf, tile, ntiles, cnt, g;
     int64_t off;
 };
 __device__ __forceinline__ void rc_load_kf(RangeCursor& c, const int64_t* __restrict__ kf_off, int n_kf) {
@@ -50,17 +49,17 @@ __device__ __forceinline__ void rc_load_kf(RangeCursor& c, const int64_t* __rest
         ++c.kf;                                    // empty keyframes own no tile
     }
 }
-__device__ __forceinline__ void rc_seek(RangeCursor& c, long long g, const int* __restrict__ tile_start,
+__device__ __forceinline__ void rc_seek(RangeCursor& c, int g, const int* __restrict__ tile_start,
                                         const int64_t* __restrict__ kf_off, int n_kf) {
     int lo = 0, hi = n_kf;                         // largest kf with tile_start[kf] <= g (the last such one is non-empty)
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if ((long long)tile_start[mid] <= g) lo = mid; else hi = mid;
+        if (tile_start[mid] <= g) lo = mid; else hi = mid;
     }
     c.kf = lo;
     c.g = g;
     rc_load_kf(c, kf_off, n_kf);
-    c.tile = (int)(g - tile_start[c.kf]);
+    c.tile = g - tile_start[c.kf];
 }
 __device__ __forceinline__ void rc_next(RangeCursor& c, const int64_t* __restrict__ kf_off, int n_kf) {
     ++c.g;
@@ -232,7 +231,7 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
     uint32_t* partial = reinterpret_cast<uint32_t*>(smem_raw + kStages * kTT * 32);            // 2*NW*kTT
     uint32_t* colmin = partial + 2 * NW * kTT;                                                 // kMaxKfDesc
     uint64_t* bars = reinterpret_cast<uint64_t*>(colmin + kMaxKfDesc);                         // kStages
-    int* s_int = reinterpret_cast<int*>(bars + kStages);                                       // score, flag
+    int* s_int = reinterpret_cast<int*>(bars + kStages);                                       // score, flag, -, -, producer cursor
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = (int)gridDim.x, b = (int)blockIdx.x;
@@ -256,14 +255,11 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
     for (int kf = b * NT + tid; kf < a.n_kf; kf += G * NT)
         if (a.kf_off[kf + 1] == a.kf_off[kf]) a.scores[kf] = 0;
 
-    const long long g0 = range_begin(b, G, a.n_tiles), g1 = range_begin(b + 1, G, a.n_tiles);
-    RangeCursor prod, cons;
-    if (g0 < g1) {
-        rc_seek(cons, g0, a.tile_start, a.kf_off, a.n_kf);
-        prod = cons;
-    } else {
-        cons.g = prod.g = g1; cons.kf = prod.kf = a.n_kf; cons.tile = cons.ntiles = cons.cnt = 0; cons.off = 0; prod = cons;
-    }
+    const int g0 = range_begin(b, G, a.n_tiles), g1 = range_begin(b + 1, G, a.n_tiles);
+    RangeCursor cons;
+    RangeCursor& prod = *reinterpret_cast<RangeCursor*>(s_int + 4);   // only thread 0 walks it: kept out of everybody's registers
+    if (g0 < g1) rc_seek(cons, g0, a.tile_start, a.kf_off, a.n_kf);
+    else { cons.g = g1; cons.kf = a.n_kf; cons.tile = cons.ntiles = cons.cnt = 0; cons.off = 0; }
     int issued = 0;
     auto issue = [&]() {
         const int cnt = min(kTT, prod.cnt - prod.tile * kTT);
@@ -273,11 +269,13 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
         ++issued;
         rc_next(prod, a.kf_off, a.n_kf);
     };
-    if (tid == 0)
+    if (tid == 0) {
+        prod = cons;
         for (int s = 0; s < kStages - 1 && prod.g < g1; ++s) issue();
+    }
 
     int seg_tile0 = cons.tile;          // first tile (within its keyframe) of the piece being accumulated
-    long long seg_g0 = cons.g;
+    bool first_piece = true;            // the piece that starts at g0 (slot 2b); a later cut piece is the last one (slot 2b + 1)
     for (int it = 0; cons.g < g1; ++it) {
         const int stage = it % kStages;
         const uint32_t phase = (uint32_t)(it / kStages) & 1u;
@@ -312,7 +310,7 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
                 if (tid == 0) { a.scores[cons.kf] = s_int[0]; s_int[0] = 0; }
             } else {
                 // a keyframe cut by the range: publish this piece, the CTA that completes the keyframe scores it
-                const int slot = 2 * b + (seg_g0 == g0 ? 0 : 1);
+                const int slot = 2 * b + (first_piece ? 0 : 1);
                 uint32_t* rp = a.rowpart + (size_t)slot * (RQ * NT);
                 uint32_t* cp = a.colpart + (size_t)slot * kMaxKfDesc;
 #pragma unroll
@@ -326,7 +324,7 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
                 __syncthreads();
                 if (s_int[1]) {
                     __threadfence();
-                    const long long T0 = a.tile_start[cons.kf], T1 = T0 + cons.ntiles;
+                    const int T0 = a.tile_start[cons.kf], T1 = T0 + cons.ntiles;
                     const int c_lo = range_owner(T0, G, a.n_tiles), c_hi = range_owner(T1 - 1, G, a.n_tiles);
                     int c = 0;
 #pragma unroll
@@ -339,9 +337,9 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
                         if (Q.off[j] < kKeyInvalid && rk != 0xffffffffu && (int)key_dist(rk) <= a.tau) {
                             const int t = (int)key_tidx<QB>(rk);
                             const int cc = range_owner(T0 + t / kTT, G, a.n_tiles);
-                            const long long sb = max(T0, range_begin(cc, G, a.n_tiles));
+                            const int sb = max(T0, range_begin(cc, G, a.n_tiles));
                             const int sl = 2 * cc + (T0 <= range_begin(cc, G, a.n_tiles) ? 0 : 1);
-                            if (__ldcg(a.colpart + (size_t)sl * kMaxKfDesc + (t - (int)(sb - T0) * kTT)) == rk) ++c;
+                            if (__ldcg(a.colpart + (size_t)sl * kMaxKfDesc + (t - (sb - T0) * kTT)) == rk) ++c;
                         }
                     }
                     c = (int)warp_add_u32((uint32_t)c);
@@ -352,11 +350,10 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
             }
 #pragma unroll
             for (int j = 0; j < RQ; ++j) rowmin[j] = 0xffffffffu;
-            seg_tile0 = kf_end ? 0 : cons.tile + 1;
-            seg_g0 = cons.g + 1;
+            seg_tile0 = 0;               // a piece only ends at a keyframe end or at the end of the range
+            first_piece = false;
         }
         rc_next(cons, a.kf_off, a.n_kf);
-        if (cons.tile == 0) seg_tile0 = 0;
     }
 
     // ---- tail: the CTA that finishes last turns the scores into the (global) top-k ----
@@ -379,7 +376,7 @@ lc_sweep_range_kernel(const LcSweepArgs a) {
 
 template <int NT>
 static size_t lc_range_smem() {
-    size_t s = (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * (NT / 32) * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16;
+    size_t s = (size_t)kStages * kTT * 32 + sizeof(uint32_t) * (2 * (NT / 32) * kTT + kMaxKfDesc) + sizeof(uint64_t) * kStages + 16 + 48;
     const size_t tail = kTopkSmemBytes > sizeof(unsigned long long) * 1024 ? kTopkSmemBytes : sizeof(unsigned long long) * 1024;
     return s > tail ? s : tail;
 }
