@@ -624,6 +624,7 @@ def run_ours(args):
     launches = ctx.launches - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
 
+    xmode = ctx.lc_exchange_mode()
     # ---- e2e: the public C-ABI call with HOST buffers (pinned staging, H2D query, D2H top-k inside) ----
     for i in range(args.warmup):
         ctx.lc_query_sharded(queries[i % 4] if (rank == 0 or world == 1) else None, root=root, tau=TAU, k=TOPK, nq=NQ)
@@ -691,9 +692,13 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"C4 loop-closure sweep: {NQ} query descriptors vs {n_kf} keyframes x {PER_KF} ORB "
                                    f"descriptors ({total_desc * 32 / 1e6:.0f} MB map resident in HBM), tau {TAU}, top-{TOPK}",
-                       "parallelism": (f"keyframes sharded over {world} rank(s); inside the timed region every step: broadcast of the "
-                                       f"query from rank 0, sweep + top-k on every shard, exchange + merge of the top-k; no host "
-                                       f"barrier between steps") if world > 1 else "1 GPU, no collective",
+                       "parallelism": (f"keyframes sharded over {world} rank(s); inside the timed region every step: the query goes "
+                                       f"from rank 0 to every rank, sweep + top-k on every shard, exchange + merge of the top-k; no "
+                                       f"host barrier between steps; exchange = " +
+                                       ("peer memory over NVLink inside the sweep kernel (CUDA-IPC buffers, stores + flags)"
+                                        if xmode == 2 else "NCCL (ncclBroadcast + ncclAllGather + merge kernel)"))
+                                      if world > 1 else "1 GPU, no collective",
+                       "exchange_mode": xmode,
                        "l2": "L2 flushed (256 MiB write) between timed steps; step time = CUDA events on the ctx stream",
                        "result_ok": ok, "result_check": check},
             "e2e": {"value": e2e_val, "unit": "Gcmp/s", "ms_per_step": e2e_ms / args.steps,

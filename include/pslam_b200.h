@@ -452,12 +452,18 @@ PSLAM_API int pslam_lc_last_sweep_ms(pslam_ctx* ctx, float* ms_out);
 /* Multi-GPU (one process per GPU, keyframes sharded by rank).  The library brings up its own NCCL
  * communicator from a caller-distributed ncclUniqueId (128 bytes): rank 0 calls pslam_comm_unique_id,
  * ships the bytes to the other ranks over whatever the host application already has, every rank calls
- * pslam_comm_init.  pslam_lc_query_sharded: ncclBroadcast of the query descriptors from `root`
- * (root < 0: every rank already passes the same query), local sweep + local top-k, ncclAllGather of
- * k {score, id} pairs per rank, merge -> the same global top-k on every rank. */
+ * pslam_comm_init.  pslam_lc_query_sharded: the query descriptors go from `root` to every rank (root < 0: every rank already
+ * passes the same query), local sweep + local top-k, exchange of k {score, id} pairs per rank, merge -> the same global
+ * top-k on every rank.  With peer access between the GPUs the exchange runs inside the sweep kernel over NVLink
+ * (pslam_lc_exchange_mode); otherwise ncclBroadcast / ncclAllGather + a merge kernel. */
 PSLAM_API int pslam_comm_unique_id(uint8_t id_out[128]);
 PSLAM_API int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world);
 PSLAM_API int pslam_comm_destroy(pslam_ctx* ctx);
+/* How a sharded sweep exchanges its per-rank results: 0 = single rank, 1 = NCCL (ncclBroadcast of the query, ncclAllGather of
+ * the top-k, merge kernel), 2 = peer memory over NVLink (pslam_comm_init opened every rank's exchange buffer through CUDA IPC):
+ * the root rank stores the query into every peer's buffer, every rank stores its top-k into every peer's buffer from the tail
+ * of the sweep kernel and merges there.  PSLAM_LC_P2P=0 in the environment selects 1. */
+PSLAM_API int pslam_lc_exchange_mode(const pslam_ctx* ctx);
 PSLAM_API int pslam_lc_query_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int tau, int k,
                                      int* out_kf_ids, int* out_scores);
 PSLAM_API int pslam_lc_query_sharded_resident(pslam_ctx* ctx, int tau, int k);

@@ -2224,6 +2224,12 @@ int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world) 
     return PSLAM_OK;
 }
 
+int pslam_lc_exchange_mode(const pslam_ctx* ctx) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (ctx->world <= 1) return 0;
+    return (ctx->p2p && ctx->lc_work_unit == 0) ? 2 : 1;
+}
+
 int pslam_comm_destroy(pslam_ctx* ctx) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (ctx->comm && nccl_api()->ok) {
