@@ -65,6 +65,21 @@ int main(int argc, char** argv) {
         ratio = matcher.matchXYZCore(map, curDesc, cur3D, curKp, cdet, 0.12, 0.55, 1, rp, K, T, mm, mi);
     }
     const double map_ms = (now_ms() - t0) / frames;
+    // the same call with the map side's buffers page-locked once (MatcherB200::pinMapSide -> pslam_host_register): the
+    // 0.34 MB of map arrays go to the device from where they lie, without the staging copy
+    double map_pinned_ms = -1.0;
+    if (matcher.pinMapSide(map)) {
+        std::vector<cv::DMatch> pm, pi;
+        Eigen::Matrix4f Tp;
+        for (int i = 0; i < warmup + frames; ++i) {
+            if (i == warmup) t0 = now_ms();
+            matcher.setSeed((uint64_t)i);
+            matcher.matchXYZCore(map, curDesc, cur3D, curKp, cdet, 0.12, 0.55, 1, rp, K, Tp, pm, pi);
+        }
+        map_pinned_ms = (now_ms() - t0) / frames;
+        if (pm.size() != mm.size() || pi.size() != mi.size()) map_pinned_ms = -2.0;
+        matcher.unpinMapSide();
+    }
 
     // the same frame against the map resident in HBM: only the pose and the current keypoints are sent.  The map is in
     // the camera frame here, so the pose is the identity, every view axis is the optical axis and all 5000 features
@@ -191,6 +206,7 @@ int main(int argc, char** argv) {
            "\"orb_detect_describe_ms\": %.5f, \"orb_detect_describe_rgb_frame_ms\": %.5f, \"orb_rgb_described\": %zu, "
            "\"orb_detect_describe_one_upload_ms\": %.5f, \"orb_detect_describe_rgb_frame_one_upload_ms\": %.5f, ",
            orb_ms, orb_kept, det_ms, det_n, det_desc_ms, det_desc_rgb_ms, det_rgb_n, det_desc_once_ms, det_desc_rgb_once_ms);
+    printf("\"frame_to_map_pinned_map_ms\": %.5f, ", map_pinned_ms);
     printf("\"frame_to_map_ms\": %.5f, \"frame_to_resident_map_ms\": %.5f, \"resident_kept\": %zu, "
            "\"resident_equals_host_map\": %s, \"map_matches\": %zu, \"map_inliers\": %zu, \"map_ratio\": %.4f, "
            "\"vo_three_calls_ms\": %.5f, \"vo_fused_ms\": %.5f, \"vo_matches\": %zu, \"vo_inliers\": %zu, \"vo_fused_inliers\": %zu, "

@@ -200,6 +200,29 @@ static int predictedLevel(int detLevel, double detDist, double curDist) {
     return curLevel;
 }
 
+void MatcherB200::unpinMapSide() {
+    pslam_ctx* c = dev_.ctx();
+    for (const void* p : pinnedMap_) if (c) pslam_host_unregister(c, p);
+    pinnedMap_.clear();
+}
+
+bool MatcherB200::pinMapSide(const MapSide& map) {
+    unpinMapSide();
+    pslam_ctx* c = dev_.ctx();
+    if (!c || map.octave.empty()) return false;
+    const size_t M = map.octave.size();
+    struct R { const void* p; size_t bytes; } ranges[4] = {
+        {map.xyz.data(), 24 * M}, {map.descriptors.data, map.descriptors.isContinuous() ? 32 * M : 0},
+        {map.octave.data(), 4 * M}, {map.detDist.data(), 8 * M}};
+    bool all = true;
+    for (const R& r : ranges) {
+        if (!r.p || !r.bytes) { all = false; continue; }
+        if (pslam_host_register(c, r.p, r.bytes) == PSLAM_OK) pinnedMap_.push_back(r.p);
+        else all = false;
+    }
+    return all;
+}
+
 double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescriptors,
                                  std::vector<Eigen::Vector3f>& currentPoseFeatures3D,
                                  std::vector<cv::KeyPoint>& currentPoseKeyPoints, std::vector<double>& currentPoseDetDists,

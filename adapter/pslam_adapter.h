@@ -203,7 +203,13 @@ public:
     // to the device; false (default): computed on the device (pslam_frame_to_map_features), same values, ~0.2 ms less
     // host time per frame
     void setHostLevels(bool on) { hostLevels_ = on; }
+    // Page-lock the buffers of a map side that is handed to matchXYZCore frame after frame (pslam_host_register): its
+    // descriptors, positions, octaves and detDists then go to the device straight from the MapSide, without the staging
+    // copy (0.34 MB per frame at 5000 features).  Call again after the MapSide changed size; unpinMapSide before it dies.
+    bool pinMapSide(const MapSide& map);
+    void unpinMapSide();
 private:
+    std::vector<const void*> pinnedMap_;
     Device dev_;
     uint64_t seed_ = 0x5eed5eedULL;
     int numHyp_ = 0;

@@ -449,6 +449,14 @@ PSLAM_API int pslam_lc_query_resident(pslam_ctx* ctx, int tau, int k);
 /* device time (CUDA events on the ctx stream) of the sweep kernel of the most recent query on this ctx */
 PSLAM_API int pslam_lc_last_sweep_ms(pslam_ctx* ctx, float* ms_out);
 
+/* Caller-pinned input buffers.  Every entry point copies its host inputs through a page-locked staging arena (one memcpy +
+ * one cudaMemcpyAsync).  A caller whose buffers live across calls (a map side kept on the host, descriptor matrices reused
+ * from frame to frame) can page-lock them once: inputs that lie inside a registered range are copied to the device straight
+ * from where they are, without the staging memcpy (pslam_frame_to_map / pslam_frame_to_map_features use this for every
+ * array).  The range must stay valid and unchanged in size until pslam_host_unregister (or pslam_ctx_destroy). */
+PSLAM_API int pslam_host_register(pslam_ctx* ctx, const void* ptr, size_t bytes);
+PSLAM_API int pslam_host_unregister(pslam_ctx* ctx, const void* ptr);
+
 /* Multi-GPU (one process per GPU, keyframes sharded by rank).  The library brings up its own NCCL
  * communicator from a caller-distributed ncclUniqueId (128 bytes): rank 0 calls pslam_comm_unique_id,
  * ships the bytes to the other ranks over whatever the host application already has, every rank calls

@@ -118,6 +118,9 @@ struct pslam_ctx {
     char err[512] = {0};
     uint64_t launches = 0;
     HostBuf h_in, h_out;
+    // caller memory page-locked through pslam_host_register: copied to the device straight from where it lies
+    struct PinnedRange { const uint8_t* p; size_t bytes; };
+    std::vector<PinnedRange> pinned;
     DevBuf d_in, d_out, d_work;
     // loop-closure database
     uint8_t* d_db = nullptr;
@@ -387,11 +390,15 @@ int pslam_ctx_create(int device, pslam_ctx** out) {
     return PSLAM_OK;
 }
 
+static void lc_peer_teardown(pslam_ctx* ctx);
 void pslam_ctx_destroy(pslam_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    lc_peer_teardown(ctx);
     if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
+    for (const auto& r : ctx->pinned) cudaHostUnregister(const_cast<uint8_t*>(r.p));
+    cudaGetLastError();
     cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p); cudaFree(ctx->d_knn.p);
     cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p); cudaFree(ctx->d_range.p); cudaFree(ctx->d_kf_done); cudaFree(ctx->d_cta_done);
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
@@ -837,6 +844,57 @@ int pslam_transform_uncertainty_batch(pslam_ctx* ctx, const double* A, const dou
     return PSLAM_OK;
 }
 
+// ---- caller-pinned input buffers ---------------------------------------------------------------------
+int pslam_host_register(pslam_ctx* ctx, const void* ptr, size_t bytes) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (!ptr || bytes == 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_host_register: empty range");
+    CK(cudaSetDevice(ctx->device));
+    for (const auto& r : ctx->pinned)
+        if (r.p == (const uint8_t*)ptr && r.bytes == bytes) return PSLAM_OK;
+    const cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, PSLAM_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    ctx->pinned.push_back({(const uint8_t*)ptr, bytes});
+    return PSLAM_OK;
+}
+int pslam_host_unregister(pslam_ctx* ctx, const void* ptr) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    for (size_t i = 0; i < ctx->pinned.size(); ++i)
+        if (ctx->pinned[i].p == (const uint8_t*)ptr) {
+            cudaSetDevice(ctx->device);
+            cudaStreamSynchronize(ctx->stream);          // no copy from the range may still be in flight
+            cudaHostUnregister(const_cast<void*>(ptr));
+            cudaGetLastError();
+            ctx->pinned.erase(ctx->pinned.begin() + (long)i);
+            return PSLAM_OK;
+        }
+    return fail(ctx, PSLAM_ERR_ARG, "pslam_host_unregister: range was not registered on this ctx");
+}
+static bool host_is_pinned(const pslam_ctx* ctx, const void* p, size_t bytes) {
+    const uint8_t* q = (const uint8_t*)p;
+    for (const auto& r : ctx->pinned)
+        if (q >= r.p && q + bytes <= r.p + r.bytes) return true;
+    return false;
+}
+// Host -> device placement of the inputs of one call.  Inputs inside a registered range go with their own asynchronous
+// copy from where they lie; the others are packed into the pinned arena and leave with one copy.
+struct Uploader {
+    pslam_ctx* ctx; uint8_t* d; uint8_t* h;
+    size_t lo = (size_t)-1, hi = 0;
+    cudaError_t err = cudaSuccess;
+    void put(size_t off, const void* src, size_t bytes) {
+        if (bytes == 0 || err != cudaSuccess) return;
+        if (host_is_pinned(ctx, src, bytes)) { err = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream); return; }
+        memcpy(h + off, src, bytes);
+        if (off < lo) lo = off;
+        if (off + bytes > hi) hi = off + bytes;
+    }
+    cudaError_t flush() {
+        if (err != cudaSuccess) return err;
+        if (hi > lo) return cudaMemcpyAsync(d + lo, h + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream);
+        return cudaSuccess;
+    }
+};
+
 // ---- fused pipelines ----------------------------------------------------------------------------
 // host-libm tables for the device level prediction (see guided.cu)
 struct HostLevelTables {
@@ -905,8 +963,9 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     Arena in, out, work;
     // host-level path: map xyz (float) + levels are inputs; device-level path: map xyz (double), octaves, detDists
     const size_t o_mx = in.take((dev_levels ? 24 : 12) * (size_t)M), o_md = in.take(32 * (size_t)M), o_ml = in.take(4 * (size_t)M);
+    const size_t o_mdet = in.take(dev_levels ? 8 * (size_t)M : 8);
     const size_t o_cx = in.take(12 * (size_t)N), o_cd = in.take(32 * (size_t)N), o_cl = in.take(4 * (size_t)N);
-    const size_t o_mdet = in.take(dev_levels ? 8 * (size_t)M : 8), o_cdet = in.take(dev_levels ? 8 * (size_t)N : 8);
+    const size_t o_cdet = in.take(dev_levels ? 8 * (size_t)N : 8);
     const size_t o_wx = work.take(12 * (size_t)M), o_wml = work.take(4 * (size_t)M), o_wcl = work.take(4 * (size_t)N);
     const size_t o_g = out.take(sizeof(int) * (2 + 3 * (size_t)cap));
     const size_t o_res = out.take(sizeof(int) * ransac_result_ints(cap));
@@ -916,19 +975,21 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     TRY(ensure_dev(ctx, ctx->d_work, work.off));
-    uint8_t* h = ctx->h_in.p;
-    memcpy(h + o_md, map_desc, 32 * (size_t)M);
-    memcpy(h + o_cx, cur_xyz, 12 * (size_t)N); memcpy(h + o_cd, cur_desc, 32 * (size_t)N);
-    if (dev_levels) {
-        memcpy(h + o_mx, raw.map_xyz_d, 24 * (size_t)M); memcpy(h + o_ml, raw.map_oct, 4 * (size_t)M);
-        memcpy(h + o_mdet, raw.map_det, 8 * (size_t)M);
-        memcpy(h + o_cl, raw.cur_oct, 4 * (size_t)N); memcpy(h + o_cdet, raw.cur_det, 8 * (size_t)N);
-    } else {
-        memcpy(h + o_mx, map_xyz, 12 * (size_t)M); memcpy(h + o_ml, map_level, 4 * (size_t)M);
-        memcpy(h + o_cl, cur_level, 4 * (size_t)N);
-    }
-    CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* d = ctx->d_in.p;
+    Uploader up{ctx, d, ctx->h_in.p};
+    // the current frame's (small) arrays sit together at the end of the arena so that they leave with one copy; the map
+    // side goes straight from the caller's memory when that is registered (pslam_host_register)
+    up.put(o_cx, cur_xyz, 12 * (size_t)N); up.put(o_cd, cur_desc, 32 * (size_t)N);
+    if (dev_levels) { up.put(o_cl, raw.cur_oct, 4 * (size_t)N); up.put(o_cdet, raw.cur_det, 8 * (size_t)N); }
+    else up.put(o_cl, cur_level, 4 * (size_t)N);
+    up.put(o_md, map_desc, 32 * (size_t)M);
+    if (dev_levels) {
+        up.put(o_mx, raw.map_xyz_d, 24 * (size_t)M); up.put(o_ml, raw.map_oct, 4 * (size_t)M);
+        up.put(o_mdet, raw.map_det, 8 * (size_t)M);
+    } else {
+        up.put(o_mx, map_xyz, 12 * (size_t)M); up.put(o_ml, map_level, 4 * (size_t)M);
+    }
+    CK(up.flush());
     F2MState& s = ctx->f2m;
     s.device_levels = dev_levels;
     s.M = M; s.N = N;

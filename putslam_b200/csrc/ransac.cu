@@ -713,9 +713,17 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     // shared-memory staging of the winner's inliers for the refit: up to 8192 inliers (192 KB)
     int stage_cap = ws.m_cap < 8192 ? ws.m_cap : 8192;
     const size_t sel_smem = sizeof(float) * 6 * (size_t)stage_cap;
-    // per-device function attribute; setting it again is harmless, so no cross-thread state is kept
-    if ((e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4)) != cudaSuccess)
-        return e;
+    // per-device function attribute, set once per device (a relaxed flag: setting it twice is harmless)
+    {
+        static bool configured[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+            if ((e = cudaFuncSetAttribute(ransac_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * 8192 * 4)) != cudaSuccess)
+                return e;
+            if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+    }
     if ((e = launch_chained(ransac_select_kernel, dim3(1), dim3(kSelThreads), sel_smem, st, ws.pts, ws.m_cap, ws.keep,
                             ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf, P.min_matches,
                             P.min_inlier_ratio, P.iters_min_ratio, S, P.seed_lo, P.seed_hi,
