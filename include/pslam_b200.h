@@ -454,6 +454,10 @@ PSLAM_API int pslam_lc_last_sweep_ms(pslam_ctx* ctx, float* ms_out);
  * from frame to frame) can page-lock them once: inputs that lie inside a registered range are copied to the device straight
  * from where they are, without the staging memcpy (pslam_frame_to_map / pslam_frame_to_map_features use this for every
  * array).  The range must stay valid and unchanged in size until pslam_host_unregister (or pslam_ctx_destroy). */
+/* Diagnostics: host-side phase times (microseconds since the call began) of the last pslam_frame_to_map* call on this ctx:
+ * [1] inputs packed  [2] host->device copies enqueued  [3] kernels enqueued  [4] device->host copy enqueued
+ * [5] stream synchronised  [6] results unpacked. */
+PSLAM_API int pslam_debug_host_stamps(const pslam_ctx* ctx, double out8[8]);
 PSLAM_API int pslam_host_register(pslam_ctx* ctx, const void* ptr, size_t bytes);
 PSLAM_API int pslam_host_unregister(pslam_ctx* ctx, const void* ptr);
 

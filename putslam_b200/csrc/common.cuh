@@ -19,9 +19,51 @@ __device__ __forceinline__ void chain_begin() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next kernel in the stream be scheduled
     asm volatile("griddepcontrol.wait;" ::: "memory");                // predecessor complete, memory visible
 }
+// A frame's chain can also be RECORDED instead of launched: while a ChainRecorder is active on the calling thread every
+// launch_chained() appends {function, grid, block, shared memory, a copy of the arguments} to it, and the owner replays the
+// list as one CUDA graph (ctx.cu: one cudaGraphLaunch per frame instead of one launch call per kernel; the executable graph
+// is kept while the chain's shape -- functions, grids, blocks -- stays the same and only the node arguments are refreshed).
+#ifndef __CUDACC_RTC__
+#include <cstring>
+#include <vector>
+struct ChainRecorder {
+    struct Node {
+        const void* func; dim3 grid, block; size_t smem;
+        std::vector<unsigned char> blob;       // argument values, each at an 16-byte aligned offset
+        std::vector<size_t> offs;
+    };
+    std::vector<Node> nodes;
+    size_t used = 0;                           // nodes of the current recording (the vector's entries are reused)
+    bool active = false;
+    Node& next() {
+        if (used == nodes.size()) nodes.emplace_back();
+        Node& n = nodes[used++];
+        n.offs.clear();
+        return n;
+    }
+};
+extern thread_local ChainRecorder* g_chain_recorder;   // defined in ctx.cu
+template <typename T>
+inline void chain_record_arg(ChainRecorder::Node& n, size_t& at, const T& v) {
+    at = (at + 15) & ~(size_t)15;
+    if (n.blob.size() < at + sizeof(T)) n.blob.resize(at + sizeof(T) + 256);
+    std::memcpy(n.blob.data() + at, &v, sizeof(T));
+    n.offs.push_back(at);
+    at += sizeof(T);
+}
+#endif
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                   Args&&... args) {
+    if (g_chain_recorder && g_chain_recorder->active) {
+        ChainRecorder::Node& n = g_chain_recorder->next();
+        n.func = (const void*)kernel; n.grid = grid; n.block = block; n.smem = smem;
+        size_t at = 0;
+        (void)at;
+        int dummy[] = {0, (chain_record_arg<KArgs>(n, at, static_cast<KArgs>(args)), 0)...};
+        (void)dummy;
+        return cudaSuccess;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -13,8 +13,10 @@
 
 #include <mutex>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
+#include "common.cuh"
 #include "geometry.cuh"
 #include "kernels.h"
 
@@ -121,6 +123,16 @@ struct pslam_ctx {
     // caller memory page-locked through pslam_host_register: copied to the device straight from where it lies
     struct PinnedRange { const uint8_t* p; size_t bytes; };
     std::vector<PinnedRange> pinned;
+    double stamps[8] = {0};   // host-side phase times (us) of the last fused frame call
+    // fused frame chains replayed as CUDA graphs (one per chain kind: frame-to-map, frame-to-frame)
+    ChainRecorder recorder;
+    struct ChainGraph {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        std::vector<cudaGraphNode_t> nodes;
+        struct Sig { const void* func; dim3 grid, block; size_t smem; };
+        std::vector<Sig> sig;
+    } graph_f2m, graph_f2f;
+    int use_graphs = 1;       // PSLAM_GRAPHS=0 in the environment: plain launches
     DevBuf d_in, d_out, d_work;
     // loop-closure database
     uint8_t* d_db = nullptr;
@@ -365,6 +377,77 @@ void unpack_ransac_result(const int* res, float* T_out, int* inl_out, int* n_inl
 }  // namespace
 
 // =============================================================================================
+// ---- frame chains as CUDA graphs -----------------------------------------------------------------------
+thread_local ChainRecorder* g_chain_recorder = nullptr;
+
+static void chain_graph_free(pslam_ctx::ChainGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr; g.nodes.clear(); g.sig.clear();
+}
+// Replays the kernels recorded in ctx->recorder as one graph launch.  The executable graph is rebuilt when the chain's
+// shape (functions, grid / block sizes, shared memory) changes; otherwise only the node arguments are refreshed.
+static cudaError_t chain_graph_submit(pslam_ctx* ctx, pslam_ctx::ChainGraph& g) {
+    ChainRecorder& R = ctx->recorder;
+    const size_t n = R.used;
+    if (n == 0) return cudaSuccess;
+    std::vector<void*> argv;
+    auto params_of = [&](const ChainRecorder::Node& nd, cudaKernelNodeParams& p) {
+        argv.resize(nd.offs.size());
+        for (size_t a = 0; a < nd.offs.size(); ++a) argv[a] = (void*)(nd.blob.data() + nd.offs[a]);
+        p = cudaKernelNodeParams();
+        p.func = const_cast<void*>(nd.func); p.gridDim = nd.grid; p.blockDim = nd.block;
+        p.sharedMemBytes = (unsigned int)nd.smem; p.kernelParams = argv.data(); p.extra = nullptr;
+    };
+    bool same = g.exec && g.sig.size() == n;
+    for (size_t i = 0; same && i < n; ++i) {
+        const auto& a = g.sig[i]; const auto& b = R.nodes[i];
+        same = a.func == b.func && a.smem == b.smem && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.grid.z == b.grid.z &&
+               a.block.x == b.block.x && a.block.y == b.block.y && a.block.z == b.block.z;
+    }
+    cudaError_t e;
+    if (!same) {
+        chain_graph_free(g);
+        if ((e = cudaGraphCreate(&g.graph, 0)) != cudaSuccess) return e;
+        g.nodes.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            cudaKernelNodeParams p;
+            params_of(R.nodes[i], p);
+            if ((e = cudaGraphAddKernelNode(&g.nodes[i], g.graph, i ? &g.nodes[i - 1] : nullptr, i ? 1 : 0, &p)) != cudaSuccess) return e;
+            g.sig.push_back({R.nodes[i].func, R.nodes[i].grid, R.nodes[i].block, R.nodes[i].smem});
+        }
+        if ((e = cudaGraphInstantiate(&g.exec, g.graph, 0)) != cudaSuccess) return e;
+    } else {
+        for (size_t i = 0; i < n; ++i) {
+            cudaKernelNodeParams p;
+            params_of(R.nodes[i], p);
+            if ((e = cudaGraphExecKernelNodeSetParams(g.exec, g.nodes[i], &p)) != cudaSuccess) return e;
+        }
+    }
+    return cudaGraphLaunch(g.exec, ctx->stream);
+}
+// run `enqueue` (a function that only issues launch_chained calls on the ctx stream) either directly or recorded + replayed
+template <typename F>
+static int chain_run(pslam_ctx* ctx, pslam_ctx::ChainGraph& g, F enqueue) {
+    if (!ctx->use_graphs) return enqueue();
+    ctx->recorder.used = 0;
+    ctx->recorder.active = true;
+    g_chain_recorder = &ctx->recorder;
+    const int r = enqueue();
+    ctx->recorder.active = false;
+    g_chain_recorder = nullptr;
+    if (r != PSLAM_OK) return r;
+    const cudaError_t e = chain_graph_submit(ctx, g);
+    if (e != cudaSuccess) {   // graphs unavailable for this chain: fall back to plain launches for good
+        cudaGetLastError();
+        chain_graph_free(g);
+        ctx->use_graphs = 0;
+        return enqueue();
+    }
+    return PSLAM_OK;
+}
+
+
 extern "C" {
 
 int pslam_version(void) { return 100; }
@@ -382,6 +465,7 @@ int pslam_ctx_create(int device, pslam_ctx** out) {
     pslam_ctx* ctx = new pslam_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    { const char* g = getenv("PSLAM_GRAPHS"); ctx->use_graphs = !(g && g[0] == '0'); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return PSLAM_ERR_CUDA;
@@ -396,6 +480,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     lc_peer_teardown(ctx);
+    chain_graph_free(ctx->graph_f2m); chain_graph_free(ctx->graph_f2f);
     if (ctx->comm && nccl_api()->ok) nccl_api()->CommDestroy(ctx->comm);
     for (const auto& r : ctx->pinned) cudaHostUnregister(const_cast<uint8_t*>(r.p));
     cudaGetLastError();
@@ -895,6 +980,18 @@ struct Uploader {
     }
 };
 
+// host-side phase stamps of the last fused call (pslam_debug_host_stamps): nanoseconds since the call began
+struct Stamp {
+    pslam_ctx* c; std::chrono::steady_clock::time_point t0;
+    explicit Stamp(pslam_ctx* ctx) : c(ctx), t0(std::chrono::steady_clock::now()) { for (double& v : c->stamps) v = 0; }
+    void mark(int k) { c->stamps[k] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+};
+int pslam_debug_host_stamps(const pslam_ctx* ctx, double out8[8]) {
+    if (!ctx || !out8) return PSLAM_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->stamps[i];
+    return PSLAM_OK;
+}
+
 // ---- fused pipelines ----------------------------------------------------------------------------
 // host-libm tables for the device level prediction (see guided.cu)
 struct HostLevelTables {
@@ -915,7 +1012,11 @@ static const HostLevelTables& level_tables() {
     return t;
 }
 
-static int enqueue_f2m(pslam_ctx* ctx) {
+static int enqueue_f2m_launches(pslam_ctx* ctx);
+static int enqueue_f2m(pslam_ctx* ctx) {   // the chain of one frame-to-map frame, replayed as one CUDA graph
+    return chain_run(ctx, ctx->graph_f2m, [&]() { return enqueue_f2m_launches(ctx); });
+}
+static int enqueue_f2m_launches(pslam_ctx* ctx) {
     F2MState& s = ctx->f2m;
     int l = 0;
     if (s.device_levels) {
@@ -946,6 +1047,7 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     const bool dev_levels = raw.map_xyz_d != nullptr;
     if (!ctx) return PSLAM_ERR_ARG;
     if (!result || M < 0 || N < 0 || match_cap <= 0) return fail(ctx, PSLAM_ERR_ARG, "pslam_frame_to_map: bad argument");
+    Stamp stamp(ctx);
     memset(result, 0, sizeof(*result));
     for (int i = 0; i < 16; ++i) result->T[i] = (i % 5 == 0) ? 1.f : 0.f;
     result->inlier_ratio = -1.0;
@@ -989,7 +1091,9 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     } else {
         up.put(o_mx, map_xyz, 12 * (size_t)M); up.put(o_ml, map_level, 4 * (size_t)M);
     }
+    stamp.mark(1);
     CK(up.flush());
+    stamp.mark(2);
     F2MState& s = ctx->f2m;
     s.device_levels = dev_levels;
     s.M = M; s.N = N;
@@ -1009,9 +1113,12 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     s.rp = rp; s.ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
     s.valid = true;
     TRY(enqueue_f2m(ctx));
+    stamp.mark(3);
     ctx->d_last_counts = s.ws.counts; ctx->last_H = s.ws.h_cap;
     CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
+    stamp.mark(4);
     CK(cudaStreamSynchronize(ctx->stream));
+    stamp.mark(5);
     const int* g = (const int*)(ctx->h_out.p + o_g);
     const int total = g[0];
     const int n = total < cap ? total : cap;
@@ -1028,6 +1135,7 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     std::vector<int> inl_t((size_t)result->n_inliers);
     for (int i = 0; i < result->n_inliers; ++i) inl_t[i] = match_train_out[inlier_idx_out[i]];
     result->inlier_ratio = point_inlier_ratio(inl_t.data(), result->n_inliers, match_train_out, n);
+    stamp.mark(6);
     return PSLAM_OK;
 }
 
@@ -1067,7 +1175,11 @@ int pslam_frame_to_map_resident(pslam_ctx* ctx) {
     return enqueue_f2m(ctx);
 }
 
+static int enqueue_f2f_launches(pslam_ctx* ctx);
 static int enqueue_f2f(pslam_ctx* ctx) {
+    return chain_run(ctx, ctx->graph_f2f, [&]() { return enqueue_f2f_launches(ctx); });
+}
+static int enqueue_f2f_launches(pslam_ctx* ctx) {
     F2FState& s = ctx->f2f;
     int l = 0;
     CK(launch_bf_mutual(s.prev_desc, s.n_prev, s.cur_desc, s.n_cur, s.rowmin, s.colmin, s.mout, s.cap, ctx->sm_count,
