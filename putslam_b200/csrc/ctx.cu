@@ -244,6 +244,9 @@ int ensure_host(pslam_ctx* ctx, HostBuf& b, size_t bytes) {
     }
     CK(cudaMallocHost((void**)&b.p, want));
     b.cap = want;
+    // the result buffer moved: the resident chains write into it from the device (RansacWorkspace::out_host)
+    ctx->f2m.valid = false;
+    ctx->f2f.valid = false;
     return PSLAM_OK;
 }
 #define TRY(x)                     \
@@ -410,13 +413,35 @@ static cudaError_t chain_graph_submit(pslam_ctx* ctx, pslam_ctx::ChainGraph& g) 
         chain_graph_free(g);
         if ((e = cudaGraphCreate(&g.graph, 0)) != cudaSuccess) return e;
         g.nodes.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            cudaKernelNodeParams p;
-            params_of(R.nodes[i], p);
-            if ((e = cudaGraphAddKernelNode(&g.nodes[i], g.graph, i ? &g.nodes[i - 1] : nullptr, i ? 1 : 0, &p)) != cudaSuccess) return e;
-            g.sig.push_back({R.nodes[i].func, R.nodes[i].grid, R.nodes[i].block, R.nodes[i].smem});
+        // programmatic edges (the graph form of programmatic dependent launch): node k+1 is scheduled when node k executes
+        // griddepcontrol.launch_dependents (first statement of every chained kernel) and parks in griddepcontrol.wait until
+        // k has completed -- the same overlap of launch latency the plain launches get from launch_chained()
+        static const int pdl_edges = []() { const char* e = getenv("PSLAM_GRAPH_PDL"); return (e && e[0] == '1') ? 1 : 0; }();   // measured: plain edges are faster end to end
+        for (int programmatic = pdl_edges; programmatic >= 0; --programmatic) {
+            bool ok = true;
+            g.sig.clear();
+            for (size_t i = 0; i < n && ok; ++i) {
+                cudaKernelNodeParams p;
+                params_of(R.nodes[i], p);
+                if (programmatic) {
+                    ok = cudaGraphAddKernelNode(&g.nodes[i], g.graph, nullptr, 0, &p) == cudaSuccess;
+                    if (ok && i) {
+                        cudaGraphEdgeData ed = {};
+                        ed.from_port = cudaGraphKernelNodePortProgrammatic; ed.to_port = 0; ed.type = cudaGraphDependencyTypeProgrammatic;
+                        ok = cudaGraphAddDependencies_v2(g.graph, &g.nodes[i - 1], &g.nodes[i], &ed, 1) == cudaSuccess;
+                    }
+                } else {
+                    ok = cudaGraphAddKernelNode(&g.nodes[i], g.graph, i ? &g.nodes[i - 1] : nullptr, i ? 1 : 0, &p) == cudaSuccess;
+                }
+                g.sig.push_back({R.nodes[i].func, R.nodes[i].grid, R.nodes[i].block, R.nodes[i].smem});
+            }
+            if (ok && cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess) break;
+            cudaGetLastError();
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            cudaGraphDestroy(g.graph); g.graph = nullptr;
+            if (!programmatic) return cudaErrorUnknown;
+            if ((e = cudaGraphCreate(&g.graph, 0)) != cudaSuccess) return e;
         }
-        if ((e = cudaGraphInstantiate(&g.exec, g.graph, 0)) != cudaSuccess) return e;
     } else {
         for (size_t i = 0; i < n; ++i) {
             cudaKernelNodeParams p;
@@ -1111,11 +1136,13 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     s.count = (int*)(ctx->d_work.p + o_cnt); s.best = (int*)(ctx->d_work.p + o_best); s.cache = ctx->d_work.p + o_cache;
     s.gout = (int*)(ctx->d_out.p + o_g);
     s.rp = rp; s.ws = bind_ransac(L, ctx->d_work.p, (int*)(ctx->d_out.p + o_res));
+    // the last kernel of the chain writes the output arena into the page-locked result buffer itself: no copy-engine
+    // transfer (and its scheduling latency) between the end of the chain and the host
+    s.ws.out_host = ctx->h_out.p; s.ws.out_dev = ctx->d_out.p; s.ws.out_bytes = out.off;
     s.valid = true;
     TRY(enqueue_f2m(ctx));
     stamp.mark(3);
     ctx->d_last_counts = s.ws.counts; ctx->last_H = s.ws.h_cap;
-    CK(cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, out.off, cudaMemcpyDeviceToHost, ctx->stream));
     stamp.mark(4);
     CK(cudaStreamSynchronize(ctx->stream));
     stamp.mark(5);

@@ -136,6 +136,9 @@ struct RansacWorkspace {
     float* models;     // 12 * h_cap : per-hypothesis R (row-major) and t
     int* result;       // header (see ransac.cu) + inlier list (m_cap)
     int m_cap, h_cap;
+    // optional: when the selection kernel has written the result it copies out_bytes of the device output arena (match list
+    // + result) into page-locked host memory itself (posted writes over PCIe), so the call needs no device->host copy
+    void* out_host = nullptr; const void* out_dev = nullptr; size_t out_bytes = 0;
 };
 size_t ransac_result_ints(int m_cap);
 cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_mq, const int* d_mt,

@@ -336,12 +336,12 @@ __device__ long long g_sel_clk[16];
 #define SEL_CLK(k) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kSelThreads, 1)
-ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
-                     const int* __restrict__ n_filtered, const int* __restrict__ counts,
-                     const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
-                     int min_matches, double min_ratio, int iters_min, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
-                     int* __restrict__ inl_tmp /* m_cap scratch */, int stage_cap, int* __restrict__ result) {
+__device__ __forceinline__ void
+ransac_select_body(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
+                   const int* __restrict__ n_filtered, const int* __restrict__ counts,
+                   const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
+                   int min_matches, double min_ratio, int iters_min, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
+                   int* __restrict__ inl_tmp /* m_cap scratch */, int stage_cap, int* __restrict__ result) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     __shared__ unsigned long long best_key;
@@ -351,7 +351,6 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     __shared__ float s_R[9], s_t[3];
     __shared__ int s_ok;
 
-    chain_begin();
     SEL_CLK(0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mf = *n_filtered;
@@ -677,6 +676,23 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
     }
 }
 
+// the selection, then (optionally) the copy of the call's output arena into page-locked host memory by the same CTA
+__global__ void __launch_bounds__(kSelThreads, 1)
+ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __restrict__ keep,
+                     const int* __restrict__ n_filtered, const int* __restrict__ counts,
+                     const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
+                     int min_matches, double min_ratio, int iters_min, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
+                     int* __restrict__ inl_tmp, int stage_cap, int* __restrict__ result, uint4* __restrict__ out_host,
+                     const uint4* __restrict__ out_dev, int out_n16) {
+    chain_begin();
+    ransac_select_body(pts, m_cap, keep, n_filtered, counts, models, H, adaptive, stop_rule, usac_conf, min_matches, min_ratio,
+                       iters_min, S, seed_lo, seed_hi, inl_tmp, stage_cap, result);
+    if (out_host) {
+        __syncthreads();          // the result written above (and the match list of the earlier kernels) is visible
+        for (int i = threadIdx.x; i < out_n16; i += kSelThreads) out_host[i] = __ldcg(out_dev + i);
+    }
+}
+
 cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_mq, const int* d_mt, const int* d_m,
                           int m_host, const RansacDeviceParams& P, const RansacWorkspace& ws, int sm_count,
                           cudaStream_t st, int* launches) {
@@ -727,7 +743,9 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
     if ((e = launch_chained(ransac_select_kernel, dim3(1), dim3(kSelThreads), sel_smem, st, ws.pts, ws.m_cap, ws.keep,
                             ws.n_filtered, ws.counts, ws.models, H, adaptive, P.stop_rule, P.usac_conf, P.min_matches,
                             P.min_inlier_ratio, P.iters_min_ratio, S, P.seed_lo, P.seed_hi,
-                            ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap, ws.result)) != cudaSuccess)
+                            ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap, ws.result,
+                            reinterpret_cast<uint4*>(ws.out_host), reinterpret_cast<const uint4*>(ws.out_dev),
+                            (int)((ws.out_bytes + 15) / 16))) != cudaSuccess)
         return e;
     if (launches) *launches += 4;
     return cudaGetLastError();
