@@ -10,6 +10,15 @@
 #include <unordered_map>
 
 namespace putslam_b200 {
+// bytes from one row of a cv::Mat to the next: cv::Mat::step[0] in OpenCV, step0 in the stand-in types of shim/
+static inline size_t matRowBytes(const cv::Mat& m) {
+#ifdef PSLAM_USE_REAL_HEADERS
+    return (size_t)m.step[0];
+#else
+    return m.step0;
+#endif
+}
+
 
 static void logError(pslam_ctx* c, const char* where, int code) {
     std::cerr << "[putslam_b200] " << where << " failed (" << code << "): " << (c ? pslam_last_error(c) : "no context")
@@ -87,7 +96,7 @@ std::vector<Eigen::Vector3f> keypoints2Dto3D(std::vector<cv::Point2f> undistorte
     if (n <= 0) return features3D;
     pslam_ctx* c = defaultDevice().ctx();
     pslam_camera cam = cameraFrom(cameraMatrix, nullptr);
-    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
+    const int stride = (int)(matRowBytes(depthImage) / sizeof(uint16_t));
     const int r = c ? pslam_backproject(c, &undistortedFeatures2D[(size_t)startingID].x, n, depthImage.ptr<uint16_t>(0),
                                         depthImage.cols, depthImage.rows, stride, &cam, 0, depthImageScale, nullptr,
                                         features3D[0].data(), nullptr, nullptr, nullptr)
@@ -362,11 +371,7 @@ std::vector<cv::KeyPoint> MatcherB200::detectGrid(cv::Mat rgbImage, int gridCols
     }
     const auto compare_response = [](const cv::KeyPoint& p1, const cv::KeyPoint& p2) { return p1.response > p2.response; };
     const int W = rgbImage.cols, H = rgbImage.rows, ch = rgbImage.channels();
-#ifdef PSLAM_USE_REAL_HEADERS
-    const int rowBytes = (int)rgbImage.step[0];
-#else
-    const int rowBytes = (int)rgbImage.step0;
-#endif
+    const int rowBytes = (int)matRowBytes(rgbImage);
     const int maximalFeaturesInROI = maximalTrackedFeatures * 3 / (gridCols * gridRows);
     lastFrameData_ = nullptr;
     if (!fast && gridCols == 1 && gridRows == 1) {   // the whole frame goes to the device in one piece: describeFeatures may reuse it
@@ -426,11 +431,7 @@ cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint
     }
     descriptors.create(n, 32, CV_8U);
     int nOut = 0;
-#ifdef PSLAM_USE_REAL_HEADERS
-    const int rowBytes = (int)rgbImage.step[0];
-#else
-    const int rowBytes = (int)rgbImage.step0;
-#endif
+    const int rowBytes = (int)matRowBytes(rgbImage);
     const bool resident = reuseFrame_ && lastFrameData_ == rgbImage.data && lastFrameRows_ == rgbImage.rows &&
                           lastFrameCols_ == rgbImage.cols && lastFrameStep_ == rowBytes && lastFrameCh_ == rgbImage.channels();
     const int r = pslam_orb_describe(c, resident ? nullptr : rgbImage.data, rgbImage.cols, rgbImage.rows, rowBytes,
@@ -469,11 +470,7 @@ std::vector<cv::DMatch> MatcherB200::performTracking(cv::Mat prevImg, cv::Mat im
     if (prevImg.empty() || img.empty() || prevImg.rows != img.rows || prevImg.cols != img.cols || prevImg.channels() != img.channels() ||
         (init && (int)features.size() != n) || (int)prevKeyPoints.size() != n || (int)prevDetDists.size() != n)
         return giveUp(PSLAM_ERR_ARG);
-#ifdef PSLAM_USE_REAL_HEADERS
-    const int rowBytes = (int)img.step[0], prevRowBytes = (int)prevImg.step[0];
-#else
-    const int rowBytes = (int)img.step0, prevRowBytes = (int)prevImg.step0;
-#endif
+    const int rowBytes = (int)matRowBytes(img), prevRowBytes = (int)matRowBytes(prevImg);
     if (prevRowBytes != rowBytes) return giveUp(PSLAM_ERR_ARG);
     std::vector<float> prevXY(2 * (size_t)n + 2), curXY(2 * (size_t)n + 2), err((size_t)n + 1);
     std::vector<unsigned char> status((size_t)n + 1);
@@ -638,7 +635,7 @@ double MatcherB200::matchCore(cv::Mat prevDescriptors, const std::vector<Eigen::
     std::vector<float> md((size_t)cap);
     pslam_frame_result res;
     pslam_ctx* c = dev_.ctx();
-    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
+    const int stride = (int)(matRowBytes(depthImage) / sizeof(uint16_t));
     const int r = c ? pslam_frame_to_frame(c, pd, nPrev ? prevFeatures3D[0].data() : nullptr, nPrev, cd, uv.data(), nCur,
                                            depthImage.ptr<uint16_t>(0), depthImage.cols, depthImage.rows, stride, &cam,
                                            distCoeffs.empty() ? 0 : 1, depthImageScale, &a, seed_, numHyp_,
@@ -676,13 +673,8 @@ double MatcherB200::trackKLTCore(cv::Mat prevRgbImage, cv::Mat rgbImage, const s
         logError(c, "trackKLT", PSLAM_ERR_ARG);
         return 0.0;
     }
-#ifdef PSLAM_USE_REAL_HEADERS
-    const int rowBytes = (int)rgbImage.step[0], prevRowBytes = (int)prevRgbImage.step[0];
-    const int stride = (int)(depthImage.step[0] / sizeof(uint16_t));
-#else
-    const int rowBytes = (int)rgbImage.step0, prevRowBytes = (int)prevRgbImage.step0;
-    const int stride = (int)(depthImage.step0 / sizeof(uint16_t));
-#endif
+    const int rowBytes = (int)matRowBytes(rgbImage), prevRowBytes = (int)matRowBytes(prevRgbImage);
+    const int stride = (int)(matRowBytes(depthImage) / sizeof(uint16_t));
     if (prevRowBytes != rowBytes) { logError(c, "trackKLT", PSLAM_ERR_ARG); return 0.0; }
     RANSAC::parameters rp = ransacParams;
     rp.errorVersion = rp.errorVersionVO;                       // matcher.cpp:196-197

@@ -265,3 +265,50 @@ def merge_tracked(undist_xy, sandbox_undist_xy, min_reproj):
     added = np.empty(max(1, s.shape[0]), np.int32)
     k = lib().ref_merge_tracked(_p(u, C.c_float), u.shape[0], _p(s, C.c_float), s.shape[0], C.c_double(min_reproj), _p(added, C.c_int))
     return added[:k].copy()
+
+
+# ---- libref_tree.so: the reference's Matcher driving adapter/putslam_tree's MatcherB200 (needs a GPU to run) ------------
+class TreeArgs(C.Structure):
+    _fields_ = [("vo_tracking", C.c_int), ("error_version", C.c_int), ("thr_e", C.c_double), ("thr_r", C.c_double),
+                ("min_ratio", C.c_double), ("min_matches", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("dist", C.c_float * 5), ("grid_cols", C.c_int), ("grid_rows", C.c_int),
+                ("maximal_tracked_features", C.c_int), ("minimal_tracked_features", C.c_int), ("dbscan_eps", C.c_double),
+                ("win_size", C.c_int), ("max_levels", C.c_int), ("max_iter", C.c_int), ("eps", C.c_float),
+                ("tracking_error_threshold", C.c_double), ("tracking_min_eig_threshold", C.c_double),
+                ("min_reproj_dist", C.c_double), ("min_euclid_dist", C.c_double), ("remove_too_close", C.c_int)]
+
+
+def tree_args(vo_tracking=0, error_version=0, dist=(0, 0, 0, 0, 0), dbscan_eps=10.0, maximal_tracked=500, minimal_tracked=0):
+    """defaults = resources/putslammatcherOpenCVParameters.xml (RANSAC 0.04 / 2.0 / 0.2 / 15, grid 1 x 1, window 7, 3 levels,
+    30 iterations / 0.01, tracking thresholds 25 / 0 / 3 px)"""
+    return TreeArgs(vo_tracking, error_version, 0.04, 2.0, 0.2, 15, 517.3, 516.5, 318.6, 255.3, (C.c_float * 5)(*dist), 1, 1,
+                    maximal_tracked, minimal_tracked, dbscan_eps, 7, 3, 30, 0.01, 25.0, 0.0, 3.0, 0.0, 0)
+
+
+def tree_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_tree.so"))
+
+
+_tree = None
+
+
+def tree_run_vo(rgb0, depth0, rgb1, depth1, args=None, depth_scale=5000.0, seed=0, cap=4096):
+    """Matcher::detectInitFeatures(frame 0) + Matcher::runVO(frame 1) of the reference on a MatcherB200
+    -> dict(T, inliers (q, t), ratio, kp0 (x, y, octave), kp1, xyz1, hyp_used)"""
+    global _tree
+    if _tree is None:
+        _tree = C.CDLL(os.path.join(_HERE, "_ref", "libref_tree.so"))
+    rgb0 = np.ascontiguousarray(rgb0, np.uint8); rgb1 = np.ascontiguousarray(rgb1, np.uint8)
+    depth0 = np.ascontiguousarray(depth0, np.uint16); depth1 = np.ascontiguousarray(depth1, np.uint16)
+    H, W = depth0.shape
+    ch = 1 if rgb0.ndim == 2 else rgb0.shape[2]
+    args = args or tree_args()
+    T = np.empty((4, 4), np.float32); iq = np.empty(cap, np.int32); it = np.empty(cap, np.int32)
+    kp0 = np.empty((cap, 3), np.float32); kp1 = np.empty((cap, 3), np.float32); xyz1 = np.empty((cap, 3), np.float32)
+    ratio = C.c_double(0); n0 = C.c_int(0); n1 = C.c_int(0); used = C.c_int(0)
+    n = _tree.tree_run_vo(_p(rgb0, C.c_uint8), _p(depth0, C.c_uint16), _p(rgb1, C.c_uint8), _p(depth1, C.c_uint16), W, H, ch,
+                          C.c_double(depth_scale), C.byref(args), C.c_uint64(seed), _p(T, C.c_float), _p(iq, C.c_int), _p(it, C.c_int),
+                          C.byref(ratio), cap, _p(kp0, C.c_float), C.byref(n0), _p(kp1, C.c_float), _p(xyz1, C.c_float), C.byref(n1),
+                          C.byref(used))
+    return dict(T=T, inliers=np.stack([iq[:n], it[:n]], 1).copy(), ratio=ratio.value, kp0=kp0[:n0.value].copy(),
+                kp1=kp1[:n1.value].copy(), xyz1=xyz1[:n1.value].copy(), hyp_used=used.value)

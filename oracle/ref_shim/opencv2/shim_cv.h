@@ -123,13 +123,22 @@ struct DMatch {
     bool operator<(const DMatch& m) const { return distance < m.distance; }
 };
 
+struct MatStep {                                   // cv::MatStep: step[0] = bytes per row, converts to size_t
+    std::size_t p[2];
+    MatStep(std::size_t s = 0) { p[0] = s; p[1] = 0; }
+    operator std::size_t() const { return p[0]; }
+    std::size_t& operator[](int i) { return p[i]; }
+    const std::size_t& operator[](int i) const { return p[i]; }
+    MatStep& operator=(std::size_t s) { p[0] = s; return *this; }
+};
+
 class Mat {
     std::shared_ptr<std::vector<uchar> > buf;     // null for headers over user memory
     int type_;
 public:
     uchar* data;
     int rows, cols;
-    std::size_t step;                              // bytes per row
+    MatStep step;                                  // bytes per row
     Mat() : type_(0), data(nullptr), rows(0), cols(0), step(0) {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(int r, int c, int type, void* p) : type_(type), data((uchar*)p), rows(r), cols(c), step((std::size_t)c * elemSize()) {}
@@ -243,6 +252,14 @@ inline void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& D
         o[0] = (float)x; o[1] = (float)y;
     }
 }
+
+// ---- features2d types that appear as members of MatcherOpenCV (include/putslam/Matcher/matcherOpenCV.h:71-73); only
+// declared, never used: matcherOpenCV.cpp itself (ORB / SURF / SIFT creation) is not compiled into oracle/_ref
+template <typename T> using Ptr = std::shared_ptr<T>;
+class Feature2D { public: virtual ~Feature2D() {} };
+typedef Feature2D FeatureDetector;
+typedef Feature2D DescriptorExtractor;
+class BFMatcher { public: explicit BFMatcher(int = NORM_L2, bool = false) {} };
 
 // ---- display / colour helpers the reference calls only for debugging -----------------------------------------------
 inline void cvtColor(const Mat& src, Mat& dst, int) { dst.create(src.rows, src.cols, CV_8UC1); }   // result never read (RGBD.cpp:151-152)
