@@ -54,7 +54,7 @@ def test_reference_matcher_runs_vo_through_the_b200_virtuals(O, error_version, e
     out = R.tree_run_vo(rgb0, depth, rgb1, depth, args=args, seed=11)
     kp0, d0 = expected_features(cv2, a, eps)
     kp1, d1 = expected_features(cv2, b, eps)
-    assert np.array_equal(out["kp0"], kp0) and np.array_equal(out["kp1"], kp1) and len(kp0) > 150
+    assert np.array_equal(out["kp0"], kp0) and np.array_equal(out["kp1"], kp1) and len(kp0) > 80
     cam = (synth.FX, synth.FY, synth.CX, synth.CY)
     zero = (0, 0, 0, 0, 0)
     x0, _ = O.backproject(O.undistort(kp0[:, :2], *cam, zero), depth, *cam, 5000.0)
@@ -62,7 +62,7 @@ def test_reference_matcher_runs_vo_through_the_b200_virtuals(O, error_version, e
     assert np.array_equal(bits(out["xyz1"]), bits(x1))
     mq, mt, md = O.bf_mutual(d0, d1)
     ref = O.ransac(x0, x1, mq, mt, params=O.default_ransac_params(error_version), seed=11)
-    assert np.array_equal(out["inliers"], np.stack([mq[ref["inliers"]], mt[ref["inliers"]]], 1)) and len(ref["inliers"]) > 80
+    assert np.array_equal(out["inliers"], np.stack([mq[ref["inliers"]], mt[ref["inliers"]]], 1)) and len(ref["inliers"]) > 30
     assert out["hyp_used"] == ref["hyp_used"] and np.array_equal(bits(out["T"]), bits(ref["T"]))
     assert out["ratio"] == O.point_inlier_ratio(mt[ref["inliers"]], mt, len(kp1))
     # the estimated motion is the planted shift: (dx, dy) px at 2 m
