@@ -246,6 +246,15 @@ double MatcherB200::matchXYZCore(const MapSide& map, cv::Mat currentPoseDescript
         matchingXYZacceptRatioOfBestMatch = std::max(0.1, matchingXYZacceptRatioOfBestMatch - 0.05 * (computationNumber - 1));
     }
     const int N = (int)currentPoseKeyPoints.size(), M = (int)map.octave.size();
+    // no matches possible -> -1.0 like matcher.cpp:755-756; also keeps &v[0][0] off empty vectors.  Inconsistent list sizes
+    // (the reference asserts them, matcher.cpp:631-636) are refused instead of read out of bounds.
+    if (N == 0 || M == 0) return -1.0;
+    if ((int)currentPoseFeatures3D.size() != N || (int)currentPoseDetDists.size() != N || currentPoseDescriptors.rows != N ||
+        currentPoseDescriptors.cols * (int)currentPoseDescriptors.elemSize() != 32 || map.descriptors.rows != M ||
+        (int)map.xyz.size() != 3 * M || (int)map.detDist.size() != M) {
+        logError(dev_.ctx(), "matchXYZ", PSLAM_ERR_ARG);
+        return -1.0;
+    }
     std::vector<int> curLevels, mapLevels, curOct;
     std::vector<float> mapXyz;
     if (hostLevels_) {
@@ -373,10 +382,7 @@ std::vector<cv::KeyPoint> MatcherB200::detectGrid(cv::Mat rgbImage, int gridCols
     const int W = rgbImage.cols, H = rgbImage.rows, ch = rgbImage.channels();
     const int rowBytes = (int)matRowBytes(rgbImage);
     const int maximalFeaturesInROI = maximalTrackedFeatures * 3 / (gridCols * gridRows);
-    lastFrameData_ = nullptr;
-    if (!fast && gridCols == 1 && gridRows == 1) {   // the whole frame goes to the device in one piece: describeFeatures may reuse it
-        lastFrameData_ = rgbImage.data; lastFrameRows_ = H; lastFrameCols_ = W; lastFrameStep_ = rowBytes; lastFrameCh_ = ch;
-    }
+    lastFrameData_ = nullptr;   // set again below, only once the device really holds this frame
     // cv::ORB::create() keeps 500 per call (tied responses can add a few); cv::FAST has no budget: strict 3x3 maxima,
     // at most one per 2x2 pixels
     const int w = W / gridCols, h = H / gridRows;
@@ -393,6 +399,9 @@ std::vector<cv::KeyPoint> MatcherB200::detectGrid(cv::Mat rgbImage, int gridCols
                                : pslam_orb_detect(c, roi, w, h, rowBytes, ch, 1, 500, xy.data(), size.data(), angle.data(),
                                                   response.data(), octave.data(), cap, &n);
             if (r != PSLAM_OK) { logError(c, "detectFeatures", r); continue; }
+            if (!fast && gridCols == 1 && gridRows == 1) {   // the whole frame went to the device in one piece: describeFeatures may reuse it
+                lastFrameData_ = rgbImage.data; lastFrameRows_ = H; lastFrameCols_ = W; lastFrameStep_ = rowBytes; lastFrameCh_ = ch;
+            }
             std::vector<cv::KeyPoint> keypointsInROI((size_t)n);
             for (int j = 0; j < n; ++j) {
                 cv::KeyPoint& kp = keypointsInROI[(size_t)j];
@@ -440,7 +449,12 @@ cv::Mat MatcherB200::describeFeatures(cv::Mat rgbImage, std::vector<cv::KeyPoint
     if (r != PSLAM_OK) {
         logError(c, "describeFeatures", r);
         features.clear();
+        lastFrameData_ = nullptr;
         return cv::Mat();
+    }
+    if (!resident) {   // the frame resident on the device is now THIS one (uploaded by the call above)
+        lastFrameData_ = rgbImage.data; lastFrameRows_ = rgbImage.rows; lastFrameCols_ = rgbImage.cols; lastFrameStep_ = rowBytes;
+        lastFrameCh_ = rgbImage.channels();
     }
     std::vector<cv::KeyPoint> kept((size_t)nOut);
     for (int k = 0; k < nOut; ++k) kept[(size_t)k] = features[(size_t)order[(size_t)k]];

@@ -219,5 +219,21 @@ __device__ __forceinline__ uint32_t satsub_popc32(uint32_t a, uint32_t b) {
     return __popc(__vsubus4(a, b));
 }
 
+// Logical CTA index for grid-wide ordered compactions with look-back: the order in which the CTAs of this launch arrive
+// here, not blockIdx.x.  A CTA only ever waits on lower logical indices, i.e. on CTAs that are already running, so the
+// look-back cannot hang when other streams or processes keep part of the grid from being co-resident or the hardware hands
+// out block indices in another order.  The ticket word is {epoch : 32 | arrivals : 32}: the first CTA of a launch (a new
+// epoch) restarts the count, so nothing has to be reset between launches.
+__device__ __forceinline__ unsigned int take_cta_ticket(unsigned long long* word, unsigned int epoch) {
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(word), assumed;
+    unsigned int cnt;
+    do {
+        assumed = old;
+        cnt = ((unsigned int)(assumed >> 32) == epoch) ? (unsigned int)(assumed & 0xffffffffu) : 0u;
+        old = atomicCAS(word, assumed, ((unsigned long long)epoch << 32) | (unsigned long long)(cnt + 1u));
+    } while (old != assumed);
+    return cnt;
+}
+
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 __device__ __forceinline__ uint32_t warp_add_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }

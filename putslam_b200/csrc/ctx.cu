@@ -216,8 +216,9 @@ int fail(pslam_ctx* c, int code, const char* fmt, ...) {
 // Stamped per-CTA sums of the grid-wide ordered compactions (mapprep.cu, guided.cu): slots [0, sm) belong to
 // map_prepare_kernel, [sm, 3 sm) to guided_emit_kernel.  Zeroed once; every launch gets a fresh non-zero epoch.
 int next_epoch(pslam_ctx* ctx, unsigned int* epoch);
-unsigned long long* prep_slots(pslam_ctx* ctx) { return ctx->d_prep_counts; }
-unsigned long long* emit_slots(pslam_ctx* ctx) { return ctx->d_prep_counts + (ctx->sm_count > 0 ? ctx->sm_count : 1); }
+// look-back slot arrays, each preceded by its ticket word (common.cuh take_cta_ticket): [t][prep: sm][t][emit: 2 sm]
+unsigned long long* prep_slots(pslam_ctx* ctx) { return ctx->d_prep_counts + 1; }
+unsigned long long* emit_slots(pslam_ctx* ctx) { return ctx->d_prep_counts + 2 + (ctx->sm_count > 0 ? ctx->sm_count : 1); }
 
 int ensure_dev(pslam_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return PSLAM_OK;
@@ -235,6 +236,10 @@ int ensure_dev(pslam_ctx* ctx, DevBuf& b, size_t bytes) {
     return PSLAM_OK;
 }
 int ensure_host(pslam_ctx* ctx, HostBuf& b, size_t bytes) {
+    // every entry point that stages inputs passes through here with the input arena before it overwrites d_in / d_out /
+    // d_work: whatever resident frame chain pointed into them is stale from now on (the frame entry points set their own
+    // flag again once their inputs are in place)
+    if (&b == &ctx->h_in) { ctx->f2m.valid = false; ctx->f2f.valid = false; }
     if (bytes <= b.cap) return PSLAM_OK;
     size_t want = bytes + bytes / 4 + 4096;
     if (b.p) {
@@ -257,7 +262,7 @@ int ensure_host(pslam_ctx* ctx, HostBuf& b, size_t bytes) {
 
 int next_epoch(pslam_ctx* ctx, unsigned int* epoch) {
     if (!ctx->d_prep_counts) {
-        const size_t bytes = sizeof(unsigned long long) * 3 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1);
+        const size_t bytes = sizeof(unsigned long long) * (3 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1) + 2);
         CK(cudaMalloc((void**)&ctx->d_prep_counts, bytes));
         CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
     }
@@ -564,7 +569,7 @@ int pslam_backproject(pslam_ctx* ctx, const float* uv, int n, const uint16_t* de
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     memcpy(ctx->h_in.p + o_uv, uv, sizeof(float) * 2 * (size_t)n);
-    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * ((size_t)(H - 1) * row_stride + (size_t)W));   // not past the last row of an ROI
     CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
     int l = 0;
     CK(launch_backproject((const float*)(ctx->d_in.p + o_uv), n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H,
@@ -595,7 +600,7 @@ int pslam_normal_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint16_
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     memcpy(ctx->h_in.p + o_px, px, 8 * (size_t)n);
-    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * ((size_t)(H - 1) * row_stride + (size_t)W));   // not past the last row of an ROI
     CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
     int l = 0;
     CK(launch_normal_cov((const int*)(ctx->d_in.p + o_px), n, (const uint16_t*)(ctx->d_in.p + o_depth), W, H, row_stride, *cam,
@@ -639,8 +644,8 @@ int pslam_gradient_uncertainty(pslam_ctx* ctx, const int* px, int n, const uint8
     TRY(ensure_host(ctx, ctx->h_in, in.off)); TRY(ensure_dev(ctx, ctx->d_in, in.off));
     TRY(ensure_host(ctx, ctx->h_out, out.off)); TRY(ensure_dev(ctx, ctx->d_out, out.off));
     memcpy(ctx->h_in.p + o_px, px, 8 * (size_t)n);
-    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
-    memcpy(ctx->h_in.p + o_rgb, rgb, (size_t)H * rgb_row_bytes);
+    memcpy(ctx->h_in.p + o_depth, depth, sizeof(uint16_t) * ((size_t)(H - 1) * row_stride + (size_t)W));   // not past the last row of an ROI
+    memcpy(ctx->h_in.p + o_rgb, rgb, (size_t)(H - 1) * rgb_row_bytes + 3 * (size_t)W);
     CK(cudaMemcpyAsync(ctx->d_in.p, ctx->h_in.p, in.off, cudaMemcpyHostToDevice, ctx->stream));
     int diag[16];
     gradient_diag_table(diag);
@@ -1255,7 +1260,7 @@ int pslam_frame_to_frame(pslam_ctx* ctx, const uint8_t* prev_desc, const float* 
     uint8_t* h = ctx->h_in.p;
     if (n_prev > 0) { memcpy(h + o_pd, prev_desc, 32 * (size_t)n_prev); memcpy(h + o_px, prev_xyz, 12 * (size_t)n_prev); }
     memcpy(h + o_cd, cur_desc, 32 * (size_t)n_cur); memcpy(h + o_uv, cur_uv, 8 * (size_t)n_cur);
-    memcpy(h + o_depth, depth, sizeof(uint16_t) * (size_t)H * row_stride);
+    memcpy(h + o_depth, depth, sizeof(uint16_t) * ((size_t)(H - 1) * row_stride + (size_t)W));   // not past the last row of an ROI
     CK(cudaMemcpyAsync(ctx->d_in.p, h, in.off, cudaMemcpyHostToDevice, ctx->stream));
     uint8_t* d = ctx->d_in.p;
     F2FState& s = ctx->f2f;
@@ -1782,7 +1787,7 @@ static int klt_run(pslam_ctx* ctx, const char* who, const uint8_t* prev_image, c
                                   cudaMemcpyHostToDevice, ctx->stream));
     if (fr && n > 0) {
         memcpy(h + o_pxyz, fr->prev_xyz, 12 * (size_t)n);
-        memcpy(h + o_depth, fr->depth, depth_bytes);
+        memcpy(h + o_depth, fr->depth, sizeof(uint16_t) * ((size_t)(H - 1) * fr->depth_stride + (size_t)W));   // not past the last row of an ROI
         CK(cudaMemcpyAsync(ctx->d_in.p + o_pxyz, h + o_pxyz, o_depth + depth_bytes - o_pxyz, cudaMemcpyHostToDevice, ctx->stream));
     }
     int l = 0;

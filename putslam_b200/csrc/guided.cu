@@ -198,15 +198,19 @@ __global__ void __launch_bounds__(kEmitThreads)
 guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* __restrict__ count,
                    const uint2* __restrict__ cache, int* __restrict__ offsets, int cap, int* __restrict__ header,
                    int* __restrict__ out_q, int* __restrict__ out_t, float* __restrict__ out_d, int per_cta,
-                   unsigned long long* __restrict__ cta_sums /* 2 x gridDim.x: matches | perfect */, unsigned int epoch) {
+                   unsigned long long* __restrict__ cta_sums /* 2 x gridDim.x: matches | perfect; [-1] = ticket word */, unsigned int epoch) {
     constexpr int kW = kEmitThreads / 32;
     __shared__ int warp_tot[kW], warp_perf[kW];
     __shared__ int s_base, n_ovf;
     __shared__ int ovf_list[kEmitThreads];
+    __shared__ unsigned int s_bid;
     chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = take_cta_ticket(cta_sums - 1, epoch);
+    __syncthreads();
+    const int bid = (int)s_bid;                  // logical CTA index: arrival order (common.cuh take_cta_ticket)
     const int M = A.M_dev ? min(*A.M_dev, A.M) : A.M;
-    const int lo = min(M, (int)blockIdx.x * per_cta), hi = min(M, lo + per_cta);
+    const int lo = min(M, bid * per_cta), hi = min(M, lo + per_cta);
     const uint32_t lt = (1u << lane) - 1u;
 
     // range totals
@@ -227,11 +231,11 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
         volatile unsigned long long* sums = cta_sums;
         volatile unsigned long long* perfs = cta_sums + gridDim.x;
         if (lane == 0) {
-            sums[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)total;
-            perfs[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)perfect;
+            sums[bid] = ((unsigned long long)epoch << 32) | (unsigned int)total;
+            perfs[bid] = ((unsigned long long)epoch << 32) | (unsigned int)perfect;
         }
         int before = 0, perf_before = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+        for (int b = lane; b < bid; b += 32) {
             unsigned long long v, p;
             do { v = sums[b]; } while ((unsigned int)(v >> 32) != epoch);
             do { p = perfs[b]; } while ((unsigned int)(p >> 32) != epoch);
@@ -242,7 +246,7 @@ guided_emit_kernel(GuidedArgs A, const uint32_t* __restrict__ best, const int* _
         perf_before = (int)warp_add_u32((uint32_t)perf_before);
         if (lane == 0) {
             s_base = before;
-            if (blockIdx.x == gridDim.x - 1) {
+            if (bid == (int)gridDim.x - 1) {
                 offsets[M] = before + total; header[0] = before + total; header[1] = perf_before + perfect;
             }
         }

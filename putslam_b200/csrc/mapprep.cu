@@ -62,19 +62,24 @@ __device__ __forceinline__ MapFeatureEval eval_feature(const double* __restrict_
 // Ordered compaction over the whole grid.  Every CTA owns a contiguous range of features.  Pass 1 counts the kept
 // ones and publishes the count stamped with this launch's epoch; warp 0 then reads the stamped counts of all
 // preceding CTAs in parallel (a decoupled look-back: one L2 round trip after the slowest predecessor) to get the
-// CTA's output offset; pass 2 re-evaluates and writes in feature order.  The grid never exceeds the SM count, so all
-// CTAs are co-resident and the spin cannot deadlock; the stamps make a reset between launches unnecessary.
+// CTA's output offset; pass 2 re-evaluates and writes in feature order.  CTAs are numbered by
+// arrival (take_cta_ticket), so a CTA only waits on CTAs that are already running; the stamps make a reset between launches
+// unnecessary.
 constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads)
 map_prepare_kernel(const double* __restrict__ xyz, const float* __restrict__ view_axis, int M, int per_cta, MapPrepArgs A,
                    int* __restrict__ kept, double* __restrict__ xyz_local, double* __restrict__ uv,
                    double* __restrict__ angles, int* __restrict__ n_out, MapGather G,
-                   unsigned long long* __restrict__ cta_counts, unsigned int epoch) {
+                   unsigned long long* __restrict__ cta_counts /* [-1] = ticket word */, unsigned int epoch) {
     __shared__ int warp_tot[kPrepThreads / 32];
     __shared__ int s_base;
+    __shared__ unsigned int s_bid;
     chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lo = blockIdx.x * per_cta, hi = min(M, lo + per_cta);
+    if (tid == 0) s_bid = take_cta_ticket(cta_counts - 1, epoch);
+    __syncthreads();
+    const int bid = (int)s_bid;                  // logical CTA index: arrival order (see take_cta_ticket)
+    const int lo = min(M, bid * per_cta), hi = min(M, lo + per_cta);
 
     // pass 1: count
     int mine = 0;
@@ -87,10 +92,10 @@ map_prepare_kernel(const double* __restrict__ xyz, const float* __restrict__ vie
         for (int w = 0; w < kPrepThreads / 32; ++w) total += warp_tot[w];
         if (lane == 0) {
             const unsigned long long stamped = ((unsigned long long)epoch << 32) | (unsigned int)total;
-            *reinterpret_cast<volatile unsigned long long*>(cta_counts + blockIdx.x) = stamped;
+            *reinterpret_cast<volatile unsigned long long*>(cta_counts + bid) = stamped;
         }
         int before = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+        for (int b = lane; b < bid; b += 32) {
             unsigned long long v;
             do {
                 v = *reinterpret_cast<volatile unsigned long long*>(cta_counts + b);
@@ -100,7 +105,7 @@ map_prepare_kernel(const double* __restrict__ xyz, const float* __restrict__ vie
         before = (int)warp_add_u32((uint32_t)before);
         if (lane == 0) {
             s_base = before;
-            if (blockIdx.x == gridDim.x - 1) *n_out = before + total;
+            if (bid == (int)gridDim.x - 1) *n_out = before + total;
         }
     }
     __syncthreads();

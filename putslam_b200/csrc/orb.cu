@@ -235,10 +235,14 @@ orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_ct
     constexpr int kW = kCandThreads / 32;
     __shared__ int warp_tot[kW];
     __shared__ int s_base;
+    __shared__ unsigned int s_bid;
     chain_begin();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = take_cta_ticket(cta_counts - 1, epoch);
+    __syncthreads();
+    const int bid = (int)s_bid;                  // logical CTA index: arrival order (common.cuh take_cta_ticket)
     const int total = L.pix_start[L.n];
-    const int lo = min(total, (int)blockIdx.x * per_cta), hi = min(total, lo + per_cta);   // per_cta is a multiple of 4096
+    const int lo = min(total, bid * per_cta), hi = min(total, lo + per_cta);   // per_cta is a multiple of 4096
     int rec[2][4];
     int mine = 0;
     for (int g = lo + 4 * tid; g < hi; g += 4 * kCandThreads) mine += orb_quad_candidates(L, score, g, hi, rec);
@@ -249,9 +253,9 @@ orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_ct
         int tot = warp_tot[lane];   // kW == 32
         tot = (int)warp_add_u32((uint32_t)tot);
         volatile unsigned long long* sums = cta_counts;
-        if (lane == 0) sums[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned int)tot;
+        if (lane == 0) sums[bid] = ((unsigned long long)epoch << 32) | (unsigned int)tot;
         int before = 0;
-        for (int b = lane; b < (int)blockIdx.x; b += 32) {
+        for (int b = lane; b < bid; b += 32) {
             unsigned long long v;
             do { v = sums[b]; } while ((unsigned int)(v >> 32) != epoch);
             before += (int)(unsigned int)(v & 0xffffffffu);
@@ -259,7 +263,7 @@ orb_candidates_kernel(OrbLevels L, const uint8_t* __restrict__ score, int per_ct
         before = (int)warp_add_u32((uint32_t)before);
         if (lane == 0) {
             s_base = before;
-            if (blockIdx.x == gridDim.x - 1) header[0] = before + tot;
+            if (bid == (int)gridDim.x - 1) header[0] = before + tot;
         }
     }
     __syncthreads();
