@@ -53,8 +53,10 @@ def test_lc_empty_keyframes_and_incremental_append(ctx, O):
     assert (ids == -1).all()
 
 
-def test_lc_full_size_planted_recall(ctx):
-    """C4 size (10k keyframes x 1000): the 20 planted keyframes must be the top-20, random ones score ~0."""
+def test_lc_full_size_planted_recall(ctx, O):
+    """C4 size (10k keyframes x 1000): the 20 planted keyframes must be the top-20, random ones score ~0; the scores of a
+    random sample of 512 keyframes (plus the planted ones) equal the oracle's per-keyframe cross-check count
+    (matcher.cpp:835 + matcherOpenCV.cpp:198-206 per keyframe) exactly."""
     from putslam_b200 import synth
     db = synth.keyframe_db(n_kf=10000, per_kf=1000, n_query=1000, n_planted=20, shared=400, seed=7)
     _fresh(ctx)
@@ -63,6 +65,10 @@ def test_lc_full_size_planted_recall(ctx):
     ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=20, want_scores=True)
     assert sorted(ids.tolist()) == db["planted"].tolist()
     assert sc.min() > 300 and np.delete(scores, db["planted"]).max() < 5
+    sample = np.unique(np.concatenate([np.random.default_rng(3).choice(10000, 512, replace=False), db["planted"]]))
+    sub_off = np.concatenate([[0], np.cumsum(db["kf_off"][sample + 1] - db["kf_off"][sample])]).astype(np.int64)
+    sub_db = np.concatenate([db["db"][db["kf_off"][k]: db["kf_off"][k + 1]] for k in sample])
+    assert np.array_equal(scores[sample], O.lc_scores(db["query"], sub_db, sub_off, tau=64, threads=4))
     # idempotence: the resident replay gives the same answer
     ctx.lc_query_resident(tau=64, k=20); ctx.sync()
     ids2, sc2 = ctx.lc_query(db["query"], tau=64, k=20)
