@@ -225,14 +225,11 @@ __device__ __forceinline__ uint32_t satsub_popc32(uint32_t a, uint32_t b) {
 // out block indices in another order.  The ticket word is {epoch : 32 | arrivals : 32}: the first CTA of a launch (a new
 // epoch) restarts the count, so nothing has to be reset between launches.
 __device__ __forceinline__ unsigned int take_cta_ticket(unsigned long long* word, unsigned int epoch) {
-    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(word), assumed;
-    unsigned int cnt;
-    do {
-        assumed = old;
-        cnt = ((unsigned int)(assumed >> 32) == epoch) ? (unsigned int)(assumed & 0xffffffffu) : 0u;
-        old = atomicCAS(word, assumed, ((unsigned long long)epoch << 32) | (unsigned long long)(cnt + 1u));
-    } while (old != assumed);
-    return cnt;
+    // two contention-free atomics instead of a compare-and-swap loop (which serialises the CTAs of a launch that arrive
+    // together): epochs only grow (ctx.cu next_epoch clears the words when the 32-bit epoch wraps), so a 64-bit max moves
+    // the word to {epoch, 0} exactly once per launch, and the add hands out 0, 1, 2, ...
+    atomicMax(word, (unsigned long long)epoch << 32);
+    return (unsigned int)(atomicAdd(word, 1ull) & 0xffffffffull);
 }
 
 __device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }

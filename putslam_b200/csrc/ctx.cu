@@ -266,7 +266,11 @@ int next_epoch(pslam_ctx* ctx, unsigned int* epoch) {
         CK(cudaMalloc((void**)&ctx->d_prep_counts, bytes));
         CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
     }
-    if (++ctx->prep_epoch == 0) ctx->prep_epoch = 1;   // 0 is the value of a never-written slot
+    if (++ctx->prep_epoch == 0) {   // 0 is the value of a never-written slot; the ticket words need growing epochs
+        ctx->prep_epoch = 1;
+        const size_t bytes = sizeof(unsigned long long) * (3 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 1) + 2);
+        CK(cudaMemsetAsync(ctx->d_prep_counts, 0, bytes, ctx->stream));
+    }
     *epoch = ctx->prep_epoch;
     return PSLAM_OK;
 }
