@@ -1148,6 +1148,7 @@ static int frame_to_map_core(pslam_ctx* ctx, const float* map_xyz, const uint8_t
     // the last kernel of the chain writes the output arena into the page-locked result buffer itself: no copy-engine
     // transfer (and its scheduling latency) between the end of the chain and the host
     s.ws.out_host = ctx->h_out.p; s.ws.out_dev = ctx->d_out.p; s.ws.out_bytes = out.off;
+    s.ws.out_cap = cap; s.ws.out_res_ints = (int)(o_res / sizeof(int));   // o_g is the start of the arena
     s.valid = true;
     TRY(enqueue_f2m(ctx));
     stamp.mark(3);

@@ -139,6 +139,9 @@ struct RansacWorkspace {
     // optional: when the selection kernel has written the result it copies out_bytes of the device output arena (match list
     // + result) into page-locked host memory itself (posted writes over PCIe), so the call needs no device->host copy
     void* out_host = nullptr; const void* out_dev = nullptr; size_t out_bytes = 0;
+    // layout hint: the arena starts with a match list {total, perfect, q[cap], t[cap], d[cap]} and holds the result at
+    // int offset out_res_ints -- only the used prefixes are copied (out_cap == 0: the whole arena)
+    int out_cap = 0, out_res_ints = 0;
 };
 size_t ransac_result_ints(int m_cap);
 cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_mq, const int* d_mt,

@@ -683,13 +683,30 @@ ransac_select_kernel(const float* __restrict__ pts, int m_cap, const int* __rest
                      const float* __restrict__ models, int H, int adaptive, int stop_rule, double usac_conf,
                      int min_matches, double min_ratio, int iters_min, Scorer S, uint32_t seed_lo, uint32_t seed_hi,
                      int* __restrict__ inl_tmp, int stage_cap, int* __restrict__ result, uint4* __restrict__ out_host,
-                     const uint4* __restrict__ out_dev, int out_n16) {
+                     const uint4* __restrict__ out_dev, int out_n16, int out_cap, int out_res_ints) {
     chain_begin();
     ransac_select_body(pts, m_cap, keep, n_filtered, counts, models, H, adaptive, stop_rule, usac_conf, min_matches, min_ratio,
                        iters_min, S, seed_lo, seed_hi, inl_tmp, stage_cap, result);
     if (out_host) {
         __syncthreads();          // the result written above (and the match list of the earlier kernels) is visible
-        for (int i = threadIdx.x; i < out_n16; i += kSelThreads) out_host[i] = __ldcg(out_dev + i);
+        if (out_cap > 0) {        // match list + result: only what is in use crosses the bus
+            const int* gd = reinterpret_cast<const int*>(out_dev);
+            int* gh = reinterpret_cast<int*>(out_host);
+            const int total = __ldcg(gd);
+            const int n = total < out_cap ? total : out_cap;
+            if (threadIdx.x < 2) gh[threadIdx.x] = __ldcg(gd + threadIdx.x);
+            for (int i = threadIdx.x; i < n; i += kSelThreads) {
+                gh[2 + i] = __ldcg(gd + 2 + i);
+                gh[2 + out_cap + i] = __ldcg(gd + 2 + out_cap + i);
+                gh[2 + 2 * out_cap + i] = __ldcg(gd + 2 + 2 * out_cap + i);
+            }
+            const int* rd = gd + out_res_ints;
+            int* rh = gh + out_res_ints;
+            const int n_res = kHdrInts + __ldcg(rd);
+            for (int i = threadIdx.x; i < n_res; i += kSelThreads) rh[i] = __ldcg(rd + i);
+        } else {
+            for (int i = threadIdx.x; i < out_n16; i += kSelThreads) out_host[i] = __ldcg(out_dev + i);
+        }
     }
 }
 
@@ -745,7 +762,7 @@ cudaError_t launch_ransac(const float* d_prev, const float* d_cur, const int* d_
                             P.min_inlier_ratio, P.iters_min_ratio, S, P.seed_lo, P.seed_hi,
                             ws.keep + ws.m_cap /* scratch: second half of keep */, stage_cap, ws.result,
                             reinterpret_cast<uint4*>(ws.out_host), reinterpret_cast<const uint4*>(ws.out_dev),
-                            (int)((ws.out_bytes + 15) / 16))) != cudaSuccess)
+                            (int)((ws.out_bytes + 15) / 16), ws.out_cap, ws.out_res_ints)) != cudaSuccess)
         return e;
     if (launches) *launches += 4;
     return cudaGetLastError();
