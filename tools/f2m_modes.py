@@ -23,7 +23,7 @@ for i in range(50): ctx.frame_to_map_resident()
 e1.record(st); ctx.sync()
 print("packed %%.1f h2d %%.1f kernels-enq %%.1f d2h-enq %%.1f synced %%.1f done %%.1f us | device chain (resident replays) %%.1f us" %% (tuple(acc[1:7]) + (e0.elapsed_time(e1) / 50 * 1e3,)))
 ''' % ROOT
-for name, env in (("graph + programmatic edges", {}), ("graph, plain edges", {"PSLAM_GRAPH_PDL": "0"}), ("plain launches (PDL)", {"PSLAM_GRAPHS": "0"})):
+for name, env in (("graph, plain edges (default)", {}), ("graph + programmatic edges", {"PSLAM_GRAPH_PDL": "1"}), ("plain launches (PDL)", {"PSLAM_GRAPHS": "0"})):
     for rep in range(2):
         out = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, **env), capture_output=True, text=True)
         print(f"{name:28s}", out.stdout.strip() or out.stderr[-300:], flush=True)

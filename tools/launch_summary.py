@@ -1,11 +1,15 @@
-"""per-kernel medians of an `ncu --metrics gpu__time_duration.sum --csv` launch list: python tools/launch_summary.py file.csv"""
-import collections
+"""per-kernel totals of an ncu launch list (--metrics gpu__time_duration.sum --csv): python tools/launch_summary.py launches.csv"""
 import csv
 import sys
+from collections import defaultdict
 rows = [l for l in open(sys.argv[1]) if l.startswith('"')]
-agg = collections.OrderedDict()
-for x in csv.DictReader(rows):
-    k = x["Kernel Name"].split("(")[0] + " " + x["Grid Size"]
-    agg.setdefault(k, []).append(int(x["Metric Value"]))
-for k, v in agg.items():
-    print(f"{k:60s} n={len(v):3d} med={sorted(v)[len(v) // 2] / 1000:.2f} us")
+tot = defaultdict(lambda: [0, 0.0])
+for r in csv.DictReader(rows):
+    if r.get("Metric Name") != "gpu__time_duration.sum":
+        continue
+    v = float(r["Metric Value"].replace(",", "")); u = r.get("Metric Unit", "ns")
+    us = v / 1e3 if u in ("ns", "nsecond") else v if u in ("us", "usecond") else v * 1e3
+    k = r["Kernel Name"].split("(")[0]
+    tot[k][0] += 1; tot[k][1] += us
+for k, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    print(f"{k:60s} n={n:4d} avg={us / n:8.2f} us total={us:9.1f} us")

@@ -13,4 +13,4 @@ run $n "PSLAM_X=1" n${n}_p2p ""
 run $n "PSLAM_LC_P2P=0" n${n}_nccl "--no-cpu-baseline"
 if [ "$n" -ge 4 ]; then run 2 "PSLAM_X=1" n2_p2p "--no-cpu-baseline"; run 4 "PSLAM_X=1" n4_p2p "--no-cpu-baseline"; fi
 timeout 300 python bench.py --no-frontend --no-cpu-baseline > $out/bench_n1.json 2> $out/bench_n1.err
-cat $out/multirank_test.log $out/multirank_test_nccl.log; python tools/summ.py $out/bench_*.json; tail -3 $out/*.err
+cat $out/multirank_test.log $out/multirank_test_nccl.log; python tools/summ.py $out/bench_*.json; for f in $out/*.err; do tail -n 3 $f; done
