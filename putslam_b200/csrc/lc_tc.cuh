@@ -1,0 +1,400 @@
+// lc_tc.cuh -- the loop-closure sweep (K7) on the 5th-generation tensor cores (tcgen05 / TMEM), bit-exact.
+//
+// What it computes is what lc_sweep_range_kernel computes: for every keyframe of the map, the number of query descriptors
+// q whose nearest keyframe descriptor t* (Hamming, lowest index on ties) has q as ITS nearest query (lowest index on
+// ties) at a distance <= tau -- cv::BFMatcher(NORM_HAMMING, crossCheck = true).match per keyframe
+// (reference: src/Matcher/matcherOpenCV.cpp:198-206 called from src/Matcher/matcher.cpp:835).
+//
+// Arithmetic.  Descriptor rows are expanded to signed bytes, bit 0 -> +16, bit 1 -> -16.  Then
+//     sum_k q_k t_k = 256 (256 - 2 Ham) = 512 (128 - Ham)                       (int32 accumulation, exact)
+// and 20 of the 32 slots that pad K from 256 to 288 (kind::i8 takes K in steps of 32) carry
+//     + (255 - t_local) + (255 - q_local)          the index fields: the raw accumulator IS the comparison key
+//     - 130 048 if the target row or the query row is padding (beyond the keyframe / beyond nq): never the maximum
+// so that  max over a row    (fixed q)  = lowest distance, then lowest t
+//          max over a column (fixed t)  = lowest distance, then lowest q
+// with no ALU instruction per pair beyond the 3-input maximum itself.  Both maxima are wanted along the direction a
+// thread owns after tcgen05.ld (one TMEM lane = one accumulator row), so every block of pairs goes through the tensor
+// cores twice: queries as A / targets as B (rows = queries), and targets as A / queries as B (rows = targets) -- the
+// tensor pipe has the room (the integer pipes, which bound the popcount kernel, are nearly idle here).
+//
+// Work split.  A CTA keeps 256 expanded queries resident in shared memory (72 KB), so a keyframe is swept by four CTAs
+// (query quarters, "splits"); each streams the keyframe's rows through a ring of four 128-row tiles (144 KB), expanding
+// them on the fly from the 32-byte rows in HBM (the map's layout does not change).  Per 256-row pair of tiles a CTA
+// issues four accumulation groups of 9 MMAs (M = 128, N = 256, K = 32): rows = query block 0 / 1 against the pair, and
+// rows = tile 0 / 1 of the pair against the 256 queries; two 256-column TMEM buffers alternate between the MMA warp and
+// two sets of four epilogue warps.  Per-query results are complete inside a CTA; per-target results are partial (one per
+// split) and merged by lc_tc_finalize_kernel, which also does the cross-check and the count.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pslam {
+namespace tc {
+
+constexpr int kRowBytes = 288;                    // 256 data slots + 32 extra
+constexpr int kChunks = kRowBytes / 16;           // 16-byte K chunks per row
+constexpr int kLBO = 128;                         // bytes between K-adjacent core matrices (8 rows x 16 B)
+constexpr int kSBO = kChunks * 128;               // bytes between 8-row groups
+constexpr int kTileRows = 128;
+constexpr int kTileBytes = kTileRows * kRowBytes; // 36 864
+constexpr int kPairRows = 256;
+constexpr int kQRows = 256;                       // resident queries per CTA
+constexpr int kSplits = 4;                        // query quarters: up to 1024 queries
+constexpr int kMaxQueries = kQRows * kSplits;
+constexpr int kVal = 16;                          // |q_k| = |t_k|
+constexpr int kStepShift = 9;                     // accumulator = (128 - Ham) << 9 | index fields (< 512)
+constexpr int kThreads = 13 * 32;                 // warps 0-3 producers, 4-7 / 8-11 epilogue sets, 12 MMA
+constexpr int kSmemBytes = 2 * kTileBytes + 4 * kTileBytes + 256;
+constexpr long long kSpinLimit = 2000000000ll;    // ~1 s of clocks: a wrong barrier shows up as an error, not as a hang
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: canonical layout ((8,n),2):((16 B, SBO), LBO)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((kLBO >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((kSBO >> 4) & 0x3fff) << 32;
+    d |= 1ull << 46;                               // descriptor version (Blackwell)
+    return d;                                      // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// false on time-out or when another role has given up (abort flag in shared memory)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+    if (mbar_try(bar, parity)) return true;
+    const long long t0 = clock64();
+    int spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 1023) == 0) {
+            if (*abort_flag) return false;
+            if (clock64() - t0 > kSpinLimit) { *abort_flag = 1; return false; }
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ int max3(int a, int b, int c) {
+    int r;
+    asm("max.s32 %0, %1, %2;\n\tmax.s32 %0, %0, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));   // ptxas fuses to VIMNMX3
+    return r;
+}
+
+// 4 descriptor bits -> 4 signed bytes: bit 0 -> +kVal, bit 1 -> -kVal
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) {
+    const uint32_t bits = (nib * 0x00204081u) & 0x01010101u;            // bit j of the nibble -> byte j
+    return (0x01010101u * (uint32_t)kVal) ^ (bits * (uint32_t)((kVal ^ (256 - kVal)) & 0xff));
+}
+// the two extra chunks of a row.  Slots (bytes of chunk 16, then chunk 17):
+//   0,1   target index:  target rows (idx & 1, idx >> 1)            query rows (1, 2)
+//   2,3   query index:   query rows  (idx & 1, idx >> 1)            target rows (1, 2)
+//   4-11  padding target: target rows 0 / -128 when padding         query rows +127
+//   12-19 padding query:  query rows  0 / -128 when padding         target rows +127
+__device__ __forceinline__ void extra_chunks(bool is_query, int idx, bool valid, uint4& c16, uint4& c17) {
+    const uint32_t own = (uint32_t)(idx & 1) | ((uint32_t)(idx >> 1) << 8), wts = 1u | (2u << 8);
+    const uint32_t pad = valid ? 0u : 0x80808080u, full = 0x7f7f7f7fu;
+    if (is_query) { c16 = make_uint4(wts | (own << 16), full, full, pad); c17 = make_uint4(pad, 0u, 0u, 0u); }
+    else          { c16 = make_uint4(own | (wts << 16), pad, pad, full);  c17 = make_uint4(full, 0u, 0u, 0u); }
+}
+// one 32-byte descriptor row (8 words, already decoded to the plain bit order) -> the 288-byte operand row r of a tile
+__device__ __forceinline__ void expand_row(const uint32_t (&w)[8], bool valid, uint8_t* tile, int r, int idx, bool is_query) {
+    uint8_t* base = tile + (r >> 3) * kSBO + (r & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t x = w[i];
+        uint4 lo, hi;
+        if (valid) {
+            lo.x = spread4(x & 15u);         lo.y = spread4((x >> 4) & 15u);
+            lo.z = spread4((x >> 8) & 15u);  lo.w = spread4((x >> 12) & 15u);
+            hi.x = spread4((x >> 16) & 15u); hi.y = spread4((x >> 20) & 15u);
+            hi.z = spread4((x >> 24) & 15u); hi.w = spread4(x >> 28);
+        } else {
+            lo = make_uint4(0, 0, 0, 0); hi = lo;
+        }
+        *reinterpret_cast<uint4*>(base + (2 * i) * kLBO) = lo;
+        *reinterpret_cast<uint4*>(base + (2 * i + 1) * kLBO) = hi;
+    }
+    uint4 c16, c17;
+    extra_chunks(is_query, idx, valid, c16, c17);
+    *reinterpret_cast<uint4*>(base + 16 * kLBO) = c16;
+    *reinterpret_cast<uint4*>(base + 17 * kLBO) = c17;
+}
+// rows of the map are stored re-encoded for the popcount kernel (ham256_encode, common.cuh); undo it
+__device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
+    const uint32_t e2 = w[2], e5 = w[5];
+    w[2] = e2 ^ w[0] ^ w[1];
+    w[5] = e5 ^ w[3] ^ w[4];
+    w[6] = w[6] ^ e2 ^ e5;
+}
+
+// maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address)
+__device__ __forceinline__ int row_max_256(uint32_t taddr) {
+    int m = -0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 256; c += 64) {
+        int a[32], b[32];
+        tmem_ld32(taddr + (uint32_t)c, a);
+        tmem_ld32(taddr + (uint32_t)(c + 32), b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) m = max3(m, a[j], a[j + 1]);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) m = max3(m, b[j], b[j + 1]);
+    }
+    return m;
+}
+
+struct SweepArgs {
+    const uint32_t* db;          // n_desc x 8 words
+    const long long* kf_off;     // n_kf + 1
+    int n_kf;
+    int db_encoded;              // rows stored with ham256_encode
+    const uint32_t* query;       // nq x 8 words, plain
+    int nq;
+    long long n_desc;            // stride of col_best between splits
+    uint32_t* row_best;          // [n_kf][kMaxQueries]: Ham << 16 | t (index inside the keyframe)
+    uint32_t* col_best;          // [kSplits][n_desc]:   Ham << 16 | q
+    int* status;                 // set non-zero when a wait timed out
+};
+
+__global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sq = smem;                                 // 2 tiles: the CTA's 256 queries
+    uint8_t* st = smem + 2 * kTileBytes;                // ring of 4 tiles = 2 pairs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);   // full[2], empty[2], tfull[2], tempty[2]
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x & (kSplits - 1), group = blockIdx.x >> 2, n_groups = gridDim.x >> 2;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
+
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + 8 * i, 4);       // one arrival per producer warp
+            mbar_init(bar_empty + 8 * i, 1);      // tcgen05.commit
+            mbar_init(bar_tfull + 8 * i, 1);      // tcgen05.commit
+            mbar_init(bar_tempty + 8 * i, 4);     // one arrival per epilogue warp of the set
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) tmem_alloc(smem_u32(&s_tmem), 512);
+    // the CTA's queries, expanded once
+    if (tid < kQRows) {
+        const int q = split * kQRows + tid;
+        uint32_t w[8];
+        const bool valid = q < A.nq;
+        if (valid) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 0;
+        }
+        expand_row(w, valid, sq + (tid >> 7) * kTileBytes, tid & 127, 255 - tid, true);
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = s_tmem;
+    volatile int* abort_flag = &s_abort;
+
+    if (warp < 4) {
+        // ===== producers: two rows per thread and pair (row tid of each tile) =====
+        uint32_t it = 0;
+        for (int kf = group; kf < A.n_kf; kf += n_groups) {
+            const long long r0 = A.kf_off[kf], r1 = A.kf_off[kf + 1];
+            const int pairs = (int)((r1 - r0 + kPairRows - 1) / kPairRows);
+            for (int p = 0; p < pairs; ++p, ++it) {
+                const int s = it & 1;
+                uint32_t w[2][8];
+                bool valid[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const long long row = r0 + (long long)p * kPairRows + h * kTileRows + tid;
+                    valid[h] = row < r1;
+                    if (valid[h]) {
+                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8));
+                        const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8) + 1);
+                        w[h][0] = a.x; w[h][1] = a.y; w[h][2] = a.z; w[h][3] = a.w; w[h][4] = b.x; w[h][5] = b.y; w[h][6] = b.z; w[h][7] = b.w;
+                        if (A.db_encoded) decode_row(w[h]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[h][i] = 0;
+                    }
+                }
+                if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    expand_row(w[h], valid[h], st + (2 * s + h) * kTileBytes, tid, 255 - (h * kTileRows + tid), false);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + 8 * s);
+            }
+        }
+    } else if (warp == 12) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint64_t dq = make_desc(smem_u32(sq));
+            const uint32_t idesc = make_idesc(128, 256);
+            uint32_t it = 0, g = 0;
+            for (int kf = group; kf < A.n_kf; kf += n_groups) {
+                const long long r0 = A.kf_off[kf], r1 = A.kf_off[kf + 1];
+                const int pairs = (int)((r1 - r0 + kPairRows - 1) / kPairRows);
+                for (int p = 0; p < pairs; ++p, ++it) {
+                    const int s = it & 1;
+                    if (!mbar_wait(bar_full + 8 * s, (it >> 1) & 1, abort_flag)) goto done;
+                    fence_after();
+                    const uint64_t dt = make_desc(smem_u32(st + 2 * s * kTileBytes));
+#pragma unroll 1
+                    for (int grp = 0; grp < 4; ++grp, ++g) {
+                        const int buf = grp & 1;      // = g & 1: four groups per pair
+                        // rows = query block `buf` vs the pair (grp 0, 1); rows = tile `buf` of the pair vs the queries (grp 2, 3)
+                        const uint64_t ad = (grp < 2 ? dq : dt) + (uint64_t)((buf * kTileBytes) >> 4);
+                        const uint64_t bd = grp < 2 ? dt : dq;
+                        if (!mbar_wait(bar_tempty + 8 * buf, ((g >> 1) & 1) ^ 1, abort_flag)) goto done;
+                        fence_after();
+#pragma unroll
+                        for (int k = 0; k < kRowBytes / 32; ++k)
+                            mma_i8(tm + (uint32_t)(buf * 256), ad + (uint64_t)((k * 2 * kLBO) >> 4), bd + (uint64_t)((k * 2 * kLBO) >> 4), idesc, k > 0);
+                        mma_commit(bar_tfull + 8 * buf);
+                    }
+                    mma_commit(bar_empty + 8 * s);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: set b = (warp - 4) >> 2 owns TMEM buffer b; lane quarter = warp & 3 =====
+        const int b = (warp - 4) >> 2, lq = warp & 3;
+        const uint32_t taddr = tm + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * 256);
+        const int row_in_blk = lq * 32 + lane;                 // accumulator row of this thread
+        const int q_local = b * kTileRows + row_in_blk;        // its query in the O1 groups
+        const int iq = 255 - q_local;
+        uint32_t n = 0;                                        // groups seen on this buffer
+        for (int kf = group; kf < A.n_kf; kf += n_groups) {
+            const long long r0 = A.kf_off[kf], r1 = A.kf_off[kf + 1];
+            const int n_t = (int)(r1 - r0);
+            const int pairs = (n_t + kPairRows - 1) / kPairRows;
+            int best_h = -0x7fffffff, best_m = 0, best_p = 0;
+            for (int p = 0; p < pairs; ++p) {
+                // --- rows = queries: best target of the pair for this thread's query ---
+                if (!mbar_wait(bar_tfull + 8 * b, n & 1, abort_flag)) goto done;
+                fence_after();
+                int m = row_max_256(taddr);
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                ++n;
+                const int h = m >> kStepShift;                 // 128 - Ham (the index fields sum to < 512)
+                if (h > best_h) { best_h = h; best_m = m; best_p = p; }     // later pairs hold higher t: strictly better only
+                // --- rows = targets: best query (of this split) for this thread's target ---
+                if (!mbar_wait(bar_tfull + 8 * b, n & 1, abort_flag)) goto done;
+                fence_after();
+                m = row_max_256(taddr);
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                ++n;
+                const int t_local = b * kTileRows + row_in_blk;            // row inside the pair
+                const int t_kf = p * kPairRows + t_local;
+                if (t_kf < n_t) {
+                    const int ham = 128 - (m >> kStepShift);
+                    const int itv = 255 - t_local;
+                    const int ql = 255 - ((m & 511) - itv);
+                    A.col_best[(size_t)split * (size_t)A.n_desc + (size_t)(r0 + t_kf)] = ((uint32_t)ham << 16) | (uint32_t)(split * kQRows + ql);
+                }
+            }
+            if (pairs > 0) {
+                const int ham = 128 - best_h;
+                const int tl = 255 - ((best_m & 511) - iq);
+                A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = ((uint32_t)ham << 16) | (uint32_t)(best_p * kPairRows + tl);
+            } else {
+                A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = 0xffffffffu;
+            }
+        }
+    }
+done:
+    __syncwarp();
+    fence_before();
+    __syncthreads();
+    if (warp == 12) tmem_free(tm, 512);
+    if (tid == 0 && s_abort) *A.status = 1;
+}
+
+// cross-check + count per keyframe: merges the per-split column results, then score[kf] = #{q : colbest[t*(q)].q == q, Ham <= tau}
+__global__ void __launch_bounds__(256) lc_tc_finalize_kernel(const long long* __restrict__ kf_off, int nq, long long n_desc,
+                                                             const uint32_t* __restrict__ row_best, const uint32_t* __restrict__ col_best,
+                                                             int tau, int* __restrict__ scores) {
+    __shared__ uint32_t s_col[4096];
+    __shared__ int s_cnt;
+    const int kf = blockIdx.x;
+    const long long r0 = kf_off[kf];
+    const int n_t = (int)(kf_off[kf + 1] - r0);
+    const int splits = (nq + kQRows - 1) / kQRows;
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int t = threadIdx.x; t < n_t; t += blockDim.x) {
+        uint32_t m = 0xffffffffu;
+        for (int s = 0; s < splits; ++s) m = min(m, __ldcs(col_best + (size_t)s * (size_t)n_desc + (size_t)(r0 + t)));
+        s_col[t] = m;
+    }
+    __syncthreads();
+    int cnt = 0;
+    if (n_t > 0)
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const uint32_t rb = __ldcs(row_best + (size_t)kf * kMaxQueries + q);
+            const int ham = (int)(rb >> 16), t = (int)(rb & 0xffffu);
+            if (ham <= tau && (int)(s_col[t] & 0xffffu) == q) ++cnt;
+        }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) scores[kf] = s_cnt;
+}
+
+}  // namespace tc
+}  // namespace pslam
