@@ -97,20 +97,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_capture(n_kf, world):
+def ncu_capture(n_kf, world, name="ncu_sweep_r2.json"):
     """Per-launch DRAM traffic and pipe utilisation of the sweep kernel from the committed `ncu --set full` capture
-    (profiles/ncu_sweep_r2.json, taken on C4 at 1 GPU): only valid for that configuration, and says so."""
-    p = os.path.join(ROOT, "profiles", "ncu_sweep_r2.json")
+    (profiles/<name>, taken on C4 at 1 GPU): only valid for that configuration, and says so."""
+    p = os.path.join(ROOT, "profiles", name)
     out = {"traffic": None, "traffic_source": "no committed capture for this configuration (the capture is C4 at 1 GPU)"}
     if n_kf != N_KF or world != 1 or not os.path.exists(p):
         return out
     try:
         d = json.load(open(p))
         out = {"traffic": float(d["dram_traffic_bytes_per_launch"]),
-               "traffic_source": "profiles/ncu_sweep_r2.json (ncu --set full of this kernel on C4, 1 GPU; a constant read from the "
+               "traffic_source": f"profiles/{name} (ncu --set full of this kernel on C4, 1 GPU; a constant read from the "
                                  "committed capture, not re-measured by this run)",
                "alu_pipe_pct": d.get("alu_pipe_pct"), "xu_pipe_pct": d.get("xu_pipe_pct"), "fma_pipe_pct": d.get("fma_pipe_pct"),
                "issue_active_pct": d.get("issue_active_pct")}
+        if d.get("tensor_pipe_pct") is not None:
+            out["tensor_pipe_pct"] = d.get("tensor_pipe_pct")
     except Exception:  # noqa: BLE001
         pass
     return out
@@ -134,6 +136,18 @@ def measured_peaks():
             pass
     out["hbm_gbs_peak"] = hbm
     out["hbm_peak_source"] = how
+    out["bf16_tflops_peak"], out["bf16_peak_source"] = 2250.0, "fallback (nominal dense bf16)"
+    if os.path.exists(p):
+        try:
+            out["bf16_tflops_peak"] = float(json.load(open(p))["bf16_tflops"]); out["bf16_peak_source"] = "measured (MEASURED_PEAKS.json, burst)"
+        except Exception:  # noqa: BLE001
+            pass
+    pr = os.path.join(ROOT, "profiles", "tc_probe_r2.json")
+    if os.path.exists(pr):
+        try:
+            out["int8_mma_tops_probe"] = float(json.load(open(pr))["mma_n256"]["chip_tops_event_time"])
+        except Exception:  # noqa: BLE001
+            pass
     return out
 
 
@@ -267,7 +281,9 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gcmp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 (popcount of XOR, 256-bit descriptors)",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": ("s8 (256-bit descriptors expanded to +-16 bytes, int32 accumulation on the tensor cores; exact)" if used_tensor
+                      else "u8 (popcount of XOR, 256-bit descriptors)"),
         "data": "synthetic",
         "config": {"workload": f"C4 loop-closure sweep: {NQ} query descriptors vs {n_kf} keyframes x {PER_KF} ORB "
                                f"descriptors ({float(db['kf_off'][-1]) * 32 / 1e6:.0f} MB map), tau {TAU}, top-{TOPK}",
@@ -625,6 +641,7 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1)
 
     xmode = ctx.lc_exchange_mode()
+    used_tensor, tc_timeout = ctx.lc_tensor_status()
     # ---- e2e: the public C-ABI call with HOST buffers (pinned staging, H2D query, D2H top-k inside) ----
     for i in range(args.warmup):
         ctx.lc_query_sharded(queries[i % 4] if (rank == 0 or world == 1) else None, root=root, tau=TAU, k=TOPK, nq=NQ)
@@ -659,11 +676,11 @@ def run_ours(args):
         lop3_rate = peaks.get("lop3_per_clk_per_sm")
         xu_side = (popc_peak / POPC_PER_PAIR) if popc_peak else 148 * 16 * 1.965 / POPC_PER_PAIR
         alu_side = (lop3_rate * 148 * sm_ghz / ALU_PER_PAIR) if lop3_rate else 148 * 64 * 1.965 / ALU_PER_PAIR
-        roofline = {
+        popcount_roofline = {
             "bound": "int-pipe",
             "bound_note": "integer pipes (POPC on the XU pipe, LOP3 / min on the ALU pipe), not hbm and not tensor: every 32-byte "
                           "descriptor read from HBM feeds 1000 comparisons, so the HBM side of the roofline is ~350x higher",
-            "kernel": "lc_sweep_kernel<4> (re-encoded rows: 13 LOP3 + 4 POPC per pair)",
+            "kernel": "lc_sweep_range_kernel<4> (re-encoded rows: 13 LOP3 + 4 POPC per pair)",
             "achieved": ach_gcmps, "peak": min(alg_peak, hbm_side), "unit": "Gcmp/s",
             "frac": ach_gcmps / min(alg_peak, hbm_side),
             "peak_def": "min(measured POPC rate / 8 popc32 per 256-bit pair, measured HBM GB/s * Q/32): the algorithmic 8-POPC "
@@ -675,20 +692,55 @@ def run_ours(args):
             "frac_of_issued_mix": ach_gcmps / min(xu_side, alu_side),
             "ceiling_regonly_gcmps": peaks.get("ham_enc13_gcmps"),
             "frac_of_regonly_ceiling": (ach_gcmps / peaks["ham_enc13_gcmps"]) if peaks.get("ham_enc13_gcmps") else None,
+        }
+        common = {
             "avg_launch_ms": sweep_avg_ms,
             "non_sweep_us_per_step": (dev_ms / args.steps - sweep_avg_ms) * 1e3,
             "hbm": {"achieved_gbs": (32.0 * shard_desc + 40.0 * NQ) / (sweep_avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": peaks.get("hbm_peak_source")},
-            **ncu_capture(n_kf, world),
             "measured_pipe_rates": {k: peaks.get(k) for k in ("popc_per_clk_per_sm", "lop3_per_clk_per_sm",
                                                                "imad_per_clk_per_sm", "min_u32_per_clk_per_sm",
                                                                "ham_plain8_gcmps", "ham_csa4_gcmps", "ham_enc13_gcmps",
                                                                "ham_enc13_clk_per_pair_per_sm", "hbm_copy_gbs")},
         }
+        if used_tensor:
+            # one 256-bit comparison = one 256-long dot product of +-1 vectors = 256 multiply-adds = 512 int8 operations
+            OPS_PER_PAIR = 512.0
+            int8_peak = 2.0 * peaks["bf16_tflops_peak"]                 # TOP/s: dense int8 issues at twice the bf16 rate on B200
+            ach_tops = ach_gcmps * OPS_PER_PAIR / 1e3
+            # issued: both orientations (rows = queries and rows = targets), K padded 256 -> 288, queries 1000 -> 1024,
+            # keyframes of 1000 rows -> 4 pairs of 256
+            issued = 2.0 * (288.0 / 256.0) * (1024.0 / NQ) * (1024.0 / PER_KF if PER_KF <= 1024 else 1.0)
+            roofline = {
+                "bound": "tensor",
+                "bound_note": "the sweep is a 1000 x 1e7 x 256-bit binary contraction; on +-16-expanded rows it is exact in tcgen05.mma "
+                              "kind::i8 with int32 accumulation, and four extra K slots put the index fields into the accumulator so "
+                              "that the cross-check reductions are plain maxima.  HBM side: 32 B per map descriptor per sweep",
+                "kernel": "lc_tc_sweep_kernel (tcgen05.mma cta_group::1 kind::i8 M128 N256 K32, TMEM accumulators, tcgen05.ld epilogue)",
+                "achieved": ach_tops, "peak": int8_peak, "unit": "TOP/s", "frac": ach_tops / int8_peak,
+                "peak_def": f"2 x the measured dense bf16 rate ({peaks['bf16_tflops_peak']:.0f} TF/s, {peaks['bf16_peak_source']}): "
+                            "int8 MMAs issue at twice the bf16 rate; achieved counts the ALGORITHMIC work, 512 int8 ops per 256-bit pair",
+                "issued_ops_per_algorithmic_op": issued,
+                "frac_issued": ach_tops * issued / int8_peak,
+                "issued_def": "what the kernel really puts through the tensor cores: both orientations (per-query and per-target "
+                              "maxima each along TMEM lanes), K 256 -> 288, queries 1000 -> 1024, keyframe rows 1000 -> 1024",
+                "int8_mma_tops_probe": peaks.get("int8_mma_tops_probe"),
+                "frac_issued_of_probe_rate": (ach_tops * issued / peaks["int8_mma_tops_probe"]) if peaks.get("int8_mma_tops_probe") else None,
+                "gcmps": ach_gcmps,
+                "popcount_form": {"note": "the popcount kernel this replaced (pslam_lc_set_work_unit(3) / PSLAM_LC_TENSOR=0) and its "
+                                          "integer-pipe roofline, for reference", "peak_gcmps": min(alg_peak, hbm_side),
+                                  "issued_mix_peak_gcmps": min(xu_side, alu_side), "measured_gcmps_r2": 931.0},
+                **common,
+                **ncu_capture(n_kf, world, "ncu_sweep_tc_r2.json"),
+            }
+        else:
+            roofline = {**popcount_roofline, **common, **ncu_capture(n_kf, world)}
         line = {
             "metric": METRIC, "value": value, "unit": "Gcmp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u8 (popcount of XOR, 256-bit descriptors)",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": ("s8 (256-bit descriptors expanded to +-16 bytes, int32 accumulation on the tensor cores; exact)" if used_tensor
+                      else "u8 (popcount of XOR, 256-bit descriptors)"),
             "data": "synthetic",
             "config": {"workload": f"C4 loop-closure sweep: {NQ} query descriptors vs {n_kf} keyframes x {PER_KF} ORB "
                                    f"descriptors ({total_desc * 32 / 1e6:.0f} MB map resident in HBM), tau {TAU}, top-{TOPK}",
@@ -698,7 +750,8 @@ def run_ours(args):
                                        ("peer memory over NVLink inside the sweep kernel (CUDA-IPC buffers, stores + flags)"
                                         if xmode == 2 else "NCCL (ncclBroadcast + ncclAllGather + merge kernel)"))
                                       if world > 1 else "1 GPU, no collective",
-                       "exchange_mode": xmode,
+                       "exchange_mode": xmode, "sweep_form": "tensor-core (tcgen05 kind::i8)" if used_tensor else "popcount",
+                       "tensor_wait_timeouts": tc_timeout,
                        "l2": "L2 flushed (256 MiB write) between timed steps; step time = CUDA events on the ctx stream",
                        "result_ok": ok, "result_check": check},
             "e2e": {"value": e2e_val, "unit": "Gcmp/s", "ms_per_step": e2e_ms / args.steps,

@@ -168,6 +168,12 @@ __global__ void __launch_bounds__(256) ldtm_rate_kernel(int iters, int fold, lon
 // ---------------------------------------------------------------------------------------------------------------------
 // section "sweep": the whole tensor-core sweep (lc_tc.cuh) on a synthetic map against a plain popcount kernel
 // ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const long long* __restrict__ kf_off, int nq, long long n_desc, const uint32_t* __restrict__ row_best,
+                                                       const uint32_t* __restrict__ col_best, int tau, int* __restrict__ scores) {
+    __shared__ uint32_t s_col[4096];
+    __shared__ int s_cnt;
+    finalize_keyframe((int)blockIdx.x, kf_off, nq, n_desc, row_best, col_best, tau, scores, s_col, &s_cnt);
+}
 __global__ void __launch_bounds__(1024) ref_scores_kernel(const uint32_t* __restrict__ db, const long long* __restrict__ kf_off,
                                                           const uint32_t* __restrict__ query, int nq, int tau, int* __restrict__ scores) {
     __shared__ uint32_t s_row[1024], s_col[4096];
@@ -340,15 +346,16 @@ int main(int argc, char** argv) {
         tc::SweepArgs A;
         A.db = ddb; A.kf_off = doff; A.n_kf = n_kf; A.db_encoded = 0; A.query = dq; A.nq = nq; A.n_desc = n_desc;
         A.row_best = drow; A.col_best = dcol; A.status = d_status;
+        A.n_splits = (nq + tc::kQRows - 1) / tc::kQRows; A.qflag = nullptr; A.qepoch = 0;
         CK(cudaFuncSetAttribute(tc::lc_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        const int grid = (sms / tc::kSplits) * tc::kSplits;
+        const int grid = (sms / A.n_splits) * A.n_splits;
         cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
         float ms_sweep = 0, ms_fin = 0;
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(e0);
             tc::lc_tc_sweep_kernel<<<grid, tc::kThreads, tc::kSmemBytes>>>(A);
             cudaEventRecord(e1);
-            tc::lc_tc_finalize_kernel<<<n_kf, 256>>>(doff, nq, n_desc, drow, dcol, tau, dsc);
+            tc::finalize_kernel<<<n_kf, 256>>>(doff, nq, n_desc, drow, dcol, tau, dsc);
             cudaEventRecord(e2);
             CK(cudaDeviceSynchronize());
             cudaEventElapsedTime(&ms_sweep, e0, e1); cudaEventElapsedTime(&ms_fin, e1, e2);

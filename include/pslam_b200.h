@@ -436,9 +436,14 @@ PSLAM_API int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* 
 /* global id of local keyframe 0 (rank r of a sharded map owns ids [base, base + n_keyframes)) */
 PSLAM_API int pslam_lc_set_id_base(pslam_ctx* ctx, int kf_id_base);
 
-/* Work unit of the V1 sweep: 0 = automatic (whole keyframes when the GPU holds >= 4096 of them, 128-row tiles with a
- * finalize pass below that), 1 = keyframes, 2 = tiles.  Results are identical; this is a performance knob. */
+/* Form of the V1 sweep: 0 = automatic -- the tensor-core form (tcgen05 kind::i8 on +-1-expanded rows, exact) for up to
+ * 1024 query descriptors, the popcount range form beyond; 3 = popcount range form always; 1 = whole keyframes per CTA,
+ * 2 = 128-row tiles + finalize pass (the round-1 forms).  Results are identical; this is a performance knob.
+ * PSLAM_LC_TENSOR=0 in the environment makes 0 behave like 3. */
 PSLAM_API int pslam_lc_set_work_unit(pslam_ctx* ctx, int mode);
+/* After a sweep: *used_tensor_cores = 1 when the last V1 sweep ran in the tensor-core form; *timed_out != 0 when one of its
+ * internal waits ever gave up (a bug, never expected: results of that sweep are then undefined).  Synchronises the stream. */
+PSLAM_API int pslam_lc_tensor_status(pslam_ctx* ctx, int* used_tensor_cores, int* timed_out);
 
 /* Single-GPU query.  out_* sized k (<= PSLAM_LC_MAX_TOPK); unused slots -1.  scores_out (nullable):
  * n_keyframes per-keyframe scores. */

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "pslam_ransac_sample", "pslam_point_inlier_ratio", "pslam_kabsch_batch", "pslam_frame_to_frame",
     "pslam_frame_to_map", "pslam_frame_to_map_features", "pslam_map_prepare", "pslam_map_reserve", "pslam_map_write", "pslam_map_truncate", "pslam_map_size", "pslam_frame_to_resident_map", "pslam_loop_closure_pair", "pslam_frame_to_map_resident", "pslam_frame_to_frame_resident", "pslam_lc_db_reserve",
     "pslam_lc_db_append", "pslam_lc_db_clear", "pslam_lc_db_size", "pslam_lc_set_id_base", "pslam_lc_set_work_unit", "pslam_lc_query",
-    "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_lc_exchange_mode", "pslam_debug_host_stamps", "pslam_host_register", "pslam_host_unregister", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
+    "pslam_lc_query_resident", "pslam_lc_last_sweep_ms", "pslam_lc_exchange_mode", "pslam_lc_tensor_status", "pslam_debug_host_stamps", "pslam_host_register", "pslam_host_unregister", "pslam_comm_unique_id", "pslam_comm_init", "pslam_comm_destroy",
     "pslam_lc_query_sharded", "pslam_lc_query_sharded_resident", "pslam_lc_query_sharded_resident_bcast", "pslam_lc_knn2", "pslam_lc_set_desc_base",
     "pslam_lc_knn2_sharded", "pslam_lc_knn2_resident",
 ]
@@ -583,6 +583,12 @@ class Context:
 
     def lc_set_work_unit(self, mode):
         self._ck(self.lib.pslam_lc_set_work_unit(self.h, int(mode)))
+
+    def lc_tensor_status(self):
+        """(used_tensor_cores, timed_out) of the last V1 sweep"""
+        used, to = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.pslam_lc_tensor_status(self.h, C.byref(used), C.byref(to)))
+        return bool(used.value), int(to.value)
 
     def lc_set_id_base(self, base):
         self._ck(self.lib.pslam_lc_set_id_base(self.h, int(base)))

@@ -144,7 +144,11 @@ struct pslam_ctx {
     int n_tiles = 0;
     bool tiles_dirty = true;
     int max_kf_desc = 0;        // largest keyframe appended so far
-    int lc_work_unit = 0;       // 0 range form (contiguous tile ranges, fused tail), 1 keyframes, 2 tiles (round-1 forms)
+    int lc_work_unit = 0;       // 0 fused-tail forms (tensor-core sweep when it applies, else the range form), 1 keyframes, 2 tiles (round-1 forms), 3 range form only
+    DevBuf d_tc_row, d_tc_col;  // tensor-core form: per-query results per keyframe | per-split per-target results
+    int* d_tc_status = nullptr; // non-zero after a barrier time-out inside the tensor-core sweep
+    bool lc_tensor = true;      // PSLAM_LC_TENSOR=0 keeps the popcount kernels
+    bool lc_last_tensor = false;
     DevBuf d_range;             // range form: row pieces | column pieces of the keyframes cut by CTA ranges
     int* d_kf_done = nullptr;   // per-keyframe tile counters of those keyframes (zero between launches)
     unsigned int* d_cta_done = nullptr;
@@ -519,7 +523,7 @@ void pslam_ctx_destroy(pslam_ctx* ctx) {
     for (const auto& r : ctx->pinned) cudaHostUnregister(const_cast<uint8_t*>(r.p));
     cudaGetLastError();
     cudaFree(ctx->d_in.p); cudaFree(ctx->d_out.p); cudaFree(ctx->d_work.p); cudaFree(ctx->d_knn.p);
-    cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p); cudaFree(ctx->d_range.p); cudaFree(ctx->d_kf_done); cudaFree(ctx->d_cta_done);
+    cudaFree(ctx->d_tile_start.p); cudaFree(ctx->d_split.p); cudaFree(ctx->d_range.p); cudaFree(ctx->d_tc_row.p); cudaFree(ctx->d_tc_col.p); cudaFree(ctx->d_tc_status); cudaFree(ctx->d_kf_done); cudaFree(ctx->d_cta_done);
     cudaFreeHost(ctx->h_in.p); cudaFreeHost(ctx->h_out.p);
     cudaFree(ctx->d_db); cudaFree(ctx->d_kf_off); cudaFree(ctx->d_scores); cudaFree(ctx->d_lc_query);
     cudaFree(ctx->d_lc_pairs);
@@ -2183,9 +2187,23 @@ int pslam_lc_db_size(const pslam_ctx* ctx, int* n_keyframes, int64_t* n_descript
 
 int pslam_lc_set_work_unit(pslam_ctx* ctx, int mode) {
     if (!ctx) return PSLAM_ERR_ARG;
-    if (mode < 0 || mode > 2) return fail(ctx, PSLAM_ERR_ARG, "work unit mode must be 0, 1 or 2");
+    if (mode < 0 || mode > 3) return fail(ctx, PSLAM_ERR_ARG, "work unit mode must be 0 .. 3");
     ctx->lc_work_unit = mode;
     ctx->tiles_dirty = true;
+    return PSLAM_OK;
+}
+
+int pslam_lc_tensor_status(pslam_ctx* ctx, int* used_tensor_cores, int* timed_out) {
+    if (!ctx) return PSLAM_ERR_ARG;
+    if (used_tensor_cores) *used_tensor_cores = ctx->lc_last_tensor ? 1 : 0;
+    if (timed_out) {
+        *timed_out = 0;
+        if (ctx->d_tc_status) {
+            CK(cudaSetDevice(ctx->device));
+            CK(cudaMemcpyAsync(timed_out, ctx->d_tc_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     return PSLAM_OK;
 }
 
@@ -2202,6 +2220,13 @@ static int lc_prepare(pslam_ctx* ctx, const uint8_t* query, int nq, int k) {
     if (!ctx->lc_configured) {
         CK(lc_sweep_configure());
         CK(lc_sweep_range_configure());
+        CK(lc_sweep_tc_configure());
+        {
+            const char* env = getenv("PSLAM_LC_TENSOR");
+            ctx->lc_tensor = !(env && env[0] == '0');
+        }
+        CK(cudaMalloc((void**)&ctx->d_tc_status, sizeof(int)));
+        CK(cudaMemsetAsync(ctx->d_tc_status, 0, sizeof(int), ctx->stream));
         CK(cudaMalloc((void**)&ctx->d_cta_done, sizeof(unsigned int)));
         CK(cudaMemsetAsync(ctx->d_cta_done, 0, sizeof(unsigned int), ctx->stream));
         CK(cudaMalloc((void**)&ctx->d_lc_query, (size_t)PSLAM_LC_MAX_QUERY * 32));
@@ -2241,25 +2266,33 @@ static int lc_refresh_tiles(pslam_ctx* ctx) {
     return PSLAM_OK;
 }
 
+static bool lc_fused_tail(const pslam_ctx* ctx) { return ctx->lc_work_unit == 0 || ctx->lc_work_unit == 3; }
 static int* lc_merged_pairs(pslam_ctx* ctx) { return ctx->d_lc_pairs + 2 * PSLAM_LC_MAX_TOPK + 2 * PSLAM_LC_MAX_TOPK * 64; }
 
 // One sweep of the resident query over this ctx's keyframes + local top-k.  exchange: the peer exchange and merge of the
 // per-rank top-k run in the kernel's tail (range form with peer access only); pushed_query: the query sits in the exchange
 // buffer (pushed by the root rank) and the kernel waits for its flag.
 static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k, bool exchange = false, bool pushed_query = false) {
-    const bool query_in_xchg = pushed_query || (ctx->lc_query_in_xchg && ctx->lc_work_unit == 0 && ctx->d_xchg);
+    const bool query_in_xchg = pushed_query || (ctx->lc_query_in_xchg && lc_fused_tail(ctx) && ctx->d_xchg);
     int l = 0;
     if (ctx->lc_nq > 1024 && ctx->max_kf_desc > lc_max_kf_desc_wide())
         return fail(ctx, PSLAM_ERR_UNSUPPORTED, "more than 1024 query descriptors need keyframes of at most %d descriptors (largest: %d)",
                     lc_max_kf_desc_wide(), ctx->max_kf_desc);
     TRY(lc_refresh_tiles(ctx));
-    if (ctx->lc_work_unit == 0) {
-        // range form: contiguous 128-row tile ranges per CTA, keyframes cut by a range are merged by the last piece,
-        // the last CTA computes the top-k (and the peer exchange) -- one launch
+    if (lc_fused_tail(ctx)) {
+        // one sweep + top-k (+ peer exchange) without leaving the device.  Tensor-core form (lc_tc.cuh) when the query fits
+        // its four resident quarters; otherwise the range form: contiguous 128-row tile ranges per CTA, keyframes cut by a
+        // range merged by the last piece, the last CTA computes the top-k -- one launch
+        const bool tensor = ctx->lc_tensor && ctx->lc_work_unit == 0 && ctx->lc_nq <= lc_tc_max_query() && ctx->max_kf_desc <= lc_max_kf_desc();
         const int grid = lc_range_grid(ctx->lc_nq, ctx->n_tiles, ctx->sm_count);
         const size_t o_col = (lc_range_rowpart_bytes(grid) + 255) & ~(size_t)255;
         const bool keep_f2m = ctx->f2m.valid, keep_f2f = ctx->f2f.valid;
-        TRY(ensure_dev(ctx, ctx->d_range, o_col + lc_range_colpart_bytes(grid)));
+        if (tensor) {
+            TRY(ensure_dev(ctx, ctx->d_tc_row, lc_tc_rowbest_bytes(ctx->n_kf)));
+            TRY(ensure_dev(ctx, ctx->d_tc_col, lc_tc_colbest_bytes(ctx->db_n, ctx->lc_nq)));
+        } else {
+            TRY(ensure_dev(ctx, ctx->d_range, o_col + lc_range_colpart_bytes(grid)));
+        }
         ctx->f2m.valid = keep_f2m; ctx->f2f.valid = keep_f2f;
         LcSweepArgs a;
         a.query = reinterpret_cast<const uint4*>(query_in_xchg ? (const uint8_t*)(ctx->d_xchg + kLcXchgQueryOff) : ctx->d_lc_query);
@@ -2277,12 +2310,15 @@ static int lc_enqueue_local(pslam_ctx* ctx, int tau, int k, bool exchange = fals
         a.qflag = pushed_query ? reinterpret_cast<const uint32_t*>(ctx->d_xchg) + kLcXchgQFlagOff : nullptr;
         a.qepoch = ctx->lc_qepoch;
         CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
-        CK(launch_lc_sweep_range(a, grid, ctx->stream, &l));
+        if (tensor) CK(launch_lc_sweep_tc(a, ctx->db_n, (uint32_t*)ctx->d_tc_row.p, (uint32_t*)ctx->d_tc_col.p, ctx->d_tc_status, ctx->sm_count, ctx->stream, &l));
+        else CK(launch_lc_sweep_range(a, grid, ctx->stream, &l));
         CK(cudaEventRecord(ctx->ev_sweep1, ctx->stream));
+        ctx->lc_last_tensor = tensor;
         ctx->launches += l;
         return PSLAM_OK;
     }
     // round-1 forms, kept behind pslam_lc_set_work_unit: whole keyframes per CTA (1) / 128-row tiles + finalize (2)
+    ctx->lc_last_tensor = false;
     CK(cudaEventRecord(ctx->ev_sweep0, ctx->stream));
     if (ctx->lc_work_unit == 2) {
         const size_t o_col = (lc_split_rowpart_bytes(ctx->n_tiles) + 255) & ~(size_t)255;
@@ -2437,7 +2473,7 @@ int pslam_comm_init(pslam_ctx* ctx, const uint8_t id[128], int rank, int world) 
 int pslam_lc_exchange_mode(const pslam_ctx* ctx) {
     if (!ctx) return PSLAM_ERR_ARG;
     if (ctx->world <= 1) return 0;
-    return (ctx->p2p && ctx->lc_work_unit == 0) ? 2 : 1;
+    return (ctx->p2p && lc_fused_tail(ctx)) ? 2 : 1;
 }
 
 int pslam_comm_destroy(pslam_ctx* ctx) {
@@ -2457,7 +2493,7 @@ int pslam_comm_destroy(pslam_ctx* ctx) {
 static int lc_enqueue_sharded(pslam_ctx* ctx, int root, int tau, int k) {
     NcclApi* api = nccl_api();
     if (ctx->world <= 1) return lc_enqueue_local(ctx, tau, k);
-    const bool peer = ctx->p2p && ctx->lc_work_unit == 0;
+    const bool peer = ctx->p2p && lc_fused_tail(ctx);
     ++ctx->lc_epoch;
     bool pushed = false;
     if (root >= 0) {

@@ -63,6 +63,14 @@ int lc_range_grid(int nq, int n_tiles, int sm_count);
 size_t lc_range_rowpart_bytes(int grid);
 size_t lc_range_colpart_bytes(int grid);
 cudaError_t launch_lc_sweep_range(const LcSweepArgs& a, int grid, cudaStream_t st, int* launches);
+// tensor-core form (lc_tc.cuh): tcgen05 kind::i8 sweep into per-split partial results + finalize with the same fused tail.
+// Needs nq <= lc_tc_max_query() and keyframes of at most lc_max_kf_desc() rows.  d_status: one int, non-zero after a time-out.
+cudaError_t lc_sweep_tc_configure();
+int lc_tc_max_query();
+size_t lc_tc_rowbest_bytes(int n_kf);
+size_t lc_tc_colbest_bytes(long long n_desc, int nq);
+cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t* d_rowbest, uint32_t* d_colbest, int* d_status,
+                               int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_lc_push_query(const uint8_t* d_query, int nq, const LcExchange& x, uint32_t qepoch, cudaStream_t st, int* launches);
 // in-place re-encoding of n descriptor rows (32 B each) for the encoded Hamming compare of the sweep kernels
 cudaError_t launch_lc_encode_rows(uint8_t* d_rows, long long n, cudaStream_t st, int* launches);

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "hamming_tile.cuh"
 #include "kernels.h"
+#include "lc_tc.cuh"
 
 namespace pslam {
 
@@ -408,6 +409,75 @@ cudaError_t launch_lc_sweep_range(const LcSweepArgs& a, int grid, cudaStream_t s
     else if (rq == 1) lc_sweep_range_kernel<1, 256><<<grid, 256, lc_range_smem<256>(), st>>>(a);
     else if (rq == 2) lc_sweep_range_kernel<2, 256><<<grid, 256, lc_range_smem<256>(), st>>>(a);
     else lc_sweep_range_kernel<4, 256><<<grid, 256, lc_range_smem<256>(), st>>>(a);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// ---- tensor-core form (lc_tc.cuh): sweep kernel + this finalize, whose last CTA runs the same tail as the range form ----
+__global__ void __launch_bounds__(256) lc_tc_finalize_kernel(const LcSweepArgs a, const uint32_t* __restrict__ row_best,
+                                                             const uint32_t* __restrict__ col_best, long long n_desc) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint32_t* s_col = reinterpret_cast<uint32_t*>(smem_raw);               // kMaxKfDesc words
+    int* s_int = reinterpret_cast<int*>(smem_raw + sizeof(uint32_t) * kMaxKfDesc);
+    const int tid = threadIdx.x;
+    for (int kf = (int)blockIdx.x; kf < a.n_kf; kf += (int)gridDim.x)
+        tc::finalize_keyframe(kf, reinterpret_cast<const long long*>(a.kf_off), a.nq, n_desc, row_best, col_best, a.tau, a.scores,
+                              s_col, s_int);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_int[1] = (atomicAdd(a.cta_done, 1u) == (unsigned)(gridDim.x - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_int[1]) return;
+    __threadfence();
+    if (tid == 0) *a.cta_done = 0u;
+    block_topk<256>(a.scores, a.n_kf, a.kf_id_base, a.k, smem_raw, a.out_pairs);
+    if (a.x.world > 1 && a.x.local) {
+        __threadfence();
+        __syncthreads();
+        exchange_and_merge<256>(a.x, a.out_pairs, a.k, smem_raw, a.out_merged);
+    }
+}
+static size_t lc_tc_finalize_smem() {
+    const size_t fin = sizeof(uint32_t) * kMaxKfDesc + 16;
+    const size_t tail = kTopkSmemBytes > sizeof(unsigned long long) * 1024 ? kTopkSmemBytes : sizeof(unsigned long long) * 1024;
+    return fin > tail ? fin : tail;
+}
+cudaError_t lc_sweep_tc_configure() {
+    cudaError_t e = cudaFuncSetAttribute(tc::lc_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lc_tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_tc_finalize_smem());
+}
+int lc_tc_max_query() { return tc::kMaxQueries; }
+size_t lc_tc_rowbest_bytes(int n_kf) { return sizeof(uint32_t) * (size_t)tc::kMaxQueries * (size_t)(n_kf > 0 ? n_kf : 1); }
+size_t lc_tc_colbest_bytes(long long n_desc, int nq) {
+    const int splits = (nq + tc::kQRows - 1) / tc::kQRows;
+    return sizeof(uint32_t) * (size_t)splits * (size_t)(n_desc > 0 ? n_desc : 1);
+}
+cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t* d_rowbest, uint32_t* d_colbest, int* d_status,
+                               int sm_count, cudaStream_t st, int* launches) {
+    tc::SweepArgs A;
+    A.db = reinterpret_cast<const uint32_t*>(a.db);
+    A.kf_off = reinterpret_cast<const long long*>(a.kf_off);
+    A.n_kf = a.n_kf;
+    A.db_encoded = 1;                       // the resident map is stored re-encoded (lc_encode_rows_kernel)
+    A.query = reinterpret_cast<const uint32_t*>(a.query);
+    A.nq = a.nq;
+    A.n_desc = n_desc;
+    A.row_best = d_rowbest; A.col_best = d_colbest; A.status = d_status;
+    A.n_splits = (a.nq + tc::kQRows - 1) / tc::kQRows;
+    A.qflag = a.qflag; A.qepoch = a.qepoch;
+    if (a.n_kf > 0) {
+        const int groups = sm_count / A.n_splits > 0 ? sm_count / A.n_splits : 1;
+        tc::lc_tc_sweep_kernel<<<A.n_splits * groups, tc::kThreads, tc::kSmemBytes, st>>>(A);
+        if (launches) *launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    int grid = a.n_kf < 8 * sm_count ? a.n_kf : 8 * sm_count;
+    if (grid < 1) grid = 1;
+    lc_tc_finalize_kernel<<<grid, 256, lc_tc_finalize_smem(), st>>>(a, d_rowbest, d_colbest, n_desc);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -196,8 +196,11 @@ struct SweepArgs {
     int nq;
     long long n_desc;            // stride of col_best between splits
     uint32_t* row_best;          // [n_kf][kMaxQueries]: Ham << 16 | t (index inside the keyframe)
-    uint32_t* col_best;          // [kSplits][n_desc]:   Ham << 16 | q
+    uint32_t* col_best;          // [n_splits][n_desc]:  Ham << 16 | q
     int* status;                 // set non-zero when a wait timed out
+    int n_splits;                // ceil(nq / kQRows): query quarters in use; the grid is n_splits x groups
+    const uint32_t* qflag;       // wait until *qflag == qepoch before reading the query (pushed by a peer over NVLink); null: it is here
+    uint32_t qepoch;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) {
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
     __shared__ uint32_t s_tmem;
     __shared__ int s_abort;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int split = blockIdx.x & (kSplits - 1), group = blockIdx.x >> 2, n_groups = gridDim.x >> 2;
+    const int split = (int)blockIdx.x % A.n_splits, group = (int)blockIdx.x / A.n_splits, n_groups = (int)gridDim.x / A.n_splits;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
 
     if (tid == 0) {
@@ -222,6 +225,13 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 12) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (A.qflag) {
+        if (tid == 0) {
+            uint32_t v;
+            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(A.qflag) : "memory"); if (v != A.qepoch) __nanosleep(32); } while (v != A.qepoch);
+        }
+        __syncthreads();
+    }
     // the CTA's queries, expanded once
     if (tid < kQRows) {
         const int q = split * kQRows + tid;
@@ -366,17 +376,15 @@ done:
     if (tid == 0 && s_abort) *A.status = 1;
 }
 
-// cross-check + count per keyframe: merges the per-split column results, then score[kf] = #{q : colbest[t*(q)].q == q, Ham <= tau}
-__global__ void __launch_bounds__(256) lc_tc_finalize_kernel(const long long* __restrict__ kf_off, int nq, long long n_desc,
-                                                             const uint32_t* __restrict__ row_best, const uint32_t* __restrict__ col_best,
-                                                             int tau, int* __restrict__ scores) {
-    __shared__ uint32_t s_col[4096];
-    __shared__ int s_cnt;
-    const int kf = blockIdx.x;
+// cross-check + count of one keyframe (whole CTA): merges the per-split column results, then
+// score[kf] = #{q : colbest[t*(q)].q == q, Ham <= tau}.  s_col: 4096 words, s_cnt: 1 int of shared memory.
+__device__ __forceinline__ void finalize_keyframe(int kf, const long long* __restrict__ kf_off, int nq, long long n_desc,
+                                                  const uint32_t* __restrict__ row_best, const uint32_t* __restrict__ col_best,
+                                                  int tau, int* __restrict__ scores, uint32_t* s_col, int* s_cnt) {
     const long long r0 = kf_off[kf];
     const int n_t = (int)(kf_off[kf + 1] - r0);
     const int splits = (nq + kQRows - 1) / kQRows;
-    if (threadIdx.x == 0) s_cnt = 0;
+    if (threadIdx.x == 0) *s_cnt = 0;
     for (int t = threadIdx.x; t < n_t; t += blockDim.x) {
         uint32_t m = 0xffffffffu;
         for (int s = 0; s < splits; ++s) m = min(m, __ldcs(col_best + (size_t)s * (size_t)n_desc + (size_t)(r0 + t)));
@@ -391,9 +399,10 @@ __global__ void __launch_bounds__(256) lc_tc_finalize_kernel(const long long* __
             if (ham <= tau && (int)(s_col[t] & 0xffffu) == q) ++cnt;
         }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(s_cnt, cnt);
     __syncthreads();
-    if (threadIdx.x == 0) scores[kf] = s_cnt;
+    if (threadIdx.x == 0) scores[kf] = *s_cnt;
+    __syncthreads();
 }
 
 }  // namespace tc

@@ -47,10 +47,11 @@ def test_fuzz_lc_sweep(ctx, O):
         if off[-1] or n_kf:
             ctx.lc_append(db if off[-1] else np.zeros((1, 32), np.uint8), off)
         ref = O.lc_scores(q, db if off[-1] else np.zeros((1, 32), np.uint8), off, tau=70, threads=4)
-        for unit in (1, 2):
+        for unit in (1, 2, 3, 0):
             ctx.lc_set_work_unit(unit)
             ids, sc, scores = ctx.lc_query(q, tau=70, k=5, want_scores=True)
             assert np.array_equal(scores, ref), (k, unit)
+            assert ctx.lc_tensor_status()[1] == 0
             assert np.array_equal(ids, O.topk(ref, 5)[0]) and np.array_equal(sc, O.topk(ref, 5)[1])
         ctx.lc_set_work_unit(0)
         if off[-1] >= 1:

@@ -21,11 +21,12 @@ def test_lc_scores_vs_oracle(ctx, O, n_kf, per_kf, nq, ragged):
     ctx.lc_append(db["db"], db["kf_off"])
     ref = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=8)
     eid, esc = O.topk(ref, 16)
-    for unit in (1, 2, 0):     # keyframe work units, tile work units, automatic
+    for unit in (1, 2, 3, 0):     # keyframe work units, tile work units, popcount range form, automatic (tensor cores)
         ctx.lc_set_work_unit(unit)
         ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=16, want_scores=True)
         assert np.array_equal(scores, ref), unit
         assert np.array_equal(ids, eid) and np.array_equal(sc, esc), unit
+        assert ctx.lc_tensor_status() == (unit == 0, 0), unit      # the automatic form IS the tcgen05 kernel, and it never timed out
     for tau in (0, 30, 256):
         _, _, s2 = ctx.lc_query(db["query"], tau=tau, k=4, want_scores=True)
         assert np.array_equal(s2, O.lc_scores(db["query"], db["db"], db["kf_off"], tau=tau, threads=8))
@@ -119,12 +120,12 @@ def test_lc_wide_query_sets(ctx, O, nq):
     _fresh(ctx)
     ctx.lc_append(db["db"], db["kf_off"])
     ref = O.lc_scores(db["query"], db["db"], db["kf_off"], tau=64, threads=8)
-    for unit in (1, 2):
+    for unit in (1, 2, 0):
         ctx.lc_set_work_unit(unit)
         ids, sc, scores = ctx.lc_query(db["query"], tau=64, k=8, want_scores=True)
         assert np.array_equal(scores, ref), unit
         assert np.array_equal(ids, O.topk(ref, 8)[0])
-    ctx.lc_set_work_unit(0)
+        assert ctx.lc_tensor_status() == (False, 0)      # beyond 1024 queries the popcount form runs
     idx, dist = ctx.lc_knn2(db["query"])
     oi, od = O.knn2(db["query"], db["db"])
     assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32))
