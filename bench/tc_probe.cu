@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int groups, int n, long l
 // section "ldtm": TMEM read rate.  `warps` warps (4 or 8) each read x32 chunks of their lane quarter in a loop and fold
 // them with 3-input maxima (what the sweep's epilogue does with them)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ldtm_rate_kernel(int iters, int fold, long long* __restrict__ clk, int* __restrict__ sink) {
+template <int fold>
+__global__ void __launch_bounds__(256) ldtm_rate_kernel(int iters, long long* __restrict__ clk, int* __restrict__ sink) {
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem), 512);
@@ -141,6 +142,9 @@ __global__ void __launch_bounds__(256) ldtm_rate_kernel(int iters, int fold, lon
     const uint32_t tm = s_tmem;
     const uint32_t base = tm + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
     int m = -0x7fffffff;
+    int colmax[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) colmax[i] = -0x7fffffff;
     const long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
@@ -149,16 +153,28 @@ __global__ void __launch_bounds__(256) ldtm_rate_kernel(int iters, int fold, lon
             int v[32];
             tmem_ld32(base + (uint32_t)c, v);
             tmem_ld_wait();
-            if (fold) {
+            if (fold == 2) {          // both reductions of a single-orientation epilogue: row maximum + warp-wide column maxima
+                int keep = -0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    m = max(m, max(v[j], v[j + 1]));
+                    const int r0 = __reduce_max_sync(0xffffffffu, v[j]), r1 = __reduce_max_sync(0xffffffffu, v[j + 1]);
+                    if ((tid & 31) == j) keep = r0;
+                    if ((tid & 31) == j + 1) keep = r1;
+                }
+                colmax[c >> 5] = max(colmax[c >> 5], keep);
+            } else if (fold) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) m = max(m, max(v[j], v[j + 1]));
             } else {
-                m ^= v[it & 31];
+                m ^= v[0] + v[31];
             }
         }
     }
     const long long t1 = clock64();
     if (tid == 0) clk[blockIdx.x] = t1 - t0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m ^= colmax[i];
     sink[blockIdx.x * blockDim.x + tid] = m;
     fence_before();
     __syncthreads();
@@ -228,8 +244,9 @@ int main(int argc, char** argv) {
     CK(cudaMemset(d_status, 0, 16));
     int h_status = 0;
 
+    const bool only_sweep = argc > 5 && atoi(argv[5]);
     // ---- layout ----
-    {
+    if (!only_sweep) {
         std::vector<uint32_t> q(128 * 8), t(256 * 8);
         uint64_t s = 0x9e3779b97f4a7c15ull;
         auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 16); };
@@ -264,6 +281,7 @@ int main(int argc, char** argv) {
     // ---- mma rate ----
     long long* d_clk; CK(cudaMalloc(&d_clk, sizeof(long long) * 1024));
     for (int n : {256, 128}) {
+        if (only_sweep) break;
         const int groups = 2000, smem = (128 + 256) * tc::kRowBytes;
         CK(cudaFuncSetAttribute(tc::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -286,11 +304,17 @@ int main(int argc, char** argv) {
     // ---- ldtm rate ----
     int* d_sink; CK(cudaMalloc(&d_sink, 4 * 256 * sms));
     for (int warps : {4, 8})
-        for (int fold : {0, 1}) {
+        for (int fold : {0, 1, 2}) {
+            if (only_sweep) break;
             const int iters = 2000;
-            tc::ldtm_rate_kernel<<<sms, warps * 32>>>(100, fold, d_clk, d_sink);
+            auto launch = [&](int n) {
+                if (fold == 0) tc::ldtm_rate_kernel<0><<<sms, warps * 32>>>(n, d_clk, d_sink);
+                else if (fold == 1) tc::ldtm_rate_kernel<1><<<sms, warps * 32>>>(n, d_clk, d_sink);
+                else tc::ldtm_rate_kernel<2><<<sms, warps * 32>>>(n, d_clk, d_sink);
+            };
+            launch(100);
             CK(cudaDeviceSynchronize());
-            tc::ldtm_rate_kernel<<<sms, warps * 32>>>(iters, fold, d_clk, d_sink);
+            launch(iters);
             CK(cudaDeviceSynchronize());
             std::vector<long long> clk(sms);
             CK(cudaMemcpy(clk.data(), d_clk, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
@@ -338,7 +362,7 @@ int main(int argc, char** argv) {
         uint32_t *dq, *ddb, *drow, *dcol; long long* doff; int *dsc, *dref;
         CK(cudaMalloc(&dq, q.size() * 4)); CK(cudaMalloc(&ddb, db.size() * 4)); CK(cudaMalloc(&doff, off.size() * 8));
         CK(cudaMalloc(&drow, (size_t)n_kf * tc::kMaxQueries * 4)); CK(cudaMalloc(&dcol, (size_t)n_desc * tc::kSplits * 4));
-        CK(cudaMalloc(&dsc, n_kf * 4)); CK(cudaMalloc(&dref, n_kf * 4));
+        CK(cudaMalloc(&dsc, n_kf * 4)); CK(cudaMalloc(&dref, n_kf * 4)); int* dref2; CK(cudaMalloc(&dref2, n_kf * 4));
         CK(cudaMemcpy(dq, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ddb, db.data(), db.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(doff, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
@@ -347,6 +371,9 @@ int main(int argc, char** argv) {
         A.db = ddb; A.kf_off = doff; A.n_kf = n_kf; A.db_encoded = 0; A.query = dq; A.nq = nq; A.n_desc = n_desc;
         A.row_best = drow; A.col_best = dcol; A.status = d_status;
         A.n_splits = (nq + tc::kQRows - 1) / tc::kQRows; A.qflag = nullptr; A.qepoch = 0;
+        int* dkfd; CK(cudaMalloc(&dkfd, n_kf * 4)); CK(cudaMemset(dkfd, 0, n_kf * 4));
+        const int fused = argc > 4 ? atoi(argv[4]) : 1;
+        A.tau = tau; A.scores = fused ? dsc : nullptr; A.kf_done = dkfd; A.fin_mode = fused > 1 ? fused : 0;     // fused finalize (the separate kernel below then only re-derives the same scores)
         CK(cudaFuncSetAttribute(tc::lc_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         const int grid = (sms / A.n_splits) * A.n_splits;
         cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
@@ -355,7 +382,8 @@ int main(int argc, char** argv) {
             cudaEventRecord(e0);
             tc::lc_tc_sweep_kernel<<<grid, tc::kThreads, tc::kSmemBytes>>>(A);
             cudaEventRecord(e1);
-            tc::finalize_kernel<<<n_kf, 256>>>(doff, nq, n_desc, drow, dcol, tau, dsc);
+            tc::finalize_kernel<<<n_kf, 256>>>(doff, nq, n_desc, drow, dcol, tau, fused ? dref2 : dsc);
+            if (!fused) cudaMemcpyAsync(dref2, dsc, n_kf * 4, cudaMemcpyDeviceToDevice);
             cudaEventRecord(e2);
             CK(cudaDeviceSynchronize());
             cudaEventElapsedTime(&ms_sweep, e0, e1); cudaEventElapsedTime(&ms_fin, e1, e2);
@@ -364,15 +392,18 @@ int main(int argc, char** argv) {
         const int nchk = check_kf < n_kf ? check_kf : n_kf;
         tc::ref_scores_kernel<<<nchk, 1024>>>(ddb, doff, dq, nq, tau, dref);
         CK(cudaDeviceSynchronize());
-        std::vector<int> sc(n_kf), rf(nchk);
+        std::vector<int> sc(n_kf), rf(nchk), sc2(n_kf);
         CK(cudaMemcpy(sc.data(), dsc, n_kf * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(sc2.data(), dref2, n_kf * 4, cudaMemcpyDeviceToHost));
+        int fused_vs_separate = 0;
+        for (int k = 0; k < n_kf; ++k) fused_vs_separate += sc[k] != sc2[k];
         CK(cudaMemcpy(rf.data(), dref, nchk * 4, cudaMemcpyDeviceToHost));
         int bad = 0, first = -1; long long sum = 0;
         for (int k = 0; k < nchk; ++k) { if (sc[k] != rf[k]) { if (first < 0) first = k; ++bad; } sum += rf[k]; }
         const double pairs = (double)nq * (double)n_desc;
-        printf("{\"section\": \"sweep\", \"status\": %d, \"nq\": %d, \"n_kf\": %d, \"n_desc\": %lld, \"checked_kf\": %d, \"score_mismatches\": %d, \"first_bad\": %d, "
+        printf("{\"section\": \"sweep\", \"chains\": %d, \"fused_finalize\": %d, \"status\": %d, \"nq\": %d, \"n_kf\": %d, \"n_desc\": %lld, \"checked_kf\": %d, \"fused_vs_separate_finalize_mismatches\": %d, \"score_mismatches\": %d, \"first_bad\": %d, "
                "\"got\": %d, \"want\": %d, \"mean_score\": %.2f, \"sweep_ms\": %.4f, \"finalize_ms\": %.4f, \"gcmp_per_s\": %.1f, \"gcmp_per_s_sweep_only\": %.1f}\n",
-               h_status, nq, n_kf, n_desc, nchk, bad, first, first >= 0 ? sc[first] : 0, first >= 0 ? rf[first] : 0, (double)sum / nchk,
+               PSLAM_TC_CHAINS, fused, h_status, nq, n_kf, n_desc, nchk, fused_vs_separate, bad, first, first >= 0 ? sc[first] : 0, first >= 0 ? rf[first] : 0, (double)sum / nchk,
                ms_sweep, ms_fin, pairs / ((ms_sweep + ms_fin) * 1e-3) / 1e9, pairs / (ms_sweep * 1e-3) / 1e9);
         fflush(stdout);
     }

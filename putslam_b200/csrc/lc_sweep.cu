@@ -413,41 +413,31 @@ cudaError_t launch_lc_sweep_range(const LcSweepArgs& a, int grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-// ---- tensor-core form (lc_tc.cuh): sweep kernel + this finalize, whose last CTA runs the same tail as the range form ----
-__global__ void __launch_bounds__(256) lc_tc_finalize_kernel(const LcSweepArgs a, const uint32_t* __restrict__ row_best,
-                                                             const uint32_t* __restrict__ col_best, long long n_desc) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint32_t* s_col = reinterpret_cast<uint32_t*>(smem_raw);               // kMaxKfDesc words
-    int* s_int = reinterpret_cast<int*>(smem_raw + sizeof(uint32_t) * kMaxKfDesc);
+// ---- tensor-core form (lc_tc.cuh): the sweep (per-keyframe finalize fused into its epilogue warps), then -- in the CTA
+//      that finishes last -- the same tail as the range form: top-k, peer exchange, merge.  One launch per query.
+__global__ void __launch_bounds__(tc::kThreads, 1) lc_tc_sweep_tail_kernel(const tc::SweepArgs A, const LcSweepArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ int s_last;
+    tc::sweep_body(A);                      // ends with a CTA-wide barrier; shared memory is free from here on
     const int tid = threadIdx.x;
-    for (int kf = (int)blockIdx.x; kf < a.n_kf; kf += (int)gridDim.x)
-        tc::finalize_keyframe(kf, reinterpret_cast<const long long*>(a.kf_off), a.nq, n_desc, row_best, col_best, a.tau, a.scores,
-                              s_col, s_int);
-    __syncthreads();
     if (tid == 0) {
         __threadfence();
-        s_int[1] = (atomicAdd(a.cta_done, 1u) == (unsigned)(gridDim.x - 1)) ? 1 : 0;
+        s_last = (atomicAdd(a.cta_done, 1u) == (unsigned)(gridDim.x - 1)) ? 1 : 0;
     }
     __syncthreads();
-    if (!s_int[1]) return;
+    if (!s_last) return;
     __threadfence();
     if (tid == 0) *a.cta_done = 0u;
-    block_topk<256>(a.scores, a.n_kf, a.kf_id_base, a.k, smem_raw, a.out_pairs);
+    // keyframes beyond the reach of the grid's groups do not exist (every group strides the whole list); empty maps: n_kf == 0
+    block_topk<tc::kThreads>(a.scores, a.n_kf, a.kf_id_base, a.k, smem, a.out_pairs);
     if (a.x.world > 1 && a.x.local) {
         __threadfence();
         __syncthreads();
-        exchange_and_merge<256>(a.x, a.out_pairs, a.k, smem_raw, a.out_merged);
+        exchange_and_merge<tc::kThreads>(a.x, a.out_pairs, a.k, smem, a.out_merged);
     }
 }
-static size_t lc_tc_finalize_smem() {
-    const size_t fin = sizeof(uint32_t) * kMaxKfDesc + 16;
-    const size_t tail = kTopkSmemBytes > sizeof(unsigned long long) * 1024 ? kTopkSmemBytes : sizeof(unsigned long long) * 1024;
-    return fin > tail ? fin : tail;
-}
 cudaError_t lc_sweep_tc_configure() {
-    cudaError_t e = cudaFuncSetAttribute(tc::lc_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lc_tc_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc_tc_finalize_smem());
+    return cudaFuncSetAttribute(lc_tc_sweep_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 int lc_tc_max_query() { return tc::kMaxQueries; }
 size_t lc_tc_rowbest_bytes(int n_kf) { return sizeof(uint32_t) * (size_t)tc::kMaxQueries * (size_t)(n_kf > 0 ? n_kf : 1); }
@@ -457,6 +447,7 @@ size_t lc_tc_colbest_bytes(long long n_desc, int nq) {
 }
 cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t* d_rowbest, uint32_t* d_colbest, int* d_status,
                                int sm_count, cudaStream_t st, int* launches) {
+    static_assert(tc::kSmemBytes >= (int)kTopkSmemBytes && tc::kSmemBytes >= (int)(sizeof(unsigned long long) * 1024), "tail scratch fits the tile buffers");
     tc::SweepArgs A;
     A.db = reinterpret_cast<const uint32_t*>(a.db);
     A.kf_off = reinterpret_cast<const long long*>(a.kf_off);
@@ -466,18 +457,11 @@ cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t*
     A.nq = a.nq;
     A.n_desc = n_desc;
     A.row_best = d_rowbest; A.col_best = d_colbest; A.status = d_status;
+    A.tau = a.tau; A.scores = a.scores; A.kf_done = a.kf_done; A.fin_mode = 0;
     A.n_splits = (a.nq + tc::kQRows - 1) / tc::kQRows;
     A.qflag = a.qflag; A.qepoch = a.qepoch;
-    if (a.n_kf > 0) {
-        const int groups = sm_count / A.n_splits > 0 ? sm_count / A.n_splits : 1;
-        tc::lc_tc_sweep_kernel<<<A.n_splits * groups, tc::kThreads, tc::kSmemBytes, st>>>(A);
-        if (launches) *launches += 1;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    int grid = a.n_kf < 8 * sm_count ? a.n_kf : 8 * sm_count;
-    if (grid < 1) grid = 1;
-    lc_tc_finalize_kernel<<<grid, 256, lc_tc_finalize_smem(), st>>>(a, d_rowbest, d_colbest, n_desc);
+    const int groups = sm_count / A.n_splits > 0 ? sm_count / A.n_splits : 1;
+    lc_tc_sweep_tail_kernel<<<A.n_splits * groups, tc::kThreads, tc::kSmemBytes, st>>>(A, a);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

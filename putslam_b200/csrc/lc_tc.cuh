@@ -43,7 +43,13 @@ constexpr int kSplits = 4;                        // query quarters: up to 1024 
 constexpr int kMaxQueries = kQRows * kSplits;
 constexpr int kVal = 16;                          // |q_k| = |t_k|
 constexpr int kStepShift = 9;                     // accumulator = (128 - Ham) << 9 | index fields (< 512)
-constexpr int kThreads = 13 * 32;                 // warps 0-3 producers, 4-7 / 8-11 epilogue sets, 12 MMA
+#ifndef PSLAM_TC_PROD_WARPS
+#define PSLAM_TC_PROD_WARPS 4
+#endif
+constexpr int kProdWarps = PSLAM_TC_PROD_WARPS;   // 4: two rows per thread and pair; 8: one
+constexpr int kEpiWarp0 = kProdWarps;             // epilogue sets: warps kEpiWarp0 .. +3 and +4 .. +7 (lane quarter = warp & 3)
+constexpr int kMmaWarp = kProdWarps + 8, kFinWarp = kProdWarps + 9;
+constexpr int kThreads = (kProdWarps + 10) * 32;  // producers | 8 epilogue | MMA issuer | per-keyframe finalize
 constexpr int kSmemBytes = 2 * kTileBytes + 4 * kTileBytes + 256;
 constexpr long long kSpinLimit = 2000000000ll;    // ~1 s of clocks: a wrong barrier shows up as an error, not as a hang
 
@@ -170,21 +176,44 @@ __device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
     w[6] = w[6] ^ e2 ^ e5;
 }
 
-// maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address)
+// maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address).
+// Four independent chains: a single dependent chain of 128 3-input maxima is latency-bound and makes the MMA warp wait
+// for its TMEM buffer.
+#ifndef PSLAM_TC_CHAINS
+#define PSLAM_TC_CHAINS 1
+#endif
 __device__ __forceinline__ int row_max_256(uint32_t taddr) {
-    int m = -0x7fffffff;
+    int m0 = -0x7fffffff, m1 = m0, m2 = m0, m3 = m0;
 #pragma unroll
     for (int c = 0; c < 256; c += 64) {
         int a[32], b[32];
         tmem_ld32(taddr + (uint32_t)c, a);
         tmem_ld32(taddr + (uint32_t)(c + 32), b);
         tmem_ld_wait();
+#if PSLAM_TC_CHAINS == 1
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) m = max3(m, a[j], a[j + 1]);
+        for (int j = 0; j < 32; j += 2) m0 = max3(m0, a[j], a[j + 1]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) m = max3(m, b[j], b[j + 1]);
+        for (int j = 0; j < 32; j += 2) m0 = max3(m0, b[j], b[j + 1]);
+#elif PSLAM_TC_CHAINS == 2
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { m0 = max3(m0, a[j], a[j + 1]); m1 = max3(m1, a[j + 2], a[j + 3]); }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { m0 = max3(m0, b[j], b[j + 1]); m1 = max3(m1, b[j + 2], b[j + 3]); }
+#else
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            m0 = max3(m0, a[j], a[j + 1]); m1 = max3(m1, a[j + 2], a[j + 3]);
+            m2 = max3(m2, a[j + 4], a[j + 5]); m3 = max3(m3, a[j + 6], a[j + 7]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            m0 = max3(m0, b[j], b[j + 1]); m1 = max3(m1, b[j + 2], b[j + 3]);
+            m2 = max3(m2, b[j + 4], b[j + 5]); m3 = max3(m3, b[j + 6], b[j + 7]);
+        }
+#endif
     }
-    return m;
+    return max(max(m0, m1), max(m2, m3));
 }
 
 struct SweepArgs {
@@ -198,33 +227,40 @@ struct SweepArgs {
     uint32_t* row_best;          // [n_kf][kMaxQueries]: Ham << 16 | t (index inside the keyframe)
     uint32_t* col_best;          // [n_splits][n_desc]:  Ham << 16 | q
     int* status;                 // set non-zero when a wait timed out
+    int tau;                     // fused finalize: score[kf] = #{cross-check matches with Ham <= tau}
+    int* scores;                 // [n_kf]; written by the CTA that finishes a keyframe last (null: no fused finalize, see finalize_keyframe)
+    int* kf_done;                // [n_kf] arrival counters of the splits, zero between launches
+    int fin_mode;                // debug: 0 normal, 2 handshake only, 3 handshake + fence + counter
     int n_splits;                // ceil(nq / kQRows): query quarters in use; the grid is n_splits x groups
     const uint32_t* qflag;       // wait until *qflag == qepoch before reading the query (pushed by a peer over NVLink); null: it is here
     uint32_t qepoch;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) {
+__device__ __forceinline__ void sweep_body(const SweepArgs& A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sq = smem;                                 // 2 tiles: the CTA's 256 queries
     uint8_t* st = smem + 2 * kTileBytes;                // ring of 4 tiles = 2 pairs
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);   // full[2], empty[2], tfull[2], tempty[2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);   // full[2], empty[2], tfull[2], tempty[2], fin_full, fin_free
     __shared__ uint32_t s_tmem;
     __shared__ int s_abort;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int split = (int)blockIdx.x % A.n_splits, group = (int)blockIdx.x / A.n_splits, n_groups = (int)gridDim.x / A.n_splits;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
+    const uint32_t bar_fin_full = smem_u32(bars + 8), bar_fin_free = smem_u32(bars + 9);
 
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_full + 8 * i, 4);       // one arrival per producer warp
+            mbar_init(bar_full + 8 * i, kProdWarps);   // one arrival per producer warp
             mbar_init(bar_empty + 8 * i, 1);      // tcgen05.commit
             mbar_init(bar_tfull + 8 * i, 1);      // tcgen05.commit
             mbar_init(bar_tempty + 8 * i, 4);     // one arrival per epilogue warp of the set
         }
+        mbar_init(bar_fin_full, 8);               // the eight epilogue warps have written a keyframe's results
+        mbar_init(bar_fin_free, 1);               // the finalize warp is done with the previous keyframe
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&s_tmem), 512);
     if (A.qflag) {
         if (tid == 0) {
             uint32_t v;
@@ -254,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
     const uint32_t tm = s_tmem;
     volatile int* abort_flag = &s_abort;
 
-    if (warp < 4) {
+    if (warp < kProdWarps) {
         // ===== producers: two rows per thread and pair (row tid of each tile) =====
         uint32_t it = 0;
         for (int kf = group; kf < A.n_kf; kf += n_groups) {
@@ -262,11 +298,13 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
             const int pairs = (int)((r1 - r0 + kPairRows - 1) / kPairRows);
             for (int p = 0; p < pairs; ++p, ++it) {
                 const int s = it & 1;
-                uint32_t w[2][8];
-                bool valid[2];
+                constexpr int R = 256 / (kProdWarps * 32);          // rows of the pair per thread
+                uint32_t w[R][8];
+                bool valid[R];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const long long row = r0 + (long long)p * kPairRows + h * kTileRows + tid;
+                for (int h = 0; h < R; ++h) {
+                    const int rp = h * (kProdWarps * 32) + tid;       // row inside the pair
+                    const long long row = r0 + (long long)p * kPairRows + rp;
                     valid[h] = row < r1;
                     if (valid[h]) {
                         const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8));
@@ -280,14 +318,16 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
                 }
                 if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    expand_row(w[h], valid[h], st + (2 * s + h) * kTileBytes, tid, 255 - (h * kTileRows + tid), false);
+                for (int h = 0; h < R; ++h) {
+                    const int rp = h * (kProdWarps * 32) + tid;
+                    expand_row(w[h], valid[h], st + (2 * s + (rp >> 7)) * kTileBytes, rp & 127, 255 - rp, false);
+                }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_full + 8 * s);
             }
         }
-    } else if (warp == 12) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint64_t dq = make_desc(smem_u32(sq));
@@ -318,14 +358,62 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
                 }
             }
         }
+    } else if (warp == kFinWarp) {
+        // ===== per-keyframe finalize.  The split that finishes a keyframe last merges the partial column results,
+        //       cross-checks and counts -- off the critical path: the epilogue warps never wait for a fence or an atomic.
+        if (A.scores) {
+            uint32_t kfi = 0;
+            for (int kf = group; kf < A.n_kf; kf += n_groups, ++kfi) {
+                const long long r0 = A.kf_off[kf];
+                const int n_t = (int)(A.kf_off[kf + 1] - r0);
+                if (!mbar_wait(bar_fin_full, kfi & 1, abort_flag)) goto done;
+                int last = 0;
+                if (lane == 0 && A.fin_mode != 2) {
+                    __threadfence();                                      // the epilogue warps' results, observed through the barrier
+                    last = atomicAdd(A.kf_done + kf, 1) == A.n_splits - 1;
+                    if (last) A.kf_done[kf] = 0;
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last && A.fin_mode == 0) {
+                    __threadfence();
+                    int cnt = 0;
+                    if (n_t > 0)
+                        for (int q0 = 0; q0 < A.nq; q0 += 256) {              // 8 queries per lane in flight
+                            uint32_t rb[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { const int q = q0 + 32 * i + lane; rb[i] = q < A.nq ? __ldcg(A.row_best + (size_t)kf * kMaxQueries + q) : 0xffffffffu; }
+                            // all column loads of the 8 queries issued before the first use: one L2 round trip, not 32
+                            uint32_t c[8][kSplits];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int ham = (int)(rb[i] >> 16), t = (int)(rb[i] & 0xffffu);
+                                const bool ok = ham <= A.tau && t < n_t;
+#pragma unroll
+                                for (int sp = 0; sp < kSplits; ++sp)
+                                    c[i][sp] = (ok && sp < A.n_splits) ? __ldcg(A.col_best + (size_t)sp * (size_t)A.n_desc + (size_t)(r0 + t)) : 0xffffffffu;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t m = min(min(c[i][0], c[i][1]), min(c[i][2], c[i][3]));
+                                cnt += (m != 0xffffffffu && (int)(m & 0xffffu) == q0 + 32 * i + lane) ? 1 : 0;
+                            }
+                        }
+                    cnt = __reduce_add_sync(0xffffffffu, cnt);
+                    if (lane == 0) A.scores[kf] = cnt;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_fin_free);
+            }
+        }
     } else {
         // ===== epilogue: set b = (warp - 4) >> 2 owns TMEM buffer b; lane quarter = warp & 3 =====
-        const int b = (warp - 4) >> 2, lq = warp & 3;
+        const int b = (warp - kEpiWarp0) >> 2, lq = warp & 3;
         const uint32_t taddr = tm + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * 256);
         const int row_in_blk = lq * 32 + lane;                 // accumulator row of this thread
         const int q_local = b * kTileRows + row_in_blk;        // its query in the O1 groups
         const int iq = 255 - q_local;
         uint32_t n = 0;                                        // groups seen on this buffer
+        uint32_t kfi = 0;                                      // keyframes finished by this CTA
         for (int kf = group; kf < A.n_kf; kf += n_groups) {
             const long long r0 = A.kf_off[kf], r1 = A.kf_off[kf + 1];
             const int n_t = (int)(r1 - r0);
@@ -359,22 +447,31 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArg
                     A.col_best[(size_t)split * (size_t)A.n_desc + (size_t)(r0 + t_kf)] = ((uint32_t)ham << 16) | (uint32_t)(split * kQRows + ql);
                 }
             }
-            if (pairs > 0) {
-                const int ham = 128 - best_h;
-                const int tl = 255 - ((best_m & 511) - iq);
-                A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = ((uint32_t)ham << 16) | (uint32_t)(best_p * kPairRows + tl);
-            } else {
-                A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = 0xffffffffu;
+            {
+                uint32_t rb = 0xffffffffu;
+                if (pairs > 0) {
+                    const int ham = 128 - best_h;
+                    const int tl = 255 - ((best_m & 511) - iq);
+                    rb = ((uint32_t)ham << 16) | (uint32_t)(best_p * kPairRows + tl);
+                }
+                A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = rb;
             }
+            if (A.scores) {      // hand the keyframe to the finalize warp (which must be done with the previous one)
+                if (!mbar_wait(bar_fin_free, (kfi & 1) ^ 1, abort_flag)) goto done;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_fin_full);
+            }
+            ++kfi;
         }
     }
 done:
     __syncwarp();
     fence_before();
     __syncthreads();
-    if (warp == 12) tmem_free(tm, 512);
+    if (warp == kMmaWarp) tmem_free(tm, 512);
     if (tid == 0 && s_abort) *A.status = 1;
 }
+__global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) { sweep_body(A); }
 
 // cross-check + count of one keyframe (whole CTA): merges the per-split column results, then
 // score[kf] = #{q : colbest[t*(q)].q == q, Ham <= tau}.  s_col: 4096 words, s_cnt: 1 int of shared memory.
