@@ -401,9 +401,9 @@ int main(int argc, char** argv) {
         int bad = 0, first = -1; long long sum = 0;
         for (int k = 0; k < nchk; ++k) { if (sc[k] != rf[k]) { if (first < 0) first = k; ++bad; } sum += rf[k]; }
         const double pairs = (double)nq * (double)n_desc;
-        printf("{\"section\": \"sweep\", \"chains\": %d, \"fused_finalize\": %d, \"status\": %d, \"nq\": %d, \"n_kf\": %d, \"n_desc\": %lld, \"checked_kf\": %d, \"fused_vs_separate_finalize_mismatches\": %d, \"score_mismatches\": %d, \"first_bad\": %d, "
+        printf("{\"section\": \"sweep\", \"fused_finalize\": %d, \"status\": %d, \"nq\": %d, \"n_kf\": %d, \"n_desc\": %lld, \"checked_kf\": %d, \"fused_vs_separate_finalize_mismatches\": %d, \"score_mismatches\": %d, \"first_bad\": %d, "
                "\"got\": %d, \"want\": %d, \"mean_score\": %.2f, \"sweep_ms\": %.4f, \"finalize_ms\": %.4f, \"gcmp_per_s\": %.1f, \"gcmp_per_s_sweep_only\": %.1f}\n",
-               PSLAM_TC_CHAINS, fused, h_status, nq, n_kf, n_desc, nchk, fused_vs_separate, bad, first, first >= 0 ? sc[first] : 0, first >= 0 ? rf[first] : 0, (double)sum / nchk,
+               fused, h_status, nq, n_kf, n_desc, nchk, fused_vs_separate, bad, first, first >= 0 ? sc[first] : 0, first >= 0 ? rf[first] : 0, (double)sum / nchk,
                ms_sweep, ms_fin, pairs / ((ms_sweep + ms_fin) * 1e-3) / 1e9, pairs / (ms_sweep * 1e-3) / 1e9);
         fflush(stdout);
     }

@@ -177,43 +177,23 @@ __device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
 }
 
 // maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address).
-// Four independent chains: a single dependent chain of 128 3-input maxima is latency-bound and makes the MMA warp wait
-// for its TMEM buffer.
-#ifndef PSLAM_TC_CHAINS
-#define PSLAM_TC_CHAINS 1
-#endif
+// (Measured: 2 or 4 independent chains instead of one, eight producer warps instead of four, and all eight epilogue warps
+// on every group with the halves merged through shared memory are each 2-6 % SLOWER: neither the epilogue nor the
+// producers are the limiter; the tensor pipe is 87 % busy.)
 __device__ __forceinline__ int row_max_256(uint32_t taddr) {
-    int m0 = -0x7fffffff, m1 = m0, m2 = m0, m3 = m0;
+    int m = -0x7fffffff;
 #pragma unroll
     for (int c = 0; c < 256; c += 64) {
         int a[32], b[32];
         tmem_ld32(taddr + (uint32_t)c, a);
         tmem_ld32(taddr + (uint32_t)(c + 32), b);
         tmem_ld_wait();
-#if PSLAM_TC_CHAINS == 1
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) m0 = max3(m0, a[j], a[j + 1]);
+        for (int j = 0; j < 32; j += 2) m = max3(m, a[j], a[j + 1]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) m0 = max3(m0, b[j], b[j + 1]);
-#elif PSLAM_TC_CHAINS == 2
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) { m0 = max3(m0, a[j], a[j + 1]); m1 = max3(m1, a[j + 2], a[j + 3]); }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) { m0 = max3(m0, b[j], b[j + 1]); m1 = max3(m1, b[j + 2], b[j + 3]); }
-#else
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            m0 = max3(m0, a[j], a[j + 1]); m1 = max3(m1, a[j + 2], a[j + 3]);
-            m2 = max3(m2, a[j + 4], a[j + 5]); m3 = max3(m3, a[j + 6], a[j + 7]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            m0 = max3(m0, b[j], b[j + 1]); m1 = max3(m1, b[j + 2], b[j + 3]);
-            m2 = max3(m2, b[j + 4], b[j + 5]); m3 = max3(m3, b[j + 6], b[j + 7]);
-        }
-#endif
+        for (int j = 0; j < 32; j += 2) m = max3(m, b[j], b[j + 1]);
     }
-    return max(max(m0, m1), max(m2, m3));
+    return m;
 }
 
 struct SweepArgs {
