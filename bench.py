@@ -282,8 +282,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gcmp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": ("s8 (256-bit descriptors expanded to +-16 bytes, int32 accumulation on the tensor cores; exact)" if used_tensor
-                      else "u8 (popcount of XOR, 256-bit descriptors)"),
+        "dtype": "u8 (popcount of XOR, 256-bit descriptors)",
         "data": "synthetic",
         "config": {"workload": f"C4 loop-closure sweep: {NQ} query descriptors vs {n_kf} keyframes x {PER_KF} ORB "
                                f"descriptors ({float(db['kf_off'][-1]) * 32 / 1e6:.0f} MB map), tau {TAU}, top-{TOPK}",

@@ -31,7 +31,8 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 def test_committed_bench_lines_carry_the_contract():
     """the bench lines committed under profiles/ (measured on B200) hold every key of the contract, with sane values"""
-    for name in ("bench_r1_final_n1.json", "bench_r1_late_n1.json", "bench_r1_final_n8.json"):
+    for name in ("bench_r1_final_n1.json", "bench_r1_late_n1.json", "bench_r1_final_n8.json", "bench_r2_n1.json", "bench_r2_n8.json",
+                 "bench_r2_tc_full_n1.json", "bench_r2_tc_n8.json"):
         p = os.path.join(ROOT, "profiles", name)
         line = json.loads(open(p).read().strip().splitlines()[-1])
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -44,7 +45,12 @@ def test_committed_bench_lines_carry_the_contract():
         assert r["bound"] in ("hbm", "tensor", "int-pipe") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-6
         assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         assert "workload" in line["config"] and "model" not in line["config"]
-        if line["n_gpus"] == 1:
+        if name.startswith("bench_r2"):      # round 2: the result of every timed configuration is checked against the oracle
+            assert line["config"]["result_ok"] is True
+        if "_tc_" in name:                   # tensor-core form: tensor roofline, int8 ops
+            assert r["bound"] == "tensor" and r["unit"] == "TOP/s" and line["value"] > 2500 * line["n_gpus"] * 0.8
+            assert line["config"]["sweep_form"].startswith("tensor") and line["config"]["tensor_wait_timeouts"] == 0
+        if line["n_gpus"] == 1 and "cpu_baseline" in line:
             assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     late = json.loads(open(os.path.join(ROOT, "profiles", "bench_r1_late_n1.json")).read().strip().splitlines()[-1])
     fe = late["frontend"]
