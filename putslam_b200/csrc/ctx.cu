@@ -2578,7 +2578,8 @@ static int lc_knn2_run(pslam_ctx* ctx, const uint8_t* query, int nq, int root, b
     if (nq <= 0 || nq > PSLAM_LC_MAX_QUERY) return fail(ctx, PSLAM_ERR_UNSUPPORTED, "query size %d outside 1..%d", nq, PSLAM_LC_MAX_QUERY);
     TRY(lc_prepare(ctx, query, nq, 1));
     const int world = sharded ? ctx->world : 1;
-    const int grid = lc_knn2_grid(ctx->db_n, ctx->sm_count);
+    const bool tensor = ctx->lc_tensor && ctx->lc_work_unit == 0 && nq <= lc_tc_max_query();
+    const int grid = tensor ? lc_knn2_tc_parts(nq, ctx->sm_count) : lc_knn2_grid(ctx->db_n, ctx->sm_count);   // partial results per query
     Arena A;
     const size_t o_part = A.take(16 * (size_t)grid * nq), o_keys = A.take(16 * (size_t)nq);
     const size_t o_gath = A.take(16 * (size_t)world * nq), o_idx = A.take(16 * (size_t)nq), o_dist = A.take(8 * (size_t)nq);
@@ -2591,8 +2592,10 @@ static int lc_knn2_run(pslam_ctx* ctx, const uint8_t* query, int nq, int root, b
         if (r != 0) return fail(ctx, PSLAM_ERR_NCCL, "ncclBroadcast failed");
     }
     if (ctx->db_n > 0) {
-        CK(launch_lc_knn2(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, grid, ctx->sm_count, ctx->stream, &l));
+        if (tensor) CK(launch_lc_knn2_tc(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, ctx->d_tc_status, ctx->sm_count, ctx->stream, &l));
+        else CK(launch_lc_knn2(ctx->d_lc_query, nq, ctx->d_db, ctx->db_n, ctx->desc_id_base, d + o_part, grid, ctx->sm_count, ctx->stream, &l));
     }
+    ctx->lc_last_tensor = tensor && ctx->db_n > 0;
     CK(launch_lc_knn2_merge(d + o_part, ctx->db_n > 0 ? grid : 0, nq, (unsigned long long*)(d + o_keys),
                             world > 1 ? nullptr : (long long*)(d + o_idx), (float*)(d + o_dist), ctx->stream, &l));
     if (world > 1) {

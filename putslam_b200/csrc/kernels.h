@@ -71,6 +71,9 @@ size_t lc_tc_rowbest_bytes(int n_kf);
 size_t lc_tc_colbest_bytes(long long n_desc, int nq);
 cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t* d_rowbest, uint32_t* d_colbest, int* d_status,
                                int sm_count, cudaStream_t st, int* launches);
+int lc_knn2_tc_parts(int nq, int sm_count);
+cudaError_t launch_lc_knn2_tc(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
+                              void* d_partial, int* d_status, int sm_count, cudaStream_t st, int* launches);
 cudaError_t launch_lc_push_query(const uint8_t* d_query, int nq, const LcExchange& x, uint32_t qepoch, cudaStream_t st, int* launches);
 // in-place re-encoding of n descriptor rows (32 B each) for the encoded Hamming compare of the sweep kernels
 cudaError_t launch_lc_encode_rows(uint8_t* d_rows, long long n, cudaStream_t st, int* launches);

@@ -437,7 +437,25 @@ __global__ void __launch_bounds__(tc::kThreads, 1) lc_tc_sweep_tail_kernel(const
     }
 }
 cudaError_t lc_sweep_tc_configure() {
-    return cudaFuncSetAttribute(lc_tc_sweep_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(lc_tc_sweep_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc::lc_tc_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+}
+// V2 on the tensor cores: number of partial results per query (= CTA groups) and the launch
+int lc_knn2_tc_parts(int nq, int sm_count) {
+    const int splits = (nq + tc::kQRows - 1) / tc::kQRows;
+    return sm_count / splits > 0 ? sm_count / splits : 1;
+}
+cudaError_t launch_lc_knn2_tc(const uint8_t* d_query, int nq, const uint8_t* d_db, long long n_desc, long long desc_id_base,
+                              void* d_partial, int* d_status, int sm_count, cudaStream_t st, int* launches) {
+    tc::Knn2Args A;
+    A.db = reinterpret_cast<const uint32_t*>(d_db); A.n_desc = n_desc; A.desc_id_base = desc_id_base; A.db_encoded = 1;
+    A.query = reinterpret_cast<const uint32_t*>(d_query); A.nq = nq;
+    A.partial = reinterpret_cast<ulonglong2*>(d_partial); A.status = d_status;
+    A.n_splits = (nq + tc::kQRows - 1) / tc::kQRows;
+    tc::lc_tc_knn2_kernel<<<A.n_splits * lc_knn2_tc_parts(nq, sm_count), tc::kThreads, tc::kSmemBytes, st>>>(A);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 int lc_tc_max_query() { return tc::kMaxQueries; }
 size_t lc_tc_rowbest_bytes(int n_kf) { return sizeof(uint32_t) * (size_t)tc::kMaxQueries * (size_t)(n_kf > 0 ? n_kf : 1); }

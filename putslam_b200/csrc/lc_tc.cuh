@@ -453,6 +453,189 @@ done:
 }
 __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) { sweep_body(A); }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// V2: the two nearest map descriptors of every query descriptor over the WHOLE map (knnMatch(query, map, 2): the ratio
+// test's input).  Same operands and pipeline as the sweep, one orientation only (rows = queries): a pair of tiles costs
+// two accumulation groups instead of four.  The epilogue keeps a running (best, second) per query row; a batch of 64
+// accumulators is reduced to its maximum (the same 3-input maxima as the sweep) and only looked at value by value when
+// that maximum beats the current SECOND best -- which, rows being visited in ascending index order and ties going to the
+// lower index, happens O(log n) times per query over the whole map (but 32 x that per warp: the second look is therefore
+// branch-free for the whole warp; the first version, a per-value scan with divergent branches, ran at a third of the speed).
+// ---------------------------------------------------------------------------------------------------------------------
+struct Knn2Args {
+    const uint32_t* db;          // n_desc x 8 words
+    long long n_desc;
+    long long desc_id_base;      // global index of row 0 (sharded maps)
+    int db_encoded;
+    const uint32_t* query;       // nq x 8 words, plain
+    int nq;
+    ulonglong2* partial;         // [groups][nq]: the two smallest keys  Ham << 40 | global index  (~0 = none)
+    int* status;
+    int n_splits;
+};
+
+__device__ __forceinline__ void top2_push(int h, int p, int t, int& h1, int& p1, int& t1, int& h2, int& p2, int& t2) {
+    if (h > h1) { h2 = h1; p2 = p1; t2 = t1; h1 = h; p1 = p; t1 = t; }
+    else if (h > h2) { h2 = h; p2 = p; t2 = t; }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sq = smem;
+    uint8_t* st = smem + 2 * kTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);   // full[2], empty[2], tfull[2], tempty[2]
+    __shared__ uint32_t s_tmem;
+    __shared__ int s_abort;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = (int)blockIdx.x % A.n_splits, group = (int)blockIdx.x / A.n_splits, n_groups = (int)gridDim.x / A.n_splits;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
+    const long long n_pairs = (A.n_desc + kPairRows - 1) / kPairRows;
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + 8 * i, kProdWarps);
+            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (tid < kQRows) {
+        const int q = split * kQRows + tid;
+        uint32_t w[8];
+        const bool valid = q < A.nq;
+        if (valid) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = 0;
+        }
+        expand_row(w, valid, sq + (tid >> 7) * kTileBytes, tid & 127, 255 - tid, true);
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = s_tmem;
+    volatile int* abort_flag = &s_abort;
+
+    if (warp < kProdWarps) {
+        uint32_t it = 0;
+        for (long long p = group; p < n_pairs; p += n_groups, ++it) {
+            const int s = it & 1;
+            constexpr int R = 256 / (kProdWarps * 32);
+            uint32_t w[R][8];
+            bool valid[R];
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const long long row = p * kPairRows + h * (kProdWarps * 32) + tid;
+                valid[h] = row < A.n_desc;
+                if (valid[h]) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8));
+                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8) + 1);
+                    w[h][0] = a.x; w[h][1] = a.y; w[h][2] = a.z; w[h][3] = a.w; w[h][4] = b.x; w[h][5] = b.y; w[h][6] = b.z; w[h][7] = b.w;
+                    if (A.db_encoded) decode_row(w[h]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[h][i] = 0;
+                }
+            }
+            if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
+#pragma unroll
+            for (int h = 0; h < R; ++h) {
+                const int rp = h * (kProdWarps * 32) + tid;
+                expand_row(w[h], valid[h], st + (2 * s + (rp >> 7)) * kTileBytes, rp & 127, 255 - rp, false);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            const uint64_t dq = make_desc(smem_u32(sq));
+            const uint32_t idesc = make_idesc(128, 256);
+            uint32_t it = 0;
+            for (long long p = group; p < n_pairs; p += n_groups, ++it) {
+                const int s = it & 1;
+                if (!mbar_wait(bar_full + 8 * s, (it >> 1) & 1, abort_flag)) goto done;
+                fence_after();
+                const uint64_t dt = make_desc(smem_u32(st + 2 * s * kTileBytes));
+#pragma unroll 1
+                for (int buf = 0; buf < 2; ++buf) {                  // rows = query block `buf` against the pair
+                    if (!mbar_wait(bar_tempty + 8 * buf, (it & 1) ^ 1, abort_flag)) goto done;
+                    fence_after();
+                    const uint64_t ad = dq + (uint64_t)((buf * kTileBytes) >> 4);
+#pragma unroll
+                    for (int k = 0; k < kRowBytes / 32; ++k)
+                        mma_i8(tm + (uint32_t)(buf * 256), ad + (uint64_t)((k * 2 * kLBO) >> 4), dt + (uint64_t)((k * 2 * kLBO) >> 4), idesc, k > 0);
+                    mma_commit(bar_tfull + 8 * buf);
+                }
+                mma_commit(bar_empty + 8 * s);
+            }
+        }
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
+        const int b = (warp - kEpiWarp0) >> 2, lq = warp & 3;
+        const uint32_t taddr = tm + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * 256);
+        const int q_local = b * kTileRows + lq * 32 + lane;
+        const int iq = 255 - q_local;
+        constexpr int kNone = -0x7fffffff;
+        int h1 = kNone, p1 = 0, t1 = 0, h2 = kNone, p2 = 0, t2 = 0;
+        if (split * kQRows + q_local >= A.nq) h1 = h2 = 0x7fffffff;    // padding query rows never ask for the slow path
+        uint32_t it = 0;
+        int pi = 0;                                               // pair counter of this CTA (global pair = group + pi * n_groups)
+        for (long long p = group; p < n_pairs; p += n_groups, ++it, ++pi) {
+            if (!mbar_wait(bar_tfull + 8 * b, it & 1, abort_flag)) goto done;
+            fence_after();
+#pragma unroll
+            for (int c = 0; c < 256; c += 64) {
+                int a[32], bb[32];
+                tmem_ld32(taddr + (uint32_t)c, a);
+                tmem_ld32(taddr + (uint32_t)(c + 32), bb);
+                tmem_ld_wait();
+                int m = kNone;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) m = max3(m, a[j], a[j + 1]);
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) m = max3(m, bb[j], bb[j + 1]);
+                // Rare per lane, not per warp (32 lanes x 64 values): when any lane needs it the whole warp takes the exact top
+                // two of the batch WITHOUT branches (the raw accumulators of a row are all distinct and ordered like
+                // (distance, index)), then the lanes that asked push them; rows come in ascending index order, so a new
+                // entry must be strictly better than what is already there.
+                if (__any_sync(0xffffffffu, (m >> kStepShift) > h2)) {
+                    int b1 = kNone, b2 = kNone;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { b2 = max(b2, min(b1, a[j])); b1 = max(b1, a[j]); }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { b2 = max(b2, min(b1, bb[j])); b1 = max(b1, bb[j]); }
+                    const int g1 = b1 >> kStepShift, g2 = b2 >> kStepShift;
+                    if (g1 > h2 && g1 >= -128) top2_push(g1, pi, 255 - ((b1 & 511) - iq), h1, p1, t1, h2, p2, t2);
+                    if (g2 > h2 && g2 >= -128) top2_push(g2, pi, 255 - ((b2 & 511) - iq), h1, p1, t1, h2, p2, t2);
+                }
+                __syncwarp();
+            }
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        const int q = split * kQRows + q_local;
+        if (q < A.nq) {
+            unsigned long long k1 = ~0ull, k2 = ~0ull;
+            if (h1 != kNone) k1 = ((unsigned long long)(128 - h1) << 40) | (unsigned long long)(A.desc_id_base + ((long long)group + (long long)p1 * n_groups) * kPairRows + t1);
+            if (h2 != kNone) k2 = ((unsigned long long)(128 - h2) << 40) | (unsigned long long)(A.desc_id_base + ((long long)group + (long long)p2 * n_groups) * kPairRows + t2);
+            A.partial[(size_t)group * A.nq + q] = make_ulonglong2(k1, k2);
+        }
+    }
+done:
+    __syncwarp();
+    fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_free(tm, 512);
+    if (tid == 0 && s_abort) *A.status = 1;
+}
+
 // cross-check + count of one keyframe (whole CTA): merges the per-split column results, then
 // score[kf] = #{q : colbest[t*(q)].q == q, Ham <= tau}.  s_col: 4096 words, s_cnt: 1 int of shared memory.
 __device__ __forceinline__ void finalize_keyframe(int kf, const long long* __restrict__ kf_off, int nq, long long n_desc,

@@ -55,9 +55,12 @@ def test_fuzz_lc_sweep(ctx, O):
             assert np.array_equal(ids, O.topk(ref, 5)[0]) and np.array_equal(sc, O.topk(ref, 5)[1])
         ctx.lc_set_work_unit(0)
         if off[-1] >= 1:
-            idx, dist = ctx.lc_knn2(q)
             oi, od = O.knn2(q, db)
-            assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32)), k
+            for unit in (3, 0):
+                ctx.lc_set_work_unit(unit)
+                idx, dist = ctx.lc_knn2(q)
+                assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32)), (k, unit)
+                assert ctx.lc_tensor_status()[1] == 0
     ctx.lc_clear()
 
 

@@ -102,9 +102,12 @@ def test_lc_knn2_whole_db_vs_oracle(ctx, O, n_desc, nq):
     ctx.lc_set_desc_base(0)
     ctx.lc_append(db, np.array([0, n_desc], np.int64) if n_desc <= 4096 else
                   np.arange(0, n_desc + 1, 1000).tolist() + ([n_desc] if n_desc % 1000 else []))
-    idx, dist = ctx.lc_knn2(q)
     oi, od = O.knn2(q, db)
-    assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32))
+    for unit in (3, 0):          # popcount kernel, tensor-core kernel
+        ctx.lc_set_work_unit(unit)
+        idx, dist = ctx.lc_knn2(q)
+        assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32)), unit
+        assert ctx.lc_tensor_status() == (unit == 0, 0), unit
     ctx.lc_set_desc_base(10 ** 10)   # global ids beyond 32 bits
     idx2, _ = ctx.lc_knn2(q)
     assert np.array_equal(idx2[oi >= 0], oi[oi >= 0].astype(np.int64) + 10 ** 10) and (idx2[oi < 0] == -1).all()
