@@ -86,7 +86,8 @@ __device__ void block_topk(const int* __restrict__ scores, int n_kf, int kf_id_b
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kTopkMaxScore + 2; i += NT) hist[i] = 0;
     if (tid < 64) sel[tid] = 0ull;
-    if (tid == 0) { s_vars[2] = 0; s_vars[3] = 0; }
+    int* s_max = warp_tot + 31;                    // highest score present (warp_tot itself uses NW <= 16 slots)
+    if (tid == 0) { s_vars[2] = 0; s_vars[3] = 0; *s_max = 0; }
     __syncthreads();
     // most keyframes score ~0: aggregate equal scores inside the warp first so the shared atomics do not serialise
     for (int base = 0; base < n_kf; base += NT) {
@@ -94,12 +95,14 @@ __device__ void block_topk(const int* __restrict__ scores, int n_kf, int kf_id_b
         const int sc = i < n_kf ? min(max(__ldcg(scores + i), 0), kTopkMaxScore + 1) : -1;
         const uint32_t peers = __match_any_sync(0xffffffffu, sc);
         if (sc >= 0 && lane == __ffs(peers) - 1) atomicAdd(hist + sc, __popc(peers));
+        const int wm = __reduce_max_sync(0xffffffffu, sc);
+        if (lane == 0 && wm > 0) atomicMax(s_max, wm);
     }
     __syncthreads();
     if (warp == 0) {  // cut = largest s with count(score >= s) >= k (or 0); above = count(score > cut)
         int acc = 0, cut = 0, above = 0;
         bool found = false;
-        for (int hi = kTopkMaxScore + 1; hi >= 0 && !found; hi -= 32) {
+        for (int hi = *s_max; hi >= 0 && !found; hi -= 32) {      // nothing scores above *s_max
             const int sidx = hi - lane;
             const int c = sidx >= 0 ? hist[sidx] : 0;
             int incl = c;

@@ -241,32 +241,38 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(&s_tmem), 512);
-    if (A.qflag) {
-        if (tid == 0) {
-            uint32_t v;
-            do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(A.qflag) : "memory"); if (v != A.qepoch) __nanosleep(32); } while (v != A.qepoch);
-        }
-        __syncthreads();
-    }
-    // the CTA's queries, expanded once
-    if (tid < kQRows) {
-        const int q = split * kQRows + tid;
-        uint32_t w[8];
-        const bool valid = q < A.nq;
-        if (valid) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8));
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8) + 1);
-            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = 0;
-        }
-        expand_row(w, valid, sq + (tid >> 7) * kTileBytes, tid & 127, 255 - tid, true);
-    }
-    fence_async_smem();
     fence_before();
-    __syncthreads();
+    __syncthreads();                                     // barriers initialised, TMEM address published
     fence_after();
+    // The producers go straight to the map (their first pair takes longer than the query takes to arrive and expand);
+    // everybody else expands the CTA's queries first and meets at a named barrier of their own.
+    if (warp >= kProdWarps) {
+        constexpr int kRest = kThreads - kProdWarps * 32;
+        const int t2 = tid - kProdWarps * 32;
+        if (A.qflag) {        // the query is pushed by the root rank over NVLink: wait until this query's copy has landed
+            if (t2 == 0) {
+                uint32_t v;
+                do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(A.qflag) : "memory"); if (v != A.qepoch) __nanosleep(32); } while (v != A.qepoch);
+            }
+            asm volatile("bar.sync 2, %0;" :: "n"(kRest) : "memory");
+        }
+        if (t2 < kQRows) {
+            const int q = split * kQRows + t2;
+            uint32_t w[8];
+            const bool valid = q < A.nq;
+            if (valid) {      // L2 loads: with a pushed query the bytes were written by a peer while this kernel was already running
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8));
+                const uint4 b = __ldcg(reinterpret_cast<const uint4*>(A.query + (size_t)q * 8) + 1);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = 0;
+            }
+            expand_row(w, valid, sq + (t2 >> 7) * kTileBytes, t2 & 127, 255 - t2, true);
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 2, %0;" :: "n"(kRest) : "memory");
+    }
     const uint32_t tm = s_tmem;
     volatile int* abort_flag = &s_abort;
 
