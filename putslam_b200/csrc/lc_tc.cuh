@@ -130,7 +130,7 @@ __device__ __forceinline__ int max3(int a, int b, int c) {
 }
 
 // 4 descriptor bits -> 4 signed bytes: bit 0 -> +kVal, bit 1 -> -kVal
-__device__ __forceinline__ uint32_t spread4(uint32_t nib) {
+__host__ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
     const uint32_t bits = (nib * 0x00204081u) & 0x01010101u;            // bit j of the nibble -> byte j
     return (0x01010101u * (uint32_t)kVal) ^ (bits * (uint32_t)((kVal ^ (256 - kVal)) & 0xff));
 }
@@ -139,14 +139,14 @@ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
 //   2,3   query index:   query rows  (idx & 1, idx >> 1)            target rows (1, 2)
 //   4-11  padding target: target rows 0 / -128 when padding         query rows +127
 //   12-19 padding query:  query rows  0 / -128 when padding         target rows +127
-__device__ __forceinline__ void extra_chunks(bool is_query, int idx, bool valid, uint4& c16, uint4& c17) {
+__host__ __device__ __forceinline__ void extra_chunks(bool is_query, int idx, bool valid, uint4& c16, uint4& c17) {
     const uint32_t own = (uint32_t)(idx & 1) | ((uint32_t)(idx >> 1) << 8), wts = 1u | (2u << 8);
     const uint32_t pad = valid ? 0u : 0x80808080u, full = 0x7f7f7f7fu;
     if (is_query) { c16 = make_uint4(wts | (own << 16), full, full, pad); c17 = make_uint4(pad, 0u, 0u, 0u); }
     else          { c16 = make_uint4(own | (wts << 16), pad, pad, full);  c17 = make_uint4(full, 0u, 0u, 0u); }
 }
 // one 32-byte descriptor row (8 words, already decoded to the plain bit order) -> the 288-byte operand row r of a tile
-__device__ __forceinline__ void expand_row(const uint32_t (&w)[8], bool valid, uint8_t* tile, int r, int idx, bool is_query) {
+__host__ __device__ __forceinline__ void expand_row(const uint32_t (&w)[8], bool valid, uint8_t* tile, int r, int idx, bool is_query) {
     uint8_t* base = tile + (r >> 3) * kSBO + (r & 7) * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -169,7 +169,7 @@ __device__ __forceinline__ void expand_row(const uint32_t (&w)[8], bool valid, u
     *reinterpret_cast<uint4*>(base + 17 * kLBO) = c17;
 }
 // rows of the map are stored re-encoded for the popcount kernel (ham256_encode, common.cuh); undo it
-__device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
+__host__ __device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
     const uint32_t e2 = w[2], e5 = w[5];
     w[2] = e2 ^ w[0] ^ w[1];
     w[5] = e5 ^ w[3] ^ w[4];
