@@ -140,3 +140,35 @@ def test_lc_wide_query_sets(ctx, O, nq):
     assert ei.value.code == api.ERR_UNSUPPORTED
     ids, sc = ctx.lc_query(db["query"][:1000], tau=64, k=8)      # still fine with <= 1024 queries
     _fresh(ctx)
+
+
+@pytest.mark.parametrize("nq", [1, 255, 256, 257, 512, 513, 768, 1023, 1024])
+def test_lc_tensor_form_boundaries(ctx, O, nq):
+    """Tensor-core form at the edges of its tiling: query counts around the 256-row quarters, keyframes of 1 / 255 / 256 / 257 /
+    511 / 512 / 513 / 4096 rows and empty ones (a pair of tiles holds 256 rows), fewer keyframes than CTA groups, duplicated
+    rows (ties), tau at both ends -- scores and 2-NN against the oracle, with the popcount form as a second opinion."""
+    rng = np.random.default_rng(1000 + nq)
+    counts = np.array([1, 255, 256, 257, 0, 511, 512, 513, 4096, 3, 0, 1000], np.int64)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    db = rng.integers(0, 256, (int(off[-1]), 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    plant = rng.choice(int(off[-1]), min(400, int(off[-1])), replace=False)
+    db[plant] = q[rng.integers(0, nq, plant.size)]                 # exact duplicates: distance 0 and many ties
+    db[off[3]:off[3] + 2] = q[0]; db[off[8] + 4095] = q[nq - 1]    # first rows of a keyframe, last row of a 4096-row keyframe
+    _fresh(ctx)
+    ctx.lc_append(db, off)
+    for tau in (0, 64, 256):
+        ref = O.lc_scores(q, db, off, tau=tau, threads=4)
+        for unit in (0, 3):
+            ctx.lc_set_work_unit(unit)
+            ids, sc, scores = ctx.lc_query(q, tau=tau, k=5, want_scores=True)
+            assert np.array_equal(scores, ref), (tau, unit)
+            assert np.array_equal(ids, O.topk(ref, 5)[0]) and np.array_equal(sc, O.topk(ref, 5)[1])
+            assert ctx.lc_tensor_status() == (unit == 0, 0)
+    oi, od = O.knn2(q, db)
+    for unit in (0, 3):
+        ctx.lc_set_work_unit(unit)
+        idx, dist = ctx.lc_knn2(q)
+        assert np.array_equal(idx, oi.astype(np.int64)) and np.array_equal(dist, od.astype(np.float32)), unit
+    ctx.lc_set_work_unit(0)
+    _fresh(ctx)
