@@ -371,6 +371,7 @@ int main(int argc, char** argv) {
         A.db = ddb; A.kf_off = doff; A.n_kf = n_kf; A.db_encoded = 0; A.query = dq; A.nq = nq; A.n_desc = n_desc;
         A.row_best = drow; A.col_best = dcol; A.status = d_status;
         A.n_splits = (nq + tc::kQRows - 1) / tc::kQRows; A.qflag = nullptr; A.qepoch = 0;
+        unsigned long long* dst; CK(cudaMalloc(&dst, 64)); CK(cudaMemset(dst, 0, 64)); A.stamps = dst;
         int* dkfd; CK(cudaMalloc(&dkfd, n_kf * 4)); CK(cudaMemset(dkfd, 0, n_kf * 4));
         const int fused = argc > 4 ? atoi(argv[4]) : 1;
         A.tau = tau; A.scores = fused ? dsc : nullptr; A.kf_done = dkfd; A.fin_mode = fused > 1 ? fused : 0;     // fused finalize (the separate kernel below then only re-derives the same scores)
@@ -389,6 +390,9 @@ int main(int argc, char** argv) {
             cudaEventElapsedTime(&ms_sweep, e0, e1); cudaEventElapsedTime(&ms_fin, e1, e2);
         }
         CK(cudaMemcpy(&h_status, d_status, 4, cudaMemcpyDeviceToHost));
+        unsigned long long stp[8]; CK(cudaMemcpy(stp, dst, 64, cudaMemcpyDeviceToHost));
+        printf("{\"section\": \"sweep_phases_cta0_us\", \"n_kf\": %d, \"prologue_producers\": %.2f, \"prologue_rest\": %.2f, \"first_group_read\": %.2f, \"last_keyframe_read\": %.2f, \"last_finalize\": %.2f, \"exit\": %.2f}\n",
+               n_kf, (stp[1] - stp[0]) * 1e-3, (stp[2] - stp[0]) * 1e-3, (stp[3] - stp[0]) * 1e-3, (stp[4] - stp[0]) * 1e-3, (stp[5] - stp[0]) * 1e-3, (stp[6] - stp[0]) * 1e-3);
         const int nchk = check_kf < n_kf ? check_kf : n_kf;
         tc::ref_scores_kernel<<<nchk, 1024>>>(ddb, doff, dq, nq, tau, dref);
         CK(cudaDeviceSynchronize());

@@ -214,8 +214,10 @@ struct SweepArgs {
     int n_splits;                // ceil(nq / kQRows): query quarters in use; the grid is n_splits x groups
     const uint32_t* qflag;       // wait until *qflag == qepoch before reading the query (pushed by a peer over NVLink); null: it is here
     uint32_t qepoch;
+    unsigned long long* stamps;  // null, or 8 x %globaltimer of CTA 0 (bench/tc_probe.cu): entry, roles start, first / last accumulator group read, exit
 };
 
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sq = smem;                                 // 2 tiles: the CTA's 256 queries
@@ -227,6 +229,8 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
     const int split = (int)blockIdx.x % A.n_splits, group = (int)blockIdx.x / A.n_splits, n_groups = (int)gridDim.x / A.n_splits;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 2), bar_tfull = smem_u32(bars + 4), bar_tempty = smem_u32(bars + 6);
     const uint32_t bar_fin_full = smem_u32(bars + 8), bar_fin_free = smem_u32(bars + 9);
+    const bool stamp = A.stamps && blockIdx.x == 0;
+    if (stamp && tid == 0) A.stamps[0] = global_ns();
 
     if (tid == 0) {
         s_abort = 0;
@@ -275,6 +279,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
     }
     const uint32_t tm = s_tmem;
     volatile int* abort_flag = &s_abort;
+    if (stamp && (tid == 0 || tid == kMmaWarp * 32)) A.stamps[tid == 0 ? 1 : 2] = global_ns();   // producers / the rest past the prologue
 
     if (warp < kProdWarps) {
         // ===== producers: two rows per thread and pair (row tid of each tile) =====
@@ -387,6 +392,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
                     cnt = __reduce_add_sync(0xffffffffu, cnt);
                     if (lane == 0) A.scores[kf] = cnt;
                 }
+                if (stamp && lane == 0) A.stamps[5] = global_ns();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_fin_free);
             }
@@ -413,6 +419,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
                 fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                if (stamp && tid == kEpiWarp0 * 32 && n == 0) A.stamps[3] = global_ns();
                 ++n;
                 const int h = m >> kStepShift;                 // 128 - Ham (the index fields sum to < 512)
                 if (h > best_h) { best_h = h; best_m = m; best_p = p; }     // later pairs hold higher t: strictly better only
@@ -442,6 +449,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
                 }
                 A.row_best[(size_t)kf * kMaxQueries + split * kQRows + q_local] = rb;
             }
+            if (stamp && tid == kEpiWarp0 * 32) A.stamps[4] = global_ns();      // overwritten per keyframe: the last one stays
             if (A.scores) {      // hand the keyframe to the finalize warp (which must be done with the previous one)
                 if (!mbar_wait(bar_fin_free, (kfi & 1) ^ 1, abort_flag)) goto done;
                 __syncwarp();
@@ -456,6 +464,7 @@ done:
     __syncthreads();
     if (warp == kMmaWarp) tmem_free(tm, 512);
     if (tid == 0 && s_abort) *A.status = 1;
+    if (stamp && tid == 0) A.stamps[6] = global_ns();
 }
 __global__ void __launch_bounds__(kThreads, 1) lc_tc_sweep_kernel(const SweepArgs A) { sweep_body(A); }
 
