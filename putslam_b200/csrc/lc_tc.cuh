@@ -129,10 +129,11 @@ __device__ __forceinline__ int max3(int a, int b, int c) {
     return r;
 }
 
-// 4 descriptor bits -> 4 signed bytes: bit 0 -> +kVal, bit 1 -> -kVal
+// 4 descriptor bits -> 4 signed bytes: bit 0 -> +kVal, bit 1 -> -kVal.  Two multiply-adds and one AND: the second one adds
+// 0x10 + bit * 0xE0 per byte (0x10 or 0xF0, no carry between bytes), which an XOR could not fold into the multiply.
 __host__ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
     const uint32_t bits = (nib * 0x00204081u) & 0x01010101u;            // bit j of the nibble -> byte j
-    return (0x01010101u * (uint32_t)kVal) ^ (bits * (uint32_t)((kVal ^ (256 - kVal)) & 0xff));
+    return bits * (uint32_t)(256 - 2 * kVal) + 0x01010101u * (uint32_t)kVal;
 }
 // the two extra chunks of a row.  Slots (bytes of chunk 16, then chunk 17):
 //   0,1   target index:  target rows (idx & 1, idx >> 1)            query rows (1, 2)
