@@ -5,7 +5,7 @@
 // ties) at a distance <= tau -- cv::BFMatcher(NORM_HAMMING, crossCheck = true).match per keyframe
 // (reference: src/Matcher/matcherOpenCV.cpp:198-206 called from src/Matcher/matcher.cpp:835).
 //
-// Arithmetic.  Descriptor rows are expanded to signed bytes, bit 0 -> +16, bit 1 -> -16.  Then
+// Arithmetic.  Descriptor rows are expanded to signed bytes: query rows bit 0 -> +4, bit 1 -> -4, map rows +-64.  Then
 //     sum_k q_k t_k = 256 (256 - 2 Ham) = 512 (128 - Ham)                       (int32 accumulation, exact)
 // and 20 of the 32 slots that pad K from 256 to 288 (kind::i8 takes K in steps of 32) carry
 //     + (255 - t_local) + (255 - q_local)          the index fields: the raw accumulator IS the comparison key
@@ -41,7 +41,7 @@ constexpr int kPairRows = 256;
 constexpr int kQRows = 256;                       // resident queries per CTA
 constexpr int kSplits = 4;                        // query quarters: up to 1024 queries
 constexpr int kMaxQueries = kQRows * kSplits;
-constexpr int kVal = 16;                          // |q_k| = |t_k|
+constexpr int kQVal = 4, kTVal = 64;               // |q_k|, |t_k|: product 256 per agreeing slot, -256 per differing one
 constexpr int kStepShift = 9;                     // accumulator = (128 - Ham) << 9 | index fields (< 512)
 #ifndef PSLAM_TC_PROD_WARPS
 #define PSLAM_TC_PROD_WARPS 4
@@ -129,11 +129,28 @@ __device__ __forceinline__ int max3(int a, int b, int c) {
     return r;
 }
 
-// 4 descriptor bits -> 4 signed bytes: bit 0 -> +kVal, bit 1 -> -kVal.  Two multiply-adds and one AND: the second one adds
-// 0x10 + bit * 0xE0 per byte (0x10 or 0xF0, no carry between bytes), which an XOR could not fold into the multiply.
-__host__ __device__ __forceinline__ uint32_t spread4(uint32_t nib) {
+// 4 descriptor bits -> 4 signed bytes.  Query rows (expanded once per CTA): bit 0 -> +4, bit 1 -> -4, two multiply-adds
+// and an AND (the second adds 0x04 + bit * 0xF8 per byte: 0x04 or 0xFC, no carry between bytes).
+__host__ __device__ __forceinline__ uint32_t spread4_query(uint32_t nib) {
     const uint32_t bits = (nib * 0x00204081u) & 0x01010101u;            // bit j of the nibble -> byte j
-    return bits * (uint32_t)(256 - 2 * kVal) + 0x01010101u * (uint32_t)kVal;
+    return bits * (uint32_t)(256 - 2 * kQVal) + 0x01010101u * (uint32_t)kQVal;
+}
+// Map rows (expanded for every sweep -- the producers' inner loop): bit 0 -> +64 = 0x40, bit 1 -> -64 = 0xC0, which differ
+// in the sign bit only: one multiply puts bit j of the field at position 8 j + 7, one LOP3 masks and ORs 0x40 in.  `field`
+// may carry up to three bits of garbage above the nibble (7 bits in all land on distinct positions, none of them a sign
+// position, so nothing carries); the same holds for bits 4-10 with the multiplier that takes bit 4 + j to 8 j + 7, so one
+// shifted word serves both nibbles of a byte.
+template <uint32_t kMul = 0x10204080u>
+__host__ __device__ __forceinline__ uint32_t spread4_map(uint32_t field7) {
+#ifdef __CUDA_ARCH__
+    // one LOP3 ((y & m) | c, LUT 0xEA) with both constants in registers: with two immediates the compiler emits two
+    uint32_t r;
+    const uint32_t m = 0x80808080u, c = 0x40404040u;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(field7 * kMul), "r"(m), "r"(c));
+    return r;
+#else
+    return ((field7 * kMul) & 0x80808080u) | 0x40404040u;
+#endif
 }
 // the two extra chunks of a row.  Slots (bytes of chunk 16, then chunk 17):
 //   0,1   target index:  target rows (idx & 1, idx >> 1)            query rows (1, 2)
@@ -154,10 +171,21 @@ __host__ __device__ __forceinline__ void expand_row(const uint32_t (&w)[8], bool
         const uint32_t x = w[i];
         uint4 lo, hi;
         if (valid) {
-            lo.x = spread4(x & 15u);         lo.y = spread4((x >> 4) & 15u);
-            lo.z = spread4((x >> 8) & 15u);  lo.w = spread4((x >> 12) & 15u);
-            hi.x = spread4((x >> 16) & 15u); hi.y = spread4((x >> 20) & 15u);
-            hi.z = spread4((x >> 24) & 15u); hi.w = spread4(x >> 28);
+            if (is_query) {
+                lo.x = spread4_query(x & 15u);         lo.y = spread4_query((x >> 4) & 15u);
+                lo.z = spread4_query((x >> 8) & 15u);  lo.w = spread4_query((x >> 12) & 15u);
+                hi.x = spread4_query((x >> 16) & 15u); hi.y = spread4_query((x >> 20) & 15u);
+                hi.z = spread4_query((x >> 24) & 15u); hi.w = spread4_query(x >> 28);
+            } else {
+                // per byte: one shift, two masks (bits 0-6 and 4-10 of the shifted word: seven consecutive bits each), and
+                // for the high nibble a multiplier that takes bit 4 + j to position 8 j + 7
+                constexpr uint32_t kHi = 0x01020408u;      // 2^3 + 2^10 + 2^17 + 2^24
+                const uint32_t x1 = x >> 8, x2 = x >> 16, x3 = x >> 24;
+                lo.x = spread4_map(x & 0x7fu);   lo.y = spread4_map<kHi>(x & 0x7f0u);
+                lo.z = spread4_map(x1 & 0x7fu);  lo.w = spread4_map<kHi>(x1 & 0x7f0u);
+                hi.x = spread4_map(x2 & 0x7fu);  hi.y = spread4_map<kHi>(x2 & 0x7f0u);
+                hi.z = spread4_map(x3 & 0x7fu);  hi.w = spread4_map<kHi>(x3 & 0xf0u);
+            }
         } else {
             lo = make_uint4(0, 0, 0, 0); hi = lo;
         }
