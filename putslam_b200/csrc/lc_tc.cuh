@@ -205,6 +205,36 @@ __host__ __device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
     w[6] = w[6] ^ e2 ^ e5;
 }
 
+// producer helper: this thread's rows of the pair that starts at `row0` (rows beyond `row_end` are padding)
+constexpr int kRowsPerProducer = 256 / (kProdWarps * 32);
+struct PairRows {
+    uint32_t w[kRowsPerProducer][8];
+    bool valid[kRowsPerProducer];
+};
+__device__ __forceinline__ void load_pair_rows(const uint32_t* __restrict__ db, long long row0, long long row_end, int tid, PairRows& r) {
+#pragma unroll
+    for (int h = 0; h < kRowsPerProducer; ++h) {
+        const long long row = row0 + h * (kProdWarps * 32) + tid;
+        r.valid[h] = row < row_end;
+        if (r.valid[h]) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(db + (size_t)row * 8));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(db + (size_t)row * 8) + 1);
+            r.w[h][0] = a.x; r.w[h][1] = a.y; r.w[h][2] = a.z; r.w[h][3] = a.w; r.w[h][4] = b.x; r.w[h][5] = b.y; r.w[h][6] = b.z; r.w[h][7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r.w[h][i] = 0;
+        }
+    }
+}
+__device__ __forceinline__ void expand_pair_rows(PairRows& r, bool db_encoded, uint8_t* pair_tiles, int tid) {
+#pragma unroll
+    for (int h = 0; h < kRowsPerProducer; ++h) {
+        const int rp = h * (kProdWarps * 32) + tid;       // row inside the pair
+        if (db_encoded && r.valid[h]) decode_row(r.w[h]);
+        expand_row(r.w[h], r.valid[h], pair_tiles + (rp >> 7) * kTileBytes, rp & 127, 255 - rp, false);
+    }
+}
+
 // maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address).
 // (Measured: 2 or 4 independent chains instead of one, eight producer warps instead of four, and all eight epilogue warps
 // on every group with the halves merged through shared memory are each 2-6 % SLOWER: neither the epilogue nor the
@@ -311,41 +341,33 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
     if (stamp && (tid == 0 || tid == kMmaWarp * 32)) A.stamps[tid == 0 ? 1 : 2] = global_ns();   // producers / the rest past the prologue
 
     if (warp < kProdWarps) {
-        // ===== producers: two rows per thread and pair (row tid of each tile) =====
+        // ===== producers: two rows per thread and pair.  The loads of the NEXT pair are issued before this pair is
+        //       expanded, so their latency (an L2 miss is ~2000 clk, as long as a pair's MMAs) never sits between two pairs. =====
         uint32_t it = 0;
-        for (int kf = group; kf < A.n_kf; kf += n_groups) {
-            const long long r0 = A.kf_off[kf], r1 = A.kf_off[kf + 1];
-            const int pairs = (int)((r1 - r0 + kPairRows - 1) / kPairRows);
-            for (int p = 0; p < pairs; ++p, ++it) {
-                const int s = it & 1;
-                constexpr int R = 256 / (kProdWarps * 32);          // rows of the pair per thread
-                uint32_t w[R][8];
-                bool valid[R];
-#pragma unroll
-                for (int h = 0; h < R; ++h) {
-                    const int rp = h * (kProdWarps * 32) + tid;       // row inside the pair
-                    const long long row = r0 + (long long)p * kPairRows + rp;
-                    valid[h] = row < r1;
-                    if (valid[h]) {
-                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8));
-                        const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8) + 1);
-                        w[h][0] = a.x; w[h][1] = a.y; w[h][2] = a.z; w[h][3] = a.w; w[h][4] = b.x; w[h][5] = b.y; w[h][6] = b.z; w[h][7] = b.w;
-                        if (A.db_encoded) decode_row(w[h]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) w[h][i] = 0;
-                    }
-                }
-                if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
-#pragma unroll
-                for (int h = 0; h < R; ++h) {
-                    const int rp = h * (kProdWarps * 32) + tid;
-                    expand_row(w[h], valid[h], st + (2 * s + (rp >> 7)) * kTileBytes, rp & 127, 255 - rp, false);
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        int kf = group, p = 0, pairs = 0;
+        long long r0 = 0, r1 = 0;
+        auto seek = [&]() {          // (kf, p) -> the next pair that exists; kf >= n_kf when there is none
+            while (kf < A.n_kf) {
+                r0 = A.kf_off[kf]; r1 = A.kf_off[kf + 1];
+                pairs = (int)((r1 - r0 + kPairRows - 1) / kPairRows);
+                if (p < pairs) return;
+                kf += n_groups; p = 0;
             }
+        };
+        PairRows cur, nxt;
+        seek();
+        if (kf < A.n_kf) load_pair_rows(A.db, r0 + (long long)p * kPairRows, r1, tid, nxt);
+        while (kf < A.n_kf) {
+            cur = nxt;
+            ++p; seek();
+            if (kf < A.n_kf) load_pair_rows(A.db, r0 + (long long)p * kPairRows, r1, tid, nxt);
+            const int s = it & 1;
+            if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
+            expand_pair_rows(cur, A.db_encoded != 0, st + 2 * s * kTileBytes, tid);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+            ++it;
         }
     } else if (warp == kMmaWarp) {
         // ===== MMA issuer =====
@@ -568,31 +590,14 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args 
 
     if (warp < kProdWarps) {
         uint32_t it = 0;
+        PairRows cur, nxt;
+        if (group < n_pairs) load_pair_rows(A.db, (long long)group * kPairRows, A.n_desc, tid, nxt);
         for (long long p = group; p < n_pairs; p += n_groups, ++it) {
             const int s = it & 1;
-            constexpr int R = 256 / (kProdWarps * 32);
-            uint32_t w[R][8];
-            bool valid[R];
-#pragma unroll
-            for (int h = 0; h < R; ++h) {
-                const long long row = p * kPairRows + h * (kProdWarps * 32) + tid;
-                valid[h] = row < A.n_desc;
-                if (valid[h]) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8));
-                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(A.db + (size_t)row * 8) + 1);
-                    w[h][0] = a.x; w[h][1] = a.y; w[h][2] = a.z; w[h][3] = a.w; w[h][4] = b.x; w[h][5] = b.y; w[h][6] = b.z; w[h][7] = b.w;
-                    if (A.db_encoded) decode_row(w[h]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) w[h][i] = 0;
-                }
-            }
+            cur = nxt;
+            if (p + n_groups < n_pairs) load_pair_rows(A.db, (p + n_groups) * kPairRows, A.n_desc, tid, nxt);   // next pair's loads in flight
             if (!mbar_wait(bar_empty + 8 * s, ((it >> 1) & 1) ^ 1, abort_flag)) goto done;
-#pragma unroll
-            for (int h = 0; h < R; ++h) {
-                const int rp = h * (kProdWarps * 32) + tid;
-                expand_row(w[h], valid[h], st + (2 * s + (rp >> 7)) * kTileBytes, rp & 127, 255 - rp, false);
-            }
+            expand_pair_rows(cur, A.db_encoded != 0, st + 2 * s * kTileBytes, tid);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
