@@ -439,10 +439,11 @@ __global__ void __launch_bounds__(tc::kThreads, 1) lc_tc_sweep_tail_kernel(const
         exchange_and_merge<tc::kThreads>(a.x, a.out_pairs, a.k, smem, a.out_merged);
     }
 }
+constexpr int kKnn2ProdWarps = 4;     // eight (one row per thread) measured 3 % slower
 cudaError_t lc_sweep_tc_configure() {
     cudaError_t e = cudaFuncSetAttribute(lc_tc_sweep_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc::lc_tc_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    return cudaFuncSetAttribute(tc::lc_tc_knn2_kernel<kKnn2ProdWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
 }
 // V2 on the tensor cores: number of partial results per query (= CTA groups) and the launch
 int lc_knn2_tc_parts(int nq, int sm_count) {
@@ -456,7 +457,7 @@ cudaError_t launch_lc_knn2_tc(const uint8_t* d_query, int nq, const uint8_t* d_d
     A.query = reinterpret_cast<const uint32_t*>(d_query); A.nq = nq;
     A.partial = reinterpret_cast<ulonglong2*>(d_partial); A.status = d_status;
     A.n_splits = (nq + tc::kQRows - 1) / tc::kQRows;
-    tc::lc_tc_knn2_kernel<<<A.n_splits * lc_knn2_tc_parts(nq, sm_count), tc::kThreads, tc::kSmemBytes, st>>>(A);
+    tc::lc_tc_knn2_kernel<kKnn2ProdWarps><<<A.n_splits * lc_knn2_tc_parts(nq, sm_count), (kKnn2ProdWarps + 9) * 32, tc::kSmemBytes, st>>>(A);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -206,15 +206,17 @@ __host__ __device__ __forceinline__ void decode_row(uint32_t (&w)[8]) {
 }
 
 // producer helper: this thread's rows of the pair that starts at `row0` (rows beyond `row_end` are padding)
-constexpr int kRowsPerProducer = 256 / (kProdWarps * 32);
+template <int PW = kProdWarps>
 struct PairRows {
-    uint32_t w[kRowsPerProducer][8];
-    bool valid[kRowsPerProducer];
+    static constexpr int R = 256 / (PW * 32);
+    uint32_t w[R][8];
+    bool valid[R];
 };
-__device__ __forceinline__ void load_pair_rows(const uint32_t* __restrict__ db, long long row0, long long row_end, int tid, PairRows& r) {
+template <int PW>
+__device__ __forceinline__ void load_pair_rows(const uint32_t* __restrict__ db, long long row0, long long row_end, int tid, PairRows<PW>& r) {
 #pragma unroll
-    for (int h = 0; h < kRowsPerProducer; ++h) {
-        const long long row = row0 + h * (kProdWarps * 32) + tid;
+    for (int h = 0; h < PairRows<PW>::R; ++h) {
+        const long long row = row0 + h * (PW * 32) + tid;
         r.valid[h] = row < row_end;
         if (r.valid[h]) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(db + (size_t)row * 8));
@@ -226,10 +228,11 @@ __device__ __forceinline__ void load_pair_rows(const uint32_t* __restrict__ db, 
         }
     }
 }
-__device__ __forceinline__ void expand_pair_rows(PairRows& r, bool db_encoded, uint8_t* pair_tiles, int tid) {
+template <int PW>
+__device__ __forceinline__ void expand_pair_rows(PairRows<PW>& r, bool db_encoded, uint8_t* pair_tiles, int tid) {
 #pragma unroll
-    for (int h = 0; h < kRowsPerProducer; ++h) {
-        const int rp = h * (kProdWarps * 32) + tid;       // row inside the pair
+    for (int h = 0; h < PairRows<PW>::R; ++h) {
+        const int rp = h * (PW * 32) + tid;               // row inside the pair
         if (db_encoded && r.valid[h]) decode_row(r.w[h]);
         expand_row(r.w[h], r.valid[h], pair_tiles + (rp >> 7) * kTileBytes, rp & 127, 255 - rp, false);
     }
@@ -354,7 +357,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
                 kf += n_groups; p = 0;
             }
         };
-        PairRows cur, nxt;
+        PairRows<kProdWarps> cur, nxt;
         seek();
         if (kf < A.n_kf) load_pair_rows(A.db, r0 + (long long)p * kPairRows, r1, tid, nxt);
         while (kf < A.n_kf) {
@@ -545,7 +548,11 @@ __device__ __forceinline__ void top2_push(int h, int p, int t, int& h1, int& p1,
     else if (h > h2) { h2 = h; p2 = p; t2 = t; }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args A) {
+// PW producer warps (4: two rows of a pair per thread; 8 was tried -- V2 issues half the MMAs per pair -- and is slower),
+// then 8 epilogue warps and the MMA warp
+template <int PW>
+__global__ void __launch_bounds__((PW + 9) * 32, 1) lc_tc_knn2_kernel(const Knn2Args A) {
+    constexpr int kEpi0 = PW, kMma = PW + 8;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sq = smem;
     uint8_t* st = smem + 2 * kTileBytes;
@@ -559,14 +566,14 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args 
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_full + 8 * i, kProdWarps);
+            mbar_init(bar_full + 8 * i, PW);
             mbar_init(bar_empty + 8 * i, 1);
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaWarp) tmem_alloc(smem_u32(&s_tmem), 512);
+    if (warp == kMma) tmem_alloc(smem_u32(&s_tmem), 512);
     if (tid < kQRows) {
         const int q = split * kQRows + tid;
         uint32_t w[8];
@@ -588,9 +595,9 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args 
     const uint32_t tm = s_tmem;
     volatile int* abort_flag = &s_abort;
 
-    if (warp < kProdWarps) {
+    if (warp < PW) {
         uint32_t it = 0;
-        PairRows cur, nxt;
+        PairRows<PW> cur, nxt;
         if (group < n_pairs) load_pair_rows(A.db, (long long)group * kPairRows, A.n_desc, tid, nxt);
         for (long long p = group; p < n_pairs; p += n_groups, ++it) {
             const int s = it & 1;
@@ -602,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args 
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * s);
         }
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kMma) {
         if (lane == 0) {
             const uint64_t dq = make_desc(smem_u32(sq));
             const uint32_t idesc = make_idesc(128, 256);
@@ -625,8 +632,8 @@ __global__ void __launch_bounds__(kThreads, 1) lc_tc_knn2_kernel(const Knn2Args 
                 mma_commit(bar_empty + 8 * s);
             }
         }
-    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
-        const int b = (warp - kEpiWarp0) >> 2, lq = warp & 3;
+    } else {
+        const int b = (warp - kEpi0) >> 2, lq = warp & 3;
         const uint32_t taddr = tm + ((uint32_t)(lq * 32) << 16) + (uint32_t)(b * 256);
         const int q_local = b * kTileRows + lq * 32 + lane;
         const int iq = 255 - q_local;
@@ -681,7 +688,7 @@ done:
     __syncwarp();
     fence_before();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_free(tm, 512);
+    if (warp == kMma) tmem_free(tm, 512);
     if (tid == 0 && s_abort) *A.status = 1;
 }
 
