@@ -374,7 +374,7 @@ int main(int argc, char** argv) {
         unsigned long long* dst; CK(cudaMalloc(&dst, 64)); CK(cudaMemset(dst, 0, 64)); A.stamps = dst;
         int* dkfd; CK(cudaMalloc(&dkfd, n_kf * 4)); CK(cudaMemset(dkfd, 0, n_kf * 4));
         const int fused = argc > 4 ? atoi(argv[4]) : 1;
-        A.tau = tau; A.scores = fused ? dsc : nullptr; A.kf_done = dkfd; A.fin_mode = fused > 1 ? fused : 0;     // fused finalize (the separate kernel below then only re-derives the same scores)
+        A.tau = tau; A.scores = fused ? dsc : nullptr; A.kf_done = dkfd;     // fused finalize (the separate kernel below then only re-derives the same scores)
         CK(cudaFuncSetAttribute(tc::lc_tc_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
         const int grid = (sms / A.n_splits) * A.n_splits;
         cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);

@@ -479,7 +479,7 @@ cudaError_t launch_lc_sweep_tc(const LcSweepArgs& a, long long n_desc, uint32_t*
     A.nq = a.nq;
     A.n_desc = n_desc;
     A.row_best = d_rowbest; A.col_best = d_colbest; A.status = d_status;
-    A.tau = a.tau; A.scores = a.scores; A.kf_done = a.kf_done; A.fin_mode = 0;
+    A.tau = a.tau; A.scores = a.scores; A.kf_done = a.kf_done;
     A.n_splits = (a.nq + tc::kQRows - 1) / tc::kQRows;
     A.qflag = a.qflag; A.qepoch = a.qepoch; A.stamps = nullptr;
     const int groups = sm_count / A.n_splits > 0 ? sm_count / A.n_splits : 1;

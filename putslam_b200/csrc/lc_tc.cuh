@@ -23,7 +23,9 @@
 // issues four accumulation groups of 9 MMAs (M = 128, N = 256, K = 32): rows = query block 0 / 1 against the pair, and
 // rows = tile 0 / 1 of the pair against the 256 queries; two 256-column TMEM buffers alternate between the MMA warp and
 // two sets of four epilogue warps.  Per-query results are complete inside a CTA; per-target results are partial (one per
-// split) and merged by lc_tc_finalize_kernel, which also does the cross-check and the count.
+// split): the finalize warp of the split that finishes a keyframe last merges them, cross-checks and counts.  The kernel
+// around sweep_body (lc_sweep.cu: lc_tc_sweep_tail_kernel) then turns the scores into the top-k in its last CTA.
+// lc_tc_knn2_kernel below is the V2 sweep (two nearest map descriptors per query) on the same pipeline.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,10 +45,7 @@ constexpr int kSplits = 4;                        // query quarters: up to 1024 
 constexpr int kMaxQueries = kQRows * kSplits;
 constexpr int kQVal = 4, kTVal = 64;               // |q_k|, |t_k|: product 256 per agreeing slot, -256 per differing one
 constexpr int kStepShift = 9;                     // accumulator = (128 - Ham) << 9 | index fields (< 512)
-#ifndef PSLAM_TC_PROD_WARPS
-#define PSLAM_TC_PROD_WARPS 4
-#endif
-constexpr int kProdWarps = PSLAM_TC_PROD_WARPS;   // 4: two rows per thread and pair; 8: one
+constexpr int kProdWarps = 4;                     // two rows of a pair per thread (8 warps, one row each, measured slower)
 constexpr int kEpiWarp0 = kProdWarps;             // epilogue sets: warps kEpiWarp0 .. +3 and +4 .. +7 (lane quarter = warp & 3)
 constexpr int kMmaWarp = kProdWarps + 8, kFinWarp = kProdWarps + 9;
 constexpr int kThreads = (kProdWarps + 10) * 32;  // producers | 8 epilogue | MMA issuer | per-keyframe finalize
@@ -123,11 +122,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ int max3(int a, int b, int c) {
-    int r;
-    asm("max.s32 %0, %1, %2;\n\tmax.s32 %0, %0, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));   // ptxas fuses to VIMNMX3
-    return r;
-}
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }   // ptxas fuses the pair into VIMNMX3
 
 // 4 descriptor bits -> 4 signed bytes.  Query rows (expanded once per CTA): bit 0 -> +4, bit 1 -> -4, two multiply-adds
 // and an AND (the second adds 0x04 + bit * 0xF8 per byte: 0x04 or 0xFC, no carry between bytes).
@@ -241,7 +236,8 @@ __device__ __forceinline__ void expand_pair_rows(PairRows<PW>& r, bool db_encode
 // maximum of the 256 accumulators of this thread's TMEM lane in buffer `taddr` (lane already folded into the address).
 // (Measured: 2 or 4 independent chains instead of one, eight producer warps instead of four, and all eight epilogue warps
 // on every group with the halves merged through shared memory are each 2-6 % SLOWER: neither the epilogue nor the
-// producers are the limiter; the tensor pipe is 87 % busy.)
+// producers' instruction count is the limiter; what did help was hiding the producers' load latency and making the
+// expansion cheaper.  The tensor pipe is 92 % busy.)
 __device__ __forceinline__ int row_max_256(uint32_t taddr) {
     int m = -0x7fffffff;
 #pragma unroll
@@ -272,7 +268,6 @@ struct SweepArgs {
     int tau;                     // fused finalize: score[kf] = #{cross-check matches with Ham <= tau}
     int* scores;                 // [n_kf]; written by the CTA that finishes a keyframe last (null: no fused finalize, see finalize_keyframe)
     int* kf_done;                // [n_kf] arrival counters of the splits, zero between launches
-    int fin_mode;                // debug: 0 normal, 2 handshake only, 3 handshake + fence + counter
     int n_splits;                // ceil(nq / kQRows): query quarters in use; the grid is n_splits x groups
     const uint32_t* qflag;       // wait until *qflag == qepoch before reading the query (pushed by a peer over NVLink); null: it is here
     uint32_t qepoch;
@@ -413,13 +408,13 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& A) {
                 const int n_t = (int)(A.kf_off[kf + 1] - r0);
                 if (!mbar_wait(bar_fin_full, kfi & 1, abort_flag)) goto done;
                 int last = 0;
-                if (lane == 0 && A.fin_mode != 2) {
+                if (lane == 0) {
                     __threadfence();                                      // the epilogue warps' results, observed through the barrier
                     last = atomicAdd(A.kf_done + kf, 1) == A.n_splits - 1;
                     if (last) A.kf_done[kf] = 0;
                 }
                 last = __shfl_sync(0xffffffffu, last, 0);
-                if (last && A.fin_mode == 0) {
+                if (last) {
                     __threadfence();
                     int cnt = 0;
                     if (n_t > 0)
