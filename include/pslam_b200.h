@@ -492,7 +492,9 @@ PSLAM_API int pslam_lc_query_sharded_resident_bcast(pslam_ctx* ctx, int root, in
 /* Per-query-descriptor 2-NN against the whole resident database (SURVEY 8e variant V2; the oracle is
  * cv::BFMatcher::knnMatch(query, whole_db, 2)): out_idx nq x 2 GLOBAL descriptor indices (int64, -1 = none;
  * global = desc_id_base + position in this ctx's database), out_dist nq x 2 float, ascending distance, lowest
- * index first on ties.  _sharded: ncclBroadcast(query) / local sweep / ncclAllGather of nq x 2 keys / merge. */
+ * index first on ties.  _sharded: ncclBroadcast(query) / local sweep / ncclAllGather of nq x 2 keys / merge.
+ * Like the V1 sweep it runs on the tensor cores (tcgen05 kind::i8, exact) for up to 1024 query descriptors and on the
+ * integer pipes beyond or when pslam_lc_set_work_unit / PSLAM_LC_TENSOR say so; pslam_lc_tensor_status reports which. */
 PSLAM_API int pslam_lc_set_desc_base(pslam_ctx* ctx, int64_t desc_id_base);
 PSLAM_API int pslam_lc_knn2(pslam_ctx* ctx, const uint8_t* query, int nq, int64_t* out_idx, float* out_dist);
 PSLAM_API int pslam_lc_knn2_sharded(pslam_ctx* ctx, const uint8_t* query, int nq, int root, int64_t* out_idx,
